@@ -1,0 +1,217 @@
+"""Generate golden vectors FROM THE REAL REFERENCE (run in the build container only; /root/reference is not on the
+GPU box).  TEST INFRASTRUCTURE.
+
+    PYTHONPATH=oracle/shim:/root/reference python oracle/gen_golden.py
+
+Writes tests/golden/*.npz: seeded inputs, the reference modules' weights (state_dict) and the reference's outputs
+(hidden states, train loss, gradients, eval logits, SeenItemsFilter + torch.topk result, one Adam step).
+tests/test_oracle_golden.py checks oracle/ against these; tests/test_parity_gpu.py checks the CUDA path against them.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "shim"))
+sys.path.insert(1, "/root/reference")
+warnings.filterwarnings("ignore")
+
+from replay.data import FeatureHint, FeatureSource, FeatureType  # noqa: E402
+from replay.data.nn import TensorFeatureInfo, TensorFeatureSource, TensorSchema  # noqa: E402
+from replay.models.nn.sequential.bert4rec.model import Bert4RecModel  # noqa: E402
+from replay.models.nn.sequential.sasrec.model import SasRecModel  # noqa: E402
+from replay.nn.lightning.postprocessor import SeenItemsFilter  # noqa: E402
+from replay.nn.sequential import SasRec  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def schema(n_items, d, pad):
+    return TensorSchema(
+        [
+            TensorFeatureInfo(
+                name="item_id",
+                is_seq=True,
+                cardinality=n_items,
+                padding_value=pad,
+                embedding_dim=d,
+                feature_type=FeatureType.CATEGORICAL,
+                feature_sources=[TensorFeatureSource(FeatureSource.INTERACTIONS, "item_id")],
+                feature_hint=FeatureHint.ITEM_ID,
+            )
+        ]
+    )
+
+
+def make_batch(g, B, L, n_items, pad, min_len=1):
+    """Left-padded windows of L+1 ids -> inputs/labels shifted by one (sasrec/dataset.py:104-126)."""
+    lens = torch.randint(min_len, L + 2, (B,), generator=g)
+    lens[0] = L + 1  # one full row
+    lens[1] = 2  # one nearly empty row
+    full = torch.full((B, L + 1), pad, dtype=torch.int64)
+    msk = torch.zeros(B, L + 1, dtype=torch.bool)
+    for b in range(B):
+        n = int(lens[b])
+        full[b, L + 1 - n :] = torch.randint(0, n_items, (n,), generator=g)
+        msk[b, L + 1 - n :] = True
+    return full[:, :-1].contiguous(), msk[:, :-1].contiguous(), full[:, 1:].contiguous(), msk[:, 1:].contiguous()
+
+
+def randomise_small_params(module, g):
+    """xavier leaves biases 0 and LN at (1,0); perturb so the golden vectors exercise them."""
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+
+
+def sd_np(module):
+    return {"sd::" + k: v.detach().cpu().numpy().copy() for k, v in module.state_dict().items()}
+
+
+def gen_new_sasrec(tag, B, L, d, H, n_items, n_blocks, seed):
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    pad = n_items
+    model = SasRec.from_params(schema(n_items, d, pad), embedding_dim=d, num_heads=H, num_blocks=n_blocks,
+                               max_sequence_length=L, dropout=0.0)
+    randomise_small_params(model, g)
+    ids, pmask, labels, tmask = make_batch(g, B, L, n_items, pad)
+    out = dict(sd_np(model))
+    out.update(ids=ids.numpy(), pad_mask=pmask.numpy(), labels=labels.numpy(), target_mask=tmask.numpy(),
+               n_items=n_items, d=d, H=H, L=L, n_blocks=n_blocks)
+    # --- train mode: loss + grads (dropout 0)
+    model.train()
+    res = model(feature_tensors={"item_id": ids}, padding_mask=pmask, positive_labels=labels.unsqueeze(-1),
+                negative_labels=None, target_padding_mask=tmask.unsqueeze(-1))
+    loss = res["loss"]
+    loss.backward()
+    out["train_hidden"] = res["hidden_states"][0].detach().numpy()
+    out["train_loss"] = loss.detach().numpy()
+    for k, p in model.named_parameters():
+        out["grad::" + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy().copy()
+    # --- one Adam step with the reference's optimizer settings (optimizer_factory.py:56-63)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.98))
+    opt.step()
+    for k, p in model.named_parameters():
+        out["adam1::" + k] = p.detach().numpy().copy()
+    # restore weights for the eval leg
+    model.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in out.items() if k.startswith("sd::")})
+    model.eval()
+    with torch.no_grad():
+        inf = model(feature_tensors={"item_id": ids}, padding_mask=pmask)
+        logits = inf["logits"]
+        out["eval_logits"] = logits.numpy()
+        out["eval_hidden_last"] = inf["hidden_states"][0][:, -1].numpy()
+        # SeenItemsFilter + topk (seen = the window ids, padding = n_items which the filter ignores)
+        seen = ids.clone()
+        filt = SeenItemsFilter(item_count=n_items, seen_items_column="seen_ids")
+        fl = filt.on_prediction({"seen_ids": seen}, logits)
+        k = 10
+        top_s, top_i = torch.topk(fl, k=k, dim=1)
+        out.update(seen_ids=seen.numpy(), topk_scores=top_s.numpy(), topk_ids=top_i.numpy())
+        cands = torch.randperm(n_items, generator=g)[: max(k + L + 2, n_items // 3)]
+        inf_c = model(feature_tensors={"item_id": ids}, padding_mask=pmask, candidates_to_score=cands)
+        out.update(candidates=cands.numpy(), cand_logits=inf_c["logits"].numpy())
+    np.savez_compressed(os.path.join(OUT, f"sasrec_new_{tag}.npz"), **out)
+    print("wrote sasrec_new_" + tag, "loss", float(loss))
+
+
+def gen_legacy_sasrec(tag, B, L, d, H, n_items, n_blocks, seed):
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    pad = n_items
+    model = SasRecModel(schema(n_items, d, pad), num_blocks=n_blocks, num_heads=H, hidden_size=d, max_len=L, dropout=0.0)
+    randomise_small_params(model, g)
+    ids, pmask, labels, tmask = make_batch(g, B, L, n_items, pad)
+    out = dict(sd_np(model))
+    out.update(ids=ids.numpy(), pad_mask=pmask.numpy(), labels=labels.numpy(), target_mask=tmask.numpy(),
+               n_items=n_items, d=d, H=H, L=L, n_blocks=n_blocks)
+    model.train()
+    hidden = model.forward_step({"item_id": ids}, pmask)
+    logits = model.get_logits(hidden)
+    # sasrec/lightning.py:335-355
+    lab = labels.masked_fill(~tmask, -100)
+    loss = torch.nn.CrossEntropyLoss()(logits.view(-1, logits.size(-1)), lab.view(-1))
+    loss.backward()
+    out["train_hidden"] = hidden.detach().numpy()
+    out["train_loss"] = loss.detach().numpy()
+    for k, p in model.named_parameters():
+        out["grad::" + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy().copy()
+    model.eval()
+    with torch.no_grad():
+        out["eval_logits"] = model.predict({"item_id": ids}, pmask).numpy()
+        out["eval_hidden_last"] = model.get_query_embeddings({"item_id": ids}, pmask).numpy()
+    np.savez_compressed(os.path.join(OUT, f"sasrec_legacy_{tag}.npz"), **out)
+    print("wrote sasrec_legacy_" + tag, "loss", float(loss))
+
+
+def gen_bert4rec(tag, B, L, d, H, n_items, n_blocks, seed, tying):
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    model = Bert4RecModel(schema(n_items, d, 0), max_len=L, hidden_size=d, num_blocks=n_blocks, num_heads=H,
+                          num_passes_over_block=1, dropout=0.0, enable_positional_embedding=True,
+                          enable_embedding_tying=tying)
+    randomise_small_params(model, g)
+    # left padded inputs, uniform token mask (bert4rec/dataset.py:71-92): tok False = <MASK>; pads are False too
+    lens = torch.randint(2, L + 1, (B,), generator=g)
+    lens[0] = L
+    ids = torch.zeros(B, L, dtype=torch.int64)
+    pmask = torch.zeros(B, L, dtype=torch.bool)
+    for b in range(B):
+        n = int(lens[b])
+        ids[b, L - n :] = torch.randint(0, n_items, (n,), generator=g)
+        pmask[b, L - n :] = True
+    tok = (torch.rand(B, L, generator=g) > 0.3) & pmask
+    tok[:, -1] = False  # make sure every row has a masked real position
+    labels = ids.clone()
+    out = dict(sd_np(model))
+    out.update(ids=ids.numpy(), pad_mask=pmask.numpy(), token_mask=tok.numpy(), labels=labels.numpy(),
+               n_items=n_items, d=d, H=H, L=L, n_blocks=n_blocks, tying=int(tying))
+    model.train()
+    hidden = model.forward_step({"item_id": ids}, pmask, tok)
+    logits = model.get_logits(hidden)
+    # bert4rec/lightning.py:332-351
+    labels_mask = (~pmask) + tok
+    masked = ~labels_mask
+    loss = torch.nn.CrossEntropyLoss()(logits[masked], labels[masked])
+    loss.backward()
+    out["train_hidden"] = hidden.detach().numpy()
+    out["train_loss"] = loss.detach().numpy()
+    for k, p in model.named_parameters():
+        out["grad::" + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy().copy()
+    model.eval()
+    with torch.no_grad():
+        out["eval_logits"] = model.predict({"item_id": ids}, pmask, tok).numpy()
+    np.savez_compressed(os.path.join(OUT, f"bert4rec_{tag}.npz"), **out)
+    print("wrote bert4rec_" + tag, "loss", float(loss))
+
+
+def gen_seen_filter_known_answers():
+    """tests/nn/lightning/postprocessor/conftest.py:7-31 + test_postprocessor.py:7-46, run through the reference."""
+    g = torch.Generator().manual_seed(3)
+    seen = torch.LongTensor([[5, 5, 0, 1, 1], [1, 2, 4, 0, 3], [5, 5, 5, 5, 5], [0, 1, 2, 2, 2]])
+    logits = torch.rand(4, 5, generator=g)
+    filt = SeenItemsFilter(item_count=5)
+    o1 = filt.on_prediction({"seen_ids": seen}, logits)
+    cands = torch.LongTensor([1, 3, 2, 4])
+    lc = torch.rand(4, 4, generator=g)
+    filt2 = SeenItemsFilter(item_count=5)
+    filt2.candidates = cands
+    o2 = filt2.on_prediction({"seen_ids": seen}, lc)
+    np.savez_compressed(os.path.join(OUT, "seen_filter_known.npz"), seen=seen.numpy(), logits=logits.numpy(),
+                        out=o1.numpy(), candidates=cands.numpy(), cand_logits=lc.numpy(), cand_out=o2.numpy())
+    print("wrote seen_filter_known")
+
+
+if __name__ == "__main__":
+    gen_new_sasrec("tiny", B=6, L=16, d=32, H=2, n_items=300, n_blocks=2, seed=11)
+    gen_new_sasrec("small", B=8, L=50, d=64, H=2, n_items=1000, n_blocks=2, seed=12)
+    gen_legacy_sasrec("tiny", B=6, L=16, d=32, H=2, n_items=300, n_blocks=2, seed=13)
+    gen_bert4rec("tiny", B=6, L=16, d=32, H=2, n_items=300, n_blocks=2, seed=14, tying=False)
+    gen_bert4rec("tiny_tied", B=6, L=16, d=32, H=2, n_items=300, n_blocks=2, seed=15, tying=True)
+    gen_seen_filter_known_answers()

@@ -1,0 +1,103 @@
+"""The CPU oracle (oracle/) must reproduce the golden vectors that oracle/gen_golden.py produced by running the REAL
+reference (sb-ai-lab/RePlay @ b4e051e8) in the build container.  This is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bert4rec as ob
+from oracle import sasrec as osr
+
+TOL = dict(rtol=2e-5, atol=2e-6)
+
+
+def load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name))
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}
+    return z, sd
+
+
+@pytest.mark.parametrize("name", ["sasrec_new_tiny.npz", "sasrec_new_small.npz"])
+def test_new_sasrec_matches_reference(golden_dir, name):
+    z, sd = load(golden_dir, name)
+    P = osr.params_from_new_state_dict(sd)
+    ids, pm = torch.from_numpy(z["ids"]), torch.from_numpy(z["pad_mask"])
+    labels, tm = torch.from_numpy(z["labels"]), torch.from_numpy(z["target_mask"])
+    H, n_items = int(z["H"]), int(z["n_items"])
+    h = osr.sasrec_body(P, ids, pm, H, "new")
+    torch.testing.assert_close(h, torch.from_numpy(z["train_hidden"]), **TOL)  # all rows incl. pad rows
+    loss, G = osr.loss_and_grads(P, ids, pm, labels, tm, H, "new")
+    torch.testing.assert_close(loss, torch.from_numpy(z["train_loss"]), rtol=1e-5, atol=1e-6)
+    # gradients of every parameter
+    gref = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad::")}
+    Gref = osr.params_from_new_state_dict(gref)
+    for a, b in zip(osr.flat_param_list(G), osr.flat_param_list(Gref)):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-6)
+    # eval logits of the last position (real rows identical in eval)
+    h_eval = osr.sasrec_body(P, ids, pm, H, "new", mode="eval")  # differs from train only on pad query rows
+    real = pm[:, -1]
+    torch.testing.assert_close(h_eval[pm], h[pm], rtol=0, atol=0)  # real rows: bit-identical
+    h = h_eval
+    logits = h[:, -1] @ P["item_emb"][:n_items].T
+    torch.testing.assert_close(logits, torch.from_numpy(z["eval_logits"]), **TOL)
+    # SeenItemsFilter + topk
+    ids_k, sc_k = osr.score_topk(h[:, -1], P["item_emb"][:n_items], torch.from_numpy(z["seen_ids"]), 10,
+                                 acc_dtype=torch.float32)
+    assert torch.equal(ids_k, torch.from_numpy(z["topk_ids"]))
+    torch.testing.assert_close(sc_k, torch.from_numpy(z["topk_scores"]), **TOL)
+    # candidates
+    c = torch.from_numpy(z["candidates"])
+    torch.testing.assert_close(h[:, -1] @ P["item_emb"][:n_items][c].T, torch.from_numpy(z["cand_logits"]), **TOL)
+    # one Adam step (optimizer_factory.py:56-63)
+    a1 = osr.params_from_new_state_dict({k[7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("adam1::")})
+    for p, g, ref in zip(osr.flat_param_list(P), osr.flat_param_list(Gref), osr.flat_param_list(a1)):
+        p1, _, _ = osr.adam_step(p, g, torch.zeros_like(p), torch.zeros_like(p), 1)
+        torch.testing.assert_close(p1, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_legacy_sasrec_matches_reference(golden_dir):
+    z, sd = load(golden_dir, "sasrec_legacy_tiny.npz")
+    P = osr.params_from_legacy_state_dict(sd)
+    ids, pm = torch.from_numpy(z["ids"]), torch.from_numpy(z["pad_mask"])
+    labels, tm = torch.from_numpy(z["labels"]), torch.from_numpy(z["target_mask"])
+    H, n_items = int(z["H"]), int(z["n_items"])
+    h = osr.sasrec_body(P, ids, pm, H, "legacy")
+    torch.testing.assert_close(h, torch.from_numpy(z["train_hidden"]), **TOL)
+    loss, G = osr.loss_and_grads(P, ids, pm, labels, tm, H, "legacy")
+    torch.testing.assert_close(loss, torch.from_numpy(z["train_loss"]), rtol=1e-5, atol=1e-6)
+    gref = osr.params_from_legacy_state_dict({k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad::")})
+    for a, b in zip(osr.flat_param_list(G), osr.flat_param_list(gref)):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(h[:, -1] @ P["item_emb"][:n_items].T, torch.from_numpy(z["eval_logits"]), **TOL)
+
+
+@pytest.mark.parametrize("name", ["bert4rec_tiny.npz", "bert4rec_tiny_tied.npz"])
+def test_bert4rec_matches_reference(golden_dir, name):
+    z, sd = load(golden_dir, name)
+    P = ob.params_from_state_dict(sd)
+    ids, pm, tok = (torch.from_numpy(z[k]) for k in ("ids", "pad_mask", "token_mask"))
+    H = int(z["H"])
+    h = ob.bert4rec_body(P, ids, pm, tok, H)
+    torch.testing.assert_close(h, torch.from_numpy(z["train_hidden"]), **TOL)
+    loss = ob.train_loss(P, ids, pm, tok, torch.from_numpy(z["labels"]), H)
+    torch.testing.assert_close(loss, torch.from_numpy(z["train_loss"]), rtol=1e-5, atol=1e-6)
+    w, b = ob.head_weights(P)
+    torch.testing.assert_close(h[:, -1] @ w.T + b, torch.from_numpy(z["eval_logits"]), **TOL)
+
+
+def test_seen_filter_known_answers(golden_dir):
+    """tests/nn/lightning/postprocessor/test_postprocessor.py:7-46 (reference), via golden outputs of the reference."""
+    z = np.load(os.path.join(golden_dir, "seen_filter_known.npz"))
+    out = osr.seen_filter(torch.from_numpy(z["logits"]), torch.from_numpy(z["seen"]), 5)
+    assert torch.equal(out, torch.from_numpy(z["out"]))
+    expect_mask = torch.tensor([[1, 1, 0, 0, 0], [1, 1, 1, 1, 1], [0, 0, 0, 0, 0], [1, 1, 1, 0, 0]], dtype=torch.bool)
+    assert torch.equal(torch.isinf(out), expect_mask)
+
+
+def test_sasrec_training_example_layout():
+    """tests/models/nn/sequential/sasrec/test_sasrec_dataset.py:40-48 known answer (sequence [0, 1], max_len 8)."""
+    ids, pm, labels, tm = osr.sasrec_training_example([0, 1], 8, pad_value=-1)
+    assert pm.tolist() == [False] * 7 + [True]
+    assert tm.tolist() == [False] * 6 + [True, True]
+    assert labels.tolist() == [-1] * 6 + [0, 1]

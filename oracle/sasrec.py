@@ -302,7 +302,7 @@ def score_topk(hq, table, seen_ids, k, candidates=None, acc_dtype=torch.float64)
     """Predict head: scores = hq @ table.T, seen filter, top-k sorted descending.
 
     predictions_callback.py:80-96 (torch.topk(k, dim=1)); torch's tie order is unspecified, the oracle (and the CUDA
-    kernel) use (score desc, item id asc).  With ``candidates`` the scores are over table[candidates] in the given
+    kernel) use (score desc, scored column asc).  With ``candidates`` the scores are over table[candidates] in the given
     order and the returned ids are mapped back through ``candidates`` (predictions_callback.py:91-92); the seen filter
     applies to the real item ids (seen_items.py:68-71,80-81).
     Returns (ids int64 [B,k], scores acc_dtype [B,k]).
@@ -321,14 +321,11 @@ def score_topk(hq, table, seen_ids, k, candidates=None, acc_dtype=torch.float64)
             full[:, candidates] = scores
             full = seen_filter(full, seen_ids, item_count)
             scores = full[:, candidates]
-    n = scores.shape[1]
-    item_of_col = candidates if candidates is not None else torch.arange(n)
-    # stable sort by (score desc, id asc): sort by id first, then stable-sort by -score
-    order_id = torch.argsort(item_of_col, stable=True)
-    s2 = scores[:, order_id]
-    order_s = torch.argsort(-s2, dim=1, stable=True)[:, :k]
-    cols = order_id[order_s]
-    return item_of_col[cols], torch.gather(scores, 1, cols)
+    # ties: smaller column (position in the scored list) first - torch.argsort(stable) on -score
+    cols = torch.argsort(-scores, dim=1, stable=True)[:, :k]
+    top = torch.gather(scores, 1, cols)
+    ids = candidates[cols] if candidates is not None else cols
+    return ids, top
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,409 @@
+// rp_score_topk.cu - fused predict head:  scores = Hq[B,d] . E[I,d]^T  ->  seen-item mask  ->  per-row top-K.
+//
+// Replaces, for one batch of users, the reference chain
+//   EmbeddingTyingHead.forward            replay/nn/head.py:29-34   (legacy: models/nn/sequential/sasrec/model.py:286-307)
+//   SeenItemsFilter._compute_scores       replay/nn/lightning/postprocessor/seen_items.py:56-83
+//   torch.topk(logits, k, dim=1)          replay/nn/lightning/callback/predictions_callback.py:90
+// without ever materialising the [B, |I|] logits.
+//
+// Kernel 1 (score_topk_kernel): one CTA = 128 users x a contiguous range of 128-item tiles.
+//   warp 0   TMA producer: user tile A (resident in smem) + ring of item-table K-chunks [128 items x 64]
+//   warp 1   tcgen05.mma issuer: S[128x128] fp32 in TMEM, double buffered (2 x 128 columns)
+//   warps 2-5 epilogue: tcgen05.ld 32 columns at a time, thread = user row, seen-mask via a cursor into the user's
+//            sorted seen list, running top-K (sorted, registers), partial top-K written per (user, item split)
+// Kernel 2 (topk_merge_kernel): one warp per user merges the per-split partial lists (score desc, column asc).
+#include "rp_host.h"
+#include "rp_sm100.cuh"
+
+namespace rp {
+
+static constexpr int kTileM = 128;   // users per CTA
+static constexpr int kTileN = 128;   // items per MMA tile
+static constexpr int kChunkBytes = 128 * 128;  // [128 rows x 64 bf16]
+static constexpr int kNoId = 0x7fffffff;
+
+template <int KMAX>
+struct TopK {
+  float v[KMAX];
+  int id[KMAX];
+  float thr;
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      v[i] = -INFINITY;
+      id[i] = kNoId;
+    }
+    thr = -INFINITY;
+  }
+  // sorted insert (descending, earlier insert wins ties because ids arrive in ascending order)
+  __device__ __forceinline__ void insert(float x, int xi, int K) {
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      const bool gt = x > v[i];
+      const float tv = gt ? v[i] : x;
+      const int ti = gt ? id[i] : xi;
+      v[i] = gt ? x : v[i];
+      id[i] = gt ? xi : id[i];
+      x = tv;
+      xi = ti;
+    }
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i)
+      if (i == K - 1) thr = v[i];
+  }
+};
+
+template <int KCH /* d / 64 */, int NSTAGE, int KMAX>
+__global__ void __launch_bounds__(192, 1)
+score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const int32_t* __restrict__ seen_sorted, int S, int n_users, int n_items, int K, int n_splits,
+                  float* __restrict__ part_vals, int32_t* __restrict__ part_ids) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                          // KCH chunks of 16 KB
+  uint8_t* sB = smem + KCH * kChunkBytes;      // NSTAGE chunks of 16 KB
+  __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int user_tile = blockIdx.x / n_splits, split = blockIdx.x % n_splits;
+  const int u0 = user_tile * kTileM;
+  const int n_tiles_total = (n_items + kTileN - 1) / kTileN;
+  const int t_begin = (int)(((long long)n_tiles_total * split) / n_splits);
+  const int t_end = (int)(((long long)n_tiles_total * (split + 1)) / n_splits);
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_a, 1);
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_tfull[i], 1);
+      mbar_init(&bar_tempty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bar_a, KCH * kChunkBytes);
+      for (int kc = 0; kc < KCH; ++kc) tma_load_2d(sA + kc * kChunkBytes, &tmA, &bar_a, kc * 64, u0);
+      uint32_t it = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        for (int kc = 0; kc < KCH; ++kc, ++it) {
+          const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
+          mbar_wait(&bar_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&bar_full[s], kChunkBytes);
+          tma_load_2d(sB + s * kChunkBytes, &tmB, &bar_full[s], kc * 64, t * kTileN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, kTileN);
+      mbar_wait(&bar_a, 0);
+      tc_fence_after();
+      uint32_t it = 0;
+      for (int t = t_begin, j = 0; t < t_end; ++t, ++j) {
+        const uint32_t as = j & 1, aph = (j >> 1) & 1;
+        mbar_wait(&bar_tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t dcol = tmem + as * kTileN;
+        for (int kc = 0; kc < KCH; ++kc, ++it) {
+          const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
+          mbar_wait(&bar_full[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + kc * kChunkBytes), b0 = smem_u32(sB + s * kChunkBytes);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss(dcol, umma_desc_sw128(a0 + ks * 32, 16, 1024), umma_desc_sw128(b0 + ks * 32, 16, 1024), idesc,
+                    (kc | ks) != 0);
+          umma_commit(&bar_empty[s]);
+        }
+        umma_commit(&bar_tfull[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue: 4 warps, warp%4 = TMEM lane quarter
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int u = u0 + row;
+    const bool live = u < n_users;
+    TopK<KMAX> top;
+    top.init();
+    // cursor into this user's sorted seen list (ascending, kNoId = padding)
+    const int32_t* sp = seen_sorted ? seen_sorted + (size_t)(live ? u : 0) * S : nullptr;
+    int ci = 0;
+    int next_seen = kNoId;
+    if (sp && live) {
+      const int first_col = t_begin * kTileN;
+      int lo = 0, hi = S;  // lower_bound(first_col)
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sp[mid] < first_col) lo = mid + 1; else hi = mid;
+      }
+      ci = lo;
+      next_seen = ci < S ? sp[ci] : kNoId;
+    }
+    for (int t = t_begin, j = 0; t < t_end; ++t, ++j) {
+      const uint32_t as = j & 1, aph = (j >> 1) & 1;
+      mbar_wait(&bar_tfull[as], aph);
+      tc_fence_after();
+      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + as * kTileN;
+#pragma unroll 1
+      for (int c = 0; c < kTileN; c += 32) {
+        uint32_t raw[32];
+        tmem_ld32(tbase + c, raw);
+        tmem_ld_wait();
+        const int col0 = t * kTileN + c;
+        float x[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) x[q] = __uint_as_float(raw[q]);
+        if (col0 + 32 > n_items) {  // ragged last tile: columns beyond the catalog do not exist
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (col0 + q >= n_items) x[q] = -INFINITY;
+        }
+        while (next_seen < col0 + 32) {  // rare: a seen item falls in this 32-column chunk
+          const int q0 = next_seen - col0;
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (q == q0) x[q] = -INFINITY;
+          ++ci;
+          next_seen = ci < S ? sp[ci] : kNoId;
+        }
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) any |= (x[q] > top.thr);
+        if (any) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (x[q] > top.thr) top.insert(x[q], col0 + q, K);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[as]);
+    }
+    if (live) {
+      float* pv = part_vals + ((size_t)u * n_splits + split) * K;
+      int32_t* pi = part_ids + ((size_t)u * n_splits + split) * K;
+#pragma unroll
+      for (int i = 0; i < KMAX; ++i)
+        if (i < K) {
+          pv[i] = top.v[i];
+          pi[i] = top.id[i];
+        }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// one warp per user: merge n_splits sorted partial lists -> final top-K; ties: smaller column first.
+// Slots that no finite candidate fills (fewer than K unmasked items) are filled with the user's masked columns in
+// ascending order, score -inf (torch.topk would return arbitrary -inf entries there).
+__global__ void topk_merge_kernel(const float* __restrict__ part_vals, const int32_t* __restrict__ part_ids,
+                                  const int32_t* __restrict__ seen_sorted, int S, int n_users, int n_items, int K,
+                                  int n_splits, const int64_t* __restrict__ candidates, int64_t* __restrict__ out_ids,
+                                  float* __restrict__ out_scores) {
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (u >= n_users) return;
+  const int n = n_splits * K;
+  const float* pv = part_vals + (size_t)u * n;
+  const int32_t* pi = part_ids + (size_t)u * n;
+  // each lane owns candidates lane, lane+32, ...  ; consumed ones are flagged by setting id to kNoId+(-inf)
+  float last_v = INFINITY;
+  int last_id = -1;
+  int n_out = 0;
+  for (int k = 0; k < K; ++k) {
+    // best candidate strictly after (last_v, last_id) in (score desc, id asc) order
+    float bv = -INFINITY;
+    int bi = kNoId;
+    for (int i = lane; i < n; i += 32) {
+      const float v = pv[i];
+      const int id = pi[i];
+      if (id == kNoId) continue;
+      const bool after = (v < last_v) || (v == last_v && id > last_id);
+      if (!after) continue;
+      if (v > bv || (v == bv && id < bi)) {
+        bv = v;
+        bi = id;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ov > bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if (bi == kNoId) break;
+    if (lane == 0) {
+      out_ids[(size_t)u * K + k] = candidates ? candidates[bi] : (int64_t)bi;
+      out_scores[(size_t)u * K + k] = bv;
+    }
+    last_v = bv;
+    last_id = bi;
+    ++n_out;
+  }
+  if (n_out < K && lane == 0) {
+    int ci = 0;
+    int prev = -1;
+    for (int k = n_out; k < K; ++k) {
+      int col = kNoId;
+      while (seen_sorted && ci < S) {
+        const int c = seen_sorted[(size_t)u * S + ci++];
+        if (c != prev && c < n_items) {
+          col = c;
+          prev = c;
+          break;
+        }
+      }
+      out_ids[(size_t)u * K + k] = (col == kNoId) ? -1 : (candidates ? candidates[col] : (int64_t)col);
+      out_scores[(size_t)u * K + k] = -INFINITY;
+    }
+  }
+}
+
+// Prepare the seen lists for score_topk: int64 ids [B,S] -> int32 columns sorted ascending, padding = kNoId.
+// Ids outside [0, item_count) are padding (seen_items.py:62).  With inv_map (candidates_to_score) an id becomes its
+// position in the candidate list (or padding when it is not a candidate).  One block per user, bitonic sort in smem.
+template <int SPAD>
+__global__ void seen_prepare_kernel(const int64_t* __restrict__ seen, int S, int item_count,
+                                    const int32_t* __restrict__ inv_map, int32_t* __restrict__ out) {
+  __shared__ int32_t buf[SPAD];
+  const int u = blockIdx.x;
+  for (int i = threadIdx.x; i < SPAD; i += blockDim.x) {
+    int32_t v = kNoId;
+    if (i < S) {
+      const int64_t id = seen[(size_t)u * S + i];
+      if (id >= 0 && id < item_count) {
+        v = (int32_t)id;
+        if (inv_map) {
+          v = inv_map[v];
+          if (v < 0) v = kNoId;
+        }
+      }
+    }
+    buf[i] = v;
+  }
+  __syncthreads();
+  for (int k = 2; k <= SPAD; k <<= 1) {
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      for (int i = threadIdx.x; i < SPAD; i += blockDim.x) {
+        const int ixj = i ^ jj;
+        if (ixj > i) {
+          const bool up = (i & k) == 0;
+          const int32_t a = buf[i], b = buf[ixj];
+          if ((a > b) == up) {
+            buf[i] = b;
+            buf[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < S; i += blockDim.x) out[(size_t)u * S + i] = buf[i];
+}
+
+static int choose_splits(int n_user_tiles, int n_item_tiles) {
+  const int sms = sm_count();
+  int p = sms / n_user_tiles;
+  if (p < 1) p = 1;
+  if (p > n_item_tiles) p = n_item_tiles;
+  if (p > 64) p = 64;
+  return p;
+}
+
+template <int KCH, int NSTAGE>
+static int launch_score_topk(const CUtensorMap& tmA, const CUtensorMap& tmB, const int32_t* seen_sorted, int S, int B,
+                             int I, int K, int n_splits, float* pv, int32_t* pi, cudaStream_t stream) {
+  const int smem = (KCH + NSTAGE) * kChunkBytes + 1024;
+  const int grid = ((B + kTileM - 1) / kTileM) * n_splits;
+  if (K <= 16) {
+    auto kern = score_topk_kernel<KCH, NSTAGE, 16>;
+    RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, 192, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, pv, pi);
+  } else {
+    auto kern = score_topk_kernel<KCH, NSTAGE, 32>;
+    RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, 192, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, pv, pi);
+  }
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+}  // namespace rp
+
+RP_API size_t rp_score_topk_workspace(int n_users, int n_items, int d, int K) {
+  (void)d;
+  if (n_users <= 0 || n_items <= 0 || K <= 0) return 0;
+  const int ut = (n_users + rp::kTileM - 1) / rp::kTileM, it = (n_items + rp::kTileN - 1) / rp::kTileN;
+  const int p = rp::choose_splits(ut, it);
+  return (size_t)n_users * p * K * 8 + 256;
+}
+
+RP_API int rp_seen_prepare(const int64_t* seen_ids, int n_users, int S, int item_count, const int32_t* inv_map,
+                    int32_t* out_sorted, void* stream_) {
+  using namespace rp;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (n_users <= 0 || S <= 0) return RP_ESHAPE;
+  if (S <= 64) seen_prepare_kernel<64><<<n_users, 64, 0, stream>>>(seen_ids, S, item_count, inv_map, out_sorted);
+  else if (S <= 256) seen_prepare_kernel<256><<<n_users, 128, 0, stream>>>(seen_ids, S, item_count, inv_map, out_sorted);
+  else if (S <= 1024) seen_prepare_kernel<1024><<<n_users, 256, 0, stream>>>(seen_ids, S, item_count, inv_map, out_sorted);
+  else if (S <= 4096) seen_prepare_kernel<4096><<<n_users, 512, 0, stream>>>(seen_ids, S, item_count, inv_map, out_sorted);
+  else return RP_ESHAPE;
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+RP_API int rp_score_topk(const void* hq, const void* table, const float* bias, const int32_t* seen_sorted, int S, int n_users,
+                  int n_items, int d, int K, const int64_t* candidates, int64_t* out_ids, float* out_scores,
+                  void* workspace, size_t workspace_bytes, void* stream_) {
+  using namespace rp;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!hq || !table || !out_ids || !out_scores || !workspace) return RP_EINVAL;
+  if (bias) return RP_EINVAL;  // TODO(bert4rec head bias)
+  if (n_users <= 0 || n_items <= 0 || K <= 0 || K > 32 || K > n_items) return RP_ESHAPE;
+  if (d != 64 && d != 128 && d != 256 && d != 512) return RP_ESHAPE;
+  if (seen_sorted && S <= 0) return RP_ESHAPE;
+  if (workspace_bytes < rp_score_topk_workspace(n_users, n_items, d, K)) return RP_EWORKSPACE;
+  const int ut = (n_users + kTileM - 1) / kTileM, it = (n_items + kTileN - 1) / kTileN;
+  const int p = choose_splits(ut, it);
+  float* pv = reinterpret_cast<float*>(workspace);
+  int32_t* pi = reinterpret_cast<int32_t*>(pv + (size_t)n_users * p * K);
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap_bf16(&tmA, hq, n_users, d, d, 128)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmB, table, n_items, d, d, 128)) != RP_OK) return rc;
+  switch (d) {
+    case 64: rc = launch_score_topk<1, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, pv, pi, stream); break;
+    case 128: rc = launch_score_topk<2, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, pv, pi, stream); break;
+    case 256: rc = launch_score_topk<4, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, pv, pi, stream); break;
+    default: rc = launch_score_topk<8, 5>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, pv, pi, stream); break;
+  }
+  if (rc != RP_OK) return rc;
+  const int threads = 128;
+  const int blocks = (n_users * 32 + threads - 1) / threads;
+  topk_merge_kernel<<<blocks, threads, 0, stream>>>(pv, pi, seen_sorted, S, n_users, n_items, K, p, candidates, out_ids,
+                                                    out_scores);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+

@@ -1,0 +1,62 @@
+"""Tensor-level wrappers over the C ABI (include/rp_b200.h).  torch is used for device memory and streams only; every
+function launches hand-written sm_100a kernels from librp_b200.so on the current CUDA stream."""
+from __future__ import annotations
+
+import torch
+
+from ._lib import check, lib
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(t, dtype, name):
+    if t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{name}: expected contiguous CUDA tensor of {dtype}, got {t.dtype} on {t.device}")
+
+
+def selftest_umma(mode: int, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    _need(a, torch.bfloat16, "a")
+    _need(b, torch.bfloat16, "b")
+    d = torch.empty(128, 128, device=a.device, dtype=torch.float32)
+    check(lib().rp_selftest_umma(mode, _ptr(a), _ptr(b), _ptr(d), _stream()), "rp_selftest_umma")
+    return d
+
+
+def seen_prepare(seen_ids: torch.Tensor, item_count: int, inv_map: torch.Tensor | None = None) -> torch.Tensor:
+    """int64 [B,S] seen ids -> int32 [B,S] sorted ascending, padding = INT32_MAX (include/rp_b200.h rp_seen_prepare)."""
+    _need(seen_ids, torch.int64, "seen_ids")
+    B, S = seen_ids.shape
+    out = torch.empty(B, S, device=seen_ids.device, dtype=torch.int32)
+    if inv_map is not None:
+        _need(inv_map, torch.int32, "inv_map")
+    check(lib().rp_seen_prepare(_ptr(seen_ids), B, S, item_count, _ptr(inv_map), _ptr(out), _stream()), "rp_seen_prepare")
+    return out
+
+
+def score_topk(hq: torch.Tensor, table: torch.Tensor, k: int, seen_sorted: torch.Tensor | None = None,
+               candidates: torch.Tensor | None = None, bias: torch.Tensor | None = None):
+    """Fused scores -> seen mask -> top-k.  hq bf16 [B,d], table bf16 [I,d].  Returns (ids int64 [B,k], scores fp32 [B,k])."""
+    _need(hq, torch.bfloat16, "hq")
+    _need(table, torch.bfloat16, "table")
+    B, d = hq.shape
+    n_items = table.shape[0]
+    S = 0
+    if seen_sorted is not None:
+        _need(seen_sorted, torch.int32, "seen_sorted")
+        S = seen_sorted.shape[1]
+    if candidates is not None:
+        _need(candidates, torch.int64, "candidates")
+    L = lib()
+    ws_bytes = L.rp_score_topk_workspace(B, n_items, d, k)
+    ws = torch.empty(ws_bytes, device=hq.device, dtype=torch.uint8)
+    ids = torch.empty(B, k, device=hq.device, dtype=torch.int64)
+    scores = torch.empty(B, k, device=hq.device, dtype=torch.float32)
+    check(L.rp_score_topk(_ptr(hq), _ptr(table), _ptr(bias), _ptr(seen_sorted), S, B, n_items, d, k, _ptr(candidates),
+                          _ptr(ids), _ptr(scores), _ptr(ws), ws_bytes, _stream()), "rp_score_topk")
+    return ids, scores

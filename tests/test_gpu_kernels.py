@@ -1,0 +1,87 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C ABI (ctypes), against the CPU oracle."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from replay_b200 import ops as _ops
+
+    return _ops
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
+def test_umma_operand_modes(ops, mode):
+    """tcgen05 descriptor encodings: K-major / MN-major smem operands, A from TMEM."""
+    g = torch.Generator().manual_seed(mode)
+    a = torch.randn(128, 128, generator=g).to(torch.bfloat16)
+    b = torch.randn(128, 128, generator=g).to(torch.bfloat16)
+    ref = a.double() @ b.double().T
+    a_in = a.T.contiguous() if mode & 4 else a
+    b_in = b.T.contiguous() if mode & 1 else b
+    d = ops.selftest_umma(mode, a_in.cuda(), b_in.cuda()).cpu().double()
+    err = (d - ref).abs().max().item()
+    assert err < 1e-3, f"mode {mode}: max err {err}"
+
+
+def _topk_case(ops, B, I, d, K, S, seed, with_seen=True):
+    from oracle import sasrec as osr
+
+    g = torch.Generator().manual_seed(seed)
+    hq = (torch.randn(B, d, generator=g) * 0.5).to(torch.bfloat16)
+    table = (torch.randn(I, d, generator=g) * 0.5).to(torch.bfloat16)
+    seen = torch.randint(0, I + 5, (B, S), generator=g) if with_seen else None  # ids >= I are padding
+    if with_seen:
+        seen[0, :] = I  # a user with nothing seen
+        seen[1, : S // 2] = seen[1, 0]  # duplicates
+    ids_ref, sc_ref = osr.score_topk(hq.float(), table.float(), seen, K, acc_dtype=torch.float64)
+    seen_sorted = ops.seen_prepare(seen.cuda(), I) if with_seen else None
+    ids, sc = ops.score_topk(hq.cuda(), table.cuda(), K, seen_sorted)
+    ids, sc = ids.cpu(), sc.cpu()
+    torch.testing.assert_close(sc.double(), sc_ref, rtol=1e-4, atol=1e-4)
+    mism = ids != ids_ref
+    if mism.any():
+        # adjudicate in fp64: a swap is only acceptable between scores closer than fp32 accumulation noise
+        full = hq.double() @ table.double().T
+        gap = (torch.gather(full, 1, ids.clamp_min(0)) - torch.gather(full, 1, ids_ref)).abs()
+        assert (gap[mism] < 1e-5).all(), f"{int(mism.sum())} index mismatches beyond fp32 noise"
+        assert mism.float().mean() < 1e-3
+    return ids, sc
+
+
+@pytest.mark.parametrize("B,I,d,K,S", [(6, 300, 64, 10, 16), (128, 4000, 64, 10, 50), (300, 50000, 128, 10, 200),
+                                       (512, 20001, 128, 20, 64), (130, 9000, 256, 5, 32), (64, 5000, 512, 10, 32)])
+def test_score_topk_matches_oracle(ops, B, I, d, K, S):
+    _topk_case(ops, B, I, d, K, S, seed=B + I)
+
+
+def test_score_topk_no_filter(ops):
+    _topk_case(ops, 200, 10000, 128, 10, 0, seed=5, with_seen=False)
+
+
+def test_score_topk_golden_reference(ops, golden_dir):
+    """End of the reference chain on the golden vectors generated from the real reference: eval hidden (bf16-rounded)
+    x item table -> SeenItemsFilter -> torch.topk.  The hidden/table are rounded to bf16 for the kernel, so compare against
+    the oracle on the same rounded inputs, and check the reference's own top-k set overlaps almost entirely."""
+    import os
+
+    import numpy as np
+
+    from oracle import sasrec as osr
+
+    z = np.load(os.path.join(golden_dir, "sasrec_new_small.npz"))
+    n_items, d = int(z["n_items"]), int(z["d"])
+    table = torch.from_numpy(z["sd::body.embedder.feature_embedders.item_id.emb.weight"])[:n_items]
+    hq = torch.from_numpy(z["eval_hidden_last"])
+    seen = torch.from_numpy(z["seen_ids"])
+    hq16, tb16 = hq.to(torch.bfloat16), table.to(torch.bfloat16)
+    ids_ref, _ = osr.score_topk(hq16.float(), tb16.float(), seen, 10)
+    ids, sc = ops.score_topk(hq16.cuda(), tb16.cuda(), 10, ops.seen_prepare(seen.cuda(), n_items))
+    assert torch.equal(ids.cpu(), ids_ref)
+    ref_ids = torch.from_numpy(z["topk_ids"])
+    overlap = np.mean([len(set(a.tolist()) & set(b.tolist())) / 10 for a, b in zip(ids.cpu(), ref_ids)])
+    assert overlap > 0.9

@@ -60,6 +60,30 @@ int rp_score_topk(const void* hq, const void* table, const float* bias, const in
                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Training head: full-catalog cross entropy fused with the logits GEMM, forward and backward
+ *   replaces  logits = hidden . E^T                 replay/nn/head.py:29-34 ; replay/nn/sequential/sasrec/model.py:258-265
+ *             torch.nn.CrossEntropyLoss (mean)       replay/nn/loss/ce.py:49-81
+ *                                                    replay/models/nn/sequential/sasrec/lightning.py:335-355
+ *                                                    replay/models/nn/sequential/bert4rec/lightning.py:332-351
+ *             and autograd's backward of both.
+ * hc bf16 [capacity, d]: hidden rows of the VALID targets, compacted (rows >= *n_valid are ignored but must be finite);
+ * table bf16 [n_items, d]; labels int32 [capacity]; n_valid int32 [1] IN DEVICE MEMORY (keeps the step graph-capturable).
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t rp_ce_head_workspace(int capacity_tokens, int n_items, int d);
+
+/* loss_out fp32 [2] = { mean CE over the valid targets, 1 / n_valid }; lse fp32 [capacity];
+ * cvec fp32 [round_up(capacity,128)] (per-token exponent offsets for the backward; entries >= capacity must be -inf). */
+int rp_ce_head_fwd(const void* hc, const void* table, const int32_t* labels, const int32_t* n_valid, int capacity,
+                   int n_items, int d, float* loss_out, float* lse, float* cvec, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* gradients of the mean CE for d(loss) = 1:  d_hc bf16 [capacity, d] (rows < *n_valid written);
+ * d_table fp32 [n_items, d] is OVERWRITTEN (softmax part) and then atomically corrected by the one-hot part.
+ * d in {64,128,256}. */
+int rp_ce_head_bwd(const void* hc, const void* table, const int32_t* labels, const int32_t* n_valid, int capacity,
+                   int n_items, int d, const float* loss_out, const float* cvec, void* d_hc, float* d_table, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Bring-up self test of the tcgen05 operand encodings (used by tests/, not by the product path).
  * A, B: bf16 [128,128]; D: fp32 [128,128].  mode bit0: B given as Bt[K,N]; bit1: A staged through TMEM;
  * bit2: A given as At[K,M].  D = A . B^T in every mode.

@@ -51,6 +51,9 @@ def lib():
     _sig(L.rp_seen_prepare, c_int, [P, c_int, c_int, c_int, P, P, P])
     _sig(L.rp_score_topk_workspace, c_size_t, [c_int, c_int, c_int, c_int])
     _sig(L.rp_score_topk, c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P])
+    _sig(L.rp_ce_head_workspace, c_size_t, [c_int, c_int, c_int])
+    _sig(L.rp_ce_head_fwd, c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, c_size_t, P])
+    _sig(L.rp_ce_head_bwd, c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P])
     for name, restype, argtypes in _EXTRA_SIGS:
         _sig(getattr(L, name), restype, argtypes)
     _lib = L

@@ -1,0 +1,581 @@
+// rp_ce_head.cu - fused full-catalog cross-entropy head (training), forward and backward, without ever materialising the
+// [tokens, items] logits.
+//
+// Replaces   logits = hidden . E^T               replay/nn/head.py:29-34, replay/nn/sequential/sasrec/model.py:258-265
+//            torch.nn.CrossEntropyLoss(mean)     replay/nn/loss/ce.py:49-81 ; models/nn/sequential/sasrec/lightning.py:335-355
+// and their autograd backward (dHidden, dE).
+//
+// Inputs are the COMPACTED valid-target rows Hc[T_v, d] (bf16, capacity T rows; T_v lives in device memory so the whole
+// step stays CUDA-graph capturable), the item table E[I, d] (bf16) and labels[T_v].
+//
+//   ce_fwd_kernel      CTA = 128 tokens x an item split.  S = Hc.E^T tile by tile in TMEM; epilogue keeps an online
+//                      (max, sum-exp) per row and picks the target logit.                      -> partial (m, s), z_y
+//   ce_finalize_kernel lse, loss = mean(lse - z_y), per-token exponent offset c_t = -lse*log2e + log2(1/T_v)
+//   ce_bwd_kernel<ROW> CTA = 128 tokens, loops over item tiles:   G = exp2(S*log2e + c_row) (bf16, written back into
+//                      TMEM over S), dH += G . E_tile  (A from TMEM, B = the same smem tile, MN-major)
+//                      final: dH[t] -= E[y_t] / T_v                                             -> dHc bf16 [T_v, d]
+//   ce_bwd_kernel<COL> CTA = 128 items, loops over token tiles:   S^T = E_tile . Hc^T, G = exp2(S^T*log2e + c_col),
+//                      dE += G . Hc_tile                                                          -> dE fp32 [I, d] (=)
+//   ce_label_scatter   dE[y_t] -= Hc[t] / T_v   (the one-hot part of softmax - onehot, sparse)
+#include "rp_host.h"
+#include "rp_sm100.cuh"
+
+namespace rp {
+
+static constexpr int kT = 128;                  // tile edge (rows per CTA, columns per MMA tile)
+static constexpr int kChunk = 128 * 128;        // bytes of one [128 rows x 64 bf16] swizzled chunk
+static constexpr float kLog2e = 1.4426950408889634f;
+static constexpr float kLn2 = 0.6931471805599453f;
+static constexpr int kEpiWarps = 8;
+static constexpr int kThreads = 64 + kEpiWarps * 32;
+
+// ----------------------------------------------------------------------------------------------------------------
+// forward
+// ----------------------------------------------------------------------------------------------------------------
+template <int KCH, int NSTAGE>
+__global__ void __launch_bounds__(kThreads, 1)
+ce_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const int32_t* __restrict__ labels, const int32_t* __restrict__ n_valid_ptr, int n_items, int n_splits,
+              float2* __restrict__ part /* [T, n_splits, 2] (m in log2 units, s) */, float* __restrict__ zt /* [T] */) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + KCH * kChunk;
+  __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tok_tile = blockIdx.x / n_splits, split = blockIdx.x % n_splits;
+  const int n_valid = *n_valid_ptr;
+  const int t0 = tok_tile * kT;
+  if (t0 >= n_valid) return;  // uniform for the CTA
+  const int n_tiles_total = (n_items + kT - 1) / kT;
+  const int j_begin = (int)(((long long)n_tiles_total * split) / n_splits);
+  const int j_end = (int)(((long long)n_tiles_total * (split + 1)) / n_splits);
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_a, 1);
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_tfull[i], 1);
+      mbar_init(&bar_tempty[i], kEpiWarps);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bar_a, KCH * kChunk);
+      for (int kc = 0; kc < KCH; ++kc) tma_load_2d(sA + kc * kChunk, &tmA, &bar_a, kc * 64, t0);
+      uint32_t it = 0;
+      for (int j = j_begin; j < j_end; ++j)
+        for (int kc = 0; kc < KCH; ++kc, ++it) {
+          const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
+          mbar_wait(&bar_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&bar_full[s], kChunk);
+          tma_load_2d(sB + s * kChunk, &tmB, &bar_full[s], kc * 64, j * kT);
+        }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kT, kT);
+      mbar_wait(&bar_a, 0);
+      tc_fence_after();
+      uint32_t it = 0;
+      for (int j = j_begin, n = 0; j < j_end; ++j, ++n) {
+        const uint32_t as = n & 1, aph = (n >> 1) & 1;
+        mbar_wait(&bar_tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t dcol = tmem + as * kT;
+        for (int kc = 0; kc < KCH; ++kc, ++it) {
+          const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
+          mbar_wait(&bar_full[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + kc * kChunk), b0 = smem_u32(sB + s * kChunk);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss(dcol, umma_desc_sw128(a0 + ks * 32, 16, 1024), umma_desc_sw128(b0 + ks * 32, 16, 1024), idesc,
+                    (kc | ks) != 0);
+          umma_commit(&bar_empty[s]);
+        }
+        umma_commit(&bar_tfull[as]);
+      }
+    }
+  } else {
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const int t = t0 + row;
+    const int y = (t < n_valid) ? labels[t] : -1;
+    float m = -1e30f, ssum = 0.f;  // m in log2 units
+    for (int j = j_begin, n = 0; j < j_end; ++j, ++n) {
+      const uint32_t as = n & 1, aph = (n >> 1) & 1;
+      mbar_wait(&bar_tfull[as], aph);
+      tc_fence_after();
+      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + as * kT + half * 64;
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t raw[32];
+        tmem_ld32(tbase + c, raw);
+        tmem_ld_wait();
+        const int col0 = j * kT + half * 64 + c;
+        float x[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) x[q] = __uint_as_float(raw[q]);
+        if (col0 + 32 > n_items) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (col0 + q >= n_items) x[q] = -INFINITY;
+        }
+        if (y >= col0 && y < col0 + 32) {
+          float z = 0.f;
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (q == y - col0) z = x[q];
+          zt[t] = z;
+        }
+        float cm = x[0];
+#pragma unroll
+        for (int q = 1; q < 32; ++q) cm = fmaxf(cm, x[q]);
+        const float mn = fmaxf(m, cm * kLog2e);
+        ssum *= ex2f(m - mn);
+        m = mn;
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) {
+          acc0 += ex2f(fmaf(x[q], kLog2e, -mn));
+          acc1 += ex2f(fmaf(x[q + 1], kLog2e, -mn));
+        }
+        ssum += acc0 + acc1;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[as]);
+    }
+    if (t < n_valid) part[((size_t)t * n_splits + split) * 2 + half] = make_float2(m, ssum);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// lse / loss / per-token exponent offsets.  Deterministic: per-block partial sums, last block adds them in order.
+__global__ void ce_finalize_kernel(const float2* __restrict__ part, const float* __restrict__ zt,
+                                   const int32_t* __restrict__ n_valid_ptr, int n_part, int capacity,
+                                   float* __restrict__ lse_out, float* __restrict__ cvec, float* __restrict__ block_sums,
+                                   unsigned int* __restrict__ ticket, float* __restrict__ loss_out) {
+  const int n_valid = *n_valid_ptr;
+  const float inv_n = n_valid > 0 ? 1.f / (float)n_valid : 0.f;
+  const float log2_inv_n = n_valid > 0 ? -log2f((float)n_valid) : 0.f;
+  float local = 0.f;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < capacity; t += gridDim.x * blockDim.x) {
+    if (t < n_valid) {
+      const float2* p = part + (size_t)t * n_part;
+      float M = -1e30f;
+      for (int i = 0; i < n_part; ++i) M = fmaxf(M, p[i].x);
+      float S = 0.f;
+      for (int i = 0; i < n_part; ++i) S += p[i].y * exp2f(p[i].x - M);
+      const float lse2 = M + log2f(S);  // log2 units
+      const float lse = lse2 * kLn2;
+      lse_out[t] = lse;
+      cvec[t] = -lse2 + log2_inv_n;
+      local += lse - zt[t];
+    } else {
+      cvec[t] = -INFINITY;  // rows beyond T_v contribute nothing to the backward
+    }
+  }
+  __shared__ float red[32];
+  __shared__ bool last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    block_sums[blockIdx.x] = s;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float s = 0.f;
+    for (int i = 0; i < (int)gridDim.x; ++i) s += reinterpret_cast<volatile float*>(block_sums)[i];
+    loss_out[0] = s * inv_n;  // mean over valid targets
+    loss_out[1] = inv_n;
+    *ticket = 0;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// backward (both directions share one kernel)
+//   COLCONST = false : rows = tokens (A = Hc tile), columns = items  -> acc = dHc tile [128, d]
+//   COLCONST = true  : rows = items  (A = E tile),  columns = tokens -> acc = dE tile  [128, d]
+// ----------------------------------------------------------------------------------------------------------------
+template <int KCH, int NSTAGE, bool COLCONST>
+__global__ void __launch_bounds__(kThreads, 1)
+ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const float* __restrict__ cvec /* [T] exponent offsets per token */, const int32_t* __restrict__ labels,
+              const __nv_bfloat16* __restrict__ table, const float* __restrict__ loss_inv /* [1] = 1/T_v */,
+              const int32_t* __restrict__ n_valid_ptr, int n_items, void* __restrict__ out) {
+  constexpr int D = KCH * 64;
+  constexpr int kStage = KCH * kChunk;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStage;
+  __shared__ __align__(16) float s_cc[NSTAGE][kT];
+  __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_sfull[2], bar_sfree[2], bar_pfull[2], bar_acc;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_valid = *n_valid_ptr;
+  const int r0 = blockIdx.x * kT;                           // first row (token or item) of this CTA
+  const int n_rows = COLCONST ? n_items : n_valid;
+  if (r0 >= n_rows) return;
+  const int n_cols = COLCONST ? n_valid : n_items;
+  const int n_ct = (n_cols + kT - 1) / kT;                  // column tiles
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_a, 1);
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_sfull[i], 1);
+      mbar_init(&bar_sfree[i], 1);
+      mbar_init(&bar_pfull[i], kEpiWarps);
+    }
+    mbar_init(&bar_acc, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem_acc = tmem + 256;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bar_a, kStage);
+      for (int kc = 0; kc < KCH; ++kc) tma_load_2d(sA + kc * kChunk, &tmA, &bar_a, kc * 64, r0);
+      for (int j = 0; j < n_ct; ++j) {
+        const uint32_t s = j % NSTAGE, ph = (j / NSTAGE) & 1;
+        mbar_wait(&bar_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&bar_full[s], kStage + (COLCONST ? kT * 4 : 0));
+        for (int kc = 0; kc < KCH; ++kc) tma_load_2d(sB + s * kStage + kc * kChunk, &tmB, &bar_full[s], kc * 64, j * kT);
+        if (COLCONST) {
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                  smem_u32(&s_cc[s][0])),
+              "l"(cvec + (size_t)j * kT), "r"(kT * 4), "r"(smem_u32(&bar_full[s]))
+              : "memory");
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(kT, kT);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(kT, D, false, true);
+      mbar_wait(&bar_a, 0);
+      tc_fence_after();
+      auto issue_mma1 = [&](int j) {
+        const uint32_t s = j % NSTAGE, ph = (j / NSTAGE) & 1;
+        mbar_wait(&bar_full[s], ph);
+        if (j >= 2) mbar_wait(&bar_sfree[j & 1], ((j >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t dcol = tmem + (j & 1) * kT;
+#pragma unroll
+        for (int kc = 0; kc < KCH; ++kc) {
+          const uint32_t a0 = smem_u32(sA + kc * kChunk), b0 = smem_u32(sB + s * kStage + kc * kChunk);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss(dcol, umma_desc_sw128(a0 + ks * 32, 16, 1024), umma_desc_sw128(b0 + ks * 32, 16, 1024), idesc1,
+                    (kc | ks) != 0);
+        }
+        umma_commit(&bar_sfull[j & 1]);
+      };
+      issue_mma1(0);
+      for (int j = 0; j < n_ct; ++j) {
+        if (j + 1 < n_ct) issue_mma1(j + 1);
+        const uint32_t s = j % NSTAGE;
+        mbar_wait(&bar_pfull[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t pcol = tmem + (j & 1) * kT;  // G (bf16 pairs) lives over S: k-steps 0-3 at +0, 4-7 at +64
+        const uint32_t b0 = smem_u32(sB + s * kStage);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_ts(tmem_acc, pcol + (ks >> 2) * 64 + (ks & 3) * 8, umma_desc_sw128(b0 + ks * 2048, kChunk, 1024), idesc2,
+                  (j | ks) != 0);
+        umma_commit(&bar_empty[s]);
+        umma_commit(&bar_sfree[j & 1]);
+      }
+      umma_commit(&bar_acc);
+    }
+  } else {
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    float crow = 0.f;
+    if (!COLCONST) crow = (r0 + row < n_valid) ? cvec[r0 + row] : -INFINITY;
+    for (int j = 0; j < n_ct; ++j) {
+      const uint32_t b = j & 1, s = j % NSTAGE;
+      if (COLCONST) mbar_wait(&bar_full[s], (j / NSTAGE) & 1);  // s_cc[s] was written by the async proxy
+      mbar_wait(&bar_sfull[b], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t sbase = tmem + lane_base + b * kT + half * 64;
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t raw[32];
+        tmem_ld32(sbase + c, raw);
+        tmem_ld_wait();
+        uint32_t pk[16];
+        if (COLCONST) {
+          const float4* cc = reinterpret_cast<const float4*>(&s_cc[s][half * 64 + c]);
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            const float4 o = cc[q >> 2];
+            const float g0 = ex2f(fmaf(__uint_as_float(raw[q + 0]), kLog2e, o.x));
+            const float g1 = ex2f(fmaf(__uint_as_float(raw[q + 1]), kLog2e, o.y));
+            const float g2 = ex2f(fmaf(__uint_as_float(raw[q + 2]), kLog2e, o.z));
+            const float g3 = ex2f(fmaf(__uint_as_float(raw[q + 3]), kLog2e, o.w));
+            pk[(q >> 1) + 0] = pack_bf16(g0, g1);
+            pk[(q >> 1) + 1] = pack_bf16(g2, g3);
+          }
+        } else {
+          const int col0 = j * kT + half * 64 + c;
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) {
+            float g0 = ex2f(fmaf(__uint_as_float(raw[q + 0]), kLog2e, crow));
+            float g1 = ex2f(fmaf(__uint_as_float(raw[q + 1]), kLog2e, crow));
+            if (col0 + 32 > n_items) {  // columns beyond the catalog do not exist
+              if (col0 + q >= n_items) g0 = 0.f;
+              if (col0 + q + 1 >= n_items) g1 = 0.f;
+            }
+            pk[q >> 1] = pack_bf16(g0, g1);
+          }
+        }
+        // in place over the already-consumed S columns of this warp: chunk c -> columns [c/2, c/2+16)
+        tmem_st16(sbase + (c >> 1), pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_pfull[b]);
+    }
+    // ---- final: accumulator -> global
+    mbar_wait(&bar_acc, 0);
+    tc_fence_after();
+    const int r = r0 + row;
+    constexpr int HALF_D = D / 2;
+    const uint32_t abase = tmem_acc + lane_base + half * HALF_D;
+    if (COLCONST) {
+      float* o = reinterpret_cast<float*>(out);
+#pragma unroll 1
+      for (int c = 0; c < HALF_D; c += 32) {
+        uint32_t raw[32];
+        tmem_ld32(abase + c, raw);
+        tmem_ld_wait();
+        if (r < n_items) {
+          float4* dst = reinterpret_cast<float4*>(o + (size_t)r * D + half * HALF_D + c);
+#pragma unroll
+          for (int q = 0; q < 32; q += 4)
+            dst[q >> 2] = make_float4(__uint_as_float(raw[q]), __uint_as_float(raw[q + 1]), __uint_as_float(raw[q + 2]),
+                                      __uint_as_float(raw[q + 3]));
+        }
+      }
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+      const float inv_n = loss_inv[0];
+      const int y = (r < n_valid) ? labels[r] : 0;
+#pragma unroll 1
+      for (int c = 0; c < HALF_D; c += 32) {
+        uint32_t raw[32];
+        tmem_ld32(abase + c, raw);
+        tmem_ld_wait();
+        if (r < n_valid) {
+          const uint4* ey = reinterpret_cast<const uint4*>(table + (size_t)y * D + half * HALF_D + c);
+          uint4* dst = reinterpret_cast<uint4*>(o + (size_t)r * D + half * HALF_D + c);
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) {
+            const uint4 e = ey[q >> 3];
+            const __nv_bfloat162* e2 = reinterpret_cast<const __nv_bfloat162*>(&e);
+            uint4 w;
+            uint32_t* w32 = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              const float2 ef = __bfloat1622float2(e2[p]);
+              w32[p] = pack_bf16(__uint_as_float(raw[q + 2 * p]) - inv_n * ef.x,
+                                 __uint_as_float(raw[q + 2 * p + 1]) - inv_n * ef.y);
+            }
+            dst[q >> 3] = w;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// dE[y_t, :] -= Hc[t, :] / T_v   (fp32 atomics; several tokens may share a label)
+__global__ void ce_label_scatter_kernel(const __nv_bfloat16* __restrict__ hc, const int32_t* __restrict__ labels,
+                                        const float* __restrict__ loss_inv, const int32_t* __restrict__ n_valid_ptr,
+                                        int d, float* __restrict__ dE) {
+  const int n_valid = *n_valid_ptr;
+  const float inv_n = loss_inv[0];
+  const int per_row = d / 2;
+  const long long total = (long long)n_valid * per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / per_row), c = (int)(i % per_row) * 2;
+    const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hc + (size_t)t * d + c));
+    float* dst = dE + (size_t)labels[t] * d + c;
+    atomicAdd(dst, -inv_n * h.x);
+    atomicAdd(dst + 1, -inv_n * h.y);
+  }
+}
+
+static int pick_splits(int n_row_tiles, int n_col_tiles) {
+  const int sms = sm_count();
+  int best = 1;
+  double best_eff = 0.0;
+  for (int p = 1; p <= 8 && p <= n_col_tiles; ++p) {
+    const long long ctas = (long long)n_row_tiles * p;
+    const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best = p;
+    }
+  }
+  return best;
+}
+
+}  // namespace rp
+
+using namespace rp;
+
+// workspace layout for the CE head: [part float2 T*P*2][zt T][block_sums 256][ticket]
+RP_API size_t rp_ce_head_workspace(int capacity_tokens, int n_items, int d) {
+  (void)d;
+  if (capacity_tokens <= 0 || n_items <= 0) return 0;
+  const int P = 8;
+  return (size_t)capacity_tokens * P * 2 * sizeof(float2) + (size_t)capacity_tokens * 4 + 1024 + 256;
+}
+
+template <int KCH, int NSTAGE>
+static int launch_ce_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const int32_t* labels, const int32_t* n_valid,
+                         int n_items, int n_splits, int n_tok_tiles, float2* part, float* zt, cudaStream_t stream) {
+  const int smem = (KCH + NSTAGE) * kChunk + 1024;
+  auto kern = ce_fwd_kernel<KCH, NSTAGE>;
+  RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<n_tok_tiles * n_splits, kThreads, smem, stream>>>(tmA, tmB, labels, n_valid, n_items, n_splits, part, zt);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+// hc bf16 [capacity, d] (rows >= *n_valid ignored), table bf16 [n_items, d], labels int32 [capacity],
+// n_valid int32 [1] (device).  Outputs: loss_out fp32 [2] = {mean CE, 1/T_v}; lse fp32 [capacity];
+// cvec fp32 [capacity] (exponent offsets consumed by rp_ce_head_bwd).
+RP_API int rp_ce_head_fwd(const void* hc, const void* table, const int32_t* labels, const int32_t* n_valid,
+                          int capacity, int n_items, int d, float* loss_out, float* lse, float* cvec, void* workspace,
+                          size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!hc || !table || !labels || !n_valid || !loss_out || !lse || !cvec || !workspace) return RP_EINVAL;
+  if (capacity <= 0 || n_items <= 0) return RP_ESHAPE;
+  if (d != 64 && d != 128 && d != 256 && d != 512) return RP_ESHAPE;
+  if (workspace_bytes < rp_ce_head_workspace(capacity, n_items, d)) return RP_EWORKSPACE;
+  const int n_tok_tiles = (capacity + kT - 1) / kT, n_item_tiles = (n_items + kT - 1) / kT;
+  const int P = pick_splits(n_tok_tiles, n_item_tiles);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float2* part = reinterpret_cast<float2*>(ws);
+  float* zt = reinterpret_cast<float*>(ws + (size_t)capacity * 8 * 2 * sizeof(float2));
+  float* block_sums = zt + capacity;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(block_sums + 256);
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap_bf16(&tmA, hc, capacity, d, d, 128)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmB, table, n_items, d, d, 128)) != RP_OK) return rc;
+  switch (d) {
+    case 64: rc = launch_ce_fwd<1, 8>(tmA, tmB, labels, n_valid, n_items, P, n_tok_tiles, part, zt, stream); break;
+    case 128: rc = launch_ce_fwd<2, 8>(tmA, tmB, labels, n_valid, n_items, P, n_tok_tiles, part, zt, stream); break;
+    case 256: rc = launch_ce_fwd<4, 8>(tmA, tmB, labels, n_valid, n_items, P, n_tok_tiles, part, zt, stream); break;
+    default: rc = launch_ce_fwd<8, 5>(tmA, tmB, labels, n_valid, n_items, P, n_tok_tiles, part, zt, stream); break;
+  }
+  if (rc != RP_OK) return rc;
+  RP_CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, stream));
+  int blocks = (capacity + 255) / 256;
+  if (blocks > 256) blocks = 256;
+  ce_finalize_kernel<<<blocks, 256, 0, stream>>>(part, zt, n_valid, P * 2, capacity, lse, cvec, block_sums, ticket,
+                                                 loss_out);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+template <int KCH, int NSTAGE, bool COLCONST>
+static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* cvec, const int32_t* labels,
+                         const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, void* out,
+                         int grid, cudaStream_t stream) {
+  const int smem = (1 + NSTAGE) * KCH * kChunk + 1024;
+  auto kern = ce_bwd_kernel<KCH, NSTAGE, COLCONST>;
+  RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, cvec, labels, reinterpret_cast<const __nv_bfloat16*>(table), loss_inv,
+                                         n_valid, n_items, out);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+// Backward of rp_ce_head_fwd w.r.t. its two inputs, for d(loss) = 1:
+//   d_hc   bf16 [capacity, d]  (rows < *n_valid written)
+//   d_table fp32 [n_items, d]  OVERWRITTEN with softmax^T . hc / T_v, then the one-hot part is atomically subtracted.
+// d in {64,128,256}.
+RP_API int rp_ce_head_bwd(const void* hc, const void* table, const int32_t* labels, const int32_t* n_valid,
+                          int capacity, int n_items, int d, const float* loss_out /* from fwd */,
+                          const float* cvec /* from fwd */, void* d_hc, float* d_table, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!hc || !table || !labels || !n_valid || !loss_out || !cvec || !d_hc || !d_table) return RP_EINVAL;
+  if (capacity <= 0 || n_items <= 0) return RP_ESHAPE;
+  if (d != 64 && d != 128 && d != 256) return RP_ESHAPE;
+  CUtensorMap tmH, tmE;
+  int rc;
+  if ((rc = make_tmap_bf16(&tmH, hc, capacity, d, d, 128)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmE, table, n_items, d, d, 128)) != RP_OK) return rc;
+  const int n_tok_tiles = (capacity + kT - 1) / kT, n_item_tiles = (n_items + kT - 1) / kT;
+  const float* loss_inv = loss_out + 1;
+  switch (d) {
+    case 64:
+      rc = launch_ce_bwd<1, 6, false>(tmH, tmE, cvec, labels, table, loss_inv, n_valid, n_items, d_hc, n_tok_tiles, stream);
+      if (rc == RP_OK)
+        rc = launch_ce_bwd<1, 6, true>(tmE, tmH, cvec, labels, table, loss_inv, n_valid, n_items, d_table, n_item_tiles, stream);
+      break;
+    case 128:
+      rc = launch_ce_bwd<2, 4, false>(tmH, tmE, cvec, labels, table, loss_inv, n_valid, n_items, d_hc, n_tok_tiles, stream);
+      if (rc == RP_OK)
+        rc = launch_ce_bwd<2, 4, true>(tmE, tmH, cvec, labels, table, loss_inv, n_valid, n_items, d_table, n_item_tiles, stream);
+      break;
+    default:
+      rc = launch_ce_bwd<4, 2, false>(tmH, tmE, cvec, labels, table, loss_inv, n_valid, n_items, d_hc, n_tok_tiles, stream);
+      if (rc == RP_OK)
+        rc = launch_ce_bwd<4, 2, true>(tmE, tmH, cvec, labels, table, loss_inv, n_valid, n_items, d_table, n_item_tiles, stream);
+      break;
+  }
+  if (rc != RP_OK) return rc;
+  ce_label_scatter_kernel<<<sm_count() * 4, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hc), labels, loss_inv,
+                                                               n_valid, d, d_table);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}

@@ -60,3 +60,38 @@ def score_topk(hq: torch.Tensor, table: torch.Tensor, k: int, seen_sorted: torch
     check(L.rp_score_topk(_ptr(hq), _ptr(table), _ptr(bias), _ptr(seen_sorted), S, B, n_items, d, k, _ptr(candidates),
                           _ptr(ids), _ptr(scores), _ptr(ws), ws_bytes, _stream()), "rp_score_topk")
     return ids, scores
+
+
+class CEHeadState:
+    """Buffers shared by rp_ce_head_fwd / rp_ce_head_bwd for one (capacity, n_items, d)."""
+
+    def __init__(self, capacity: int, n_items: int, d: int, device):
+        L = lib()
+        self.capacity, self.n_items, self.d = capacity, n_items, d
+        self.ws_bytes = L.rp_ce_head_workspace(capacity, n_items, d)
+        self.ws = torch.zeros(self.ws_bytes, device=device, dtype=torch.uint8)
+        self.loss = torch.zeros(2, device=device, dtype=torch.float32)
+        self.lse = torch.zeros(capacity, device=device, dtype=torch.float32)
+        cap128 = (capacity + 127) // 128 * 128
+        self.cvec = torch.full((cap128,), float("-inf"), device=device, dtype=torch.float32)
+
+
+def ce_head_fwd(st: CEHeadState, hc, table, labels, n_valid):
+    """hc bf16 [capacity,d] (zero/finite beyond n_valid), table bf16 [I,d], labels int32 [capacity], n_valid int32 [1].
+    Returns st.loss (fp32 [2]: mean CE, 1/n_valid) - a view that the next call overwrites."""
+    _need(hc, torch.bfloat16, "hc")
+    _need(table, torch.bfloat16, "table")
+    _need(labels, torch.int32, "labels")
+    _need(n_valid, torch.int32, "n_valid")
+    check(lib().rp_ce_head_fwd(_ptr(hc), _ptr(table), _ptr(labels), _ptr(n_valid), st.capacity, st.n_items, st.d,
+                               _ptr(st.loss), _ptr(st.lse), _ptr(st.cvec), _ptr(st.ws), st.ws_bytes, _stream()),
+          "rp_ce_head_fwd")
+    return st.loss
+
+
+def ce_head_bwd(st: CEHeadState, hc, table, labels, n_valid, d_hc, d_table):
+    """d_hc bf16 [capacity,d], d_table fp32 [>=I, d] (rows < I overwritten)."""
+    _need(d_hc, torch.bfloat16, "d_hc")
+    _need(d_table, torch.float32, "d_table")
+    check(lib().rp_ce_head_bwd(_ptr(hc), _ptr(table), _ptr(labels), _ptr(n_valid), st.capacity, st.n_items, st.d,
+                               _ptr(st.loss), _ptr(st.cvec), _ptr(d_hc), _ptr(d_table), _stream()), "rp_ce_head_bwd")

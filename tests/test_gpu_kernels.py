@@ -85,3 +85,42 @@ def test_score_topk_golden_reference(ops, golden_dir):
     ref_ids = torch.from_numpy(z["topk_ids"])
     overlap = np.mean([len(set(a.tolist()) & set(b.tolist())) / 10 for a, b in zip(ids.cpu(), ref_ids)])
     assert overlap > 0.9
+
+
+@pytest.mark.parametrize("T,n_valid,I,d", [(256, 256, 1000, 64), (300, 217, 5000, 128), (1024, 1000, 20001, 128),
+                                           (384, 300, 3000, 256)])
+def test_ce_head_fwd_bwd_matches_oracle(ops, T, n_valid, I, d):
+    """Fused CE head vs the oracle's logsumexp CE (nn/loss/ce.py:49-81) and its autograd gradients."""
+    g = torch.Generator().manual_seed(T + I)
+    hc = (torch.randn(T, d, generator=g) * 1.0).to(torch.bfloat16)
+    hc[n_valid:] = 0
+    table = (torch.randn(I, d, generator=g) * 0.3).to(torch.bfloat16)
+    labels = torch.randint(0, I, (T,), generator=g, dtype=torch.int64)
+    # oracle in fp64 on the same bf16-rounded inputs
+    h64 = hc[:n_valid].double().requires_grad_(True)
+    e64 = table.double().requires_grad_(True)
+    logits = h64 @ e64.T
+    lse = torch.logsumexp(logits, -1)
+    loss = (lse - logits.gather(1, labels[:n_valid, None])[:, 0]).mean()
+    loss.backward()
+
+    st = ops.CEHeadState(T, I, d, "cuda")
+    nv = torch.tensor([n_valid], dtype=torch.int32, device="cuda")
+    out = ops.ce_head_fwd(st, hc.cuda(), table.cuda(), labels.int().cuda(), nv)
+    torch.cuda.synchronize()
+    assert abs(out[0].item() - loss.item()) < 2e-4 * max(1.0, abs(loss.item())), (out[0].item(), loss.item())
+    assert abs(out[1].item() - 1.0 / n_valid) < 1e-9
+    torch.testing.assert_close(st.lse[:n_valid].cpu().double(), lse.detach(), rtol=1e-5, atol=1e-4)
+
+    d_hc = torch.zeros(T, d, device="cuda", dtype=torch.bfloat16)
+    d_tab = torch.full((I + 1, d), 7.0, device="cuda", dtype=torch.float32)  # must be overwritten, pad row untouched
+    ops.ce_head_bwd(st, hc.cuda(), table.cuda(), labels.int().cuda(), nv, d_hc, d_tab)
+    torch.cuda.synchronize()
+    gh, ge = h64.grad, e64.grad
+    # softmax probabilities travel through bf16 (8 bit mantissa): compare with a norm-relative tolerance
+    eh = (d_hc[:n_valid].cpu().double() - gh).norm() / gh.norm()
+    ee = (d_tab[:I].cpu().double() - ge).norm() / ge.norm()
+    assert eh < 1e-2, f"dH rel err {eh}"
+    assert ee < 1e-2, f"dE rel err {ee}"
+    assert (d_tab[I] == 7.0).all()
+    assert (d_hc[n_valid:] == 0).all()

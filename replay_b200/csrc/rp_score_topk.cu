@@ -22,21 +22,23 @@ static constexpr int kTileN = 128;   // items per MMA tile
 static constexpr int kChunkBytes = 128 * 128;  // [128 rows x 64 bf16]
 static constexpr int kNoId = 0x7fffffff;
 
+// Per-thread running top-K kept in registers.  The K live entries occupy slots [KMAX-K, KMAX) in descending order so
+// that the admission threshold is always the statically indexed last slot; slots below hold +inf sentinels that never
+// move.  (A runtime-indexed v[K-1] would push the whole structure into local memory.)
 template <int KMAX>
 struct TopK {
   float v[KMAX];
   int id[KMAX];
-  float thr;
-  __device__ __forceinline__ void init() {
+  __device__ __forceinline__ void init(int K) {
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
-      v[i] = -INFINITY;
+      v[i] = (i < KMAX - K) ? INFINITY : -INFINITY;
       id[i] = kNoId;
     }
-    thr = -INFINITY;
   }
-  // sorted insert (descending, earlier insert wins ties because ids arrive in ascending order)
-  __device__ __forceinline__ void insert(float x, int xi, int K) {
+  __device__ __forceinline__ float thr() const { return v[KMAX - 1]; }
+  // sorted insert (descending, earlier insert wins ties because columns arrive in ascending order)
+  __device__ __forceinline__ void insert(float x, int xi) {
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
       const bool gt = x > v[i];
@@ -47,14 +49,14 @@ struct TopK {
       x = tv;
       xi = ti;
     }
-#pragma unroll
-    for (int i = 0; i < KMAX; ++i)
-      if (i == K - 1) thr = v[i];
   }
 };
 
+static constexpr int kEpiWarps = 8;
+static constexpr int kThreads = 64 + kEpiWarps * 32;
+
 template <int KCH /* d / 64 */, int NSTAGE, int KMAX>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const int32_t* __restrict__ seen_sorted, int S, int n_users, int n_items, int K, int n_splits,
                   float* __restrict__ part_vals, int32_t* __restrict__ part_ids) {
@@ -64,6 +66,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* sB = smem + KCH * kChunkBytes;      // NSTAGE chunks of 16 KB
   __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_scratch[32 * kEpiWarps * 32];  // [q][epilogue thread]: chunk values for the rare insert path
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int user_tile = blockIdx.x / n_splits, split = blockIdx.x % n_splits;
@@ -80,7 +83,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_tfull[i], 1);
-      mbar_init(&bar_tempty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&bar_tempty[i], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
@@ -134,41 +137,48 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------ epilogue: 4 warps, warp%4 = TMEM lane quarter
-    const int quarter = warp & 3;
+    // ------------------------------------------------ epilogue: 8 warps; warp%4 = TMEM lane quarter, (warp-2)/4 = column half
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
     const int row = quarter * 32 + lane;
     const int u = u0 + row;
     const bool live = u < n_users;
+    float* sc = s_scratch + ew * 32 + lane;  // element q of this thread at sc[q * (kEpiWarps*32)]
     TopK<KMAX> top;
-    top.init();
+    top.init(K);
     // cursor into this user's sorted seen list (ascending, kNoId = padding)
     const int32_t* sp = seen_sorted ? seen_sorted + (size_t)(live ? u : 0) * S : nullptr;
     int ci = 0;
     int next_seen = kNoId;
-    if (sp && live) {
-      const int first_col = t_begin * kTileN;
-      int lo = 0, hi = S;  // lower_bound(first_col)
+    auto seek = [&](int first_col) {  // lower_bound(first_col) from the current cursor
+      int lo = ci, hi = S;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (sp[mid] < first_col) lo = mid + 1; else hi = mid;
       }
       ci = lo;
       next_seen = ci < S ? sp[ci] : kNoId;
-    }
+    };
+    if (sp && live) next_seen = sp[0];
     for (int t = t_begin, j = 0; t < t_end; ++t, ++j) {
       const uint32_t as = j & 1, aph = (j >> 1) & 1;
       mbar_wait(&bar_tfull[as], aph);
       tc_fence_after();
-      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + as * kTileN;
-#pragma unroll 1
-      for (int c = 0; c < kTileN; c += 32) {
-        uint32_t raw[32];
-        tmem_ld32(tbase + c, raw);
-        tmem_ld_wait();
-        const int col0 = t * kTileN + c;
+      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + as * kTileN + half * 64;
+      uint32_t raw0[32], raw1[32];
+      tmem_ld32(tbase, raw0);
+      tmem_ld32(tbase + 32, raw1);
+      tmem_ld_wait();
+      // the accumulator stage can be reused as soon as its values sit in registers
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[as]);
+      if (sp && live && next_seen < t * kTileN + half * 64) seek(t * kTileN + half * 64);  // skip the other half's columns
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        const int col0 = t * kTileN + half * 64 + c;
         float x[32];
 #pragma unroll
-        for (int q = 0; q < 32; ++q) x[q] = __uint_as_float(raw[q]);
+        for (int q = 0; q < 32; ++q) x[q] = __uint_as_float(c == 0 ? raw0[q] : raw1[q]);
         if (col0 + 32 > n_items) {  // ragged last tile: columns beyond the catalog do not exist
 #pragma unroll
           for (int q = 0; q < 32; ++q)
@@ -184,25 +194,26 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         bool any = false;
 #pragma unroll
-        for (int q = 0; q < 32; ++q) any |= (x[q] > top.thr);
-        if (any) {
+        for (int q = 0; q < 32; ++q) any |= (x[q] > top.thr());
+        if (any) {  // rare after warm-up: stage the chunk in smem and walk it with ONE insert site (small code)
 #pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if (x[q] > top.thr) top.insert(x[q], col0 + q, K);
+          for (int q = 0; q < 32; ++q) sc[q * (kEpiWarps * 32)] = x[q];
+#pragma unroll 1
+          for (int q = 0; q < 32; ++q) {
+            const float val = sc[q * (kEpiWarps * 32)];
+            if (val > top.thr()) top.insert(val, col0 + q);
+          }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_tempty[as]);
     }
     if (live) {
-      float* pv = part_vals + ((size_t)u * n_splits + split) * K;
-      int32_t* pi = part_ids + ((size_t)u * n_splits + split) * K;
+      float* pv = part_vals + (((size_t)u * n_splits + split) * 2 + half) * K;
+      int32_t* pi = part_ids + (((size_t)u * n_splits + split) * 2 + half) * K;
 #pragma unroll
       for (int i = 0; i < KMAX; ++i)
-        if (i < K) {
-          pv[i] = top.v[i];
-          pi[i] = top.id[i];
+        if (i >= KMAX - K) {
+          pv[i - (KMAX - K)] = top.v[i];
+          pi[i - (KMAX - K)] = top.id[i];
         }
     }
   }
@@ -339,11 +350,11 @@ static int launch_score_topk(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   if (K <= 16) {
     auto kern = score_topk_kernel<KCH, NSTAGE, 16>;
     RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 192, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, pv, pi);
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, pv, pi);
   } else {
     auto kern = score_topk_kernel<KCH, NSTAGE, 32>;
     RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 192, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, pv, pi);
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, pv, pi);
   }
   RP_LAUNCH_CHECK();
   return RP_OK;
@@ -356,7 +367,7 @@ RP_API size_t rp_score_topk_workspace(int n_users, int n_items, int d, int K) {
   if (n_users <= 0 || n_items <= 0 || K <= 0) return 0;
   const int ut = (n_users + rp::kTileM - 1) / rp::kTileM, it = (n_items + rp::kTileN - 1) / rp::kTileN;
   const int p = rp::choose_splits(ut, it);
-  return (size_t)n_users * p * K * 8 + 256;
+  return (size_t)n_users * p * 2 * K * 8 + 256;
 }
 
 RP_API int rp_seen_prepare(const int64_t* seen_ids, int n_users, int S, int item_count, const int32_t* inv_map,
@@ -387,7 +398,7 @@ RP_API int rp_score_topk(const void* hq, const void* table, const float* bias, c
   const int ut = (n_users + kTileM - 1) / kTileM, it = (n_items + kTileN - 1) / kTileN;
   const int p = choose_splits(ut, it);
   float* pv = reinterpret_cast<float*>(workspace);
-  int32_t* pi = reinterpret_cast<int32_t*>(pv + (size_t)n_users * p * K);
+  int32_t* pi = reinterpret_cast<int32_t*>(pv + (size_t)n_users * p * 2 * K);
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = make_tmap_bf16(&tmA, hq, n_users, d, d, 128)) != RP_OK) return rc;
@@ -395,13 +406,13 @@ RP_API int rp_score_topk(const void* hq, const void* table, const float* bias, c
   switch (d) {
     case 64: rc = launch_score_topk<1, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, pv, pi, stream); break;
     case 128: rc = launch_score_topk<2, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, pv, pi, stream); break;
-    case 256: rc = launch_score_topk<4, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, pv, pi, stream); break;
-    default: rc = launch_score_topk<8, 5>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, pv, pi, stream); break;
+    case 256: rc = launch_score_topk<4, 6>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, pv, pi, stream); break;
+    default: rc = launch_score_topk<8, 3>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, pv, pi, stream); break;
   }
   if (rc != RP_OK) return rc;
   const int threads = 128;
   const int blocks = (n_users * 32 + threads - 1) / threads;
-  topk_merge_kernel<<<blocks, threads, 0, stream>>>(pv, pi, seen_sorted, S, n_users, n_items, K, p, candidates, out_ids,
+  topk_merge_kernel<<<blocks, threads, 0, stream>>>(pv, pi, seen_sorted, S, n_users, n_items, K, p * 2, candidates, out_ids,
                                                     out_scores);
   RP_LAUNCH_CHECK();
   return RP_OK;

@@ -73,7 +73,7 @@ def sd_np(module):
     return {"sd::" + k: v.detach().cpu().numpy().copy() for k, v in module.state_dict().items()}
 
 
-def gen_new_sasrec(tag, B, L, d, H, n_items, n_blocks, seed):
+def gen_new_sasrec(tag, B, L, d, H, n_items, n_blocks, seed, with_adam=True):
     g = torch.Generator().manual_seed(seed)
     torch.manual_seed(seed)
     pad = n_items
@@ -97,8 +97,9 @@ def gen_new_sasrec(tag, B, L, d, H, n_items, n_blocks, seed):
     # --- one Adam step with the reference's optimizer settings (optimizer_factory.py:56-63)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.98))
     opt.step()
-    for k, p in model.named_parameters():
-        out["adam1::" + k] = p.detach().numpy().copy()
+    if with_adam:
+        for k, p in model.named_parameters():
+            out["adam1::" + k] = p.detach().numpy().copy()
     # restore weights for the eval leg
     model.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in out.items() if k.startswith("sd::")})
     model.eval()
@@ -209,9 +210,10 @@ def gen_seen_filter_known_answers():
 
 
 if __name__ == "__main__":
-    gen_new_sasrec("tiny", B=6, L=16, d=32, H=2, n_items=300, n_blocks=2, seed=11)
-    gen_new_sasrec("small", B=8, L=50, d=64, H=2, n_items=1000, n_blocks=2, seed=12)
-    gen_legacy_sasrec("tiny", B=6, L=16, d=32, H=2, n_items=300, n_blocks=2, seed=13)
-    gen_bert4rec("tiny", B=6, L=16, d=32, H=2, n_items=300, n_blocks=2, seed=14, tying=False)
-    gen_bert4rec("tiny_tied", B=6, L=16, d=32, H=2, n_items=300, n_blocks=2, seed=15, tying=True)
+    # shapes respect the CUDA path's tile constraints: hidden in {64,128,256,512}, head_dim in {64,128}
+    gen_new_sasrec("tiny", B=6, L=16, d=64, H=1, n_items=300, n_blocks=2, seed=11)
+    gen_new_sasrec("small", B=8, L=50, d=128, H=2, n_items=600, n_blocks=2, seed=12, with_adam=False)
+    gen_legacy_sasrec("tiny", B=6, L=16, d=64, H=1, n_items=300, n_blocks=2, seed=13)
+    gen_bert4rec("tiny", B=6, L=16, d=64, H=1, n_items=300, n_blocks=2, seed=14, tying=False)
+    gen_bert4rec("tiny_tied", B=6, L=16, d=64, H=1, n_items=300, n_blocks=2, seed=15, tying=True)
     gen_seen_filter_known_answers()

@@ -54,13 +54,61 @@ def lib():
     _sig(L.rp_ce_head_workspace, c_size_t, [c_int, c_int, c_int])
     _sig(L.rp_ce_head_fwd, c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, c_size_t, P])
     _sig(L.rp_ce_head_bwd, c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P])
+    U64, LL = ctypes.c_ulonglong, ctypes.c_longlong
+    _sig(L.rp_gemm, c_int, [ctypes.POINTER(GemmDesc), P])
+    _sig(L.rp_attn_fwd, c_int, [ctypes.POINTER(AttnDesc), P])
+    _sig(L.rp_attn_softmax_bwd, c_int, [P, P, P, c_int, c_int, c_float, c_float, U64, U64, P, P])
+    _sig(L.rp_prepare_batch, c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P])
+    _sig(L.rp_embed_fwd, c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_float, U64, U64, P, P, P])
+    _sig(L.rp_embed_bwd, c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_float, U64, U64, P, P, P, P])
+    _sig(L.rp_layernorm_fwd, c_int, [P, P, P, c_float, c_int, c_int, P, P, P, P, P, P])
+    _sig(L.rp_layernorm_bwd, c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P])
+    _sig(L.rp_dropout_bwd, c_int, [P, P, LL, c_int, P, c_float, U64, U64, P, P])
+    _sig(L.rp_colsum, c_int, [P, c_int, c_int, LL, P, P])
+    _sig(L.rp_adam_step, c_int, [P, P, P, P, P, LL, P, P, c_float, c_float, c_float, c_float, P, c_int, P])
+    _sig(L.rp_cast_bf16, c_int, [P, P, LL, P])
+    _sig(L.rp_counter_add, c_int, [P, U64, P])
     for name, restype, argtypes in _EXTRA_SIGS:
         _sig(getattr(L, name), restype, argtypes)
     _lib = L
     return L
 
 
-# filled in by replay_b200.ops as kernels are added (keeps one place per kernel family)
+class GemmDesc(ctypes.Structure):
+    """Mirror of ``struct rp_gemm_desc`` (include/rp_b200.h)."""
+
+    _fields_ = [
+        ("A", c_void_p), ("a_rows", ctypes.c_longlong), ("a_cols", ctypes.c_longlong), ("lda", ctypes.c_longlong), ("a_mn", c_int),
+        ("B", c_void_p), ("b_rows", ctypes.c_longlong), ("b_cols", ctypes.c_longlong), ("ldb", ctypes.c_longlong), ("b_mn", c_int),
+        ("M", c_int), ("N", c_int), ("K", c_int), ("batch", c_int), ("inner", c_int),
+        ("a_r0", c_int), ("a_ro", c_int), ("a_ri", c_int), ("a_c0", c_int), ("a_co", c_int), ("a_ci", c_int),
+        ("b_r0", c_int), ("b_ro", c_int), ("b_ri", c_int), ("b_c0", c_int), ("b_co", c_int), ("b_ci", c_int),
+        ("C", c_void_p), ("ldc", ctypes.c_longlong), ("c_off0", ctypes.c_longlong), ("c_oo", ctypes.c_longlong),
+        ("c_oi", ctypes.c_longlong), ("out_mode", c_int),
+        ("alpha", c_float), ("bias", c_void_p), ("act", c_int),
+        ("residual", c_void_p), ("rowmask", c_void_p), ("rowmask_off0", ctypes.c_longlong), ("rowmask_oo", ctypes.c_longlong),
+        ("drop_p", c_float), ("seed", ctypes.c_ulonglong), ("drop_offset", ctypes.c_ulonglong), ("seed_ptr", c_void_p),
+        ("split_k", c_int),
+        ("gate", c_void_p), ("gate_scale", c_float),
+    ]
+
+
+class AttnDesc(ctypes.Structure):
+    """Mirror of ``struct rp_attn_desc`` (include/rp_b200.h)."""
+
+    _fields_ = [
+        ("q", c_void_p), ("q_rows", ctypes.c_longlong), ("q_cols", ctypes.c_longlong), ("ldq", ctypes.c_longlong), ("q_c0", c_int),
+        ("k", c_void_p), ("k_rows", ctypes.c_longlong), ("k_cols", ctypes.c_longlong), ("ldk", ctypes.c_longlong), ("k_c0", c_int),
+        ("v", c_void_p), ("v_rows", ctypes.c_longlong), ("v_cols", ctypes.c_longlong), ("ldv", ctypes.c_longlong), ("v_c0", c_int),
+        ("B", c_int), ("H", c_int), ("L", c_int), ("head_dim", c_int),
+        ("causal", c_int), ("mask_pad_keys", c_int),
+        ("pad_mask", c_void_p),
+        ("out", c_void_p), ("ldo", c_int),
+        ("p_save", c_void_p), ("inv_sum", c_void_p),
+        ("drop_p", c_float), ("seed", ctypes.c_ulonglong), ("drop_off", ctypes.c_ulonglong), ("seed_ptr", c_void_p),
+    ]
+
+
 _EXTRA_SIGS: list = []
 
-__all__ = ["lib", "check", "RpError", "LIB_PATH", "c_float", "c_int", "c_int32", "c_int64", "c_size_t", "c_void_p"]
+__all__ = ["GemmDesc", "AttnDesc", "lib", "check", "RpError", "LIB_PATH", "c_float", "c_int", "c_int32", "c_int64", "c_size_t", "c_void_p"]

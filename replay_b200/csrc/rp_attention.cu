@@ -1,0 +1,334 @@
+// rp_attention.cu - padded-sequence multi-head attention for L <= 256 (SASRec causal + key-padding, BERT4Rec key-padding):
+// fused forward on tcgen05 (S = Q.K^T in TMEM -> masked softmax in registers -> P bf16 back into TMEM -> O = P.V),
+// and the row-wise softmax backward that sits between the batched backward GEMMs (rp_gemm).
+//
+// Replaces torch.nn.MultiheadAttention's scaled-dot-product core as configured by the reference:
+//   replay/nn/sequential/sasrec/transformer.py:36-46,99-106 + replay/nn/mask.py:18-51 (float [B*H,L,L] mask never built)
+//   replay/models/nn/sequential/sasrec/model.py:407-414,435 (bool causal mask, pad keys NOT masked)
+//   replay/models/nn/sequential/bert4rec/model.py:471,494 (key_padding_mask only)
+// Fully masked query rows produce a zero output (torch >= 2.5 safe-softmax semantics of the training path).
+#include "rp_host.h"
+#include "rp_philox.cuh"
+#include "rp_sm100.cuh"
+
+namespace rp {
+
+struct AttnParams {
+  int B, H, L, Lp;             // Lp = round_up(L, 64): row pitch / row count of the saved probability buffers
+  int causal, mask_pad_keys;
+  float scale;                 // 1/sqrt(head_dim)
+  const uint8_t* pad_mask;     // [B*L] 1 = real token
+  __nv_bfloat16* out;          // [B*L, ldo] ; head h writes columns [h*HD, (h+1)*HD)
+  int ldo;
+  __nv_bfloat16* p_save;       // [B*H, Lp, Lp] unnormalised exp(s - max) (bf16) or null
+  float* inv_sum;              // [B*H, Lp] 1 / row sum (0 for fully masked rows)
+  int q_c0, k_c0, v_c0;        // column offsets of head 0 inside the Q / K / V 2-D arrays
+  float drop_p;
+  unsigned long long seed, drop_off;
+  const unsigned long long* seed_ptr;
+};
+
+static constexpr float kLog2eA = 1.4426950408889634f;
+
+template <int HD>
+__global__ void __launch_bounds__(160, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  constexpr int HC = HD / 64;                 // 64-wide head-dim chunks
+  constexpr int Q_BYTES = HC * 128 * 128;     // [128 x HD]
+  constexpr int KV_BYTES = HC * 256 * 128;    // [256 x HD]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;
+  uint8_t* sV = sK + KV_BYTES;
+  __shared__ uint64_t bar_load, bar_s, bar_p, bar_o;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int bz = b * p.H + h;
+  const int L = p.L;
+  int nk = p.causal ? min(L, q0 + 128) : L;        // keys that can be visible to this query tile
+  const int nk32 = (nk + 31) & ~31;                // MMA N / K extent (<= 256)
+  const int n_boxes = (nk32 + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_p, 4);
+    mbar_init(&bar_o, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem_o = tmem + 128;   // reuses S columns [128, 128+HD) once P is complete
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const int row0 = b * L;
+      mbar_arrive_expect_tx(&bar_load, HC * 128 * 128 + 2 * HC * n_boxes * 128 * 128);
+      for (int c = 0; c < HC; ++c) {
+        tma_load_2d(sQ + c * 16384, &tmQ, &bar_load, p.q_c0 + h * HD + c * 64, row0 + q0);
+        for (int bx = 0; bx < n_boxes; ++bx) {
+          tma_load_2d(sK + c * 32768 + bx * 16384, &tmK, &bar_load, p.k_c0 + h * HD + c * 64, row0 + bx * 128);
+          tma_load_2d(sV + c * 32768 + bx * 16384, &tmV, &bar_load, p.v_c0 + h * HD + c * 64, row0 + bx * 128);
+        }
+      }
+      mbar_wait(&bar_load, 0);
+      tc_fence_after();
+      const uint32_t idesc1 = umma_idesc_bf16(128, nk32);
+#pragma unroll
+      for (int c = 0; c < HC; ++c)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss(tmem, umma_desc_sw128(smem_u32(sQ) + c * 16384 + ks * 32, 16, 1024),
+                  umma_desc_sw128(smem_u32(sK) + c * 32768 + ks * 32, 16, 1024), idesc1, (c | ks) != 0);
+      umma_commit(&bar_s);
+      // ---- second GEMM once the softmax warps have written P
+      mbar_wait(&bar_p, 0);
+      tc_fence_after();
+      constexpr uint32_t idesc2 = umma_idesc_bf16(128, HD, false, true);
+      for (int ks = 0; ks < nk32 / 16; ++ks)
+        umma_ts(tmem_o, tmem + ks * 8, umma_desc_sw128(smem_u32(sV) + ks * 2048, 32768, 1024), idesc2, ks != 0);
+      umma_commit(&bar_o);
+    }
+  } else {
+    // ------------------------------------------------ softmax warps: thread = query row
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int i = q0 + row;                 // query position inside the sequence
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    // key-visibility bit masks, 32 keys per word
+    uint32_t kmask[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int j = c * 32 + lane;
+      bool ok = j < L;
+      if (ok && p.mask_pad_keys) ok = p.pad_mask[(size_t)b * L + j] != 0;
+      kmask[c] = __ballot_sync(0xffffffffu, ok);
+    }
+    const float sl2 = p.scale * kLog2eA;
+    const uint32_t thr = p.drop_p > 0.f ? (uint32_t)(p.drop_p * 4294967296.0) : 0u;
+    const float ks_drop = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    const unsigned long long seed_eff = p.seed + ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
+    mbar_wait(&bar_s, 0);
+    tc_fence_after();
+    const int n_chunks = nk32 / 32;
+    auto vis_mask = [&](int c) -> uint32_t {
+      uint32_t m = 0;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc)
+        if (cc == c) m = kmask[cc];
+      if (p.causal) {
+        const int rel = i - c * 32;
+        const uint32_t cm = rel >= 31 ? 0xffffffffu : (rel < 0 ? 0u : ((2u << rel) - 1u));
+        m &= cm;
+      }
+      return m;
+    };
+    // pass 1: row max over the visible keys
+    float mx = -INFINITY;
+    for (int c = 0; c < n_chunks; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(tmem + lane_base + c * 32, raw);
+      tmem_ld_wait();
+      const uint32_t vm = vis_mask(c);
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (vm & (1u << q)) mx = fmaxf(mx, __uint_as_float(raw[q]));
+    }
+    const float moff = (mx == -INFINITY) ? 0.f : mx * sl2;
+    // pass 2: exponentials, row sum, P (bf16) back into TMEM over S, optional copy of the un-dropped P to global
+    float sum = 0.f;
+    __nv_bfloat16* prow =
+        (p.p_save && i < L) ? p.p_save + ((size_t)bz * p.Lp + i) * p.Lp : nullptr;
+    for (int c = 0; c < n_chunks; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(tmem + lane_base + c * 32, raw);
+      tmem_ld_wait();
+      const uint32_t vm = vis_mask(c);
+      float e[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const float v = ex2f(fmaf(__uint_as_float(raw[q]), sl2, -moff));
+        e[q] = (vm & (1u << q)) ? v : 0.f;
+        sum += e[q];
+      }
+      if (prow) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 8) {
+          uint4 w;
+          w.x = pack_bf16(e[q], e[q + 1]);
+          w.y = pack_bf16(e[q + 2], e[q + 3]);
+          w.z = pack_bf16(e[q + 4], e[q + 5]);
+          w.w = pack_bf16(e[q + 6], e[q + 7]);
+          *reinterpret_cast<uint4*>(prow + c * 32 + q) = w;
+        }
+      }
+      if (p.drop_p > 0.f) {
+        const unsigned long long e0 = p.drop_off + ((unsigned long long)bz * p.Lp + (unsigned long long)i) * p.Lp + c * 32;
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          const uint4 r = philox4x32(seed_eff, (e0 + q) >> 2);
+          e[q + 0] = r.x >= thr ? e[q + 0] * ks_drop : 0.f;
+          e[q + 1] = r.y >= thr ? e[q + 1] * ks_drop : 0.f;
+          e[q + 2] = r.z >= thr ? e[q + 2] * ks_drop : 0.f;
+          e[q + 3] = r.w >= thr ? e[q + 3] * ks_drop : 0.f;
+        }
+      }
+      uint32_t pk[16];
+#pragma unroll
+      for (int q = 0; q < 32; q += 2) pk[q >> 1] = pack_bf16(e[q], e[q + 1]);
+      tmem_st16(tmem + lane_base + c * 16, pk);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_p);
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    if (p.inv_sum && i < L) p.inv_sum[(size_t)bz * p.Lp + i] = inv;
+    // ---- O = (P.V) / sum
+    mbar_wait(&bar_o, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < HD; c += 32) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_o + lane_base + c, raw);
+      tmem_ld_wait();
+      if (i < L) {
+        __nv_bfloat16* o = p.out + ((size_t)b * L + i) * p.ldo + h * HD + c;
+#pragma unroll
+        for (int q = 0; q < 32; q += 8) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(raw[q]) * inv, __uint_as_float(raw[q + 1]) * inv);
+          w.y = pack_bf16(__uint_as_float(raw[q + 2]) * inv, __uint_as_float(raw[q + 3]) * inv);
+          w.z = pack_bf16(__uint_as_float(raw[q + 4]) * inv, __uint_as_float(raw[q + 5]) * inv);
+          w.w = pack_bf16(__uint_as_float(raw[q + 6]) * inv, __uint_as_float(raw[q + 7]) * inv);
+          *reinterpret_cast<uint4*>(o + q) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// Row-wise softmax backward between the batched GEMMs.  One warp per (batch*head, query) row.
+//   in : p_save  = exp(s - max) (bf16), inv_sum, dpd = dO.V^T (bf16, w.r.t. the dropped & rescaled probabilities)
+//   out: ds (over dpd) = P * (dP - sum_j P_j dP_j) * scale      with P = p_save * inv_sum, dP = dpd * mask / keep
+//        pd (over p_save) = P * mask / keep                       (A operand of dV = Pd^T . dO)
+__global__ void attn_softmax_bwd_kernel(__nv_bfloat16* __restrict__ p_save, __nv_bfloat16* __restrict__ dpd,
+                                        const float* __restrict__ inv_sum, int BH, int L, int Lp, float scale,
+                                        float drop_p, unsigned long long seed, unsigned long long drop_off,
+                                        const unsigned long long* __restrict__ seed_ptr) {
+  if (drop_p > 0.f && seed_ptr) seed += *seed_ptr;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 4294967296.0) : 0u;
+  const float ksd = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const long long n_rows = (long long)BH * L;
+  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rows; r += (long long)gridDim.x * wpb) {
+    const int bz = (int)(r / L), i = (int)(r % L);
+    const size_t base = ((size_t)bz * Lp + i) * Lp;
+    const float inv = inv_sum[(size_t)bz * Lp + i];
+    float P[8], dP[8], keep[8];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = k * 32 + lane;
+      P[k] = 0.f; dP[k] = 0.f; keep[k] = 0.f;
+      if (j < L) {
+        P[k] = __bfloat162float(p_save[base + j]) * inv;
+        keep[k] = ksd;
+        if (drop_p > 0.f && !philox_keep(seed, drop_off + base + j, thr)) keep[k] = 0.f;
+        dP[k] = __bfloat162float(dpd[base + j]) * keep[k];
+        dot += P[k] * dP[k];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = k * 32 + lane;
+      if (j < L) {
+        dpd[base + j] = __float2bfloat16(P[k] * (dP[k] - dot) * scale);
+        p_save[base + j] = __float2bfloat16(P[k] * keep[k]);
+      }
+    }
+  }
+}
+
+}  // namespace rp
+
+using namespace rp;
+
+struct rp_attn_desc {
+  const void* q; long long q_rows, q_cols, ldq; int q_c0;
+  const void* k; long long k_rows, k_cols, ldk; int k_c0;
+  const void* v; long long v_rows, v_cols, ldv; int v_c0;
+  int B, H, L, head_dim;
+  int causal, mask_pad_keys;
+  const uint8_t* pad_mask;
+  void* out; int ldo;
+  void* p_save; float* inv_sum;
+  float drop_p; unsigned long long seed, drop_off; const unsigned long long* seed_ptr;
+};
+
+RP_API int rp_attn_fwd(const rp_attn_desc* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a || !a->q || !a->k || !a->v || !a->out || !a->pad_mask) return RP_EINVAL;
+  if (a->L <= 0 || a->L > 256 || a->B <= 0 || a->H <= 0) return RP_ESHAPE;
+  if (a->head_dim != 64 && a->head_dim != 128) return RP_ESHAPE;
+  if (a->ldo % 8 != 0) return RP_EALIGN;
+  AttnParams p;
+  p.B = a->B; p.H = a->H; p.L = a->L; p.Lp = (a->L + 63) & ~63;
+  p.causal = a->causal; p.mask_pad_keys = a->mask_pad_keys;
+  p.scale = 1.f / sqrtf((float)a->head_dim);
+  p.pad_mask = a->pad_mask;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
+  p.p_save = reinterpret_cast<__nv_bfloat16*>(a->p_save); p.inv_sum = a->inv_sum;
+  p.q_c0 = a->q_c0; p.k_c0 = a->k_c0; p.v_c0 = a->v_c0;
+  p.drop_p = a->drop_p; p.seed = a->seed; p.drop_off = a->drop_off; p.seed_ptr = a->seed_ptr;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = make_tmap_bf16(&tmQ, a->q, a->q_rows, a->q_cols, a->ldq, 128)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmK, a->k, a->k_rows, a->k_cols, a->ldk, 128)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmV, a->v, a->v_rows, a->v_cols, a->ldv, 128)) != RP_OK) return rc;
+  dim3 grid((a->L + 127) / 128, a->H, a->B);
+  if (a->head_dim == 64) {
+    const int smem = 16384 + 2 * 32768 + 1024;
+    RP_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attn_fwd_kernel<64><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+  } else {
+    const int smem = 2 * (16384 + 2 * 32768) + 1024;
+    RP_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attn_fwd_kernel<128><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+  }
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+RP_API int rp_attn_softmax_bwd(void* p_save, void* dpd, const float* inv_sum, int BH, int L, float scale, float drop_p,
+                               unsigned long long seed, unsigned long long drop_off, const unsigned long long* seed_ptr,
+                               void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!p_save || !dpd || !inv_sum || BH <= 0 || L <= 0 || L > 256) return RP_EINVAL;
+  const int Lp = (L + 63) & ~63;
+  const long long rows = (long long)BH * L;
+  long long blocks = (rows + 7) / 8;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  attn_softmax_bwd_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(p_save),
+                                                           reinterpret_cast<__nv_bfloat16*>(dpd), inv_sum, BH, L, Lp, scale,
+                                                           drop_p, seed, drop_off, seed_ptr);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}

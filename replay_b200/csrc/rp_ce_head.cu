@@ -35,8 +35,8 @@ static constexpr int kThreads = 64 + kEpiWarps * 32;
 template <int KCH, int NSTAGE>
 __global__ void __launch_bounds__(kThreads, 1)
 ce_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-              const int32_t* __restrict__ labels, const int32_t* __restrict__ n_valid_ptr, int n_items, int n_splits,
-              float2* __restrict__ part /* [T, n_splits, 2] (m in log2 units, s) */, float* __restrict__ zt /* [T] */) {
+              const int32_t* __restrict__ n_valid_ptr, int n_items, int n_splits,
+              float2* __restrict__ part /* [T, n_splits, 2] (m in log2 units, s) */) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -115,7 +115,6 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
     const int row = quarter * 32 + lane;
     const int t = t0 + row;
-    const int y = (t < n_valid) ? labels[t] : -1;
     float m = -1e30f, ssum = 0.f;  // m in log2 units
     for (int j = j_begin, n = 0; j < j_end; ++j, ++n) {
       const uint32_t as = n & 1, aph = (n >> 1) & 1;
@@ -135,13 +134,6 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
           for (int q = 0; q < 32; ++q)
             if (col0 + q >= n_items) x[q] = -INFINITY;
-        }
-        if (y >= col0 && y < col0 + 32) {
-          float z = 0.f;
-#pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if (q == y - col0) z = x[q];
-          zt[t] = z;
         }
         float cm = x[0];
 #pragma unroll
@@ -168,40 +160,60 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
-// lse / loss / per-token exponent offsets.  Deterministic: per-block partial sums, last block adds them in order.
-__global__ void ce_finalize_kernel(const float2* __restrict__ part, const float* __restrict__ zt,
-                                   const int32_t* __restrict__ n_valid_ptr, int n_part, int capacity,
+// lse / loss / per-token exponent offsets.  One warp per token: merges the (max, sum) partials, computes the target logit
+// z_y = hc[t] . E[y_t] as a gather-dot (keeps the per-element target pick out of the MMA epilogue), accumulates the loss.
+// Deterministic: per-block partial sums, the last block adds them in index order.
+__global__ void ce_finalize_kernel(const float2* __restrict__ part, const __nv_bfloat16* __restrict__ hc,
+                                   const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ labels,
+                                   const int32_t* __restrict__ n_valid_ptr, int n_part, int capacity, int d,
                                    float* __restrict__ lse_out, float* __restrict__ cvec, float* __restrict__ block_sums,
                                    unsigned int* __restrict__ ticket, float* __restrict__ loss_out) {
   const int n_valid = *n_valid_ptr;
   const float inv_n = n_valid > 0 ? 1.f / (float)n_valid : 0.f;
   const float log2_inv_n = n_valid > 0 ? -log2f((float)n_valid) : 0.f;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   float local = 0.f;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < capacity; t += gridDim.x * blockDim.x) {
+  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < capacity; t += gridDim.x * wpb) {
     if (t < n_valid) {
       const float2* p = part + (size_t)t * n_part;
       float M = -1e30f;
-      for (int i = 0; i < n_part; ++i) M = fmaxf(M, p[i].x);
+      for (int i = lane; i < n_part; i += 32) M = fmaxf(M, p[i].x);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
       float S = 0.f;
-      for (int i = 0; i < n_part; ++i) S += p[i].y * exp2f(p[i].x - M);
+      for (int i = lane; i < n_part; i += 32) S += p[i].y * exp2f(p[i].x - M);
+      const __nv_bfloat16* hr = hc + (size_t)t * d;
+      const __nv_bfloat16* er = table + (size_t)labels[t] * d;
+      float z = 0.f;
+      for (int c = lane * 2; c < d; c += 64) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hr + c));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(er + c));
+        z = fmaf(a.x, b.x, z);
+        z = fmaf(a.y, b.y, z);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, o);
+        z += __shfl_xor_sync(0xffffffffu, z, o);
+      }
       const float lse2 = M + log2f(S);  // log2 units
       const float lse = lse2 * kLn2;
-      lse_out[t] = lse;
-      cvec[t] = -lse2 + log2_inv_n;
-      local += lse - zt[t];
-    } else {
+      if (lane == 0) {
+        lse_out[t] = lse;
+        cvec[t] = -lse2 + log2_inv_n;
+        local += lse - z;
+      }
+    } else if (lane == 0) {
       cvec[t] = -INFINITY;  // rows beyond T_v contribute nothing to the backward
     }
   }
   __shared__ float red[32];
   __shared__ bool last;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  if (lane == 0) red[threadIdx.x >> 5] = local;
   __syncthreads();
   if (threadIdx.x == 0) {
     float s = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    for (int i = 0; i < wpb; ++i) s += red[i];
     block_sums[blockIdx.x] = s;
     __threadfence();
     last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
@@ -213,7 +225,6 @@ __global__ void ce_finalize_kernel(const float2* __restrict__ part, const float*
     for (int i = 0; i < (int)gridDim.x; ++i) s += reinterpret_cast<volatile float*>(block_sums)[i];
     loss_out[0] = s * inv_n;  // mean over valid targets
     loss_out[1] = inv_n;
-    *ticket = 0;
   }
 }
 
@@ -478,12 +489,12 @@ RP_API size_t rp_ce_head_workspace(int capacity_tokens, int n_items, int d) {
 }
 
 template <int KCH, int NSTAGE>
-static int launch_ce_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const int32_t* labels, const int32_t* n_valid,
-                         int n_items, int n_splits, int n_tok_tiles, float2* part, float* zt, cudaStream_t stream) {
+static int launch_ce_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const int32_t* n_valid, int n_items,
+                         int n_splits, int n_tok_tiles, float2* part, cudaStream_t stream) {
   const int smem = (KCH + NSTAGE) * kChunk + 1024;
   auto kern = ce_fwd_kernel<KCH, NSTAGE>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<n_tok_tiles * n_splits, kThreads, smem, stream>>>(tmA, tmB, labels, n_valid, n_items, n_splits, part, zt);
+  kern<<<n_tok_tiles * n_splits, kThreads, smem, stream>>>(tmA, tmB, n_valid, n_items, n_splits, part);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }
@@ -511,17 +522,18 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const int32_t* labe
   if ((rc = make_tmap_bf16(&tmA, hc, capacity, d, d, 128)) != RP_OK) return rc;
   if ((rc = make_tmap_bf16(&tmB, table, n_items, d, d, 128)) != RP_OK) return rc;
   switch (d) {
-    case 64: rc = launch_ce_fwd<1, 8>(tmA, tmB, labels, n_valid, n_items, P, n_tok_tiles, part, zt, stream); break;
-    case 128: rc = launch_ce_fwd<2, 8>(tmA, tmB, labels, n_valid, n_items, P, n_tok_tiles, part, zt, stream); break;
-    case 256: rc = launch_ce_fwd<4, 8>(tmA, tmB, labels, n_valid, n_items, P, n_tok_tiles, part, zt, stream); break;
-    default: rc = launch_ce_fwd<8, 5>(tmA, tmB, labels, n_valid, n_items, P, n_tok_tiles, part, zt, stream); break;
+    case 64: rc = launch_ce_fwd<1, 8>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, part, stream); break;
+    case 128: rc = launch_ce_fwd<2, 8>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, part, stream); break;
+    case 256: rc = launch_ce_fwd<4, 8>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, part, stream); break;
+    default: rc = launch_ce_fwd<8, 5>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, part, stream); break;
   }
   if (rc != RP_OK) return rc;
   RP_CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, stream));
-  int blocks = (capacity + 255) / 256;
+  int blocks = (capacity + 7) / 8;
   if (blocks > 256) blocks = 256;
-  ce_finalize_kernel<<<blocks, 256, 0, stream>>>(part, zt, n_valid, P * 2, capacity, lse, cvec, block_sums, ticket,
-                                                 loss_out);
+  ce_finalize_kernel<<<blocks, 256, 0, stream>>>(part, reinterpret_cast<const __nv_bfloat16*>(hc),
+                                                 reinterpret_cast<const __nv_bfloat16*>(table), labels, n_valid, P * 2,
+                                                 capacity, d, lse, cvec, block_sums, ticket, loss_out);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }

@@ -1,0 +1,535 @@
+// rp_elementwise.cu - the HBM-bound kernels of the transformer body and of the optimizer: batch preparation / target
+// compaction, embedding gather + positional add (+dropout) and its backward, LayerNorm forward/backward (optionally
+// gathering / scattering the valid-target rows), dropout backward, bias-gradient column sums, Adam.
+// All are coalesced, vectorised (8/16-byte accesses) row-per-warp kernels sized in multiples of the SM count.
+//
+// Reference call sites: replay/nn/sequential/sasrec/agg.py:37-53, replay/models/nn/sequential/sasrec/model.py:346-357
+// (embedding), transformer.py:47-49,60-62 + model.py:415-417,463 (LayerNorm eps 1e-8 / 1e-5),
+// replay/models/nn/optimizer_utils/optimizer_factory.py:71-87 (torch.optim.Adam).
+#include "rp_host.h"
+#include "rp_philox.cuh"
+#include "rp_sm100.cuh"
+
+namespace rp {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// batch preparation: int64 ids / bool masks from the data layer -> int32 ids (pads replaced by pad_id), compacted list of
+// valid targets (ascending token index), their labels, and the count (device memory).
+// Single block: T is at most a few hundred thousand tokens.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+prepare_batch_kernel(const int64_t* __restrict__ ids64, const uint8_t* __restrict__ pad_mask,
+                     const int64_t* __restrict__ labels64, const uint8_t* __restrict__ target_mask, int T, int pad_id,
+                     int n_items, int32_t* __restrict__ ids32, int32_t* __restrict__ valid_idx,
+                     int32_t* __restrict__ labels_c, int32_t* __restrict__ n_valid) {
+  __shared__ int warp_tot[32];
+  __shared__ int block_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) block_base = 0;
+  __syncthreads();
+  for (int base = 0; base < T; base += 1024) {
+    const int t = base + tid;
+    bool valid = false;
+    if (t < T) {
+      const int64_t id = ids64[t];
+      ids32[t] = (pad_mask[t] && id >= 0 && id < n_items) ? (int32_t)id : pad_id;
+      if (target_mask) {
+        const int64_t y = labels64[t];
+        valid = target_mask[t] != 0 && y >= 0 && y < n_items;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, valid);
+    const int pre = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+    const int pos = block_base + woff + pre;
+    if (valid) {
+      valid_idx[pos] = t;
+      labels_c[pos] = (int32_t)labels64[t];
+    }
+    __syncthreads();
+    if (tid == 1023) block_base = pos + (valid ? 1 : 0);
+    __syncthreads();
+  }
+  if (tid == 0 && n_valid) *n_valid = block_base;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// embedding:  x[t] = E[ids[t]] * scale + P[pos0 + t % L]  -> dropout -> (* pad)        one warp per token
+// ------------------------------------------------------------------------------------------------------------------
+template <int VEC /* bf16 elements per lane = d / 32 */>
+__global__ void embed_fwd_kernel(const __nv_bfloat16* __restrict__ table, const float* __restrict__ pos,
+                                 const int32_t* __restrict__ ids, const uint8_t* __restrict__ pad_mask, int T, int L,
+                                 int pos0, float scale, int zero_pad_rows, float drop_p, unsigned long long seed,
+                                 unsigned long long drop_off, const unsigned long long* __restrict__ seed_ptr,
+                                 __nv_bfloat16* __restrict__ out) {
+  if (drop_p > 0.f && seed_ptr) seed += *seed_ptr;
+  constexpr int D = VEC * 32;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 4294967296.0) : 0u;
+  const float ks = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < T; t += gridDim.x * wpb) {
+    const int id = ids[t];
+    const __nv_bfloat16* e = table + (size_t)id * D + lane * VEC;
+    const float* p = pos + (size_t)(pos0 + t % L) * D + lane * VEC;
+    float v[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; i += 2) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(e + i));
+      v[i] = f.x * scale + p[i];
+      v[i + 1] = f.y * scale + p[i + 1];
+    }
+    if (drop_p > 0.f) {
+      const unsigned long long e0 = drop_off + (unsigned long long)t * D + lane * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[i] = philox_keep(seed, e0 + i, thr) ? v[i] * ks : 0.f;
+    }
+    if (zero_pad_rows && !pad_mask[t]) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[i] = 0.f;
+    }
+    __nv_bfloat16* o = out + (size_t)t * D + lane * VEC;
+#pragma unroll
+    for (int i = 0; i < VEC; i += 2) *reinterpret_cast<uint32_t*>(o + i) = pack_bf16(v[i], v[i + 1]);
+  }
+}
+
+// backward of the gather: dE[ids[t]] += dx[t] * scale * mask   (fp32 atomics, pad row frozen)
+template <int VEC>
+__global__ void embed_bwd_table_kernel(const __nv_bfloat16* __restrict__ dx, const int32_t* __restrict__ ids,
+                                       const uint8_t* __restrict__ pad_mask, int T, int pad_id, float scale,
+                                       int zero_pad_rows, float drop_p, unsigned long long seed,
+                                       unsigned long long drop_off, const unsigned long long* __restrict__ seed_ptr,
+                                       float* __restrict__ dE) {
+  if (drop_p > 0.f && seed_ptr) seed += *seed_ptr;
+  constexpr int D = VEC * 32;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 4294967296.0) : 0u;
+  const float ks = (drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f) * scale;
+  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < T; t += gridDim.x * wpb) {
+    const int id = ids[t];
+    if (id == pad_id) continue;
+    if (zero_pad_rows && !pad_mask[t]) continue;
+    const __nv_bfloat16* g = dx + (size_t)t * D + lane * VEC;
+    float* dst = dE + (size_t)id * D + lane * VEC;
+    const unsigned long long e0 = drop_off + (unsigned long long)t * D + lane * VEC;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float v = __bfloat162float(g[i]) * ks;
+      if (drop_p > 0.f && !philox_keep(seed, e0 + i, thr)) v = 0.f;
+      atomicAdd(dst + i, v);
+    }
+  }
+}
+
+// dP[pos0 + l] += sum_b dx[b*L + l] * mask      one block per position, no atomics
+__global__ void embed_bwd_pos_kernel(const __nv_bfloat16* __restrict__ dx, const uint8_t* __restrict__ pad_mask, int B,
+                                     int L, int D, int pos0, int zero_pad_rows, float drop_p, unsigned long long seed,
+                                     unsigned long long drop_off, const unsigned long long* __restrict__ seed_ptr,
+                                     float* __restrict__ dP) {
+  if (drop_p > 0.f && seed_ptr) seed += *seed_ptr;
+  const int l = blockIdx.x;
+  const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 4294967296.0) : 0u;
+  const float ks = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const int t = b * L + l;
+      if (zero_pad_rows && !pad_mask[t]) continue;
+      float v = __bfloat162float(dx[(size_t)t * D + c]);
+      if (drop_p > 0.f) v = philox_keep(seed, drop_off + (unsigned long long)t * D + c, thr) ? v * ks : 0.f;
+      acc += v;
+    }
+    dP[(size_t)(pos0 + l) * D + c] += acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm forward.  One warp per output row.  gather != null: output row r reads input row gather[r] and only
+// r < *n_rows_dev rows are produced (compaction of the valid targets for the CE head).
+// ------------------------------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                     const float* __restrict__ b, float eps, int n_rows,
+                                     const int32_t* __restrict__ n_rows_dev, const int32_t* __restrict__ gather,
+                                     __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                                     float* __restrict__ rstd_out) {
+  constexpr int D = VEC * 32;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int rows = n_rows_dev ? min(n_rows, *n_rows_dev) : n_rows;
+  float wv[VEC], bv[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    wv[i] = w[lane * VEC + i];
+    bv[i] = b[lane * VEC + i];
+  }
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const int src = gather ? gather[r] : r;
+    const __nv_bfloat16* xr = x + (size_t)src * D + lane * VEC;
+    float v[VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; i += 2) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xr + i));
+      v[i] = f.x;
+      v[i + 1] = f.y;
+      s += f.x + f.y;
+    }
+    const float mean = warp_sum(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float dlt = v[i] - mean;
+      q += dlt * dlt;
+    }
+    const float var = warp_sum(q) * (1.f / D);
+    const float rstd = rsqrtf(var + eps);
+    __nv_bfloat16* yr = y + (size_t)r * D + lane * VEC;
+#pragma unroll
+    for (int i = 0; i < VEC; i += 2)
+      *reinterpret_cast<uint32_t*>(yr + i) =
+          pack_bf16((v[i] - mean) * rstd * wv[i] + bv[i], (v[i + 1] - mean) * rstd * wv[i + 1] + bv[i + 1]);
+    if (lane == 0) {
+      mean_out[r] = mean;
+      rstd_out[r] = rstd;
+    }
+  }
+}
+
+// LayerNorm backward.  dy row r (compact index when gather != null) -> dx row (gather ? gather[r] : r).
+//   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w ;  dw += sum dy * xhat ; db += sum dy
+// add_to != null: dx += add_to[row] (fuses the residual-branch gradient).  Rows not covered by a gather stay untouched
+// (the caller zero-fills dx first when it scatters).
+template <int VEC>
+__global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                     const float* __restrict__ w, const float* __restrict__ mean_in,
+                                     const float* __restrict__ rstd_in, int n_rows,
+                                     const int32_t* __restrict__ n_rows_dev, const int32_t* __restrict__ gather,
+                                     const __nv_bfloat16* __restrict__ add_to, __nv_bfloat16* __restrict__ dx,
+                                     float* __restrict__ dw, float* __restrict__ db) {
+  constexpr int D = VEC * 32;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int rows = n_rows_dev ? min(n_rows, *n_rows_dev) : n_rows;
+  float wv[VEC], dw_acc[VEC], db_acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    wv[i] = w[lane * VEC + i];
+    dw_acc[i] = 0.f;
+    db_acc[i] = 0.f;
+  }
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const int row = gather ? gather[r] : r;
+    const __nv_bfloat16* xr = x + (size_t)row * D + lane * VEC;
+    const __nv_bfloat16* gr = dy + (size_t)r * D + lane * VEC;
+    const float mean = mean_in[r], rstd = rstd_in[r];
+    float xh[VEC], g[VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; i += 2) {
+      const float2 xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xr + i));
+      const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gr + i));
+      xh[i] = (xf.x - mean) * rstd;
+      xh[i + 1] = (xf.y - mean) * rstd;
+      dw_acc[i] += gf.x * xh[i];
+      dw_acc[i + 1] += gf.y * xh[i + 1];
+      db_acc[i] += gf.x;
+      db_acc[i + 1] += gf.y;
+      g[i] = gf.x * wv[i];
+      g[i + 1] = gf.y * wv[i + 1];
+      s1 += g[i] + g[i + 1];
+      s2 += g[i] * xh[i] + g[i + 1] * xh[i + 1];
+    }
+    s1 = warp_sum(s1) * (1.f / D);
+    s2 = warp_sum(s2) * (1.f / D);
+    __nv_bfloat16* o = dx + (size_t)row * D + lane * VEC;
+    const __nv_bfloat16* a = add_to ? add_to + (size_t)row * D + lane * VEC : nullptr;
+#pragma unroll
+    for (int i = 0; i < VEC; i += 2) {
+      float o0 = rstd * (g[i] - s1 - xh[i] * s2), o1 = rstd * (g[i + 1] - s1 - xh[i + 1] * s2);
+      if (a) {
+        const float2 af = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + i));
+        o0 += af.x;
+        o1 += af.y;
+      }
+      *reinterpret_cast<uint32_t*>(o + i) = pack_bf16(o0, o1);
+    }
+  }
+  // block reduction of dw/db through shared memory, then one atomic per column per block
+  extern __shared__ float red[];  // [2][wpb][D]
+  float* rw = red;
+  float* rb = red + (size_t)wpb * D;
+  const int wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    rw[wid * D + lane * VEC + i] = dw_acc[i];
+    rb[wid * D + lane * VEC + i] = db_acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float a = 0.f, bsum = 0.f;
+    for (int k = 0; k < wpb; ++k) {
+      a += rw[k * D + c];
+      bsum += rb[k * D + c];
+    }
+    atomicAdd(dw + c, a);
+    atomicAdd(db + c, bsum);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// out = in * dropout_mask / keep  (the mask is regenerated from the forward's (seed, offset, geometry)); optional row mask
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void dropout_bwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n,
+                                   int cols, const uint8_t* __restrict__ rowmask, float drop_p,
+                                   unsigned long long seed, unsigned long long drop_off,
+                                   const unsigned long long* __restrict__ seed_ptr) {
+  if (drop_p > 0.f && seed_ptr) seed += *seed_ptr;
+  const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 4294967296.0) : 0u;
+  const float ks = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
+       i += (long long)gridDim.x * blockDim.x * 4) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(in + i);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    float v[4] = {a.x, a.y, b.x, b.y};
+    if (drop_p > 0.f) {
+      const uint4 r = philox4x32(seed, (drop_off + (unsigned long long)i) >> 2);
+      v[0] = r.x >= thr ? v[0] * ks : 0.f;
+      v[1] = r.y >= thr ? v[1] * ks : 0.f;
+      v[2] = r.z >= thr ? v[2] * ks : 0.f;
+      v[3] = r.w >= thr ? v[3] * ks : 0.f;
+    }
+    if (rowmask && !rowmask[i / cols]) v[0] = v[1] = v[2] = v[3] = 0.f;
+    uint2 w;
+    w.x = pack_bf16(v[0], v[1]);
+    w.y = pack_bf16(v[2], v[3]);
+    *reinterpret_cast<uint2*>(out + i) = w;
+  }
+}
+
+// db[c] += sum_r dY[r, c]        dY bf16 [rows, cols] with pitch ld; each block sums a slab of rows
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, int rows, int cols, long long ld,
+                              float* __restrict__ db) {
+  const int rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  for (int c = threadIdx.x * 2; c < cols; c += blockDim.x * 2) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy + (size_t)r * ld + c));
+      a0 += f.x;
+      a1 += f.y;
+    }
+    atomicAdd(db + c, a0);
+    atomicAdd(db + c + 1, a1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam, no weight decay / amsgrad) over one flat fp32 parameter buffer; also refreshes the bf16 shadow
+// copy the kernels consume and zeroes the gradient for the next step.  The step counter and lr live in device memory so
+// the launch is CUDA-graph replayable.  grad_scale multiplies the gradient (1/world_size after a sum all-reduce).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            __nv_bfloat16* __restrict__ shadow, long long n, const float* __restrict__ lr_dev,
+                            const int32_t* __restrict__ step_dev, float beta1, float beta2, float eps, float grad_scale,
+                            const uint8_t* __restrict__ frozen /* per-element freeze mask or null */, int zero_grad) {
+  const float lr = *lr_dev;
+  const int step = *step_dev;  // 1-based, already incremented by adam_tick_kernel
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
+       i += (long long)gridDim.x * blockDim.x * 4) {
+    float4 pp = *reinterpret_cast<float4*>(p + i), gg = *reinterpret_cast<float4*>(g + i);
+    float4 mm = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+    float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = ga[k] * grad_scale;
+      ma[k] = beta1 * ma[k] + (1.f - beta1) * gk;
+      va[k] = beta2 * va[k] + (1.f - beta2) * gk * gk;
+      const float denom = sqrtf(va[k]) * inv_sqrt_bc2 + eps;
+      const float upd = step_size * ma[k] / denom;
+      if (!frozen || !frozen[i + k]) pa[k] -= upd;
+    }
+    *reinterpret_cast<float4*>(p + i) = pp;
+    *reinterpret_cast<float4*>(m + i) = mm;
+    *reinterpret_cast<float4*>(v + i) = vv;
+    if (zero_grad) *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (shadow) {
+      uint2 w;
+      w.x = pack_bf16(pp.x, pp.y);
+      w.y = pack_bf16(pp.z, pp.w);
+      *reinterpret_cast<uint2*>(shadow + i) = w;
+    }
+  }
+}
+
+__global__ void adam_tick_kernel(int32_t* step_dev) { *step_dev += 1; }
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
+       i += (long long)gridDim.x * blockDim.x * 4) {
+    const float4 f = *reinterpret_cast<const float4*>(src + i);
+    uint2 w;
+    w.x = pack_bf16(f.x, f.y);
+    w.y = pack_bf16(f.z, f.w);
+    *reinterpret_cast<uint2*>(dst + i) = w;
+  }
+}
+
+static inline int grid_for(long long work_items, int per_block) {
+  long long b = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)sm_count() * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace rp
+
+using namespace rp;
+
+RP_API int rp_prepare_batch(const int64_t* ids, const uint8_t* pad_mask, const int64_t* labels, const uint8_t* target_mask,
+                            int T, int pad_id, int n_items, int32_t* ids32, int32_t* valid_idx, int32_t* labels_c,
+                            int32_t* n_valid, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!ids || !pad_mask || !ids32 || T <= 0) return RP_EINVAL;
+  if (target_mask && (!labels || !valid_idx || !labels_c || !n_valid)) return RP_EINVAL;
+  prepare_batch_kernel<<<1, 1024, 0, stream>>>(ids, pad_mask, labels, target_mask, T, pad_id, n_items, ids32, valid_idx,
+                                               labels_c, n_valid);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+#define RP_DISPATCH_D(d, CALL)            \
+  switch (d) {                            \
+    case 64: { constexpr int VEC = 2; CALL; } break;   \
+    case 128: { constexpr int VEC = 4; CALL; } break;  \
+    case 256: { constexpr int VEC = 8; CALL; } break;  \
+    case 512: { constexpr int VEC = 16; CALL; } break; \
+    default: return RP_ESHAPE;            \
+  }
+
+RP_API int rp_embed_fwd(const void* table, const float* pos, const int32_t* ids, const uint8_t* pad_mask, int T, int L,
+                        int d, int pos0, float scale, int zero_pad_rows, float drop_p, unsigned long long seed,
+                        unsigned long long drop_off, const unsigned long long* seed_ptr, void* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!table || !pos || !ids || !out || T <= 0 || L <= 0) return RP_EINVAL;
+  const int grid = grid_for(T, 8);
+  RP_DISPATCH_D(d, (embed_fwd_kernel<VEC><<<grid, 256, 0, stream>>>(
+                       reinterpret_cast<const __nv_bfloat16*>(table), pos, ids, pad_mask, T, L, pos0, scale, zero_pad_rows,
+                       drop_p, seed, drop_off, seed_ptr, reinterpret_cast<__nv_bfloat16*>(out))));
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+RP_API int rp_embed_bwd(const void* dx, const int32_t* ids, const uint8_t* pad_mask, int B, int L, int d, int pad_id,
+                        int pos0, float scale, int zero_pad_rows, float drop_p, unsigned long long seed,
+                        unsigned long long drop_off, const unsigned long long* seed_ptr, float* d_table, float* d_pos,
+                        void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!dx || !ids || !d_table || !d_pos || B <= 0 || L <= 0) return RP_EINVAL;
+  const int T = B * L;
+  const int grid = grid_for(T, 8);
+  RP_DISPATCH_D(d, (embed_bwd_table_kernel<VEC><<<grid, 256, 0, stream>>>(
+                       reinterpret_cast<const __nv_bfloat16*>(dx), ids, pad_mask, T, pad_id, scale, zero_pad_rows, drop_p,
+                       seed, drop_off, seed_ptr, d_table)));
+  RP_LAUNCH_CHECK();
+  embed_bwd_pos_kernel<<<L, d < 256 ? d : 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dx), pad_mask, B, L, d,
+                                                            pos0, zero_pad_rows, drop_p, seed, drop_off, seed_ptr, d_pos);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+RP_API int rp_layernorm_fwd(const void* x, const float* w, const float* b, float eps, int n_rows, int d,
+                            const int32_t* n_rows_dev, const int32_t* gather, void* y, float* mean, float* rstd,
+                            void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !w || !b || !y || !mean || !rstd || n_rows <= 0) return RP_EINVAL;
+  const int grid = grid_for(n_rows, 8);
+  RP_DISPATCH_D(d, (layernorm_fwd_kernel<VEC><<<grid, 256, 0, stream>>>(
+                       reinterpret_cast<const __nv_bfloat16*>(x), w, b, eps, n_rows, n_rows_dev, gather,
+                       reinterpret_cast<__nv_bfloat16*>(y), mean, rstd)));
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+RP_API int rp_layernorm_bwd(const void* dy, const void* x, const float* w, const float* mean, const float* rstd,
+                            int n_rows, int d, const int32_t* n_rows_dev, const int32_t* gather, const void* add_to,
+                            void* dx, float* dw, float* db, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!dy || !x || !w || !mean || !rstd || !dx || !dw || !db || n_rows <= 0) return RP_EINVAL;
+  int grid = grid_for(n_rows, 8 * 16);  // each warp walks ~16 rows so the dw/db atomics stay few
+  const size_t smem = (size_t)2 * 8 * d * sizeof(float);
+  RP_DISPATCH_D(d, (layernorm_bwd_kernel<VEC><<<grid, 256, smem, stream>>>(
+                       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), w, mean, rstd,
+                       n_rows, n_rows_dev, gather, reinterpret_cast<const __nv_bfloat16*>(add_to),
+                       reinterpret_cast<__nv_bfloat16*>(dx), dw, db)));
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+RP_API int rp_dropout_bwd(const void* in, void* out, long long rows, int cols, const uint8_t* rowmask, float drop_p,
+                          unsigned long long seed, unsigned long long drop_off, const unsigned long long* seed_ptr,
+                          void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!in || !out || rows <= 0 || cols <= 0 || (cols & 3)) return RP_EINVAL;
+  const long long n = rows * cols;
+  dropout_bwd_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                                                reinterpret_cast<__nv_bfloat16*>(out), n, cols, rowmask,
+                                                                drop_p, seed, drop_off, seed_ptr);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+RP_API int rp_colsum(const void* dy, int rows, int cols, long long ld, float* db, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!dy || !db || rows <= 0 || cols <= 0 || (cols & 1)) return RP_EINVAL;
+  int grid = sm_count() * 2;
+  if (grid > rows) grid = rows;
+  colsum_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), rows, cols, ld, db);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+RP_API int rp_adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, long long n, const float* lr_dev,
+                        int32_t* step_dev, float beta1, float beta2, float eps, float grad_scale, const uint8_t* frozen,
+                        int zero_grad, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!p || !g || !m || !v || !lr_dev || !step_dev || n <= 0 || (n & 3)) return RP_EINVAL;
+  adam_tick_kernel<<<1, 1, 0, stream>>>(step_dev);
+  adam_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr_dev,
+                                                        step_dev, beta1, beta2, eps, grad_scale, frozen, zero_grad);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+RP_API int rp_cast_bf16(const float* src, void* dst, long long n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!src || !dst || n <= 0 || (n & 3)) return RP_EINVAL;
+  cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+
+RP_API int rp_counter_add(unsigned long long* counter, unsigned long long inc, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!counter) return RP_EINVAL;
+  counter_add_kernel<<<1, 1, 0, stream>>>(counter, inc);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}

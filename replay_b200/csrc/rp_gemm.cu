@@ -1,0 +1,308 @@
+// rp_gemm.cu - generic batched bf16 GEMM on tcgen05 with a fused epilogue; the workhorse of the transformer body.
+//
+//   C[m, n] = epilogue( alpha * sum_k A(m, k) * B(n, k) )            (per batch element)
+//
+// Operands may be K-major (stored [rows = M/N, cols = K]) or MN-major (stored [rows = K, cols = M/N]); both are fed to
+// the tensor core straight from TMA-written 128B-swizzled shared memory (no transposes in HBM).  Replaces, on the body:
+//   torch.nn.MultiheadAttention in/out projections, Conv1d(d,d,1)/Linear FFN layers and their autograd backward
+//   (replay/nn/sequential/sasrec/transformer.py:36-46,99-106 ; replay/nn/ffn.py:43-57 ;
+//    replay/models/nn/sequential/sasrec/model.py:407-414,490-506 ; replay/models/nn/sequential/bert4rec/model.py:471-527).
+//
+// CTA = one 128 x BN output tile (x one K split).  warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue.
+#include "rp_host.h"
+#include "rp_philox.cuh"
+#include "rp_sm100.cuh"
+
+namespace rp {
+
+struct GemmParams {
+  int M, N, K;                 // per-batch problem size
+  int inner;                   // batch index bz = outer * inner + in
+  int a_r0, a_ro, a_ri;        // A row offset = a_r0 + outer*a_ro + in*a_ri   (rows of the stored 2-D array)
+  int a_c0, a_co, a_ci;        // A col offset
+  int b_r0, b_ro, b_ri, b_c0, b_co, b_ci;
+  void* C;                     // output
+  long long ldc, c_off0, c_oo, c_oi;   // element offsets: c_off0 + outer*c_oo + in*c_oi, row pitch ldc
+  int out_mode;                // 0: bf16 store, 1: fp32 atomic add, 2: fp32 store
+  float alpha;
+  const float* bias;           // [N] or null
+  int act;                     // 0 none, 1 relu, 2 gelu(erf)
+  const __nv_bfloat16* residual;  // same geometry as C (bf16) or null
+  const uint8_t* rowmask;      // [>= rows] multiply row m by rowmask[row_index] (row_index = c row) or null
+  long long rowmask_off0, rowmask_oo;   // row index base per batch: rowmask_off0 + outer*rowmask_oo
+  float drop_p;                // dropout prob applied after act, before residual (0 = off)
+  unsigned long long seed, drop_offset;
+  const unsigned long long* seed_ptr;  // optional device counter added to seed (CUDA-graph replays get fresh masks)
+  int split_k;                 // number of K splits (out_mode 1 only)
+  const __nv_bfloat16* gate;   // same geometry as C: x *= (gate != 0) ? gate_scale : 0   (ReLU+dropout backward) or null
+  float gate_scale;
+};
+
+static constexpr int kGemmThreads = 192;
+
+template <int BN, bool A_MN, bool B_MN, int NSTAGE>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int A_BYTES = 128 * 128;       // [128 x 64] bf16
+  constexpr int B_BYTES = BN * 128;        // [BN x 64] bf16
+  constexpr int STAGE = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_acc;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_bias[BN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x;
+  const int m_tile = blockIdx.y / p.split_k, ksplit = blockIdx.y % p.split_k;
+  const int bz = blockIdx.z, outer = bz / p.inner, in = bz % p.inner;
+  const int m0 = m_tile * 128, n0 = n_tile * BN;
+  const int k_chunks = (p.K + 63) / 64;
+  const int kc_begin = (int)(((long long)k_chunks * ksplit) / p.split_k);
+  const int kc_end = (int)(((long long)k_chunks * (ksplit + 1)) / p.split_k);
+  const int a_r = p.a_r0 + outer * p.a_ro + in * p.a_ri, a_c = p.a_c0 + outer * p.a_co + in * p.a_ci;
+  const int b_r = p.b_r0 + outer * p.b_ro + in * p.b_ri, b_c = p.b_c0 + outer * p.b_co + in * p.b_ci;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    mbar_init(&bar_acc, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, BN < 32 ? 32 : BN);
+  if (p.bias != nullptr && threadIdx.x >= 64) {
+    for (int i = threadIdx.x - 64; i < BN; i += 128) s_bias[i] = (n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int kc = kc_begin, it = 0; kc < kc_end; ++kc, ++it) {
+        const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
+        mbar_wait(&bar_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&bar_full[s], STAGE);
+        uint8_t* sa = smem + s * STAGE;
+        uint8_t* sb = sa + A_BYTES;
+        if (A_MN) {  // stored [K rows, M cols]: two boxes of [64 k-rows x 64 m]
+          tma_load_2d(sa, &tmA, &bar_full[s], a_c + m0, a_r + kc * 64);
+          tma_load_2d(sa + 8192, &tmA, &bar_full[s], a_c + m0 + 64, a_r + kc * 64);
+        } else {     // stored [M rows, K cols]: one box of [128 rows x 64 k]
+          tma_load_2d(sa, &tmA, &bar_full[s], a_c + kc * 64, a_r + m0);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_2d(sb + c * 8192, &tmB, &bar_full[s], b_c + n0 + c * 64, b_r + kc * 64);
+        } else {
+          tma_load_2d(sb, &tmB, &bar_full[s], b_c + kc * 64, b_r + n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, A_MN, B_MN);
+      for (int kc = kc_begin, it = 0; kc < kc_end; ++kc, ++it) {
+        const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
+        mbar_wait(&bar_full[s], ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + s * STAGE), b0 = a0 + A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ad = A_MN ? umma_desc_sw128(a0 + ks * 2048, 8192, 1024) : umma_desc_sw128(a0 + ks * 32, 16, 1024);
+          const uint64_t bd = B_MN ? umma_desc_sw128(b0 + ks * 2048, 8192, 1024) : umma_desc_sw128(b0 + ks * 32, 16, 1024);
+          umma_ss(tmem, ad, bd, idesc, (it | ks) != 0);
+        }
+        umma_commit(&bar_empty[s]);
+      }
+      umma_commit(&bar_acc);
+    }
+  } else {
+    // ------------------------------------------------ epilogue: thread = output row
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int m = m0 + row;
+    mbar_wait(&bar_acc, 0);
+    tc_fence_after();
+    const bool row_ok = m < p.M;
+    const long long c_base = p.c_off0 + (long long)outer * p.c_oo + (long long)in * p.c_oi + (long long)m * p.ldc;
+    float rm = 1.f;
+    if (p.rowmask && row_ok) rm = p.rowmask[p.rowmask_off0 + (long long)outer * p.rowmask_oo + m] ? 1.f : 0.f;
+    const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    const uint32_t drop_thr = p.drop_p > 0.f ? (uint32_t)(p.drop_p * 4294967296.0) : 0u;
+    const unsigned long long seed_eff = p.seed + ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t raw[32];
+      tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + c, raw);
+      tmem_ld_wait();
+      if (!row_ok || n0 + c >= p.N) continue;
+      float x[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) x[q] = __uint_as_float(raw[q]) * p.alpha;
+      if (p.bias) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c + q]);
+          x[q] += b4.x; x[q + 1] += b4.y; x[q + 2] += b4.z; x[q + 3] += b4.w;
+        }
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) x[q] = fmaxf(x[q], 0.f);
+      } else if (p.act == 2) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) x[q] = 0.5f * x[q] * (1.f + erff(x[q] * 0.70710678118654752f));
+      }
+      if (p.drop_p > 0.f) {
+        // one Philox call per 4 consecutive output elements; element index = c_base + column
+        const unsigned long long e0 = p.drop_offset + (unsigned long long)(c_base + n0 + c);
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          const uint4 r = philox4x32(seed_eff, (e0 + q) >> 2);
+          x[q + 0] = (r.x >= drop_thr) ? x[q + 0] * keep_scale : 0.f;
+          x[q + 1] = (r.y >= drop_thr) ? x[q + 1] * keep_scale : 0.f;
+          x[q + 2] = (r.z >= drop_thr) ? x[q + 2] * keep_scale : 0.f;
+          x[q + 3] = (r.w >= drop_thr) ? x[q + 3] * keep_scale : 0.f;
+        }
+      }
+      const bool full = (n0 + c + 32 <= p.N);
+      if (p.gate) {
+        const __nv_bfloat16* gp = p.gate + c_base + n0 + c;
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          if (n0 + c + q < p.N) x[q] = (__bfloat162float(gp[q]) != 0.f) ? x[q] * p.gate_scale : 0.f;
+      }
+      if (p.residual) {
+        const __nv_bfloat16* rp_ = p.residual + c_base + n0 + c;
+        if (full) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(rp_ + q);
+            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __bfloat1622float2(r2[t]);
+              x[q + 2 * t] += f.x;
+              x[q + 2 * t + 1] += f.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (n0 + c + q < p.N) x[q] += __bfloat162float(rp_[q]);
+        }
+      }
+      if (p.rowmask) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) x[q] *= rm;
+      }
+      if (p.out_mode == 0) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.C) + c_base + n0 + c;
+        if (full) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) {
+            uint4 w;
+            w.x = pack_bf16(x[q], x[q + 1]);
+            w.y = pack_bf16(x[q + 2], x[q + 3]);
+            w.z = pack_bf16(x[q + 4], x[q + 5]);
+            w.w = pack_bf16(x[q + 6], x[q + 7]);
+            *reinterpret_cast<uint4*>(o + q) = w;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (n0 + c + q < p.N) o[q] = __float2bfloat16(x[q]);
+        }
+      } else {
+        float* o = reinterpret_cast<float*>(p.C) + c_base + n0 + c;
+        if (p.out_mode == 1) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (n0 + c + q < p.N) atomicAdd(o + q, x[q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (n0 + c + q < p.N) o[q] = x[q];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, BN < 32 ? 32 : BN);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int batch, cudaStream_t st) {
+  constexpr int NSTAGE = 4;
+  const int smem = NSTAGE * (128 * 128 + BN * 128) + 1024;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, NSTAGE>;
+  RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid((p.N + BN - 1) / BN, ((p.M + 127) / 128) * p.split_k, batch);
+  kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+}  // namespace rp
+
+using namespace rp;
+
+// Flat C view of the parameter block (mirrors rp::GemmParams; see include/rp_b200.h rp_gemm_desc).
+struct rp_gemm_desc {
+  const void* A; long long a_rows, a_cols, lda; int a_mn;
+  const void* B; long long b_rows, b_cols, ldb; int b_mn;
+  int M, N, K, batch, inner;
+  int a_r0, a_ro, a_ri, a_c0, a_co, a_ci;
+  int b_r0, b_ro, b_ri, b_c0, b_co, b_ci;
+  void* C; long long ldc, c_off0, c_oo, c_oi; int out_mode;
+  float alpha; const float* bias; int act;
+  const void* residual; const uint8_t* rowmask; long long rowmask_off0, rowmask_oo;
+  float drop_p; unsigned long long seed, drop_offset; const unsigned long long* seed_ptr;
+  int split_k;
+  const void* gate; float gate_scale;
+};
+
+RP_API int rp_gemm(const rp_gemm_desc* g, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!g || !g->A || !g->B || !g->C) return RP_EINVAL;
+  if (g->M <= 0 || g->N <= 0 || g->K <= 0 || g->batch <= 0 || g->inner <= 0) return RP_ESHAPE;
+  if (g->split_k < 1 || (g->split_k > 1 && g->out_mode != 1)) return RP_EINVAL;
+  if (g->out_mode == 0 && (g->ldc % 8 != 0)) return RP_EALIGN;
+  GemmParams p;
+  p.M = g->M; p.N = g->N; p.K = g->K; p.inner = g->inner;
+  p.a_r0 = g->a_r0; p.a_ro = g->a_ro; p.a_ri = g->a_ri; p.a_c0 = g->a_c0; p.a_co = g->a_co; p.a_ci = g->a_ci;
+  p.b_r0 = g->b_r0; p.b_ro = g->b_ro; p.b_ri = g->b_ri; p.b_c0 = g->b_c0; p.b_co = g->b_co; p.b_ci = g->b_ci;
+  p.C = g->C; p.ldc = g->ldc; p.c_off0 = g->c_off0; p.c_oo = g->c_oo; p.c_oi = g->c_oi; p.out_mode = g->out_mode;
+  p.alpha = g->alpha; p.bias = g->bias; p.act = g->act;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(g->residual);
+  p.rowmask = g->rowmask; p.rowmask_off0 = g->rowmask_off0; p.rowmask_oo = g->rowmask_oo;
+  p.drop_p = g->drop_p; p.seed = g->seed; p.drop_offset = g->drop_offset; p.seed_ptr = g->seed_ptr; p.split_k = g->split_k;
+  p.gate = reinterpret_cast<const __nv_bfloat16*>(g->gate); p.gate_scale = g->gate_scale;
+  CUtensorMap tmA, tmB;
+  int rc;
+  // K-major operand: box [128 (or BN) rows x 64 cols]; MN-major operand: box [64 k-rows x 64 cols]
+  const int bn = (g->N <= 64) ? 64 : 128;
+  if ((rc = make_tmap_bf16(&tmA, g->A, g->a_rows, g->a_cols, g->lda, g->a_mn ? 64 : 128)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmB, g->B, g->b_rows, g->b_cols, g->ldb, g->b_mn ? 64 : bn)) != RP_OK) return rc;
+#define RP_GEMM_CASE(BN_, AMN_, BMN_) return launch_gemm<BN_, AMN_, BMN_>(tmA, tmB, p, g->batch, stream)
+  if (bn == 64) {
+    if (!g->a_mn && !g->b_mn) RP_GEMM_CASE(64, false, false);
+    if (!g->a_mn && g->b_mn) RP_GEMM_CASE(64, false, true);
+    if (g->a_mn && !g->b_mn) RP_GEMM_CASE(64, true, false);
+    RP_GEMM_CASE(64, true, true);
+  } else {
+    if (!g->a_mn && !g->b_mn) RP_GEMM_CASE(128, false, false);
+    if (!g->a_mn && g->b_mn) RP_GEMM_CASE(128, false, true);
+    if (g->a_mn && !g->b_mn) RP_GEMM_CASE(128, true, false);
+    RP_GEMM_CASE(128, true, true);
+  }
+#undef RP_GEMM_CASE
+}

@@ -1,0 +1,447 @@
+"""Execution engine of the SASRec hot path on B200: owns the flat parameter / gradient / optimizer buffers and the
+activation workspace, and sequences the hand-written sm_100a kernels (librp_b200.so, include/rp_b200.h) for
+
+    train step  = batch prep -> embedding -> N x [LN, QKV GEMMs, fused attention, out-proj, LN, FFN] -> final LN with
+                  valid-target compaction -> fused CE head  -> full backward -> (gradient all-reduce) -> Adam
+    predict     = same body without dropout -> last hidden state -> fused score + seen-mask + top-K head
+
+It is the host-side counterpart of the reference's torch modules (replay/nn/sequential/sasrec/model.py:85-113,258-307 and
+replay/models/nn/sequential/sasrec/model.py:159-180); the ``replay_b200.nn`` / ``replay_b200.models`` classes that mirror
+the reference API delegate to it.  torch supplies device memory, streams, CUDA graphs and the NCCL process group only.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+
+import torch
+
+from ._lib import AttnDesc, GemmDesc, check, lib
+
+
+@dataclass
+class EncoderConfig:
+    n_items: int
+    d: int
+    n_heads: int
+    n_blocks: int
+    max_len: int
+    dropout: float = 0.0
+    variant: str = "new"  # "new": replay.nn.sequential.SasRec ; "legacy": replay.models.nn.sequential.SasRecModel
+    lnf_eps: float | None = None
+
+    def __post_init__(self):
+        if self.variant not in ("new", "legacy"):
+            raise ValueError(f"unknown variant {self.variant}")
+        if self.d % self.n_heads:
+            raise ValueError("d must be divisible by n_heads")
+        if self.d not in (64, 128, 256, 512):
+            raise ValueError("hidden size must be one of 64/128/256/512 (kernel tile constraint)")
+        if self.d // self.n_heads not in (64, 128):
+            raise ValueError("head_dim must be 64 or 128 (tcgen05 128B-swizzle tile constraint)")
+        if self.lnf_eps is None:
+            # new: torch.nn.LayerNorm default (nn/sequential/sasrec/model.py:248); legacy: 1e-8 (sasrec/model.py:463)
+            self.lnf_eps = 1e-5 if self.variant == "new" else 1e-8
+
+    @property
+    def pad_id(self) -> int:
+        return self.n_items
+
+
+_BLOCK_PARAMS = ("ln1_w", "ln1_b", "in_w", "in_b", "out_w", "out_b", "ln2_w", "ln2_b", "w1", "b1", "w2", "b2")
+
+
+def _ru(x, m):
+    return (x + m - 1) // m * m
+
+
+class SasRecEngine:
+    def __init__(self, cfg: EncoderConfig, max_batch: int, seq_len: int, device="cuda", seed: int = 0,
+                 with_grad: bool = True):
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        self.B, self.L = max_batch, seq_len
+        if seq_len > cfg.max_len:
+            raise ValueError(f"sequence length {seq_len} exceeds max_len {cfg.max_len}")
+        if cfg.variant == "legacy" and seq_len != cfg.max_len:
+            raise ValueError("legacy SASRec needs seq_len == max_len (sasrec/model.py:528-529)")
+        if seq_len > 256:
+            raise ValueError("fused attention kernel supports seq_len <= 256")
+        self.T = max_batch * seq_len
+        self.Lp = _ru(seq_len, 64)
+        self.with_grad = with_grad
+        self.lib = lib()
+        d, I = cfg.d, cfg.n_items
+        # ---------------------------------------------------------------- flat parameter layout
+        shapes = [("item_emb", (I + 1, d)), ("pos_emb", (cfg.max_len, d))]
+        for i in range(cfg.n_blocks):
+            shapes += [(f"b{i}.ln1_w", (d,)), (f"b{i}.ln1_b", (d,)), (f"b{i}.in_w", (3 * d, d)), (f"b{i}.in_b", (3 * d,)),
+                       (f"b{i}.out_w", (d, d)), (f"b{i}.out_b", (d,)), (f"b{i}.ln2_w", (d,)), (f"b{i}.ln2_b", (d,)),
+                       (f"b{i}.w1", (d, d)), (f"b{i}.b1", (d,)), (f"b{i}.w2", (d, d)), (f"b{i}.b2", (d,))]
+        shapes += [("lnf_w", (d,)), ("lnf_b", (d,))]
+        self.layout = {}
+        off = 0
+        for name, shp in shapes:
+            n = math.prod(shp)
+            self.layout[name] = (off, shp)
+            off = _ru(off + n, 64)
+        self.n_flat = off
+        f32 = dict(device=self.dev, dtype=torch.float32)
+        self.p32 = torch.zeros(off, **f32)
+        self.p16 = torch.zeros(off, device=self.dev, dtype=torch.bfloat16)
+        self.params = {k: self.p32[o:o + math.prod(s)].view(s) for k, (o, s) in self.layout.items()}
+        self.params16 = {k: self.p16[o:o + math.prod(s)].view(s) for k, (o, s) in self.layout.items()}
+        if with_grad:
+            self.g32 = torch.zeros(off, **f32)
+            self.adam_m = torch.zeros(off, **f32)
+            self.adam_v = torch.zeros(off, **f32)
+            self.grads = {k: self.g32[o:o + math.prod(s)].view(s) for k, (o, s) in self.layout.items()}
+            self.lr = torch.full((1,), 1e-3, **f32)
+            self.step_count = torch.zeros(1, device=self.dev, dtype=torch.int32)
+        self.rng_counter = torch.zeros(1, device=self.dev, dtype=torch.int64)
+        self.seed = seed & 0xFFFFFFFFFFFF
+        self.training = with_grad
+        self._alloc_workspace()
+        self.init_parameters(seed)
+
+    # ------------------------------------------------------------------------------------------------ parameters
+    def init_parameters(self, seed: int = 0):
+        """Reference-style init: xavier_normal_ on >=2-D tensors, LN (1, 0), biases zero / U(+-1/sqrt(fan_in)) for the
+        conv layers, pad row zero (new path, nn/embedding.py:198-200).  Weights are normally loaded from a reference
+        state_dict instead (``load_canonical``)."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        d = self.cfg.d
+        with torch.no_grad():
+            for name, (o, shp) in self.layout.items():
+                p = self.params[name]
+                if len(shp) == 2:
+                    std = math.sqrt(2.0 / (shp[0] + shp[1]))
+                    p.copy_((torch.randn(shp, generator=g) * std).to(self.dev))
+                elif name.endswith(("ln1_w", "ln2_w", "lnf_w")):
+                    p.fill_(1.0)
+                elif name.endswith((".b1", ".b2")):
+                    bound = 1.0 / math.sqrt(d)
+                    p.copy_(((torch.rand(shp, generator=g) * 2 - 1) * bound).to(self.dev))
+                else:
+                    p.zero_()
+            if self.cfg.variant == "new":
+                self.params["item_emb"][self.cfg.pad_id].zero_()
+        self.refresh_shadow()
+
+    def refresh_shadow(self):
+        check(self.lib.rp_cast_bf16(self.p32.data_ptr(), self.p16.data_ptr(), self.n_flat, self._stream()), "rp_cast_bf16")
+
+    def load_canonical(self, P: dict):
+        """Copy weights from the canonical dict used by oracle/ (keys item_emb, pos_emb, blocks[i][...], lnf_w, lnf_b)."""
+        with torch.no_grad():
+            self.params["item_emb"].copy_(P["item_emb"].to(self.dev, torch.float32))
+            self.params["pos_emb"].copy_(P["pos_emb"].to(self.dev, torch.float32))
+            for i, blk in enumerate(P["blocks"]):
+                for k in _BLOCK_PARAMS:
+                    self.params[f"b{i}.{k}"].copy_(blk[k].to(self.dev, torch.float32))
+            self.params["lnf_w"].copy_(P["lnf_w"].to(self.dev, torch.float32))
+            self.params["lnf_b"].copy_(P["lnf_b"].to(self.dev, torch.float32))
+        self.refresh_shadow()
+
+    def export_canonical(self, source=None) -> dict:
+        src = self.params if source is None else source
+        P = {"item_emb": src["item_emb"].detach().cpu().clone(), "pos_emb": src["pos_emb"].detach().cpu().clone(),
+             "blocks": [], "lnf_w": src["lnf_w"].detach().cpu().clone(), "lnf_b": src["lnf_b"].detach().cpu().clone()}
+        for i in range(self.cfg.n_blocks):
+            P["blocks"].append({k: src[f"b{i}.{k}"].detach().cpu().clone() for k in _BLOCK_PARAMS})
+        return P
+
+    # ------------------------------------------------------------------------------------------------ workspace
+    def _alloc_workspace(self):
+        cfg, T, d, dev = self.cfg, self.T, self.cfg.d, self.dev
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        f32 = dict(device=dev, dtype=torch.float32)
+        i32 = dict(device=dev, dtype=torch.int32)
+        BH = self.B * cfg.n_heads
+        self.ids32 = torch.zeros(T, **i32)
+        self.pad_u8 = torch.zeros(T, device=dev, dtype=torch.uint8)
+        self.in_ids = torch.zeros(T, device=dev, dtype=torch.int64)
+        self.in_pad = torch.zeros(T, device=dev, dtype=torch.bool)
+        self.in_labels = torch.zeros(T, device=dev, dtype=torch.int64)
+        self.in_tmask = torch.zeros(T, device=dev, dtype=torch.bool)
+        self.valid_idx = torch.zeros(T, **i32)
+        self.labels_c = torch.zeros(T, **i32)
+        self.n_valid = torch.zeros(1, **i32)
+        nb = cfg.n_blocks
+        self.x = [torch.zeros(T, d, **bf) for _ in range(nb + 1)]
+        self.act = []
+        for _ in range(nb):
+            a = {k: torch.zeros(T, d, **bf) for k in ("q_in", "Q", "O", "h", "y", "u")}
+            a["KV"] = torch.zeros(T, 2 * d, **bf)
+            for k in ("mean1", "rstd1", "mean2", "rstd2"):
+                a[k] = torch.zeros(T, **f32)
+            if self.with_grad:
+                a["P"] = torch.zeros(BH, self.Lp, self.Lp, **bf)
+                a["inv_sum"] = torch.zeros(BH, self.Lp, **f32)
+            self.act.append(a)
+        self.hc = torch.zeros(T, d, **bf)
+        self.meanf = torch.zeros(T, **f32)
+        self.rstdf = torch.zeros(T, **f32)
+        self.hq = torch.zeros(self.B, d, **bf)
+        self.last_idx = (torch.arange(self.B, device=dev, dtype=torch.int32) * self.L + (self.L - 1)).contiguous()
+        if self.with_grad:
+            from .ops import CEHeadState
+
+            self.ce = CEHeadState(T, cfg.n_items, d, dev)
+            self.s = {k: torch.zeros(T, d, **bf) for k in ("dhc", "dxa", "dxb", "d_t", "du", "dy", "dh", "d_o", "dQ", "dq_in", "tmp")}
+            self.s["dKV"] = torch.zeros(T, 2 * d, **bf)
+            self.s["dpd"] = torch.zeros(BH, self.Lp, self.Lp, **bf)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    # ------------------------------------------------------------------------------------------------ kernel helpers
+    def _gemm(self, A, B, C, M, N, K, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, rowmask=None,
+              drop_p=0.0, drop_site=0, out_mode=0, split_k=1, gate=None, gate_scale=1.0, alpha=1.0, batch=1, inner=1,
+              a_off=(0, 0, 0, 0, 0, 0), b_off=(0, 0, 0, 0, 0, 0), c_geom=None, rowmask_oo=0):
+        g = GemmDesc()
+        g.A, g.a_rows, g.a_cols, g.lda, g.a_mn = A.data_ptr(), A.shape[0], A.shape[1], A.stride(0), int(a_mn)
+        g.B, g.b_rows, g.b_cols, g.ldb, g.b_mn = B.data_ptr(), B.shape[0], B.shape[1], B.stride(0), int(b_mn)
+        g.M, g.N, g.K, g.batch, g.inner = M, N, K, batch, inner
+        g.a_r0, g.a_ro, g.a_ri, g.a_c0, g.a_co, g.a_ci = a_off
+        g.b_r0, g.b_ro, g.b_ri, g.b_c0, g.b_co, g.b_ci = b_off
+        g.C = C.data_ptr()
+        if c_geom is None:
+            g.ldc, g.c_off0, g.c_oo, g.c_oi = C.stride(0), 0, 0, 0
+        else:
+            g.ldc, g.c_off0, g.c_oo, g.c_oi = c_geom
+        g.out_mode = out_mode
+        g.alpha = alpha
+        g.bias = None if bias is None else bias.data_ptr()
+        g.act = act
+        g.residual = None if residual is None else residual.data_ptr()
+        g.rowmask = None if rowmask is None else rowmask.data_ptr()
+        g.rowmask_off0, g.rowmask_oo = 0, rowmask_oo
+        g.drop_p = drop_p
+        g.seed = self.seed
+        g.drop_offset = drop_site << 40
+        g.seed_ptr = self.rng_counter.data_ptr()
+        g.split_k = split_k
+        g.gate = None if gate is None else gate.data_ptr()
+        g.gate_scale = gate_scale
+        check(self.lib.rp_gemm(ctypes.byref(g), self._stream()), "rp_gemm")
+
+    def _wgrad(self, dY, X, dW, n_out, n_in):
+        """dW[n_out, n_in] += dY[T, n_out]^T . X[T, n_in]  (both operands MN-major, split-K, fp32 atomics)."""
+        tiles = ((n_out + 127) // 128) * ((n_in + 127) // 128 if n_in > 64 else 1)
+        chunks = (self.T + 63) // 64
+        split = max(1, min(chunks, (2 * 148 + tiles - 1) // tiles))
+        self._gemm(dY, X, dW, n_out, n_in, self.T, a_mn=True, b_mn=True, out_mode=1, split_k=split)
+
+    def _colsum(self, dY, db):
+        check(self.lib.rp_colsum(dY.data_ptr(), dY.shape[0], dY.shape[1], dY.stride(0), db.data_ptr(), self._stream()),
+              "rp_colsum")
+
+    def _ln_fwd(self, x, w, b, eps, y, mean, rstd, n_rows, gather=None, n_rows_dev=None):
+        check(self.lib.rp_layernorm_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), eps, n_rows, self.cfg.d,
+                                        None if n_rows_dev is None else n_rows_dev.data_ptr(),
+                                        None if gather is None else gather.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                        rstd.data_ptr(), self._stream()), "rp_layernorm_fwd")
+
+    def _ln_bwd(self, dy, x, w, mean, rstd, dx, dw, db, n_rows, gather=None, n_rows_dev=None, add_to=None):
+        check(self.lib.rp_layernorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                        n_rows, self.cfg.d, None if n_rows_dev is None else n_rows_dev.data_ptr(),
+                                        None if gather is None else gather.data_ptr(),
+                                        None if add_to is None else add_to.data_ptr(), dx.data_ptr(), dw.data_ptr(),
+                                        db.data_ptr(), self._stream()), "rp_layernorm_bwd")
+
+    def _site(self, blk, k):
+        return 1 + blk * 8 + k
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def set_batch(self, ids, pad_mask, labels=None, target_mask=None):
+        """Stage one batch ([B, L] int64 ids, bool masks) into the engine's static input buffers (device copies)."""
+        B, L = ids.shape
+        if L != self.L or B > self.B:
+            raise ValueError(f"batch shape {tuple(ids.shape)} does not fit engine ({self.B}, {self.L})")
+        self.cur_B = B
+        n = B * L
+        self.in_ids[:n].copy_(ids.reshape(-1), non_blocking=True)
+        self.in_pad[:n].copy_(pad_mask.reshape(-1), non_blocking=True)
+        if labels is not None:
+            self.in_labels[:n].copy_(labels.reshape(-1), non_blocking=True)
+            self.in_tmask[:n].copy_(target_mask.reshape(-1), non_blocking=True)
+        if n < self.T:
+            self.in_pad[n:].zero_()
+            self.in_tmask[n:].zero_()
+
+    def _prepare(self, with_targets: bool):
+        cfg = self.cfg
+        check(self.lib.rp_prepare_batch(self.in_ids.data_ptr(), self.in_pad.data_ptr(),
+                                        self.in_labels.data_ptr() if with_targets else None,
+                                        self.in_tmask.data_ptr() if with_targets else None, self.T, cfg.pad_id, cfg.n_items,
+                                        self.ids32.data_ptr(), self.valid_idx.data_ptr(), self.labels_c.data_ptr(),
+                                        self.n_valid.data_ptr(), self._stream()), "rp_prepare_batch")
+
+    def _body_forward(self, training: bool):
+        cfg, T, d, L = self.cfg, self.T, self.cfg.d, self.L
+        p16, prm = self.params16, self.params
+        legacy = cfg.variant == "legacy"
+        drop = cfg.dropout if training else 0.0
+        pad = self.in_pad
+        pos0 = 0 if legacy else cfg.max_len - L
+        check(self.lib.rp_embed_fwd(p16["item_emb"].data_ptr(), prm["pos_emb"].data_ptr(), self.ids32.data_ptr(),
+                                    pad.data_ptr(), T, L, d, pos0, math.sqrt(d), int(legacy), drop, self.seed, 0,
+                                    self.rng_counter.data_ptr(), self.x[0].data_ptr(), self._stream()), "rp_embed_fwd")
+        H, hd = cfg.n_heads, d // cfg.n_heads
+        for i in range(cfg.n_blocks):
+            a, x = self.act[i], self.x[i]
+            w = lambda k: p16[f"b{i}.{k}"]  # noqa: E731
+            f = lambda k: prm[f"b{i}.{k}"]  # noqa: E731
+            self._ln_fwd(x, f("ln1_w"), f("ln1_b"), 1e-8, a["q_in"], a["mean1"], a["rstd1"], T)
+            in_w, in_b = w("in_w"), f("in_b")
+            self._gemm(a["q_in"], in_w[:d], a["Q"], T, d, d, bias=in_b[:d])
+            self._gemm(x, in_w[d:], a["KV"], T, 2 * d, d, bias=in_b[d:])
+            ad = AttnDesc()
+            ad.q, ad.q_rows, ad.q_cols, ad.ldq, ad.q_c0 = a["Q"].data_ptr(), T, d, d, 0
+            ad.k, ad.k_rows, ad.k_cols, ad.ldk, ad.k_c0 = a["KV"].data_ptr(), T, 2 * d, 2 * d, 0
+            ad.v, ad.v_rows, ad.v_cols, ad.ldv, ad.v_c0 = a["KV"].data_ptr(), T, 2 * d, 2 * d, d
+            ad.B, ad.H, ad.L, ad.head_dim = self.B, H, L, hd
+            ad.causal, ad.mask_pad_keys = 1, int(not legacy)
+            ad.pad_mask = pad.data_ptr()
+            ad.out, ad.ldo = a["O"].data_ptr(), d
+            if training and self.with_grad:
+                ad.p_save, ad.inv_sum = a["P"].data_ptr(), a["inv_sum"].data_ptr()
+            else:
+                ad.p_save, ad.inv_sum = None, None
+            ad.drop_p, ad.seed, ad.drop_off, ad.seed_ptr = drop, self.seed, self._site(i, 0) << 40, self.rng_counter.data_ptr()
+            check(self.lib.rp_attn_fwd(ctypes.byref(ad), self._stream()), "rp_attn_fwd")
+            self._gemm(a["O"], w("out_w"), a["h"], T, d, d, bias=f("out_b"), residual=a["q_in"])
+            self._ln_fwd(a["h"], f("ln2_w"), f("ln2_b"), 1e-8, a["y"], a["mean2"], a["rstd2"], T)
+            self._gemm(a["y"], w("w1"), a["u"], T, d, d, bias=f("b1"), act=1, drop_p=drop, drop_site=self._site(i, 1))
+            self._gemm(a["u"], w("w2"), self.x[i + 1], T, d, d, bias=f("b2"), drop_p=drop, drop_site=self._site(i, 2),
+                       residual=a["y"], rowmask=pad if legacy else None)
+
+    def forward_train(self):
+        """Loss of the staged batch (device fp32 [2] view: mean CE over the valid targets, 1/n_valid)."""
+        cfg, T = self.cfg, self.T
+        self._prepare(True)
+        self._body_forward(True)
+        self._ln_fwd(self.x[-1], self.params["lnf_w"], self.params["lnf_b"], cfg.lnf_eps, self.hc, self.meanf, self.rstdf, T,
+                     gather=self.valid_idx, n_rows_dev=self.n_valid)
+        from .ops import ce_head_fwd
+
+        return ce_head_fwd(self.ce, self.hc, self.params16["item_emb"][: cfg.n_items], self.labels_c, self.n_valid)
+
+    # ------------------------------------------------------------------------------------------------ backward
+    def backward(self):
+        cfg, T, d, L = self.cfg, self.T, self.cfg.d, self.L
+        p16, prm, G, s = self.params16, self.params, self.grads, self.s
+        legacy = cfg.variant == "legacy"
+        drop = cfg.dropout
+        ks = 1.0 / (1.0 - drop) if drop > 0 else 1.0
+        H, hd, Lp = cfg.n_heads, d // cfg.n_heads, self.Lp
+        BH = self.B * H
+        st = self._stream
+        from .ops import ce_head_bwd
+
+        ce_head_bwd(self.ce, self.hc, p16["item_emb"][: cfg.n_items], self.labels_c, self.n_valid, s["dhc"], G["item_emb"])
+        dx = s["dxa"]
+        dx.zero_()
+        self._ln_bwd(s["dhc"], self.x[-1], prm["lnf_w"], self.meanf, self.rstdf, dx, G["lnf_w"], G["lnf_b"], T,
+                     gather=self.valid_idx, n_rows_dev=self.n_valid)
+        other = s["dxb"]
+        for i in reversed(range(cfg.n_blocks)):
+            a, x = self.act[i], self.x[i]
+            w = lambda k: p16[f"b{i}.{k}"]  # noqa: E731
+            f = lambda k: prm[f"b{i}.{k}"]  # noqa: E731
+            g = lambda k: G[f"b{i}.{k}"]  # noqa: E731
+            dz = dx
+            if legacy:  # x_next = (...) * pad   (sasrec/model.py:441)
+                check(self.lib.rp_dropout_bwd(dz.data_ptr(), dz.data_ptr(), T, d, self.in_pad.data_ptr(), 0.0, 0, 0, None, st()),
+                      "rp_dropout_bwd")
+            if drop > 0:
+                check(self.lib.rp_dropout_bwd(dz.data_ptr(), s["d_t"].data_ptr(), T, d, None, drop, self.seed,
+                                              self._site(i, 2) << 40, self.rng_counter.data_ptr(), st()), "rp_dropout_bwd")
+                d_t = s["d_t"]
+            else:
+                d_t = dz
+            # ---- FFN backward
+            self._wgrad(d_t, a["u"], g("w2"), d, d)
+            self._colsum(d_t, g("b2"))
+            self._gemm(d_t, w("w2"), s["du"], T, d, d, b_mn=True, gate=a["u"], gate_scale=ks)
+            self._wgrad(s["du"], a["y"], g("w1"), d, d)
+            self._colsum(s["du"], g("b1"))
+            self._gemm(s["du"], w("w1"), s["dy"], T, d, d, b_mn=True, residual=dz)
+            self._ln_bwd(s["dy"], a["h"], f("ln2_w"), a["mean2"], a["rstd2"], s["dh"], g("ln2_w"), g("ln2_b"), T)
+            # ---- out projection
+            self._gemm(s["dh"], w("out_w"), s["d_o"], T, d, d, b_mn=True)
+            self._wgrad(s["dh"], a["O"], g("out_w"), d, d)
+            self._colsum(s["dh"], g("out_b"))
+            # ---- attention backward (batched over (b, h))
+            KV, Q, P, dpd = a["KV"], a["Q"], a["P"].view(BH * Lp, Lp), s["dpd"].view(BH * Lp, Lp)
+            # dPd = dO . V^T
+            self._gemm(s["d_o"], KV, dpd, L, L, hd, batch=BH, inner=H, a_off=(0, L, 0, 0, 0, hd), b_off=(0, L, 0, d, 0, hd),
+                       c_geom=(Lp, 0, H * Lp * Lp, Lp * Lp))
+            check(self.lib.rp_attn_softmax_bwd(P.data_ptr(), dpd.data_ptr(), a["inv_sum"].data_ptr(), BH, L,
+                                               1.0 / math.sqrt(hd), drop, self.seed, self._site(i, 0) << 40,
+                                               self.rng_counter.data_ptr(), st()), "rp_attn_softmax_bwd")
+            # dQ = dS . K      (A = dS [BH*Lp, Lp] K-major, B = K MN-major)
+            self._gemm(dpd, KV, s["dQ"], L, hd, L, b_mn=True, batch=BH, inner=H, a_off=(0, H * Lp, Lp, 0, 0, 0),
+                       b_off=(0, L, 0, 0, 0, hd), c_geom=(d, 0, L * d, hd))
+            # dK = dS^T . Q    (A = dS MN-major, B = Q MN-major)
+            self._gemm(dpd, Q, s["dKV"], L, hd, L, a_mn=True, b_mn=True, batch=BH, inner=H, a_off=(0, H * Lp, Lp, 0, 0, 0),
+                       b_off=(0, L, 0, 0, 0, hd), c_geom=(2 * d, 0, L * 2 * d, hd))
+            # dV = Pd^T . dO
+            self._gemm(P, s["d_o"], s["dKV"], L, hd, L, a_mn=True, b_mn=True, batch=BH, inner=H,
+                       a_off=(0, H * Lp, Lp, 0, 0, 0), b_off=(0, L, 0, 0, 0, hd), c_geom=(2 * d, d, L * 2 * d, hd))
+            # ---- projections
+            in_w = w("in_w")
+            self._gemm(s["dQ"], in_w[:d], s["dq_in"], T, d, d, b_mn=True, residual=s["dh"])
+            self._wgrad(s["dQ"], a["q_in"], g("in_w")[:d], d, d)
+            self._colsum(s["dQ"], g("in_b")[:d])
+            self._ln_bwd(s["dq_in"], x, f("ln1_w"), a["mean1"], a["rstd1"], s["tmp"], g("ln1_w"), g("ln1_b"), T)
+            self._gemm(s["dKV"], in_w[d:], other, T, d, 2 * d, b_mn=True, residual=s["tmp"])
+            self._wgrad(s["dKV"], x, g("in_w")[d:], 2 * d, d)
+            self._colsum(s["dKV"], g("in_b")[d:])
+            dx, other = other, dx
+        pos0 = 0 if legacy else cfg.max_len - L
+        check(self.lib.rp_embed_bwd(dx.data_ptr(), self.ids32.data_ptr(), self.in_pad.data_ptr(), self.B, L, d, cfg.pad_id,
+                                    pos0, math.sqrt(d), int(legacy), drop, self.seed, 0, self.rng_counter.data_ptr(),
+                                    G["item_emb"].data_ptr(), G["pos_emb"].data_ptr(), st()), "rp_embed_bwd")
+
+    def optimizer_step(self, grad_scale: float = 1.0, beta1=0.9, beta2=0.98, eps=1e-8):
+        """torch.optim.Adam(lr, betas=(0.9, 0.98)) (optimizer_factory.py:56-63,79-80) on the flat buffers; also refreshes
+        the bf16 shadow weights and zeroes the gradients."""
+        check(self.lib.rp_adam_step(self.p32.data_ptr(), self.g32.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr(),
+                                    self.p16.data_ptr(), self.n_flat, self.lr.data_ptr(), self.step_count.data_ptr(), beta1,
+                                    beta2, eps, grad_scale, None, 1, self._stream()), "rp_adam_step")
+
+    def tick_rng(self):
+        check(self.lib.rp_counter_add(self.rng_counter.data_ptr(), 0x9E3779B97F4A7C15 & 0xFFFFFFFFFFFF, self._stream()),
+              "rp_counter_add")
+
+    def train_step(self, all_reduce=None):
+        """forward + backward + (optional gradient all-reduce callback on the flat fp32 gradient) + Adam."""
+        self.tick_rng()
+        loss = self.forward_train()
+        self.backward()
+        scale = 1.0
+        if all_reduce is not None:
+            scale = all_reduce(self.g32)
+        self.optimizer_step(grad_scale=scale)
+        return loss
+
+    # ------------------------------------------------------------------------------------------------ inference
+    def forward_last_hidden(self):
+        """Eval-mode body (no dropout) -> final LayerNorm of the LAST position of every sequence -> self.hq bf16 [B, d]
+        (SasRec.forward_inference, nn/sequential/sasrec/model.py:292-307 ; legacy get_query_embeddings, model.py:157)."""
+        self._prepare(False)
+        self._body_forward(False)
+        self._ln_fwd(self.x[-1], self.params["lnf_w"], self.params["lnf_b"], self.cfg.lnf_eps, self.hq, self.meanf, self.rstdf,
+                     self.B, gather=self.last_idx)
+        return self.hq
+
+    def forward_hidden_all(self):
+        """Eval-mode hidden states of every position, bf16 [T, d] (for parity tests / HiddenStatesCallback)."""
+        self._prepare(False)
+        self._body_forward(False)
+        out = torch.empty(self.T, self.cfg.d, device=self.dev, dtype=torch.bfloat16)
+        self._ln_fwd(self.x[-1], self.params["lnf_w"], self.params["lnf_b"], self.cfg.lnf_eps, out, self.meanf, self.rstdf, self.T)
+        return out

@@ -50,10 +50,11 @@ def test_new_sasrec_matches_reference(golden_dir, name):
     c = torch.from_numpy(z["candidates"])
     torch.testing.assert_close(h[:, -1] @ P["item_emb"][:n_items][c].T, torch.from_numpy(z["cand_logits"]), **TOL)
     # one Adam step (optimizer_factory.py:56-63)
-    a1 = osr.params_from_new_state_dict({k[7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("adam1::")})
-    for p, g, ref in zip(osr.flat_param_list(P), osr.flat_param_list(Gref), osr.flat_param_list(a1)):
-        p1, _, _ = osr.adam_step(p, g, torch.zeros_like(p), torch.zeros_like(p), 1)
-        torch.testing.assert_close(p1, ref, rtol=1e-5, atol=1e-6)
+    if any(k.startswith("adam1::") for k in z.files):
+        a1 = osr.params_from_new_state_dict({k[7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("adam1::")})
+        for p, g, ref in zip(osr.flat_param_list(P), osr.flat_param_list(Gref), osr.flat_param_list(a1)):
+            p1, _, _ = osr.adam_step(p, g, torch.zeros_like(p), torch.zeros_like(p), 1)
+            torch.testing.assert_close(p1, ref, rtol=1e-5, atol=1e-6)
 
 
 def test_legacy_sasrec_matches_reference(golden_dir):

@@ -239,28 +239,52 @@ __global__ void attn_softmax_bwd_kernel(__nv_bfloat16* __restrict__ p_save, __nv
     const int bz = (int)(r / L), i = (int)(r % L);
     const size_t base = ((size_t)bz * Lp + i) * Lp;
     const float inv = inv_sum[(size_t)bz * Lp + i];
+    // lane owns columns [4*lane + 128*k, +4), k = 0,1   (Lp <= 256; columns >= L hold zeros and are never written)
     float P[8], dP[8], keep[8];
     float dot = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int j = k * 32 + lane;
-      P[k] = 0.f; dP[k] = 0.f; keep[k] = 0.f;
-      if (j < L) {
-        P[k] = __bfloat162float(p_save[base + j]) * inv;
-        keep[k] = ksd;
-        if (drop_p > 0.f && !philox_keep(seed, drop_off + base + j, thr)) keep[k] = 0.f;
-        dP[k] = __bfloat162float(dpd[base + j]) * keep[k];
-        dot += P[k] * dP[k];
+    for (int k = 0; k < 2; ++k) {
+      const int j0 = k * 128 + lane * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { P[k * 4 + q] = 0.f; dP[k * 4 + q] = 0.f; keep[k * 4 + q] = 0.f; }
+      if (j0 < L) {
+        const uint2 pr = *reinterpret_cast<const uint2*>(p_save + base + j0);
+        const uint2 dr = *reinterpret_cast<const uint2*>(dpd + base + j0);
+        const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&pr);
+        const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&dr);
+        const float2 p0 = __bfloat1622float2(ph[0]), p1 = __bfloat1622float2(ph[1]);
+        const float2 d0 = __bfloat1622float2(dh[0]), d1 = __bfloat1622float2(dh[1]);
+        const float pv[4] = {p0.x, p0.y, p1.x, p1.y}, dv[4] = {d0.x, d0.y, d1.x, d1.y};
+        uint4 rnd = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (drop_p > 0.f) rnd = philox4x32(seed, (drop_off + base + j0) >> 2);
+        const uint32_t rv[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool in = (j0 + q) < L;
+          keep[k * 4 + q] = (in && rv[q] >= thr) ? ksd : 0.f;
+          P[k * 4 + q] = in ? pv[q] * inv : 0.f;
+          dP[k * 4 + q] = dv[q] * keep[k * 4 + q];
+          dot += P[k * 4 + q] * dP[k * 4 + q];
+        }
       }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int j = k * 32 + lane;
-      if (j < L) {
-        dpd[base + j] = __float2bfloat16(P[k] * (dP[k] - dot) * scale);
-        p_save[base + j] = __float2bfloat16(P[k] * keep[k]);
+    for (int k = 0; k < 2; ++k) {
+      const int j0 = k * 128 + lane * 4;
+      if (j0 < L) {
+        float ds[4], pd[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          ds[q] = P[k * 4 + q] * (dP[k * 4 + q] - dot) * scale;
+          pd[q] = P[k * 4 + q] * keep[k * 4 + q];
+        }
+        uint2 w0, w1;
+        w0.x = pack_bf16(ds[0], ds[1]); w0.y = pack_bf16(ds[2], ds[3]);
+        w1.x = pack_bf16(pd[0], pd[1]); w1.y = pack_bf16(pd[2], pd[3]);
+        *reinterpret_cast<uint2*>(dpd + base + j0) = w0;
+        *reinterpret_cast<uint2*>(p_save + base + j0) = w1;
       }
     }
   }

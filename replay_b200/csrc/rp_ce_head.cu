@@ -485,7 +485,7 @@ RP_API size_t rp_ce_head_workspace(int capacity_tokens, int n_items, int d) {
   (void)d;
   if (capacity_tokens <= 0 || n_items <= 0) return 0;
   const int P = 8;
-  return (size_t)capacity_tokens * P * 2 * sizeof(float2) + (size_t)capacity_tokens * 4 + 1024 + 256;
+  return (size_t)capacity_tokens * P * 2 * sizeof(float2) + (size_t)capacity_tokens * 4 + 4096 + 256;
 }
 
 template <int KCH, int NSTAGE>
@@ -516,7 +516,7 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const int32_t* labe
   float2* part = reinterpret_cast<float2*>(ws);
   float* zt = reinterpret_cast<float*>(ws + (size_t)capacity * 8 * 2 * sizeof(float2));
   float* block_sums = zt + capacity;
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(block_sums + 256);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(block_sums + 1024);
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = make_tmap_bf16(&tmA, hc, capacity, d, d, 128)) != RP_OK) return rc;
@@ -530,7 +530,7 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const int32_t* labe
   if (rc != RP_OK) return rc;
   RP_CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, stream));
   int blocks = (capacity + 7) / 8;
-  if (blocks > 256) blocks = 256;
+  if (blocks > 1024) blocks = 1024;
   ce_finalize_kernel<<<blocks, 256, 0, stream>>>(part, reinterpret_cast<const __nv_bfloat16*>(hc),
                                                  reinterpret_cast<const __nv_bfloat16*>(table), labels, n_valid, P * 2,
                                                  capacity, d, lse, cvec, block_sums, ticket, loss_out);

@@ -29,37 +29,49 @@ prepare_batch_kernel(const int64_t* __restrict__ ids64, const uint8_t* __restric
                      int n_items, int32_t* __restrict__ ids32, int32_t* __restrict__ valid_idx,
                      int32_t* __restrict__ labels_c, int32_t* __restrict__ n_valid) {
   __shared__ int warp_tot[32];
-  __shared__ int block_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) block_base = 0;
-  __syncthreads();
-  for (int base = 0; base < T; base += 1024) {
-    const int t = base + tid;
-    bool valid = false;
-    if (t < T) {
-      const int64_t id = ids64[t];
-      ids32[t] = (pad_mask[t] && id >= 0 && id < n_items) ? (int32_t)id : pad_id;
-      if (target_mask) {
-        const int64_t y = labels64[t];
-        valid = target_mask[t] != 0 && y >= 0 && y < n_items;
-      }
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, valid);
-    const int pre = __popc(bal & ((1u << lane) - 1));
-    if (lane == 0) warp_tot[warp] = __popc(bal);
-    __syncthreads();
-    int woff = 0;
-    for (int w = 0; w < warp; ++w) woff += warp_tot[w];
-    const int pos = block_base + woff + pre;
-    if (valid) {
-      valid_idx[pos] = t;
-      labels_c[pos] = (int32_t)labels64[t];
-    }
-    __syncthreads();
-    if (tid == 1023) block_base = pos + (valid ? 1 : 0);
-    __syncthreads();
+  // coalesced pass: ids
+  for (int t = tid; t < T; t += 1024) {
+    const int64_t id = ids64[t];
+    ids32[t] = (pad_mask[t] && id >= 0 && id < n_items) ? (int32_t)id : pad_id;
   }
-  if (tid == 0 && n_valid) *n_valid = block_base;
+  if (!target_mask) return;
+  // each thread owns a contiguous slab of tokens so the compacted order is the token order
+  const int per = (T + 1023) / 1024;
+  const int t0 = tid * per, t1 = min(T, t0 + per);
+  int cnt = 0;
+  for (int t = t0; t < t1; ++t) {
+    const int64_t y = labels64[t];
+    cnt += (target_mask[t] != 0 && y >= 0 && y < n_items) ? 1 : 0;
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    warp_tot[lane] = w;  // inclusive
+  }
+  __syncthreads();
+  int pos = incl - cnt + (warp > 0 ? warp_tot[warp - 1] : 0);
+  for (int t = t0; t < t1; ++t) {
+    const int64_t y = labels64[t];
+    if (target_mask[t] != 0 && y >= 0 && y < n_items) {
+      valid_idx[pos] = t;
+      labels_c[pos] = (int32_t)y;
+      ++pos;
+    }
+  }
+  if (tid == 1023) *n_valid = warp_tot[31];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -132,25 +144,47 @@ __global__ void embed_bwd_table_kernel(const __nv_bfloat16* __restrict__ dx, con
   }
 }
 
-// dP[pos0 + l] += sum_b dx[b*L + l] * mask      one block per position, no atomics
+// dP[pos0 + l] += sum_b dx[b*L + l] * mask.   grid = (L, G): block (l, g) sums a slab of the batch; thread = 4 columns x
+// one batch lane; smem reduce over the batch lanes, then one atomic per column per block.
 __global__ void embed_bwd_pos_kernel(const __nv_bfloat16* __restrict__ dx, const uint8_t* __restrict__ pad_mask, int B,
                                      int L, int D, int pos0, int zero_pad_rows, float drop_p, unsigned long long seed,
                                      unsigned long long drop_off, const unsigned long long* __restrict__ seed_ptr,
                                      float* __restrict__ dP) {
   if (drop_p > 0.f && seed_ptr) seed += *seed_ptr;
+  extern __shared__ float red4[];  // [rows_per_iter][D]
   const int l = blockIdx.x;
+  const int tpr = D / 4;                       // threads per row
+  const int rlanes = blockDim.x / tpr;         // batch lanes
+  const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  const int per = (B + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * per, b1 = min(B, b0 + per);
   const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 4294967296.0) : 0u;
   const float ks = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float acc = 0.f;
-    for (int b = 0; b < B; ++b) {
-      const int t = b * L + l;
-      if (zero_pad_rows && !pad_mask[t]) continue;
-      float v = __bfloat162float(dx[(size_t)t * D + c]);
-      if (drop_p > 0.f) v = philox_keep(seed, drop_off + (unsigned long long)t * D + c, thr) ? v * ks : 0.f;
-      acc += v;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int b = b0 + rl; b < b1; b += rlanes) {
+    const int t = b * L + l;
+    if (zero_pad_rows && !pad_mask[t]) continue;
+    const uint2 raw = *reinterpret_cast<const uint2*>(dx + (size_t)t * D + cg * 4);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const float2 a = __bfloat1622float2(h[0]), c = __bfloat1622float2(h[1]);
+    float v[4] = {a.x, a.y, c.x, c.y};
+    if (drop_p > 0.f) {
+      const uint4 r = philox4x32(seed, (drop_off + (unsigned long long)t * D + cg * 4) >> 2);
+      v[0] = r.x >= thr ? v[0] * ks : 0.f;
+      v[1] = r.y >= thr ? v[1] * ks : 0.f;
+      v[2] = r.z >= thr ? v[2] * ks : 0.f;
+      v[3] = r.w >= thr ? v[3] * ks : 0.f;
     }
-    dP[(size_t)(pos0 + l) * D + c] += acc;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] += v[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) red4[rl * D + cg * 4 + k] = acc[k];
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float sum = 0.f;
+    for (int r = 0; r < rlanes; ++r) sum += red4[r * D + c];
+    atomicAdd(dP + (size_t)(pos0 + l) * D + c, sum);
   }
 }
 
@@ -319,20 +353,42 @@ __global__ void dropout_bwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bf
   }
 }
 
-// db[c] += sum_r dY[r, c]        dY bf16 [rows, cols] with pitch ld; each block sums a slab of rows
+// db[c] += sum_r dY[r, c]        dY bf16 [rows, cols] with pitch ld.  thread = 4 columns x one row lane (8-byte loads,
+// 4 rows in flight per thread), smem reduce over the row lanes, one atomic per column per block.
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, int rows, int cols, long long ld,
                               float* __restrict__ db) {
-  const int rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-  for (int c = threadIdx.x * 2; c < cols; c += blockDim.x * 2) {
-    float a0 = 0.f, a1 = 0.f;
-    for (int r = r0; r < r1; ++r) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy + (size_t)r * ld + c));
-      a0 += f.x;
-      a1 += f.y;
+  extern __shared__ float red4[];  // [rlanes][cols]
+  const int tpr = cols / 4, rlanes = blockDim.x / tpr;
+  const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rl < rlanes) {
+    const int stride = gridDim.x * rlanes;
+    int r = blockIdx.x * rlanes + rl;
+    for (; r + 3 * stride < rows; r += 4 * stride) {
+      uint2 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) raw[u] = *reinterpret_cast<const uint2*>(dy + (size_t)(r + u * stride) * ld + cg * 4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+        const float2 a = __bfloat1622float2(h[0]), c = __bfloat1622float2(h[1]);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += c.x; acc[3] += c.y;
+      }
     }
-    atomicAdd(db + c, a0);
-    atomicAdd(db + c + 1, a1);
+    for (; r < rows; r += stride) {
+      const uint2 raw = *reinterpret_cast<const uint2*>(dy + (size_t)r * ld + cg * 4);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      const float2 a = __bfloat1622float2(h[0]), c = __bfloat1622float2(h[1]);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += c.x; acc[3] += c.y;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red4[rl * cols + cg * 4 + k] = acc[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float sum = 0.f;
+    for (int r = 0; r < rlanes; ++r) sum += red4[r * cols + c];
+    atomicAdd(db + c, sum);
   }
 }
 
@@ -447,8 +503,15 @@ RP_API int rp_embed_bwd(const void* dx, const int32_t* ids, const uint8_t* pad_m
                        reinterpret_cast<const __nv_bfloat16*>(dx), ids, pad_mask, T, pad_id, scale, zero_pad_rows, drop_p,
                        seed, drop_off, seed_ptr, d_table)));
   RP_LAUNCH_CHECK();
-  embed_bwd_pos_kernel<<<L, d < 256 ? d : 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dx), pad_mask, B, L, d,
-                                                            pos0, zero_pad_rows, drop_p, seed, drop_off, seed_ptr, d_pos);
+  {
+    const int rlanes = 256 / (d / 4);
+    int G = (B + 31) / 32;
+    if (G < 1) G = 1;
+    if (G > 16) G = 16;
+    embed_bwd_pos_kernel<<<dim3(L, G), 256, (size_t)rlanes * d * sizeof(float), stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dx), pad_mask, B, L, d, pos0, zero_pad_rows, drop_p, seed, drop_off, seed_ptr,
+        d_pos);
+  }
   RP_LAUNCH_CHECK();
   return RP_OK;
 }
@@ -496,10 +559,12 @@ RP_API int rp_dropout_bwd(const void* in, void* out, long long rows, int cols, c
 
 RP_API int rp_colsum(const void* dy, int rows, int cols, long long ld, float* db, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (!dy || !db || rows <= 0 || cols <= 0 || (cols & 1)) return RP_EINVAL;
-  int grid = sm_count() * 2;
-  if (grid > rows) grid = rows;
-  colsum_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), rows, cols, ld, db);
+  if (!dy || !db || rows <= 0 || cols <= 0 || (cols & 3) || cols > 1024 || (ld & 3)) return RP_EINVAL;
+  const int rlanes = 256 / (cols / 4);
+  int grid = sm_count() * 4;
+  if (grid > (rows + rlanes - 1) / rlanes) grid = (rows + rlanes - 1) / rlanes;
+  colsum_kernel<<<grid, 256, (size_t)rlanes * cols * sizeof(float), stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), rows,
+                                                                             cols, ld, db);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }

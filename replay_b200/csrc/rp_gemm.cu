@@ -239,9 +239,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1) tmem_dealloc(tmem, BN < 32 ? 32 : BN);
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int batch, cudaStream_t st) {
-  constexpr int NSTAGE = 4;
+template <int BN, bool A_MN, bool B_MN, int NSTAGE>
+static int launch_gemm_n(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int batch, cudaStream_t st) {
   const int smem = NSTAGE * (128 * 128 + BN * 128) + 1024;
   auto kern = gemm_kernel<BN, A_MN, B_MN, NSTAGE>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -249,6 +248,15 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
   RP_LAUNCH_CHECK();
   return RP_OK;
+}
+
+// short-K problems (the body's d x d projections) use 2 stages so that 3 CTAs share an SM and their prologues,
+// main loops and epilogues overlap; long-K problems (weight gradients) use a 4-deep ring.
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int batch, cudaStream_t st) {
+  const int chunks_per_cta = ((p.K + 63) / 64 + p.split_k - 1) / p.split_k;
+  if (chunks_per_cta <= 2) return launch_gemm_n<BN, A_MN, B_MN, 2>(tmA, tmB, p, batch, st);
+  return launch_gemm_n<BN, A_MN, B_MN, 4>(tmA, tmB, p, batch, st);
 }
 
 }  // namespace rp

@@ -84,6 +84,101 @@ int rp_ce_head_bwd(const void* hc, const void* table, const int32_t* labels, con
                    int n_items, int d, const float* loss_out, const float* cvec, void* d_hc, float* d_table, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Transformer body.  All activations are token-major bf16 [T = B*L, d]; weights are the bf16 shadow of the fp32 masters.
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Generic batched GEMM  C[m,n] = epilogue(alpha * sum_k A(m,k) B(n,k))  on tcgen05.
+ *   replaces  torch.nn.MultiheadAttention in/out projections   replay/nn/sequential/sasrec/transformer.py:36-46,99-106
+ *             Conv1d(d,d,1) / Linear FFN layers                  replay/nn/ffn.py:43-57 ; models/nn/sequential/sasrec/model.py:490-506
+ *                                                                models/nn/sequential/bert4rec/model.py:516-527
+ *             and autograd's backward of all of them (dX = dY.W, dW = dY^T.X read in place through MN-major descriptors).
+ * Operand X is a 2-D bf16 array [x_rows, x_cols] with pitch ldx; x_mn = 0: stored [M or N rows, K cols] (K-major),
+ * x_mn = 1: stored [K rows, M or N cols].  Batch element bz = outer*inner + in addresses rows r0 + outer*ro + in*ri and
+ * columns c0 + outer*co + in*ci.  C: element offset c_off0 + outer*c_oo + in*c_oi, row pitch ldc.
+ * out_mode 0: bf16 store, 1: fp32 atomic add (split_k >= 1), 2: fp32 store.
+ * Epilogue order: alpha, bias[N], act (0 none, 1 ReLU, 2 GELU-erf), Philox dropout(drop_p; seed + *seed_ptr, drop_offset +
+ * element offset in C), gate (x *= gate != 0 ? gate_scale : 0, same geometry as C), residual (bf16, same geometry as C),
+ * rowmask[rowmask_off0 + outer*rowmask_oo + m]. */
+typedef struct rp_gemm_desc {
+  const void* A; long long a_rows, a_cols, lda; int a_mn;
+  const void* B; long long b_rows, b_cols, ldb; int b_mn;
+  int M, N, K, batch, inner;
+  int a_r0, a_ro, a_ri, a_c0, a_co, a_ci;
+  int b_r0, b_ro, b_ri, b_c0, b_co, b_ci;
+  void* C; long long ldc, c_off0, c_oo, c_oi; int out_mode;
+  float alpha; const float* bias; int act;
+  const void* residual; const uint8_t* rowmask; long long rowmask_off0, rowmask_oo;
+  float drop_p; unsigned long long seed, drop_offset; const unsigned long long* seed_ptr;
+  int split_k;
+  const void* gate; float gate_scale;
+} rp_gemm_desc;
+int rp_gemm(const rp_gemm_desc* g, void* stream);
+
+/* Fused multi-head attention forward for L <= 256, head_dim in {64,128}: S = Q.K^T, causal / key-padding mask derived
+ * from pad_mask (no [B*H,L,L] mask tensor), softmax, dropout, O = P.V.
+ *   replaces  torch.nn.MultiheadAttention's SDPA core + replay/nn/mask.py:18-51 (new path: causal & pad keys masked)
+ *             models/nn/sequential/sasrec/model.py:229-231,435 (legacy: causal only) ; bert4rec/model.py:494 (pad keys only)
+ * q/k/v: 2-D bf16 arrays whose rows are tokens; head h reads columns x_c0 + h*head_dim.  out: bf16 [B*L, ldo].
+ * p_save (optional) bf16 [B*H, Lp, Lp] receives exp(s - rowmax) (Lp = round_up(L,64), must be zero-initialised once),
+ * inv_sum fp32 [B*H, Lp] the reciprocal row sums - the inputs of rp_attn_softmax_bwd. */
+typedef struct rp_attn_desc {
+  const void* q; long long q_rows, q_cols, ldq; int q_c0;
+  const void* k; long long k_rows, k_cols, ldk; int k_c0;
+  const void* v; long long v_rows, v_cols, ldv; int v_c0;
+  int B, H, L, head_dim;
+  int causal, mask_pad_keys;
+  const uint8_t* pad_mask;
+  void* out; int ldo;
+  void* p_save; float* inv_sum;
+  float drop_p; unsigned long long seed, drop_off; const unsigned long long* seed_ptr;
+} rp_attn_desc;
+int rp_attn_fwd(const rp_attn_desc* a, void* stream);
+
+/* Softmax backward between the batched attention-backward GEMMs: in place, dpd := dS = P*(dP - sum P*dP)*scale and
+ * p_save := P*dropmask/keep (the A operand of dV). */
+int rp_attn_softmax_bwd(void* p_save, void* dpd, const float* inv_sum, int BH, int L, float scale, float drop_p,
+                        unsigned long long seed, unsigned long long drop_off, const unsigned long long* seed_ptr,
+                        void* stream);
+
+/* int64 ids / bool masks of one [B, L] batch -> int32 ids (pads -> pad_id) and the compacted valid-target list
+ * (replaces the masked_fill / boolean-index preparation in nn/loss/ce.py:70-80 and models/.../sasrec/model.py:236-239).
+ * labels/target_mask may be NULL (predict). */
+int rp_prepare_batch(const int64_t* ids, const uint8_t* pad_mask, const int64_t* labels, const uint8_t* target_mask, int T,
+                     int pad_id, int n_items, int32_t* ids32, int32_t* valid_idx, int32_t* labels_c, int32_t* n_valid,
+                     void* stream);
+
+/* x[t] = table[ids[t]] * scale + pos[pos0 + t % L] -> dropout -> (zero pad rows)      nn/sequential/sasrec/agg.py:37-53,
+ * models/nn/sequential/sasrec/model.py:346-357 ; and its backward (fp32 atomics into d_table, pad row frozen). */
+int rp_embed_fwd(const void* table, const float* pos, const int32_t* ids, const uint8_t* pad_mask, int T, int L, int d,
+                 int pos0, float scale, int zero_pad_rows, float drop_p, unsigned long long seed, unsigned long long drop_off,
+                 const unsigned long long* seed_ptr, void* out, void* stream);
+int rp_embed_bwd(const void* dx, const int32_t* ids, const uint8_t* pad_mask, int B, int L, int d, int pad_id, int pos0,
+                 float scale, int zero_pad_rows, float drop_p, unsigned long long seed, unsigned long long drop_off,
+                 const unsigned long long* seed_ptr, float* d_table, float* d_pos, void* stream);
+
+/* torch.nn.LayerNorm forward / backward (transformer.py:47-49,60-62 eps 1e-8; model.py:248 eps 1e-5).  With `gather`
+ * output row r reads input row gather[r] and only *n_rows_dev rows exist (valid-target compaction); the backward then
+ * scatters dx to those rows.  add_to (optional, bf16 [*, d]) is added to dx (residual-branch gradient). */
+int rp_layernorm_fwd(const void* x, const float* w, const float* b, float eps, int n_rows, int d, const int32_t* n_rows_dev,
+                     const int32_t* gather, void* y, float* mean, float* rstd, void* stream);
+int rp_layernorm_bwd(const void* dy, const void* x, const float* w, const float* mean, const float* rstd, int n_rows, int d,
+                     const int32_t* n_rows_dev, const int32_t* gather, const void* add_to, void* dx, float* dw, float* db,
+                     void* stream);
+
+/* out = in * regenerated dropout mask / keep (and optional row mask); db[c] += column sums of a bf16 [rows, cols] array. */
+int rp_dropout_bwd(const void* in, void* out, long long rows, int cols, const uint8_t* rowmask, float drop_p,
+                   unsigned long long seed, unsigned long long drop_off, const unsigned long long* seed_ptr, void* stream);
+int rp_colsum(const void* dy, int rows, int cols, long long ld, float* db, void* stream);
+
+/* torch.optim.Adam (models/nn/optimizer_utils/optimizer_factory.py:71-87; no weight decay) on flat fp32 buffers; refreshes
+ * the bf16 shadow, optionally zeroes the gradient; lr and the step counter live in device memory. */
+int rp_adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, long long n, const float* lr_dev,
+                 int32_t* step_dev, float beta1, float beta2, float eps, float grad_scale, const uint8_t* frozen,
+                 int zero_grad, void* stream);
+int rp_cast_bf16(const float* src, void* dst, long long n, void* stream);
+int rp_counter_add(unsigned long long* counter, unsigned long long inc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Bring-up self test of the tcgen05 operand encodings (used by tests/, not by the product path).
  * A, B: bf16 [128,128]; D: fp32 [128,128].  mode bit0: B given as Bt[K,N]; bit1: A staged through TMEM;
  * bit2: A given as At[K,M].  D = A . B^T in every mode.

@@ -1,0 +1,206 @@
+"""``SasRecCore``: torch.nn.Module facade over the CUDA engine, shared by the new-path and legacy API mirrors.
+
+* parameters live in ONE flat fp32 ``nn.Parameter`` (the engine's master buffer); ``state_dict`` / ``load_state_dict`` use the
+  REFERENCE's key names so checkpoints interchange with RePlay's modules;
+* the loss is produced by an ``autograd.Function`` whose backward runs the engine's hand-written backward kernels and
+  hands the flat gradient to autograd, so ``loss.backward()`` + any torch optimizer (or Lightning's automatic
+  optimization) work unchanged; ``fused_step()`` instead runs forward+backward+Adam entirely in the engine.
+"""
+from __future__ import annotations
+
+import torch
+
+from .engine import _BLOCK_PARAMS, EncoderConfig, SasRecEngine
+
+_LEAF = {"ln1_w": "attention_layernorms.{i}.weight", "ln1_b": "attention_layernorms.{i}.bias",
+         "in_w": "attention_layers.{i}.in_proj_weight", "in_b": "attention_layers.{i}.in_proj_bias",
+         "out_w": "attention_layers.{i}.out_proj.weight", "out_b": "attention_layers.{i}.out_proj.bias",
+         "ln2_w": "forward_layernorms.{i}.weight", "ln2_b": "forward_layernorms.{i}.bias",
+         "w1": "forward_layers.{i}.conv1.weight", "b1": "forward_layers.{i}.conv1.bias",
+         "w2": "forward_layers.{i}.conv2.weight", "b2": "forward_layers.{i}.conv2.bias"}
+
+
+def reference_key_map(variant: str, n_blocks: int, item_feature: str = "item_id") -> dict:
+    """engine parameter name -> reference state_dict key (without the Lightning prefix)."""
+    if variant == "new":
+        m = {"item_emb": f"body.embedder.feature_embedders.{item_feature}.emb.weight",
+             "pos_emb": "body.embedding_aggregator.pe.weight",
+             "lnf_w": "body.output_normalization.weight", "lnf_b": "body.output_normalization.bias"}
+        enc = "body.encoder."
+    else:
+        m = {"item_emb": "item_embedder.item_emb.weight", "pos_emb": "item_embedder.pos_emb.pe.weight",
+             "lnf_w": "output_normalization.last_layernorm.weight", "lnf_b": "output_normalization.last_layernorm.bias"}
+        enc = "sasrec_layers."
+    for i in range(n_blocks):
+        for k in _BLOCK_PARAMS:
+            m[f"b{i}.{k}"] = enc + _LEAF[k].format(i=i)
+    return m
+
+
+class _EngineLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flat, core):
+        ctx.core = core
+        eng = core.engine
+        if core._shadow_dirty:
+            eng.refresh_shadow()
+            core._shadow_dirty = False
+        eng.tick_rng()
+        loss = eng.forward_train()
+        return loss[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        eng = ctx.core.engine
+        eng.g32.zero_()
+        eng.backward()
+        ctx.core._shadow_dirty = True  # an optimizer is about to change the fp32 master weights
+        return eng.g32 * grad_out, None
+
+
+class SasRecCore(torch.nn.Module):
+    def __init__(self, cfg: EncoderConfig, item_feature: str = "item_id", device=None, seed: int = 0):
+        super().__init__()
+        self.cfg = cfg
+        self.item_feature = item_feature
+        self._device = torch.device(device) if device is not None else torch.device("cuda")
+        self._seed = seed
+        self.engine: SasRecEngine | None = None
+        self.flat: torch.nn.Parameter | None = None
+        self._pending_state = None
+        self._shadow_dirty = True
+        self._keymap = reference_key_map(cfg.variant, cfg.n_blocks, item_feature)
+
+    # ---- engine lifetime: created on first use for the batch geometry it sees (re-created if a larger batch arrives)
+    def ensure_engine(self, batch: int, seq_len: int, with_grad: bool = True) -> SasRecEngine:
+        e = self.engine
+        if e is None or batch > e.B or seq_len != e.L or (with_grad and not e.with_grad):
+            state = self._export() if e is not None else self._pending_state
+            opt = (e.adam_m.clone(), e.adam_v.clone(), e.step_count.clone()) if (e is not None and e.with_grad) else None
+            self.engine = SasRecEngine(self.cfg, batch, seq_len, self._device, seed=self._seed, with_grad=with_grad)
+            if state is not None:
+                self._import(state)
+            if opt is not None and self.engine.with_grad:
+                self.engine.adam_m.copy_(opt[0]); self.engine.adam_v.copy_(opt[1]); self.engine.step_count.copy_(opt[2])
+            self.flat = torch.nn.Parameter(self.engine.p32, requires_grad=with_grad)
+            self._pending_state = None
+            self._shadow_dirty = True
+        return self.engine
+
+    def _export(self) -> dict:
+        return {self._keymap[k]: self._to_ref(k, v.detach().clone()) for k, v in self.engine.params.items()}
+
+    def _to_ref(self, k, v):
+        return v.unsqueeze(-1) if k.endswith((".w1", ".w2")) else v  # Conv1d weight [d, d, 1]
+
+    def _import(self, state: dict):
+        inv = {v: k for k, v in self._keymap.items()}
+        with torch.no_grad():
+            for rk, val in state.items():
+                k = inv.get(rk)
+                if k is None:
+                    continue
+                val = val.to(self.engine.dev, torch.float32)
+                if k.endswith((".w1", ".w2")) and val.dim() == 3:
+                    val = val[:, :, 0]
+                self.engine.params[k].copy_(val)
+        self._shadow_dirty = True
+
+    # ---- reference-compatible checkpoints
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):  # noqa: D102
+        out = destination if destination is not None else {}
+        src = self._export() if self.engine is not None else (self._pending_state or {})
+        for k, v in src.items():
+            out[prefix + k] = v
+        if self.cfg.variant == "legacy":  # the reference's head registers the embedder again (Appendix B aliases)
+            for a, b in (("_head._item_embedder.item_emb.weight", "item_embedder.item_emb.weight"),
+                         ("_head._item_embedder.pos_emb.pe.weight", "item_embedder.pos_emb.pe.weight")):
+                if b in src:
+                    out[prefix + a] = src[b]
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):  # noqa: D102
+        known = set(self._keymap.values())
+        sd = {k: v for k, v in state_dict.items() if k in known}
+        missing = known - set(sd)
+        if strict and missing:
+            raise RuntimeError(f"missing keys in state_dict: {sorted(missing)[:5]} ...")
+        if self.engine is None:
+            self._pending_state = {k: v.detach().clone() for k, v in sd.items()}
+        else:
+            self._import(sd)
+        return torch.nn.modules.module._IncompatibleKeys(sorted(missing), [])
+
+    # ---- training / inference on [B, L] batches
+    def loss(self, ids, pad_mask, labels, target_mask) -> torch.Tensor:
+        B, L = ids.shape
+        eng = self.ensure_engine(B, L, with_grad=True)
+        eng.set_batch(ids, pad_mask, labels, target_mask)
+        return _EngineLoss.apply(self.flat, self)
+
+    def fused_step(self, ids, pad_mask, labels, target_mask, all_reduce=None, lr: float | None = None) -> torch.Tensor:
+        """forward + backward + Adam entirely inside the engine (no autograd, no torch optimizer)."""
+        B, L = ids.shape
+        eng = self.ensure_engine(B, L, with_grad=True)
+        if self._shadow_dirty:
+            eng.refresh_shadow()
+            self._shadow_dirty = False
+        if lr is not None and lr != getattr(self, "_lr_set", None):
+            eng.lr.fill_(lr)
+            self._lr_set = lr
+        eng.set_batch(ids, pad_mask, labels, target_mask)
+        return eng.train_step(all_reduce)[0]
+
+    def mark_params_updated(self):
+        """Call after an external optimizer changed ``flat`` (done automatically by the API mirrors)."""
+        self._shadow_dirty = True
+
+    def _eval_engine(self, ids):
+        B, L = ids.shape
+        eng = self.ensure_engine(B, L, with_grad=self.engine.with_grad if self.engine is not None else False)
+        if self._shadow_dirty:
+            eng.refresh_shadow()
+            self._shadow_dirty = False
+        return eng
+
+    @torch.no_grad()
+    def query_embeddings(self, ids, pad_mask) -> torch.Tensor:
+        """Last-position hidden state, bf16 [B, d] (get_query_embeddings / forward_inference's last_hidden_state)."""
+        eng = self._eval_engine(ids)
+        eng.set_batch(ids, pad_mask)
+        return eng.forward_last_hidden()[: ids.shape[0]]
+
+    @torch.no_grad()
+    def hidden_states(self, ids, pad_mask) -> torch.Tensor:
+        eng = self._eval_engine(ids)
+        eng.set_batch(ids, pad_mask)
+        B, L = ids.shape
+        return eng.forward_hidden_all().view(eng.B, L, -1)[:B]
+
+    @torch.no_grad()
+    def item_table(self, candidates=None) -> torch.Tensor:
+        t = self.engine.params16["item_emb"][: self.cfg.n_items]
+        return t if candidates is None else t[candidates].contiguous()
+
+    @torch.no_grad()
+    def logits(self, ids, pad_mask, candidates=None) -> torch.Tensor:
+        """Materialised fp32 scores [B, |I|] or [B, |C|] (API compatibility; the fused top-K path never builds them)."""
+        hq = self.query_embeddings(ids, pad_mask)
+        tab = self.item_table(candidates)
+        out = torch.empty(hq.shape[0], tab.shape[0], device=hq.device, dtype=torch.float32)
+        self.engine._gemm(hq, tab, out, hq.shape[0], tab.shape[0], self.cfg.d, out_mode=2)
+        return out
+
+    @torch.no_grad()
+    def predict_topk(self, ids, pad_mask, k: int, seen_ids=None, candidates=None):
+        """Fused predict: body -> last hidden -> scores -> seen filter -> top-k.  Returns (item ids int64 [B,k], scores)."""
+        from . import ops
+
+        hq = self.query_embeddings(ids, pad_mask).contiguous()
+        n_items = self.cfg.n_items
+        inv = None
+        if candidates is not None:
+            inv = torch.full((n_items,), -1, device=hq.device, dtype=torch.int32)
+            inv[candidates] = torch.arange(candidates.numel(), device=hq.device, dtype=torch.int32)
+        seen = None if seen_ids is None else ops.seen_prepare(seen_ids.contiguous(), n_items, inv)
+        return ops.score_topk(hq, self.item_table(candidates), k, seen, candidates)

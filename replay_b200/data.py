@@ -1,0 +1,47 @@
+"""Host-side input-layout producers with the reference's semantics: left padding, shift-by-one
+labels (replay/models/nn/sequential/sasrec/dataset.py:104-126, replay/data/nn/torch_sequential_dataset.py:115-136) for
+SASRec, uniform token masking for BERT4Rec (bert4rec/dataset.py:71-92).  Vectorised over a list of id sequences."""
+from __future__ import annotations
+
+import torch
+
+
+def left_pad(sequences, length: int, pad_value: int):
+    """[n] variable-length id lists -> (ids [n, length] int64, mask [n, length] bool): keep the LAST ``length`` items."""
+    n = len(sequences)
+    ids = torch.full((n, length), pad_value, dtype=torch.int64)
+    mask = torch.zeros(n, length, dtype=torch.bool)
+    for r, s in enumerate(sequences):
+        s = torch.as_tensor(s, dtype=torch.int64)[-length:]
+        k = s.numel()
+        if k:
+            ids[r, length - k:] = s
+            mask[r, length - k:] = True
+    return ids, mask
+
+
+def sasrec_training_batch(sequences, max_len: int, pad_value: int, query_ids=None):
+    """Batch dict with the legacy key names (sasrec/dataset.py:120-126)."""
+    full, msk = left_pad(sequences, max_len + 1, pad_value)
+    q = torch.arange(len(sequences)) if query_ids is None else torch.as_tensor(query_ids)
+    return {"query_id": q.view(-1, 1), "feature_tensor": {"item_id": full[:, :-1].contiguous()},
+            "padding_mask": msk[:, :-1].contiguous(), "positive_labels": full[:, 1:].contiguous(),
+            "target_padding_mask": msk[:, 1:].contiguous()}
+
+
+def sasrec_prediction_batch(sequences, max_len: int, pad_value: int, query_ids=None):
+    ids, msk = left_pad(sequences, max_len, pad_value)
+    q = torch.arange(len(sequences)) if query_ids is None else torch.as_tensor(query_ids)
+    return {"query_id": q.view(-1, 1), "feature_tensor": {"item_id": ids}, "padding_mask": msk}
+
+
+def to_new_path_batch(b: dict, with_seen: bool = True) -> dict:
+    """legacy batch dict -> the new path's model inputs (make_default_sasrec_transforms, nn/transform/template/sasrec.py:9-42):
+    feature_tensors, padding_mask, positive_labels [B,L,1], target_padding_mask [B,L,1] (+ seen_ids = the window)."""
+    out = {"query_id": b["query_id"], "feature_tensors": b["feature_tensor"], "padding_mask": b["padding_mask"]}
+    if "positive_labels" in b:
+        out["positive_labels"] = b["positive_labels"].unsqueeze(-1)
+        out["target_padding_mask"] = b["target_padding_mask"].unsqueeze(-1)
+    if with_seen:
+        out["seen_ids"] = b["feature_tensor"]["item_id"]
+    return out

@@ -1,0 +1,4 @@
+"""Mirror of ``replay.models.nn.sequential`` (legacy Lightning modules) for the hot path."""
+from .callbacks import PandasPredictionCallback, TorchPredictionCallback  # noqa: F401
+from .postprocessors import RemoveSeenItems  # noqa: F401
+from .sasrec import SasRec, SasRecModel  # noqa: F401

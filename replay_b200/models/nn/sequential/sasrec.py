@@ -1,0 +1,160 @@
+"""Mirror of the legacy ``replay.models.nn.sequential.sasrec`` modules on the B200 engine:
+``SasRecModel`` (model.py:15-197) and the Lightning module ``SasRec`` (lightning.py:22-658).  Legacy semantics: causal mask
+only (pad keys are NOT masked), pad rows zeroed after the embedding and after every block, final LayerNorm eps 1e-8,
+sequence length must equal ``max_len`` (predict batches are left-padded up to it, lightning.py:624-658)."""
+from __future__ import annotations
+
+import torch
+
+from ....compat import LightningModuleBase
+from ....core import SasRecCore
+from ....engine import EncoderConfig
+from ....schema import item_feature_of
+
+
+def _prepare_prediction_batch(schema, max_len: int, batch: dict) -> dict:
+    """lightning.py:624-658: raise if longer than max_len, left-pad (ids with 0, mask with False) if shorter."""
+    seq_len = batch["padding_mask"].shape[1]
+    if seq_len > max_len:
+        msg = ("The length of the submitted sequence must not exceed the maximum length of the sequence. "
+               f"The length of the sequence is given {seq_len}, while the maximum length is {max_len}")
+        raise ValueError(msg)
+    if seq_len < max_len:
+        pad = (max_len - seq_len, 0)
+        batch = dict(batch)
+        batch["feature_tensor"] = {k: torch.nn.functional.pad(v, pad, value=0) for k, v in batch["feature_tensor"].items()}
+        batch["padding_mask"] = torch.nn.functional.pad(batch["padding_mask"], pad, value=0)
+    return batch
+
+
+class SasRecModel(torch.nn.Module):
+    def __init__(self, schema, num_blocks: int = 2, num_heads: int = 1, hidden_size: int = 50, max_len: int = 200,
+                 dropout: float = 0.2, ti_modification: bool = False, time_span: int = 256, device=None, seed: int = 0):
+        super().__init__()
+        if ti_modification:
+            raise NotImplementedError("TiSASRec is outside the B200 hot-path scope (SURVEY.md §2)")
+        name, card, pad, _ = item_feature_of(schema)
+        self.schema = schema
+        self.item_feature_name = name
+        self.item_count = card
+        self.padding_idx = card
+        self.max_len = max_len
+        self.hidden_size, self.num_blocks, self.num_heads, self.dropout = hidden_size, num_blocks, num_heads, dropout
+        cfg = EncoderConfig(n_items=card, d=hidden_size, n_heads=num_heads, n_blocks=num_blocks, max_len=max_len,
+                            dropout=dropout, variant="legacy")
+        self.core = SasRecCore(cfg, item_feature=name, device=device, seed=seed)
+
+    def state_dict(self, *a, **k):
+        return self.core.state_dict(*a, **k)
+
+    def load_state_dict(self, sd, strict=True, assign=False):
+        return self.core.load_state_dict(sd, strict=strict)
+
+    def forward_step(self, feature_tensor, padding_mask):
+        """Hidden states [B, L, d] (model.py:159-180)."""
+        return self.core.hidden_states(feature_tensor[self.item_feature_name], padding_mask).float()
+
+    def get_query_embeddings(self, feature_tensor, padding_mask):
+        return self.core.query_embeddings(feature_tensor[self.item_feature_name], padding_mask).float()
+
+    def get_logits(self, out_embeddings, item_ids=None):
+        h = out_embeddings.reshape(-1, out_embeddings.shape[-1]).to(torch.bfloat16).contiguous()
+        tab = self.core.item_table(item_ids)
+        out = torch.empty(h.shape[0], tab.shape[0], device=h.device, dtype=torch.float32)
+        self.core.engine._gemm(h, tab, out, h.shape[0], tab.shape[0], self.hidden_size, out_mode=2)
+        return out.view(*out_embeddings.shape[:-1], tab.shape[0])
+
+    def forward(self, feature_tensor, padding_mask):
+        """All-position scores [B, L, |I|] (model.py:111-125) - materialised; use only for small problems."""
+        return self.get_logits(self.forward_step(feature_tensor, padding_mask))
+
+    def predict(self, feature_tensor, padding_mask, candidates_to_score=None):
+        return self.core.logits(feature_tensor[self.item_feature_name], padding_mask, candidates_to_score)
+
+
+class SasRec(LightningModuleBase):
+    def __init__(self, tensor_schema, block_count: int = 2, head_count: int = 1, hidden_size: int = 50,
+                 max_seq_len: int = 200, dropout_rate: float = 0.2, ti_modification: bool = False, time_span: int = 256,
+                 loss_type: str = "CE", loss_sample_count=None, negative_sampling_strategy: str = "global_uniform",
+                 negatives_sharing: bool = False, optimizer_factory=None, lr_scheduler_factory=None, sce_params=None,
+                 fused_optimizer: bool = True, device=None):
+        super().__init__()
+        self.save_hyperparameters()
+        if loss_type != "CE" or loss_sample_count is not None:
+            raise NotImplementedError("Not supported loss_type")  # lightning.py:485 ; sampled losses: SURVEY §8(f)
+        self._model = SasRecModel(tensor_schema, num_blocks=block_count, num_heads=head_count, hidden_size=hidden_size,
+                                  max_len=max_seq_len, dropout=dropout_rate, ti_modification=ti_modification,
+                                  time_span=time_span, device=device)
+        self._schema = tensor_schema
+        self._optimizer_factory = optimizer_factory
+        self._lr_scheduler_factory = lr_scheduler_factory
+        self._candidates_to_score = None
+        self.fused_optimizer = fused_optimizer
+        if fused_optimizer:
+            self.automatic_optimization = False
+        self._lr = getattr(optimizer_factory, "learning_rate", 1e-3)
+
+    def state_dict(self, *a, prefix="", **k):
+        return {prefix + "_model." + key: v for key, v in self._model.state_dict().items()}
+
+    def load_state_dict(self, sd, strict=True, assign=False):
+        return self._model.load_state_dict({k[len("_model."):]: v for k, v in sd.items() if k.startswith("_model.")}, strict)
+
+    def training_step(self, batch: dict, batch_idx: int = 0):
+        ids = batch["feature_tensor"][self._model.item_feature_name]
+        args = (ids, batch["padding_mask"], batch["positive_labels"], batch["target_padding_mask"])
+        core = self._model.core
+        if self.fused_optimizer:
+            loss = core.fused_step(*args, lr=self._lr)
+        else:
+            loss = core.loss(*args)
+        self.log("train_loss", loss, on_step=True, on_epoch=True, prog_bar=True, sync_dist=True)
+        return loss
+
+    def forward(self, feature_tensors, padding_mask, candidates_to_score=None):
+        return self._model.predict(feature_tensors, padding_mask, candidates_to_score)
+
+    def predict_step(self, batch: dict, batch_idx: int = 0, dataloader_idx: int = 0):
+        batch = _prepare_prediction_batch(self._schema, self._model.max_len, batch)
+        return self._model.predict(batch["feature_tensor"], batch["padding_mask"], self._candidates_to_score)
+
+    def predict(self, batch: dict, candidates_to_score=None):
+        batch = _prepare_prediction_batch(self._schema, self._model.max_len, batch)
+        return self._model.predict(batch["feature_tensor"], batch["padding_mask"], candidates_to_score)
+
+    def predict_topk(self, batch: dict, k: int, seen_ids=None, candidates_to_score=None):
+        """Fused predict (no [B, |I|] scores): (item ids [B,k] int64, scores [B,k])."""
+        batch = _prepare_prediction_batch(self._schema, self._model.max_len, batch)
+        ids = batch["feature_tensor"][self._model.item_feature_name]
+        return self._model.core.predict_topk(ids, batch["padding_mask"], k, seen_ids, candidates_to_score)
+
+    def configure_optimizers(self):
+        params = [self._model.core.flat]
+        if self._optimizer_factory is not None:
+            opt = self._optimizer_factory.create(params)
+        else:
+            opt = torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.98))  # optimizer_factory.py:56-63
+        if self._lr_scheduler_factory is None:
+            return opt
+        return [opt], [self._lr_scheduler_factory.create(opt)]
+
+    def get_all_embeddings(self):
+        return {self._model.item_feature_name: self._model.core.engine.params["item_emb"][:-1].detach().clone()}
+
+    @property
+    def optimizer_factory(self):
+        return self._optimizer_factory
+
+    @property
+    def candidates_to_score(self):
+        return self._candidates_to_score
+
+    @candidates_to_score.setter
+    def candidates_to_score(self, candidates=None):
+        total = self._model.item_count  # lightning.py:594-610
+        if isinstance(candidates, torch.Tensor) and candidates.dtype is torch.long:
+            if not (0 < candidates.shape[0] <= total):
+                raise ValueError(f"Expected candidates length to be between 1 and total_item_count={total}")
+        elif candidates is not None:
+            raise ValueError(f"Expected candidates to be of type torch.LongTensor or None, gpt {type(candidates)}")
+        self._candidates_to_score = candidates

@@ -1,0 +1,62 @@
+from __future__ import annotations
+
+import torch
+
+from ...compat import CallbackBase
+from .postprocessor import SeenItemsFilter
+
+
+class TopItemsCallbackBase(CallbackBase):
+    """replay/nn/lightning/callback/predictions_callback.py:29-163.  When the module's model is backed by the CUDA engine and
+    the postprocessors are (only) ``SeenItemsFilter``s, scores, filter and top-K run as ONE fused kernel on the last hidden
+    state - the ``[B, |I|]`` logits the reference materialises, clones, scatters into and re-reads are never built."""
+
+    def __init__(self, top_k: int, query_column: str, item_column: str, rating_column: str = "rating", postprocessors=None):
+        self.query_column, self.item_column, self.rating_column = query_column, item_column, rating_column
+        self._top_k = top_k
+        self._postprocessors = postprocessors or []
+        self._query_batches, self._item_batches, self._item_scores = [], [], []
+
+    def on_predict_epoch_start(self, trainer, pl_module):
+        self._query_batches.clear(); self._item_batches.clear(); self._item_scores.clear()
+        for p in self._postprocessors:
+            p.candidates = pl_module.candidates_to_score
+
+    def on_predict_batch_end(self, trainer, pl_module, outputs, batch, batch_idx, dataloader_idx=0):
+        model = getattr(pl_module, "model", None)
+        fusable = hasattr(model, "core") and all(isinstance(p, SeenItemsFilter) for p in self._postprocessors)
+        if fusable:
+            seen = batch[self._postprocessors[0].seen_items_column] if self._postprocessors else None
+            ids, scores = model.predict_topk(batch["feature_tensors"], batch["padding_mask"], self._top_k, seen,
+                                             pl_module.candidates_to_score)
+        else:
+            logits = outputs["logits"]
+            for p in self._postprocessors:
+                logits = p.on_prediction(batch, logits)
+            scores, ids = torch.topk(logits, k=self._top_k, dim=1)
+            if pl_module.candidates_to_score is not None:
+                ids = torch.take(pl_module.candidates_to_score, ids)
+        self._query_batches.append(batch[self.query_column])
+        self._item_batches.append(ids)
+        self._item_scores.append(scores)
+
+    def get_result(self):
+        return self._ids_to_result(torch.cat(self._query_batches), torch.cat(self._item_batches), torch.cat(self._item_scores))
+
+    def _ids_to_result(self, query_ids, item_ids, item_scores):
+        raise NotImplementedError
+
+
+class TorchTopItemsCallback(TopItemsCallbackBase):
+    def _ids_to_result(self, query_ids, item_ids, item_scores):
+        return query_ids.flatten().cpu().long(), item_ids.cpu().long(), item_scores.cpu()
+
+
+class PandasTopItemsCallback(TopItemsCallbackBase):
+    def _ids_to_result(self, query_ids, item_ids, item_scores):
+        import pandas as pd
+
+        q = query_ids.flatten().cpu().numpy()
+        k = item_ids.shape[1]
+        return pd.DataFrame({self.query_column: q.repeat(k), self.item_column: item_ids.cpu().numpy().reshape(-1),
+                             self.rating_column: item_scores.cpu().numpy().reshape(-1)})

@@ -1,0 +1,131 @@
+"""CPU tests of the host-side mirror of the reference interface: no kernel is launched here."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from replay_b200.core import reference_key_map
+from replay_b200.data import left_pad, sasrec_prediction_batch, sasrec_training_batch, to_new_path_batch
+from replay_b200.schema import TensorFeatureInfo, TensorSchema
+
+
+def _schema(n=300, d=64):
+    return TensorSchema(TensorFeatureInfo("item_id", n, n, d))
+
+
+def test_state_dict_keys_match_reference_new(golden_dir):
+    z = np.load(os.path.join(golden_dir, "sasrec_new_tiny.npz"))
+    ref_keys = {k[4:] for k in z.files if k.startswith("sd::")}
+    assert set(reference_key_map("new", int(z["n_blocks"])).values()) == ref_keys
+
+
+def test_state_dict_keys_match_reference_legacy(golden_dir):
+    z = np.load(os.path.join(golden_dir, "sasrec_legacy_tiny.npz"))
+    ref_keys = {k[4:] for k in z.files if k.startswith("sd::")}
+    ours = set(reference_key_map("legacy", int(z["n_blocks"])).values())
+    aliases = {"_head._item_embedder.item_emb.weight", "_head._item_embedder.pos_emb.pe.weight"}
+    assert ours | aliases == ref_keys
+
+
+def test_training_batch_layout_known_answer():
+    """tests/models/nn/sequential/sasrec/test_sasrec_dataset.py:40-48 of the reference (sequence [0, 1], max_len 8)."""
+    b = sasrec_training_batch([[0, 1]], 8, pad_value=-1)
+    assert b["padding_mask"][0].tolist() == [False] * 7 + [True]
+    assert b["target_padding_mask"][0].tolist() == [False] * 6 + [True, True]
+    assert b["positive_labels"][0].tolist() == [-1] * 6 + [0, 1]
+    p = sasrec_prediction_batch([[0, 1, 2]], 8, pad_value=5)
+    assert p["padding_mask"][0].tolist() == [False] * 5 + [True] * 3
+    n = to_new_path_batch(b)
+    assert n["positive_labels"].shape == (1, 8, 1) and n["seen_ids"].shape == (1, 8)
+
+
+def test_left_pad_truncates_to_last_items_and_handles_empty():
+    ids, m = left_pad([list(range(10)), []], 4, 99)
+    assert ids[0].tolist() == [6, 7, 8, 9] and m[0].all()
+    assert ids[1].tolist() == [99] * 4 and not m[1].any()
+
+
+def test_new_path_from_params_validation():
+    from replay_b200.nn.sequential import SasRec
+
+    with pytest.raises(ValueError):  # head_dim 48 is not a tcgen05 tile size
+        SasRec.from_params(_schema(), embedding_dim=192, num_heads=4)
+    with pytest.raises(ValueError):
+        SasRec.from_params(TensorSchema(TensorFeatureInfo("item_id", 300, 0, 64)), embedding_dim=64, num_heads=1)
+    m = SasRec.from_params(_schema(), embedding_dim=128, num_heads=2, max_sequence_length=50, dropout=0.1)
+    assert m.core.cfg.lnf_eps == 1e-5 and m.core.cfg.variant == "new"
+
+
+def test_lightning_module_candidates_validation():
+    from replay_b200.nn.lightning import LightningModule
+    from replay_b200.nn.sequential import SasRec
+
+    lm = LightningModule(SasRec.from_params(_schema(), embedding_dim=64, num_heads=1))
+    with pytest.raises(ValueError):
+        lm.candidates_to_score = torch.tensor([1, 1, 2])
+    with pytest.raises(ValueError):
+        lm.candidates_to_score = torch.tensor([1.0, 2.0])
+    lm.candidates_to_score = torch.tensor([3, 1, 2])
+    assert lm.candidates_to_score.tolist() == [3, 1, 2]
+
+
+def test_legacy_module_error_conventions():
+    from replay_b200.models.nn.sequential import SasRec
+    from replay_b200.models.nn.sequential.sasrec import _prepare_prediction_batch
+
+    with pytest.raises(NotImplementedError):
+        SasRec(_schema(), hidden_size=64, loss_type="BCE")
+    m = SasRec(_schema(), hidden_size=64, head_count=1, max_seq_len=8)
+    with pytest.raises(ValueError):
+        m.candidates_to_score = torch.arange(301)
+    with pytest.raises(ValueError):
+        m.candidates_to_score = [1, 2]
+    b = {"feature_tensor": {"item_id": torch.ones(2, 9, dtype=torch.long)}, "padding_mask": torch.ones(2, 9, dtype=torch.bool)}
+    with pytest.raises(ValueError):
+        _prepare_prediction_batch(None, 8, b)
+    b = {"feature_tensor": {"item_id": torch.ones(2, 5, dtype=torch.long)}, "padding_mask": torch.ones(2, 5, dtype=torch.bool)}
+    out = _prepare_prediction_batch(None, 8, b)
+    assert out["padding_mask"].shape == (2, 8) and not out["padding_mask"][:, :3].any()
+
+
+def test_seen_items_filter_known_answers(golden_dir):
+    """reference tests/nn/lightning/postprocessor/test_postprocessor.py:7-46 on the mirror class."""
+    from replay_b200.nn.lightning import SeenItemsFilter
+
+    z = np.load(os.path.join(golden_dir, "seen_filter_known.npz"))
+    f = SeenItemsFilter(item_count=5)
+    out = f.on_prediction({"seen_ids": torch.from_numpy(z["seen"])}, torch.from_numpy(z["logits"]))
+    assert torch.equal(out, torch.from_numpy(z["out"]))
+    f.candidates = torch.from_numpy(z["candidates"])
+    out = f.on_prediction({"seen_ids": torch.from_numpy(z["seen"])}, torch.from_numpy(z["cand_logits"]))
+    assert torch.equal(out, torch.from_numpy(z["cand_out"]))
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports every entry point include/rp_b200.h declares (no compute call)."""
+    import ctypes
+    import re
+
+    from replay_b200 import _lib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "rp_b200.h")).read()
+    names = set(re.findall(r"\b(rp_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 15
+    if not os.path.exists(_lib.LIB_PATH):
+        from replay_b200.build import build
+
+        build(verbose=False)
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(h, n), n
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from replay_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.RpError):
+        _lib.lib()

@@ -67,3 +67,12 @@ class Trainer:
         self._all_reduce()
         self._g_opt.replay()
         return e.ce.loss
+
+
+def user_shard(n_users: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, exact (no wrap-around duplicates) shard of the users for predict(): SURVEY.md §8e.  The reference's
+    own DP sharding pads by wrap-around (replay/data/nn/parquet/info/partitioning.py:102-122) and can emit duplicated
+    users at the tail; here every user is scored exactly once."""
+    base, rem = divmod(n_users, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

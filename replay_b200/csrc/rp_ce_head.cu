@@ -29,6 +29,23 @@ static constexpr float kLn2 = 0.6931471805599453f;
 static constexpr int kEpiWarps = 8;
 static constexpr int kThreads = 64 + kEpiWarps * 32;
 
+// tuning knobs (measured on B200, see profiles/): every RP_CE_POLY_EVERY-th exponential goes to the FMA-pipe polynomial
+// instead of MUFU.EX2 (0 = MUFU only); RP_CE_NBUF3 = 1 triple-buffers S in TMEM for d <= 128.
+#ifndef RP_CE_POLY_EVERY
+#define RP_CE_POLY_EVERY 4   /* forward: 25 % of the exponentials on the FMA pipe (measured best, profiles/r1_ce_variants.md) */
+#endif
+#ifndef RP_CE_POLY_EVERY_BWD
+#define RP_CE_POLY_EVERY_BWD 8   /* backward: 12.5 % */
+#endif
+#ifndef RP_CE_NBUF3
+#define RP_CE_NBUF3 1
+#endif
+template <int DEG, int EVERY>
+__device__ __forceinline__ float ce_ex2(float x, int q) {
+  if (EVERY > 0 && (q % (EVERY > 0 ? EVERY : 1)) == 1) return ex2_poly<DEG>(x);
+  return ex2f(x);
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // forward
 // ----------------------------------------------------------------------------------------------------------------
@@ -121,37 +138,39 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       mbar_wait(&bar_tfull[as], aph);
       tc_fence_after();
       const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + as * kT + half * 64;
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t raw[32];
-        tmem_ld32(tbase + c, raw);
-        tmem_ld_wait();
-        const int col0 = j * kT + half * 64 + c;
-        float x[32];
-#pragma unroll
-        for (int q = 0; q < 32; ++q) x[q] = __uint_as_float(raw[q]);
-        if (col0 + 32 > n_items) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if (col0 + q >= n_items) x[q] = -INFINITY;
-        }
-        float cm = x[0];
-#pragma unroll
-        for (int q = 1; q < 32; ++q) cm = fmaxf(cm, x[q]);
-        const float mn = fmaxf(m, cm * kLog2e);
-        ssum *= ex2f(m - mn);
-        m = mn;
-        float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-        for (int q = 0; q < 32; q += 2) {
-          acc0 += ex2f(fmaf(x[q], kLog2e, -mn));
-          acc1 += ex2f(fmaf(x[q + 1], kLog2e, -mn));
-        }
-        ssum += acc0 + acc1;
-      }
+      uint32_t raw[64];
+      tmem_ld32(tbase, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+      tmem_ld32(tbase + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
+      tmem_ld_wait();
+      // the accumulator stage is free as soon as its values sit in registers
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[as]);
+      const int col0 = j * kT + half * 64;
+      if (col0 + 64 > n_items) {  // ragged last tile
+#pragma unroll
+        for (int q = 0; q < 64; ++q)
+          if (col0 + q >= n_items) raw[q] = 0xff800000u;  // -inf
+      }
+      float cm0 = __uint_as_float(raw[0]), cm1 = __uint_as_float(raw[1]);
+#pragma unroll
+      for (int q = 2; q < 64; q += 2) {
+        cm0 = fmaxf(cm0, __uint_as_float(raw[q]));
+        cm1 = fmaxf(cm1, __uint_as_float(raw[q + 1]));
+      }
+      const float mn = fmaxf(m, fmaxf(cm0, cm1) * kLog2e);
+      ssum *= ex2f(m - mn);
+      m = mn;
+      // half of the exponentials on MUFU, half on the FMA pipe
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 64; q += 4) {
+        a0 += ce_ex2<4, RP_CE_POLY_EVERY>(fmaf(__uint_as_float(raw[q + 0]), kLog2e, -mn), q + 0);
+        a1 += ce_ex2<4, RP_CE_POLY_EVERY>(fmaf(__uint_as_float(raw[q + 1]), kLog2e, -mn), q + 1);
+        a2 += ce_ex2<4, RP_CE_POLY_EVERY>(fmaf(__uint_as_float(raw[q + 2]), kLog2e, -mn), q + 2);
+        a3 += ce_ex2<4, RP_CE_POLY_EVERY>(fmaf(__uint_as_float(raw[q + 3]), kLog2e, -mn), q + 3);
+      }
+      ssum += (a0 + a1) + (a2 + a3);
     }
     if (t < n_valid) part[((size_t)t * n_splits + split) * 2 + half] = make_float2(m, ssum);
   }
@@ -233,7 +252,7 @@ __global__ void ce_finalize_kernel(const float2* __restrict__ part, const __nv_b
 //   COLCONST = false : rows = tokens (A = Hc tile), columns = items  -> acc = dHc tile [128, d]
 //   COLCONST = true  : rows = items  (A = E tile),  columns = tokens -> acc = dE tile  [128, d]
 // ----------------------------------------------------------------------------------------------------------------
-template <int KCH, int NSTAGE, bool COLCONST>
+template <int KCH, int NSTAGE, bool COLCONST, int NBUF>
 __global__ void __launch_bounds__(kThreads, 1)
 ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const float* __restrict__ cvec /* [T] exponent offsets per token */, const int32_t* __restrict__ labels,
@@ -246,7 +265,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStage;
   __shared__ __align__(16) float s_cc[NSTAGE][kT];
-  __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_sfull[2], bar_sfree[2], bar_pfull[2], bar_acc;
+  __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_sfull[NBUF], bar_sfree[NBUF], bar_pfull[NBUF], bar_acc;
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -263,7 +282,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NBUF; ++i) {
       mbar_init(&bar_sfull[i], 1);
       mbar_init(&bar_sfree[i], 1);
       mbar_init(&bar_pfull[i], kEpiWarps);
@@ -278,7 +297,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t tmem_acc = tmem + 256;
+  const uint32_t tmem_acc = tmem + NBUF * kT;   // S buffers first, then the [128 x D] accumulator
 
   if (warp == 0) {
     if (elect_one()) {
@@ -307,9 +326,9 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       auto issue_mma1 = [&](int j) {
         const uint32_t s = j % NSTAGE, ph = (j / NSTAGE) & 1;
         mbar_wait(&bar_full[s], ph);
-        if (j >= 2) mbar_wait(&bar_sfree[j & 1], ((j >> 1) - 1) & 1);
+        if (j >= NBUF) mbar_wait(&bar_sfree[j % NBUF], ((j / NBUF) - 1) & 1);
         tc_fence_after();
-        const uint32_t dcol = tmem + (j & 1) * kT;
+        const uint32_t dcol = tmem + (j % NBUF) * kT;
 #pragma unroll
         for (int kc = 0; kc < KCH; ++kc) {
           const uint32_t a0 = smem_u32(sA + kc * kChunk), b0 = smem_u32(sB + s * kStage + kc * kChunk);
@@ -318,22 +337,22 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             umma_ss(dcol, umma_desc_sw128(a0 + ks * 32, 16, 1024), umma_desc_sw128(b0 + ks * 32, 16, 1024), idesc1,
                     (kc | ks) != 0);
         }
-        umma_commit(&bar_sfull[j & 1]);
+        umma_commit(&bar_sfull[j % NBUF]);
       };
-      issue_mma1(0);
+      for (int j = 0; j < NBUF - 1 && j < n_ct; ++j) issue_mma1(j);
       for (int j = 0; j < n_ct; ++j) {
-        if (j + 1 < n_ct) issue_mma1(j + 1);
+        if (j + NBUF - 1 < n_ct) issue_mma1(j + NBUF - 1);
         const uint32_t s = j % NSTAGE;
-        mbar_wait(&bar_pfull[j & 1], (j >> 1) & 1);
+        mbar_wait(&bar_pfull[j % NBUF], (j / NBUF) & 1);
         tc_fence_after();
-        const uint32_t pcol = tmem + (j & 1) * kT;  // G (bf16 pairs) lives over S: k-steps 0-3 at +0, 4-7 at +64
+        const uint32_t pcol = tmem + (j % NBUF) * kT;  // G (bf16 pairs) lives over S: k-steps 0-3 at +0, 4-7 at +64
         const uint32_t b0 = smem_u32(sB + s * kStage);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
           umma_ts(tmem_acc, pcol + (ks >> 2) * 64 + (ks & 3) * 8, umma_desc_sw128(b0 + ks * 2048, kChunk, 1024), idesc2,
                   (j | ks) != 0);
         umma_commit(&bar_empty[s]);
-        umma_commit(&bar_sfree[j & 1]);
+        umma_commit(&bar_sfree[j % NBUF]);
       }
       umma_commit(&bar_acc);
     }
@@ -344,45 +363,45 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     float crow = 0.f;
     if (!COLCONST) crow = (r0 + row < n_valid) ? cvec[r0 + row] : -INFINITY;
     for (int j = 0; j < n_ct; ++j) {
-      const uint32_t b = j & 1, s = j % NSTAGE;
+      const uint32_t b = j % NBUF, s = j % NSTAGE;
       if (COLCONST) mbar_wait(&bar_full[s], (j / NSTAGE) & 1);  // s_cc[s] was written by the async proxy
-      mbar_wait(&bar_sfull[b], (j >> 1) & 1);
+      mbar_wait(&bar_sfull[b], (j / NBUF) & 1);
       tc_fence_after();
       const uint32_t sbase = tmem + lane_base + b * kT + half * 64;
+      uint32_t raw[64];
+      tmem_ld32(sbase, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+      tmem_ld32(sbase + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
+      tmem_ld_wait();
+      uint32_t pk[32];
+      const int col0 = j * kT + half * 64;
+      // G = exp2(S*log2e + offset): alternate MUFU.EX2 and the FMA-pipe polynomial so neither pipe paces the tile
+      if (COLCONST) {
+        const float4* cc = reinterpret_cast<const float4*>(&s_cc[s][half * 64]);
 #pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t raw[32];
-        tmem_ld32(sbase + c, raw);
-        tmem_ld_wait();
-        uint32_t pk[16];
-        if (COLCONST) {
-          const float4* cc = reinterpret_cast<const float4*>(&s_cc[s][half * 64 + c]);
-#pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            const float4 o = cc[q >> 2];
-            const float g0 = ex2f(fmaf(__uint_as_float(raw[q + 0]), kLog2e, o.x));
-            const float g1 = ex2f(fmaf(__uint_as_float(raw[q + 1]), kLog2e, o.y));
-            const float g2 = ex2f(fmaf(__uint_as_float(raw[q + 2]), kLog2e, o.z));
-            const float g3 = ex2f(fmaf(__uint_as_float(raw[q + 3]), kLog2e, o.w));
-            pk[(q >> 1) + 0] = pack_bf16(g0, g1);
-            pk[(q >> 1) + 1] = pack_bf16(g2, g3);
-          }
-        } else {
-          const int col0 = j * kT + half * 64 + c;
-#pragma unroll
-          for (int q = 0; q < 32; q += 2) {
-            float g0 = ex2f(fmaf(__uint_as_float(raw[q + 0]), kLog2e, crow));
-            float g1 = ex2f(fmaf(__uint_as_float(raw[q + 1]), kLog2e, crow));
-            if (col0 + 32 > n_items) {  // columns beyond the catalog do not exist
-              if (col0 + q >= n_items) g0 = 0.f;
-              if (col0 + q + 1 >= n_items) g1 = 0.f;
-            }
-            pk[q >> 1] = pack_bf16(g0, g1);
-          }
+        for (int q = 0; q < 64; q += 4) {
+          const float4 o = cc[q >> 2];
+          const float g0 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 0]), kLog2e, o.x), q + 0);
+          const float g1 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 1]), kLog2e, o.y), q + 1);
+          const float g2 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 2]), kLog2e, o.z), q + 2);
+          const float g3 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 3]), kLog2e, o.w), q + 3);
+          pk[(q >> 1) + 0] = pack_bf16(g0, g1);
+          pk[(q >> 1) + 1] = pack_bf16(g2, g3);
         }
-        // in place over the already-consumed S columns of this warp: chunk c -> columns [c/2, c/2+16)
-        tmem_st16(sbase + (c >> 1), pk);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 64; q += 2) {
+          float g0 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 0]), kLog2e, crow), q + 0);
+          float g1 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 1]), kLog2e, crow), q + 1);
+          if (col0 + 64 > n_items) {  // columns beyond the catalog do not exist
+            if (col0 + q >= n_items) g0 = 0.f;
+            if (col0 + q + 1 >= n_items) g1 = 0.f;
+          }
+          pk[q >> 1] = pack_bf16(g0, g1);
+        }
       }
+      // in place over this warp's own (already consumed) S columns: 64 fp32 columns -> 32 packed columns
+      tmem_st16(sbase, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+      tmem_st16(sbase + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -543,7 +562,8 @@ static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const f
                          const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, void* out,
                          int grid, cudaStream_t stream) {
   const int smem = (1 + NSTAGE) * KCH * kChunk + 1024;
-  auto kern = ce_bwd_kernel<KCH, NSTAGE, COLCONST>;
+  constexpr int NBUF = (RP_CE_NBUF3 && KCH <= 2) ? 3 : 2;  // 3 S buffers + [128 x d] accumulator fit the 512 TMEM columns up to d = 128
+  auto kern = ce_bwd_kernel<KCH, NSTAGE, COLCONST, NBUF>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, cvec, labels, reinterpret_cast<const __nv_bfloat16*>(table), loss_inv,
                                          n_valid, n_items, out);

@@ -191,6 +191,30 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2 on the FMA/ALU pipes (Cody-Waite + minimax polynomial on [-0.5, 0.5]); used next to MUFU.EX2 so that the softmax
+// exponentials of the CE head are split across two pipes (the tensor pipe outruns a MUFU-only epilogue at d = 128).
+// DEG 3: max rel. error 1.0e-4 (inputs to a bf16 operand), DEG 4: 3.6e-6 (fp32 sums).  Inputs below -126 flush to ~1e-38.
+template <int DEG>
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float magic = 12582912.f;  // 1.5 * 2^23: adding it rounds x to the nearest integer in the low mantissa bits
+  const float xr = x + magic;
+  const int n = __float_as_int(xr);
+  const float f = x - (xr - magic);
+  float p;
+  if (DEG == 3) {
+    p = fmaf(f, 0.05592203512787819f, 0.24264007806777954f);
+    p = fmaf(p, f, 0.6931210160255432f);
+    p = fmaf(p, f, 0.9999244809150696f);
+  } else {
+    p = fmaf(f, 0.009676037356257439f, 0.05592203512787819f);
+    p = fmaf(p, f, 0.2402210682630539f);
+    p = fmaf(p, f, 0.6931210160255432f);
+    p = fmaf(p, f, 1.0000001192092896f);
+  }
+  return __int_as_float(__float_as_int(p) + (n << 23));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

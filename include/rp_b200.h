@@ -51,7 +51,7 @@ int rp_seen_prepare(const int64_t* seen_ids, int n_users, int S, int item_count,
 size_t rp_score_topk_workspace(int n_users, int n_items, int d, int K);
 
 /* hq bf16 [n_users, d]; table bf16 [n_items, d] (the rows that are scored: all items, or the gathered candidates);
- * bias fp32 [n_items] or NULL; seen_sorted from rp_seen_prepare or NULL (no filter); candidates int64 [n_items] or NULL
+ * bias fp32 [round_up(n_items,128)] or NULL (BERT4Rec head); seen_sorted from rp_seen_prepare or NULL (no filter); candidates int64 [n_items] or NULL
  * (maps a scored column back to an item id, predictions_callback.py:91-92).
  * out_ids int64 [n_users, K], out_scores fp32 [n_users, K], sorted by (score desc, column asc).
  * d in {64,128,256,512}; 1 <= K <= 32. */
@@ -67,21 +67,24 @@ int rp_score_topk(const void* hq, const void* table, const float* bias, const in
  *                                                    replay/models/nn/sequential/bert4rec/lightning.py:332-351
  *             and autograd's backward of both.
  * hc bf16 [capacity, d]: hidden rows of the VALID targets, compacted (rows >= *n_valid are ignored but must be finite);
- * table bf16 [n_items, d]; labels int32 [capacity]; n_valid int32 [1] IN DEVICE MEMORY (keeps the step graph-capturable).
+ * table bf16 [n_items, d] (tied item table or the untied Linear weight); bias fp32 [round_up(n_items,128)] or NULL
+ * (bert4rec/model.py:363-382: logits = F.linear(h, W, b)); d_bias fp32 [n_items] is overwritten when bias is given;
+ * labels int32 [capacity]; n_valid int32 [1] IN DEVICE MEMORY (keeps the step graph-capturable).
  * ------------------------------------------------------------------------------------------------------------- */
 size_t rp_ce_head_workspace(int capacity_tokens, int n_items, int d);
 
 /* loss_out fp32 [2] = { mean CE over the valid targets, 1 / n_valid }; lse fp32 [capacity];
  * cvec fp32 [round_up(capacity,128)] (per-token exponent offsets for the backward; entries >= capacity must be -inf). */
-int rp_ce_head_fwd(const void* hc, const void* table, const int32_t* labels, const int32_t* n_valid, int capacity,
-                   int n_items, int d, float* loss_out, float* lse, float* cvec, void* workspace, size_t workspace_bytes,
-                   void* stream);
+int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, const int32_t* labels, const int32_t* n_valid,
+                   int capacity, int n_items, int d, float* loss_out, float* lse, float* cvec, void* workspace,
+                   size_t workspace_bytes, void* stream);
 
 /* gradients of the mean CE for d(loss) = 1:  d_hc bf16 [capacity, d] (rows < *n_valid written);
  * d_table fp32 [n_items, d] is OVERWRITTEN (softmax part) and then atomically corrected by the one-hot part.
  * d in {64,128,256}. */
-int rp_ce_head_bwd(const void* hc, const void* table, const int32_t* labels, const int32_t* n_valid, int capacity,
-                   int n_items, int d, const float* loss_out, const float* cvec, void* d_hc, float* d_table, void* stream);
+int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, const int32_t* labels, const int32_t* n_valid,
+                   int capacity, int n_items, int d, const float* loss_out, const float* cvec, void* d_hc, float* d_table,
+                   float* d_bias, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Transformer body.  All activations are token-major bf16 [T = B*L, d]; weights are the bf16 shadow of the fp32 masters.
@@ -98,7 +101,9 @@ int rp_ce_head_bwd(const void* hc, const void* table, const int32_t* labels, con
  * out_mode 0: bf16 store, 1: fp32 atomic add (split_k >= 1), 2: fp32 store.
  * Epilogue order: alpha, bias[N], act (0 none, 1 ReLU, 2 GELU-erf), Philox dropout(drop_p; seed + *seed_ptr, drop_offset +
  * element offset in C), gate (x *= gate != 0 ? gate_scale : 0, same geometry as C), residual (bf16, same geometry as C),
- * rowmask[rowmask_off0 + outer*rowmask_oo + m]. */
+ * post-residual dropout (post_drop_p, post_drop_offset), rowmask[rowmask_off0 + outer*rowmask_oo + m].
+ * C2 (optional, bf16, geometry of C) receives the value after the bias and before the activation; gate_mode 1 multiplies
+ * by gelu'(gate) instead of the (gate != 0) test. */
 typedef struct rp_gemm_desc {
   const void* A; long long a_rows, a_cols, lda; int a_mn;
   const void* B; long long b_rows, b_cols, ldb; int b_mn;
@@ -111,6 +116,7 @@ typedef struct rp_gemm_desc {
   float drop_p; unsigned long long seed, drop_offset; const unsigned long long* seed_ptr;
   int split_k;
   const void* gate; float gate_scale;
+  void* C2; int gate_mode; float post_drop_p; unsigned long long post_drop_offset;
 } rp_gemm_desc;
 int rp_gemm(const rp_gemm_desc* g, void* stream);
 
@@ -172,6 +178,17 @@ int rp_colsum(const void* dy, int rows, int cols, long long ld, float* db, void*
 
 /* torch.optim.Adam (models/nn/optimizer_utils/optimizer_factory.py:71-87; no weight decay) on flat fp32 buffers; refreshes
  * the bf16 shadow, optionally zeroes the gradient; lr and the step counter live in device memory. */
+/* BERT4Rec embedding: where(token_mask, table[ids], mask_emb) + pos[t % L] (bert4rec/model.py:239-296) and its backward;
+ * row gather / scatter with a device-side row count (dst[r] = src[idx[r]] or dst[idx[r]] = src[r]). */
+int rp_bert_embed_fwd(const void* table, const void* mask_emb, const float* pos, const int32_t* ids, const uint8_t* tok_mask,
+                      int T, int L, int d, float drop_p, unsigned long long seed, unsigned long long drop_off,
+                      const unsigned long long* seed_ptr, void* out, void* stream);
+int rp_bert_embed_bwd(const void* dx, const int32_t* ids, const uint8_t* pad_mask, const uint8_t* tok_mask, int B, int L, int d,
+                      float drop_p, unsigned long long seed, unsigned long long drop_off, const unsigned long long* seed_ptr,
+                      float* d_table, float* d_mask_emb, float* d_pos, void* stream);
+int rp_gather_rows(const void* src, const int32_t* idx, int n_max, const int32_t* n_dev, int d, void* dst, int scatter,
+                   void* stream);
+
 int rp_adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, long long n, const float* lr_dev,
                  int32_t* step_dev, float beta1, float beta2, float eps, float grad_scale, const uint8_t* frozen,
                  int zero_grad, void* stream);

@@ -52,8 +52,8 @@ def lib():
     _sig(L.rp_score_topk_workspace, c_size_t, [c_int, c_int, c_int, c_int])
     _sig(L.rp_score_topk, c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P])
     _sig(L.rp_ce_head_workspace, c_size_t, [c_int, c_int, c_int])
-    _sig(L.rp_ce_head_fwd, c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, c_size_t, P])
-    _sig(L.rp_ce_head_bwd, c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P])
+    _sig(L.rp_ce_head_fwd, c_int, [P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, c_size_t, P])
+    _sig(L.rp_ce_head_bwd, c_int, [P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P])
     U64, LL = ctypes.c_ulonglong, ctypes.c_longlong
     _sig(L.rp_gemm, c_int, [ctypes.POINTER(GemmDesc), P])
     _sig(L.rp_attn_fwd, c_int, [ctypes.POINTER(AttnDesc), P])
@@ -68,6 +68,9 @@ def lib():
     _sig(L.rp_adam_step, c_int, [P, P, P, P, P, LL, P, P, c_float, c_float, c_float, c_float, P, c_int, P])
     _sig(L.rp_cast_bf16, c_int, [P, P, LL, P])
     _sig(L.rp_counter_add, c_int, [P, U64, P])
+    _sig(L.rp_bert_embed_fwd, c_int, [P, P, P, P, P, c_int, c_int, c_int, c_float, U64, U64, P, P, P])
+    _sig(L.rp_bert_embed_bwd, c_int, [P, P, P, P, c_int, c_int, c_int, c_float, U64, U64, P, P, P, P, P])
+    _sig(L.rp_gather_rows, c_int, [P, P, c_int, P, c_int, P, c_int, P])
     for name, restype, argtypes in _EXTRA_SIGS:
         _sig(getattr(L, name), restype, argtypes)
     _lib = L
@@ -90,6 +93,7 @@ class GemmDesc(ctypes.Structure):
         ("drop_p", c_float), ("seed", ctypes.c_ulonglong), ("drop_offset", ctypes.c_ulonglong), ("seed_ptr", c_void_p),
         ("split_k", c_int),
         ("gate", c_void_p), ("gate_scale", c_float),
+        ("C2", c_void_p), ("gate_mode", c_int), ("post_drop_p", c_float), ("post_drop_offset", ctypes.c_ulonglong),
     ]
 
 

@@ -52,7 +52,7 @@ __device__ __forceinline__ float ce_ex2(float x, int q) {
 template <int KCH, int NSTAGE>
 __global__ void __launch_bounds__(kThreads, 1)
 ce_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-              const int32_t* __restrict__ n_valid_ptr, int n_items, int n_splits,
+              const int32_t* __restrict__ n_valid_ptr, int n_items, int n_splits, const float* __restrict__ bias,
               float2* __restrict__ part /* [T, n_splits, 2] (m in log2 units, s) */) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -147,6 +147,16 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[as]);
       const int col0 = j * kT + half * 64;
+      if (bias) {  // untied / biased head (BERT4Rec): logits = h.W^T + b ; warp-uniform 16-byte loads (bias is padded to 128)
+#pragma unroll
+        for (int q = 0; q < 64; q += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
+          raw[q + 0] = __float_as_uint(__uint_as_float(raw[q + 0]) + b4.x);
+          raw[q + 1] = __float_as_uint(__uint_as_float(raw[q + 1]) + b4.y);
+          raw[q + 2] = __float_as_uint(__uint_as_float(raw[q + 2]) + b4.z);
+          raw[q + 3] = __float_as_uint(__uint_as_float(raw[q + 3]) + b4.w);
+        }
+      }
       if (col0 + 64 > n_items) {  // ragged last tile
 #pragma unroll
         for (int q = 0; q < 64; ++q)
@@ -184,7 +194,8 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 // Deterministic: per-block partial sums, the last block adds them in index order.
 __global__ void ce_finalize_kernel(const float2* __restrict__ part, const __nv_bfloat16* __restrict__ hc,
                                    const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ labels,
-                                   const int32_t* __restrict__ n_valid_ptr, int n_part, int capacity, int d,
+                                   const float* __restrict__ bias, const int32_t* __restrict__ n_valid_ptr, int n_part,
+                                   int capacity, int d,
                                    float* __restrict__ lse_out, float* __restrict__ cvec, float* __restrict__ block_sums,
                                    unsigned int* __restrict__ ticket, float* __restrict__ loss_out) {
   const int n_valid = *n_valid_ptr;
@@ -215,6 +226,7 @@ __global__ void ce_finalize_kernel(const float2* __restrict__ part, const __nv_b
         S += __shfl_xor_sync(0xffffffffu, S, o);
         z += __shfl_xor_sync(0xffffffffu, z, o);
       }
+      if (bias) z += bias[labels[t]];
       const float lse2 = M + log2f(S);  // log2 units
       const float lse = lse2 * kLn2;
       if (lane == 0) {
@@ -257,7 +269,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const float* __restrict__ cvec /* [T] exponent offsets per token */, const int32_t* __restrict__ labels,
               const __nv_bfloat16* __restrict__ table, const float* __restrict__ loss_inv /* [1] = 1/T_v */,
-              const int32_t* __restrict__ n_valid_ptr, int n_items, void* __restrict__ out) {
+              const int32_t* __restrict__ n_valid_ptr, int n_items, const float* __restrict__ bias,
+              float* __restrict__ d_bias, void* __restrict__ out) {
   constexpr int D = KCH * 64;
   constexpr int kStage = KCH * kChunk;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -265,6 +278,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStage;
   __shared__ __align__(16) float s_cc[NSTAGE][kT];
+  __shared__ float s_gsum[2][kT];
   __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_sfull[NBUF], bar_sfree[NBUF], bar_pfull[NBUF], bar_acc;
   __shared__ uint32_t tmem_slot;
 
@@ -362,6 +376,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     float crow = 0.f;
     if (!COLCONST) crow = (r0 + row < n_valid) ? cvec[r0 + row] : -INFINITY;
+    float gsum = 0.f;  // COL mode with bias: sum over tokens of G (before the e^{b_i} row factor) -> bias gradient
     for (int j = 0; j < n_ct; ++j) {
       const uint32_t b = j % NBUF, s = j % NSTAGE;
       if (COLCONST) mbar_wait(&bar_full[s], (j / NSTAGE) & 1);  // s_cc[s] was written by the async proxy
@@ -384,10 +399,21 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const float g1 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 1]), kLog2e, o.y), q + 1);
           const float g2 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 2]), kLog2e, o.z), q + 2);
           const float g3 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 3]), kLog2e, o.w), q + 3);
+          if (d_bias) gsum += (g0 + g1) + (g2 + g3);
           pk[(q >> 1) + 0] = pack_bf16(g0, g1);
           pk[(q >> 1) + 1] = pack_bf16(g2, g3);
         }
       } else {
+        if (bias) {  // per-column bias: s + b before the exponential (warp-uniform 16-byte loads)
+#pragma unroll
+          for (int q = 0; q < 64; q += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
+            raw[q + 0] = __float_as_uint(__uint_as_float(raw[q + 0]) + b4.x);
+            raw[q + 1] = __float_as_uint(__uint_as_float(raw[q + 1]) + b4.y);
+            raw[q + 2] = __float_as_uint(__uint_as_float(raw[q + 2]) + b4.z);
+            raw[q + 3] = __float_as_uint(__uint_as_float(raw[q + 3]) + b4.w);
+          }
+        }
 #pragma unroll
         for (int q = 0; q < 64; q += 2) {
           float g0 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 0]), kLog2e, crow), q + 0);
@@ -415,6 +441,13 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const uint32_t abase = tmem_acc + lane_base + half * HALF_D;
     if (COLCONST) {
       float* o = reinterpret_cast<float*>(out);
+      // biased head: G carries a per-item factor e^{b_i}; it was left out of the loop and is applied to the row here
+      const float rs = (bias && r < n_items) ? __expf(bias[r]) : 1.f;
+      if (d_bias) {
+        s_gsum[half][row] = gsum;
+        asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");  // epilogue warps only
+        if (half == 0 && r < n_items) d_bias[r] = (s_gsum[0][row] + s_gsum[1][row]) * rs;
+      }
 #pragma unroll 1
       for (int c = 0; c < HALF_D; c += 32) {
         uint32_t raw[32];
@@ -424,8 +457,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           float4* dst = reinterpret_cast<float4*>(o + (size_t)r * D + half * HALF_D + c);
 #pragma unroll
           for (int q = 0; q < 32; q += 4)
-            dst[q >> 2] = make_float4(__uint_as_float(raw[q]), __uint_as_float(raw[q + 1]), __uint_as_float(raw[q + 2]),
-                                      __uint_as_float(raw[q + 3]));
+            dst[q >> 2] = make_float4(__uint_as_float(raw[q]) * rs, __uint_as_float(raw[q + 1]) * rs,
+                                      __uint_as_float(raw[q + 2]) * rs, __uint_as_float(raw[q + 3]) * rs);
         }
       }
     } else {
@@ -466,9 +499,12 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 // dE[y_t, :] -= Hc[t, :] / T_v   (fp32 atomics; several tokens may share a label)
 __global__ void ce_label_scatter_kernel(const __nv_bfloat16* __restrict__ hc, const int32_t* __restrict__ labels,
                                         const float* __restrict__ loss_inv, const int32_t* __restrict__ n_valid_ptr,
-                                        int d, float* __restrict__ dE) {
+                                        int d, float* __restrict__ dE, float* __restrict__ d_bias) {
   const int n_valid = *n_valid_ptr;
   const float inv_n = loss_inv[0];
+  if (d_bias)
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_valid; t += gridDim.x * blockDim.x)
+      atomicAdd(d_bias + labels[t], -inv_n);
   const int per_row = d / 2;
   const long long total = (long long)n_valid * per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -509,11 +545,11 @@ RP_API size_t rp_ce_head_workspace(int capacity_tokens, int n_items, int d) {
 
 template <int KCH, int NSTAGE>
 static int launch_ce_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const int32_t* n_valid, int n_items,
-                         int n_splits, int n_tok_tiles, float2* part, cudaStream_t stream) {
+                         int n_splits, int n_tok_tiles, const float* bias, float2* part, cudaStream_t stream) {
   const int smem = (KCH + NSTAGE) * kChunk + 1024;
   auto kern = ce_fwd_kernel<KCH, NSTAGE>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<n_tok_tiles * n_splits, kThreads, smem, stream>>>(tmA, tmB, n_valid, n_items, n_splits, part);
+  kern<<<n_tok_tiles * n_splits, kThreads, smem, stream>>>(tmA, tmB, n_valid, n_items, n_splits, bias, part);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }
@@ -521,9 +557,9 @@ static int launch_ce_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const i
 // hc bf16 [capacity, d] (rows >= *n_valid ignored), table bf16 [n_items, d], labels int32 [capacity],
 // n_valid int32 [1] (device).  Outputs: loss_out fp32 [2] = {mean CE, 1/T_v}; lse fp32 [capacity];
 // cvec fp32 [capacity] (exponent offsets consumed by rp_ce_head_bwd).
-RP_API int rp_ce_head_fwd(const void* hc, const void* table, const int32_t* labels, const int32_t* n_valid,
-                          int capacity, int n_items, int d, float* loss_out, float* lse, float* cvec, void* workspace,
-                          size_t workspace_bytes, void* stream_) {
+RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, const int32_t* labels,
+                          const int32_t* n_valid, int capacity, int n_items, int d, float* loss_out, float* lse, float* cvec,
+                          void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!hc || !table || !labels || !n_valid || !loss_out || !lse || !cvec || !workspace) return RP_EINVAL;
   if (capacity <= 0 || n_items <= 0) return RP_ESHAPE;
@@ -541,17 +577,17 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const int32_t* labe
   if ((rc = make_tmap_bf16(&tmA, hc, capacity, d, d, 128)) != RP_OK) return rc;
   if ((rc = make_tmap_bf16(&tmB, table, n_items, d, d, 128)) != RP_OK) return rc;
   switch (d) {
-    case 64: rc = launch_ce_fwd<1, 8>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, part, stream); break;
-    case 128: rc = launch_ce_fwd<2, 8>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, part, stream); break;
-    case 256: rc = launch_ce_fwd<4, 8>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, part, stream); break;
-    default: rc = launch_ce_fwd<8, 5>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, part, stream); break;
+    case 64: rc = launch_ce_fwd<1, 8>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, bias, part, stream); break;
+    case 128: rc = launch_ce_fwd<2, 8>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, bias, part, stream); break;
+    case 256: rc = launch_ce_fwd<4, 8>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, bias, part, stream); break;
+    default: rc = launch_ce_fwd<8, 5>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, bias, part, stream); break;
   }
   if (rc != RP_OK) return rc;
   RP_CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, stream));
   int blocks = (capacity + 7) / 8;
   if (blocks > 1024) blocks = 1024;
   ce_finalize_kernel<<<blocks, 256, 0, stream>>>(part, reinterpret_cast<const __nv_bfloat16*>(hc),
-                                                 reinterpret_cast<const __nv_bfloat16*>(table), labels, n_valid, P * 2,
+                                                 reinterpret_cast<const __nv_bfloat16*>(table), labels, bias, n_valid, P * 2,
                                                  capacity, d, lse, cvec, block_sums, ticket, loss_out);
   RP_LAUNCH_CHECK();
   return RP_OK;
@@ -559,14 +595,14 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const int32_t* labe
 
 template <int KCH, int NSTAGE, bool COLCONST>
 static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* cvec, const int32_t* labels,
-                         const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, void* out,
-                         int grid, cudaStream_t stream) {
+                         const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, const float* bias,
+                         float* d_bias, void* out, int grid, cudaStream_t stream) {
   const int smem = (1 + NSTAGE) * KCH * kChunk + 1024;
   constexpr int NBUF = (RP_CE_NBUF3 && KCH <= 2) ? 3 : 2;  // 3 S buffers + [128 x d] accumulator fit the 512 TMEM columns up to d = 128
   auto kern = ce_bwd_kernel<KCH, NSTAGE, COLCONST, NBUF>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, cvec, labels, reinterpret_cast<const __nv_bfloat16*>(table), loss_inv,
-                                         n_valid, n_items, out);
+                                         n_valid, n_items, bias, d_bias, out);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }
@@ -575,11 +611,12 @@ static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const f
 //   d_hc   bf16 [capacity, d]  (rows < *n_valid written)
 //   d_table fp32 [n_items, d]  OVERWRITTEN with softmax^T . hc / T_v, then the one-hot part is atomically subtracted.
 // d in {64,128,256}.
-RP_API int rp_ce_head_bwd(const void* hc, const void* table, const int32_t* labels, const int32_t* n_valid,
-                          int capacity, int n_items, int d, const float* loss_out /* from fwd */,
-                          const float* cvec /* from fwd */, void* d_hc, float* d_table, void* stream_) {
+RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, const int32_t* labels,
+                          const int32_t* n_valid, int capacity, int n_items, int d, const float* loss_out /* from fwd */,
+                          const float* cvec /* from fwd */, void* d_hc, float* d_table, float* d_bias, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!hc || !table || !labels || !n_valid || !loss_out || !cvec || !d_hc || !d_table) return RP_EINVAL;
+  if ((bias == nullptr) != (d_bias == nullptr)) return RP_EINVAL;
   if (capacity <= 0 || n_items <= 0) return RP_ESHAPE;
   if (d != 64 && d != 128 && d != 256) return RP_ESHAPE;
   CUtensorMap tmH, tmE;
@@ -590,24 +627,24 @@ RP_API int rp_ce_head_bwd(const void* hc, const void* table, const int32_t* labe
   const float* loss_inv = loss_out + 1;
   switch (d) {
     case 64:
-      rc = launch_ce_bwd<1, 6, false>(tmH, tmE, cvec, labels, table, loss_inv, n_valid, n_items, d_hc, n_tok_tiles, stream);
+      rc = launch_ce_bwd<1, 6, false>(tmH, tmE, cvec, labels, table, loss_inv, n_valid, n_items, bias, nullptr, d_hc, n_tok_tiles, stream);
       if (rc == RP_OK)
-        rc = launch_ce_bwd<1, 6, true>(tmE, tmH, cvec, labels, table, loss_inv, n_valid, n_items, d_table, n_item_tiles, stream);
+        rc = launch_ce_bwd<1, 6, true>(tmE, tmH, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, d_table, n_item_tiles, stream);
       break;
     case 128:
-      rc = launch_ce_bwd<2, 4, false>(tmH, tmE, cvec, labels, table, loss_inv, n_valid, n_items, d_hc, n_tok_tiles, stream);
+      rc = launch_ce_bwd<2, 4, false>(tmH, tmE, cvec, labels, table, loss_inv, n_valid, n_items, bias, nullptr, d_hc, n_tok_tiles, stream);
       if (rc == RP_OK)
-        rc = launch_ce_bwd<2, 4, true>(tmE, tmH, cvec, labels, table, loss_inv, n_valid, n_items, d_table, n_item_tiles, stream);
+        rc = launch_ce_bwd<2, 4, true>(tmE, tmH, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, d_table, n_item_tiles, stream);
       break;
     default:
-      rc = launch_ce_bwd<4, 2, false>(tmH, tmE, cvec, labels, table, loss_inv, n_valid, n_items, d_hc, n_tok_tiles, stream);
+      rc = launch_ce_bwd<4, 2, false>(tmH, tmE, cvec, labels, table, loss_inv, n_valid, n_items, bias, nullptr, d_hc, n_tok_tiles, stream);
       if (rc == RP_OK)
-        rc = launch_ce_bwd<4, 2, true>(tmE, tmH, cvec, labels, table, loss_inv, n_valid, n_items, d_table, n_item_tiles, stream);
+        rc = launch_ce_bwd<4, 2, true>(tmE, tmH, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, d_table, n_item_tiles, stream);
       break;
   }
   if (rc != RP_OK) return rc;
   ce_label_scatter_kernel<<<sm_count() * 4, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hc), labels, loss_inv,
-                                                               n_valid, d, d_table);
+                                                               n_valid, d, d_table, d_bias);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }

@@ -82,6 +82,7 @@ __global__ void embed_fwd_kernel(const __nv_bfloat16* __restrict__ table, const 
                                  const int32_t* __restrict__ ids, const uint8_t* __restrict__ pad_mask, int T, int L,
                                  int pos0, float scale, int zero_pad_rows, float drop_p, unsigned long long seed,
                                  unsigned long long drop_off, const unsigned long long* __restrict__ seed_ptr,
+                                 const uint8_t* __restrict__ tok_mask, const __nv_bfloat16* __restrict__ mask_emb,
                                  __nv_bfloat16* __restrict__ out) {
   if (drop_p > 0.f && seed_ptr) seed += *seed_ptr;
   constexpr int D = VEC * 32;
@@ -91,7 +92,8 @@ __global__ void embed_fwd_kernel(const __nv_bfloat16* __restrict__ table, const 
   const float ks = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < T; t += gridDim.x * wpb) {
     const int id = ids[t];
-    const __nv_bfloat16* e = table + (size_t)id * D + lane * VEC;
+    // BERT4Rec: positions with token_mask == 0 (<MASK> and pads) take the single mask embedding (bert4rec/model.py:285-288)
+    const __nv_bfloat16* e = (tok_mask && !tok_mask[t]) ? mask_emb + lane * VEC : table + (size_t)id * D + lane * VEC;
     const float* p = pos + (size_t)(pos0 + t % L) * D + lane * VEC;
     float v[VEC];
 #pragma unroll
@@ -121,6 +123,7 @@ __global__ void embed_bwd_table_kernel(const __nv_bfloat16* __restrict__ dx, con
                                        const uint8_t* __restrict__ pad_mask, int T, int pad_id, float scale,
                                        int zero_pad_rows, float drop_p, unsigned long long seed,
                                        unsigned long long drop_off, const unsigned long long* __restrict__ seed_ptr,
+                                       const uint8_t* __restrict__ tok_mask, float* __restrict__ d_mask_emb,
                                        float* __restrict__ dE) {
   if (drop_p > 0.f && seed_ptr) seed += *seed_ptr;
   constexpr int D = VEC * 32;
@@ -131,9 +134,9 @@ __global__ void embed_bwd_table_kernel(const __nv_bfloat16* __restrict__ dx, con
   for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < T; t += gridDim.x * wpb) {
     const int id = ids[t];
     if (id == pad_id) continue;
-    if (zero_pad_rows && !pad_mask[t]) continue;
+    if ((zero_pad_rows || tok_mask) && !pad_mask[t]) continue;  // pad positions receive no gradient
     const __nv_bfloat16* g = dx + (size_t)t * D + lane * VEC;
-    float* dst = dE + (size_t)id * D + lane * VEC;
+    float* dst = (tok_mask && !tok_mask[t]) ? d_mask_emb + lane * VEC : dE + (size_t)id * D + lane * VEC;
     const unsigned long long e0 = drop_off + (unsigned long long)t * D + lane * VEC;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -486,7 +489,7 @@ RP_API int rp_embed_fwd(const void* table, const float* pos, const int32_t* ids,
   const int grid = grid_for(T, 8);
   RP_DISPATCH_D(d, (embed_fwd_kernel<VEC><<<grid, 256, 0, stream>>>(
                        reinterpret_cast<const __nv_bfloat16*>(table), pos, ids, pad_mask, T, L, pos0, scale, zero_pad_rows,
-                       drop_p, seed, drop_off, seed_ptr, reinterpret_cast<__nv_bfloat16*>(out))));
+                       drop_p, seed, drop_off, seed_ptr, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(out))));
   RP_LAUNCH_CHECK();
   return RP_OK;
 }
@@ -501,7 +504,7 @@ RP_API int rp_embed_bwd(const void* dx, const int32_t* ids, const uint8_t* pad_m
   const int grid = grid_for(T, 8);
   RP_DISPATCH_D(d, (embed_bwd_table_kernel<VEC><<<grid, 256, 0, stream>>>(
                        reinterpret_cast<const __nv_bfloat16*>(dx), ids, pad_mask, T, pad_id, scale, zero_pad_rows, drop_p,
-                       seed, drop_off, seed_ptr, d_table)));
+                       seed, drop_off, seed_ptr, nullptr, nullptr, d_table)));
   RP_LAUNCH_CHECK();
   {
     const int rlanes = 256 / (d / 4);
@@ -595,6 +598,71 @@ RP_API int rp_counter_add(unsigned long long* counter, unsigned long long inc, v
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!counter) return RP_EINVAL;
   counter_add_kernel<<<1, 1, 0, stream>>>(counter, inc);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+// ---- BERT4Rec embedding: where(token_mask, E[ids], mask_emb) + P[t % L], no sqrt(d) scaling (bert4rec/model.py:239-296)
+RP_API int rp_bert_embed_fwd(const void* table, const void* mask_emb, const float* pos, const int32_t* ids,
+                             const uint8_t* tok_mask, int T, int L, int d, float drop_p, unsigned long long seed,
+                             unsigned long long drop_off, const unsigned long long* seed_ptr, void* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!table || !mask_emb || !pos || !ids || !tok_mask || !out || T <= 0 || L <= 0) return RP_EINVAL;
+  const int grid = grid_for(T, 8);
+  RP_DISPATCH_D(d, (embed_fwd_kernel<VEC><<<grid, 256, 0, stream>>>(
+                       reinterpret_cast<const __nv_bfloat16*>(table), pos, ids, tok_mask, T, L, 0, 1.f, 0, drop_p, seed, drop_off,
+                       seed_ptr, tok_mask, reinterpret_cast<const __nv_bfloat16*>(mask_emb), reinterpret_cast<__nv_bfloat16*>(out))));
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+RP_API int rp_bert_embed_bwd(const void* dx, const int32_t* ids, const uint8_t* pad_mask, const uint8_t* tok_mask, int B, int L,
+                             int d, float drop_p, unsigned long long seed, unsigned long long drop_off,
+                             const unsigned long long* seed_ptr, float* d_table, float* d_mask_emb, float* d_pos,
+                             void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!dx || !ids || !pad_mask || !tok_mask || !d_table || !d_mask_emb || !d_pos || B <= 0 || L <= 0) return RP_EINVAL;
+  const int T = B * L;
+  const int grid = grid_for(T, 8);
+  RP_DISPATCH_D(d, (embed_bwd_table_kernel<VEC><<<grid, 256, 0, stream>>>(
+                       reinterpret_cast<const __nv_bfloat16*>(dx), ids, pad_mask, T, -1, 1.f, 0, drop_p, seed, drop_off, seed_ptr,
+                       tok_mask, d_mask_emb, d_table)));
+  RP_LAUNCH_CHECK();
+  {
+    const int rlanes = 256 / (d / 4);
+    int G = (B + 31) / 32;
+    if (G < 1) G = 1;
+    if (G > 16) G = 16;
+    // positional gradient: pad positions carry an exactly-zero dx, so no masking is needed
+    embed_bwd_pos_kernel<<<dim3(L, G), 256, (size_t)rlanes * d * sizeof(float), stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dx), pad_mask, B, L, d, 0, 1, drop_p, seed, drop_off, seed_ptr, d_pos);
+  }
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+// ---- row gather / scatter with a device-side row count (valid-target compaction without a LayerNorm)
+template <int VEC>
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ idx, int n_max,
+                                   const int32_t* __restrict__ n_dev, __nv_bfloat16* __restrict__ dst, int scatter) {
+  constexpr int D = VEC * 32;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int n = n_dev ? min(n_max, *n_dev) : n_max;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n; r += gridDim.x * wpb) {
+    const size_t a = (size_t)(scatter ? r : idx[r]) * D + lane * VEC, b = (size_t)(scatter ? idx[r] : r) * D + lane * VEC;
+#pragma unroll
+    for (int i = 0; i < VEC; i += 2) *reinterpret_cast<uint32_t*>(dst + b + i) = *reinterpret_cast<const uint32_t*>(src + a + i);
+  }
+}
+
+// scatter = 0: dst[r] = src[idx[r]] ; scatter = 1: dst[idx[r]] = src[r]   (r < min(n_max, *n_dev))
+RP_API int rp_gather_rows(const void* src, const int32_t* idx, int n_max, const int32_t* n_dev, int d, void* dst, int scatter,
+                          void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!src || !idx || !dst || n_max <= 0) return RP_EINVAL;
+  const int grid = grid_for(n_max, 8);
+  RP_DISPATCH_D(d, (gather_rows_kernel<VEC><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), idx, n_max,
+                                                                      n_dev, reinterpret_cast<__nv_bfloat16*>(dst), scatter)));
   RP_LAUNCH_CHECK();
   return RP_OK;
 }

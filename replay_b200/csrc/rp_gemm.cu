@@ -36,6 +36,10 @@ struct GemmParams {
   int split_k;                 // number of K splits (out_mode 1 only)
   const __nv_bfloat16* gate;   // same geometry as C: x *= (gate != 0) ? gate_scale : 0   (ReLU+dropout backward) or null
   float gate_scale;
+  __nv_bfloat16* C2;           // optional second output (bf16, geometry of C): the value after bias, before the activation
+  int gate_mode;               // 0: gate != 0 ? gate_scale : 0 ;  1: gelu'(gate) * gate_scale (gate = saved pre-activation)
+  float post_drop_p;           // second dropout applied AFTER the residual add (BERT4Rec block output), 0 = off
+  unsigned long long post_drop_offset;
 };
 
 static constexpr int kGemmThreads = 192;
@@ -153,6 +157,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           x[q] += b4.x; x[q + 1] += b4.y; x[q + 2] += b4.z; x[q + 3] += b4.w;
         }
       }
+      const bool full = (n0 + c + 32 <= p.N);
+      if (p.C2) {
+        __nv_bfloat16* o2 = p.C2 + c_base + n0 + c;
+#pragma unroll
+        for (int q = 0; q < 32; q += 2)
+          if (n0 + c + q < p.N) *reinterpret_cast<uint32_t*>(o2 + q) = pack_bf16(x[q], x[q + 1]);
+      }
       if (p.act == 1) {
 #pragma unroll
         for (int q = 0; q < 32; ++q) x[q] = fmaxf(x[q], 0.f);
@@ -172,12 +183,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           x[q + 3] = (r.w >= drop_thr) ? x[q + 3] * keep_scale : 0.f;
         }
       }
-      const bool full = (n0 + c + 32 <= p.N);
       if (p.gate) {
         const __nv_bfloat16* gp = p.gate + c_base + n0 + c;
+        if (p.gate_mode == 0) {
 #pragma unroll
-        for (int q = 0; q < 32; ++q)
-          if (n0 + c + q < p.N) x[q] = (__bfloat162float(gp[q]) != 0.f) ? x[q] * p.gate_scale : 0.f;
+          for (int q = 0; q < 32; ++q)
+            if (n0 + c + q < p.N) x[q] = (__bfloat162float(gp[q]) != 0.f) ? x[q] * p.gate_scale : 0.f;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (n0 + c + q < p.N) {
+              const float z = __bfloat162float(gp[q]);
+              const float dg = 0.5f * (1.f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
+              x[q] *= dg * p.gate_scale;
+            }
+        }
       }
       if (p.residual) {
         const __nv_bfloat16* rp_ = p.residual + c_base + n0 + c;
@@ -197,6 +217,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int q = 0; q < 32; ++q)
             if (n0 + c + q < p.N) x[q] += __bfloat162float(rp_[q]);
+        }
+      }
+      if (p.post_drop_p > 0.f) {
+        const float ks2 = 1.f / (1.f - p.post_drop_p);
+        const uint32_t thr2 = (uint32_t)(p.post_drop_p * 4294967296.0);
+        const unsigned long long e0 = p.post_drop_offset + (unsigned long long)(c_base + n0 + c);
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          const uint4 r = philox4x32(p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull), (e0 + q) >> 2);
+          x[q + 0] = (r.x >= thr2) ? x[q + 0] * ks2 : 0.f;
+          x[q + 1] = (r.y >= thr2) ? x[q + 1] * ks2 : 0.f;
+          x[q + 2] = (r.z >= thr2) ? x[q + 2] * ks2 : 0.f;
+          x[q + 3] = (r.w >= thr2) ? x[q + 3] * ks2 : 0.f;
         }
       }
       if (p.rowmask) {
@@ -276,6 +309,7 @@ struct rp_gemm_desc {
   float drop_p; unsigned long long seed, drop_offset; const unsigned long long* seed_ptr;
   int split_k;
   const void* gate; float gate_scale;
+  void* C2; int gate_mode; float post_drop_p; unsigned long long post_drop_offset;
 };
 
 RP_API int rp_gemm(const rp_gemm_desc* g, void* stream_) {
@@ -294,6 +328,8 @@ RP_API int rp_gemm(const rp_gemm_desc* g, void* stream_) {
   p.rowmask = g->rowmask; p.rowmask_off0 = g->rowmask_off0; p.rowmask_oo = g->rowmask_oo;
   p.drop_p = g->drop_p; p.seed = g->seed; p.drop_offset = g->drop_offset; p.seed_ptr = g->seed_ptr; p.split_k = g->split_k;
   p.gate = reinterpret_cast<const __nv_bfloat16*>(g->gate); p.gate_scale = g->gate_scale;
+  p.C2 = reinterpret_cast<__nv_bfloat16*>(g->C2); p.gate_mode = g->gate_mode; p.post_drop_p = g->post_drop_p;
+  p.post_drop_offset = g->post_drop_offset;
   CUtensorMap tmA, tmB;
   int rc;
   // K-major operand: box [128 (or BN) rows x 64 cols]; MN-major operand: box [64 k-rows x 64 cols]

@@ -59,7 +59,7 @@ template <int KCH /* d / 64 */, int NSTAGE, int KMAX>
 __global__ void __launch_bounds__(kThreads, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const int32_t* __restrict__ seen_sorted, int S, int n_users, int n_items, int K, int n_splits,
-                  float* __restrict__ part_vals, int32_t* __restrict__ part_ids) {
+                  const float* __restrict__ bias, float* __restrict__ part_vals, int32_t* __restrict__ part_ids) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                          // KCH chunks of 16 KB
@@ -179,6 +179,13 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float x[32];
 #pragma unroll
         for (int q = 0; q < 32; ++q) x[q] = __uint_as_float(c == 0 ? raw0[q] : raw1[q]);
+        if (bias) {  // biased head (BERT4Rec): warp-uniform 16-byte loads, bias padded to a multiple of 128 entries
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
+            x[q] += b4.x; x[q + 1] += b4.y; x[q + 2] += b4.z; x[q + 3] += b4.w;
+          }
+        }
         if (col0 + 32 > n_items) {  // ragged last tile: columns beyond the catalog do not exist
 #pragma unroll
           for (int q = 0; q < 32; ++q)
@@ -344,17 +351,17 @@ static int choose_splits(int n_user_tiles, int n_item_tiles) {
 
 template <int KCH, int NSTAGE>
 static int launch_score_topk(const CUtensorMap& tmA, const CUtensorMap& tmB, const int32_t* seen_sorted, int S, int B,
-                             int I, int K, int n_splits, float* pv, int32_t* pi, cudaStream_t stream) {
+                             int I, int K, int n_splits, const float* bias, float* pv, int32_t* pi, cudaStream_t stream) {
   const int smem = (KCH + NSTAGE) * kChunkBytes + 1024;
   const int grid = ((B + kTileM - 1) / kTileM) * n_splits;
   if (K <= 16) {
     auto kern = score_topk_kernel<KCH, NSTAGE, 16>;
     RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, pv, pi);
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, bias, pv, pi);
   } else {
     auto kern = score_topk_kernel<KCH, NSTAGE, 32>;
     RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, pv, pi);
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, bias, pv, pi);
   }
   RP_LAUNCH_CHECK();
   return RP_OK;
@@ -390,7 +397,6 @@ RP_API int rp_score_topk(const void* hq, const void* table, const float* bias, c
   using namespace rp;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!hq || !table || !out_ids || !out_scores || !workspace) return RP_EINVAL;
-  if (bias) return RP_EINVAL;  // TODO(bert4rec head bias)
   if (n_users <= 0 || n_items <= 0 || K <= 0 || K > 32 || K > n_items) return RP_ESHAPE;
   if (d != 64 && d != 128 && d != 256 && d != 512) return RP_ESHAPE;
   if (seen_sorted && S <= 0) return RP_ESHAPE;
@@ -404,10 +410,10 @@ RP_API int rp_score_topk(const void* hq, const void* table, const float* bias, c
   if ((rc = make_tmap_bf16(&tmA, hq, n_users, d, d, 128)) != RP_OK) return rc;
   if ((rc = make_tmap_bf16(&tmB, table, n_items, d, d, 128)) != RP_OK) return rc;
   switch (d) {
-    case 64: rc = launch_score_topk<1, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, pv, pi, stream); break;
-    case 128: rc = launch_score_topk<2, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, pv, pi, stream); break;
-    case 256: rc = launch_score_topk<4, 6>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, pv, pi, stream); break;
-    default: rc = launch_score_topk<8, 3>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, pv, pi, stream); break;
+    case 64: rc = launch_score_topk<1, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, stream); break;
+    case 128: rc = launch_score_topk<2, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, stream); break;
+    case 256: rc = launch_score_topk<4, 6>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, stream); break;
+    default: rc = launch_score_topk<8, 3>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, stream); break;
   }
   if (rc != RP_OK) return rc;
   const int threads = 128;

@@ -225,7 +225,8 @@ class SasRecEngine:
     # ------------------------------------------------------------------------------------------------ kernel helpers
     def _gemm(self, A, B, C, M, N, K, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, rowmask=None,
               drop_p=0.0, drop_site=0, out_mode=0, split_k=1, gate=None, gate_scale=1.0, alpha=1.0, batch=1, inner=1,
-              a_off=(0, 0, 0, 0, 0, 0), b_off=(0, 0, 0, 0, 0, 0), c_geom=None, rowmask_oo=0):
+              a_off=(0, 0, 0, 0, 0, 0), b_off=(0, 0, 0, 0, 0, 0), c_geom=None, rowmask_oo=0, C2=None, gate_mode=0,
+              post_drop_p=0.0, post_drop_site=0):
         g = GemmDesc()
         g.A, g.a_rows, g.a_cols, g.lda, g.a_mn = A.data_ptr(), A.shape[0], A.shape[1], A.stride(0), int(a_mn)
         g.B, g.b_rows, g.b_cols, g.ldb, g.b_mn = B.data_ptr(), B.shape[0], B.shape[1], B.stride(0), int(b_mn)
@@ -251,6 +252,10 @@ class SasRecEngine:
         g.split_k = split_k
         g.gate = None if gate is None else gate.data_ptr()
         g.gate_scale = gate_scale
+        g.C2 = None if C2 is None else C2.data_ptr()
+        g.gate_mode = gate_mode
+        g.post_drop_p = post_drop_p
+        g.post_drop_offset = post_drop_site << 40
         check(self.lib.rp_gemm(ctypes.byref(g), self._stream()), "rp_gemm")
 
     def _wgrad(self, dY, X, dW, n_out, n_in):

@@ -129,3 +129,41 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.RpError):
         _lib.lib()
+
+
+@pytest.mark.parametrize("mask_prob,padding,result", [
+    (0.0, [0, 0, 0, 0, 0, 1, 1, 1], [1, 1, 1, 1, 1, 1, 1, 0]),
+    (1.0, [0, 0, 0, 0, 0, 1, 1, 1], [0, 0, 0, 0, 0, 0, 1, 0]),
+    (1e-6, [0, 1, 1, 1, 1, 1, 1, 1], [0, 1, 1, 1, 1, 1, 1, 1]),
+])
+def test_uniform_bert_masking_corner_cases(mask_prob, padding, result):
+    """reference tests/models/nn/sequential/bert4rec/test_bert4rec_dataset.py:15-41 (known answers) on the mirror."""
+    from replay_b200.models.nn.sequential import uniform_masker
+
+    tok = uniform_masker(torch.tensor(padding, dtype=torch.bool), mask_prob)
+    assert tok.tolist() == [bool(v) for v in result]
+    tok2 = uniform_masker(torch.tensor([padding, padding], dtype=torch.bool), mask_prob)
+    assert tok2.tolist() == [[bool(v) for v in result]] * 2
+
+
+def test_bert_shift_features_known_answer():
+    """_shift_features (bert4rec/dataset.py:322-345): roll left, last position = <MASK>, pad = True."""
+    from replay_b200.models.nn.sequential import shift_features
+
+    ids = torch.tensor([[0, 0, 5, 6, 7]]); pm = torch.tensor([[0, 0, 1, 1, 1]], dtype=torch.bool); tm = pm.clone()
+    i2, p2, t2 = shift_features(ids, pm, tm, pad_value=0)
+    assert i2.tolist() == [[0, 5, 6, 7, 0]]
+    assert p2.tolist() == [[False, True, True, True, True]]
+    assert t2.tolist() == [[False, True, True, True, False]]
+
+
+def test_bert_state_dict_keys_match_reference(golden_dir):
+    from replay_b200.models.nn.sequential.bert4rec import bert_key_map
+
+    for name, tying in (("bert4rec_tiny.npz", False), ("bert4rec_tiny_tied.npz", True)):
+        z = np.load(os.path.join(golden_dir, name))
+        ref = {k[4:] for k in z.files if k.startswith("sd::")}
+        ours = set(bert_key_map(int(z["n_blocks"]), tying).values())
+        if tying:
+            ours |= {"_head._item_embedder." + k[len("item_embedder."):] for k in ours if k.startswith("item_embedder.")}
+        assert ours == ref, (ours ^ ref)

@@ -97,3 +97,35 @@ def test_bert4rec_predict_with_biased_head(golden_dir, cuda):
     ids_o = torch.argsort(-logits16.double(), dim=1, stable=True)[:, :10]
     assert torch.equal(ids_k.cpu(), ids_o)
     assert (sc_k.cpu() - torch.gather(ref_logits, 1, ids_k.cpu())).abs().max() < 0.1
+
+
+def test_bert4rec_lightning_mirror(golden_dir, cuda):
+    """Legacy Bert4Rec module: reference checkpoint keys, training_step on the reference batch layout, predict with the
+    shifted window, fused top-k with candidates."""
+    from replay_b200.models.nn.sequential import Bert4Rec
+    from replay_b200.schema import TensorFeatureInfo, TensorSchema
+
+    z = np.load(os.path.join(golden_dir, "bert4rec_tiny.npz"))
+    sd = {"_model." + k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}
+    n_items, d, H, L = int(z["n_items"]), int(z["d"]), int(z["H"]), int(z["L"])
+    m = Bert4Rec(TensorSchema(TensorFeatureInfo("item_id", n_items, 0, d)), block_count=int(z["n_blocks"]), head_count=H,
+                 hidden_size=d, max_seq_len=L, dropout_rate=0.0)
+    m.load_state_dict(sd)
+    ids, pm, tok = (torch.from_numpy(z[k]).cuda() for k in ("ids", "pad_mask", "token_mask"))
+    batch = {"query_id": torch.arange(ids.shape[0]).view(-1, 1), "inputs": {"item_id": ids}, "pad_mask": pm, "token_mask": tok,
+             "positive_labels": torch.from_numpy(z["labels"]).cuda()}
+    loss = m.training_step(batch, 0)
+    assert abs(float(loss) - float(z["train_loss"])) < 5e-3 * float(z["train_loss"])
+    sd2 = m.state_dict()
+    assert set(sd2) == set(sd)
+    scores = m.predict(batch)
+    assert scores.shape == (ids.shape[0], n_items) and torch.isfinite(scores).all()
+    cands = torch.arange(5, 200, 3).cuda()
+    top_ids, top_sc = m.predict_topk(batch, 7, seen_ids=ids, candidates_to_score=cands)
+    assert set(top_ids.flatten().tolist()) <= set(cands.tolist())
+    sc_c = m.predict(batch, candidates_to_score=cands)
+    seen_mask = torch.zeros(ids.shape[0], n_items, dtype=torch.bool, device="cuda")
+    seen_mask.scatter_(1, ids, True)
+    sc_c = sc_c.masked_fill(seen_mask[:, cands], float("-inf"))
+    ref_top = torch.argsort(-sc_c.double(), dim=1, stable=True)[:, :7]
+    assert torch.equal(top_ids, cands[ref_top])

@@ -74,17 +74,23 @@ int rp_score_topk(const void* hq, const void* table, const float* bias, const in
 size_t rp_ce_head_workspace(int capacity_tokens, int n_items, int d);
 
 /* loss_out fp32 [2] = { mean CE over the valid targets, 1 / n_valid }; lse fp32 [capacity];
- * cvec fp32 [round_up(capacity,128)] (per-token exponent offsets for the backward; entries >= capacity must be -inf). */
+ * cvec fp32 [round_up(capacity,128)] (per-token exponent offsets for the backward; entries >= capacity must be -inf).
+ * d_hc (optional, bf16 [capacity, d], d <= 256): enables the FUSED training path - a single pass accumulates the row sums of
+ * exp(s) against a fixed reference maximum together with the un-normalised gradient sum_i exp(s_i) E_i, so the separate
+ * log-sum-exp pass disappears and d_hc is final after this call.  A device-side Cauchy-Schwarz bound on |s| guards the
+ * trick; when it fails the two-pass kernels run instead (both variants are enqueued, the losing one exits immediately), so
+ * the call stays CUDA-graph capturable.  n_valid_hint: host estimate of *n_valid (0 = unknown), load-balance only. */
 int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, const int32_t* labels, const int32_t* n_valid,
-                   int capacity, int n_items, int d, float* loss_out, float* lse, float* cvec, void* workspace,
-                   size_t workspace_bytes, void* stream);
+                   int capacity, int n_items, int d, float* loss_out, float* lse, float* cvec, void* d_hc, int n_valid_hint,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
-/* gradients of the mean CE for d(loss) = 1:  d_hc bf16 [capacity, d] (rows < *n_valid written);
- * d_table fp32 [n_items, d] is OVERWRITTEN (softmax part) and then atomically corrected by the one-hot part.
- * d in {64,128,256}. */
+/* gradients of the mean CE for d(loss) = 1:  d_hc bf16 [capacity, d] (rows < *n_valid; already produced by the forward when
+ * `fused` != 0 and the bound held, otherwise computed here); d_table fp32 [n_items, d] is OVERWRITTEN (softmax part) and
+ * then atomically corrected by the one-hot part; d_bias fp32 [n_items] likewise iff bias.  `fused` must equal
+ * (d_hc != NULL) of the matching forward call and then needs the same workspace.  d in {64,128,256}. */
 int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, const int32_t* labels, const int32_t* n_valid,
                    int capacity, int n_items, int d, const float* loss_out, const float* cvec, void* d_hc, float* d_table,
-                   float* d_bias, void* stream);
+                   float* d_bias, int fused, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Transformer body.  All activations are token-major bf16 [T = B*L, d]; weights are the bf16 shadow of the fp32 masters.

@@ -53,7 +53,8 @@ template <int KCH, int NSTAGE>
 __global__ void __launch_bounds__(kThreads, 1)
 ce_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const int32_t* __restrict__ n_valid_ptr, int n_items, int n_splits, const float* __restrict__ bias,
-              float2* __restrict__ part /* [T, n_splits, 2] (m in log2 units, s) */) {
+              float2* __restrict__ part /* [T, n_splits, 2] (m in log2 units, s) */,
+              const int32_t* __restrict__ skip_if_safe) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -63,6 +64,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tok_tile = blockIdx.x / n_splits, split = blockIdx.x % n_splits;
+  if (skip_if_safe && *skip_if_safe != 0) return;  // the fused pass covers this step
   const int n_valid = *n_valid_ptr;
   const int t0 = tok_tile * kT;
   if (t0 >= n_valid) return;  // uniform for the CTA
@@ -197,7 +199,9 @@ __global__ void ce_finalize_kernel(const float2* __restrict__ part, const __nv_b
                                    const float* __restrict__ bias, const int32_t* __restrict__ n_valid_ptr, int n_part,
                                    int capacity, int d,
                                    float* __restrict__ lse_out, float* __restrict__ cvec, float* __restrict__ block_sums,
-                                   unsigned int* __restrict__ ticket, float* __restrict__ loss_out) {
+                                   unsigned int* __restrict__ ticket, float* __restrict__ loss_out,
+                                   const int32_t* __restrict__ skip_if_safe) {
+  if (skip_if_safe && *skip_if_safe != 0) return;
   const int n_valid = *n_valid_ptr;
   const float inv_n = n_valid > 0 ? 1.f / (float)n_valid : 0.f;
   const float log2_inv_n = n_valid > 0 ? -log2f((float)n_valid) : 0.f;
@@ -264,14 +268,23 @@ __global__ void ce_finalize_kernel(const float2* __restrict__ part, const __nv_b
 //   COLCONST = false : rows = tokens (A = Hc tile), columns = items  -> acc = dHc tile [128, d]
 //   COLCONST = true  : rows = items  (A = E tile),  columns = tokens -> acc = dE tile  [128, d]
 // ----------------------------------------------------------------------------------------------------------------
-template <int KCH, int NSTAGE, bool COLCONST, int NBUF>
+// MODE 0: rows = tokens, G = softmax/T_v from the stored lse (two-pass fallback)      -> out = dHc bf16
+// MODE 1: rows = items (COLCONST), columns = tokens                                    -> out = dE fp32
+// MODE 2: rows = tokens, FUSED forward+backward: G~ = exp(s + b) with reference max 0 (valid while |s| is bounded, see
+//         ce_bound_kernel), per-row sum of G~ and un-normalised dH~ = sum_i G~ E_i over this CTA's column split
+//                                                                                      -> out = partial dH~ fp32, zpart
+template <int KCH, int NSTAGE, int MODE, int NBUF>
 __global__ void __launch_bounds__(kThreads, 1)
 ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const float* __restrict__ cvec /* [T] exponent offsets per token */, const int32_t* __restrict__ labels,
               const __nv_bfloat16* __restrict__ table, const float* __restrict__ loss_inv /* [1] = 1/T_v */,
               const int32_t* __restrict__ n_valid_ptr, int n_items, const float* __restrict__ bias,
-              float* __restrict__ d_bias, void* __restrict__ out) {
+              float* __restrict__ d_bias, void* __restrict__ out, const int32_t* __restrict__ safe_flag, int run_if_safe,
+              int n_splits, int capacity, float* __restrict__ zpart) {
+  constexpr bool COLCONST = (MODE == 1);
+  constexpr bool FUSED = (MODE == 2);
   constexpr int D = KCH * 64;
+  if (safe_flag && (*safe_flag != 0) != (run_if_safe != 0)) return;  // fused path vs two-pass fallback (uniform)
   constexpr int kStage = KCH * kChunk;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -284,11 +297,14 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_valid = *n_valid_ptr;
-  const int r0 = blockIdx.x * kT;                           // first row (token or item) of this CTA
+  const int row_tile = FUSED ? blockIdx.x / n_splits : blockIdx.x, split = FUSED ? blockIdx.x % n_splits : 0;
+  const int r0 = row_tile * kT;                             // first row (token or item) of this CTA
   const int n_rows = COLCONST ? n_items : n_valid;
   if (r0 >= n_rows) return;
   const int n_cols = COLCONST ? n_valid : n_items;
-  const int n_ct = (n_cols + kT - 1) / kT;                  // column tiles
+  const int n_ct_all = (n_cols + kT - 1) / kT;              // column tiles of the whole problem
+  const int jg0 = FUSED ? (int)(((long long)n_ct_all * split) / n_splits) : 0;        // first column tile of this CTA
+  const int n_ct = FUSED ? (int)(((long long)n_ct_all * (split + 1)) / n_splits) - jg0 : n_ct_all;
 
   if (threadIdx.x == 0) {
     mbar_init(&bar_a, 1);
@@ -321,12 +337,13 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t s = j % NSTAGE, ph = (j / NSTAGE) & 1;
         mbar_wait(&bar_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&bar_full[s], kStage + (COLCONST ? kT * 4 : 0));
-        for (int kc = 0; kc < KCH; ++kc) tma_load_2d(sB + s * kStage + kc * kChunk, &tmB, &bar_full[s], kc * 64, j * kT);
+        for (int kc = 0; kc < KCH; ++kc)
+          tma_load_2d(sB + s * kStage + kc * kChunk, &tmB, &bar_full[s], kc * 64, (jg0 + j) * kT);
         if (COLCONST) {
           asm volatile(
               "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                   smem_u32(&s_cc[s][0])),
-              "l"(cvec + (size_t)j * kT), "r"(kT * 4), "r"(smem_u32(&bar_full[s]))
+              "l"(cvec + (size_t)(jg0 + j) * kT), "r"(kT * 4), "r"(smem_u32(&bar_full[s]))
               : "memory");
         }
       }
@@ -375,7 +392,9 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     float crow = 0.f;
-    if (!COLCONST) crow = (r0 + row < n_valid) ? cvec[r0 + row] : -INFINITY;
+    if (MODE == 0) crow = (r0 + row < n_valid) ? cvec[r0 + row] : -INFINITY;
+    if (FUSED) crow = (r0 + row < n_valid) ? 0.f : -INFINITY;
+    float zacc = 0.f;  // FUSED: sum of G~ over this thread's columns
     float gsum = 0.f;  // COL mode with bias: sum over tokens of G (before the e^{b_i} row factor) -> bias gradient
     for (int j = 0; j < n_ct; ++j) {
       const uint32_t b = j % NBUF, s = j % NSTAGE;
@@ -388,7 +407,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tmem_ld32(sbase + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
       tmem_ld_wait();
       uint32_t pk[32];
-      const int col0 = j * kT + half * 64;
+      const int col0 = (jg0 + j) * kT + half * 64;
       // G = exp2(S*log2e + offset): alternate MUFU.EX2 and the FMA-pipe polynomial so neither pipe paces the tile
       if (COLCONST) {
         const float4* cc = reinterpret_cast<const float4*>(&s_cc[s][half * 64]);
@@ -422,6 +441,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (col0 + q >= n_items) g0 = 0.f;
             if (col0 + q + 1 >= n_items) g1 = 0.f;
           }
+          if (FUSED) zacc += g0 + g1;
           pk[q >> 1] = pack_bf16(g0, g1);
         }
       }
@@ -459,6 +479,23 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           for (int q = 0; q < 32; q += 4)
             dst[q >> 2] = make_float4(__uint_as_float(raw[q]) * rs, __uint_as_float(raw[q + 1]) * rs,
                                       __uint_as_float(raw[q + 2]) * rs, __uint_as_float(raw[q + 3]) * rs);
+        }
+      }
+    } else if (FUSED) {
+      // partial (this column split) un-normalised gradient and row sums; ce_fused_finalize_kernel reduces the splits
+      float* o = reinterpret_cast<float*>(out) + (size_t)split * capacity * D;
+      if (r < n_valid) zpart[((size_t)split * 2 + half) * capacity + r] = zacc;
+#pragma unroll 1
+      for (int c = 0; c < HALF_D; c += 32) {
+        uint32_t raw[32];
+        tmem_ld32(abase + c, raw);
+        tmem_ld_wait();
+        if (r < n_valid) {
+          float4* dst = reinterpret_cast<float4*>(o + (size_t)r * D + half * HALF_D + c);
+#pragma unroll
+          for (int q = 0; q < 32; q += 4)
+            dst[q >> 2] = make_float4(__uint_as_float(raw[q]), __uint_as_float(raw[q + 1]), __uint_as_float(raw[q + 2]),
+                                      __uint_as_float(raw[q + 3]));
         }
       }
     } else {
@@ -516,6 +553,113 @@ __global__ void ce_label_scatter_kernel(const __nv_bfloat16* __restrict__ hc, co
   }
 }
 
+// ---- safety bound of the fused (single-reference-max) path: |s_ti + b_i| <= max_t||h_t|| * max_i||e_i|| + max|b|
+__global__ void ce_bound_kernel(const __nv_bfloat16* __restrict__ hc, const __nv_bfloat16* __restrict__ table,
+                                const float* __restrict__ bias, const int32_t* __restrict__ n_valid_ptr, int n_items, int d,
+                                unsigned int* __restrict__ bound /* [3] float bits, zeroed */) {
+  const int n_valid = *n_valid_ptr;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int total = n_valid + n_items;
+  float mh = 0.f, me = 0.f, mb = 0.f;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < total; r += gridDim.x * wpb) {
+    const bool is_h = r < n_valid;
+    const __nv_bfloat16* row = is_h ? hc + (size_t)r * d : table + (size_t)(r - n_valid) * d;
+    float ss = 0.f;
+    for (int c = lane * 2; c < d; c += 64) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + c));
+      ss = fmaf(v.x, v.x, fmaf(v.y, v.y, ss));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (is_h) mh = fmaxf(mh, ss); else me = fmaxf(me, ss);
+    if (!is_h && bias && lane == 0) mb = fmaxf(mb, fabsf(bias[r - n_valid]));
+  }
+  if (lane == 0) {  // non-negative floats order like their bit patterns
+    atomicMax(bound + 0, __float_as_uint(mh));
+    atomicMax(bound + 1, __float_as_uint(me));
+    atomicMax(bound + 2, __float_as_uint(mb));
+  }
+}
+
+__global__ void ce_flag_kernel(const unsigned int* __restrict__ bound, int32_t* __restrict__ safe_flag) {
+  const float b = sqrtf(__uint_as_float(bound[0]) * __uint_as_float(bound[1])) + __uint_as_float(bound[2]);
+  // exp2(b * log2e) and its reciprocal must stay far inside the fp32 / bf16 exponent range
+  *safe_flag = (b * kLog2e < 100.f) ? 1 : 0;
+}
+
+// reduce the column splits of the fused pass: lse, loss, exponent offsets for the dE pass, and
+//   dHc[t] = sum_p dH~_p[t] / (z_t * T_v) - E[y_t] / T_v
+__global__ void ce_fused_finalize_kernel(const float* __restrict__ part_dh, const float* __restrict__ zpart,
+                                         const __nv_bfloat16* __restrict__ hc, const __nv_bfloat16* __restrict__ table,
+                                         const int32_t* __restrict__ labels, const float* __restrict__ bias,
+                                         const int32_t* __restrict__ n_valid_ptr, const int32_t* __restrict__ safe_flag,
+                                         int n_splits, int capacity, int d, float* __restrict__ lse_out,
+                                         float* __restrict__ cvec, __nv_bfloat16* __restrict__ d_hc,
+                                         float* __restrict__ block_sums, unsigned int* __restrict__ ticket,
+                                         float* __restrict__ loss_out) {
+  if (*safe_flag == 0) return;
+  const int n_valid = *n_valid_ptr;
+  const float inv_n = n_valid > 0 ? 1.f / (float)n_valid : 0.f;
+  const float log2_inv_n = n_valid > 0 ? -log2f((float)n_valid) : 0.f;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float local = 0.f;
+  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < capacity; t += gridDim.x * wpb) {
+    if (t >= n_valid) {
+      if (lane == 0) cvec[t] = -INFINITY;
+      continue;
+    }
+    float z = 0.f;
+    for (int i = lane; i < n_splits * 2; i += 32) z += zpart[(size_t)i * capacity + t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    const int y = labels[t];
+    const __nv_bfloat16* hr = hc + (size_t)t * d;
+    const __nv_bfloat16* er = table + (size_t)y * d;
+    const float scale = inv_n / z;
+    float dot = 0.f;
+    for (int c = lane * 2; c < d; c += 64) {
+      const float2 h2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hr + c));
+      const float2 e2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(er + c));
+      dot = fmaf(h2.x, e2.x, fmaf(h2.y, e2.y, dot));
+      float a0 = 0.f, a1 = 0.f;
+      for (int p = 0; p < n_splits; ++p) {
+        const float2 v = *reinterpret_cast<const float2*>(part_dh + ((size_t)p * capacity + t) * d + c);
+        a0 += v.x;
+        a1 += v.y;
+      }
+      *reinterpret_cast<uint32_t*>(d_hc + (size_t)t * d + c) = pack_bf16(a0 * scale - inv_n * e2.x, a1 * scale - inv_n * e2.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (bias) dot += bias[y];
+    const float lse2 = log2f(z);
+    if (lane == 0) {
+      lse_out[t] = lse2 * kLn2;
+      cvec[t] = -lse2 + log2_inv_n;
+      local += lse2 * kLn2 - dot;
+    }
+  }
+  __shared__ float red[32];
+  __shared__ bool last;
+  if (lane == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+    for (int i = 0; i < wpb; ++i) sum += red[i];
+    block_sums[blockIdx.x] = sum;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float sum = 0.f;
+    for (int i = 0; i < (int)gridDim.x; ++i) sum += reinterpret_cast<volatile float*>(block_sums)[i];
+    loss_out[0] = sum * inv_n;
+    loss_out[1] = inv_n;
+  }
+}
+
 static int pick_splits(int n_row_tiles, int n_col_tiles) {
   const int sms = sm_count();
   int best = 1;
@@ -535,113 +679,176 @@ static int pick_splits(int n_row_tiles, int n_col_tiles) {
 
 using namespace rp;
 
-// workspace layout for the CE head: [part float2 T*P*2][zt T][block_sums 256][ticket]
-RP_API size_t rp_ce_head_workspace(int capacity_tokens, int n_items, int d) {
+// workspace layout: [part float2 cap*8*2][block_sums 1024 f][ticket, bound[3], flag, pad -> 64 B][zpart 16*cap f]
+//                   [part_dh 8*cap*d f]
+struct CeWs {
+  float2* part; float* block_sums; unsigned int* ticket; unsigned int* bound; int32_t* flag; float* zpart; float* part_dh;
+};
+static const int kMaxSplits = 8;
+
+static size_t ce_ws_bytes(int cap, int d) {
+  return (size_t)cap * kMaxSplits * 2 * sizeof(float2) + 4096 + 64 + (size_t)kMaxSplits * 2 * cap * 4 +
+         (size_t)kMaxSplits * cap * d * 4 + 256;
+}
+static CeWs ce_ws(void* workspace, int cap, int d) {
+  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+  CeWs r;
+  r.part = reinterpret_cast<float2*>(w);
+  w += (size_t)cap * kMaxSplits * 2 * sizeof(float2);
+  r.block_sums = reinterpret_cast<float*>(w);
+  w += 4096;
+  r.ticket = reinterpret_cast<unsigned int*>(w);
+  r.bound = r.ticket + 1;
+  r.flag = reinterpret_cast<int32_t*>(r.ticket + 4);
+  w += 64;
+  r.zpart = reinterpret_cast<float*>(w);
+  w += (size_t)kMaxSplits * 2 * cap * 4;
+  r.part_dh = reinterpret_cast<float*>(w);
   (void)d;
-  if (capacity_tokens <= 0 || n_items <= 0) return 0;
-  const int P = 8;
-  return (size_t)capacity_tokens * P * 2 * sizeof(float2) + (size_t)capacity_tokens * 4 + 4096 + 256;
+  return r;
+}
+
+RP_API size_t rp_ce_head_workspace(int capacity_tokens, int n_items, int d) {
+  if (capacity_tokens <= 0 || n_items <= 0 || d <= 0) return 0;
+  return ce_ws_bytes(capacity_tokens, d);
 }
 
 template <int KCH, int NSTAGE>
 static int launch_ce_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const int32_t* n_valid, int n_items,
-                         int n_splits, int n_tok_tiles, const float* bias, float2* part, cudaStream_t stream) {
+                         int n_splits, int n_tok_tiles, const float* bias, float2* part, const int32_t* skip,
+                         cudaStream_t stream) {
   const int smem = (KCH + NSTAGE) * kChunk + 1024;
   auto kern = ce_fwd_kernel<KCH, NSTAGE>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<n_tok_tiles * n_splits, kThreads, smem, stream>>>(tmA, tmB, n_valid, n_items, n_splits, bias, part);
+  kern<<<n_tok_tiles * n_splits, kThreads, smem, stream>>>(tmA, tmB, n_valid, n_items, n_splits, bias, part, skip);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }
 
-// hc bf16 [capacity, d] (rows >= *n_valid ignored), table bf16 [n_items, d], labels int32 [capacity],
-// n_valid int32 [1] (device).  Outputs: loss_out fp32 [2] = {mean CE, 1/T_v}; lse fp32 [capacity];
-// cvec fp32 [capacity] (exponent offsets consumed by rp_ce_head_bwd).
+template <int KCH, int NSTAGE, int MODE>
+static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* cvec, const int32_t* labels,
+                         const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, const float* bias,
+                         float* d_bias, void* out, int grid, const int32_t* safe_flag, int run_if_safe, int n_splits,
+                         int capacity, float* zpart, cudaStream_t stream) {
+  const int smem = (1 + NSTAGE) * KCH * kChunk + 1024;
+  constexpr int NBUF = (RP_CE_NBUF3 && KCH <= 2) ? 3 : 2;  // 3 S buffers + [128 x d] accumulator fit the 512 TMEM columns up to d = 128
+  auto kern = ce_bwd_kernel<KCH, NSTAGE, MODE, NBUF>;
+  RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, cvec, labels, reinterpret_cast<const __nv_bfloat16*>(table), loss_inv,
+                                         n_valid, n_items, bias, d_bias, out, safe_flag, run_if_safe, n_splits, capacity, zpart);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+template <int MODE>
+static int dispatch_ce_bwd(int d, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* cvec, const int32_t* labels,
+                           const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, const float* bias,
+                           float* d_bias, void* out, int grid, const int32_t* safe_flag, int run_if_safe, int n_splits,
+                           int capacity, float* zpart, cudaStream_t stream) {
+  switch (d) {
+    case 64:
+      return launch_ce_bwd<1, 6, MODE>(tmA, tmB, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
+                                       safe_flag, run_if_safe, n_splits, capacity, zpart, stream);
+    case 128:
+      return launch_ce_bwd<2, 4, MODE>(tmA, tmB, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
+                                       safe_flag, run_if_safe, n_splits, capacity, zpart, stream);
+    case 256:
+      return launch_ce_bwd<4, 2, MODE>(tmA, tmB, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
+                                       safe_flag, run_if_safe, n_splits, capacity, zpart, stream);
+    default:
+      return RP_ESHAPE;
+  }
+}
+
+// Forward of the CE head.  hc bf16 [capacity, d] (rows >= *n_valid ignored), table bf16 [n_items, d], labels int32
+// [capacity], n_valid int32 [1] (device).  Outputs: loss_out fp32 [2] = {mean CE, 1/T_v}; lse fp32 [capacity]; cvec fp32
+// (exponent offsets consumed by rp_ce_head_bwd).
+// d_hc != NULL (training, d <= 256) enables the FUSED path: one pass computes the row sums of exp(s) against a fixed
+// reference maximum of 0 together with the un-normalised gradient sum_i exp(s_i) E_i, so the separate log-sum-exp pass
+// disappears and d_hc is already final after this call.  A device-side Cauchy-Schwarz bound on |s| guards the trick; if
+// it fails the two-pass kernels run instead (both variants are launched, the losing one exits at once), so the call
+// stays CUDA-graph capturable.  n_valid_hint (host estimate of *n_valid, 0 = unknown) only tunes the load balance.
 RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, const int32_t* labels,
                           const int32_t* n_valid, int capacity, int n_items, int d, float* loss_out, float* lse, float* cvec,
-                          void* workspace, size_t workspace_bytes, void* stream_) {
+                          void* d_hc, int n_valid_hint, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!hc || !table || !labels || !n_valid || !loss_out || !lse || !cvec || !workspace) return RP_EINVAL;
   if (capacity <= 0 || n_items <= 0) return RP_ESHAPE;
   if (d != 64 && d != 128 && d != 256 && d != 512) return RP_ESHAPE;
-  if (workspace_bytes < rp_ce_head_workspace(capacity, n_items, d)) return RP_EWORKSPACE;
+  if (workspace_bytes < ce_ws_bytes(capacity, d)) return RP_EWORKSPACE;
+  const bool fused = d_hc != nullptr && d <= 256;
   const int n_tok_tiles = (capacity + kT - 1) / kT, n_item_tiles = (n_items + kT - 1) / kT;
-  const int P = pick_splits(n_tok_tiles, n_item_tiles);
-  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  float2* part = reinterpret_cast<float2*>(ws);
-  float* zt = reinterpret_cast<float*>(ws + (size_t)capacity * 8 * 2 * sizeof(float2));
-  float* block_sums = zt + capacity;
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(block_sums + 1024);
+  const int hint_tiles = (n_valid_hint > 0 && n_valid_hint <= capacity) ? (n_valid_hint + kT - 1) / kT : n_tok_tiles;
+  CeWs ws = ce_ws(workspace, capacity, d);
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = make_tmap_bf16(&tmA, hc, capacity, d, d, 128)) != RP_OK) return rc;
   if ((rc = make_tmap_bf16(&tmB, table, n_items, d, d, 128)) != RP_OK) return rc;
-  switch (d) {
-    case 64: rc = launch_ce_fwd<1, 8>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, bias, part, stream); break;
-    case 128: rc = launch_ce_fwd<2, 8>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, bias, part, stream); break;
-    case 256: rc = launch_ce_fwd<4, 8>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, bias, part, stream); break;
-    default: rc = launch_ce_fwd<8, 5>(tmA, tmB, n_valid, n_items, P, n_tok_tiles, bias, part, stream); break;
-  }
-  if (rc != RP_OK) return rc;
-  RP_CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, stream));
+  RP_CUDA_CHECK(cudaMemsetAsync(ws.ticket, 0, 64, stream));  // ticket, bound[3], flag
+  const int32_t* skip = nullptr;
   int blocks = (capacity + 7) / 8;
   if (blocks > 1024) blocks = 1024;
-  ce_finalize_kernel<<<blocks, 256, 0, stream>>>(part, reinterpret_cast<const __nv_bfloat16*>(hc),
-                                                 reinterpret_cast<const __nv_bfloat16*>(table), labels, bias, n_valid, P * 2,
-                                                 capacity, d, lse, cvec, block_sums, ticket, loss_out);
+  if (fused) {
+    ce_bound_kernel<<<sm_count() * 2, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hc),
+                                                        reinterpret_cast<const __nv_bfloat16*>(table), bias, n_valid, n_items, d,
+                                                        ws.bound);
+    RP_LAUNCH_CHECK();
+    ce_flag_kernel<<<1, 1, 0, stream>>>(ws.bound, ws.flag);
+    RP_LAUNCH_CHECK();
+    const int P = pick_splits(hint_tiles, n_item_tiles);
+    rc = dispatch_ce_bwd<2>(d, tmA, tmB, cvec, labels, table, loss_out + 1, n_valid, n_items, bias, nullptr, ws.part_dh,
+                            n_tok_tiles * P, ws.flag, 1, P, capacity, ws.zpart, stream);
+    if (rc != RP_OK) return rc;
+    ce_fused_finalize_kernel<<<blocks, 256, 0, stream>>>(ws.part_dh, ws.zpart, reinterpret_cast<const __nv_bfloat16*>(hc),
+                                                         reinterpret_cast<const __nv_bfloat16*>(table), labels, bias, n_valid,
+                                                         ws.flag, P, capacity, d, lse, cvec,
+                                                         reinterpret_cast<__nv_bfloat16*>(d_hc), ws.block_sums, ws.ticket, loss_out);
+    RP_LAUNCH_CHECK();
+    skip = ws.flag;
+  }
+  const int P2 = pick_splits(hint_tiles, n_item_tiles);
+  switch (d) {
+    case 64: rc = launch_ce_fwd<1, 8>(tmA, tmB, n_valid, n_items, P2, n_tok_tiles, bias, ws.part, skip, stream); break;
+    case 128: rc = launch_ce_fwd<2, 8>(tmA, tmB, n_valid, n_items, P2, n_tok_tiles, bias, ws.part, skip, stream); break;
+    case 256: rc = launch_ce_fwd<4, 8>(tmA, tmB, n_valid, n_items, P2, n_tok_tiles, bias, ws.part, skip, stream); break;
+    default: rc = launch_ce_fwd<8, 5>(tmA, tmB, n_valid, n_items, P2, n_tok_tiles, bias, ws.part, skip, stream); break;
+  }
+  if (rc != RP_OK) return rc;
+  ce_finalize_kernel<<<blocks, 256, 0, stream>>>(ws.part, reinterpret_cast<const __nv_bfloat16*>(hc),
+                                                 reinterpret_cast<const __nv_bfloat16*>(table), labels, bias, n_valid, P2 * 2,
+                                                 capacity, d, lse, cvec, ws.block_sums, ws.ticket, loss_out, skip);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }
 
-template <int KCH, int NSTAGE, bool COLCONST>
-static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* cvec, const int32_t* labels,
-                         const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, const float* bias,
-                         float* d_bias, void* out, int grid, cudaStream_t stream) {
-  const int smem = (1 + NSTAGE) * KCH * kChunk + 1024;
-  constexpr int NBUF = (RP_CE_NBUF3 && KCH <= 2) ? 3 : 2;  // 3 S buffers + [128 x d] accumulator fit the 512 TMEM columns up to d = 128
-  auto kern = ce_bwd_kernel<KCH, NSTAGE, COLCONST, NBUF>;
-  RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, cvec, labels, reinterpret_cast<const __nv_bfloat16*>(table), loss_inv,
-                                         n_valid, n_items, bias, d_bias, out);
-  RP_LAUNCH_CHECK();
-  return RP_OK;
-}
-
-// Backward of rp_ce_head_fwd w.r.t. its two inputs, for d(loss) = 1:
-//   d_hc   bf16 [capacity, d]  (rows < *n_valid written)
-//   d_table fp32 [n_items, d]  OVERWRITTEN with softmax^T . hc / T_v, then the one-hot part is atomically subtracted.
-// d in {64,128,256}.
+// Backward of rp_ce_head_fwd for d(loss) = 1:
+//   d_hc   bf16 [capacity, d]  (rows < *n_valid) - already written by the forward when it ran fused (`fused` != 0 and the
+//          device-side bound held); otherwise computed here from the stored lse
+//   d_table fp32 [n_items, d]  OVERWRITTEN with softmax^T . hc / T_v, then the one-hot part is atomically subtracted
+//   d_bias  fp32 [n_items] (iff bias)  OVERWRITTEN likewise.        d in {64,128,256}.
 RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, const int32_t* labels,
                           const int32_t* n_valid, int capacity, int n_items, int d, const float* loss_out /* from fwd */,
-                          const float* cvec /* from fwd */, void* d_hc, float* d_table, float* d_bias, void* stream_) {
+                          const float* cvec /* from fwd */, void* d_hc, float* d_table, float* d_bias, int fused,
+                          void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!hc || !table || !labels || !n_valid || !loss_out || !cvec || !d_hc || !d_table) return RP_EINVAL;
   if ((bias == nullptr) != (d_bias == nullptr)) return RP_EINVAL;
   if (capacity <= 0 || n_items <= 0) return RP_ESHAPE;
   if (d != 64 && d != 128 && d != 256) return RP_ESHAPE;
+  if (fused && (!workspace || workspace_bytes < ce_ws_bytes(capacity, d))) return RP_EWORKSPACE;
   CUtensorMap tmH, tmE;
   int rc;
   if ((rc = make_tmap_bf16(&tmH, hc, capacity, d, d, 128)) != RP_OK) return rc;
   if ((rc = make_tmap_bf16(&tmE, table, n_items, d, d, 128)) != RP_OK) return rc;
   const int n_tok_tiles = (capacity + kT - 1) / kT, n_item_tiles = (n_items + kT - 1) / kT;
   const float* loss_inv = loss_out + 1;
-  switch (d) {
-    case 64:
-      rc = launch_ce_bwd<1, 6, false>(tmH, tmE, cvec, labels, table, loss_inv, n_valid, n_items, bias, nullptr, d_hc, n_tok_tiles, stream);
-      if (rc == RP_OK)
-        rc = launch_ce_bwd<1, 6, true>(tmE, tmH, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, d_table, n_item_tiles, stream);
-      break;
-    case 128:
-      rc = launch_ce_bwd<2, 4, false>(tmH, tmE, cvec, labels, table, loss_inv, n_valid, n_items, bias, nullptr, d_hc, n_tok_tiles, stream);
-      if (rc == RP_OK)
-        rc = launch_ce_bwd<2, 4, true>(tmE, tmH, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, d_table, n_item_tiles, stream);
-      break;
-    default:
-      rc = launch_ce_bwd<4, 2, false>(tmH, tmE, cvec, labels, table, loss_inv, n_valid, n_items, bias, nullptr, d_hc, n_tok_tiles, stream);
-      if (rc == RP_OK)
-        rc = launch_ce_bwd<4, 2, true>(tmE, tmH, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, d_table, n_item_tiles, stream);
-      break;
-  }
+  const int32_t* flag = fused ? ce_ws(workspace, capacity, d).flag : nullptr;
+  // token-major pass: only when the forward did not already produce d_hc
+  rc = dispatch_ce_bwd<0>(d, tmH, tmE, cvec, labels, table, loss_inv, n_valid, n_items, bias, nullptr, d_hc, n_tok_tiles, flag, 0,
+                          1, capacity, nullptr, stream);
+  if (rc != RP_OK) return rc;
+  rc = dispatch_ce_bwd<1>(d, tmE, tmH, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, d_table, n_item_tiles,
+                          nullptr, 0, 1, capacity, nullptr, stream);
   if (rc != RP_OK) return rc;
   ce_label_scatter_kernel<<<sm_count() * 4, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hc), labels, loss_inv,
                                                                n_valid, d, d_table, d_bias);

@@ -128,6 +128,8 @@ class SasRecEngine:
         self.rng_counter = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self.seed = seed & 0xFFFFFFFFFFFF
         self.training = with_grad
+        self.fused_ce = True      # single-pass CE forward + dH (guarded on the device by a bound on |logit|)
+        self.n_valid_hint = 0     # host estimate of the number of valid targets per step (load balance of the CE head only)
         self._alloc_workspace()
         self.init_parameters(seed)
 
@@ -359,7 +361,8 @@ class SasRecEngine:
         from .ops import ce_head_fwd
 
         self.lib.count += 2
-        return ce_head_fwd(self.ce, self.hc, self.params16["item_emb"][: cfg.n_items], self.labels_c, self.n_valid)
+        return ce_head_fwd(self.ce, self.hc, self.params16["item_emb"][: cfg.n_items], self.labels_c, self.n_valid,
+                           d_hc=self.s["dhc"] if self.fused_ce else None, n_valid_hint=self.n_valid_hint)
 
     # ------------------------------------------------------------------------------------------------ backward
     def backward(self):

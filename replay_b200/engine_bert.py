@@ -81,6 +81,8 @@ class Bert4RecEngine(SasRecEngine):
             self.step_count = torch.zeros(1, device=self.dev, dtype=torch.int32)
         self.rng_counter = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self.seed = seed & 0xFFFFFFFFFFFF
+        self.fused_ce = True
+        self.n_valid_hint = 0
         self._alloc_bert_workspace()
         self.init_parameters(seed)
 
@@ -254,7 +256,8 @@ class Bert4RecEngine(SasRecEngine):
                                       self.cfg.d, self.hc.data_ptr(), 0, self._stream()), "rp_gather_rows")
         W16, bias = self._head()
         self.lib.count += 2
-        return ce_head_fwd(self.ce, self.hc, W16, self.labels_c, self.n_valid, bias=bias)
+        return ce_head_fwd(self.ce, self.hc, W16, self.labels_c, self.n_valid, bias=bias,
+                           d_hc=self.s["dhc"] if self.fused_ce else None, n_valid_hint=self.n_valid_hint)
 
     # ------------------------------------------------------------------------------------------------ backward
     def backward(self):

@@ -76,22 +76,27 @@ class CEHeadState:
         self.cvec = torch.full((cap128,), float("-inf"), device=device, dtype=torch.float32)
 
 
-def ce_head_fwd(st: CEHeadState, hc, table, labels, n_valid, bias=None):
+def ce_head_fwd(st: CEHeadState, hc, table, labels, n_valid, bias=None, d_hc=None, n_valid_hint: int = 0):
     """hc bf16 [capacity,d] (zero/finite beyond n_valid), table bf16 [I,d], labels int32 [capacity], n_valid int32 [1].
+    With ``d_hc`` (bf16 [capacity,d]) the fused forward+dH pass runs and d_hc is final after this call.
     Returns st.loss (fp32 [2]: mean CE, 1/n_valid) - a view that the next call overwrites."""
     _need(hc, torch.bfloat16, "hc")
     _need(table, torch.bfloat16, "table")
     _need(labels, torch.int32, "labels")
     _need(n_valid, torch.int32, "n_valid")
+    if d_hc is not None:
+        _need(d_hc, torch.bfloat16, "d_hc")
+    st.fused = d_hc is not None and st.d <= 256
     check(lib().rp_ce_head_fwd(_ptr(hc), _ptr(table), _ptr(bias), _ptr(labels), _ptr(n_valid), st.capacity, st.n_items, st.d,
-                               _ptr(st.loss), _ptr(st.lse), _ptr(st.cvec), _ptr(st.ws), st.ws_bytes, _stream()),
-          "rp_ce_head_fwd")
+                               _ptr(st.loss), _ptr(st.lse), _ptr(st.cvec), _ptr(d_hc), int(n_valid_hint), _ptr(st.ws),
+                               st.ws_bytes, _stream()), "rp_ce_head_fwd")
     return st.loss
 
 
 def ce_head_bwd(st: CEHeadState, hc, table, labels, n_valid, d_hc, d_table, bias=None, d_bias=None):
-    """d_hc bf16 [capacity,d], d_table fp32 [>=I, d] (rows < I overwritten)."""
+    """d_hc bf16 [capacity,d] (computed here unless the forward ran fused), d_table fp32 [>=I, d] (rows < I overwritten)."""
     _need(d_hc, torch.bfloat16, "d_hc")
     _need(d_table, torch.float32, "d_table")
     check(lib().rp_ce_head_bwd(_ptr(hc), _ptr(table), _ptr(bias), _ptr(labels), _ptr(n_valid), st.capacity, st.n_items, st.d,
-                               _ptr(st.loss), _ptr(st.cvec), _ptr(d_hc), _ptr(d_table), _ptr(d_bias), _stream()), "rp_ce_head_bwd")
+                               _ptr(st.loss), _ptr(st.cvec), _ptr(d_hc), _ptr(d_table), _ptr(d_bias), int(getattr(st, "fused", False)),
+                               _ptr(st.ws), st.ws_bytes, _stream()), "rp_ce_head_bwd")

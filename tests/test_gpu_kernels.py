@@ -87,9 +87,10 @@ def test_score_topk_golden_reference(ops, golden_dir):
     assert overlap > 0.9
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("T,n_valid,I,d", [(256, 256, 1000, 64), (300, 217, 5000, 128), (1024, 1000, 20001, 128),
                                            (384, 300, 3000, 256)])
-def test_ce_head_fwd_bwd_matches_oracle(ops, T, n_valid, I, d):
+def test_ce_head_fwd_bwd_matches_oracle(ops, T, n_valid, I, d, fused):
     """Fused CE head vs the oracle's logsumexp CE (nn/loss/ce.py:49-81) and its autograd gradients."""
     g = torch.Generator().manual_seed(T + I)
     hc = (torch.randn(T, d, generator=g) * 1.0).to(torch.bfloat16)
@@ -106,13 +107,14 @@ def test_ce_head_fwd_bwd_matches_oracle(ops, T, n_valid, I, d):
 
     st = ops.CEHeadState(T, I, d, "cuda")
     nv = torch.tensor([n_valid], dtype=torch.int32, device="cuda")
-    out = ops.ce_head_fwd(st, hc.cuda(), table.cuda(), labels.int().cuda(), nv)
+    d_hc = torch.zeros(T, d, device="cuda", dtype=torch.bfloat16)
+    out = ops.ce_head_fwd(st, hc.cuda(), table.cuda(), labels.int().cuda(), nv, d_hc=d_hc if fused else None,
+                          n_valid_hint=n_valid)
     torch.cuda.synchronize()
     assert abs(out[0].item() - loss.item()) < 2e-4 * max(1.0, abs(loss.item())), (out[0].item(), loss.item())
     assert abs(out[1].item() - 1.0 / n_valid) < 1e-9
     torch.testing.assert_close(st.lse[:n_valid].cpu().double(), lse.detach(), rtol=1e-5, atol=1e-4)
 
-    d_hc = torch.zeros(T, d, device="cuda", dtype=torch.bfloat16)
     d_tab = torch.full((I + 1, d), 7.0, device="cuda", dtype=torch.float32)  # must be overwritten, pad row untouched
     ops.ce_head_bwd(st, hc.cuda(), table.cuda(), labels.int().cuda(), nv, d_hc, d_tab)
     torch.cuda.synchronize()
@@ -124,3 +126,28 @@ def test_ce_head_fwd_bwd_matches_oracle(ops, T, n_valid, I, d):
     assert ee < 1e-2, f"dE rel err {ee}"
     assert (d_tab[I] == 7.0).all()
     assert (d_hc[n_valid:] == 0).all()
+
+
+def test_ce_head_fused_falls_back_when_logits_are_unbounded(ops):
+    """The single-reference-max trick is guarded by a device-side bound on |logit|; huge logits must take the two-pass
+    path (and still give the right loss / gradients) without any host-side decision."""
+    T, n_valid, I, d = 256, 200, 2000, 64
+    g = torch.Generator().manual_seed(1)
+    hc = (torch.randn(T, d, generator=g) * 6.0).to(torch.bfloat16)  # ||h|| ~ 48, ||e|| ~ 16 -> bound far above 100/log2e
+    hc[n_valid:] = 0
+    table = (torch.randn(I, d, generator=g) * 2.0).to(torch.bfloat16)
+    labels = torch.randint(0, I, (T,), generator=g, dtype=torch.int64)
+    h64, e64 = hc[:n_valid].double().requires_grad_(True), table.double().requires_grad_(True)
+    logits = h64 @ e64.T
+    loss = (torch.logsumexp(logits, -1) - logits.gather(1, labels[:n_valid, None])[:, 0]).mean()
+    loss.backward()
+    st = ops.CEHeadState(T, I, d, "cuda")
+    nv = torch.tensor([n_valid], dtype=torch.int32, device="cuda")
+    d_hc = torch.zeros(T, d, device="cuda", dtype=torch.bfloat16)
+    d_tab = torch.zeros(I + 1, d, device="cuda")
+    out = ops.ce_head_fwd(st, hc.cuda(), table.cuda(), labels.int().cuda(), nv, d_hc=d_hc, n_valid_hint=n_valid)
+    ops.ce_head_bwd(st, hc.cuda(), table.cuda(), labels.int().cuda(), nv, d_hc, d_tab)
+    torch.cuda.synchronize()
+    assert abs(out[0].item() - loss.item()) < 1e-3 * abs(loss.item()), (out[0].item(), loss.item())
+    assert (d_hc[:n_valid].cpu().double() - h64.grad).norm() / h64.grad.norm() < 1e-2
+    assert (d_tab[:I].cpu().double() - e64.grad).norm() / e64.grad.norm() < 1e-2

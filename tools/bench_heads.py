@@ -38,7 +38,7 @@ for T in (28672, 51200):
     st = ops.CEHeadState(T, I, d, "cuda")
     d_hc = torch.zeros(T, d, device="cuda", dtype=torch.bfloat16)
     d_tab = torch.zeros(I + 1, d, device="cuda")
-    ms_f = timeit(lambda: ops.ce_head_fwd(st, hc, table, labels, nv))
+    ms_f = timeit(lambda: ops.ce_head_fwd(st, hc, table, labels, nv, d_hc=d_hc, n_valid_hint=int(nv.item())))
     ms_b = timeit(lambda: ops.ce_head_bwd(st, hc, table, labels, nv, d_hc, d_tab))
     fl = 2.0 * T * I * d
     res[f"ce_T{T}"] = dict(fwd_ms=ms_f, bwd_ms=ms_b, fwd_tflops=fl / ms_f / 1e9, bwd_tflops_credited=2 * fl / ms_b / 1e9,

@@ -11,6 +11,6 @@ nv = torch.tensor([nv_], dtype=torch.int32, device="cuda")
 st = ops.CEHeadState(T, I, d, "cuda")
 d_hc = torch.zeros(T, d, device="cuda", dtype=torch.bfloat16); d_tab = torch.zeros(I + 1, d, device="cuda")
 for _ in range(2):
-    ops.ce_head_fwd(st, hc, table, labels, nv)
+    ops.ce_head_fwd(st, hc, table, labels, nv, d_hc=d_hc, n_valid_hint=int(nv.item()))
     ops.ce_head_bwd(st, hc, table, labels, nv, d_hc, d_tab)
 torch.cuda.synchronize()

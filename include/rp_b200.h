@@ -157,7 +157,7 @@ int rp_attn_softmax_bwd(void* p_save, void* dpd, const float* inv_sum, int BH, i
  * labels/target_mask may be NULL (predict). */
 int rp_prepare_batch(const int64_t* ids, const uint8_t* pad_mask, const int64_t* labels, const uint8_t* target_mask, int T,
                      int pad_id, int n_items, int32_t* ids32, int32_t* valid_idx, int32_t* labels_c, int32_t* n_valid,
-                     void* stream);
+                     int32_t* scratch /* >= ceil(T/1024) ints, needed with targets */, void* stream);
 
 /* x[t] = table[ids[t]] * scale + pos[pos0 + t % L] -> dropout -> (zero pad rows)      nn/sequential/sasrec/agg.py:37-53,
  * models/nn/sequential/sasrec/model.py:346-357 ; and its backward (fp32 atomics into d_table, pad row frozen). */

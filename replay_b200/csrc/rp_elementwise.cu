@@ -23,55 +23,73 @@ __device__ __forceinline__ float warp_sum(float v) {
 // valid targets (ascending token index), their labels, and the count (device memory).
 // Single block: T is at most a few hundred thousand tokens.
 // ------------------------------------------------------------------------------------------------------------------
+// pass 1 (many blocks): ids conversion + number of valid targets per block of 1024 tokens
 __global__ void __launch_bounds__(1024, 1)
-prepare_batch_kernel(const int64_t* __restrict__ ids64, const uint8_t* __restrict__ pad_mask,
+prepare_count_kernel(const int64_t* __restrict__ ids64, const uint8_t* __restrict__ pad_mask,
                      const int64_t* __restrict__ labels64, const uint8_t* __restrict__ target_mask, int T, int pad_id,
-                     int n_items, int32_t* __restrict__ ids32, int32_t* __restrict__ valid_idx,
-                     int32_t* __restrict__ labels_c, int32_t* __restrict__ n_valid) {
+                     int n_items, int32_t* __restrict__ ids32, int32_t* __restrict__ block_counts) {
   __shared__ int warp_tot[32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // coalesced pass: ids
-  for (int t = tid; t < T; t += 1024) {
+  const int t = blockIdx.x * 1024 + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool valid = false;
+  if (t < T) {
     const int64_t id = ids64[t];
     ids32[t] = (pad_mask[t] && id >= 0 && id < n_items) ? (int32_t)id : pad_id;
+    if (target_mask) {
+      const int64_t y = labels64[t];
+      valid = target_mask[t] != 0 && y >= 0 && y < n_items;
+    }
   }
   if (!target_mask) return;
-  // each thread owns a contiguous slab of tokens so the compacted order is the token order
-  const int per = (T + 1023) / 1024;
-  const int t0 = tid * per, t1 = min(T, t0 + per);
-  int cnt = 0;
-  for (int t = t0; t < t1; ++t) {
-    const int64_t y = labels64[t];
-    cnt += (target_mask[t] != 0 && y >= 0 && y < n_items) ? 1 : 0;
-  }
-  int incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) warp_tot[warp] = incl;
+  const unsigned bal = __ballot_sync(0xffffffffu, valid);
+  if (lane == 0) warp_tot[warp] = __popc(bal);
   __syncthreads();
   if (warp == 0) {
     int w = warp_tot[lane];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += v;
-    }
-    warp_tot[lane] = w;  // inclusive
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (lane == 0) block_counts[blockIdx.x] = w;
+  }
+}
+
+// pass 2 (same grid): every block sums the counts of the blocks before it (<= a few hundred) and writes its survivors
+__global__ void __launch_bounds__(1024, 1)
+prepare_write_kernel(const int64_t* __restrict__ labels64, const uint8_t* __restrict__ target_mask, int T, int n_items,
+                     const int32_t* __restrict__ block_counts, int32_t* __restrict__ valid_idx,
+                     int32_t* __restrict__ labels_c, int32_t* __restrict__ n_valid) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  const int t = blockIdx.x * 1024 + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int part = 0;
+  for (int b = threadIdx.x; b < (int)blockIdx.x; b += 1024) part += block_counts[b];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) warp_tot[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s0 = 0;
+    for (int w = 0; w < 32; ++w) s0 += warp_tot[w];
+    base_s = s0;
   }
   __syncthreads();
-  int pos = incl - cnt + (warp > 0 ? warp_tot[warp - 1] : 0);
-  for (int t = t0; t < t1; ++t) {
-    const int64_t y = labels64[t];
-    if (target_mask[t] != 0 && y >= 0 && y < n_items) {
-      valid_idx[pos] = t;
-      labels_c[pos] = (int32_t)y;
-      ++pos;
-    }
+  bool valid = false;
+  int64_t y = 0;
+  if (t < T) {
+    y = labels64[t];
+    valid = target_mask[t] != 0 && y >= 0 && y < n_items;
   }
-  if (tid == 1023) *n_valid = warp_tot[31];
+  const unsigned bal = __ballot_sync(0xffffffffu, valid);
+  const int pre = __popc(bal & ((1u << lane) - 1));
+  __syncthreads();
+  if (lane == 0) warp_tot[warp] = __popc(bal);
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+  const int pos = base_s + woff + pre;
+  if (valid) {
+    valid_idx[pos] = t;
+    labels_c[pos] = (int32_t)y;
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1023) *n_valid = pos + (valid ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -462,13 +480,18 @@ using namespace rp;
 
 RP_API int rp_prepare_batch(const int64_t* ids, const uint8_t* pad_mask, const int64_t* labels, const uint8_t* target_mask,
                             int T, int pad_id, int n_items, int32_t* ids32, int32_t* valid_idx, int32_t* labels_c,
-                            int32_t* n_valid, void* stream_) {
+                            int32_t* n_valid, int32_t* scratch /* >= ceil(T/1024) ints */, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!ids || !pad_mask || !ids32 || T <= 0) return RP_EINVAL;
   if (target_mask && (!labels || !valid_idx || !labels_c || !n_valid)) return RP_EINVAL;
-  prepare_batch_kernel<<<1, 1024, 0, stream>>>(ids, pad_mask, labels, target_mask, T, pad_id, n_items, ids32, valid_idx,
-                                               labels_c, n_valid);
+  const int n_blocks = (T + 1023) / 1024;
+  if (target_mask && !scratch) return RP_EINVAL;
+  prepare_count_kernel<<<n_blocks, 1024, 0, stream>>>(ids, pad_mask, labels, target_mask, T, pad_id, n_items, ids32, scratch);
   RP_LAUNCH_CHECK();
+  if (target_mask) {
+    prepare_write_kernel<<<n_blocks, 1024, 0, stream>>>(labels, target_mask, T, n_items, scratch, valid_idx, labels_c, n_valid);
+    RP_LAUNCH_CHECK();
+  }
   return RP_OK;
 }
 

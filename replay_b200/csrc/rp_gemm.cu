@@ -9,6 +9,8 @@
 //    replay/models/nn/sequential/sasrec/model.py:407-414,490-506 ; replay/models/nn/sequential/bert4rec/model.py:471-527).
 //
 // CTA = one 128 x BN output tile (x one K split).  warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue.
+#include <stdlib.h>
+
 #include "rp_host.h"
 #include "rp_philox.cuh"
 #include "rp_sm100.cuh"
@@ -42,112 +44,22 @@ struct GemmParams {
   unsigned long long post_drop_offset;
 };
 
-static constexpr int kGemmThreads = 192;
+// Epilogue of one [1 row x 32 columns] strip held in registers (shared by the tile kernel and the persistent kernel).
+struct EpiRow {
+  long long c_base;   // element offset of this output row in C
+  float rm;           // row-mask factor
+  float keep_scale;
+  uint32_t drop_thr;
+  unsigned long long seed_eff;
+};
 
-template <int BN, bool A_MN, bool B_MN, int NSTAGE>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  constexpr int A_BYTES = 128 * 128;       // [128 x 64] bf16
-  constexpr int B_BYTES = BN * 128;        // [BN x 64] bf16
-  constexpr int STAGE = A_BYTES + B_BYTES;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_acc;
-  __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float s_bias[BN];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x;
-  const int m_tile = blockIdx.y / p.split_k, ksplit = blockIdx.y % p.split_k;
-  const int bz = blockIdx.z, outer = bz / p.inner, in = bz % p.inner;
-  const int m0 = m_tile * 128, n0 = n_tile * BN;
-  const int k_chunks = (p.K + 63) / 64;
-  const int kc_begin = (int)(((long long)k_chunks * ksplit) / p.split_k);
-  const int kc_end = (int)(((long long)k_chunks * (ksplit + 1)) / p.split_k);
-  const int a_r = p.a_r0 + outer * p.a_ro + in * p.a_ri, a_c = p.a_c0 + outer * p.a_co + in * p.a_ci;
-  const int b_r = p.b_r0 + outer * p.b_ro + in * p.b_ri, b_c = p.b_c0 + outer * p.b_co + in * p.b_ci;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) {
-      mbar_init(&bar_full[i], 1);
-      mbar_init(&bar_empty[i], 1);
-    }
-    mbar_init(&bar_acc, 1);
-    fence_barrier_init();
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-  }
-  if (warp == 1) tmem_alloc(&tmem_slot, BN < 32 ? 32 : BN);
-  if (p.bias != nullptr && threadIdx.x >= 64) {
-    for (int i = threadIdx.x - 64; i < BN; i += 128) s_bias[i] = (n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-
-  if (warp == 0) {
-    if (elect_one()) {
-      for (int kc = kc_begin, it = 0; kc < kc_end; ++kc, ++it) {
-        const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
-        mbar_wait(&bar_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&bar_full[s], STAGE);
-        uint8_t* sa = smem + s * STAGE;
-        uint8_t* sb = sa + A_BYTES;
-        if (A_MN) {  // stored [K rows, M cols]: two boxes of [64 k-rows x 64 m]
-          tma_load_2d(sa, &tmA, &bar_full[s], a_c + m0, a_r + kc * 64);
-          tma_load_2d(sa + 8192, &tmA, &bar_full[s], a_c + m0 + 64, a_r + kc * 64);
-        } else {     // stored [M rows, K cols]: one box of [128 rows x 64 k]
-          tma_load_2d(sa, &tmA, &bar_full[s], a_c + kc * 64, a_r + m0);
-        }
-        if (B_MN) {
-#pragma unroll
-          for (int c = 0; c < BN / 64; ++c)
-            tma_load_2d(sb + c * 8192, &tmB, &bar_full[s], b_c + n0 + c * 64, b_r + kc * 64);
-        } else {
-          tma_load_2d(sb, &tmB, &bar_full[s], b_c + kc * 64, b_r + n0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, A_MN, B_MN);
-      for (int kc = kc_begin, it = 0; kc < kc_end; ++kc, ++it) {
-        const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
-        mbar_wait(&bar_full[s], ph);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(smem + s * STAGE), b0 = a0 + A_BYTES;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ad = A_MN ? umma_desc_sw128(a0 + ks * 2048, 8192, 1024) : umma_desc_sw128(a0 + ks * 32, 16, 1024);
-          const uint64_t bd = B_MN ? umma_desc_sw128(b0 + ks * 2048, 8192, 1024) : umma_desc_sw128(b0 + ks * 32, 16, 1024);
-          umma_ss(tmem, ad, bd, idesc, (it | ks) != 0);
-        }
-        umma_commit(&bar_empty[s]);
-      }
-      umma_commit(&bar_acc);
-    }
-  } else {
-    // ------------------------------------------------ epilogue: thread = output row
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const int m = m0 + row;
-    mbar_wait(&bar_acc, 0);
-    tc_fence_after();
-    const bool row_ok = m < p.M;
-    const long long c_base = p.c_off0 + (long long)outer * p.c_oo + (long long)in * p.c_oi + (long long)m * p.ldc;
-    float rm = 1.f;
-    if (p.rowmask && row_ok) rm = p.rowmask[p.rowmask_off0 + (long long)outer * p.rowmask_oo + m] ? 1.f : 0.f;
-    const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-    const uint32_t drop_thr = p.drop_p > 0.f ? (uint32_t)(p.drop_p * 4294967296.0) : 0u;
-    const unsigned long long seed_eff = p.seed + ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t raw[32];
-      tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + c, raw);
-      tmem_ld_wait();
-      if (!row_ok || n0 + c >= p.N) continue;
-      float x[32];
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const float* __restrict__ s_bias, const EpiRow& er,
+                                                    const uint32_t (&raw)[32], int n0, int c) {
+  const long long c_base = er.c_base;
+  const float rm = er.rm, keep_scale = er.keep_scale;
+  const uint32_t drop_thr = er.drop_thr;
+  const unsigned long long seed_eff = er.seed_eff;
+  float x[32];
 #pragma unroll
       for (int q = 0; q < 32; ++q) x[q] = __uint_as_float(raw[q]) * p.alpha;
       if (p.bias) {
@@ -265,6 +177,117 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (n0 + c + q < p.N) o[q] = x[q];
         }
       }
+}
+
+static constexpr int kGemmThreads = 192;
+
+template <int BN, bool A_MN, bool B_MN, int NSTAGE>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int A_BYTES = 128 * 128;       // [128 x 64] bf16
+  constexpr int B_BYTES = BN * 128;        // [BN x 64] bf16
+  constexpr int STAGE = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_acc;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_bias[BN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x;
+  const int m_tile = blockIdx.y / p.split_k, ksplit = blockIdx.y % p.split_k;
+  const int bz = blockIdx.z, outer = bz / p.inner, in = bz % p.inner;
+  const int m0 = m_tile * 128, n0 = n_tile * BN;
+  const int k_chunks = (p.K + 63) / 64;
+  const int kc_begin = (int)(((long long)k_chunks * ksplit) / p.split_k);
+  const int kc_end = (int)(((long long)k_chunks * (ksplit + 1)) / p.split_k);
+  const int a_r = p.a_r0 + outer * p.a_ro + in * p.a_ri, a_c = p.a_c0 + outer * p.a_co + in * p.a_ci;
+  const int b_r = p.b_r0 + outer * p.b_ro + in * p.b_ri, b_c = p.b_c0 + outer * p.b_co + in * p.b_ci;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    mbar_init(&bar_acc, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, BN < 32 ? 32 : BN);
+  if (p.bias != nullptr && threadIdx.x >= 64) {
+    for (int i = threadIdx.x - 64; i < BN; i += 128) s_bias[i] = (n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int kc = kc_begin, it = 0; kc < kc_end; ++kc, ++it) {
+        const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
+        mbar_wait(&bar_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&bar_full[s], STAGE);
+        uint8_t* sa = smem + s * STAGE;
+        uint8_t* sb = sa + A_BYTES;
+        if (A_MN) {  // stored [K rows, M cols]: two boxes of [64 k-rows x 64 m]
+          tma_load_2d(sa, &tmA, &bar_full[s], a_c + m0, a_r + kc * 64);
+          tma_load_2d(sa + 8192, &tmA, &bar_full[s], a_c + m0 + 64, a_r + kc * 64);
+        } else {     // stored [M rows, K cols]: one box of [128 rows x 64 k]
+          tma_load_2d(sa, &tmA, &bar_full[s], a_c + kc * 64, a_r + m0);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_2d(sb + c * 8192, &tmB, &bar_full[s], b_c + n0 + c * 64, b_r + kc * 64);
+        } else {
+          tma_load_2d(sb, &tmB, &bar_full[s], b_c + kc * 64, b_r + n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, A_MN, B_MN);
+      for (int kc = kc_begin, it = 0; kc < kc_end; ++kc, ++it) {
+        const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
+        mbar_wait(&bar_full[s], ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + s * STAGE), b0 = a0 + A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ad = A_MN ? umma_desc_sw128(a0 + ks * 2048, 8192, 1024) : umma_desc_sw128(a0 + ks * 32, 16, 1024);
+          const uint64_t bd = B_MN ? umma_desc_sw128(b0 + ks * 2048, 8192, 1024) : umma_desc_sw128(b0 + ks * 32, 16, 1024);
+          umma_ss(tmem, ad, bd, idesc, (it | ks) != 0);
+        }
+        umma_commit(&bar_empty[s]);
+      }
+      umma_commit(&bar_acc);
+    }
+  } else {
+    // ------------------------------------------------ epilogue: thread = output row
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int m = m0 + row;
+    mbar_wait(&bar_acc, 0);
+    tc_fence_after();
+    const bool row_ok = m < p.M;
+    const long long c_base = p.c_off0 + (long long)outer * p.c_oo + (long long)in * p.c_oi + (long long)m * p.ldc;
+    float rm = 1.f;
+    if (p.rowmask && row_ok) rm = p.rowmask[p.rowmask_off0 + (long long)outer * p.rowmask_oo + m] ? 1.f : 0.f;
+    EpiRow er;
+    er.c_base = c_base;
+    er.rm = rm;
+    er.keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    er.drop_thr = p.drop_p > 0.f ? (uint32_t)(p.drop_p * 4294967296.0) : 0u;
+    er.seed_eff = p.seed + ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t raw[32];
+      tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + c, raw);
+      tmem_ld_wait();
+      if (!row_ok || n0 + c >= p.N) continue;
+      gemm_epilogue_chunk(p, s_bias, er, raw, n0, c);
     }
   }
   tc_fence_before();
@@ -279,6 +302,162 @@ static int launch_gemm_n(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((p.N + BN - 1) / BN, ((p.M + 127) / 128) * p.split_k, batch);
   kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weight-stationary persistent variant for the tall-skinny projections of the body (M = tokens, N, K <= 256):
+// the CTA keeps its [BN x K] slice of the weight in shared memory, streams 128-row activation tiles through a TMA ring,
+// double-buffers the accumulator in TMEM and overlaps the epilogue of tile i with the loads + MMAs of tile i+1.
+// grid = (ctas_per_n_tile, n_tiles); CTA x handles M tiles x, x + gridDim.x, ...
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr int kWsEpiWarps = 8;
+static constexpr int kWsThreads = 64 + kWsEpiWarps * 32;
+
+template <int BN, int KCH, bool B_MN, int NA>
+__global__ void __launch_bounds__(kWsThreads, 1)
+gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int A_STAGE = KCH * 128 * 128;          // [128 x K]
+  constexpr int B_BYTES = KCH * BN * 128;           // [BN x K]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + B_BYTES;
+  __shared__ uint64_t bar_b, bar_full[NA], bar_empty[NA], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_bias[BN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * BN;
+  const int m_tiles = (p.M + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_b, 1);
+    for (int i = 0; i < NA; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_tfull[i], 1);
+      mbar_init(&bar_tempty[i], kWsEpiWarps);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 2 * BN);
+  if (p.bias != nullptr && threadIdx.x >= 64)
+    for (int i = threadIdx.x - 64; i < BN; i += kWsEpiWarps * 32) s_bias[i] = (n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bar_b, B_BYTES);
+      for (int kc = 0; kc < KCH; ++kc) {
+        if (B_MN) {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_2d(sB + kc * (BN * 128) + c * 8192, &tmB, &bar_b, p.b_c0 + n0 + c * 64, p.b_r0 + kc * 64);
+        } else {
+          tma_load_2d(sB + kc * (BN * 128), &tmB, &bar_b, p.b_c0 + kc * 64, p.b_r0 + n0);
+        }
+      }
+      int it = 0;
+      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+        const uint32_t s = it % NA, ph = (it / NA) & 1;
+        mbar_wait(&bar_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&bar_full[s], A_STAGE);
+        for (int kc = 0; kc < KCH; ++kc)
+          tma_load_2d(sA + s * A_STAGE + kc * 16384, &tmA, &bar_full[s], p.a_c0 + kc * 64, p.a_r0 + mt * 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, B_MN);
+      mbar_wait(&bar_b, 0);
+      int it = 0;
+      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+        const uint32_t s = it % NA, ph = (it / NA) & 1, as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&bar_tempty[as], aph ^ 1);
+        mbar_wait(&bar_full[s], ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA + s * A_STAGE), b0 = smem_u32(sB);
+#pragma unroll
+        for (int kc = 0; kc < KCH; ++kc)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = umma_desc_sw128(a0 + kc * 16384 + ks * 32, 16, 1024);
+            const uint64_t bd = B_MN ? umma_desc_sw128(b0 + kc * (BN * 128) + ks * 2048, 8192, 1024)
+                                     : umma_desc_sw128(b0 + kc * (BN * 128) + ks * 32, 16, 1024);
+            umma_ss(tmem + as * BN, ad, bd, idesc, (kc | ks) != 0);
+          }
+        umma_commit(&bar_empty[s]);
+        umma_commit(&bar_tfull[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue: 8 warps, warp%4 = lane quarter, (warp-2)/4 = column half
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    const int row = quarter * 32 + lane;
+    constexpr int HALF = BN / 2;
+    EpiRow er;
+    er.keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    er.drop_thr = p.drop_p > 0.f ? (uint32_t)(p.drop_p * 4294967296.0) : 0u;
+    er.seed_eff = p.seed + ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
+    int it = 0;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      const int m = mt * 128 + row;
+      const bool row_ok = m < p.M;
+      er.c_base = p.c_off0 + (long long)m * p.ldc;
+      er.rm = 1.f;
+      if (p.rowmask && row_ok) er.rm = p.rowmask[p.rowmask_off0 + m] ? 1.f : 0.f;
+      mbar_wait(&bar_tfull[as], aph);
+      tc_fence_after();
+      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + as * BN + half * HALF;
+      if (HALF == 64) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tbase, r0);
+        tmem_ld32(tbase + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[as]);  // accumulator stage is free once its values sit in registers
+        if (row_ok && n0 + half * HALF < p.N) gemm_epilogue_chunk(p, s_bias, er, r0, n0, half * HALF);
+        if (row_ok && n0 + half * HALF + 32 < p.N) gemm_epilogue_chunk(p, s_bias, er, r1, n0, half * HALF + 32);
+      } else {
+        uint32_t r0[32];
+        tmem_ld32(tbase, r0);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[as]);
+        if (row_ok && n0 + half * HALF < p.N) gemm_epilogue_chunk(p, s_bias, er, r0, n0, half * HALF);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 2 * BN);
+}
+
+template <int BN, int KCH, bool B_MN>
+static int launch_gemm_ws(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  constexpr int NA = 2;  // B + 2 A stages: <= 96 KB for K <= 128 so that two CTAs share an SM
+  const int smem = KCH * BN * 128 + NA * KCH * 128 * 128 + 1024;
+  auto kern = gemm_ws_kernel<BN, KCH, B_MN, NA>;
+  RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + 127) / 128;
+  int per_n = (KCH <= 2 ? 2 : 1) * sm_count() / n_tiles;
+  if (per_n < 1) per_n = 1;
+  if (per_n > m_tiles) per_n = m_tiles;
+  dim3 grid(per_n, n_tiles);
+  kern<<<grid, kWsThreads, smem, st>>>(tmA, tmB, p);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }
@@ -336,6 +515,19 @@ RP_API int rp_gemm(const rp_gemm_desc* g, void* stream_) {
   const int bn = (g->N <= 64) ? 64 : 128;
   if ((rc = make_tmap_bf16(&tmA, g->A, g->a_rows, g->a_cols, g->lda, g->a_mn ? 64 : 128)) != RP_OK) return rc;
   if ((rc = make_tmap_bf16(&tmB, g->B, g->b_rows, g->b_cols, g->ldb, g->b_mn ? 64 : bn)) != RP_OK) return rc;
+  // weight-stationary persistent kernel: activation [M, K] K-major, K in {64,128,256}, one batch, no split-K
+  static const int ws_min_m = getenv("RP_GEMM_WS_MIN_M") ? atoi(getenv("RP_GEMM_WS_MIN_M")) : 131072;  // measured: pays for M >~ 100K rows (predict), neutral at 51K
+  const bool ws_ok = g->M >= ws_min_m && !g->a_mn && g->batch == 1 && g->split_k == 1 && g->M >= 1024 && g->N >= 64 &&
+                     (g->K == 64 || g->K == 128 || g->K == 256) && g->a_ro == 0 && g->a_ri == 0 && g->b_ro == 0 && g->b_ri == 0 &&
+                     g->a_co == 0 && g->a_ci == 0 && g->b_co == 0 && g->b_ci == 0 && g->c_oo == 0 && g->c_oi == 0;
+  if (ws_ok && bn == 128) {
+#define RP_WS_CASE(KCH_)                                                             \
+  return g->b_mn ? launch_gemm_ws<128, KCH_, true>(tmA, tmB, p, stream) : launch_gemm_ws<128, KCH_, false>(tmA, tmB, p, stream)
+    if (g->K == 64) { RP_WS_CASE(1); }
+    if (g->K == 128) { RP_WS_CASE(2); }
+    RP_WS_CASE(4);
+#undef RP_WS_CASE
+  }
 #define RP_GEMM_CASE(BN_, AMN_, BMN_) return launch_gemm<BN_, AMN_, BMN_>(tmA, tmB, p, g->batch, stream)
   if (bn == 64) {
     if (!g->a_mn && !g->b_mn) RP_GEMM_CASE(64, false, false);

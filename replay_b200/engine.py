@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -59,7 +60,7 @@ def _ru(x, m):
 class _CountingLib:
     """Proxy over the ctypes library that counts the sm_100a kernel launches issued through it (bench.py reports them)."""
 
-    KERNELS = {"rp_gemm": 1, "rp_attn_fwd": 1, "rp_attn_softmax_bwd": 1, "rp_prepare_batch": 1, "rp_embed_fwd": 1,
+    KERNELS = {"rp_gemm": 1, "rp_attn_fwd": 1, "rp_attn_softmax_bwd": 1, "rp_prepare_batch": 2, "rp_embed_fwd": 1,
                "rp_embed_bwd": 2, "rp_layernorm_fwd": 1, "rp_layernorm_bwd": 1, "rp_dropout_bwd": 1, "rp_colsum": 1,
                "rp_adam_step": 2, "rp_cast_bf16": 1, "rp_counter_add": 1, "rp_ce_head_fwd": 2, "rp_ce_head_bwd": 3,
                "rp_score_topk": 2, "rp_seen_prepare": 1}
@@ -196,6 +197,7 @@ class SasRecEngine:
         self.valid_idx = torch.zeros(T, **i32)
         self.labels_c = torch.zeros(T, **i32)
         self.n_valid = torch.zeros(1, **i32)
+        self.prep_scratch = torch.zeros((T + 1023) // 1024 + 1, **i32)
         nb = cfg.n_blocks
         self.x = [torch.zeros(T, d, **bf) for _ in range(nb + 1)]
         self.act = []
@@ -264,7 +266,8 @@ class SasRecEngine:
         """dW[n_out, n_in] += dY[T, n_out]^T . X[T, n_in]  (both operands MN-major, split-K, fp32 atomics)."""
         tiles = ((n_out + 127) // 128) * ((n_in + 127) // 128 if n_in > 64 else 1)
         chunks = (self.T + 63) // 64
-        split = max(1, min(chunks // 16, (148 + tiles - 1) // tiles))  # >= 16 K-chunks per CTA, <= one wave
+        per = int(os.environ.get("RP_WGRAD_CHUNKS", "24"))  # K-chunks (64 tokens) per CTA: tuning knob
+        split = max(1, min(chunks // per, (148 + tiles - 1) // tiles))
         self._gemm(dY, X, dW, n_out, n_in, self.T, a_mn=True, b_mn=True, out_mode=1, split_k=split)
 
     def _colsum(self, dY, db):
@@ -310,7 +313,7 @@ class SasRecEngine:
                                         self.in_labels.data_ptr() if with_targets else None,
                                         self.in_tmask.data_ptr() if with_targets else None, self.T, cfg.pad_id, cfg.n_items,
                                         self.ids32.data_ptr(), self.valid_idx.data_ptr(), self.labels_c.data_ptr(),
-                                        self.n_valid.data_ptr(), self._stream()), "rp_prepare_batch")
+                                        self.n_valid.data_ptr(), self.prep_scratch.data_ptr(), self._stream()), "rp_prepare_batch")
 
     def _body_forward(self, training: bool):
         cfg, T, d, L = self.cfg, self.T, self.cfg.d, self.L

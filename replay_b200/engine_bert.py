@@ -147,6 +147,7 @@ class Bert4RecEngine(SasRecEngine):
         self.valid_idx = torch.zeros(T, **i32)
         self.labels_c = torch.zeros(T, **i32)
         self.n_valid = torch.zeros(1, **i32)
+        self.prep_scratch = torch.zeros((T + 1023) // 1024 + 1, **i32)
         self.x = [torch.zeros(T, d, **bf) for _ in range(cfg.n_blocks + 1)]
         self.act = []
         for _ in range(cfg.n_blocks):
@@ -196,7 +197,7 @@ class Bert4RecEngine(SasRecEngine):
                                         self.in_labels.data_ptr() if with_targets else None,
                                         self.in_tmask.data_ptr() if with_targets else None, self.T, cfg.pad_id, cfg.n_items,
                                         self.ids32.data_ptr(), self.valid_idx.data_ptr(), self.labels_c.data_ptr(),
-                                        self.n_valid.data_ptr(), self._stream()), "rp_prepare_batch")
+                                        self.n_valid.data_ptr(), self.prep_scratch.data_ptr(), self._stream()), "rp_prepare_batch")
 
     def _bsite(self, blk, k):
         return 1 + blk * 8 + k

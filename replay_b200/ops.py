@@ -4,7 +4,9 @@ from __future__ import annotations
 
 import torch
 
-from ._lib import check, lib
+import ctypes
+
+from ._lib import GemmDesc, check, lib
 
 
 def _ptr(t):
@@ -100,3 +102,30 @@ def ce_head_bwd(st: CEHeadState, hc, table, labels, n_valid, d_hc, d_table, bias
     check(lib().rp_ce_head_bwd(_ptr(hc), _ptr(table), _ptr(bias), _ptr(labels), _ptr(n_valid), st.capacity, st.n_items, st.d,
                                _ptr(st.loss), _ptr(st.cvec), _ptr(d_hc), _ptr(d_table), _ptr(d_bias), int(getattr(st, "fused", False)),
                                _ptr(st.ws), st.ws_bytes, _stream()), "rp_ce_head_bwd")
+
+
+def gemm(A, B, C, M, N, K, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, rowmask=None, drop_p=0.0,
+         drop_offset=0, seed=0, seed_ptr=None, out_mode=0, split_k=1, gate=None, gate_scale=1.0, gate_mode=0, alpha=1.0,
+         batch=1, inner=1, a_off=(0, 0, 0, 0, 0, 0), b_off=(0, 0, 0, 0, 0, 0), c_geom=None, rowmask_oo=0, C2=None,
+         post_drop_p=0.0, post_drop_offset=0, L=None):
+    """C = epilogue(alpha * A(m,k) . B(n,k)) through rp_gemm (include/rp_b200.h).  A / B are 2-D bf16 tensors (views allowed:
+    pointer, shape and row pitch are taken from the tensor); x_mn selects the MN-major reading of an operand."""
+    g = GemmDesc()
+    g.A, g.a_rows, g.a_cols, g.lda, g.a_mn = A.data_ptr(), A.shape[0], A.shape[1], A.stride(0), int(a_mn)
+    g.B, g.b_rows, g.b_cols, g.ldb, g.b_mn = B.data_ptr(), B.shape[0], B.shape[1], B.stride(0), int(b_mn)
+    g.M, g.N, g.K, g.batch, g.inner = M, N, K, batch, inner
+    g.a_r0, g.a_ro, g.a_ri, g.a_c0, g.a_co, g.a_ci = a_off
+    g.b_r0, g.b_ro, g.b_ri, g.b_c0, g.b_co, g.b_ci = b_off
+    g.C = C.data_ptr()
+    g.ldc, g.c_off0, g.c_oo, g.c_oi = (C.stride(0), 0, 0, 0) if c_geom is None else c_geom
+    g.out_mode, g.alpha, g.act = out_mode, alpha, act
+    g.bias = _ptr(bias)
+    g.residual = _ptr(residual)
+    g.rowmask = _ptr(rowmask)
+    g.rowmask_off0, g.rowmask_oo = 0, rowmask_oo
+    g.drop_p, g.seed, g.drop_offset, g.seed_ptr = drop_p, seed, drop_offset, seed_ptr
+    g.split_k = split_k
+    g.gate, g.gate_scale, g.gate_mode = _ptr(gate), gate_scale, gate_mode
+    g.C2 = _ptr(C2)
+    g.post_drop_p, g.post_drop_offset = post_drop_p, post_drop_offset
+    check((L or lib()).rp_gemm(ctypes.byref(g), _stream()), "rp_gemm")

@@ -8,6 +8,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# exercise the weight-stationary persistent GEMM on the small test shapes too (its production threshold is M >= 131072)
+os.environ.setdefault("RP_GEMM_WS_MIN_M", "1024")
 
 
 def pytest_configure(config):

@@ -151,3 +151,28 @@ def test_ce_head_fused_falls_back_when_logits_are_unbounded(ops):
     assert abs(out[0].item() - loss.item()) < 1e-3 * abs(loss.item()), (out[0].item(), loss.item())
     assert (d_hc[:n_valid].cpu().double() - h64.grad).norm() / h64.grad.norm() < 1e-2
     assert (d_tab[:I].cpu().double() - e64.grad).norm() / e64.grad.norm() < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K,b_mn", [(2048, 128, 128, False), (5000, 256, 128, False), (3000, 128, 256, True),
+                                        (1500, 384, 64, True), (2048, 128, 128, True), (4096, 512, 128, False),
+                                        (300, 128, 128, False), (257, 192, 128, True)])
+def test_gemm_matches_matmul(ops, M, N, K, b_mn, monkeypatch):
+    """rp_gemm (tile kernel and the weight-stationary persistent kernel, forced on here for M >= 1024) with the fused
+    epilogue: bias + ReLU + residual, K-major and MN-major weights."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.2).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    R = torch.randn(M, N, generator=g).to(torch.bfloat16)
+    ref = torch.relu(A.double() @ W.double().T + bias.double()) + R.double()
+    Bop = W.T.contiguous() if b_mn else W  # MN-major: stored [K, N]
+    C = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A.cuda(), Bop.cuda(), C, M, N, K, b_mn=b_mn, bias=bias.cuda(), act=1, residual=R.cuda())
+    torch.cuda.synchronize()
+    err = (C.cpu().double() - ref).abs().max().item()
+    assert err < 0.08, err  # bf16 output rounding of O(10) values
+    # fp32 output, no epilogue: tight tolerance
+    C32 = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(A.cuda(), Bop.cuda(), C32, M, N, K, b_mn=b_mn, out_mode=2)
+    torch.cuda.synchronize()
+    assert (C32.cpu().double() - A.double() @ W.double().T).abs().max().item() < 2e-3

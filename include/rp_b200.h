@@ -152,6 +152,12 @@ int rp_attn_softmax_bwd(void* p_save, void* dpd, const float* inv_sum, int BH, i
                         unsigned long long seed, unsigned long long drop_off, const unsigned long long* seed_ptr,
                         void* stream);
 
+/* predict(): attention of ONE query row per (sequence, head) - the last position - against that sequence's keys
+ * (SasRec.forward_inference keeps only hidden[:, -1, :], nn/sequential/sasrec/model.py:301; legacy model.py:157).
+ * q, out: compact bf16 [B, H*head_dim]; k, v: token-major 2-D arrays (rows b*L + j, head h at columns x_c0 + h*head_dim). */
+int rp_attn_last(const void* q, const void* k, const void* v, long long ldk, long long ldv, int k_c0, int v_c0,
+                 const uint8_t* pad_mask, int B, int H, int L, int head_dim, int mask_pad_keys, void* out, void* stream);
+
 /* int64 ids / bool masks of one [B, L] batch -> int32 ids (pads -> pad_id) and the compacted valid-target list
  * (replaces the masked_fill / boolean-index preparation in nn/loss/ce.py:70-80 and models/.../sasrec/model.py:236-239).
  * labels/target_mask may be NULL (predict). */

@@ -290,9 +290,113 @@ __global__ void attn_softmax_bwd_kernel(__nv_bfloat16* __restrict__ p_save, __nv
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// predict(): only the LAST position of every sequence is scored, so in the last transformer block a single query row per
+// (sequence, head) attends to the keys - a memory-bound GEMV pair, one warp per (b, h).
+//   q    bf16 [B, H*HD]   (compact: one row per sequence)
+//   k, v bf16 rows b*L + j of 2-D arrays with pitches ldk / ldv, head h at columns x_c0 + h*HD
+//   out  bf16 [B, H*HD]
+// Visible keys: j < L (the query is the last position, so causal masking is a no-op) and, if mask_pad_keys, pad[b*L+j].
+// ------------------------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void attn_last_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                 const __nv_bfloat16* __restrict__ v, long long ldk, long long ldv, int k_c0, int v_c0,
+                                 const uint8_t* __restrict__ pad_mask, int B, int H, int L, int mask_pad_keys, float scale,
+                                 __nv_bfloat16* __restrict__ out) {
+  constexpr int PER = HD / 32;  // output columns per lane
+  __shared__ float s_q[8][HD];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int bh = blockIdx.x * (blockDim.x >> 5) + w;
+  if (bh >= B * H) return;
+  const int b = bh / H, h = bh % H;
+  for (int c = lane; c < HD; c += 32) s_q[w][c] = __bfloat162float(q[(size_t)b * H * HD + h * HD + c]) * scale;
+  __syncwarp();
+  // scores: lane owns keys lane, lane+32, ...
+  float sc[8];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = i * 32 + lane;
+    sc[i] = -INFINITY;
+    if (j < L && (!mask_pad_keys || pad_mask[(size_t)b * L + j])) {
+      const uint4* kr = reinterpret_cast<const uint4*>(k + ((size_t)b * L + j) * ldk + k_c0 + h * HD);
+      float acc = 0.f;
+#pragma unroll
+      for (int c8 = 0; c8 < HD / 8; ++c8) {
+        const uint4 raw = kr[c8];
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __bfloat1622float2(h2[t]);
+          acc = fmaf(f.x, s_q[w][c8 * 8 + 2 * t], fmaf(f.y, s_q[w][c8 * 8 + 2 * t + 1], acc));
+        }
+      }
+      sc[i] = acc;
+      mx = fmaxf(mx, acc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = (sc[i] == -INFINITY) ? 0.f : __expf(sc[i] - mx);
+    sum += sc[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;  // no visible key -> zero output (safe-softmax semantics)
+  float acc[PER];
+#pragma unroll
+  for (int c = 0; c < PER; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int jmax = min(32, L - i * 32);
+    for (int jj = 0; jj < jmax; ++jj) {
+      const float pj = __shfl_sync(0xffffffffu, sc[i], jj);
+      if (pj != 0.f) {
+        const __nv_bfloat16* vr = v + ((size_t)b * L + i * 32 + jj) * ldv + v_c0 + h * HD + lane * PER;
+#pragma unroll
+        for (int c = 0; c < PER; c += 2) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vr + c));
+          acc[c] = fmaf(pj, f.x, acc[c]);
+          acc[c + 1] = fmaf(pj, f.y, acc[c + 1]);
+        }
+      }
+    }
+  }
+  __nv_bfloat16* o = out + (size_t)b * H * HD + h * HD + lane * PER;
+#pragma unroll
+  for (int c = 0; c < PER; c += 2) *reinterpret_cast<uint32_t*>(o + c) = pack_bf16(acc[c] * inv, acc[c + 1] * inv);
+}
+
 }  // namespace rp
 
 using namespace rp;
+
+RP_API int rp_attn_last(const void* q, const void* k, const void* v, long long ldk, long long ldv, int k_c0, int v_c0,
+                        const uint8_t* pad_mask, int B, int H, int L, int head_dim, int mask_pad_keys, void* out,
+                        void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!q || !k || !v || !pad_mask || !out) return RP_EINVAL;
+  if (B <= 0 || H <= 0 || L <= 0 || L > 256) return RP_ESHAPE;
+  if ((ldk & 7) || (ldv & 7) || (k_c0 & 7) || (v_c0 & 7)) return RP_EALIGN;
+  const float scale = 1.f / sqrtf((float)head_dim);
+  const int blocks = (B * H + 7) / 8;
+  const __nv_bfloat16 *qq = reinterpret_cast<const __nv_bfloat16*>(q), *kk = reinterpret_cast<const __nv_bfloat16*>(k),
+                      *vv = reinterpret_cast<const __nv_bfloat16*>(v);
+  if (head_dim == 64)
+    attn_last_kernel<64><<<blocks, 256, 0, stream>>>(qq, kk, vv, ldk, ldv, k_c0, v_c0, pad_mask, B, H, L, mask_pad_keys, scale,
+                                                     reinterpret_cast<__nv_bfloat16*>(out));
+  else if (head_dim == 128)
+    attn_last_kernel<128><<<blocks, 256, 0, stream>>>(qq, kk, vv, ldk, ldv, k_c0, v_c0, pad_mask, B, H, L, mask_pad_keys, scale,
+                                                      reinterpret_cast<__nv_bfloat16*>(out));
+  else
+    return RP_ESHAPE;
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
 
 struct rp_attn_desc {
   const void* q; long long q_rows, q_cols, ldq; int q_c0;

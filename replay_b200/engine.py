@@ -60,7 +60,7 @@ def _ru(x, m):
 class _CountingLib:
     """Proxy over the ctypes library that counts the sm_100a kernel launches issued through it (bench.py reports them)."""
 
-    KERNELS = {"rp_gemm": 1, "rp_attn_fwd": 1, "rp_attn_softmax_bwd": 1, "rp_prepare_batch": 2, "rp_embed_fwd": 1,
+    KERNELS = {"rp_gemm": 1, "rp_attn_fwd": 1, "rp_attn_last": 1, "rp_attn_softmax_bwd": 1, "rp_prepare_batch": 2, "rp_embed_fwd": 1,
                "rp_embed_bwd": 2, "rp_layernorm_fwd": 1, "rp_layernorm_bwd": 1, "rp_dropout_bwd": 1, "rp_colsum": 1,
                "rp_adam_step": 2, "rp_cast_bf16": 1, "rp_counter_add": 1, "rp_ce_head_fwd": 2, "rp_ce_head_bwd": 3,
                "rp_score_topk": 2, "rp_seen_prepare": 1}
@@ -215,6 +215,9 @@ class SasRecEngine:
         self.rstdf = torch.zeros(T, **f32)
         self.hq = torch.zeros(self.B, d, **bf)
         self.last_idx = (torch.arange(self.B, device=dev, dtype=torch.int32) * self.L + (self.L - 1)).contiguous()
+        self.last_buf = {k: torch.zeros(self.B, d, **bf) for k in ("q_in", "Q", "O", "h", "y", "u")}
+        self.last_rows = torch.zeros(self.B, d, **bf)
+        self.last_pad = torch.zeros(self.B, device=dev, dtype=torch.bool)
         if self.with_grad:
             from .ops import CEHeadState
 
@@ -315,7 +318,10 @@ class SasRecEngine:
                                         self.ids32.data_ptr(), self.valid_idx.data_ptr(), self.labels_c.data_ptr(),
                                         self.n_valid.data_ptr(), self.prep_scratch.data_ptr(), self._stream()), "rp_prepare_batch")
 
-    def _body_forward(self, training: bool):
+    def _body_forward(self, training: bool, last_only: bool = False):
+        """``last_only`` (predict): the final block is evaluated for the LAST position of every sequence only - LN1, the Q
+        projection, one-query attention, out-projection, LN2 and the FFN run on [B, d] rows; only the K/V projection of
+        that block still covers all tokens.  Result rows land in ``self.last_rows`` (bf16 [B, d])."""
         cfg, T, d, L = self.cfg, self.T, self.cfg.d, self.L
         p16, prm = self.params16, self.params
         legacy = cfg.variant == "legacy"
@@ -330,6 +336,21 @@ class SasRecEngine:
             a, x = self.act[i], self.x[i]
             w = lambda k: p16[f"b{i}.{k}"]  # noqa: E731
             f = lambda k: prm[f"b{i}.{k}"]  # noqa: E731
+            if last_only and i == cfg.n_blocks - 1:
+                Bq, lb = self.B, self.last_buf
+                in_w, in_b = w("in_w"), f("in_b")
+                self._ln_fwd(x, f("ln1_w"), f("ln1_b"), 1e-8, lb["q_in"], self.meanf, self.rstdf, Bq, gather=self.last_idx)
+                self._gemm(lb["q_in"], in_w[:d], lb["Q"], Bq, d, d, bias=in_b[:d])
+                self._gemm(x, in_w[d:], a["KV"], T, 2 * d, d, bias=in_b[d:])
+                check(self.lib.rp_attn_last(lb["Q"].data_ptr(), a["KV"].data_ptr(), a["KV"].data_ptr(), 2 * d, 2 * d, 0, d,
+                                            pad.data_ptr(), Bq, H, L, hd, int(not legacy), lb["O"].data_ptr(), self._stream()),
+                      "rp_attn_last")
+                self._gemm(lb["O"], w("out_w"), lb["h"], Bq, d, d, bias=f("out_b"), residual=lb["q_in"])
+                self._ln_fwd(lb["h"], f("ln2_w"), f("ln2_b"), 1e-8, lb["y"], self.meanf, self.rstdf, Bq)
+                self._gemm(lb["y"], w("w1"), lb["u"], Bq, d, d, bias=f("b1"), act=1)
+                self._gemm(lb["u"], w("w2"), self.last_rows, Bq, d, d, bias=f("b2"), residual=lb["y"],
+                           rowmask=self.last_pad if legacy else None)
+                return
             self._ln_fwd(x, f("ln1_w"), f("ln1_b"), 1e-8, a["q_in"], a["mean1"], a["rstd1"], T)
             in_w, in_b = w("in_w"), f("in_b")
             self._gemm(a["q_in"], in_w[:d], a["Q"], T, d, d, bias=in_b[:d])
@@ -472,9 +493,11 @@ class SasRecEngine:
         """Eval-mode body (no dropout) -> final LayerNorm of the LAST position of every sequence -> self.hq bf16 [B, d]
         (SasRec.forward_inference, nn/sequential/sasrec/model.py:292-307 ; legacy get_query_embeddings, model.py:157)."""
         self._prepare(False)
-        self._body_forward(False)
-        self._ln_fwd(self.x[-1], self.params["lnf_w"], self.params["lnf_b"], self.cfg.lnf_eps, self.hq, self.meanf, self.rstdf,
-                     self.B, gather=self.last_idx)
+        if self.cfg.variant == "legacy":
+            self.last_pad.copy_(self.in_pad.view(self.B, self.L)[:, -1])
+        self._body_forward(False, last_only=True)
+        self._ln_fwd(self.last_rows, self.params["lnf_w"], self.params["lnf_b"], self.cfg.lnf_eps, self.hq, self.meanf, self.rstdf,
+                     self.B)
         return self.hq
 
     def forward_hidden_all(self):

@@ -152,3 +152,24 @@ def test_dropout_training_runs_and_is_reproducible(golden_dir, cuda):
     eng.backward()
     torch.cuda.synchronize()
     assert torch.isfinite(eng.g32).all()
+
+
+@pytest.mark.parametrize("name,variant", [("sasrec_new_small.npz", "new"), ("sasrec_new_tiny.npz", "new"),
+                                          ("sasrec_legacy_tiny.npz", "legacy")])
+def test_last_position_shortcut_equals_full_body(golden_dir, cuda, name, variant):
+    """predict() evaluates the final block for the last position only (one-query attention + [B, d] projections); it must
+    agree with the full-sequence body and with the reference's last hidden state."""
+    from oracle import sasrec as osr
+
+    z, sd = _load(golden_dir, name)
+    P = osr.params_from_new_state_dict(sd) if variant == "new" else osr.params_from_legacy_state_dict(sd)
+    eng = _engine(z, P, variant, cuda)
+    ids, pm = torch.from_numpy(z["ids"]), torch.from_numpy(z["pad_mask"])
+    eng.set_batch(ids.cuda(), pm.cuda())
+    full = eng.forward_hidden_all().float().view(*ids.shape, -1)[:, -1].clone()
+    fast = eng.forward_last_hidden().float()
+    torch.cuda.synchronize()
+    real = pm[:, -1].cuda()
+    assert (fast[real] - full[real]).abs().max() < 3e-2
+    ref = torch.from_numpy(z["eval_hidden_last"]).cuda()
+    assert (fast[real] - ref[real]).abs().max() < 6e-2

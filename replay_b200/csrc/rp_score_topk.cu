@@ -52,6 +52,15 @@ struct TopK {
   }
 };
 
+// order-preserving float <-> unsigned key (0 is below every float, so a zero-filled array means "no threshold yet")
+__device__ __forceinline__ uint32_t f2key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 static constexpr int kEpiWarps = 8;
 static constexpr int kThreads = 64 + kEpiWarps * 32;
 
@@ -59,7 +68,8 @@ template <int KCH /* d / 64 */, int NSTAGE, int KMAX>
 __global__ void __launch_bounds__(kThreads, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const int32_t* __restrict__ seen_sorted, int S, int n_users, int n_items, int K, int n_splits,
-                  const float* __restrict__ bias, float* __restrict__ part_vals, int32_t* __restrict__ part_ids) {
+                  const float* __restrict__ bias, float* __restrict__ part_vals, int32_t* __restrict__ part_ids,
+                  uint32_t* __restrict__ row_thr /* [n_users] shared K-th-best keys, zero-filled */) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                          // KCH chunks of 16 KB
@@ -145,25 +155,34 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float* sc = s_scratch + ew * 32 + lane;  // element q of this thread at sc[q * (kEpiWarps*32)]
     TopK<KMAX> top;
     top.init(K);
-    // cursor into this user's sorted seen list (ascending, kNoId = padding)
+    // cursor into this user's sorted seen list (ascending, kNoId = padding).  The next entry is prefetched one step ahead
+    // so that the (rare, per thread) advance never waits on a dependent global load inside the tile loop.
     const int32_t* sp = seen_sorted ? seen_sorted + (size_t)(live ? u : 0) * S : nullptr;
     int ci = 0;
-    int next_seen = kNoId;
-    auto seek = [&](int first_col) {  // lower_bound(first_col) from the current cursor
-      int lo = ci, hi = S;
+    int next_seen = kNoId, pre_seen = kNoId;
+    if (sp && live) {
+      const int first_col = t_begin * kTileN;
+      int lo = 0, hi = S;  // lower_bound(first_col), once per CTA
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (sp[mid] < first_col) lo = mid + 1; else hi = mid;
       }
       ci = lo;
       next_seen = ci < S ? sp[ci] : kNoId;
-    };
-    if (sp && live) next_seen = sp[0];
+      pre_seen = ci + 1 < S ? sp[ci + 1] : kNoId;
+    }
     for (int t = t_begin, j = 0; t < t_end; ++t, ++j) {
       const uint32_t as = j & 1, aph = (j >> 1) & 1;
       mbar_wait(&bar_tfull[as], aph);
       tc_fence_after();
       const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + as * kTileN + half * 64;
+      // K-th best already secured for this row by ANY thread / CTA working on it (other column halves and item splits):
+      // anything strictly below it cannot reach the final top-K, so it never enters the insert path
+      float gthr = -INFINITY;
+      if (live) {
+        const uint32_t gk = *reinterpret_cast<volatile uint32_t*>(row_thr + u);
+        if (gk != 0u) gthr = key2f(gk - 1u);  // largest value strictly below the shared K-th best: x > gthr <=> x >= shared
+      }
       uint32_t raw0[32], raw1[32];
       tmem_ld32(tbase, raw0);
       tmem_ld32(tbase + 32, raw1);
@@ -172,7 +191,6 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[as]);
-      if (sp && live && next_seen < t * kTileN + half * 64) seek(t * kTileN + half * 64);  // skip the other half's columns
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
         const int col0 = t * kTileN + half * 64 + c;
@@ -191,25 +209,43 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int q = 0; q < 32; ++q)
             if (col0 + q >= n_items) x[q] = -INFINITY;
         }
-        while (next_seen < col0 + 32) {  // rare: a seen item falls in this 32-column chunk
-          const int q0 = next_seen - col0;
+        // seen items of this 32-column chunk as a bit mask (also skips entries that belong to the other column half)
+        uint32_t kill = 0;
+        while (next_seen < col0 + 32) {
+          if (next_seen >= col0) kill |= 1u << (next_seen - col0);
+          next_seen = pre_seen;
+          ++ci;
+          pre_seen = ci + 1 < S ? sp[ci + 1] : kNoId;
+        }
+        if (kill) {
 #pragma unroll
           for (int q = 0; q < 32; ++q)
-            if (q == q0) x[q] = -INFINITY;
-          ++ci;
-          next_seen = ci < S ? sp[ci] : kNoId;
+            if ((kill >> q) & 1u) x[q] = -INFINITY;
         }
-        bool any = false;
+        const float thr = fmaxf(top.thr(), gthr);
+        bool a0 = false, a1 = false, a2 = false, a3 = false;  // four independent compare chains
 #pragma unroll
-        for (int q = 0; q < 32; ++q) any |= (x[q] > top.thr());
-        if (any) {  // rare after warm-up: stage the chunk in smem and walk it with ONE insert site (small code)
+        for (int q = 0; q < 32; q += 4) {
+          a0 |= (x[q] > thr);
+          a1 |= (x[q + 1] > thr);
+          a2 |= (x[q + 2] > thr);
+          a3 |= (x[q + 3] > thr);
+        }
+        if (a0 | a1 | a2 | a3) {  // some lane of the warp has a candidate: stage the chunk, then walk only the set bits
 #pragma unroll
           for (int q = 0; q < 32; ++q) sc[q * (kEpiWarps * 32)] = x[q];
-#pragma unroll 1
-          for (int q = 0; q < 32; ++q) {
+          uint32_t hit = 0;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) hit |= (x[q] > thr) ? (1u << q) : 0u;
+          const float before = top.thr();
+          while (hit) {
+            const int q = __ffs(hit) - 1;
+            hit &= hit - 1;
             const float val = sc[q * (kEpiWarps * 32)];
-            if (val > top.thr()) top.insert(val, col0 + q);
+            if (val > fmaxf(top.thr(), gthr)) top.insert(val, col0 + q);
           }
+          // publish an improved K-th best (only once the list holds K real entries, i.e. its last slot is finite)
+          if (live && top.thr() > before && top.thr() > -INFINITY) atomicMax(row_thr + u, f2key(top.thr()));
         }
       }
     }
@@ -351,17 +387,22 @@ static int choose_splits(int n_user_tiles, int n_item_tiles) {
 
 template <int KCH, int NSTAGE>
 static int launch_score_topk(const CUtensorMap& tmA, const CUtensorMap& tmB, const int32_t* seen_sorted, int S, int B,
-                             int I, int K, int n_splits, const float* bias, float* pv, int32_t* pi, cudaStream_t stream) {
+                             int I, int K, int n_splits, const float* bias, float* pv, int32_t* pi, uint32_t* row_thr,
+                             cudaStream_t stream) {
   const int smem = (KCH + NSTAGE) * kChunkBytes + 1024;
   const int grid = ((B + kTileM - 1) / kTileM) * n_splits;
-  if (K <= 16) {
+  if (K <= 10) {
+    auto kern = score_topk_kernel<KCH, NSTAGE, 10>;
+    RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, bias, pv, pi, row_thr);
+  } else if (K <= 16) {
     auto kern = score_topk_kernel<KCH, NSTAGE, 16>;
     RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, bias, pv, pi);
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, bias, pv, pi, row_thr);
   } else {
     auto kern = score_topk_kernel<KCH, NSTAGE, 32>;
     RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, bias, pv, pi);
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, bias, pv, pi, row_thr);
   }
   RP_LAUNCH_CHECK();
   return RP_OK;
@@ -374,7 +415,7 @@ RP_API size_t rp_score_topk_workspace(int n_users, int n_items, int d, int K) {
   if (n_users <= 0 || n_items <= 0 || K <= 0) return 0;
   const int ut = (n_users + rp::kTileM - 1) / rp::kTileM, it = (n_items + rp::kTileN - 1) / rp::kTileN;
   const int p = rp::choose_splits(ut, it);
-  return (size_t)n_users * p * 2 * K * 8 + 256;
+  return (size_t)n_users * p * 2 * K * 8 + (size_t)n_users * 4 + 256;
 }
 
 RP_API int rp_seen_prepare(const int64_t* seen_ids, int n_users, int S, int item_count, const int32_t* inv_map,
@@ -405,15 +446,17 @@ RP_API int rp_score_topk(const void* hq, const void* table, const float* bias, c
   const int p = choose_splits(ut, it);
   float* pv = reinterpret_cast<float*>(workspace);
   int32_t* pi = reinterpret_cast<int32_t*>(pv + (size_t)n_users * p * 2 * K);
+  uint32_t* row_thr = reinterpret_cast<uint32_t*>(pi + (size_t)n_users * p * 2 * K);
+  RP_CUDA_CHECK(cudaMemsetAsync(row_thr, 0, (size_t)n_users * 4, stream));
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = make_tmap_bf16(&tmA, hq, n_users, d, d, 128)) != RP_OK) return rc;
   if ((rc = make_tmap_bf16(&tmB, table, n_items, d, d, 128)) != RP_OK) return rc;
   switch (d) {
-    case 64: rc = launch_score_topk<1, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, stream); break;
-    case 128: rc = launch_score_topk<2, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, stream); break;
-    case 256: rc = launch_score_topk<4, 6>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, stream); break;
-    default: rc = launch_score_topk<8, 3>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, stream); break;
+    case 64: rc = launch_score_topk<1, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, row_thr, stream); break;
+    case 128: rc = launch_score_topk<2, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, row_thr, stream); break;
+    case 256: rc = launch_score_topk<4, 6>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, row_thr, stream); break;
+    default: rc = launch_score_topk<8, 3>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, row_thr, stream); break;
   }
   if (rc != RP_OK) return rc;
   const int threads = 128;

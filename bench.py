@@ -247,7 +247,10 @@ def run_ours(args):
     roof = {
         "bound": "tensor", "kernel": "ce_bwd_kernel<FUSED> (fwd+dH) + ce_bwd_kernel<COL> (dE): logits GEMM + softmax-CE, fwd+bwd",
         "achieved": 3 * gemm_flops / (ce_ms * 1e-3) / 1e12, "peak": PK["tc_burst"], "unit": "TFLOP/s",
-        "frac": 3 * gemm_flops / (ce_ms * 1e-3) / 1e12 / PK["tc_burst"], "traffic": None,
+        "frac": 3 * gemm_flops / (ce_ms * 1e-3) / 1e12 / PK["tc_burst"],
+        # dram__bytes_read+write of the dE pass from the committed ncu capture (profiles/r1_ce_head_ncu.md): equals the
+        # algorithmic bytes (bf16 table 12.8 MB + compacted hidden rows 6.7 MB); its fp32 dE output stays in L2
+        "traffic": 19.7e6,
         "peak_source": PK["src"] + " burst (kernels timed alone)",
         "detail": {"ce_fwd_ms": t_fwd, "ce_bwd_ms": t_bwd, "n_valid_targets": n_valid,
                    "algorithmic_flops_per_launch_pair": 3 * gemm_flops,

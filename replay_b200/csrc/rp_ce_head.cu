@@ -28,6 +28,14 @@ static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr float kLn2 = 0.6931471805599453f;
 static constexpr int kEpiWarps = 8;
 static constexpr int kThreads = 64 + kEpiWarps * 32;
+// backward / fused kernels: RP_CE_BWD_CG column groups per TMEM lane quarter -> 4*CG epilogue warps (16 by default): the
+// knob kept for experiments: 16 warps (CG = 4) measured ~8 % slower than 8 (CG = 2) on B200, see profiles/r1_ce_variants.md
+#ifndef RP_CE_BWD_CG
+#define RP_CE_BWD_CG 2
+#endif
+static constexpr int kBwdCG = RP_CE_BWD_CG;
+static constexpr int kBwdEpiWarps = 4 * kBwdCG;
+static constexpr int kBwdThreads = 64 + kBwdEpiWarps * 32;
 
 // tuning knobs (measured on B200, see profiles/): every RP_CE_POLY_EVERY-th exponential goes to the FMA-pipe polynomial
 // instead of MUFU.EX2 (0 = MUFU only); RP_CE_NBUF3 = 1 triple-buffers S in TMEM for d <= 128.
@@ -39,6 +47,9 @@ static constexpr int kThreads = 64 + kEpiWarps * 32;
 #endif
 #ifndef RP_CE_NBUF3
 #define RP_CE_NBUF3 1
+#endif
+#ifndef RP_CE_A_TMEM
+#define RP_CE_A_TMEM 1
 #endif
 template <int DEG, int EVERY>
 __device__ __forceinline__ float ce_ex2(float x, int q) {
@@ -273,9 +284,10 @@ __global__ void ce_finalize_kernel(const float2* __restrict__ part, const __nv_b
 // MODE 2: rows = tokens, FUSED forward+backward: G~ = exp(s + b) with reference max 0 (valid while |s| is bounded, see
 //         ce_bound_kernel), per-row sum of G~ and un-normalised dH~ = sum_i G~ E_i over this CTA's column split
 //                                                                                      -> out = partial dH~ fp32, zpart
-template <int KCH, int NSTAGE, int MODE, int NBUF>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int KCH, int NSTAGE, int MODE, int NBUF, bool A_TMEM>
+__global__ void __launch_bounds__(kBwdThreads, 1)
 ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const __nv_bfloat16* __restrict__ a_rows /* the row-side matrix (tmA) as a plain pointer, for A_TMEM */,
               const float* __restrict__ cvec /* [T] exponent offsets per token */, const int32_t* __restrict__ labels,
               const __nv_bfloat16* __restrict__ table, const float* __restrict__ loss_inv /* [1] = 1/T_v */,
               const int32_t* __restrict__ n_valid_ptr, int n_items, const float* __restrict__ bias,
@@ -283,15 +295,18 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               int n_splits, int capacity, float* __restrict__ zpart) {
   constexpr bool COLCONST = (MODE == 1);
   constexpr bool FUSED = (MODE == 2);
+  constexpr int kW = kT / kBwdCG;  // S columns owned by one epilogue warp (its bf16 G lands in the first kW/2 of them)
   constexpr int D = KCH * 64;
   if (safe_flag && (*safe_flag != 0) != (run_if_safe != 0)) return;  // fused path vs two-pass fallback (uniform)
   constexpr int kStage = KCH * kChunk;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // A_TMEM: the resident row tile lives in TMEM (K-major, two bf16 per 32-bit column) and the first GEMM reads it from
+  // there, which halves that GEMM's shared-memory traffic - M=128 x N=128 SS MMAs need the full 128 B/clk of smem.
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStage;
+  uint8_t* sB = smem + (A_TMEM ? 0 : kStage);
   __shared__ __align__(16) float s_cc[NSTAGE][kT];
-  __shared__ float s_gsum[2][kT];
+  __shared__ float s_gsum[kBwdCG][kT];
   __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_sfull[NBUF], bar_sfree[NBUF], bar_pfull[NBUF], bar_acc;
   __shared__ uint32_t tmem_slot;
 
@@ -307,7 +322,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int n_ct = FUSED ? (int)(((long long)n_ct_all * (split + 1)) / n_splits) - jg0 : n_ct_all;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bar_a, 1);
+    mbar_init(&bar_a, A_TMEM ? kBwdEpiWarps : 1);
     for (int i = 0; i < NSTAGE; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
@@ -315,7 +330,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     for (int i = 0; i < NBUF; ++i) {
       mbar_init(&bar_sfull[i], 1);
       mbar_init(&bar_sfree[i], 1);
-      mbar_init(&bar_pfull[i], kEpiWarps);
+      mbar_init(&bar_pfull[i], kBwdEpiWarps);
     }
     mbar_init(&bar_acc, 1);
     fence_barrier_init();
@@ -328,11 +343,14 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t tmem_acc = tmem + NBUF * kT;   // S buffers first, then the [128 x D] accumulator
+  const uint32_t tmem_a = tmem_acc + D;         // A_TMEM: [128 x D] bf16 operand, D/2 columns
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(&bar_a, kStage);
-      for (int kc = 0; kc < KCH; ++kc) tma_load_2d(sA + kc * kChunk, &tmA, &bar_a, kc * 64, r0);
+      if (!A_TMEM) {
+        mbar_arrive_expect_tx(&bar_a, kStage);
+        for (int kc = 0; kc < KCH; ++kc) tma_load_2d(sA + kc * kChunk, &tmA, &bar_a, kc * 64, r0);
+      }
       for (int j = 0; j < n_ct; ++j) {
         const uint32_t s = j % NSTAGE, ph = (j / NSTAGE) & 1;
         mbar_wait(&bar_empty[s], ph ^ 1);
@@ -364,9 +382,13 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int kc = 0; kc < KCH; ++kc) {
           const uint32_t a0 = smem_u32(sA + kc * kChunk), b0 = smem_u32(sB + s * kStage + kc * kChunk);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ss(dcol, umma_desc_sw128(a0 + ks * 32, 16, 1024), umma_desc_sw128(b0 + ks * 32, 16, 1024), idesc1,
-                    (kc | ks) != 0);
+          for (int ks = 0; ks < 4; ++ks) {
+            if (A_TMEM)
+              umma_ts(dcol, tmem_a + kc * 32 + ks * 8, umma_desc_sw128(b0 + ks * 32, 16, 1024), idesc1, (kc | ks) != 0);
+            else
+              umma_ss(dcol, umma_desc_sw128(a0 + ks * 32, 16, 1024), umma_desc_sw128(b0 + ks * 32, 16, 1024), idesc1,
+                      (kc | ks) != 0);
+          }
         }
         umma_commit(&bar_sfull[j % NBUF]);
       };
@@ -380,15 +402,15 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t b0 = smem_u32(sB + s * kStage);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
-          umma_ts(tmem_acc, pcol + (ks >> 2) * 64 + (ks & 3) * 8, umma_desc_sw128(b0 + ks * 2048, kChunk, 1024), idesc2,
-                  (j | ks) != 0);
+          umma_ts(tmem_acc, pcol + ((ks * 16) / kW) * kW + ((ks * 16) % kW) / 2, umma_desc_sw128(b0 + ks * 2048, kChunk, 1024),
+                  idesc2, (j | ks) != 0);
         umma_commit(&bar_empty[s]);
         umma_commit(&bar_sfree[j % NBUF]);
       }
       umma_commit(&bar_acc);
     }
   } else {
-    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    const int ew = warp - 2, quarter = warp & 3, cg = ew >> 2;   // lane quarter, column group
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     float crow = 0.f;
@@ -396,23 +418,44 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (FUSED) crow = (r0 + row < n_valid) ? 0.f : -INFINITY;
     float zacc = 0.f;  // FUSED: sum of G~ over this thread's columns
     float gsum = 0.f;  // COL mode with bias: sum over tokens of G (before the e^{b_i} row factor) -> bias gradient
+    if (A_TMEM) {
+      // thread (row, column group) copies its slice of the row tile from global memory into TMEM: K elements
+      // [cg*D/CG, (cg+1)*D/CG) of row r0+row -> packed columns [cg*D/(2CG), ...); rows beyond the matrix read as zero
+      constexpr int WORDS = D / 2 / kBwdCG;  // 32-bit words per thread
+      const bool in = (r0 + row) < n_rows;
+      const uint4* src = reinterpret_cast<const uint4*>(a_rows + (size_t)(in ? r0 + row : 0) * D + cg * (D / kBwdCG));
+#pragma unroll
+      for (int c = 0; c < WORDS; c += 16) {
+        uint32_t v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+          const uint4 t4 = in ? __ldg(src + ((c + q) >> 2)) : make_uint4(0u, 0u, 0u, 0u);
+          v[q] = t4.x; v[q + 1] = t4.y; v[q + 2] = t4.z; v[q + 3] = t4.w;
+        }
+        tmem_st16(tmem_a + lane_base + cg * WORDS + c, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_a);
+    }
     for (int j = 0; j < n_ct; ++j) {
       const uint32_t b = j % NBUF, s = j % NSTAGE;
       if (COLCONST) mbar_wait(&bar_full[s], (j / NSTAGE) & 1);  // s_cc[s] was written by the async proxy
       mbar_wait(&bar_sfull[b], (j / NBUF) & 1);
       tc_fence_after();
-      const uint32_t sbase = tmem + lane_base + b * kT + half * 64;
-      uint32_t raw[64];
-      tmem_ld32(sbase, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
-      tmem_ld32(sbase + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
-      tmem_ld_wait();
-      uint32_t pk[32];
-      const int col0 = (jg0 + j) * kT + half * 64;
-      // G = exp2(S*log2e + offset): alternate MUFU.EX2 and the FMA-pipe polynomial so neither pipe paces the tile
-      if (COLCONST) {
-        const float4* cc = reinterpret_cast<const float4*>(&s_cc[s][half * 64]);
+      const uint32_t sbase = tmem + lane_base + b * kT + cg * kW;
+      uint32_t raw[kW];
 #pragma unroll
-        for (int q = 0; q < 64; q += 4) {
+      for (int c = 0; c < kW; c += 32) tmem_ld32(sbase + c, *reinterpret_cast<uint32_t(*)[32]>(&raw[c]));
+      tmem_ld_wait();
+      uint32_t pk[kW / 2];
+      const int col0 = (jg0 + j) * kT + cg * kW;
+      // G = exp2(S*log2e + offset): mostly MUFU.EX2, a share on the FMA-pipe polynomial (RP_CE_POLY_EVERY_BWD)
+      if (COLCONST) {
+        const float4* cc = reinterpret_cast<const float4*>(&s_cc[s][cg * kW]);
+#pragma unroll
+        for (int q = 0; q < kW; q += 4) {
           const float4 o = cc[q >> 2];
           const float g0 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 0]), kLog2e, o.x), q + 0);
           const float g1 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 1]), kLog2e, o.y), q + 1);
@@ -425,7 +468,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       } else {
         if (bias) {  // per-column bias: s + b before the exponential (warp-uniform 16-byte loads)
 #pragma unroll
-          for (int q = 0; q < 64; q += 4) {
+          for (int q = 0; q < kW; q += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
             raw[q + 0] = __float_as_uint(__uint_as_float(raw[q + 0]) + b4.x);
             raw[q + 1] = __float_as_uint(__uint_as_float(raw[q + 1]) + b4.y);
@@ -434,10 +477,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
         }
 #pragma unroll
-        for (int q = 0; q < 64; q += 2) {
+        for (int q = 0; q < kW; q += 2) {
           float g0 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 0]), kLog2e, crow), q + 0);
           float g1 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 1]), kLog2e, crow), q + 1);
-          if (col0 + 64 > n_items) {  // columns beyond the catalog do not exist
+          if (col0 + kW > n_items) {  // columns beyond the catalog do not exist
             if (col0 + q >= n_items) g0 = 0.f;
             if (col0 + q + 1 >= n_items) g1 = 0.f;
           }
@@ -445,57 +488,62 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           pk[q >> 1] = pack_bf16(g0, g1);
         }
       }
-      // in place over this warp's own (already consumed) S columns: 64 fp32 columns -> 32 packed columns
-      tmem_st16(sbase, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
-      tmem_st16(sbase + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+      // in place over this warp's own (already consumed) S columns: kW fp32 columns -> kW/2 packed columns
+#pragma unroll
+      for (int c = 0; c < kW / 2; c += 16) tmem_st16(sbase + c, *reinterpret_cast<uint32_t(*)[16]>(&pk[c]));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_pfull[b]);
     }
-    // ---- final: accumulator -> global
+    // ---- final: accumulator -> global; this warp owns accumulator columns [cg*D/CG, (cg+1)*D/CG), 16 at a time
     mbar_wait(&bar_acc, 0);
     tc_fence_after();
     const int r = r0 + row;
-    constexpr int HALF_D = D / 2;
-    const uint32_t abase = tmem_acc + lane_base + half * HALF_D;
+    constexpr int DW = D / kBwdCG;
+    const uint32_t abase = tmem_acc + lane_base + cg * DW;
     if (COLCONST) {
       float* o = reinterpret_cast<float*>(out);
       // biased head: G carries a per-item factor e^{b_i}; it was left out of the loop and is applied to the row here
       const float rs = (bias && r < n_items) ? __expf(bias[r]) : 1.f;
       if (d_bias) {
-        s_gsum[half][row] = gsum;
-        asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");  // epilogue warps only
-        if (half == 0 && r < n_items) d_bias[r] = (s_gsum[0][row] + s_gsum[1][row]) * rs;
+        s_gsum[cg][row] = gsum;
+        asm volatile("bar.sync 1, %0;" ::"r"(kBwdEpiWarps * 32) : "memory");  // epilogue warps only
+        if (cg == 0 && r < n_items) {
+          float tot = 0.f;
+#pragma unroll
+          for (int k = 0; k < kBwdCG; ++k) tot += s_gsum[k][row];
+          d_bias[r] = tot * rs;
+        }
       }
 #pragma unroll 1
-      for (int c = 0; c < HALF_D; c += 32) {
-        uint32_t raw[32];
-        tmem_ld32(abase + c, raw);
+      for (int c = 0; c < DW; c += 16) {
+        uint32_t a16[16];
+        tmem_ld16(abase + c, a16);
         tmem_ld_wait();
         if (r < n_items) {
-          float4* dst = reinterpret_cast<float4*>(o + (size_t)r * D + half * HALF_D + c);
+          float4* dst = reinterpret_cast<float4*>(o + (size_t)r * D + cg * DW + c);
 #pragma unroll
-          for (int q = 0; q < 32; q += 4)
-            dst[q >> 2] = make_float4(__uint_as_float(raw[q]) * rs, __uint_as_float(raw[q + 1]) * rs,
-                                      __uint_as_float(raw[q + 2]) * rs, __uint_as_float(raw[q + 3]) * rs);
+          for (int q = 0; q < 16; q += 4)
+            dst[q >> 2] = make_float4(__uint_as_float(a16[q]) * rs, __uint_as_float(a16[q + 1]) * rs,
+                                      __uint_as_float(a16[q + 2]) * rs, __uint_as_float(a16[q + 3]) * rs);
         }
       }
     } else if (FUSED) {
       // partial (this column split) un-normalised gradient and row sums; ce_fused_finalize_kernel reduces the splits
       float* o = reinterpret_cast<float*>(out) + (size_t)split * capacity * D;
-      if (r < n_valid) zpart[((size_t)split * 2 + half) * capacity + r] = zacc;
+      if (r < n_valid) zpart[((size_t)split * kBwdCG + cg) * capacity + r] = zacc;
 #pragma unroll 1
-      for (int c = 0; c < HALF_D; c += 32) {
-        uint32_t raw[32];
-        tmem_ld32(abase + c, raw);
+      for (int c = 0; c < DW; c += 16) {
+        uint32_t a16[16];
+        tmem_ld16(abase + c, a16);
         tmem_ld_wait();
         if (r < n_valid) {
-          float4* dst = reinterpret_cast<float4*>(o + (size_t)r * D + half * HALF_D + c);
+          float4* dst = reinterpret_cast<float4*>(o + (size_t)r * D + cg * DW + c);
 #pragma unroll
-          for (int q = 0; q < 32; q += 4)
-            dst[q >> 2] = make_float4(__uint_as_float(raw[q]), __uint_as_float(raw[q + 1]), __uint_as_float(raw[q + 2]),
-                                      __uint_as_float(raw[q + 3]));
+          for (int q = 0; q < 16; q += 4)
+            dst[q >> 2] = make_float4(__uint_as_float(a16[q]), __uint_as_float(a16[q + 1]), __uint_as_float(a16[q + 2]),
+                                      __uint_as_float(a16[q + 3]));
         }
       }
     } else {
@@ -503,15 +551,15 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const float inv_n = loss_inv[0];
       const int y = (r < n_valid) ? labels[r] : 0;
 #pragma unroll 1
-      for (int c = 0; c < HALF_D; c += 32) {
-        uint32_t raw[32];
-        tmem_ld32(abase + c, raw);
+      for (int c = 0; c < DW; c += 16) {
+        uint32_t a16[16];
+        tmem_ld16(abase + c, a16);
         tmem_ld_wait();
         if (r < n_valid) {
-          const uint4* ey = reinterpret_cast<const uint4*>(table + (size_t)y * D + half * HALF_D + c);
-          uint4* dst = reinterpret_cast<uint4*>(o + (size_t)r * D + half * HALF_D + c);
+          const uint4* ey = reinterpret_cast<const uint4*>(table + (size_t)y * D + cg * DW + c);
+          uint4* dst = reinterpret_cast<uint4*>(o + (size_t)r * D + cg * DW + c);
 #pragma unroll
-          for (int q = 0; q < 32; q += 8) {
+          for (int q = 0; q < 16; q += 8) {
             const uint4 e = ey[q >> 3];
             const __nv_bfloat162* e2 = reinterpret_cast<const __nv_bfloat162*>(&e);
             uint4 w;
@@ -519,8 +567,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
               const float2 ef = __bfloat1622float2(e2[p]);
-              w32[p] = pack_bf16(__uint_as_float(raw[q + 2 * p]) - inv_n * ef.x,
-                                 __uint_as_float(raw[q + 2 * p + 1]) - inv_n * ef.y);
+              w32[p] = pack_bf16(__uint_as_float(a16[q + 2 * p]) - inv_n * ef.x,
+                                 __uint_as_float(a16[q + 2 * p + 1]) - inv_n * ef.y);
             }
             dst[q >> 3] = w;
           }
@@ -609,7 +657,7 @@ __global__ void ce_fused_finalize_kernel(const float* __restrict__ part_dh, cons
       continue;
     }
     float z = 0.f;
-    for (int i = lane; i < n_splits * 2; i += 32) z += zpart[(size_t)i * capacity + t];
+    for (int i = lane; i < n_splits * kBwdCG; i += 32) z += zpart[(size_t)i * capacity + t];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
     const int y = labels[t];
@@ -687,7 +735,7 @@ struct CeWs {
 static const int kMaxSplits = 8;
 
 static size_t ce_ws_bytes(int cap, int d) {
-  return (size_t)cap * kMaxSplits * 2 * sizeof(float2) + 4096 + 64 + (size_t)kMaxSplits * 2 * cap * 4 +
+  return (size_t)cap * kMaxSplits * 2 * sizeof(float2) + 4096 + 64 + (size_t)kMaxSplits * kBwdCG * cap * 4 +
          (size_t)kMaxSplits * cap * d * 4 + 256;
 }
 static CeWs ce_ws(void* workspace, int cap, int d) {
@@ -702,7 +750,7 @@ static CeWs ce_ws(void* workspace, int cap, int d) {
   r.flag = reinterpret_cast<int32_t*>(r.ticket + 4);
   w += 64;
   r.zpart = reinterpret_cast<float*>(w);
-  w += (size_t)kMaxSplits * 2 * cap * 4;
+  w += (size_t)kMaxSplits * kBwdCG * cap * 4;
   r.part_dh = reinterpret_cast<float*>(w);
   (void)d;
   return r;
@@ -726,34 +774,40 @@ static int launch_ce_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const i
 }
 
 template <int KCH, int NSTAGE, int MODE>
-static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* cvec, const int32_t* labels,
+static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const void* a_rows, const float* cvec,
+                         const int32_t* labels,
                          const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, const float* bias,
                          float* d_bias, void* out, int grid, const int32_t* safe_flag, int run_if_safe, int n_splits,
                          int capacity, float* zpart, cudaStream_t stream) {
-  const int smem = (1 + NSTAGE) * KCH * kChunk + 1024;
-  constexpr int NBUF = (RP_CE_NBUF3 && KCH <= 2) ? 3 : 2;  // 3 S buffers + [128 x d] accumulator fit the 512 TMEM columns up to d = 128
-  auto kern = ce_bwd_kernel<KCH, NSTAGE, MODE, NBUF>;
+  // d <= 128: the row tile goes to TMEM (2 S buffers + accumulator + operand = 448 columns) and its 32 KB of smem become
+  // an extra pipeline stage; d = 256: row tile in smem, 2 S buffers + accumulator = 512 columns
+  constexpr bool A_TMEM = (RP_CE_A_TMEM != 0) && KCH <= 2 && MODE == 1;  // measured: pays for the dE pass only
+  constexpr int NBUF = A_TMEM ? 2 : ((RP_CE_NBUF3 && KCH <= 2) ? 3 : 2);
+  const int smem = ((A_TMEM ? 0 : 1) + NSTAGE + (A_TMEM ? 1 : 0)) * KCH * kChunk + 1024;
+  auto kern = ce_bwd_kernel<KCH, NSTAGE + (A_TMEM ? 1 : 0), MODE, NBUF, A_TMEM>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, cvec, labels, reinterpret_cast<const __nv_bfloat16*>(table), loss_inv,
+  kern<<<grid, kBwdThreads, smem, stream>>>(tmA, tmB, reinterpret_cast<const __nv_bfloat16*>(a_rows), cvec, labels,
+                                            reinterpret_cast<const __nv_bfloat16*>(table), loss_inv,
                                          n_valid, n_items, bias, d_bias, out, safe_flag, run_if_safe, n_splits, capacity, zpart);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }
 
 template <int MODE>
-static int dispatch_ce_bwd(int d, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* cvec, const int32_t* labels,
+static int dispatch_ce_bwd(int d, const CUtensorMap& tmA, const CUtensorMap& tmB, const void* a_rows, const float* cvec,
+                           const int32_t* labels,
                            const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, const float* bias,
                            float* d_bias, void* out, int grid, const int32_t* safe_flag, int run_if_safe, int n_splits,
                            int capacity, float* zpart, cudaStream_t stream) {
   switch (d) {
     case 64:
-      return launch_ce_bwd<1, 6, MODE>(tmA, tmB, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
+      return launch_ce_bwd<1, 6, MODE>(tmA, tmB, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
                                        safe_flag, run_if_safe, n_splits, capacity, zpart, stream);
     case 128:
-      return launch_ce_bwd<2, 4, MODE>(tmA, tmB, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
+      return launch_ce_bwd<2, 4, MODE>(tmA, tmB, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
                                        safe_flag, run_if_safe, n_splits, capacity, zpart, stream);
     case 256:
-      return launch_ce_bwd<4, 2, MODE>(tmA, tmB, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
+      return launch_ce_bwd<4, 2, MODE>(tmA, tmB, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
                                        safe_flag, run_if_safe, n_splits, capacity, zpart, stream);
     default:
       return RP_ESHAPE;
@@ -796,7 +850,7 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, 
     ce_flag_kernel<<<1, 1, 0, stream>>>(ws.bound, ws.flag);
     RP_LAUNCH_CHECK();
     const int P = pick_splits(hint_tiles, n_item_tiles);
-    rc = dispatch_ce_bwd<2>(d, tmA, tmB, cvec, labels, table, loss_out + 1, n_valid, n_items, bias, nullptr, ws.part_dh,
+    rc = dispatch_ce_bwd<2>(d, tmA, tmB, hc, cvec, labels, table, loss_out + 1, n_valid, n_items, bias, nullptr, ws.part_dh,
                             n_tok_tiles * P, ws.flag, 1, P, capacity, ws.zpart, stream);
     if (rc != RP_OK) return rc;
     ce_fused_finalize_kernel<<<blocks, 256, 0, stream>>>(ws.part_dh, ws.zpart, reinterpret_cast<const __nv_bfloat16*>(hc),
@@ -844,10 +898,10 @@ RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, 
   const float* loss_inv = loss_out + 1;
   const int32_t* flag = fused ? ce_ws(workspace, capacity, d).flag : nullptr;
   // token-major pass: only when the forward did not already produce d_hc
-  rc = dispatch_ce_bwd<0>(d, tmH, tmE, cvec, labels, table, loss_inv, n_valid, n_items, bias, nullptr, d_hc, n_tok_tiles, flag, 0,
+  rc = dispatch_ce_bwd<0>(d, tmH, tmE, hc, cvec, labels, table, loss_inv, n_valid, n_items, bias, nullptr, d_hc, n_tok_tiles, flag, 0,
                           1, capacity, nullptr, stream);
   if (rc != RP_OK) return rc;
-  rc = dispatch_ce_bwd<1>(d, tmE, tmH, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, d_table, n_item_tiles,
+  rc = dispatch_ce_bwd<1>(d, tmE, tmH, table, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, d_table, n_item_tiles,
                           nullptr, 0, 1, capacity, nullptr, stream);
   if (rc != RP_OK) return rc;
   ce_label_scatter_kernel<<<sm_count() * 4, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hc), labels, loss_inv,

@@ -2,12 +2,12 @@
 # builds CE-head variants (compile-time knobs) into replay_b200/build/variants/*.so for A/B timing on the GPU box
 set -e
 cd "$(dirname "$0")/.."
-mkdir -p replay_b200/build/variants
+rm -rf replay_b200/build/variants; mkdir -p replay_b200/build/variants
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --use_fast_math -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -I include"
-for v in "0 0" "0 1" "4 1" "2 1" "4 0" "8 1"; do
+for v in "1 2 8" "0 2 8" "1 4 8" "1 2 4" "1 2 0"; do
   set -- $v
-  out=replay_b200/build/variants/ce_p$1_n$2.so
-  nvcc $FLAGS -DRP_CE_POLY_EVERY=$1 -DRP_CE_NBUF3=$2 -shared -o $out replay_b200/csrc/rp_ce_head.cu replay_b200/csrc/rp_host.cu -cudart static &
+  out=replay_b200/build/variants/ce_atmem$1_cg$2_poly$3.so
+  nvcc $FLAGS -DRP_CE_A_TMEM=$1 -DRP_CE_BWD_CG=$2 -DRP_CE_POLY_EVERY_BWD=$3 -shared -o $out replay_b200/csrc/rp_ce_head.cu replay_b200/csrc/rp_host.cu -cudart static &
 done
 wait
-ls -la replay_b200/build/variants
+ls replay_b200/build/variants

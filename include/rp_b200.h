@@ -104,7 +104,8 @@ int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, const i
  * Operand X is a 2-D bf16 array [x_rows, x_cols] with pitch ldx; x_mn = 0: stored [M or N rows, K cols] (K-major),
  * x_mn = 1: stored [K rows, M or N cols].  Batch element bz = outer*inner + in addresses rows r0 + outer*ro + in*ri and
  * columns c0 + outer*co + in*ci.  C: element offset c_off0 + outer*c_oo + in*c_oi, row pitch ldc.
- * out_mode 0: bf16 store, 1: fp32 atomic add (split_k >= 1), 2: fp32 store.
+ * out_mode 0: bf16 store, 1: fp32 atomic add (split_k >= 1), 2: fp32 store, 3: fp32 store of the split-K partial at
+ * C + ksplit * c_split_stride (deterministic two-stage split-K; reduce with rp_reduce_splits).
  * Epilogue order: alpha, bias[N], act (0 none, 1 ReLU, 2 GELU-erf), Philox dropout(drop_p; seed + *seed_ptr, drop_offset +
  * element offset in C), gate (x *= gate != 0 ? gate_scale : 0, same geometry as C), residual (bf16, same geometry as C),
  * post-residual dropout (post_drop_p, post_drop_offset), rowmask[rowmask_off0 + outer*rowmask_oo + m].
@@ -123,8 +124,11 @@ typedef struct rp_gemm_desc {
   int split_k;
   const void* gate; float gate_scale;
   void* C2; int gate_mode; float post_drop_p; unsigned long long post_drop_offset;
+  long long c_split_stride;
 } rp_gemm_desc;
 int rp_gemm(const rp_gemm_desc* g, void* stream);
+/* dst[i] (+)= sum_s src[s * stride + i], i < n (n, stride multiples of 4) */
+int rp_reduce_splits(const float* src, int n_splits, long long stride, long long n, float* dst, int accumulate, void* stream);
 
 /* Fused multi-head attention forward for L <= 256, head_dim in {64,128}: S = Q.K^T, causal / key-padding mask derived
  * from pad_mask (no [B*H,L,L] mask tensor), softmax, dropout, O = P.V.

@@ -57,6 +57,7 @@ def lib():
     U64, LL = ctypes.c_ulonglong, ctypes.c_longlong
     _sig(L.rp_gemm, c_int, [ctypes.POINTER(GemmDesc), P])
     _sig(L.rp_attn_fwd, c_int, [ctypes.POINTER(AttnDesc), P])
+    _sig(L.rp_reduce_splits, c_int, [P, c_int, LL, LL, P, c_int, P])
     _sig(L.rp_attn_softmax_bwd, c_int, [P, P, P, c_int, c_int, c_float, c_float, U64, U64, P, P])
     _sig(L.rp_prepare_batch, c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P])
     _sig(L.rp_embed_fwd, c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_float, U64, U64, P, P, P])
@@ -95,6 +96,7 @@ class GemmDesc(ctypes.Structure):
         ("split_k", c_int),
         ("gate", c_void_p), ("gate_scale", c_float),
         ("C2", c_void_p), ("gate_mode", c_int), ("post_drop_p", c_float), ("post_drop_offset", ctypes.c_ulonglong),
+        ("c_split_stride", ctypes.c_longlong),
     ]
 
 

@@ -25,7 +25,9 @@ struct GemmParams {
   int b_r0, b_ro, b_ri, b_c0, b_co, b_ci;
   void* C;                     // output
   long long ldc, c_off0, c_oo, c_oi;   // element offsets: c_off0 + outer*c_oo + in*c_oi, row pitch ldc
-  int out_mode;                // 0: bf16 store, 1: fp32 atomic add, 2: fp32 store
+  int out_mode;                // 0: bf16 store, 1: fp32 atomic add, 2: fp32 store, 3: fp32 store of the split-K partial at
+                               //    C + ksplit * c_split_stride (reduced afterwards by rp_reduce_splits; no atomics)
+  long long c_split_stride;
   float alpha;
   const float* bias;           // [N] or null
   int act;                     // 0 none, 1 relu, 2 gelu(erf)
@@ -171,6 +173,9 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const f
 #pragma unroll
           for (int q = 0; q < 32; ++q)
             if (n0 + c + q < p.N) atomicAdd(o + q, x[q]);
+        } else if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(o + q) = make_float4(x[q], x[q + 1], x[q + 2], x[q + 3]);
         } else {
 #pragma unroll
           for (int q = 0; q < 32; ++q)
@@ -272,7 +277,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     mbar_wait(&bar_acc, 0);
     tc_fence_after();
     const bool row_ok = m < p.M;
-    const long long c_base = p.c_off0 + (long long)outer * p.c_oo + (long long)in * p.c_oi + (long long)m * p.ldc;
+    const long long c_base = p.c_off0 + (long long)outer * p.c_oo + (long long)in * p.c_oi + (long long)m * p.ldc +
+                             (p.out_mode == 3 ? (long long)ksplit * p.c_split_stride : 0ll);
     float rm = 1.f;
     if (p.rowmask && row_ok) rm = p.rowmask[p.rowmask_off0 + (long long)outer * p.rowmask_oo + m] ? 1.f : 0.f;
     EpiRow er;
@@ -489,13 +495,14 @@ struct rp_gemm_desc {
   int split_k;
   const void* gate; float gate_scale;
   void* C2; int gate_mode; float post_drop_p; unsigned long long post_drop_offset;
+  long long c_split_stride;
 };
 
 RP_API int rp_gemm(const rp_gemm_desc* g, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!g || !g->A || !g->B || !g->C) return RP_EINVAL;
   if (g->M <= 0 || g->N <= 0 || g->K <= 0 || g->batch <= 0 || g->inner <= 0) return RP_ESHAPE;
-  if (g->split_k < 1 || (g->split_k > 1 && g->out_mode != 1)) return RP_EINVAL;
+  if (g->split_k < 1 || (g->split_k > 1 && g->out_mode != 1 && g->out_mode != 3)) return RP_EINVAL;
   if (g->out_mode == 0 && (g->ldc % 8 != 0)) return RP_EALIGN;
   GemmParams p;
   p.M = g->M; p.N = g->N; p.K = g->K; p.inner = g->inner;
@@ -509,6 +516,7 @@ RP_API int rp_gemm(const rp_gemm_desc* g, void* stream_) {
   p.gate = reinterpret_cast<const __nv_bfloat16*>(g->gate); p.gate_scale = g->gate_scale;
   p.C2 = reinterpret_cast<__nv_bfloat16*>(g->C2); p.gate_mode = g->gate_mode; p.post_drop_p = g->post_drop_p;
   p.post_drop_offset = g->post_drop_offset;
+  p.c_split_stride = g->c_split_stride;
   CUtensorMap tmA, tmB;
   int rc;
   // K-major operand: box [128 (or BN) rows x 64 cols]; MN-major operand: box [64 k-rows x 64 cols]
@@ -541,4 +549,28 @@ RP_API int rp_gemm(const rp_gemm_desc* g, void* stream_) {
     RP_GEMM_CASE(128, true, true);
   }
 #undef RP_GEMM_CASE
+}
+
+// dst[i] (+)= sum_s src[s * stride + i]   - second stage of the split-K weight-gradient GEMMs (out_mode 3)
+__global__ void reduce_splits_kernel(const float* __restrict__ src, int n_splits, long long stride, long long n,
+                                     float* __restrict__ dst, int accumulate) {
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
+    float4 a = accumulate ? *reinterpret_cast<const float4*>(dst + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s2 = 0; s2 < n_splits; ++s2) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (long long)s2 * stride + i);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(dst + i) = a;
+  }
+}
+
+RP_API int rp_reduce_splits(const float* src, int n_splits, long long stride, long long n, float* dst, int accumulate,
+                            void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!src || !dst || n_splits <= 0 || n <= 0 || (n & 3) || (stride & 3)) return RP_EINVAL;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > rp::sm_count() * 8) blocks = rp::sm_count() * 8;
+  reduce_splits_kernel<<<(int)blocks, 256, 0, stream>>>(src, n_splits, stride, n, dst, accumulate);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
 }

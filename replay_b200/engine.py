@@ -62,7 +62,7 @@ class _CountingLib:
 
     KERNELS = {"rp_gemm": 1, "rp_attn_fwd": 1, "rp_attn_last": 1, "rp_attn_softmax_bwd": 1, "rp_prepare_batch": 2, "rp_embed_fwd": 1,
                "rp_embed_bwd": 2, "rp_layernorm_fwd": 1, "rp_layernorm_bwd": 1, "rp_dropout_bwd": 1, "rp_colsum": 1,
-               "rp_adam_step": 2, "rp_cast_bf16": 1, "rp_counter_add": 1, "rp_ce_head_fwd": 2, "rp_ce_head_bwd": 3,
+               "rp_adam_step": 2, "rp_cast_bf16": 1, "rp_counter_add": 1, "rp_reduce_splits": 1, "rp_ce_head_fwd": 2, "rp_ce_head_bwd": 3,
                "rp_score_topk": 2, "rp_seen_prepare": 1}
 
     def __init__(self, L):
@@ -225,6 +225,7 @@ class SasRecEngine:
             self.s = {k: torch.zeros(T, d, **bf) for k in ("dhc", "dxa", "dxb", "d_t", "du", "dy", "dh", "d_o", "dQ", "dq_in", "tmp")}
             self.s["dKV"] = torch.zeros(T, 2 * d, **bf)
             self.s["dpd"] = torch.zeros(BH, self.Lp, self.Lp, **bf)
+            self.wg_ws = torch.zeros(148 * 4 * d * d, **f32)  # split-K partials of the weight-gradient GEMMs
 
     def _stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
@@ -233,7 +234,7 @@ class SasRecEngine:
     def _gemm(self, A, B, C, M, N, K, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, rowmask=None,
               drop_p=0.0, drop_site=0, out_mode=0, split_k=1, gate=None, gate_scale=1.0, alpha=1.0, batch=1, inner=1,
               a_off=(0, 0, 0, 0, 0, 0), b_off=(0, 0, 0, 0, 0, 0), c_geom=None, rowmask_oo=0, C2=None, gate_mode=0,
-              post_drop_p=0.0, post_drop_site=0):
+              post_drop_p=0.0, post_drop_site=0, c_split_stride=0):
         g = GemmDesc()
         g.A, g.a_rows, g.a_cols, g.lda, g.a_mn = A.data_ptr(), A.shape[0], A.shape[1], A.stride(0), int(a_mn)
         g.B, g.b_rows, g.b_cols, g.ldb, g.b_mn = B.data_ptr(), B.shape[0], B.shape[1], B.stride(0), int(b_mn)
@@ -263,15 +264,21 @@ class SasRecEngine:
         g.gate_mode = gate_mode
         g.post_drop_p = post_drop_p
         g.post_drop_offset = post_drop_site << 40
+        g.c_split_stride = c_split_stride
         check(self.lib.rp_gemm(ctypes.byref(g), self._stream()), "rp_gemm")
 
     def _wgrad(self, dY, X, dW, n_out, n_in):
-        """dW[n_out, n_in] += dY[T, n_out]^T . X[T, n_in]  (both operands MN-major, split-K, fp32 atomics)."""
+        """dW[n_out, n_in] += dY[T, n_out]^T . X[T, n_in]: both operands read MN-major in place; split-K over about one wave
+        of CTAs, each storing its fp32 partial tile (no atomics: 100+ CTAs hammering the same 16 K addresses serialise in
+        L2), then one reduction pass adds the partials into the gradient buffer (deterministic)."""
         tiles = ((n_out + 127) // 128) * ((n_in + 127) // 128 if n_in > 64 else 1)
         chunks = (self.T + 63) // 64
-        per = int(os.environ.get("RP_WGRAD_CHUNKS", "24"))  # K-chunks (64 tokens) per CTA: tuning knob
-        split = max(1, min(chunks // per, (148 + tiles - 1) // tiles))
-        self._gemm(dY, X, dW, n_out, n_in, self.T, a_mn=True, b_mn=True, out_mode=1, split_k=split)
+        n = n_out * n_in
+        per = int(os.environ.get("RP_WGRAD_CHUNKS", "8"))
+        split = max(1, min(chunks // per, (148 + tiles - 1) // tiles, self.wg_ws.numel() // n))
+        self._gemm(dY, X, self.wg_ws, n_out, n_in, self.T, a_mn=True, b_mn=True, out_mode=3, split_k=split,
+                   c_geom=(n_in, 0, 0, 0), c_split_stride=n)
+        check(self.lib.rp_reduce_splits(self.wg_ws.data_ptr(), split, n, n, dW.data_ptr(), 1, self._stream()), "rp_reduce_splits")
 
     def _colsum(self, dY, db):
         check(self.lib.rp_colsum(dY.data_ptr(), dY.shape[0], dY.shape[1], dY.stride(0), db.data_ptr(), self._stream()),

@@ -172,6 +172,7 @@ class Bert4RecEngine(SasRecEngine):
             self.s["du"] = torch.zeros(T, 4 * d, **bf)
             self.s["dQKV"] = torch.zeros(T, 3 * d, **bf)
             self.s["dpd"] = torch.zeros(BH, self.Lp, self.Lp, **bf)
+            self.wg_ws = torch.zeros(148 * 4 * d * d, **f32)  # split-K partials of the weight-gradient GEMMs
 
     # ------------------------------------------------------------------------------------------------ batch
     def set_batch(self, ids, pad_mask, token_mask, labels=None):

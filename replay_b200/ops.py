@@ -107,7 +107,7 @@ def ce_head_bwd(st: CEHeadState, hc, table, labels, n_valid, d_hc, d_table, bias
 def gemm(A, B, C, M, N, K, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, rowmask=None, drop_p=0.0,
          drop_offset=0, seed=0, seed_ptr=None, out_mode=0, split_k=1, gate=None, gate_scale=1.0, gate_mode=0, alpha=1.0,
          batch=1, inner=1, a_off=(0, 0, 0, 0, 0, 0), b_off=(0, 0, 0, 0, 0, 0), c_geom=None, rowmask_oo=0, C2=None,
-         post_drop_p=0.0, post_drop_offset=0, L=None):
+         post_drop_p=0.0, post_drop_offset=0, c_split_stride=0, L=None):
     """C = epilogue(alpha * A(m,k) . B(n,k)) through rp_gemm (include/rp_b200.h).  A / B are 2-D bf16 tensors (views allowed:
     pointer, shape and row pitch are taken from the tensor); x_mn selects the MN-major reading of an operand."""
     g = GemmDesc()
@@ -128,4 +128,5 @@ def gemm(A, B, C, M, N, K, *, a_mn=False, b_mn=False, bias=None, act=0, residual
     g.gate, g.gate_scale, g.gate_mode = _ptr(gate), gate_scale, gate_mode
     g.C2 = _ptr(C2)
     g.post_drop_p, g.post_drop_offset = post_drop_p, post_drop_offset
+    g.c_split_stride = c_split_stride
     check((L or lib()).rp_gemm(ctypes.byref(g), _stream()), "rp_gemm")

@@ -147,10 +147,34 @@ typedef struct rp_attn_desc {
   void* out; int ldo;
   void* p_save; float* inv_sum;
   float drop_p; unsigned long long seed, drop_off; const unsigned long long* seed_ptr;
+  float* m_save;  /* optional fp32 [B*H, Lp]: row max in exp2 units, input of rp_attn_bwd */
 } rp_attn_desc;
 int rp_attn_fwd(const rp_attn_desc* a, void* stream);
 
-/* Softmax backward between the batched attention-backward GEMMs: in place, dpd := dS = P*(dP - sum P*dP)*scale and
+/* Fused attention backward (L <= 256, head_dim 64), one CTA per (sequence, head): recomputes S^T = K.Q^T and
+ * dP^T = V.dO^T on tcgen05, forms P / dS in registers from the forward's row statistics (m_save, inv_sum) and accumulates
+ * dV = Pd^T.dO, dK = dS^T.Q, dQ = dS.K with the bf16 operands staged in TMEM / swizzled shared memory - the [B*H, L, L]
+ * matrices of the un-fused path are never written.  Replaces autograd's backward of the SDPA core of
+ * torch.nn.MultiheadAttention (replay/nn/sequential/sasrec/transformer.py:99-106 ; bert4rec/model.py:494).
+ * q/k/v/d_out/out: token-major 2-D bf16 arrays; dq/dk/dv: outputs (rows b*L + i, columns x_c0 + h*64). */
+typedef struct rp_attn_bwd_desc {
+  const void* q; long long q_rows, q_cols, ldq; int q_c0;
+  const void* k; long long k_rows, k_cols, ldk; int k_c0;
+  const void* v; long long v_rows, v_cols, ldv; int v_c0;
+  const void* d_out; long long do_rows, do_cols, ld_do;
+  const void* out; int ldo;
+  int B, H, L, head_dim;
+  int causal, mask_pad_keys;
+  const uint8_t* pad_mask;
+  const float* m_save; const float* inv_sum;
+  void* dq; int ld_dq, dq_c0;
+  void* dk; int ld_dk, dk_c0;
+  void* dv; int ld_dv, dv_c0;
+  float drop_p; unsigned long long seed, drop_off; const unsigned long long* seed_ptr;
+} rp_attn_bwd_desc;
+int rp_attn_bwd(const rp_attn_bwd_desc* a, void* stream);
+
+/* Softmax backward between the batched attention-backward GEMMs (un-fused path, any supported head_dim): in place, dpd := dS = P*(dP - sum P*dP)*scale and
  * p_save := P*dropmask/keep (the A operand of dV). */
 int rp_attn_softmax_bwd(void* p_save, void* dpd, const float* inv_sum, int BH, int L, float scale, float drop_p,
                         unsigned long long seed, unsigned long long drop_off, const unsigned long long* seed_ptr,

@@ -57,6 +57,7 @@ def lib():
     U64, LL = ctypes.c_ulonglong, ctypes.c_longlong
     _sig(L.rp_gemm, c_int, [ctypes.POINTER(GemmDesc), P])
     _sig(L.rp_attn_fwd, c_int, [ctypes.POINTER(AttnDesc), P])
+    _sig(L.rp_attn_bwd, c_int, [ctypes.POINTER(AttnBwdDesc), P])
     _sig(L.rp_reduce_splits, c_int, [P, c_int, LL, LL, P, c_int, P])
     _sig(L.rp_attn_softmax_bwd, c_int, [P, P, P, c_int, c_int, c_float, c_float, U64, U64, P, P])
     _sig(L.rp_prepare_batch, c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P])
@@ -113,9 +114,30 @@ class AttnDesc(ctypes.Structure):
         ("out", c_void_p), ("ldo", c_int),
         ("p_save", c_void_p), ("inv_sum", c_void_p),
         ("drop_p", c_float), ("seed", ctypes.c_ulonglong), ("drop_off", ctypes.c_ulonglong), ("seed_ptr", c_void_p),
+        ("m_save", c_void_p),
+    ]
+
+
+class AttnBwdDesc(ctypes.Structure):
+    """Mirror of ``struct rp_attn_bwd_desc`` (include/rp_b200.h)."""
+
+    _fields_ = [
+        ("q", c_void_p), ("q_rows", ctypes.c_longlong), ("q_cols", ctypes.c_longlong), ("ldq", ctypes.c_longlong), ("q_c0", c_int),
+        ("k", c_void_p), ("k_rows", ctypes.c_longlong), ("k_cols", ctypes.c_longlong), ("ldk", ctypes.c_longlong), ("k_c0", c_int),
+        ("v", c_void_p), ("v_rows", ctypes.c_longlong), ("v_cols", ctypes.c_longlong), ("ldv", ctypes.c_longlong), ("v_c0", c_int),
+        ("d_out", c_void_p), ("do_rows", ctypes.c_longlong), ("do_cols", ctypes.c_longlong), ("ld_do", ctypes.c_longlong),
+        ("out", c_void_p), ("ldo", c_int),
+        ("B", c_int), ("H", c_int), ("L", c_int), ("head_dim", c_int),
+        ("causal", c_int), ("mask_pad_keys", c_int),
+        ("pad_mask", c_void_p),
+        ("m_save", c_void_p), ("inv_sum", c_void_p),
+        ("dq", c_void_p), ("ld_dq", c_int), ("dq_c0", c_int),
+        ("dk", c_void_p), ("ld_dk", c_int), ("dk_c0", c_int),
+        ("dv", c_void_p), ("ld_dv", c_int), ("dv_c0", c_int),
+        ("drop_p", c_float), ("seed", ctypes.c_ulonglong), ("drop_off", ctypes.c_ulonglong), ("seed_ptr", c_void_p),
     ]
 
 
 _EXTRA_SIGS: list = []
 
-__all__ = ["GemmDesc", "AttnDesc", "lib", "check", "RpError", "LIB_PATH", "c_float", "c_int", "c_int32", "c_int64", "c_size_t", "c_void_p"]
+__all__ = ["GemmDesc", "AttnDesc", "AttnBwdDesc", "lib", "check", "RpError", "LIB_PATH", "c_float", "c_int", "c_int32", "c_int64", "c_size_t", "c_void_p"]

@@ -22,6 +22,7 @@ struct AttnParams {
   int ldo;
   __nv_bfloat16* p_save;       // [B*H, Lp, Lp] unnormalised exp(s - max) (bf16) or null
   float* inv_sum;              // [B*H, Lp] 1 / row sum (0 for fully masked rows)
+  float* m_save;               // [B*H, Lp] row max in exp2 units (max * scale * log2e), for the fused backward; or null
   int q_c0, k_c0, v_c0;        // column offsets of head 0 inside the Q / K / V 2-D arrays
   float drop_p;
   unsigned long long seed, drop_off;
@@ -175,13 +176,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (p.drop_p > 0.f) {
         const unsigned long long e0 = p.drop_off + ((unsigned long long)bz * p.Lp + (unsigned long long)i) * p.Lp + c * 32;
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          const uint4 r = philox4x32(seed_eff, (e0 + q) >> 2);
-          e[q + 0] = r.x >= thr ? e[q + 0] * ks_drop : 0.f;
-          e[q + 1] = r.y >= thr ? e[q + 1] * ks_drop : 0.f;
-          e[q + 2] = r.z >= thr ? e[q + 2] * ks_drop : 0.f;
-          e[q + 3] = r.w >= thr ? e[q + 3] * ks_drop : 0.f;
-        }
+        for (int q = 0; q < 32; ++q) e[q] = drop_hash32(seed_eff, e0 + q) >= thr ? e[q] * ks_drop : 0.f;
       }
       uint32_t pk[16];
 #pragma unroll
@@ -194,6 +189,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (lane == 0) mbar_arrive(&bar_p);
     const float inv = sum > 0.f ? 1.f / sum : 0.f;
     if (p.inv_sum && i < L) p.inv_sum[(size_t)bz * p.Lp + i] = inv;
+    if (p.m_save && i < L) p.m_save[(size_t)bz * p.Lp + i] = moff;
     // ---- O = (P.V) / sum
     mbar_wait(&bar_o, 0);
     tc_fence_after();
@@ -255,9 +251,11 @@ __global__ void attn_softmax_bwd_kernel(__nv_bfloat16* __restrict__ p_save, __nv
         const float2 p0 = __bfloat1622float2(ph[0]), p1 = __bfloat1622float2(ph[1]);
         const float2 d0 = __bfloat1622float2(dh[0]), d1 = __bfloat1622float2(dh[1]);
         const float pv[4] = {p0.x, p0.y, p1.x, p1.y}, dv[4] = {d0.x, d0.y, d1.x, d1.y};
-        uint4 rnd = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        if (drop_p > 0.f) rnd = philox4x32(seed, (drop_off + base + j0) >> 2);
-        const uint32_t rv[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+        uint32_t rv[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (drop_p > 0.f) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rv[q] = drop_hash32(seed, drop_off + base + j0 + q);
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const bool in = (j0 + q) < L;
@@ -408,6 +406,7 @@ struct rp_attn_desc {
   void* out; int ldo;
   void* p_save; float* inv_sum;
   float drop_p; unsigned long long seed, drop_off; const unsigned long long* seed_ptr;
+  float* m_save;
 };
 
 RP_API int rp_attn_fwd(const rp_attn_desc* a, void* stream_) {
@@ -422,7 +421,7 @@ RP_API int rp_attn_fwd(const rp_attn_desc* a, void* stream_) {
   p.scale = 1.f / sqrtf((float)a->head_dim);
   p.pad_mask = a->pad_mask;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
-  p.p_save = reinterpret_cast<__nv_bfloat16*>(a->p_save); p.inv_sum = a->inv_sum;
+  p.p_save = reinterpret_cast<__nv_bfloat16*>(a->p_save); p.inv_sum = a->inv_sum; p.m_save = a->m_save;
   p.q_c0 = a->q_c0; p.k_c0 = a->k_c0; p.v_c0 = a->v_c0;
   p.drop_p = a->drop_p; p.seed = a->seed; p.drop_off = a->drop_off; p.seed_ptr = a->seed_ptr;
   CUtensorMap tmQ, tmK, tmV;

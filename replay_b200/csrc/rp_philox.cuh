@@ -32,4 +32,17 @@ __device__ __forceinline__ bool philox_keep(unsigned long long seed, unsigned lo
   return w >= thr;
 }
 
+// Cheap per-element hash (murmur3 finaliser) for the attention-probability dropout: the fused attention backward walks
+// the [query, key] matrix transposed, so the mask must be computable per element in any order (Philox is used where the
+// forward and backward visit 4 consecutive elements together).
+__device__ __forceinline__ uint32_t drop_hash32(unsigned long long seed, unsigned long long idx) {
+  uint32_t h = ((uint32_t)idx * 0x9E3779B1u) ^ (uint32_t)seed ^ ((uint32_t)(idx >> 32) * 0x85EBCA77u) ^ (uint32_t)(seed >> 32);
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+
 }  // namespace rp

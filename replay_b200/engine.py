@@ -18,7 +18,7 @@ from dataclasses import dataclass
 
 import torch
 
-from ._lib import AttnDesc, GemmDesc, check, lib
+from ._lib import AttnBwdDesc, AttnDesc, GemmDesc, check, lib
 
 
 @dataclass
@@ -60,7 +60,7 @@ def _ru(x, m):
 class _CountingLib:
     """Proxy over the ctypes library that counts the sm_100a kernel launches issued through it (bench.py reports them)."""
 
-    KERNELS = {"rp_gemm": 1, "rp_attn_fwd": 1, "rp_attn_last": 1, "rp_attn_softmax_bwd": 1, "rp_prepare_batch": 2, "rp_embed_fwd": 1,
+    KERNELS = {"rp_gemm": 1, "rp_attn_fwd": 1, "rp_attn_bwd": 1, "rp_attn_last": 1, "rp_attn_softmax_bwd": 1, "rp_prepare_batch": 2, "rp_embed_fwd": 1,
                "rp_embed_bwd": 2, "rp_layernorm_fwd": 1, "rp_layernorm_bwd": 1, "rp_dropout_bwd": 1, "rp_colsum": 1,
                "rp_adam_step": 2, "rp_cast_bf16": 1, "rp_counter_add": 1, "rp_reduce_splits": 1, "rp_ce_head_fwd": 2, "rp_ce_head_bwd": 3,
                "rp_score_topk": 2, "rp_seen_prepare": 1}
@@ -129,6 +129,7 @@ class SasRecEngine:
         self.rng_counter = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self.seed = seed & 0xFFFFFFFFFFFF
         self.training = with_grad
+        self.fused_attn_bwd = (cfg.d // cfg.n_heads) == 64  # fused tcgen05 attention backward (head_dim 64, L <= 256)
         self.fused_ce = True      # single-pass CE forward + dH (guarded on the device by a bound on |logit|)
         self.n_valid_hint = 0     # host estimate of the number of valid targets per step (load balance of the CE head only)
         self._alloc_workspace()
@@ -207,8 +208,10 @@ class SasRecEngine:
             for k in ("mean1", "rstd1", "mean2", "rstd2"):
                 a[k] = torch.zeros(T, **f32)
             if self.with_grad:
-                a["P"] = torch.zeros(BH, self.Lp, self.Lp, **bf)
+                if not self.fused_attn_bwd:
+                    a["P"] = torch.zeros(BH, self.Lp, self.Lp, **bf)
                 a["inv_sum"] = torch.zeros(BH, self.Lp, **f32)
+                a["m2"] = torch.zeros(BH, self.Lp, **f32)
             self.act.append(a)
         self.hc = torch.zeros(T, d, **bf)
         self.meanf = torch.zeros(T, **f32)
@@ -224,7 +227,8 @@ class SasRecEngine:
             self.ce = CEHeadState(T, cfg.n_items, d, dev)
             self.s = {k: torch.zeros(T, d, **bf) for k in ("dhc", "dxa", "dxb", "d_t", "du", "dy", "dh", "d_o", "dQ", "dq_in", "tmp")}
             self.s["dKV"] = torch.zeros(T, 2 * d, **bf)
-            self.s["dpd"] = torch.zeros(BH, self.Lp, self.Lp, **bf)
+            if not self.fused_attn_bwd:
+                self.s["dpd"] = torch.zeros(BH, self.Lp, self.Lp, **bf)
             self.wg_ws = torch.zeros(148 * 4 * d * d, **f32)  # split-K partials of the weight-gradient GEMMs
 
     def _stream(self):
@@ -371,9 +375,10 @@ class SasRecEngine:
             ad.pad_mask = pad.data_ptr()
             ad.out, ad.ldo = a["O"].data_ptr(), d
             if training and self.with_grad:
-                ad.p_save, ad.inv_sum = a["P"].data_ptr(), a["inv_sum"].data_ptr()
+                ad.p_save = None if self.fused_attn_bwd else a["P"].data_ptr()
+                ad.inv_sum, ad.m_save = a["inv_sum"].data_ptr(), a["m2"].data_ptr()
             else:
-                ad.p_save, ad.inv_sum = None, None
+                ad.p_save, ad.inv_sum, ad.m_save = None, None, None
             ad.drop_p, ad.seed, ad.drop_off, ad.seed_ptr = drop, self.seed, self._site(i, 0) << 40, self.rng_counter.data_ptr()
             check(self.lib.rp_attn_fwd(ctypes.byref(ad), self._stream()), "rp_attn_fwd")
             self._gemm(a["O"], w("out_w"), a["h"], T, d, d, bias=f("out_b"), residual=a["q_in"])
@@ -441,23 +446,41 @@ class SasRecEngine:
             self._gemm(s["dh"], w("out_w"), s["d_o"], T, d, d, b_mn=True)
             self._wgrad(s["dh"], a["O"], g("out_w"), d, d)
             self._colsum(s["dh"], g("out_b"))
-            # ---- attention backward (batched over (b, h))
-            KV, Q, P, dpd = a["KV"], a["Q"], a["P"].view(BH * Lp, Lp), s["dpd"].view(BH * Lp, Lp)
-            # dPd = dO . V^T
-            self._gemm(s["d_o"], KV, dpd, L, L, hd, batch=BH, inner=H, a_off=(0, L, 0, 0, 0, hd), b_off=(0, L, 0, d, 0, hd),
-                       c_geom=(Lp, 0, H * Lp * Lp, Lp * Lp))
-            check(self.lib.rp_attn_softmax_bwd(P.data_ptr(), dpd.data_ptr(), a["inv_sum"].data_ptr(), BH, L,
-                                               1.0 / math.sqrt(hd), drop, self.seed, self._site(i, 0) << 40,
-                                               self.rng_counter.data_ptr(), st()), "rp_attn_softmax_bwd")
-            # dQ = dS . K      (A = dS [BH*Lp, Lp] K-major, B = K MN-major)
-            self._gemm(dpd, KV, s["dQ"], L, hd, L, b_mn=True, batch=BH, inner=H, a_off=(0, H * Lp, Lp, 0, 0, 0),
-                       b_off=(0, L, 0, 0, 0, hd), c_geom=(d, 0, L * d, hd))
-            # dK = dS^T . Q    (A = dS MN-major, B = Q MN-major)
-            self._gemm(dpd, Q, s["dKV"], L, hd, L, a_mn=True, b_mn=True, batch=BH, inner=H, a_off=(0, H * Lp, Lp, 0, 0, 0),
-                       b_off=(0, L, 0, 0, 0, hd), c_geom=(2 * d, 0, L * 2 * d, hd))
-            # dV = Pd^T . dO
-            self._gemm(P, s["d_o"], s["dKV"], L, hd, L, a_mn=True, b_mn=True, batch=BH, inner=H,
-                       a_off=(0, H * Lp, Lp, 0, 0, 0), b_off=(0, L, 0, 0, 0, hd), c_geom=(2 * d, d, L * 2 * d, hd))
+            # ---- attention backward
+            KV, Q = a["KV"], a["Q"]
+            if self.fused_attn_bwd:
+                bd = AttnBwdDesc()
+                bd.q, bd.q_rows, bd.q_cols, bd.ldq, bd.q_c0 = Q.data_ptr(), T, d, d, 0
+                bd.k, bd.k_rows, bd.k_cols, bd.ldk, bd.k_c0 = KV.data_ptr(), T, 2 * d, 2 * d, 0
+                bd.v, bd.v_rows, bd.v_cols, bd.ldv, bd.v_c0 = KV.data_ptr(), T, 2 * d, 2 * d, d
+                bd.d_out, bd.do_rows, bd.do_cols, bd.ld_do = s["d_o"].data_ptr(), T, d, d
+                bd.out, bd.ldo = a["O"].data_ptr(), d
+                bd.B, bd.H, bd.L, bd.head_dim = self.B, H, L, hd
+                bd.causal, bd.mask_pad_keys = 1, int(not legacy)
+                bd.pad_mask = self.in_pad.data_ptr()
+                bd.m_save, bd.inv_sum = a["m2"].data_ptr(), a["inv_sum"].data_ptr()
+                bd.dq, bd.ld_dq, bd.dq_c0 = s["dQ"].data_ptr(), d, 0
+                bd.dk, bd.ld_dk, bd.dk_c0 = s["dKV"].data_ptr(), 2 * d, 0
+                bd.dv, bd.ld_dv, bd.dv_c0 = s["dKV"].data_ptr(), 2 * d, d
+                bd.drop_p, bd.seed, bd.drop_off, bd.seed_ptr = drop, self.seed, self._site(i, 0) << 40, self.rng_counter.data_ptr()
+                check(self.lib.rp_attn_bwd(ctypes.byref(bd), st()), "rp_attn_bwd")
+            else:
+                P, dpd = a["P"].view(BH * Lp, Lp), s["dpd"].view(BH * Lp, Lp)
+                # dPd = dO . V^T
+                self._gemm(s["d_o"], KV, dpd, L, L, hd, batch=BH, inner=H, a_off=(0, L, 0, 0, 0, hd), b_off=(0, L, 0, d, 0, hd),
+                           c_geom=(Lp, 0, H * Lp * Lp, Lp * Lp))
+                check(self.lib.rp_attn_softmax_bwd(P.data_ptr(), dpd.data_ptr(), a["inv_sum"].data_ptr(), BH, L,
+                                                   1.0 / math.sqrt(hd), drop, self.seed, self._site(i, 0) << 40,
+                                                   self.rng_counter.data_ptr(), st()), "rp_attn_softmax_bwd")
+                # dQ = dS . K      (A = dS [BH*Lp, Lp] K-major, B = K MN-major)
+                self._gemm(dpd, KV, s["dQ"], L, hd, L, b_mn=True, batch=BH, inner=H, a_off=(0, H * Lp, Lp, 0, 0, 0),
+                           b_off=(0, L, 0, 0, 0, hd), c_geom=(d, 0, L * d, hd))
+                # dK = dS^T . Q    (A = dS MN-major, B = Q MN-major)
+                self._gemm(dpd, Q, s["dKV"], L, hd, L, a_mn=True, b_mn=True, batch=BH, inner=H, a_off=(0, H * Lp, Lp, 0, 0, 0),
+                           b_off=(0, L, 0, 0, 0, hd), c_geom=(2 * d, 0, L * 2 * d, hd))
+                # dV = Pd^T . dO
+                self._gemm(P, s["d_o"], s["dKV"], L, hd, L, a_mn=True, b_mn=True, batch=BH, inner=H,
+                           a_off=(0, H * Lp, Lp, 0, 0, 0), b_off=(0, L, 0, 0, 0, hd), c_geom=(2 * d, d, L * 2 * d, hd))
             # ---- projections
             in_w = w("in_w")
             self._gemm(s["dQ"], in_w[:d], s["dq_in"], T, d, d, b_mn=True, residual=s["dh"])

@@ -11,7 +11,7 @@ from dataclasses import dataclass
 
 import torch
 
-from ._lib import AttnDesc, check
+from ._lib import AttnBwdDesc, AttnDesc, check
 from .engine import SasRecEngine, _CountingLib, _ru
 from ._lib import lib
 
@@ -81,6 +81,7 @@ class Bert4RecEngine(SasRecEngine):
             self.step_count = torch.zeros(1, device=self.dev, dtype=torch.int32)
         self.rng_counter = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self.seed = seed & 0xFFFFFFFFFFFF
+        self.fused_attn_bwd = (cfg.d // cfg.n_heads) == 64
         self.fused_ce = True
         self.n_valid_hint = 0
         self._alloc_bert_workspace()
@@ -158,8 +159,10 @@ class Bert4RecEngine(SasRecEngine):
             for k in ("mean1", "rstd1", "mean2", "rstd2"):
                 a[k] = torch.zeros(T, **f32)
             if self.with_grad:
-                a["P"] = torch.zeros(BH, self.Lp, self.Lp, **bf)
+                if not self.fused_attn_bwd:
+                    a["P"] = torch.zeros(BH, self.Lp, self.Lp, **bf)
                 a["inv_sum"] = torch.zeros(BH, self.Lp, **f32)
+                a["m2"] = torch.zeros(BH, self.Lp, **f32)
             self.act.append(a)
         self.hc = torch.zeros(T, d, **bf)
         self.hq = torch.zeros(self.B, d, **bf)
@@ -171,7 +174,8 @@ class Bert4RecEngine(SasRecEngine):
             self.s = {k: torch.zeros(T, d, **bf) for k in ("dhc", "dxa", "dxb", "dz", "d_t", "dyn", "dy", "d_ao", "d_o", "dxn")}
             self.s["du"] = torch.zeros(T, 4 * d, **bf)
             self.s["dQKV"] = torch.zeros(T, 3 * d, **bf)
-            self.s["dpd"] = torch.zeros(BH, self.Lp, self.Lp, **bf)
+            if not self.fused_attn_bwd:
+                self.s["dpd"] = torch.zeros(BH, self.Lp, self.Lp, **bf)
             self.wg_ws = torch.zeros(148 * 4 * d * d, **f32)  # split-K partials of the weight-gradient GEMMs
 
     # ------------------------------------------------------------------------------------------------ batch
@@ -229,9 +233,10 @@ class Bert4RecEngine(SasRecEngine):
             ad.pad_mask = self.in_pad.data_ptr()
             ad.out, ad.ldo = a["O"].data_ptr(), d
             if training and self.with_grad:
-                ad.p_save, ad.inv_sum = a["P"].data_ptr(), a["inv_sum"].data_ptr()
+                ad.p_save = None if self.fused_attn_bwd else a["P"].data_ptr()
+                ad.inv_sum, ad.m_save = a["inv_sum"].data_ptr(), a["m2"].data_ptr()
             else:
-                ad.p_save, ad.inv_sum = None, None
+                ad.p_save, ad.inv_sum, ad.m_save = None, None, None
             ad.drop_p, ad.seed, ad.drop_off, ad.seed_ptr = drop, self.seed, self._bsite(i, 0) << 40, rng
             check(self.lib.rp_attn_fwd(ctypes.byref(ad), self._stream()), "rp_attn_fwd")
             # y = x + drop(O Wo^T + bo)
@@ -311,19 +316,37 @@ class Bert4RecEngine(SasRecEngine):
             self._colsum(d_ao, g("out_b"))
             self._gemm(d_ao, w("out_w"), s["d_o"], T, d, d, b_mn=True)
             # ---- attention backward, Q/K/V are column slices of QKV
-            QKV, P, dpd = a["QKV"], a["P"].view(BH * Lp, Lp), s["dpd"].view(BH * Lp, Lp)
-            self._gemm(s["d_o"], QKV, dpd, L, L, hd, batch=BH, inner=H, a_off=(0, L, 0, 0, 0, hd), b_off=(0, L, 0, 2 * d, 0, hd),
-                       c_geom=(Lp, 0, H * Lp * Lp, Lp * Lp))
-            check(self.lib.rp_attn_softmax_bwd(P.data_ptr(), dpd.data_ptr(), a["inv_sum"].data_ptr(), BH, L,
-                                               1.0 / math.sqrt(hd), drop, self.seed, self._bsite(i, 0) << 40, rng, st()),
-                  "rp_attn_softmax_bwd")
-            dq = s["dQKV"]
-            self._gemm(dpd, QKV, dq, L, hd, L, b_mn=True, batch=BH, inner=H, a_off=(0, H * Lp, Lp, 0, 0, 0),
-                       b_off=(0, L, 0, d, 0, hd), c_geom=(3 * d, 0, L * 3 * d, hd))                      # dQ = dS . K
-            self._gemm(dpd, QKV, dq, L, hd, L, a_mn=True, b_mn=True, batch=BH, inner=H, a_off=(0, H * Lp, Lp, 0, 0, 0),
-                       b_off=(0, L, 0, 0, 0, hd), c_geom=(3 * d, d, L * 3 * d, hd))                      # dK = dS^T . Q
-            self._gemm(P, s["d_o"], dq, L, hd, L, a_mn=True, b_mn=True, batch=BH, inner=H, a_off=(0, H * Lp, Lp, 0, 0, 0),
-                       b_off=(0, L, 0, 0, 0, hd), c_geom=(3 * d, 2 * d, L * 3 * d, hd))                  # dV = Pd^T . dO
+            QKV, dq = a["QKV"], s["dQKV"]
+            if self.fused_attn_bwd:
+                bd = AttnBwdDesc()
+                for nm, c0 in (("q", 0), ("k", d), ("v", 2 * d)):
+                    setattr(bd, nm, QKV.data_ptr())
+                    setattr(bd, nm + "_rows", T); setattr(bd, nm + "_cols", 3 * d); setattr(bd, "ld" + nm, 3 * d)
+                    setattr(bd, nm + "_c0", c0)
+                bd.d_out, bd.do_rows, bd.do_cols, bd.ld_do = s["d_o"].data_ptr(), T, d, d
+                bd.out, bd.ldo = a["O"].data_ptr(), d
+                bd.B, bd.H, bd.L, bd.head_dim = self.B, H, L, hd
+                bd.causal, bd.mask_pad_keys = 0, 1
+                bd.pad_mask = self.in_pad.data_ptr()
+                bd.m_save, bd.inv_sum = a["m2"].data_ptr(), a["inv_sum"].data_ptr()
+                bd.dq, bd.ld_dq, bd.dq_c0 = dq.data_ptr(), 3 * d, 0
+                bd.dk, bd.ld_dk, bd.dk_c0 = dq.data_ptr(), 3 * d, d
+                bd.dv, bd.ld_dv, bd.dv_c0 = dq.data_ptr(), 3 * d, 2 * d
+                bd.drop_p, bd.seed, bd.drop_off, bd.seed_ptr = drop, self.seed, self._bsite(i, 0) << 40, rng
+                check(self.lib.rp_attn_bwd(ctypes.byref(bd), st()), "rp_attn_bwd")
+            else:
+                P, dpd = a["P"].view(BH * Lp, Lp), s["dpd"].view(BH * Lp, Lp)
+                self._gemm(s["d_o"], QKV, dpd, L, L, hd, batch=BH, inner=H, a_off=(0, L, 0, 0, 0, hd), b_off=(0, L, 0, 2 * d, 0, hd),
+                           c_geom=(Lp, 0, H * Lp * Lp, Lp * Lp))
+                check(self.lib.rp_attn_softmax_bwd(P.data_ptr(), dpd.data_ptr(), a["inv_sum"].data_ptr(), BH, L,
+                                                   1.0 / math.sqrt(hd), drop, self.seed, self._bsite(i, 0) << 40, rng, st()),
+                      "rp_attn_softmax_bwd")
+                self._gemm(dpd, QKV, dq, L, hd, L, b_mn=True, batch=BH, inner=H, a_off=(0, H * Lp, Lp, 0, 0, 0),
+                           b_off=(0, L, 0, d, 0, hd), c_geom=(3 * d, 0, L * 3 * d, hd))                      # dQ = dS . K
+                self._gemm(dpd, QKV, dq, L, hd, L, a_mn=True, b_mn=True, batch=BH, inner=H, a_off=(0, H * Lp, Lp, 0, 0, 0),
+                           b_off=(0, L, 0, 0, 0, hd), c_geom=(3 * d, d, L * 3 * d, hd))                      # dK = dS^T . Q
+                self._gemm(P, s["d_o"], dq, L, hd, L, a_mn=True, b_mn=True, batch=BH, inner=H, a_off=(0, H * Lp, Lp, 0, 0, 0),
+                           b_off=(0, L, 0, 0, 0, hd), c_geom=(3 * d, 2 * d, L * 3 * d, hd))                  # dV = Pd^T . dO
             self._gemm(dq, w("in_w"), s["dxn"], T, d, 3 * d, b_mn=True)
             self._wgrad(dq, a["xn"], g("in_w"), 3 * d, d)
             self._colsum(dq, g("in_b"))

@@ -214,17 +214,6 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e = float(t.item())
     h2d = sum(h[0].numel() * h[0].element_size() for h in host)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    seq_s = world * B * K / ms * 1e3
-    seq_s_e2e = world * B * K / ms_e2e * 1e3
-    fl_seq = train_flops_per_seq(L, d, c["blocks"], I, valid_per_seq)
-    step_tflops = seq_s / world * fl_seq / 1e12
-
-    # ---- roofline of the dominant kernels: the three tcgen05 CE-head kernels, timed live with CUDA events (standalone,
-    # same buffers as the last step; each launch streams > L2 worth of operands through TMEM/SMEM)
     def time_kernel(fn, iters=10):
         fn()
         torch.cuda.synchronize()
@@ -236,6 +225,68 @@ def run_ours(args):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / iters
 
+    # ---- scoring leg (every rank scores its own contiguous shard of the users, no collective: SURVEY 8e):
+    # body forward (eval, last block evaluated for the last position only) + fused score/seen-mask/top-K at |I| = 500K
+    sc = SCORE_CFG
+    scoring = None
+    if not args.no_scoring:
+        from replay_b200.trainer import user_shard
+
+        torch.cuda.empty_cache()
+        Bu = sc["users_per_call"]
+        cfg_s = EncoderConfig(n_items=sc["n_items"], d=sc["d"], n_heads=2, n_blocks=2, max_len=sc["seq_len"], variant="new")
+        es = SasRecEngine(cfg_s, Bu, sc["seq_len"], dev, seed=7, with_grad=False)
+        n_calls = 6
+        lo, hi = user_shard(world * Bu * 2, rank, world)  # 2 distinct calls' worth of users per rank
+        uid, upm, _, _ = make_sequences(world * Bu * 2, sc["n_items"], sc["seq_len"], seed=7)
+        uid, upm = uid[lo:hi].view(2, Bu, -1).to(dev), upm[lo:hi].view(2, Bu, -1).to(dev)
+        tab = es.params16["item_emb"][: sc["n_items"]]
+
+        def predict(i):
+            j = i % 2
+            es.set_batch(uid[j], upm[j])
+            hq = es.forward_last_hidden()
+            seen = ops.seen_prepare(uid[j], sc["n_items"])
+            return ops.score_topk(hq, tab, sc["k"], seen)
+
+        for i in range(3):
+            predict(i)
+        barrier()
+        e0.record()
+        for i in range(n_calls):
+            predict(i)
+        e1.record()
+        barrier()
+        tp = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        ms_p = float(tp.item()) / n_calls
+        if rank == 0:
+            seen = ops.seen_prepare(uid[0], sc["n_items"])
+            hq = es.hq
+            t_head = time_kernel(lambda: ops.score_topk(hq, tab, sc["k"], seen))
+            head_flops = 2.0 * Bu * sc["n_items"] * sc["d"]
+            scoring = {
+                "metric": "sasrec_predict_topk10_users_per_s", "value": world * Bu / ms_p * 1e3, "unit": "users/s", "n_gpus": world,
+                "config": {"workload": "SASRec predict(): body fwd + fused score+seen-filter+top-10, users sharded over the GPUs",
+                           **sc},
+                "ms_per_call": ms_p,
+                "roofline": {"bound": "tensor", "kernel": "score_topk_kernel", "achieved": head_flops / (t_head * 1e-3) / 1e12,
+                             "peak": PK["tc_burst"], "unit": "TFLOP/s", "frac": head_flops / (t_head * 1e-3) / 1e12 / PK["tc_burst"],
+                             "head_ms": t_head, "head_users_per_s": Bu / t_head * 1e3, "traffic": None},
+            }
+        del es
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    seq_s = world * B * K / ms * 1e3
+    seq_s_e2e = world * B * K / ms_e2e * 1e3
+    fl_seq = train_flops_per_seq(L, d, c["blocks"], I, valid_per_seq)
+    step_tflops = seq_s / world * fl_seq / 1e12
+
+    # ---- roofline of the dominant kernels: the three tcgen05 CE-head kernels, timed live with CUDA events (standalone,
+    # same buffers as the last step; each launch streams > L2 worth of operands through TMEM/SMEM)
     n_valid = int(eng.n_valid.item())
     table16 = eng.params16["item_emb"][:I]
     t_fwd = time_kernel(lambda: ops.ce_head_fwd(eng.ce, eng.hc, table16, eng.labels_c, eng.n_valid, d_hc=eng.s["dhc"],
@@ -257,48 +308,6 @@ def run_ours(args):
                    "executed_tflops": n_exec * gemm_flops / (ce_ms * 1e-3) / 1e12, "fused_fwd_dh": bool(eng.fused_ce),
                    "share_of_step": ce_ms / (ms / K)},
     }
-    # ---- scoring leg: body forward (eval) + fused score/seen-mask/top-K at |I| = 500K
-    sc = SCORE_CFG
-    scoring = None
-    if not args.no_scoring:
-        torch.cuda.empty_cache()
-        Bu = sc["users_per_call"]
-        cfg_s = EncoderConfig(n_items=sc["n_items"], d=sc["d"], n_heads=2, n_blocks=2, max_len=sc["seq_len"], variant="new")
-        es = SasRecEngine(cfg_s, Bu, sc["seq_len"], dev, seed=7, with_grad=False)
-        uid, upm, _, _ = make_sequences(Bu * 2, sc["n_items"], sc["seq_len"], seed=7)
-        uid, upm = uid.view(2, Bu, -1).to(dev), upm.view(2, Bu, -1).to(dev)
-        tab = es.params16["item_emb"][: sc["n_items"]]
-
-        def predict(i):
-            j = i % 2
-            es.set_batch(uid[j], upm[j])
-            hq = es.forward_last_hidden()
-            seen = ops.seen_prepare(uid[j], sc["n_items"])
-            return ops.score_topk(hq, tab, sc["k"], seen)
-
-        for i in range(3):
-            predict(i)
-        torch.cuda.synchronize()
-        e0.record()
-        n_calls = 6
-        for i in range(n_calls):
-            predict(i)
-        e1.record()
-        torch.cuda.synchronize()
-        ms_p = e0.elapsed_time(e1) / n_calls
-        seen = ops.seen_prepare(uid[0], sc["n_items"])
-        hq = es.hq
-        t_head = time_kernel(lambda: ops.score_topk(hq, tab, sc["k"], seen))
-        head_flops = 2.0 * Bu * sc["n_items"] * sc["d"]
-        scoring = {
-            "metric": "sasrec_predict_topk10_users_per_s", "value": Bu / ms_p * 1e3, "unit": "users/s", "n_gpus": 1,
-            "config": {"workload": "SASRec predict(): body fwd + fused score+seen-filter+top-10", **sc},
-            "ms_per_call": ms_p,
-            "roofline": {"bound": "tensor", "kernel": "score_topk_kernel", "achieved": head_flops / (t_head * 1e-3) / 1e12,
-                         "peak": PK["tc_burst"], "unit": "TFLOP/s", "frac": head_flops / (t_head * 1e-3) / 1e12 / PK["tc_burst"],
-                         "head_ms": t_head, "head_users_per_s": Bu / t_head * 1e3, "traffic": None},
-        }
-        del es
     # ---- CPU baseline (bounded sample, rank 0)
     cpu = None
     if not args.no_cpu:

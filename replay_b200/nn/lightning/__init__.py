@@ -2,5 +2,6 @@
 seen-items postprocessor (module.py:13-123, optimizer.py:24-60, callback/predictions_callback.py:29-163,
 postprocessor/seen_items.py:8-83)."""
 from .callback import PandasTopItemsCallback, TopItemsCallbackBase, TorchTopItemsCallback  # noqa: F401
+from .metrics import ComputeMetricsCallback, RankingMetrics  # noqa: F401
 from .module import LightningModule, OptimizerFactory  # noqa: F401
 from .postprocessor import SeenItemsFilter  # noqa: F401

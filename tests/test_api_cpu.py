@@ -167,3 +167,25 @@ def test_bert_state_dict_keys_match_reference(golden_dir):
         if tying:
             ours |= {"_head._item_embedder." + k[len("item_embedder."):] for k in ours if k.startswith("item_embedder.")}
         assert ours == ref, (ours ^ ref)
+
+
+def test_ranking_metrics_match_reference_definitions():
+    """RankingMetrics vs a direct evaluation of TorchMetricsBuilder's formulas (torch_metrics_builder.py:305-393) on a
+    hand-checkable case."""
+    import math
+
+    from replay_b200.nn.lightning import RankingMetrics
+
+    pred = torch.tensor([[5, 3, 9, 1], [7, 8, 2, 0]])
+    gt = torch.tensor([[3, 1, -1], [4, -1, -1]])
+    m = RankingMetrics(("recall", "precision", "ndcg", "map", "mrr"), (2, 4))
+    m.add_prediction(pred, gt)
+    r = m.get_metrics()
+    # user 0: hits at ranks 2 and 4 (|gt| = 2); user 1: no hit
+    assert abs(r["recall@2"] - (0.5 + 0) / 2) < 1e-6 and abs(r["recall@4"] - (1.0 + 0) / 2) < 1e-6
+    assert abs(r["precision@4"] - (0.5 + 0) / 2) < 1e-6
+    dcg4 = 1 / math.log2(3) + 1 / math.log2(5)
+    idcg2 = 1 / math.log2(2) + 1 / math.log2(3)
+    assert abs(r["ndcg@4"] - (dcg4 / idcg2) / 2) < 1e-6
+    assert abs(r["mrr@4"] - (0.5 + 0) / 2) < 1e-6
+    assert abs(r["map@4"] - ((1 / 2 + 2 / 4) / 2) / 2) < 1e-6

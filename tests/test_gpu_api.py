@@ -144,3 +144,60 @@ def test_legacy_module_predict(golden_dir, cuda):
                             "positive_labels": torch.from_numpy(z["labels"]).cuda(),
                             "target_padding_mask": torch.from_numpy(z["target_mask"]).cuda()}, 0)
     assert abs(float(loss) - float(z["train_loss"])) < 5e-3 * float(z["train_loss"])
+
+
+def test_end_to_end_plumbing_config1(cuda):
+    """BASELINE configs[0] shape (L=50, d=64, |I|=4K, 1K users): host batch layout -> LightningModule.training_step (fused
+    fwd+bwd+Adam) for a few epochs -> predict with SeenItemsFilter + fused top-10 -> validation metrics callback.
+    The data is a noisy 'next item = previous + 1' chain, so a working pipeline must lift recall@10 far above chance."""
+    from replay_b200.data import sasrec_prediction_batch, sasrec_training_batch, to_new_path_batch
+    from replay_b200.nn.lightning import (ComputeMetricsCallback, LightningModule, OptimizerFactory, SeenItemsFilter,
+                                          TorchTopItemsCallback)
+    from replay_b200.nn.sequential import SasRec
+    from replay_b200.schema import TensorFeatureInfo, TensorSchema
+
+    n_items, d, L, U, B = 4000, 64, 50, 1024, 128
+    g = torch.Generator().manual_seed(0)
+    seqs = []
+    for u in range(U):
+        n = int(torch.randint(12, 70, (1,), generator=g))
+        start = int(torch.randint(0, n_items, (1,), generator=g))
+        s = [(start + i) % n_items for i in range(n)]
+        seqs.append(s)
+    train = [s[:-1] for s in seqs]          # hold out the last item
+    truth = torch.tensor([[s[-1]] for s in seqs])
+    model = SasRec.from_params(TensorSchema(TensorFeatureInfo("item_id", n_items, n_items, d)), embedding_dim=d, num_heads=1,
+                               num_blocks=2, max_sequence_length=L, dropout=0.1, seed=3)
+    lm = LightningModule(model, optimizer_factory=OptimizerFactory(learning_rate=3e-3))
+    model.train()
+    first = last = None
+    for epoch in range(6):
+        perm = torch.randperm(U, generator=g)
+        for i in range(0, U, B):
+            idx = perm[i:i + B].tolist()
+            b = to_new_path_batch(sasrec_training_batch([train[j] for j in idx], L, n_items, query_ids=idx), with_seen=False)
+            b = {k: (v.cuda() if torch.is_tensor(v) else {kk: vv.cuda() for kk, vv in v.items()}) for k, v in b.items()}
+            loss = float(lm.training_step(b, i))
+            first = loss if first is None else first
+            last = loss
+    assert last < first - 2.0, (first, last)
+    # predict + validation metrics
+    model.eval()
+    cb = TorchTopItemsCallback(10, "query_id", "item_id", postprocessors=[SeenItemsFilter(n_items, "seen_ids")])
+    mc = ComputeMetricsCallback(metrics=("recall", "ndcg"), ks=(10,), postprocessors=[SeenItemsFilter(n_items, "seen_ids")])
+    cb.on_predict_epoch_start(None, lm)
+    mc.on_validation_epoch_start(None, lm)
+    for i in range(0, U, B):
+        idx = list(range(i, min(U, i + B)))
+        b = to_new_path_batch(sasrec_prediction_batch([train[j] for j in idx], L, n_items, query_ids=idx))
+        b = {k: (v.cuda() if torch.is_tensor(v) else {kk: vv.cuda() for kk, vv in v.items()}) for k, v in b.items()}
+        b["ground_truth"] = truth[idx].cuda()
+        cb.on_predict_batch_end(None, lm, lm.predict_step(b, i), b, i)
+        mc.on_validation_batch_end(None, lm, None, b, i)
+    q, items, scores = cb.get_result()
+    assert q.tolist() == list(range(U)) and items.shape == (U, 10)
+    m = mc.on_validation_epoch_end(None, lm)
+    hit = (items == truth).any(1).float().mean().item()
+    assert abs(hit - m["recall@10"]) < 1e-6
+    assert m["recall@10"] > 0.5, m       # chance level is 10 / 4000
+    assert (scores[:, :-1] >= scores[:, 1:]).all()

@@ -42,7 +42,9 @@ struct AttnBwdParams {
 
 static constexpr float kL2e = 1.4426950408889634f;
 
-__global__ void __launch_bounds__(160, 1)
+static constexpr int kAbThreads = 32 + 8 * 32;  // issuer warp + 8 softmax warps (lane quarter x 64-query column half)
+
+__global__ void __launch_bounds__(kAbThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnBwdParams p) {
   constexpr int HD = 64;
@@ -67,7 +69,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (threadIdx.x == 0) {
     mbar_init(&bar_load, 1);
     mbar_init(&bar_s, 1);
-    mbar_init(&bar_p, 4);
+    mbar_init(&bar_p, 8);
     mbar_init(&bar_acc, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmQ);
@@ -78,7 +80,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   // row statistics of this (sequence, head): m, 1/sum from the forward, delta from O and dO
   if (threadIdx.x >= 32) {
-    for (int i = threadIdx.x - 32; i < 256; i += 128) {
+    for (int i = threadIdx.x - 32; i < 256; i += 256) {
       float m = 0.f, inv = 0.f, dl = 0.f;
       if (i < L) {
         m = p.m_save[(size_t)bz * p.Lp + i];
@@ -148,8 +150,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint32_t ds0 = smem_u32(sdS);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {  // contraction over the 128 queries of this tile, 16 at a time
-            umma_ts(t_dv, t_st + ks * 8, umma_desc_sw128(g0 + ks * 2048, 16, 1024), id_kv, kv_started || ks != 0);
-            umma_ts(t_dk, t_dpt + ks * 8, umma_desc_sw128(q0 + ks * 2048, 16, 1024), id_kv, kv_started || ks != 0);
+            const uint32_t acol = (ks >> 2) * 64 + (ks & 3) * 8;  // queries 0-63 packed at +0, 64-127 at +64
+            umma_ts(t_dv, t_st + acol, umma_desc_sw128(g0 + ks * 2048, 16, 1024), id_kv, kv_started || ks != 0);
+            umma_ts(t_dk, t_dpt + acol, umma_desc_sw128(q0 + ks * 2048, 16, 1024), id_kv, kv_started || ks != 0);
           }
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)    // contraction over the 128 keys of this tile
@@ -167,8 +170,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {
-    // ------------------------------------------------ 4 warps: thread = key row (then query row for dQ)
-    const int quarter = warp & 3;
+    // ------------------------------------------------ 8 warps: thread = key row (then query row for dQ) x column half
+    const int quarter = warp & 3, cgp = (warp - 1) >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const float sl2 = p.scale * kL2e;
@@ -186,7 +189,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         ++np;
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
+        for (int c = cgp * 64; c < cgp * 64 + 64; c += 32) {
           uint32_t rs[32], rd[32];
           tmem_ld32(t_st + lane_base + c, rs);
           tmem_ld32(t_dpt + lane_base + c, rd);
@@ -212,8 +215,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             pk_p[q >> 1] = pack_bf16(pd2[0], pd2[1]);
             pk_s[q >> 1] = pack_bf16(ds2[0], ds2[1]);
           }
-          tmem_st16(t_st + lane_base + (c >> 1), pk_p);    // Pd^T over the consumed S^T columns
-          tmem_st16(t_dpt + lane_base + (c >> 1), pk_s);   // dS^T over the consumed dP^T columns
+          // bf16 operands go into the first half of THIS warp's own (already consumed) 64 columns
+          tmem_st16(t_st + lane_base + cgp * 64 + ((c & 63) >> 1), pk_p);    // Pd^T over S^T
+          tmem_st16(t_dpt + lane_base + cgp * 64 + ((c & 63) >> 1), pk_s);   // dS^T over dP^T
           // dS^T also to shared memory as the MN-major A operand of dQ: row = key (K index), 64-query chunks
           uint8_t* dst = sdS + (c >> 6) * 16384;
 #pragma unroll
@@ -233,8 +237,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&bar_acc, acc_it & 1);
       tc_fence_after();
       ++acc_it;
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {
+      {
+        const int which = cgp;  // column-half 0 drains dK, column-half 1 drains dV
         const uint32_t src = (which == 0 ? t_dk : t_dv) + lane_base;
         __nv_bfloat16* outp = which == 0 ? p.dK + ((size_t)b * L + j) * p.ld_dk + p.dk_c0 + h * HD
                                          : p.dV + ((size_t)b * L + j) * p.ld_dv + p.dv_c0 + h * HD;
@@ -263,8 +267,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ---- dQ: all pairs done (the last bar_acc wait above ordered every MMA); thread = query row
     for (int qt = 0; qt < n_t; ++qt) {
       const int i = qt * 128 + row;
-#pragma unroll
-      for (int c = 0; c < HD; c += 32) {
+      {
+        const int c = cgp * 32;
         uint32_t r[32];
         tmem_ld32(t_dq + qt * HD + lane_base + c, r);
         tmem_ld_wait();
@@ -338,7 +342,7 @@ RP_API int rp_attn_bwd(const rp_attn_bwd_desc* a, void* stream_) {
   if ((rc = make_tmap_bf16(&tmdO, a->d_out, a->do_rows, a->do_cols, a->ld_do, 128)) != RP_OK) return rc;
   const int smem = 10 * 128 * 128 + 1024;
   RP_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  attn_bwd_kernel<<<a->B * a->H, 160, smem, stream>>>(tmQ, tmK, tmV, tmdO, p);
+  attn_bwd_kernel<<<a->B * a->H, kAbThreads, smem, stream>>>(tmQ, tmK, tmV, tmdO, p);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }

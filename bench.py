@@ -214,6 +214,39 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e = float(t.item())
     h2d = sum(h[0].numel() * h[0].element_size() for h in host)
+    # ---- same step fed by device-side batch construction: histories resident in HBM as CSR, one rp_build_batch launch
+    # per step cuts / left-pads / shifts the windows of B randomly drawn users, loss read back every step
+    dev_batches = None
+    if not args.no_device_batches:
+        from replay_b200.device_data import DeviceSequenceStore
+        from replay_b200.synthetic import make_histories
+
+        n_hist = 65536
+        off_h, items_h = make_histories(n_hist, I, seed=1234 + rank)
+        store = DeviceSequenceStore(offsets=off_h.numpy(), items=items_h.numpy(), device=dev)
+        picks = torch.randint(0, n_hist, (n_batches, B), generator=torch.Generator().manual_seed(rank), dtype=torch.int32).to(dev)
+
+        def step_store(i):
+            b = store.sasrec_training_batch(picks[i % n_batches], L, I)
+            loss = tr.step(b["feature_tensor"]["item_id"], b["padding_mask"], b["positive_labels"], b["target_padding_mask"])
+            return float(loss[0].item())
+
+        for i in range(2):
+            step_store(i)
+        barrier()
+        e0.record()
+        for i in range(K):
+            step_store(i)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_batches = {"value": world * B * K / float(t.item()) * 1e3, "unit": "seq/s", "ms_per_step": float(t.item()) / K,
+                       "histories_per_gpu": n_hist, "store_bytes": int(items_h.numel() * 4 + off_h.numel() * 8),
+                       "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
+                       "note": "batches cut on the GPU from the HBM-resident CSR history store (rp_build_batch), no host input"}
+        del store
     def time_kernel(fn, iters=10):
         fn()
         torch.cuda.synchronize()
@@ -324,6 +357,7 @@ def run_ours(args):
                    "parallelism": f"dp{world}", "valid_targets_per_seq": valid_per_seq, "cuda_graph": not args.no_graph},
         "e2e": {"value": seq_s_e2e, "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / K},
+        "e2e_device_batches": dev_batches,
         "gpu_launches": (tr.launches_per_step or 0) * K,
         "clocks": clocks,
         "roofline": roof,
@@ -348,6 +382,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-scoring", action="store_true")
+    ap.add_argument("--no-device-batches", action="store_true", help="skip the device-side batch construction leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -236,6 +236,30 @@ int rp_cast_bf16(const float* src, void* dst, long long n, void* stream);
 int rp_counter_add(unsigned long long* counter, unsigned long long inc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Device-side batch construction.  All histories are resident in HBM as CSR: offsets [n_seq+1] int64,
+ * items [offsets[n_seq]] int32.  One call builds B rows of a [B, L] batch: row b is the window of history seq_index[b]
+ * starting at seq_offset[b] (NULL: the LAST L(+1) items), left-padded with pad_value.  Replaces the per-sample host path
+ *   TorchSequentialDataset.__getitem__/_pad_sequence/_generate_padding_mask  replay/data/nn/torch_sequential_dataset.py:69-136
+ *   SasRecTrainingDataset.__getitem__ (window L+1, inputs [:-1], labels [1:])  replay/models/nn/sequential/sasrec/dataset.py:104-126
+ *   Bert4RecUniformMasker.mask + Bert4RecTrainingDataset.__getitem__          .../bert4rec/dataset.py:71-92,163-177
+ *   _shift_features (predict: roll left, last = pad, token/pad masks)         .../bert4rec/dataset.py:322-351
+ * and the default collate.  mode: RP_BATCH_SASREC_TRAIN -> ids, pad_mask, labels, aux_mask = target_padding_mask;
+ * RP_BATCH_PREDICT -> ids, pad_mask; RP_BATCH_BERT_TRAIN -> ids (= inputs), pad_mask, labels (= positive_labels),
+ * aux_mask = token_mask (0 = masked) drawn as (u * pad) >= mask_prob with the reference's two corner-case fix-ups, u from
+ * `uniforms` [B, L] when given (bit-exact against the reference masker fed the same numbers) else Philox4x32-10 keyed by
+ * (seed, draw0 + b); RP_BATCH_BERT_PREDICT -> shifted ids, pad_mask, aux_mask = token_mask.
+ * query_out [B] (optional) = query_ids[seq_index[b]] (or the index itself when query_ids is NULL).
+ * ------------------------------------------------------------------------------------------------------------- */
+#define RP_BATCH_SASREC_TRAIN 0
+#define RP_BATCH_PREDICT 1
+#define RP_BATCH_BERT_TRAIN 2
+#define RP_BATCH_BERT_PREDICT 3
+int rp_build_batch(const int64_t* offsets, const int32_t* items, long long n_seq, const int32_t* seq_index,
+                   const int32_t* seq_offset, int B, int L, int mode, int pad_value, float mask_prob, const float* uniforms,
+                   unsigned long long seed, unsigned long long draw0, const int64_t* query_ids, int64_t* ids,
+                   uint8_t* pad_mask, int64_t* labels, uint8_t* aux_mask, int64_t* query_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Bring-up self test of the tcgen05 operand encodings (used by tests/, not by the product path).
  * A, B: bf16 [128,128]; D: fp32 [128,128].  mode bit0: B given as Bt[K,N]; bit1: A staged through TMEM;
  * bit2: A given as At[K,M].  D = A . B^T in every mode.

@@ -209,6 +209,87 @@ def gen_seen_filter_known_answers():
     print("wrote seen_filter_known")
 
 
+def gen_dataset_layout():
+    """The reference's per-sample dataset classes run on a tiny history store (sliding windows, short / empty-ish /
+    over-long histories) -> tests/golden/dataset_layout.npz.  The BERT masker is fed a seeded generator; the same uniform
+    draws are regenerated here and stored so the restatement and the device kernel can be checked bit-exactly."""
+    from replay.models.nn.sequential.bert4rec.dataset import (Bert4RecPredictionDataset, Bert4RecTrainingDataset,
+                                                              Bert4RecUniformMasker)
+    from replay.models.nn.sequential.sasrec.dataset import SasRecPredictionDataset, SasRecTrainingDataset
+
+    n_items, L, step, prob = 40, 6, 2, 0.3
+    sch = schema(n_items, 8, n_items)
+    rng = np.random.default_rng(5)
+    lens = [1, 2, 3, 6, 7, 8, 13, 20, 5, 6, 1, 30]
+    seqs = [rng.integers(0, n_items, n).astype(np.int64) for n in lens]
+
+    class Store:
+        schema = sch
+
+        def __len__(self):
+            return len(seqs)
+
+        def get_query_id(self, i):
+            return 1000 + 3 * i
+
+        def get_sequence_length(self, i):
+            return len(seqs[i])
+
+        def get_sequence(self, i, name):
+            return seqs[i]
+
+        def get_max_sequence_length(self):
+            return max(lens)
+
+    ds = Store()
+    out = {"lengths": np.asarray(lens), "items": np.concatenate(seqs), "L": L, "step": step, "mask_prob": prob,
+           "pad": n_items, "query_ids": np.asarray([1000 + 3 * i for i in range(len(seqs))])}
+
+    def stack(samples, path):
+        def get(s):
+            for k in path:
+                s = s[k]
+            return s.numpy()
+        return np.stack([get(s) for s in samples])
+
+    for tag, st in (("slide", step), ("last", None)):
+        t = SasRecTrainingDataset(ds, max_sequence_length=L, sliding_window_step=st)
+        smp = [t[i] for i in range(len(t))]
+        out[f"sas_{tag}_index"] = np.asarray(t._inner._index2sequence_map)
+        out[f"sas_{tag}_query"] = stack(smp, ["query_id"])[:, 0]
+        out[f"sas_{tag}_ids"] = stack(smp, ["feature_tensor", "item_id"])
+        out[f"sas_{tag}_pad"] = stack(smp, ["padding_mask"])
+        out[f"sas_{tag}_labels"] = stack(smp, ["positive_labels"])
+        out[f"sas_{tag}_tmask"] = stack(smp, ["target_padding_mask"])
+    p = SasRecPredictionDataset(ds, max_sequence_length=L)
+    smp = [p[i] for i in range(len(p))]
+    out["pred_ids"] = stack(smp, ["feature_tensor", "item_id"])
+    out["pred_pad"] = stack(smp, ["padding_mask"])
+
+    for tag, st in (("slide", step), ("last", None)):
+        bt = Bert4RecTrainingDataset(ds, L, sliding_window_step=st,
+                                     custom_masker=Bert4RecUniformMasker(prob, torch.Generator().manual_seed(21)))
+        smp = [bt[i] for i in range(len(bt))]
+        g2 = torch.Generator().manual_seed(21)
+        out[f"bert_{tag}_uniforms"] = np.stack([torch.rand(L, dtype=torch.float32, generator=g2).numpy() for _ in smp])
+        out[f"bert_{tag}_index"] = np.asarray(bt._inner._index2sequence_map)
+        out[f"bert_{tag}_ids"] = stack(smp, ["inputs", "item_id"])
+        out[f"bert_{tag}_pad"] = stack(smp, ["pad_mask"])
+        out[f"bert_{tag}_tok"] = stack(smp, ["token_mask"])
+        out[f"bert_{tag}_labels"] = stack(smp, ["positive_labels"])
+    # corner cases of the masker: nothing masked (prob 0 -> last token masked), everything masked (prob > 1)
+    for tag, pr in (("p0", 0.0), ("p2", 2.0)):
+        bt = Bert4RecTrainingDataset(ds, L, custom_masker=Bert4RecUniformMasker(pr, torch.Generator().manual_seed(22)))
+        out[f"bert_{tag}_tok"] = stack([bt[i] for i in range(len(bt))], ["token_mask"])
+    bp = Bert4RecPredictionDataset(ds, L)
+    smp = [bp[i] for i in range(len(bp))]
+    out["bertpred_ids"] = stack(smp, ["inputs", "item_id"])
+    out["bertpred_pad"] = stack(smp, ["pad_mask"])
+    out["bertpred_tok"] = stack(smp, ["token_mask"])
+    np.savez_compressed(os.path.join(OUT, "dataset_layout.npz"), **out)
+    print("wrote dataset_layout", {k: np.asarray(v).shape for k, v in out.items() if k.endswith("_ids")})
+
+
 if __name__ == "__main__":
     # shapes respect the CUDA path's tile constraints: hidden in {64,128,256,512}, head_dim in {64,128}
     gen_new_sasrec("tiny", B=6, L=16, d=64, H=1, n_items=300, n_blocks=2, seed=11)
@@ -217,3 +298,4 @@ if __name__ == "__main__":
     gen_bert4rec("tiny", B=6, L=16, d=64, H=1, n_items=300, n_blocks=2, seed=14, tying=False)
     gen_bert4rec("tiny_tied", B=6, L=16, d=64, H=1, n_items=300, n_blocks=2, seed=15, tying=True)
     gen_seen_filter_known_answers()
+    gen_dataset_layout()

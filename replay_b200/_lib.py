@@ -74,6 +74,7 @@ def lib():
     _sig(L.rp_bert_embed_bwd, c_int, [P, P, P, P, c_int, c_int, c_int, c_float, U64, U64, P, P, P, P, P])
     _sig(L.rp_attn_last, c_int, [P, P, P, LL, LL, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P])
     _sig(L.rp_gather_rows, c_int, [P, P, c_int, P, c_int, P, c_int, P])
+    _sig(L.rp_build_batch, c_int, [P, P, LL, P, P, c_int, c_int, c_int, c_int, c_float, P, U64, U64, P, P, P, P, P, P, P])
     for name, restype, argtypes in _EXTRA_SIGS:
         _sig(getattr(L, name), restype, argtypes)
     _lib = L

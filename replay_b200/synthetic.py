@@ -25,3 +25,16 @@ def make_sequences(n_users: int, n_items: int, seq_len: int, seed: int = 1234, p
     win[real] = items
     msk[real] = True
     return win[:, :-1].contiguous(), msk[:, :-1].contiguous(), win[:, 1:].contiguous(), msk[:, 1:].contiguous()
+
+
+def make_histories(n_users: int, n_items: int, seed: int = 1234):
+    """Full (un-windowed) histories as CSR: (offsets int64 [U+1], items int64 [sum n_u]) on the CPU, same length and
+    popularity model as ``make_sequences`` - the input of the device-side batch construction (replay_b200.device_data)."""
+    g = torch.Generator().manual_seed(seed)
+    n_u = torch.exp(torch.randn(n_users, generator=g) * 0.95 + 4.56).round().clamp(20, 2314).long()
+    prob = (torch.arange(n_items, dtype=torch.float64) + 10.0) ** -0.8
+    prob = prob[torch.randperm(n_items, generator=g)]
+    offsets = torch.zeros(n_users + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(n_u, 0)
+    items = torch.multinomial(prob, int(offsets[-1]), replacement=True, generator=g)
+    return offsets, items

@@ -189,3 +189,23 @@ def test_ranking_metrics_match_reference_definitions():
     assert abs(r["ndcg@4"] - (dcg4 / idcg2) / 2) < 1e-6
     assert abs(r["mrr@4"] - (0.5 + 0) / 2) < 1e-6
     assert abs(r["map@4"] - ((1 / 2 + 2 / 4) / 2) / 2) < 1e-6
+
+
+def test_window_index_vectorised_matches_reference_order():
+    """replay_b200.device_data.window_index (numpy, no GPU needed) against the loop restatement and the reference's own
+    index maps stored in the golden fixture."""
+    import os
+    from oracle import dataset as od
+    from replay_b200.device_data import window_index
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "dataset_layout.npz"))
+    L, step = int(z["L"]), int(z["step"])
+    for window, st, key in ((L + 1, step, "sas_slide_index"), (L + 1, None, "sas_last_index"), (L, step, "bert_slide_index")):
+        s, o = window_index(z["lengths"], window, st)
+        assert np.array_equal(np.stack([s, o], 1), z[key])
+    rng = np.random.default_rng(0)
+    lens = rng.integers(0, 60, 500)
+    for window in (1, 7, 33):
+        for st in (None, 1, 3, 50):
+            s, o = window_index(lens, window, st)
+            ref = np.asarray(od.window_index(lens, window, st)).reshape(-1, 2)
+            assert np.array_equal(np.stack([s, o], 1), ref)

@@ -102,3 +102,49 @@ def test_sasrec_training_example_layout():
     assert pm.tolist() == [False] * 7 + [True]
     assert tm.tolist() == [False] * 6 + [True, True]
     assert labels.tolist() == [-1] * 6 + [0, 1]
+
+
+# ------------------------------------------------------------------------------------------------ dataset layout (§8 a15/f.1)
+def _layout():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataset_layout.npz"))
+
+
+def _histories(z):
+    off = np.concatenate([[0], np.cumsum(z["lengths"])])
+    return [z["items"][off[i]:off[i + 1]] for i in range(len(z["lengths"]))]
+
+
+def test_dataset_restatement_matches_reference_samples():
+    """oracle/dataset.py against samples produced by the reference's own dataset classes (sliding windows, short and
+    over-long histories, both BERT masker corner cases)."""
+    from oracle import dataset as od
+    z = _layout()
+    seqs, L, pad, step, prob = _histories(z), int(z["L"]), int(z["pad"]), int(z["step"]), float(z["mask_prob"])
+    for tag, st in (("slide", step), ("last", None)):
+        idx = od.window_index(z["lengths"], L + 1, st)
+        assert np.array_equal(np.asarray(idx), z[f"sas_{tag}_index"])
+        smp = [od.sasrec_training_sample(seqs[i], o, L, pad) for i, o in idx]
+        assert np.array_equal(np.stack([s["item_id"] for s in smp]), z[f"sas_{tag}_ids"])
+        assert np.array_equal(np.stack([s["padding_mask"] for s in smp]), z[f"sas_{tag}_pad"])
+        assert np.array_equal(np.stack([s["positive_labels"] for s in smp]), z[f"sas_{tag}_labels"])
+        assert np.array_equal(np.stack([s["target_padding_mask"] for s in smp]), z[f"sas_{tag}_tmask"])
+        bidx = od.window_index(z["lengths"], L, st)
+        assert np.array_equal(np.asarray(bidx), z[f"bert_{tag}_index"])
+        u = z[f"bert_{tag}_uniforms"]
+        bs = [od.bert_training_sample(seqs[i], o, L, pad, u[r], prob) for r, (i, o) in enumerate(bidx)]
+        assert np.array_equal(np.stack([s["item_id"] for s in bs]), z[f"bert_{tag}_ids"])
+        assert np.array_equal(np.stack([s["pad_mask"] for s in bs]), z[f"bert_{tag}_pad"])
+        assert np.array_equal(np.stack([s["token_mask"] for s in bs]), z[f"bert_{tag}_tok"])
+        assert np.array_equal(np.stack([s["positive_labels"] for s in bs]), z[f"bert_{tag}_labels"])
+    pr = [od.prediction_sample(s, L, pad) for s in seqs]
+    assert np.array_equal(np.stack([s["item_id"] for s in pr]), z["pred_ids"])
+    assert np.array_equal(np.stack([s["padding_mask"] for s in pr]), z["pred_pad"])
+    bp = [od.bert_prediction_sample(s, L, pad) for s in seqs]
+    assert np.array_equal(np.stack([s["item_id"] for s in bp]), z["bertpred_ids"])
+    assert np.array_equal(np.stack([s["pad_mask"] for s in bp]), z["bertpred_pad"])
+    assert np.array_equal(np.stack([s["token_mask"] for s in bp]), z["bertpred_tok"])
+    # masker corner cases are independent of the draws: prob 0 keeps everything -> last token masked;
+    # prob > 1 masks everything -> the one before last is un-masked
+    for tag, p_ in (("p0", 0.0), ("p2", 2.0)):
+        got = np.stack([od.bert_token_mask(z["bert_last_pad"][r], np.full(L, 0.5, np.float32), p_) for r in range(len(seqs))])
+        assert np.array_equal(got, z[f"bert_{tag}_tok"])

@@ -105,8 +105,9 @@ int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, const i
  * x_mn = 1: stored [K rows, M or N cols].  Batch element bz = outer*inner + in addresses rows r0 + outer*ro + in*ri and
  * columns c0 + outer*co + in*ci.  C: element offset c_off0 + outer*c_oo + in*c_oi, row pitch ldc.
  * out_mode 0: bf16 store, 1: fp32 atomic add (split_k >= 1), 2: fp32 store, 3: fp32 store of the split-K partial at
- * C + ksplit * c_split_stride (deterministic two-stage split-K; reduce with rp_reduce_splits).
- * Epilogue order: alpha, bias[N], act (0 none, 1 ReLU, 2 GELU-erf), Philox dropout(drop_p; seed + *seed_ptr, drop_offset +
+ * C + ksplit * c_split_stride (deterministic two-stage split-K; reduce with rp_reduce_splits), 4: fp32 C += x as a plain
+ * read-modify-write (split_k == 1, every element has one owner).
+ * Epilogue order: alpha, bias[N], act (0 none, 1 ReLU, 2 GELU-erf, 3 exp2 with a per-row offset), Philox dropout(drop_p; seed + *seed_ptr, drop_offset +
  * element offset in C), gate (x *= gate != 0 ? gate_scale : 0, same geometry as C), residual (bf16, same geometry as C),
  * post-residual dropout (post_drop_p, post_drop_offset), rowmask[rowmask_off0 + outer*rowmask_oo + m].
  * C2 (optional, bf16, geometry of C) receives the value after the bias and before the activation; gate_mode 1 multiplies
@@ -125,6 +126,10 @@ typedef struct rp_gemm_desc {
   const void* gate; float gate_scale;
   void* C2; int gate_mode; float post_drop_p; unsigned long long post_drop_offset;
   long long c_split_stride;
+  const float* row_exp2_offset;                    /* act 3: x = exp2(x * log2(e) + row_exp2_offset[m]) */
+  const int32_t* m_limit_dev; int m_limit_base;    /* device scalar: 128-row tiles with m0 + base >= *limit are skipped */
+  const int32_t* k_limit_dev; int k_limit_base;    /* device scalar: the contraction stops at *limit - base, rounded up to
+                                                      a whole 64-element chunk (operands beyond the limit must be finite) */
 } rp_gemm_desc;
 int rp_gemm(const rp_gemm_desc* g, void* stream);
 /* dst[i] (+)= sum_s src[s * stride + i], i < n (n, stride multiples of 4) */

@@ -99,6 +99,8 @@ class GemmDesc(ctypes.Structure):
         ("gate", c_void_p), ("gate_scale", c_float),
         ("C2", c_void_p), ("gate_mode", c_int), ("post_drop_p", c_float), ("post_drop_offset", ctypes.c_ulonglong),
         ("c_split_stride", ctypes.c_longlong),
+        ("row_exp2_offset", c_void_p), ("m_limit_dev", c_void_p), ("m_limit_base", c_int),
+        ("k_limit_dev", c_void_p), ("k_limit_base", c_int),
     ]
 
 

@@ -1,4 +1,4 @@
-// rp_attention.cu - padded-sequence multi-head attention for L <= 256 (SASRec causal + key-padding, BERT4Rec key-padding):
+// rp_attention.cu - padded-sequence multi-head attention for L <= 512 (L > 256: head_dim 64 only) (SASRec causal + key-padding, BERT4Rec key-padding):
 // fused forward on tcgen05 (S = Q.K^T in TMEM -> masked softmax in registers -> P bf16 back into TMEM -> O = P.V),
 // and the row-wise softmax backward that sits between the batched backward GEMMs (rp_gemm).
 //
@@ -31,13 +31,16 @@ struct AttnParams {
 
 static constexpr float kLog2eA = 1.4426950408889634f;
 
-template <int HD>
+// KB = number of 256-key blocks the CTA keeps resident (1: L <= 256, 2: L <= 512).  S [128 x 256*KB] fp32 fills 256*KB
+// TMEM columns; P (bf16) is written back over its first half and O accumulates behind it.
+template <int HD, int KB>
 __global__ void __launch_bounds__(160, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   constexpr int HC = HD / 64;                 // 64-wide head-dim chunks
   constexpr int Q_BYTES = HC * 128 * 128;     // [128 x HD]
-  constexpr int KV_BYTES = HC * 256 * 128;    // [256 x HD]
+  constexpr int KV_CHUNK = KB * 256 * 128;    // one 64-wide head-dim chunk of all resident keys
+  constexpr int KV_BYTES = HC * KV_CHUNK;     // [256*KB x HD]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -51,7 +54,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int bz = b * p.H + h;
   const int L = p.L;
   int nk = p.causal ? min(L, q0 + 128) : L;        // keys that can be visible to this query tile
-  const int nk32 = (nk + 31) & ~31;                // MMA N / K extent (<= 256)
+  const int nk32 = (nk + 31) & ~31;                // MMA N / K extent (<= 256 per block, KB blocks)
   const int n_boxes = (nk32 + 127) / 128;
 
   if (threadIdx.x == 0) {
@@ -64,12 +67,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  if (warp == 0) tmem_alloc(&tmem_slot, 256 * KB);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t tmem_o = tmem + 128;   // reuses S columns [128, 128+HD) once P is complete
+  const uint32_t tmem_o = tmem + 128 * KB;   // reuses the S columns behind the packed P once P is complete
 
   if (warp == 0) {
     if (elect_one()) {
@@ -78,26 +81,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int c = 0; c < HC; ++c) {
         tma_load_2d(sQ + c * 16384, &tmQ, &bar_load, p.q_c0 + h * HD + c * 64, row0 + q0);
         for (int bx = 0; bx < n_boxes; ++bx) {
-          tma_load_2d(sK + c * 32768 + bx * 16384, &tmK, &bar_load, p.k_c0 + h * HD + c * 64, row0 + bx * 128);
-          tma_load_2d(sV + c * 32768 + bx * 16384, &tmV, &bar_load, p.v_c0 + h * HD + c * 64, row0 + bx * 128);
+          tma_load_2d(sK + c * KV_CHUNK + bx * 16384, &tmK, &bar_load, p.k_c0 + h * HD + c * 64, row0 + bx * 128);
+          tma_load_2d(sV + c * KV_CHUNK + bx * 16384, &tmV, &bar_load, p.v_c0 + h * HD + c * 64, row0 + bx * 128);
         }
       }
       mbar_wait(&bar_load, 0);
       tc_fence_after();
-      const uint32_t idesc1 = umma_idesc_bf16(128, nk32);
 #pragma unroll
-      for (int c = 0; c < HC; ++c)
+      for (int kb = 0; kb < KB; ++kb) {           // one MMA N extent is at most 256 keys
+        const int nb = min(256, nk32 - kb * 256);
+        if (nb <= 0) break;
+        const uint32_t idesc1 = umma_idesc_bf16(128, nb);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_ss(tmem, umma_desc_sw128(smem_u32(sQ) + c * 16384 + ks * 32, 16, 1024),
-                  umma_desc_sw128(smem_u32(sK) + c * 32768 + ks * 32, 16, 1024), idesc1, (c | ks) != 0);
+        for (int c = 0; c < HC; ++c)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss(tmem + kb * 256, umma_desc_sw128(smem_u32(sQ) + c * 16384 + ks * 32, 16, 1024),
+                    umma_desc_sw128(smem_u32(sK) + c * KV_CHUNK + kb * 32768 + ks * 32, 16, 1024), idesc1, (c | ks) != 0);
+      }
       umma_commit(&bar_s);
       // ---- second GEMM once the softmax warps have written P
       mbar_wait(&bar_p, 0);
       tc_fence_after();
       constexpr uint32_t idesc2 = umma_idesc_bf16(128, HD, false, true);
       for (int ks = 0; ks < nk32 / 16; ++ks)
-        umma_ts(tmem_o, tmem + ks * 8, umma_desc_sw128(smem_u32(sV) + ks * 2048, 32768, 1024), idesc2, ks != 0);
+        umma_ts(tmem_o, tmem + ks * 8, umma_desc_sw128(smem_u32(sV) + ks * 2048, KV_CHUNK, 1024), idesc2, ks != 0);
       umma_commit(&bar_o);
     }
   } else {
@@ -107,9 +115,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int i = q0 + row;                 // query position inside the sequence
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     // key-visibility bit masks, 32 keys per word
-    uint32_t kmask[8];
+    uint32_t kmask[8 * KB];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 8 * KB; ++c) {
       const int j = c * 32 + lane;
       bool ok = j < L;
       if (ok && p.mask_pad_keys) ok = p.pad_mask[(size_t)b * L + j] != 0;
@@ -125,7 +133,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     auto vis_mask = [&](int c) -> uint32_t {
       uint32_t m = 0;
 #pragma unroll
-      for (int cc = 0; cc < 8; ++cc)
+      for (int cc = 0; cc < 8 * KB; ++cc)
         if (cc == c) m = kmask[cc];
       if (p.causal) {
         const int rel = i - c * 32;
@@ -214,13 +222,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 256 * KB);
 }
 
 // Row-wise softmax backward between the batched GEMMs.  One warp per (batch*head, query) row.
 //   in : p_save  = exp(s - max) (bf16), inv_sum, dpd = dO.V^T (bf16, w.r.t. the dropped & rescaled probabilities)
 //   out: ds (over dpd) = P * (dP - sum_j P_j dP_j) * scale      with P = p_save * inv_sum, dP = dpd * mask / keep
 //        pd (over p_save) = P * mask / keep                       (A operand of dV = Pd^T . dO)
+template <int NK>  // 128-column blocks per row: Lp <= 128 * NK
 __global__ void attn_softmax_bwd_kernel(__nv_bfloat16* __restrict__ p_save, __nv_bfloat16* __restrict__ dpd,
                                         const float* __restrict__ inv_sum, int BH, int L, int Lp, float scale,
                                         float drop_p, unsigned long long seed, unsigned long long drop_off,
@@ -235,11 +244,11 @@ __global__ void attn_softmax_bwd_kernel(__nv_bfloat16* __restrict__ p_save, __nv
     const int bz = (int)(r / L), i = (int)(r % L);
     const size_t base = ((size_t)bz * Lp + i) * Lp;
     const float inv = inv_sum[(size_t)bz * Lp + i];
-    // lane owns columns [4*lane + 128*k, +4), k = 0,1   (Lp <= 256; columns >= L hold zeros and are never written)
-    float P[8], dP[8], keep[8];
+    // lane owns columns [4*lane + 128*k, +4), k < NK   (columns >= L hold zeros and are never written)
+    float P[4 * NK], dP[4 * NK], keep[4 * NK];
     float dot = 0.f;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < NK; ++k) {
       const int j0 = k * 128 + lane * 4;
 #pragma unroll
       for (int q = 0; q < 4; ++q) { P[k * 4 + q] = 0.f; dP[k * 4 + q] = 0.f; keep[k * 4 + q] = 0.f; }
@@ -269,7 +278,7 @@ __global__ void attn_softmax_bwd_kernel(__nv_bfloat16* __restrict__ p_save, __nv
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < NK; ++k) {
       const int j0 = k * 128 + lane * 4;
       if (j0 < L) {
         float ds[4], pd[4];
@@ -311,10 +320,10 @@ __global__ void attn_last_kernel(const __nv_bfloat16* __restrict__ q, const __nv
   for (int c = lane; c < HD; c += 32) s_q[w][c] = __bfloat162float(q[(size_t)b * H * HD + h * HD + c]) * scale;
   __syncwarp();
   // scores: lane owns keys lane, lane+32, ...
-  float sc[8];
+  float sc[16];  // L <= 512
   float mx = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 16; ++i) {
     const int j = i * 32 + lane;
     sc[i] = -INFINITY;
     if (j < L && (!mask_pad_keys || pad_mask[(size_t)b * L + j])) {
@@ -338,7 +347,7 @@ __global__ void attn_last_kernel(const __nv_bfloat16* __restrict__ q, const __nv
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 16; ++i) {
     sc[i] = (sc[i] == -INFINITY) ? 0.f : __expf(sc[i] - mx);
     sum += sc[i];
   }
@@ -349,7 +358,7 @@ __global__ void attn_last_kernel(const __nv_bfloat16* __restrict__ q, const __nv
 #pragma unroll
   for (int c = 0; c < PER; ++c) acc[c] = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 16; ++i) {
     const int jmax = min(32, L - i * 32);
     for (int jj = 0; jj < jmax; ++jj) {
       const float pj = __shfl_sync(0xffffffffu, sc[i], jj);
@@ -378,7 +387,7 @@ RP_API int rp_attn_last(const void* q, const void* k, const void* v, long long l
                         void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!q || !k || !v || !pad_mask || !out) return RP_EINVAL;
-  if (B <= 0 || H <= 0 || L <= 0 || L > 256) return RP_ESHAPE;
+  if (B <= 0 || H <= 0 || L <= 0 || L > 512) return RP_ESHAPE;
   if ((ldk & 7) || (ldv & 7) || (k_c0 & 7) || (v_c0 & 7)) return RP_EALIGN;
   const float scale = 1.f / sqrtf((float)head_dim);
   const int blocks = (B * H + 7) / 8;
@@ -412,8 +421,9 @@ struct rp_attn_desc {
 RP_API int rp_attn_fwd(const rp_attn_desc* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!a || !a->q || !a->k || !a->v || !a->out || !a->pad_mask) return RP_EINVAL;
-  if (a->L <= 0 || a->L > 256 || a->B <= 0 || a->H <= 0) return RP_ESHAPE;
+  if (a->L <= 0 || a->L > 512 || a->B <= 0 || a->H <= 0) return RP_ESHAPE;
   if (a->head_dim != 64 && a->head_dim != 128) return RP_ESHAPE;
+  if (a->L > 256 && a->head_dim != 64) return RP_ESHAPE;  // 512 resident keys x 128 head dims do not fit shared memory
   if (a->ldo % 8 != 0) return RP_EALIGN;
   AttnParams p;
   p.B = a->B; p.H = a->H; p.L = a->L; p.Lp = (a->L + 63) & ~63;
@@ -430,14 +440,18 @@ RP_API int rp_attn_fwd(const rp_attn_desc* a, void* stream_) {
   if ((rc = make_tmap_bf16(&tmK, a->k, a->k_rows, a->k_cols, a->ldk, 128)) != RP_OK) return rc;
   if ((rc = make_tmap_bf16(&tmV, a->v, a->v_rows, a->v_cols, a->ldv, 128)) != RP_OK) return rc;
   dim3 grid((a->L + 127) / 128, a->H, a->B);
-  if (a->head_dim == 64) {
+  if (a->L > 256) {
+    const int smem = 16384 + 2 * 65536 + 1024;
+    RP_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attn_fwd_kernel<64, 2><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+  } else if (a->head_dim == 64) {
     const int smem = 16384 + 2 * 32768 + 1024;
-    RP_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_fwd_kernel<64><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+    RP_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attn_fwd_kernel<64, 1><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
   } else {
     const int smem = 2 * (16384 + 2 * 32768) + 1024;
-    RP_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_fwd_kernel<128><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+    RP_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attn_fwd_kernel<128, 1><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
   }
   RP_LAUNCH_CHECK();
   return RP_OK;
@@ -447,15 +461,20 @@ RP_API int rp_attn_softmax_bwd(void* p_save, void* dpd, const float* inv_sum, in
                                unsigned long long seed, unsigned long long drop_off, const unsigned long long* seed_ptr,
                                void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (!p_save || !dpd || !inv_sum || BH <= 0 || L <= 0 || L > 256) return RP_EINVAL;
+  if (!p_save || !dpd || !inv_sum || BH <= 0 || L <= 0 || L > 512) return RP_EINVAL;
   const int Lp = (L + 63) & ~63;
   const long long rows = (long long)BH * L;
   long long blocks = (rows + 7) / 8;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  attn_softmax_bwd_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(p_save),
-                                                           reinterpret_cast<__nv_bfloat16*>(dpd), inv_sum, BH, L, Lp, scale,
-                                                           drop_p, seed, drop_off, seed_ptr);
+  if (L > 256)
+    attn_softmax_bwd_kernel<4><<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(p_save),
+                                                                reinterpret_cast<__nv_bfloat16*>(dpd), inv_sum, BH, L, Lp, scale,
+                                                                drop_p, seed, drop_off, seed_ptr);
+  else
+    attn_softmax_bwd_kernel<2><<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(p_save),
+                                                                reinterpret_cast<__nv_bfloat16*>(dpd), inv_sum, BH, L, Lp, scale,
+                                                                drop_p, seed, drop_off, seed_ptr);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }

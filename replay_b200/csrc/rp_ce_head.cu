@@ -18,6 +18,7 @@
 //                      dE += G . Hc_tile                                                          -> dE fp32 [I, d] (=)
 //   ce_label_scatter   dE[y_t] -= Hc[t] / T_v   (the one-hot part of softmax - onehot, sparse)
 #include "rp_host.h"
+#include "rp_gemm_desc.h"
 #include "rp_sm100.cuh"
 
 namespace rp {
@@ -708,6 +709,45 @@ __global__ void ce_fused_finalize_kernel(const float* __restrict__ part_dh, cons
   }
 }
 
+// d = 512 path: dH[t, :] -= E[y_t, :] / T_v  (the one-hot part of softmax - onehot; the GEMM wrote softmax . E / T_v)
+__global__ void ce_dh_label_sub_kernel(__nv_bfloat16* __restrict__ d_hc, const __nv_bfloat16* __restrict__ table,
+                                       const int32_t* __restrict__ labels, const float* __restrict__ loss_inv,
+                                       const int32_t* __restrict__ n_valid_ptr, int d) {
+  const int n_valid = *n_valid_ptr;
+  const float inv_n = loss_inv[0];
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < n_valid; t += gridDim.x * wpb) {
+    const uint4* e = reinterpret_cast<const uint4*>(table + (size_t)labels[t] * d);
+    uint4* o = reinterpret_cast<uint4*>(d_hc + (size_t)t * d);
+    for (int c = lane; c < d / 8; c += 32) {
+      const uint4 ev = e[c];
+      uint4 ov = o[c];
+      const __nv_bfloat162* e2 = reinterpret_cast<const __nv_bfloat162*>(&ev);
+      uint32_t* o32 = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o32[q])), b = __bfloat1622float2(e2[q]);
+        o32[q] = pack_bf16(a.x - inv_n * b.x, a.y - inv_n * b.y);
+      }
+      o[c] = ov;
+    }
+  }
+}
+
+// d = 512: S and the [128 x 512] fp32 gradient accumulator do not fit the 512 TMEM columns together, so the backward
+// materialises the softmax numerators G (bf16) for a chunk of tokens at a time and runs three plain GEMMs per chunk.
+// Chunk rows: as many as fit the G budget (RP_CE_WIDE_G_BYTES, default 8 GiB), multiple of 128.
+static long long wide_ldg(int n_items) { return ((long long)n_items + 63) / 64 * 64; }
+static int wide_chunk_rows(int cap, int n_items) {
+  const char* env = getenv("RP_CE_WIDE_G_BYTES");  // read per call: the workspace query and the launch must agree
+  const long long budget = env ? atoll(env) : (8ll << 30);
+  long long rows = budget / (wide_ldg(n_items) * 2) / 128 * 128;
+  const long long cap128 = ((long long)cap + 127) / 128 * 128;
+  if (rows < 128) rows = 128;
+  if (rows > cap128) rows = cap128;
+  return (int)rows;
+}
+
 static int pick_splits(int n_row_tiles, int n_col_tiles) {
   const int sms = sm_count();
   int best = 1;
@@ -734,9 +774,14 @@ struct CeWs {
 };
 static const int kMaxSplits = 8;
 
-static size_t ce_ws_bytes(int cap, int d) {
+static size_t ce_ws_base_bytes(int cap, int d) {
   return (size_t)cap * kMaxSplits * 2 * sizeof(float2) + 4096 + 64 + (size_t)kMaxSplits * kBwdCG * cap * 4 +
-         (size_t)kMaxSplits * cap * d * 4 + 256;
+         (d <= 256 ? (size_t)kMaxSplits * cap * d * 4 : 0) + 256;
+}
+static size_t ce_ws_bytes(int cap, int n_items, int d) {
+  size_t b = (ce_ws_base_bytes(cap, d) + 1023) / 1024 * 1024;
+  if (d > 256) b += (size_t)wide_chunk_rows(cap, n_items) * wide_ldg(n_items) * 2;  // G chunk (bf16)
+  return b;
 }
 static CeWs ce_ws(void* workspace, int cap, int d) {
   uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
@@ -758,7 +803,7 @@ static CeWs ce_ws(void* workspace, int cap, int d) {
 
 RP_API size_t rp_ce_head_workspace(int capacity_tokens, int n_items, int d) {
   if (capacity_tokens <= 0 || n_items <= 0 || d <= 0) return 0;
-  return ce_ws_bytes(capacity_tokens, d);
+  return ce_ws_bytes(capacity_tokens, n_items, d);
 }
 
 template <int KCH, int NSTAGE>
@@ -829,7 +874,7 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, 
   if (!hc || !table || !labels || !n_valid || !loss_out || !lse || !cvec || !workspace) return RP_EINVAL;
   if (capacity <= 0 || n_items <= 0) return RP_ESHAPE;
   if (d != 64 && d != 128 && d != 256 && d != 512) return RP_ESHAPE;
-  if (workspace_bytes < ce_ws_bytes(capacity, d)) return RP_EWORKSPACE;
+  if (workspace_bytes < ce_ws_bytes(capacity, n_items, d)) return RP_EWORKSPACE;
   const bool fused = d_hc != nullptr && d <= 256;
   const int n_tok_tiles = (capacity + kT - 1) / kT, n_item_tiles = (n_items + kT - 1) / kT;
   const int hint_tiles = (n_valid_hint > 0 && n_valid_hint <= capacity) ? (n_valid_hint + kT - 1) / kT : n_tok_tiles;
@@ -877,9 +922,10 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, 
 
 // Backward of rp_ce_head_fwd for d(loss) = 1:
 //   d_hc   bf16 [capacity, d]  (rows < *n_valid) - already written by the forward when it ran fused (`fused` != 0 and the
-//          device-side bound held); otherwise computed here from the stored lse
+//          device-side bound held); otherwise computed here from the stored lse.  d = 512: chunked materialised-G path
+//          (three GEMMs per token chunk, see wide_chunk_rows), workspace required
 //   d_table fp32 [n_items, d]  OVERWRITTEN with softmax^T . hc / T_v, then the one-hot part is atomically subtracted
-//   d_bias  fp32 [n_items] (iff bias)  OVERWRITTEN likewise.        d in {64,128,256}.
+//   d_bias  fp32 [n_items] (iff bias)  OVERWRITTEN likewise.        d in {64,128,256}; 512 without bias.
 RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, const int32_t* labels,
                           const int32_t* n_valid, int capacity, int n_items, int d, const float* loss_out /* from fwd */,
                           const float* cvec /* from fwd */, void* d_hc, float* d_table, float* d_bias, int fused,
@@ -888,8 +934,55 @@ RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, 
   if (!hc || !table || !labels || !n_valid || !loss_out || !cvec || !d_hc || !d_table) return RP_EINVAL;
   if ((bias == nullptr) != (d_bias == nullptr)) return RP_EINVAL;
   if (capacity <= 0 || n_items <= 0) return RP_ESHAPE;
-  if (d != 64 && d != 128 && d != 256) return RP_ESHAPE;
-  if (fused && (!workspace || workspace_bytes < ce_ws_bytes(capacity, d))) return RP_EWORKSPACE;
+  if (d != 64 && d != 128 && d != 256 && d != 512) return RP_ESHAPE;
+  if ((fused || d == 512) && (!workspace || workspace_bytes < ce_ws_bytes(capacity, n_items, d))) return RP_EWORKSPACE;
+  if (d == 512) {
+    // ---- wide-hidden path: per token chunk  G = exp2((hc.E^T + b) log2e + c_t)  ->  dH = G.E,  dE += G^T.hc
+    if (bias) return RP_ESHAPE;  // biased (BERT4Rec) head at d = 512 is not built
+    const long long ldg = wide_ldg(n_items);
+    const int chunk = wide_chunk_rows(capacity, n_items);
+    void* G = reinterpret_cast<uint8_t*>(workspace) + (ce_ws_base_bytes(capacity, d) + 1023) / 1024 * 1024;
+    int rc;
+    for (int c0 = 0, it = 0; c0 < capacity; c0 += chunk, ++it) {
+      const int rows = (capacity - c0 < chunk) ? capacity - c0 : chunk;
+      rp_gemm_desc g;
+      memset(&g, 0, sizeof(g));
+      g.batch = 1; g.inner = 1; g.alpha = 1.f; g.split_k = 1;
+      // G [rows, n_items] = exp2((hc[c0:c0+rows] . E^T) log2e + cvec)
+      g.A = reinterpret_cast<const __nv_bfloat16*>(hc) + (size_t)c0 * d; g.a_rows = rows; g.a_cols = d; g.lda = d; g.a_mn = 0;
+      g.B = table; g.b_rows = n_items; g.b_cols = d; g.ldb = d; g.b_mn = 0;
+      g.M = rows; g.N = n_items; g.K = d;
+      g.C = G; g.ldc = ldg; g.out_mode = 0; g.act = 3; g.row_exp2_offset = cvec + c0;
+      g.m_limit_dev = n_valid; g.m_limit_base = c0;
+      if ((rc = rp_gemm(&g, stream_)) != RP_OK) return rc;
+      // dH[c0:c0+rows] = G . E            (A = G K-major over the items, B = E read MN-major)
+      memset(&g, 0, sizeof(g));
+      g.batch = 1; g.inner = 1; g.alpha = 1.f; g.split_k = 1;
+      g.A = G; g.a_rows = rows; g.a_cols = n_items; g.lda = ldg; g.a_mn = 0;
+      g.B = table; g.b_rows = n_items; g.b_cols = d; g.ldb = d; g.b_mn = 1;
+      g.M = rows; g.N = d; g.K = n_items;
+      g.C = reinterpret_cast<__nv_bfloat16*>(d_hc) + (size_t)c0 * d; g.ldc = d; g.out_mode = 0;
+      g.m_limit_dev = n_valid; g.m_limit_base = c0;
+      if ((rc = rp_gemm(&g, stream_)) != RP_OK) return rc;
+      // dE (+)= G^T . hc[c0:c0+rows]      (A = G read MN-major, contraction over the chunk's valid tokens)
+      memset(&g, 0, sizeof(g));
+      g.batch = 1; g.inner = 1; g.alpha = 1.f; g.split_k = 1;
+      g.A = G; g.a_rows = rows; g.a_cols = n_items; g.lda = ldg; g.a_mn = 1;
+      g.B = reinterpret_cast<const __nv_bfloat16*>(hc) + (size_t)c0 * d; g.b_rows = rows; g.b_cols = d; g.ldb = d; g.b_mn = 1;
+      g.M = n_items; g.N = d; g.K = rows;
+      g.C = d_table; g.ldc = d; g.out_mode = it == 0 ? 2 : 4;
+      g.k_limit_dev = n_valid; g.k_limit_base = c0;
+      if ((rc = rp_gemm(&g, stream_)) != RP_OK) return rc;
+    }
+    ce_dh_label_sub_kernel<<<sm_count() * 4, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(d_hc),
+                                                                reinterpret_cast<const __nv_bfloat16*>(table), labels,
+                                                                loss_out + 1, n_valid, d);
+    RP_LAUNCH_CHECK();
+    ce_label_scatter_kernel<<<sm_count() * 4, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hc), labels, loss_out + 1,
+                                                                 n_valid, d, d_table, d_bias);
+    RP_LAUNCH_CHECK();
+    return RP_OK;
+  }
   CUtensorMap tmH, tmE;
   int rc;
   if ((rc = make_tmap_bf16(&tmH, hc, capacity, d, d, 128)) != RP_OK) return rc;

@@ -44,12 +44,18 @@ struct GemmParams {
   int gate_mode;               // 0: gate != 0 ? gate_scale : 0 ;  1: gelu'(gate) * gate_scale (gate = saved pre-activation)
   float post_drop_p;           // second dropout applied AFTER the residual add (BERT4Rec block output), 0 = off
   unsigned long long post_drop_offset;
+  const float* row_exp2_offset;  // act 3: x = exp2(x * log2(e) + row_exp2_offset[m])   (softmax numerators from stored lse)
+  const int32_t* m_limit_dev;    // optional device scalar: rows m with m_limit_base + m >= *m_limit_dev are not computed
+  int m_limit_base;
+  const int32_t* k_limit_dev;    // optional device scalar: the contraction stops at *k_limit_dev - k_limit_base (whole 64-chunks)
+  int k_limit_base;
 };
 
 // Epilogue of one [1 row x 32 columns] strip held in registers (shared by the tile kernel and the persistent kernel).
 struct EpiRow {
   long long c_base;   // element offset of this output row in C
   float rm;           // row-mask factor
+  float exp_off;      // act 3: per-row exponent offset
   float keep_scale;
   uint32_t drop_thr;
   unsigned long long seed_eff;
@@ -84,6 +90,9 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const f
       } else if (p.act == 2) {
 #pragma unroll
         for (int q = 0; q < 32; ++q) x[q] = 0.5f * x[q] * (1.f + erff(x[q] * 0.70710678118654752f));
+      } else if (p.act == 3) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) x[q] = ex2f(fmaf(x[q], 1.4426950408889634f, er.exp_off));
       }
       if (p.drop_p > 0.f) {
         // one Philox call per 4 consecutive output elements; element index = c_base + column
@@ -173,6 +182,19 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const f
 #pragma unroll
           for (int q = 0; q < 32; ++q)
             if (n0 + c + q < p.N) atomicAdd(o + q, x[q]);
+        } else if (p.out_mode == 4) {  // C += x, plain read-modify-write (every element has exactly one owner: split_k == 1)
+          if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+              float4 v = *reinterpret_cast<float4*>(o + q);
+              v.x += x[q]; v.y += x[q + 1]; v.z += x[q + 2]; v.w += x[q + 3];
+              *reinterpret_cast<float4*>(o + q) = v;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (n0 + c + q < p.N) o[q] += x[q];
+          }
         } else if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
           for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(o + q) = make_float4(x[q], x[q + 1], x[q + 2], x[q + 3]);
@@ -203,7 +225,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int m_tile = blockIdx.y / p.split_k, ksplit = blockIdx.y % p.split_k;
   const int bz = blockIdx.z, outer = bz / p.inner, in = bz % p.inner;
   const int m0 = m_tile * 128, n0 = n_tile * BN;
-  const int k_chunks = (p.K + 63) / 64;
+  if (p.m_limit_dev != nullptr && m0 + p.m_limit_base >= *p.m_limit_dev) return;  // whole tile beyond the dynamic row count
+  int k_eff = p.K;
+  if (p.k_limit_dev != nullptr) k_eff = max(0, min(p.K, *p.k_limit_dev - p.k_limit_base));
+  const int k_chunks = (k_eff + 63) / 64;
   const int kc_begin = (int)(((long long)k_chunks * ksplit) / p.split_k);
   const int kc_end = (int)(((long long)k_chunks * (ksplit + 1)) / p.split_k);
   const int a_r = p.a_r0 + outer * p.a_ro + in * p.a_ri, a_c = p.a_c0 + outer * p.a_co + in * p.a_ci;
@@ -284,6 +309,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     EpiRow er;
     er.c_base = c_base;
     er.rm = rm;
+    er.exp_off = (p.act == 3 && row_ok) ? p.row_exp2_offset[m] : 0.f;
     er.keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     er.drop_thr = p.drop_p > 0.f ? (uint32_t)(p.drop_p * 4294967296.0) : 0u;
     er.seed_eff = p.seed + ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
@@ -293,6 +319,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + c, raw);
       tmem_ld_wait();
       if (!row_ok || n0 + c >= p.N) continue;
+      if (kc_begin >= kc_end) {  // empty contraction (dynamic K limit): the accumulator was never written
+#pragma unroll
+        for (int q = 0; q < 32; ++q) raw[q] = 0u;
+      }
       gemm_epilogue_chunk(p, s_bias, er, raw, n0, c);
     }
   }
@@ -422,6 +452,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = m < p.M;
       er.c_base = p.c_off0 + (long long)m * p.ldc;
       er.rm = 1.f;
+      er.exp_off = 0.f;
       if (p.rowmask && row_ok) er.rm = p.rowmask[p.rowmask_off0 + m] ? 1.f : 0.f;
       mbar_wait(&bar_tfull[as], aph);
       tc_fence_after();
@@ -481,22 +512,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 
 using namespace rp;
 
-// Flat C view of the parameter block (mirrors rp::GemmParams; see include/rp_b200.h rp_gemm_desc).
-struct rp_gemm_desc {
-  const void* A; long long a_rows, a_cols, lda; int a_mn;
-  const void* B; long long b_rows, b_cols, ldb; int b_mn;
-  int M, N, K, batch, inner;
-  int a_r0, a_ro, a_ri, a_c0, a_co, a_ci;
-  int b_r0, b_ro, b_ri, b_c0, b_co, b_ci;
-  void* C; long long ldc, c_off0, c_oo, c_oi; int out_mode;
-  float alpha; const float* bias; int act;
-  const void* residual; const uint8_t* rowmask; long long rowmask_off0, rowmask_oo;
-  float drop_p; unsigned long long seed, drop_offset; const unsigned long long* seed_ptr;
-  int split_k;
-  const void* gate; float gate_scale;
-  void* C2; int gate_mode; float post_drop_p; unsigned long long post_drop_offset;
-  long long c_split_stride;
-};
+#include "rp_gemm_desc.h"
 
 RP_API int rp_gemm(const rp_gemm_desc* g, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -517,6 +533,11 @@ RP_API int rp_gemm(const rp_gemm_desc* g, void* stream_) {
   p.C2 = reinterpret_cast<__nv_bfloat16*>(g->C2); p.gate_mode = g->gate_mode; p.post_drop_p = g->post_drop_p;
   p.post_drop_offset = g->post_drop_offset;
   p.c_split_stride = g->c_split_stride;
+  p.row_exp2_offset = g->row_exp2_offset;
+  p.m_limit_dev = g->m_limit_dev; p.m_limit_base = g->m_limit_base;
+  p.k_limit_dev = g->k_limit_dev; p.k_limit_base = g->k_limit_base;
+  if (g->act == 3 && !g->row_exp2_offset) return RP_EINVAL;
+  if (g->out_mode == 4 && g->split_k != 1) return RP_EINVAL;
   CUtensorMap tmA, tmB;
   int rc;
   // K-major operand: box [128 (or BN) rows x 64 cols]; MN-major operand: box [64 k-rows x 64 cols]
@@ -525,7 +546,7 @@ RP_API int rp_gemm(const rp_gemm_desc* g, void* stream_) {
   if ((rc = make_tmap_bf16(&tmB, g->B, g->b_rows, g->b_cols, g->ldb, g->b_mn ? 64 : bn)) != RP_OK) return rc;
   // weight-stationary persistent kernel: activation [M, K] K-major, K in {64,128,256}, one batch, no split-K
   static const int ws_min_m = getenv("RP_GEMM_WS_MIN_M") ? atoi(getenv("RP_GEMM_WS_MIN_M")) : 131072;  // measured: pays for M >~ 100K rows (predict), neutral at 51K
-  const bool ws_ok = g->M >= ws_min_m && !g->a_mn && g->batch == 1 && g->split_k == 1 && g->M >= 1024 && g->N >= 64 &&
+  const bool ws_ok = g->act != 3 && g->out_mode != 4 && !g->m_limit_dev && !g->k_limit_dev && g->M >= ws_min_m && !g->a_mn && g->batch == 1 && g->split_k == 1 && g->M >= 1024 && g->N >= 64 &&
                      (g->K == 64 || g->K == 128 || g->K == 256) && g->a_ro == 0 && g->a_ri == 0 && g->b_ro == 0 && g->b_ri == 0 &&
                      g->a_co == 0 && g->a_ci == 0 && g->b_co == 0 && g->b_ci == 0 && g->c_oo == 0 && g->c_oi == 0;
   if (ws_ok && bn == 128) {

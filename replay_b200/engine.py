@@ -93,8 +93,8 @@ class SasRecEngine:
             raise ValueError(f"sequence length {seq_len} exceeds max_len {cfg.max_len}")
         if cfg.variant == "legacy" and seq_len != cfg.max_len:
             raise ValueError("legacy SASRec needs seq_len == max_len (sasrec/model.py:528-529)")
-        if seq_len > 256:
-            raise ValueError("fused attention kernel supports seq_len <= 256")
+        if seq_len > 512 or (seq_len > 256 and cfg.d // cfg.n_heads != 64):
+            raise ValueError("attention kernels support seq_len <= 256 (head_dim 128) / <= 512 (head_dim 64)")
         self.T = max_batch * seq_len
         self.Lp = _ru(seq_len, 64)
         self.with_grad = with_grad
@@ -129,7 +129,8 @@ class SasRecEngine:
         self.rng_counter = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self.seed = seed & 0xFFFFFFFFFFFF
         self.training = with_grad
-        self.fused_attn_bwd = (cfg.d // cfg.n_heads) == 64  # fused tcgen05 attention backward (head_dim 64, L <= 256)
+        # fused tcgen05 attention backward: head_dim 64, L <= 256; otherwise saved probabilities + batched GEMMs
+        self.fused_attn_bwd = (cfg.d // cfg.n_heads) == 64 and seq_len <= 256
         self.fused_ce = True      # single-pass CE forward + dH (guarded on the device by a bound on |logit|)
         self.n_valid_hint = 0     # host estimate of the number of valid targets per step (load balance of the CE head only)
         self._alloc_workspace()

@@ -46,8 +46,8 @@ class Bert4RecEngine(SasRecEngine):
         self.B, self.L = max_batch, seq_len
         if seq_len != cfg.max_len:
             raise ValueError("BERT4Rec needs seq_len == max_len (bert4rec/model.py:276)")
-        if seq_len > 256:
-            raise ValueError("fused attention kernel supports seq_len <= 256")
+        if seq_len > 512 or (seq_len > 256 and cfg.d // cfg.n_heads != 64):
+            raise ValueError("attention kernels support seq_len <= 256 (head_dim 128) / <= 512 (head_dim 64)")
         self.T = max_batch * seq_len
         self.Lp = _ru(seq_len, 64)
         self.with_grad = with_grad
@@ -81,7 +81,7 @@ class Bert4RecEngine(SasRecEngine):
             self.step_count = torch.zeros(1, device=self.dev, dtype=torch.int32)
         self.rng_counter = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self.seed = seed & 0xFFFFFFFFFFFF
-        self.fused_attn_bwd = (cfg.d // cfg.n_heads) == 64
+        self.fused_attn_bwd = (cfg.d // cfg.n_heads) == 64 and seq_len <= 256
         self.fused_ce = True
         self.n_valid_hint = 0
         self._alloc_bert_workspace()

@@ -107,7 +107,8 @@ def ce_head_bwd(st: CEHeadState, hc, table, labels, n_valid, d_hc, d_table, bias
 def gemm(A, B, C, M, N, K, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, rowmask=None, drop_p=0.0,
          drop_offset=0, seed=0, seed_ptr=None, out_mode=0, split_k=1, gate=None, gate_scale=1.0, gate_mode=0, alpha=1.0,
          batch=1, inner=1, a_off=(0, 0, 0, 0, 0, 0), b_off=(0, 0, 0, 0, 0, 0), c_geom=None, rowmask_oo=0, C2=None,
-         post_drop_p=0.0, post_drop_offset=0, c_split_stride=0, L=None):
+         post_drop_p=0.0, post_drop_offset=0, c_split_stride=0, row_exp2_offset=None, m_limit=None, m_limit_base=0,
+         k_limit=None, k_limit_base=0, L=None):
     """C = epilogue(alpha * A(m,k) . B(n,k)) through rp_gemm (include/rp_b200.h).  A / B are 2-D bf16 tensors (views allowed:
     pointer, shape and row pitch are taken from the tensor); x_mn selects the MN-major reading of an operand."""
     g = GemmDesc()
@@ -129,4 +130,7 @@ def gemm(A, B, C, M, N, K, *, a_mn=False, b_mn=False, bias=None, act=0, residual
     g.C2 = _ptr(C2)
     g.post_drop_p, g.post_drop_offset = post_drop_p, post_drop_offset
     g.c_split_stride = c_split_stride
+    g.row_exp2_offset = _ptr(row_exp2_offset)
+    g.m_limit_dev, g.m_limit_base = _ptr(m_limit), m_limit_base
+    g.k_limit_dev, g.k_limit_base = _ptr(k_limit), k_limit_base
     check((L or lib()).rp_gemm(ctypes.byref(g), _stream()), "rp_gemm")

@@ -206,3 +206,44 @@ def test_fused_attention_backward_matches_unfused(golden_dir, cuda, dropout):
     cos = float((a.double() @ b.double()) / (a.double().norm() * b.double().norm()))
     assert cos > 0.9995, cos
     assert abs(float(a.norm() / b.norm()) - 1) < 5e-3
+
+
+def test_config5_shape_train_step_matches_oracle(cuda):
+    """BASELINE configs[4] shape at a small catalog: L = 512, d = 512, H = 8 (head_dim 64), 2 blocks.  Exercises the
+    512-key attention forward, the saved-probability attention backward and the d = 512 CE head against the oracle on the
+    same seeded weights and batch (the reference's modules at this size would need 50 MB fixtures)."""
+    from oracle import sasrec as osr
+    from replay_b200.engine import EncoderConfig, SasRecEngine
+    from replay_b200.synthetic import make_sequences
+
+    B, L, d, H, I = 3, 512, 512, 8, 1500
+    P = osr.random_params(I, d, L, 2, seed=21)
+    ids, pm, lab, tm = make_sequences(B, I, L, seed=5)
+    ids[0, :300], pm[0, :300] = I, False          # one short history: left padding inside a 512 window
+    lab[0, :299], tm[0, :299] = I, False
+    cfg = EncoderConfig(n_items=I, d=d, n_heads=H, n_blocks=2, max_len=L, dropout=0.0, variant="new")
+    eng = SasRecEngine(cfg, B, L, cuda)
+    assert not eng.fused_attn_bwd
+    eng.load_canonical(P)
+    eng.set_batch(ids.cuda(), pm.cuda(), lab.cuda(), tm.cuda())
+    hid = eng.forward_hidden_all().float().cpu().view(B, L, d)
+    ref_h = osr.sasrec_body(P, ids, pm, H, "new")
+    assert (hid - ref_h).abs().max() < 8e-2, (hid - ref_h).abs().max()
+    loss = eng.forward_train()
+    ref_loss, Gref = osr.loss_and_grads(P, ids, pm, lab, tm, H, "new")
+    assert abs(loss[0].item() - float(ref_loss)) < 5e-3 * float(ref_loss), (loss[0].item(), float(ref_loss))
+    eng.g32.zero_()
+    eng.backward()
+    torch.cuda.synchronize()
+    G = eng.export_canonical(eng.grads)
+    bad = []
+    for k, (a, b) in enumerate(zip(osr.flat_param_list(G), osr.flat_param_list(Gref))):
+        c, r = _cos(a, b), float(a.double().norm() / (b.double().norm() + 1e-30))
+        if c < 0.99 or abs(r - 1) > 0.04:
+            bad.append((k, round(c, 5), round(r, 4)))
+    assert not bad, bad
+    # predict: last hidden state through the last-position shortcut (attn_last over 512 keys)
+    eng.set_batch(ids.cuda(), pm.cuda())
+    hq = eng.forward_last_hidden().float().cpu()
+    ref_e = osr.sasrec_body(P, ids, pm, H, "new", mode="eval")[:, -1]
+    assert (hq - ref_e).abs().max() < 8e-2

@@ -176,3 +176,71 @@ def test_gemm_matches_matmul(ops, M, N, K, b_mn, monkeypatch):
     ops.gemm(A.cuda(), Bop.cuda(), C32, M, N, K, b_mn=b_mn, out_mode=2)
     torch.cuda.synchronize()
     assert (C32.cpu().double() - A.double() @ W.double().T).abs().max().item() < 2e-3
+
+
+def test_gemm_exp2_epilogue_dynamic_limits_and_accumulate(ops):
+    """The additions behind the d = 512 CE backward: act 3 (exp2 with a per-row offset), device-side M / K limits and the
+    non-atomic accumulate store."""
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 700, 1000, 512
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.1).to(torch.bfloat16)
+    off = torch.randn(M, generator=g) - 3.0
+    n_rows = torch.tensor([533], dtype=torch.int32, device="cuda")
+    C = torch.full((M, 1024), 9.0, device="cuda", dtype=torch.bfloat16)  # pitch 1024 > N
+    ops.gemm(A.cuda(), W.cuda(), C, M, N, K, act=3, row_exp2_offset=off.cuda(), m_limit=n_rows)
+    torch.cuda.synchronize()
+    ref = torch.exp2((A.double() @ W.double().T) * 1.4426950408889634 + off.double()[:, None])
+    got = C[:, :N].cpu().double()
+    assert ((got[:533] - ref[:533]).abs() / (ref[:533].abs() + 1e-6)).max() < 1.5e-2      # bf16 output
+    assert (C[640:, :N] == 9.0).all() and (C[:, N:] == 9.0).all()                          # skipped tiles / pitch untouched
+    # K limit + accumulate: D (+)= A^T . B over the first *k rows only
+    Kt, Mo, No = 900, 304, 512
+    X = (torch.randn(Kt, Mo, generator=g) * 0.3).to(torch.bfloat16)   # stored [K, M]  (A read MN-major)
+    Y = (torch.randn(Kt, No, generator=g) * 0.3).to(torch.bfloat16)   # stored [K, N]  (B read MN-major)
+    for kl in (0, 1, 450, 900, 5000):
+        klim = torch.tensor([kl + 100], dtype=torch.int32, device="cuda")
+        D = torch.full((Mo, No), 2.0, device="cuda")
+        ops.gemm(X.cuda(), Y.cuda(), D, Mo, No, Kt, a_mn=True, b_mn=True, out_mode=4, k_limit=klim, k_limit_base=100)
+        E = torch.full((Mo, No), 2.0, device="cuda")
+        ops.gemm(X.cuda(), Y.cuda(), E, Mo, No, Kt, a_mn=True, b_mn=True, out_mode=2, k_limit=klim, k_limit_base=100)
+        torch.cuda.synchronize()
+        k = min(kl, Kt)
+        refd = X[:k].double().T @ Y[:k].double()
+        assert (E.cpu().double() - refd).abs().max() < 5e-3, kl
+        assert (D.cpu().double() - 2.0 - refd).abs().max() < 5e-3, kl
+
+
+@pytest.mark.parametrize("T,n_valid,I,budget", [(700, 533, 3000, None), (700, 533, 3000, 256 * 3008 * 2), (384, 384, 1001, 1),
+                                                (512, 0, 640, None)])
+def test_ce_head_wide_hidden_matches_oracle(ops, T, n_valid, I, budget, monkeypatch):
+    """d = 512 (config 5): two-pass forward + chunked materialised-G backward, several chunk sizes (budget env)."""
+    d = 512
+    if budget is not None:
+        monkeypatch.setenv("RP_CE_WIDE_G_BYTES", str(budget))
+    g = torch.Generator().manual_seed(T + I)
+    hc = (torch.randn(T, d, generator=g) * 0.7).to(torch.bfloat16)
+    hc[n_valid:] = 0
+    table = (torch.randn(I, d, generator=g) * 0.15).to(torch.bfloat16)
+    labels = torch.randint(0, I, (T,), generator=g, dtype=torch.int64)
+    st = ops.CEHeadState(T, I, d, "cuda")
+    nv = torch.tensor([n_valid], dtype=torch.int32, device="cuda")
+    d_hc = torch.zeros(T, d, device="cuda", dtype=torch.bfloat16)
+    d_tab = torch.full((I + 1, d), 7.0, device="cuda", dtype=torch.float32)
+    out = ops.ce_head_fwd(st, hc.cuda(), table.cuda(), labels.int().cuda(), nv, d_hc=d_hc, n_valid_hint=n_valid)
+    ops.ce_head_bwd(st, hc.cuda(), table.cuda(), labels.int().cuda(), nv, d_hc, d_tab)
+    torch.cuda.synchronize()
+    if n_valid == 0:
+        assert (d_tab[:I] == 0).all() and (d_tab[I] == 7.0).all()
+        return
+    h64, e64 = hc[:n_valid].double().requires_grad_(True), table.double().requires_grad_(True)
+    logits = h64 @ e64.T
+    lse = torch.logsumexp(logits, -1)
+    loss = (lse - logits.gather(1, labels[:n_valid, None])[:, 0]).mean()
+    loss.backward()
+    assert abs(out[0].item() - loss.item()) < 2e-4 * max(1.0, abs(loss.item())), (out[0].item(), loss.item())
+    torch.testing.assert_close(st.lse[:n_valid].cpu().double(), lse.detach(), rtol=1e-5, atol=1e-4)
+    eh = (d_hc[:n_valid].cpu().double() - h64.grad).norm() / h64.grad.norm()
+    ee = (d_tab[:I].cpu().double() - e64.grad).norm() / e64.grad.norm()
+    assert eh < 1e-2 and ee < 1e-2, (eh, ee)
+    assert (d_tab[I] == 7.0).all()

@@ -87,10 +87,14 @@ int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, const i
 /* gradients of the mean CE for d(loss) = 1:  d_hc bf16 [capacity, d] (rows < *n_valid; already produced by the forward when
  * `fused` != 0 and the bound held, otherwise computed here); d_table fp32 [n_items, d] is OVERWRITTEN (softmax part) and
  * then atomically corrected by the one-hot part; d_bias fp32 [n_items] likewise iff bias.  `fused` must equal
- * (d_hc != NULL) of the matching forward call and then needs the same workspace.  d in {64,128,256}. */
+ * (d_hc != NULL) of the matching forward call and then needs the same workspace.  d in {64,128,256}: fused tcgen05 passes
+ * (logits never leave TMEM).  d = 512 (bias == NULL only): S plus a [128 x 512] fp32 accumulator exceed the 512 TMEM columns, so
+ * the softmax numerators of a token chunk are materialised in bf16 inside the workspace (chunk sized by RP_CE_WIDE_G_BYTES,
+ * default 8 GiB) and three GEMMs per chunk produce dH and dE; the workspace is then always required.
+ * n_valid_hint: host estimate of *n_valid (0 = unknown), load-balance only. */
 int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, const int32_t* labels, const int32_t* n_valid,
                    int capacity, int n_items, int d, const float* loss_out, const float* cvec, void* d_hc, float* d_table,
-                   float* d_bias, int fused, void* workspace, size_t workspace_bytes, void* stream);
+                   float* d_bias, int fused, int n_valid_hint, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Transformer body.  All activations are token-major bf16 [T = B*L, d]; weights are the bf16 shadow of the fp32 masters.

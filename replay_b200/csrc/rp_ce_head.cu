@@ -709,27 +709,31 @@ __global__ void ce_fused_finalize_kernel(const float* __restrict__ part_dh, cons
   }
 }
 
-// d = 512 path: dH[t, :] -= E[y_t, :] / T_v  (the one-hot part of softmax - onehot; the GEMM wrote softmax . E / T_v)
-__global__ void ce_dh_label_sub_kernel(__nv_bfloat16* __restrict__ d_hc, const __nv_bfloat16* __restrict__ table,
-                                       const int32_t* __restrict__ labels, const float* __restrict__ loss_inv,
-                                       const int32_t* __restrict__ n_valid_ptr, int d) {
+// d = 512 path: dH[c0 + r, :] = sum_s part[s][r, :] - E[y, :] / T_v   (split-K partials of softmax . E / T_v; the one-hot
+// part of softmax - onehot is subtracted here), rows c0 + r < *n_valid.  One warp per row.
+__global__ void ce_dh_reduce_kernel(const float* __restrict__ part, int n_splits, long long split_stride, int rows, int c0,
+                                    __nv_bfloat16* __restrict__ d_hc, const __nv_bfloat16* __restrict__ table,
+                                    const int32_t* __restrict__ labels, const float* __restrict__ loss_inv,
+                                    const int32_t* __restrict__ n_valid_ptr, int d) {
   const int n_valid = *n_valid_ptr;
   const float inv_n = loss_inv[0];
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < n_valid; t += gridDim.x * wpb) {
-    const uint4* e = reinterpret_cast<const uint4*>(table + (size_t)labels[t] * d);
-    uint4* o = reinterpret_cast<uint4*>(d_hc + (size_t)t * d);
-    for (int c = lane; c < d / 8; c += 32) {
-      const uint4 ev = e[c];
-      uint4 ov = o[c];
-      const __nv_bfloat162* e2 = reinterpret_cast<const __nv_bfloat162*>(&ev);
-      uint32_t* o32 = reinterpret_cast<uint32_t*>(&ov);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o32[q])), b = __bfloat1622float2(e2[q]);
-        o32[q] = pack_bf16(a.x - inv_n * b.x, a.y - inv_n * b.y);
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows && c0 + r < n_valid; r += gridDim.x * wpb) {
+    const int t = c0 + r;
+    const __nv_bfloat16* e = table + (size_t)labels[t] * d;
+    for (int c = lane * 4; c < d; c += 128) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int sp = 0; sp < n_splits; ++sp) {
+        const float4 v = *reinterpret_cast<const float4*>(part + (size_t)sp * split_stride + (size_t)r * d + c);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
       }
-      o[c] = ov;
+      const uint2 ev = *reinterpret_cast<const uint2*>(e + c);
+      const float2 e0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ev.x));
+      const float2 e1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ev.y));
+      uint2 o;
+      o.x = pack_bf16(a.x - inv_n * e0.x, a.y - inv_n * e0.y);
+      o.y = pack_bf16(a.z - inv_n * e1.x, a.w - inv_n * e1.y);
+      *reinterpret_cast<uint2*>(d_hc + (size_t)t * d + c) = o;
     }
   }
 }
@@ -748,11 +752,11 @@ static int wide_chunk_rows(int cap, int n_items) {
   return (int)rows;
 }
 
-static int pick_splits(int n_row_tiles, int n_col_tiles) {
+static int pick_splits(int n_row_tiles, int n_col_tiles, int max_splits = 8) {
   const int sms = sm_count();
   int best = 1;
   double best_eff = 0.0;
-  for (int p = 1; p <= 8 && p <= n_col_tiles; ++p) {
+  for (int p = 1; p <= max_splits && p <= n_col_tiles; ++p) {
     const long long ctas = (long long)n_row_tiles * p;
     const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
     if (eff > best_eff + 0.02) {
@@ -772,22 +776,28 @@ using namespace rp;
 struct CeWs {
   float2* part; float* block_sums; unsigned int* ticket; unsigned int* bound; int32_t* flag; float* zpart; float* part_dh;
 };
-static const int kMaxSplits = 8;
+static const int kMaxSplits = 8;       // fused forward + dH: partial gradients per split
+static const int kMaxSplitsFwd = 32;   // two-pass forward: only (max, sum) pairs per split
+static const int kWideSplitK = 16;     // d = 512 backward: split-K partials of the dH GEMM
 
 static size_t ce_ws_base_bytes(int cap, int d) {
-  return (size_t)cap * kMaxSplits * 2 * sizeof(float2) + 4096 + 64 + (size_t)kMaxSplits * kBwdCG * cap * 4 +
+  return (size_t)cap * kMaxSplitsFwd * 2 * sizeof(float2) + 4096 + 64 + (size_t)kMaxSplits * kBwdCG * cap * 4 +
          (d <= 256 ? (size_t)kMaxSplits * cap * d * 4 : 0) + 256;
 }
 static size_t ce_ws_bytes(int cap, int n_items, int d) {
   size_t b = (ce_ws_base_bytes(cap, d) + 1023) / 1024 * 1024;
-  if (d > 256) b += (size_t)wide_chunk_rows(cap, n_items) * wide_ldg(n_items) * 2;  // G chunk (bf16)
+  if (d > 256) {
+    const size_t rows = (size_t)wide_chunk_rows(cap, n_items);
+    b += rows * wide_ldg(n_items) * 2;              // G chunk (bf16)
+    b += (size_t)kWideSplitK * rows * d * 4;        // split-K partials of dH (fp32)
+  }
   return b;
 }
 static CeWs ce_ws(void* workspace, int cap, int d) {
   uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
   CeWs r;
   r.part = reinterpret_cast<float2*>(w);
-  w += (size_t)cap * kMaxSplits * 2 * sizeof(float2);
+  w += (size_t)cap * kMaxSplitsFwd * 2 * sizeof(float2);
   r.block_sums = reinterpret_cast<float*>(w);
   w += 4096;
   r.ticket = reinterpret_cast<unsigned int*>(w);
@@ -905,7 +915,7 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, 
     RP_LAUNCH_CHECK();
     skip = ws.flag;
   }
-  const int P2 = pick_splits(hint_tiles, n_item_tiles);
+  const int P2 = pick_splits(hint_tiles, n_item_tiles, kMaxSplitsFwd);
   switch (d) {
     case 64: rc = launch_ce_fwd<1, 8>(tmA, tmB, n_valid, n_items, P2, n_tok_tiles, bias, ws.part, skip, stream); break;
     case 128: rc = launch_ce_fwd<2, 8>(tmA, tmB, n_valid, n_items, P2, n_tok_tiles, bias, ws.part, skip, stream); break;
@@ -929,7 +939,7 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, 
 RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, const int32_t* labels,
                           const int32_t* n_valid, int capacity, int n_items, int d, const float* loss_out /* from fwd */,
                           const float* cvec /* from fwd */, void* d_hc, float* d_table, float* d_bias, int fused,
-                          void* workspace, size_t workspace_bytes, void* stream_) {
+                          int n_valid_hint, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!hc || !table || !labels || !n_valid || !loss_out || !cvec || !d_hc || !d_table) return RP_EINVAL;
   if ((bias == nullptr) != (d_bias == nullptr)) return RP_EINVAL;
@@ -941,7 +951,10 @@ RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, 
     if (bias) return RP_ESHAPE;  // biased (BERT4Rec) head at d = 512 is not built
     const long long ldg = wide_ldg(n_items);
     const int chunk = wide_chunk_rows(capacity, n_items);
-    void* G = reinterpret_cast<uint8_t*>(workspace) + (ce_ws_base_bytes(capacity, d) + 1023) / 1024 * 1024;
+    uint8_t* G = reinterpret_cast<uint8_t*>(workspace) + (ce_ws_base_bytes(capacity, d) + 1023) / 1024 * 1024;
+    float* part = reinterpret_cast<float*>(G + (size_t)chunk * ldg * 2);
+    const long long part_stride = (long long)chunk * d;
+    const int hint = (n_valid_hint > 0 && n_valid_hint < capacity) ? n_valid_hint : capacity;
     int rc;
     for (int c0 = 0, it = 0; c0 < capacity; c0 += chunk, ++it) {
       const int rows = (capacity - c0 < chunk) ? capacity - c0 : chunk;
@@ -955,15 +968,25 @@ RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, 
       g.C = G; g.ldc = ldg; g.out_mode = 0; g.act = 3; g.row_exp2_offset = cvec + c0;
       g.m_limit_dev = n_valid; g.m_limit_base = c0;
       if ((rc = rp_gemm(&g, stream_)) != RP_OK) return rc;
-      // dH[c0:c0+rows] = G . E            (A = G K-major over the items, B = E read MN-major)
+      // dH[c0:c0+rows] = G . E - onehot   (A = G K-major over the items, B = E read MN-major).  Few row tiles against a
+      // contraction over the whole catalog: split-K partials (fp32, deterministic), reduced together with the label term
+      int live = hint - c0;
+      live = live < 128 ? 128 : (live > rows ? rows : live);
+      int split = (2 * sm_count()) / (((live + 127) / 128) * (d / 128));
+      split = split < 1 ? 1 : (split > kWideSplitK ? kWideSplitK : split);
       memset(&g, 0, sizeof(g));
-      g.batch = 1; g.inner = 1; g.alpha = 1.f; g.split_k = 1;
+      g.batch = 1; g.inner = 1; g.alpha = 1.f; g.split_k = split;
       g.A = G; g.a_rows = rows; g.a_cols = n_items; g.lda = ldg; g.a_mn = 0;
       g.B = table; g.b_rows = n_items; g.b_cols = d; g.ldb = d; g.b_mn = 1;
       g.M = rows; g.N = d; g.K = n_items;
-      g.C = reinterpret_cast<__nv_bfloat16*>(d_hc) + (size_t)c0 * d; g.ldc = d; g.out_mode = 0;
+      g.C = part; g.ldc = d; g.out_mode = 3; g.c_split_stride = part_stride;
       g.m_limit_dev = n_valid; g.m_limit_base = c0;
       if ((rc = rp_gemm(&g, stream_)) != RP_OK) return rc;
+      ce_dh_reduce_kernel<<<sm_count() * 4, 256, 0, stream>>>(part, split, part_stride, rows, c0,
+                                                               reinterpret_cast<__nv_bfloat16*>(d_hc),
+                                                               reinterpret_cast<const __nv_bfloat16*>(table), labels,
+                                                               loss_out + 1, n_valid, d);
+      RP_LAUNCH_CHECK();
       // dE (+)= G^T . hc[c0:c0+rows]      (A = G read MN-major, contraction over the chunk's valid tokens)
       memset(&g, 0, sizeof(g));
       g.batch = 1; g.inner = 1; g.alpha = 1.f; g.split_k = 1;
@@ -974,10 +997,6 @@ RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, 
       g.k_limit_dev = n_valid; g.k_limit_base = c0;
       if ((rc = rp_gemm(&g, stream_)) != RP_OK) return rc;
     }
-    ce_dh_label_sub_kernel<<<sm_count() * 4, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(d_hc),
-                                                                reinterpret_cast<const __nv_bfloat16*>(table), labels,
-                                                                loss_out + 1, n_valid, d);
-    RP_LAUNCH_CHECK();
     ce_label_scatter_kernel<<<sm_count() * 4, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hc), labels, loss_out + 1,
                                                                  n_valid, d, d_table, d_bias);
     RP_LAUNCH_CHECK();

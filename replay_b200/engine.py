@@ -413,7 +413,8 @@ class SasRecEngine:
         st = self._stream
         from .ops import ce_head_bwd
 
-        ce_head_bwd(self.ce, self.hc, p16["item_emb"][: cfg.n_items], self.labels_c, self.n_valid, s["dhc"], G["item_emb"])
+        ce_head_bwd(self.ce, self.hc, p16["item_emb"][: cfg.n_items], self.labels_c, self.n_valid, s["dhc"], G["item_emb"],
+                    n_valid_hint=self.n_valid_hint)
         self.lib.count += 3
         dx = s["dxa"]
         dx.zero_()

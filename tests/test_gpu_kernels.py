@@ -205,7 +205,7 @@ def test_gemm_exp2_epilogue_dynamic_limits_and_accumulate(ops):
         E = torch.full((Mo, No), 2.0, device="cuda")
         ops.gemm(X.cuda(), Y.cuda(), E, Mo, No, Kt, a_mn=True, b_mn=True, out_mode=2, k_limit=klim, k_limit_base=100)
         torch.cuda.synchronize()
-        k = min(kl, Kt)
+        k = min((kl + 63) // 64 * 64, Kt)  # the limit acts on whole 64-row contraction chunks
         refd = X[:k].double().T @ Y[:k].double()
         assert (E.cpu().double() - refd).abs().max() < 5e-3, kl
         assert (D.cpu().double() - 2.0 - refd).abs().max() < 5e-3, kl

@@ -245,6 +245,35 @@ int rp_cast_bf16(const float* src, void* dst, long long n, void* stream);
 int rp_counter_add(unsigned long long* counter, unsigned long long inc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Sampled training heads: logits only for the positive item and n_neg sampled negatives per target.
+ *   replaces  SampledLossBase.get_sampled_logits + mask_negative_logits   replay/nn/loss/base.py:40-154,157-196
+ *             CESampled.forward / BCESampled.forward                      replay/nn/loss/ce.py:199-249 ; bce.py:154-218
+ *             legacy _compute_loss_ce_sampled / _compute_loss_bce_sampled  replay/models/nn/sequential/sasrec/lightning.py:310-376
+ * hc / labels / n_valid as for rp_ce_head_fwd (compacted valid targets).  negatives int64: neg_mode 0 = [n_neg] shared by the
+ * batch (tensor-core path), 1 = [B*seq_len, n_neg] per position, 2 = [B, n_neg] per sequence (1, 2: rows addressed through
+ * valid_idx[t] = flat b*seq_len + l of compacted row t; gather-dot kernels).  kind: RP_LOSS_CE_SAMPLED (negatives equal to the
+ * positive or to ignore_index get logit -1e9), RP_LOSS_BCE_SAMPLED (same masking, log_eps / clamp as the reference),
+ * RP_LOSS_LEGACY_CE_SAMPLED (log(vocab_size-1) - 1e6*reject - log(n_neg - #reject) correction), RP_LOSS_LEGACY_BCE_SAMPLED (no
+ * masking).  One positive per position.  fwd: loss_out[0] = mean loss, loss_out[1] = 1/T_v, d(loss)/d(logits) stays in the
+ * workspace; bwd: d_hc bf16 [capacity, d] rows < *n_valid, d_table fp32 ACCUMULATED (zero it first; dense rows untouched).
+ * ------------------------------------------------------------------------------------------------------------- */
+#define RP_LOSS_CE_SAMPLED 0
+#define RP_LOSS_BCE_SAMPLED 1
+#define RP_LOSS_LEGACY_CE_SAMPLED 2
+#define RP_LOSS_LEGACY_BCE_SAMPLED 3
+typedef struct rp_sampled_desc {
+  const void* hc; const void* table; const int32_t* labels; const int32_t* valid_idx; const int64_t* negatives;
+  const int32_t* n_valid;
+  int capacity, n_items, d, n_neg, neg_mode, seq_len, kind, ignore_index, vocab_size;
+  float log_eps, clamp;
+  float* loss_out;
+  void* workspace; size_t workspace_bytes;
+} rp_sampled_desc;
+size_t rp_sampled_head_workspace(int capacity, int d, int n_neg, int neg_mode);
+int rp_sampled_head_fwd(const rp_sampled_desc* s, void* stream);
+int rp_sampled_head_bwd(const rp_sampled_desc* s, void* d_hc, float* d_table, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Device-side batch construction.  All histories are resident in HBM as CSR: offsets [n_seq+1] int64,
  * items [offsets[n_seq]] int32.  One call builds B rows of a [B, L] batch: row b is the window of history seq_index[b]
  * starting at seq_offset[b] (NULL: the LAST L(+1) items), left-padded with pad_value.  Replaces the per-sample host path

@@ -290,6 +290,97 @@ def gen_dataset_layout():
     print("wrote dataset_layout", {k: np.asarray(v).shape for k, v in out.items() if k.endswith("_ids")})
 
 
+def gen_sampled_losses():
+    """Real reference sampled losses on the weights / batch of sasrec_new_tiny (new path: CESampled, BCESampled with the three
+    negative shapes incl. collisions with the positive and an ignore index) and of sasrec_legacy_tiny (legacy module's
+    _compute_loss_ce_sampled / _compute_loss_bce_sampled with the internally drawn negatives captured)
+    -> tests/golden/sampled_losses.npz (losses + gradient of the item table and of one block weight)."""
+    from replay.nn.loss import BCESampled, CESampled
+    from replay.models.nn.sequential.sasrec.lightning import SasRec as LegacySasRec
+
+    out = {}
+    z = np.load(os.path.join(OUT, "sasrec_new_tiny.npz"))
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}
+    n_items, d, H, L, nb = int(z["n_items"]), int(z["d"]), int(z["H"]), int(z["L"]), int(z["n_blocks"])
+    ids, pm = torch.from_numpy(z["ids"]), torch.from_numpy(z["pad_mask"])
+    labels, tm = torch.from_numpy(z["labels"]), torch.from_numpy(z["target_mask"])
+    B = ids.shape[0]
+    g = torch.Generator().manual_seed(77)
+    N = 37
+    negs = {"shared": torch.randint(0, n_items, (N,), generator=g),
+            "perseq": torch.randint(0, n_items, (B, N), generator=g),
+            "perpos": torch.randint(0, n_items, (B, L, N), generator=g)}
+    # force collisions with the positive (several per row) and entries equal to the ignore index
+    ignore = 5
+    negs["shared"][3] = labels[tm][0]
+    negs["shared"][7] = ignore
+    negs["perseq"][:, 2] = labels[:, -1]
+    negs["perseq"][1, 4] = ignore
+    negs["perpos"][:, :, 1] = labels.clamp(max=n_items - 1)
+    negs["perpos"][:, :, 9] = labels.clamp(max=n_items - 1)
+    negs["perpos"][0, -1, 5] = ignore
+    for k, v in negs.items():
+        out["neg_" + k] = v.numpy()
+    out["ignore_index"] = ignore
+    for lname, mk in (("ce", lambda: CESampled(negative_labels_ignore_index=ignore)),
+                      ("bce", lambda: BCESampled(negative_labels_ignore_index=ignore))):
+        for shape, neg in negs.items():
+            model = SasRec.from_params(schema(n_items, d, n_items), embedding_dim=d, num_heads=H, num_blocks=nb,
+                                       max_sequence_length=L, dropout=0.0)
+            model.load_state_dict(sd)
+            model.loss = mk()
+            model.loss.logits_callback = model.get_logits
+            model.train()
+            res = model(feature_tensors={"item_id": ids}, padding_mask=pm, positive_labels=labels.unsqueeze(-1),
+                        negative_labels=neg, target_padding_mask=tm.unsqueeze(-1))
+            res["loss"].backward()
+            gr = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+            ek = [k for k in gr if "item_id" in k or "item_emb" in k]
+            wk = [k for k in gr if k.endswith("in_proj_weight")]
+            out[f"new_{lname}_{shape}_loss"] = res["loss"].detach().numpy()
+            out[f"new_{lname}_{shape}_gE"] = gr[ek[0]].numpy().copy()
+            out[f"new_{lname}_{shape}_gW"] = gr[wk[0]].numpy().copy()
+            print("new", lname, shape, float(res["loss"]), ek[0], wk[0])
+
+    # ---- legacy module: negatives are drawn inside the loss (torch.randint per valid target); capture them
+    zl = np.load(os.path.join(OUT, "sasrec_legacy_tiny.npz"))
+    sdl = {k[4:]: torch.from_numpy(zl[k]) for k in zl.files if k.startswith("sd::")}
+    n_items, d, H, L, nb = int(zl["n_items"]), int(zl["d"]), int(zl["H"]), int(zl["L"]), int(zl["n_blocks"])
+    ids, pm = torch.from_numpy(zl["ids"]), torch.from_numpy(zl["pad_mask"])
+    labels, tm = torch.from_numpy(zl["labels"]), torch.from_numpy(zl["target_mask"])
+    for lname, ltype in (("ce", "CE"), ("bce", "BCE")):
+        mod = LegacySasRec(schema(n_items, d, n_items), block_count=nb, head_count=H, hidden_size=d, max_seq_len=L,
+                           dropout_rate=0.0, loss_type=ltype, loss_sample_count=23)
+        mod._model.load_state_dict(sdl)
+        mod.train()
+        rec = {}
+        orig = torch.randint
+
+        def wrap(*a, **k):
+            r = orig(*a, **k)
+            rec["neg"] = r.clone()
+            return r
+
+        torch.manual_seed(5)
+        torch.randint = wrap
+        try:
+            fn = mod._compute_loss_ce_sampled if ltype == "CE" else mod._compute_loss_bce_sampled
+            loss = fn({"item_id": ids}, labels, pm, tm)
+        finally:
+            torch.randint = orig
+        loss.backward()
+        gr = {k: p.grad for k, p in mod._model.named_parameters() if p.grad is not None}
+        ek = [k for k in gr if "item_emb" in k]
+        wk = [k for k in gr if k.endswith("in_proj_weight")]
+        out[f"legacy_{lname}_neg"] = rec["neg"].numpy()          # [M, 23] in valid-target order
+        out[f"legacy_{lname}_loss"] = loss.detach().numpy()
+        out[f"legacy_{lname}_gE"] = gr[ek[0]].numpy().copy()
+        out[f"legacy_{lname}_gW"] = gr[wk[0]].numpy().copy()
+        print("legacy", lname, float(loss), rec["neg"].shape, ek[0], wk[0])
+    np.savez_compressed(os.path.join(OUT, "sampled_losses.npz"), **out)
+    print("wrote sampled_losses")
+
+
 if __name__ == "__main__":
     # shapes respect the CUDA path's tile constraints: hidden in {64,128,256,512}, head_dim in {64,128}
     gen_new_sasrec("tiny", B=6, L=16, d=64, H=1, n_items=300, n_blocks=2, seed=11)
@@ -299,3 +390,4 @@ if __name__ == "__main__":
     gen_bert4rec("tiny_tied", B=6, L=16, d=64, H=1, n_items=300, n_blocks=2, seed=15, tying=True)
     gen_seen_filter_known_answers()
     gen_dataset_layout()
+    gen_sampled_losses()

@@ -74,6 +74,9 @@ def lib():
     _sig(L.rp_bert_embed_bwd, c_int, [P, P, P, P, c_int, c_int, c_int, c_float, U64, U64, P, P, P, P, P])
     _sig(L.rp_attn_last, c_int, [P, P, P, LL, LL, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P])
     _sig(L.rp_gather_rows, c_int, [P, P, c_int, P, c_int, P, c_int, P])
+    _sig(L.rp_sampled_head_workspace, c_size_t, [c_int, c_int, c_int, c_int])
+    _sig(L.rp_sampled_head_fwd, c_int, [P, P])
+    _sig(L.rp_sampled_head_bwd, c_int, [P, P, P, P])
     _sig(L.rp_build_batch, c_int, [P, P, LL, P, P, c_int, c_int, c_int, c_int, c_float, P, U64, U64, P, P, P, P, P, P, P])
     for name, restype, argtypes in _EXTRA_SIGS:
         _sig(getattr(L, name), restype, argtypes)
@@ -101,6 +104,20 @@ class GemmDesc(ctypes.Structure):
         ("c_split_stride", ctypes.c_longlong),
         ("row_exp2_offset", c_void_p), ("m_limit_dev", c_void_p), ("m_limit_base", c_int),
         ("k_limit_dev", c_void_p), ("k_limit_base", c_int),
+    ]
+
+
+class SampledDesc(ctypes.Structure):
+    """Mirror of ``struct rp_sampled_desc`` (include/rp_b200.h)."""
+
+    _fields_ = [
+        ("hc", c_void_p), ("table", c_void_p), ("labels", c_void_p), ("valid_idx", c_void_p), ("negatives", c_void_p),
+        ("n_valid", c_void_p),
+        ("capacity", c_int), ("n_items", c_int), ("d", c_int), ("n_neg", c_int), ("neg_mode", c_int), ("seq_len", c_int),
+        ("kind", c_int), ("ignore_index", c_int), ("vocab_size", c_int),
+        ("log_eps", c_float), ("clamp", c_float),
+        ("loss_out", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", c_size_t),
     ]
 
 

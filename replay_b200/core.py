@@ -131,14 +131,40 @@ class SasRecCore(torch.nn.Module):
             self._import(sd)
         return torch.nn.modules.module._IncompatibleKeys(sorted(missing), [])
 
+    # ---- loss selection (full-catalog CE by default; sampled heads: SURVEY §8 a9)
+    def set_loss(self, kind: str = "ce", **kw):
+        """Remembered across engine re-creations; see SasRecEngine.set_loss."""
+        self._loss_spec = (kind, kw)
+        if self.engine is not None:
+            self.engine._loss_applied = None  # re-applied with the negatives' shape when the next batch is staged
+            if kind == "ce":
+                self.engine.set_loss("ce")
+
+    def _stage(self, eng, ids, pad_mask, labels, target_mask, negatives):
+        spec = getattr(self, "_loss_spec", ("ce", {}))
+        if spec[0] != "ce":
+            shape = {1: "shared", 2: "perseq", 3: "perpos"}[negatives.dim()]
+            want = dict(spec[1], n_neg=negatives.shape[-1], neg_shape=shape)
+            if eng.sampled is None or getattr(eng, "_loss_applied", None) != (spec[0], tuple(sorted(want.items()))):
+                eng.set_loss(spec[0], **want)
+                eng._loss_applied = (spec[0], tuple(sorted(want.items())))
+        elif eng.sampled is not None:
+            eng.set_loss("ce")
+        eng.set_batch(ids, pad_mask, labels, target_mask)
+        if eng.sampled is not None:
+            if negatives is None:
+                raise ValueError("this loss needs negative_labels")
+            eng.set_negatives(negatives)
+
     # ---- training / inference on [B, L] batches
-    def loss(self, ids, pad_mask, labels, target_mask) -> torch.Tensor:
+    def loss(self, ids, pad_mask, labels, target_mask, negatives=None) -> torch.Tensor:
         B, L = ids.shape
         eng = self.ensure_engine(B, L, with_grad=True)
-        eng.set_batch(ids, pad_mask, labels, target_mask)
+        self._stage(eng, ids, pad_mask, labels, target_mask, negatives)
         return _EngineLoss.apply(self.flat, self)
 
-    def fused_step(self, ids, pad_mask, labels, target_mask, all_reduce=None, lr: float | None = None) -> torch.Tensor:
+    def fused_step(self, ids, pad_mask, labels, target_mask, all_reduce=None, lr: float | None = None,
+                   negatives=None) -> torch.Tensor:
         """forward + backward + Adam entirely inside the engine (no autograd, no torch optimizer)."""
         B, L = ids.shape
         eng = self.ensure_engine(B, L, with_grad=True)
@@ -148,7 +174,7 @@ class SasRecCore(torch.nn.Module):
         if lr is not None and lr != getattr(self, "_lr_set", None):
             eng.lr.fill_(lr)
             self._lr_set = lr
-        eng.set_batch(ids, pad_mask, labels, target_mask)
+        self._stage(eng, ids, pad_mask, labels, target_mask, negatives)
         return eng.train_step(all_reduce)[0]
 
     def mark_params_updated(self):

@@ -18,7 +18,7 @@ from dataclasses import dataclass
 
 import torch
 
-from ._lib import AttnBwdDesc, AttnDesc, GemmDesc, check, lib
+from ._lib import SampledDesc, AttnBwdDesc, AttnDesc, GemmDesc, check, lib
 
 
 @dataclass
@@ -63,7 +63,7 @@ class _CountingLib:
     KERNELS = {"rp_gemm": 1, "rp_attn_fwd": 1, "rp_attn_bwd": 1, "rp_attn_last": 1, "rp_attn_softmax_bwd": 1, "rp_prepare_batch": 2, "rp_embed_fwd": 1,
                "rp_embed_bwd": 2, "rp_layernorm_fwd": 1, "rp_layernorm_bwd": 1, "rp_dropout_bwd": 1, "rp_colsum": 1,
                "rp_adam_step": 2, "rp_cast_bf16": 1, "rp_counter_add": 1, "rp_reduce_splits": 1, "rp_ce_head_fwd": 2, "rp_ce_head_bwd": 3,
-               "rp_score_topk": 2, "rp_seen_prepare": 1}
+               "rp_score_topk": 2, "rp_seen_prepare": 1, "rp_sampled_head_fwd": 4, "rp_sampled_head_bwd": 4}
 
     def __init__(self, L):
         self._L = L
@@ -131,6 +131,7 @@ class SasRecEngine:
         self.training = with_grad
         # fused tcgen05 attention backward: head_dim 64, L <= 256; otherwise saved probabilities + batched GEMMs
         self.fused_attn_bwd = (cfg.d // cfg.n_heads) == 64 and seq_len <= 256
+        self.sampled = None       # full-catalog CE unless set_loss() selects a sampled head
         self.fused_ce = True      # single-pass CE forward + dH (guarded on the device by a bound on |logit|)
         self.n_valid_hint = 0     # host estimate of the number of valid targets per step (load balance of the CE head only)
         self._alloc_workspace()
@@ -322,6 +323,49 @@ class SasRecEngine:
             self.in_pad[n:].zero_()
             self.in_tmask[n:].zero_()
 
+    # ------------------------------------------------------------------------------------------------ sampled heads
+    SAMPLED_KINDS = {"ce_sampled": 0, "bce_sampled": 1, "legacy_ce_sampled": 2, "legacy_bce_sampled": 3}
+
+    def set_loss(self, kind: str = "ce", n_neg: int = 0, neg_shape: str = "shared", ignore_index: int = -100,
+                 log_eps: float = 1e-6, clamp: float = 100.0):
+        """``"ce"`` = full-catalog CE (default).  Sampled heads: ``ce_sampled`` / ``bce_sampled`` (new path,
+        replay/nn/loss/ce.py:146, bce.py:98) and ``legacy_ce_sampled`` / ``legacy_bce_sampled`` (sasrec/lightning.py:310-376)
+        with ``n_neg`` negatives per target, ``neg_shape`` in shared [N] / perseq [B, N] / perpos [B, L, N]."""
+        if kind == "ce":
+            self.sampled = None
+            return
+        if kind not in self.SAMPLED_KINDS:
+            raise NotImplementedError(f"Not supported loss_type {kind!r}")
+        mode = {"shared": 0, "perpos": 1, "perseq": 2}[neg_shape]
+        rows = {0: 1, 1: self.T, 2: self.B}[mode]
+        ws_bytes = self.lib.rp_sampled_head_workspace(self.T, self.cfg.d, n_neg, mode)
+        self.sampled = dict(kind=self.SAMPLED_KINDS[kind], n_neg=n_neg, mode=mode, ignore_index=ignore_index, log_eps=log_eps,
+                            clamp=clamp, neg=torch.zeros(rows, n_neg, device=self.dev, dtype=torch.int64),
+                            ws=torch.zeros(ws_bytes, device=self.dev, dtype=torch.uint8), ws_bytes=ws_bytes)
+
+    def set_negatives(self, negative_labels):
+        """Stage the negatives of the current batch ([N] | [B, N] | [B, L, N] int64, device copy)."""
+        sp = self.sampled
+        if sp is None:
+            raise RuntimeError("set_loss(<sampled kind>, ...) first")
+        neg = negative_labels.reshape(-1, sp["n_neg"])
+        if neg.shape[0] > sp["neg"].shape[0]:
+            raise ValueError(f"negative_labels {tuple(negative_labels.shape)} do not fit the configured shape")
+        sp["neg"][: neg.shape[0]].copy_(neg, non_blocking=True)
+
+    def _sampled_desc(self):
+        sp, cfg = self.sampled, self.cfg
+        sd = SampledDesc()
+        sd.hc, sd.table = self.hc.data_ptr(), self.params16["item_emb"].data_ptr()
+        sd.labels, sd.valid_idx, sd.negatives = self.labels_c.data_ptr(), self.valid_idx.data_ptr(), sp["neg"].data_ptr()
+        sd.n_valid = self.n_valid.data_ptr()
+        sd.capacity, sd.n_items, sd.d, sd.n_neg, sd.neg_mode, sd.seq_len = self.T, cfg.n_items, cfg.d, sp["n_neg"], sp["mode"], self.L
+        sd.kind, sd.ignore_index, sd.vocab_size = sp["kind"], sp["ignore_index"], cfg.n_items
+        sd.log_eps, sd.clamp = sp["log_eps"], sp["clamp"]
+        sd.loss_out = self.ce.loss.data_ptr()
+        sd.workspace, sd.workspace_bytes = sp["ws"].data_ptr(), sp["ws_bytes"]
+        return sd
+
     def _prepare(self, with_targets: bool):
         cfg = self.cfg
         check(self.lib.rp_prepare_batch(self.in_ids.data_ptr(), self.in_pad.data_ptr(),
@@ -395,6 +439,9 @@ class SasRecEngine:
         self._body_forward(True)
         self._ln_fwd(self.x[-1], self.params["lnf_w"], self.params["lnf_b"], cfg.lnf_eps, self.hc, self.meanf, self.rstdf, T,
                      gather=self.valid_idx, n_rows_dev=self.n_valid)
+        if self.sampled is not None:
+            check(self.lib.rp_sampled_head_fwd(ctypes.byref(self._sampled_desc()), self._stream()), "rp_sampled_head_fwd")
+            return self.ce.loss
         from .ops import ce_head_fwd
 
         self.lib.count += 2
@@ -413,9 +460,14 @@ class SasRecEngine:
         st = self._stream
         from .ops import ce_head_bwd
 
-        ce_head_bwd(self.ce, self.hc, p16["item_emb"][: cfg.n_items], self.labels_c, self.n_valid, s["dhc"], G["item_emb"],
-                    n_valid_hint=self.n_valid_hint)
-        self.lib.count += 3
+        if self.sampled is not None:
+            G["item_emb"].zero_()  # the sampled head accumulates sparse rows (the full-CE head overwrites the dense table)
+            check(self.lib.rp_sampled_head_bwd(ctypes.byref(self._sampled_desc()), s["dhc"].data_ptr(), G["item_emb"].data_ptr(),
+                                               st()), "rp_sampled_head_bwd")
+        else:
+            ce_head_bwd(self.ce, self.hc, p16["item_emb"][: cfg.n_items], self.labels_c, self.n_valid, s["dhc"], G["item_emb"],
+                        n_valid_hint=self.n_valid_hint)
+            self.lib.count += 3
         dx = s["dxa"]
         dx.zero_()
         self._ln_bwd(s["dhc"], self.x[-1], prm["lnf_w"], self.meanf, self.rstdf, dx, G["lnf_w"], G["lnf_b"], T,

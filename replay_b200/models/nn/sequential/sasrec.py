@@ -80,12 +80,21 @@ class SasRec(LightningModuleBase):
                  fused_optimizer: bool = True, device=None):
         super().__init__()
         self.save_hyperparameters()
-        if loss_type != "CE" or loss_sample_count is not None:
-            raise NotImplementedError("Not supported loss_type")  # lightning.py:485 ; sampled losses: SURVEY §8(f)
+        if loss_type not in ("CE", "BCE") or (loss_type == "BCE" and loss_sample_count is None):
+            raise NotImplementedError("Not supported loss_type")  # lightning.py:485 ; full-catalog BCE / SCE: no fused head
+        if negative_sampling_strategy not in {"global_uniform", "inbatch"}:
+            raise AssertionError("negative_sampling_strategy must be 'global_uniform' or 'inbatch'")
+        if loss_sample_count is not None and negative_sampling_strategy != "global_uniform":
+            raise NotImplementedError("only the 'global_uniform' negative sampling strategy has a fused head")
         self._model = SasRecModel(tensor_schema, num_blocks=block_count, num_heads=head_count, hidden_size=hidden_size,
                                   max_len=max_seq_len, dropout=dropout_rate, ti_modification=ti_modification,
                                   time_span=time_span, device=device)
         self._schema = tensor_schema
+        self._loss_type, self._loss_sample_count = loss_type, loss_sample_count
+        self._negative_sampling_strategy, self._negatives_sharing = negative_sampling_strategy, negatives_sharing
+        self._vocab_size = self._model.item_count
+        if loss_sample_count is not None:
+            self._model.core.set_loss("legacy_ce_sampled" if loss_type == "CE" else "legacy_bce_sampled")
         self._optimizer_factory = optimizer_factory
         self._lr_scheduler_factory = lr_scheduler_factory
         self._candidates_to_score = None
@@ -100,14 +109,23 @@ class SasRec(LightningModuleBase):
     def load_state_dict(self, sd, strict=True, assign=False):
         return self._model.load_state_dict({k[len("_model."):]: v for k, v in sd.items() if k.startswith("_model.")}, strict)
 
+    def _sample_negatives(self, ids):
+        """lightning.py:394-472, 'global_uniform': one shared draw without replacement (negatives_sharing) or an independent
+        uniform draw per position.  Drawn on the device with torch's generator (the reference draws inside the loss too)."""
+        n = min(self._loss_sample_count, self._vocab_size)
+        if self._negatives_sharing:
+            return torch.multinomial(torch.ones(self._vocab_size, device=ids.device), n, replacement=False)
+        return torch.randint(0, self._vocab_size, (*ids.shape, n), device=ids.device, dtype=torch.long)
+
     def training_step(self, batch: dict, batch_idx: int = 0):
         ids = batch["feature_tensor"][self._model.item_feature_name]
         args = (ids, batch["padding_mask"], batch["positive_labels"], batch["target_padding_mask"])
         core = self._model.core
+        neg = self._sample_negatives(ids) if self._loss_sample_count is not None else None
         if self.fused_optimizer:
-            loss = core.fused_step(*args, lr=self._lr)
+            loss = core.fused_step(*args, lr=self._lr, negatives=neg)
         else:
-            loss = core.loss(*args)
+            loss = core.loss(*args, negatives=neg)
         self.log("train_loss", loss, on_step=True, on_epoch=True, prog_bar=True, sync_dist=True)
         return loss
 

@@ -9,14 +9,29 @@ import warnings
 import torch
 
 from ...core import SasRecCore
+from ..loss import CE
 from ...engine import EncoderConfig
 from ...schema import item_feature_of
 
 
 class SasRec(torch.nn.Module):
-    def __init__(self, core: SasRecCore):
+    def __init__(self, core: SasRecCore, loss=None):
         super().__init__()
         self.core = core
+        self.loss = loss if loss is not None else CE(ignore_index=core.cfg.n_items)
+
+    @property
+    def loss(self):
+        """The reference's ``SasRec.loss`` attribute (model.py:181-197): assign ``CE`` / ``CESampled`` / ``BCESampled`` from
+        ``replay_b200.nn.loss`` to select the fused head."""
+        return self._loss
+
+    @loss.setter
+    def loss(self, spec):
+        if not hasattr(spec, "kind"):
+            raise NotImplementedError(f"loss {type(spec).__name__} has no fused CUDA head (supported: CE, CESampled, BCESampled)")
+        self._loss = spec
+        self.core.set_loss(spec.kind, **spec.engine_kwargs())
 
     @classmethod
     def from_params(cls, schema, embedding_dim: int = 192, num_heads: int = 4, num_blocks: int = 2,
@@ -67,7 +82,10 @@ class SasRec(torch.nn.Module):
         if target_padding_mask is not None and target_padding_mask.dim() == 3:
             target_padding_mask = target_padding_mask[..., 0]
         ids = feature_tensors[self.core.item_feature]
-        loss = self.core.loss(ids, padding_mask, positive_labels, target_padding_mask)
+        if self._loss.needs_negatives and negative_labels is None:
+            raise ValueError(f"{type(self._loss).__name__} needs negative_labels")
+        loss = self.core.loss(ids, padding_mask, positive_labels, target_padding_mask,
+                              negatives=negative_labels if self._loss.needs_negatives else None)
         return {"loss": loss, "hidden_states": ()}
 
     def forward_inference(self, feature_tensors, padding_mask, candidates_to_score=None):

@@ -148,3 +148,43 @@ def test_dataset_restatement_matches_reference_samples():
     for tag, p_ in (("p0", 0.0), ("p2", 2.0)):
         got = np.stack([od.bert_token_mask(z["bert_last_pad"][r], np.full(L, 0.5, np.float32), p_) for r in range(len(seqs))])
         assert np.array_equal(got, z[f"bert_{tag}_tok"])
+
+
+# ------------------------------------------------------------------------------------------------ sampled losses (§8 a9/f.2)
+def _scatter_neg(neg_valid, tm):
+    """[M, N] negatives in valid-target order -> [B, L, N] (the layout the restatement / the CUDA path take)."""
+    out = torch.zeros(*tm.shape, neg_valid.shape[1], dtype=torch.int64)
+    out[tm] = neg_valid
+    return out
+
+
+@pytest.mark.parametrize("loss", ["ce", "bce"])
+@pytest.mark.parametrize("shape", ["shared", "perseq", "perpos"])
+def test_sampled_losses_new_path_match_reference(golden_dir, loss, shape):
+    from oracle import sampled as osm
+    z, sd = load(golden_dir, "sasrec_new_tiny.npz")
+    zs = np.load(os.path.join(golden_dir, "sampled_losses.npz"))
+    P = osr.params_from_new_state_dict(sd)
+    ids, pm = torch.from_numpy(z["ids"]), torch.from_numpy(z["pad_mask"])
+    labels, tm = torch.from_numpy(z["labels"]), torch.from_numpy(z["target_mask"])
+    neg = torch.from_numpy(zs["neg_" + shape])
+    l, G = osm.loss_and_grads(P, ids, pm, labels, tm, neg, int(z["H"]), loss, ignore_index=int(zs["ignore_index"]))
+    torch.testing.assert_close(l, torch.from_numpy(zs[f"new_{loss}_{shape}_loss"]), rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(G["item_emb"], torch.from_numpy(zs[f"new_{loss}_{shape}_gE"]), rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(G["blocks"][0]["in_w"], torch.from_numpy(zs[f"new_{loss}_{shape}_gW"]), rtol=1e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("loss", ["ce", "bce"])
+def test_sampled_losses_legacy_match_reference(golden_dir, loss):
+    from oracle import sampled as osm
+    z, sd = load(golden_dir, "sasrec_legacy_tiny.npz")
+    zs = np.load(os.path.join(golden_dir, "sampled_losses.npz"))
+    P = osr.params_from_legacy_state_dict(sd)
+    ids, pm = torch.from_numpy(z["ids"]), torch.from_numpy(z["pad_mask"])
+    labels, tm = torch.from_numpy(z["labels"]), torch.from_numpy(z["target_mask"])
+    neg = _scatter_neg(torch.from_numpy(zs[f"legacy_{loss}_neg"]), tm)
+    kw = dict(vocab_size=int(z["n_items"])) if loss == "ce" else {}
+    l, G = osm.loss_and_grads(P, ids, pm, labels, tm, neg, int(z["H"]), "legacy_" + loss, variant="legacy", **kw)
+    torch.testing.assert_close(l, torch.from_numpy(zs[f"legacy_{loss}_loss"]), rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(G["item_emb"], torch.from_numpy(zs[f"legacy_{loss}_gE"]), rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(G["blocks"][0]["in_w"], torch.from_numpy(zs[f"legacy_{loss}_gW"]), rtol=1e-4, atol=2e-6)

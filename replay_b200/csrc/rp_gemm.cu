@@ -572,16 +572,34 @@ RP_API int rp_gemm(const rp_gemm_desc* g, void* stream_) {
 #undef RP_GEMM_CASE
 }
 
-// dst[i] (+)= sum_s src[s * stride + i]   - second stage of the split-K weight-gradient GEMMs (out_mode 3)
-__global__ void reduce_splits_kernel(const float* __restrict__ src, int n_splits, long long stride, long long n,
-                                     float* __restrict__ dst, int accumulate) {
-  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
-    float4 a = accumulate ? *reinterpret_cast<const float4*>(dst + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s2 = 0; s2 < n_splits; ++s2) {
-      const float4 v = *reinterpret_cast<const float4*>(src + (long long)s2 * stride + i);
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+// dst[i] (+)= sum_s src[s * stride + i]   - second stage of the split-K weight-gradient GEMMs (out_mode 3).
+// The sums are short (n = d*d elements) but deep (~100 splits): a block covers 32 float4 columns x 8 split groups so that
+// ~100 independent 16-byte loads per column are in flight instead of one serial chain; fixed summation order (deterministic).
+__global__ void __launch_bounds__(256) reduce_splits_kernel(const float* __restrict__ src, int n_splits, long long stride,
+                                                            long long n, float* __restrict__ dst, int accumulate) {
+  __shared__ float4 part[8][32];
+  const int col = threadIdx.x & 31, sg = threadIdx.x >> 5;
+  for (long long i0 = (long long)blockIdx.x * 128; i0 < n; i0 += (long long)gridDim.x * 128) {
+    const long long i = i0 + col * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) {
+      for (int s2 = sg; s2 < n_splits; s2 += 8) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long long)s2 * stride + i));
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
     }
-    *reinterpret_cast<float4*>(dst + i) = a;
+    part[sg][col] = a;
+    __syncthreads();
+    if (sg == 0 && i < n) {
+      float4 t = accumulate ? *reinterpret_cast<const float4*>(dst + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 v = part[g][col];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      *reinterpret_cast<float4*>(dst + i) = t;
+    }
+    __syncthreads();
   }
 }
 
@@ -589,7 +607,7 @@ RP_API int rp_reduce_splits(const float* src, int n_splits, long long stride, lo
                             void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!src || !dst || n_splits <= 0 || n <= 0 || (n & 3) || (stride & 3)) return RP_EINVAL;
-  long long blocks = (n / 4 + 255) / 256;
+  long long blocks = (n + 127) / 128;
   if (blocks > rp::sm_count() * 8) blocks = rp::sm_count() * 8;
   reduce_splits_kernel<<<(int)blocks, 256, 0, stream>>>(src, n_splits, stride, n, dst, accumulate);
   RP_LAUNCH_CHECK();

@@ -50,6 +50,27 @@ class SasRecModel(torch.nn.Module):
     def load_state_dict(self, sd, strict=True, assign=False):
         return self.core.load_state_dict(sd, strict=strict)
 
+    def item_table_fp32(self) -> torch.Tensor:
+        """fp32 master copy of the item table incl. the padding row, [item_count + 1, hidden]."""
+        if self.core.engine is None and not self.core._pending_state:
+            self.core.ensure_engine(1, self.max_len, with_grad=False)  # materialise the seeded initial weights
+        return self.core.state_dict()["item_embedder.item_emb.weight"].detach().clone()
+
+    def replace_item_table(self, table: torch.Tensor):
+        """Swap in a table for a (larger) vocabulary, keeping every other weight (lightning.py:612-621): the engine is rebuilt
+        for the new catalog size; optimizer moments restart, as they do for the reference's freshly created Embedding."""
+        import dataclasses
+        sd = {k: v for k, v in self.state_dict().items() if not k.startswith("_head.")}
+        sd["item_embedder.item_emb.weight"] = table.detach().to(torch.float32)
+        new_count = table.shape[0] - 1
+        spec = getattr(self.core, "_loss_spec", None)
+        self.core = SasRecCore(dataclasses.replace(self.core.cfg, n_items=new_count), item_feature=self.item_feature_name,
+                               device=self.core._device, seed=self.core._seed)
+        if spec is not None:
+            self.core.set_loss(spec[0], **spec[1])
+        self.core.load_state_dict(sd)
+        self.item_count = self.padding_idx = new_count
+
     def forward_step(self, feature_tensor, padding_mask):
         """Hidden states [B, L, d] (model.py:159-180)."""
         return self.core.hidden_states(feature_tensor[self.item_feature_name], padding_mask).float()
@@ -156,12 +177,75 @@ class SasRec(LightningModuleBase):
             return opt
         return [opt], [self._lr_scheduler_factory.create(opt)]
 
+    def validation_step(self, batch: dict, batch_idx: int = 0, dataloader_idx: int = 0):
+        """lightning.py:196-220: scores of the validation batch (same computation as predict)."""
+        batch = _prepare_prediction_batch(self._schema, self._model.max_len, batch)
+        return self._model.predict(batch["feature_tensor"], batch["padding_mask"])
+
+    # ---- vocabulary growth (lightning.py:493-566, 612-621)
+    def _set_new_item_table(self, table: torch.Tensor):
+        self._model.replace_item_table(table)
+        self._vocab_size = self._model.item_count
+        feats = self._schema.item_id_features
+        feat = feats.item() if hasattr(feats, "item") else feats[self._schema.item_id_feature_name]
+        feat._set_cardinality(self._model.item_count)
+
+    def set_item_embeddings_by_size(self, new_vocab_size: int):
+        """Keep the fitted item embeddings and add xavier-normal rows for the new items."""
+        old = self._model.item_table_fp32()
+        old_vocab, hidden = old.shape[0] - 1, self._model.hidden_size
+        if new_vocab_size <= old_vocab:
+            raise ValueError("New vocabulary size must be greater then already fitted")
+        new = torch.empty(new_vocab_size + 1, hidden)
+        torch.nn.init.xavier_normal_(new)
+        new[:old_vocab] = old[:-1].cpu()
+        self._set_new_item_table(new)
+
+    def set_item_embeddings_by_tensor(self, all_item_embeddings: torch.Tensor):
+        """Replace the whole item table (possibly with more items); the padding row is zero."""
+        if all_item_embeddings.dim() != 2:
+            raise ValueError("Input tensor must have (number of all items, model hidden size) shape")
+        old_vocab, hidden = self._model.item_count, self._model.hidden_size
+        if all_item_embeddings.shape[0] < old_vocab:
+            raise ValueError("New vocabulary size can't be less then already fitted")
+        if all_item_embeddings.shape[1] != hidden:
+            raise ValueError("Input tensor second dimension doesn't match model hidden size")
+        new = torch.zeros(all_item_embeddings.shape[0] + 1, hidden)
+        new[:-1] = all_item_embeddings.detach().float().cpu()
+        self._set_new_item_table(new)
+
+    def append_item_embeddings(self, item_embeddings: torch.Tensor):
+        """Append rows for new items only; the padding row is zero."""
+        if item_embeddings.dim() != 2:
+            raise ValueError("Input tensor must have (number of new items, model hidden size) shape")
+        if item_embeddings.shape[1] != self._model.hidden_size:
+            raise ValueError("Input tensor second dimension doesn't match model hidden size")
+        old = self._model.item_table_fp32()
+        old_vocab = old.shape[0] - 1
+        new = torch.zeros(old_vocab + item_embeddings.shape[0] + 1, self._model.hidden_size)
+        new[:old_vocab] = old[:-1].cpu()
+        new[old_vocab:-1] = item_embeddings.detach().float().cpu()
+        self._set_new_item_table(new)
+
     def get_all_embeddings(self):
-        return {self._model.item_feature_name: self._model.core.engine.params["item_emb"][:-1].detach().clone()}
+        """Copies, with the reference's keys (sasrec/model.py:374-381)."""
+        sd = self._model.state_dict() if (self._model.core.engine is not None or self._model.core._pending_state) else None
+        if sd is None:
+            self._model.item_table_fp32()
+            sd = self._model.state_dict()
+        return {"item_embedding": sd["item_embedder.item_emb.weight"][:-1].detach().clone(),
+                "positional_embedding": sd["item_embedder.pos_emb.pe.weight"].detach().clone()}
 
     @property
     def optimizer_factory(self):
         return self._optimizer_factory
+
+    @optimizer_factory.setter
+    def optimizer_factory(self, optimizer_factory):
+        if not hasattr(optimizer_factory, "create"):  # lightning.py:575-585 (isinstance check against OptimizerFactory)
+            raise ValueError(f"Expected optimizer_factory of type OptimizerFactory, got {type(optimizer_factory)}")
+        self._optimizer_factory = optimizer_factory
+        self._lr = getattr(optimizer_factory, "learning_rate", 1e-3)
 
     @property
     def candidates_to_score(self):

@@ -201,3 +201,62 @@ def test_end_to_end_plumbing_config1(cuda):
     assert abs(hit - m["recall@10"]) < 1e-6
     assert m["recall@10"] > 0.5, m       # chance level is 10 / 4000
     assert (scores[:, :-1] >= scores[:, 1:]).all()
+
+
+def test_legacy_vocabulary_growth_like_reference_tests(golden_dir, cuda):
+    """tests/models/nn/sequential/sasrec/test_sasrec_lightning.py:342-427 of the reference, mirrored: by_size keeps the fitted
+    rows, by_tensor replaces all rows, append adds rows; error conditions; scores of old items are unchanged by growth."""
+    from oracle import sasrec as osr
+    from replay_b200.models.nn.sequential import SasRec
+    from replay_b200.schema import TensorFeatureInfo, TensorSchema
+
+    z, sd = _golden(golden_dir, "sasrec_legacy_tiny.npz")
+    n_items, d, H, L = int(z["n_items"]), int(z["d"]), int(z["H"]), int(z["L"])
+    schema = TensorSchema(TensorFeatureInfo("item_id", n_items, 0, d))
+    model = SasRec(schema, block_count=int(z["n_blocks"]), head_count=H, hidden_size=d, max_seq_len=L, dropout_rate=0.0)
+    model.load_state_dict({"_model." + k: v for k, v in sd.items()})
+    ids, pm = torch.from_numpy(z["ids"]).cuda(), torch.from_numpy(z["pad_mask"]).cuda()
+    batch = {"feature_tensor": {"item_id": ids}, "padding_mask": pm}
+    before = model.predict(dict(batch))
+    old = model.get_all_embeddings()["item_embedding"].cpu()
+    assert old.shape == (n_items, d) and set(model.get_all_embeddings()) == {"item_embedding", "positional_embedding"}
+    # by size
+    model.set_item_embeddings_by_size(n_items + 7)
+    new = model.get_all_embeddings()["item_embedding"].cpu()
+    assert new.shape == (n_items + 7, d) and torch.equal(new[:n_items], old)
+    assert schema.item_id_features.item().cardinality == n_items + 7 and model._vocab_size == n_items + 7
+    after = model.predict(dict(batch))
+    assert after.shape == (ids.shape[0], n_items + 7)
+    torch.testing.assert_close(after[:, :n_items], before, rtol=0, atol=0)     # old items score exactly as before
+    assert model.validation_step(dict(batch), 0).shape == after.shape
+    # the grown model still trains (engine rebuilt for the new catalog)
+    lab, tm = torch.from_numpy(z["labels"]).cuda(), torch.from_numpy(z["target_mask"]).cuda()
+    l0 = float(model.training_step({**batch, "positive_labels": lab.clamp(max=n_items - 1), "target_padding_mask": tm}, 0))
+    assert np.isfinite(l0)
+    # by tensor / append
+    t = torch.rand(n_items + 9, d)
+    model.set_item_embeddings_by_tensor(t)
+    got = model.get_all_embeddings()["item_embedding"].cpu()
+    assert got.shape == (n_items + 9, d) and torch.equal(got, t)
+    extra = torch.rand(3, d)
+    model.append_item_embeddings(extra)
+    got2 = model.get_all_embeddings()["item_embedding"].cpu()
+    assert got2.shape == (n_items + 12, d) and torch.equal(got2[: n_items + 9], t) and torch.equal(got2[n_items + 9:], extra)
+    sdn = model.state_dict()
+    assert sdn["_model.item_embedder.item_emb.weight"].shape == (n_items + 13, d)
+    assert (sdn["_model.item_embedder.item_emb.weight"][-1] == 0).all()          # fresh padding row
+    # errors (test_sasrec_fine_tuning_errors)
+    with pytest.raises(ValueError):
+        model.set_item_embeddings_by_size(3)
+    with pytest.raises(ValueError):
+        model.set_item_embeddings_by_tensor(torch.rand(1, 1, 1))
+    with pytest.raises(ValueError):
+        model.set_item_embeddings_by_tensor(torch.rand(3, d))
+    with pytest.raises(ValueError):
+        model.set_item_embeddings_by_tensor(torch.rand(n_items + 20, 1))
+    with pytest.raises(ValueError):
+        model.append_item_embeddings(torch.rand(1, 1, 1))
+    with pytest.raises(ValueError):
+        model.append_item_embeddings(torch.rand(1, 1))
+    with pytest.raises(ValueError):
+        model.optimizer_factory = object()

@@ -214,23 +214,43 @@ class Bert4Rec(LightningModuleBase):
         self.log("train_loss", loss, on_step=True, on_epoch=True, prog_bar=True, sync_dist=True)
         return loss
 
-    def _shifted(self, batch):
-        ids = batch["inputs"][self._model.item_feature_name]
-        if ids.shape[1] != self._model.max_len:
-            raise ValueError(f"The length of the submitted sequence must be {self._model.max_len}, got {ids.shape[1]}")
-        return shift_features(ids, batch["pad_mask"], batch["token_mask"], self._model.core.cfg.pad_id)
+    def _prepared(self, batch):
+        """_prepare_prediction_batch (bert4rec/lightning.py:649-683): a batch of full length is taken AS IS (the prediction
+        dataset already shifted it, bert4rec/dataset.py:322-345); a shorter one is left-padded with the padding value and
+        then shifted; a longer one is an error."""
+        ids, pm, tm = batch["inputs"][self._model.item_feature_name], batch["pad_mask"], batch["token_mask"]
+        seq_len, max_len = pm.shape[1], self._model.max_len
+        if seq_len > max_len:
+            raise ValueError("The length of the submitted sequence must not exceed the maximum length of the sequence. "
+                             f"The length of the sequence is given {seq_len}, while the maximum length is {max_len}")
+        if seq_len < max_len:
+            feats = self._schema.item_id_features
+            feat = feats.item() if hasattr(feats, "item") else feats[self._schema.item_id_feature_name]
+            ids = torch.nn.functional.pad(ids, (max_len - seq_len, 0), value=int(feat.padding_value))
+            pm = torch.nn.functional.pad(pm, (max_len - seq_len, 0), value=0)
+            ids, pm, tm = shift_features(ids, pm, pm, int(feat.padding_value))
+        return ids, pm, tm
+
+    def _model_predict(self, ids, pm, tm, candidates_to_score=None):
+        cands = self._candidates_to_score if candidates_to_score is None else candidates_to_score
+        return self._model.core.logits(ids, pm, tm, cands)
+
+    def forward(self, feature_tensors, padding_mask, tokens_mask, candidates_to_score=None):
+        return self._model_predict(feature_tensors[self._model.item_feature_name], padding_mask, tokens_mask, candidates_to_score)
+
+    def validation_step(self, batch: dict, batch_idx: int = 0, dataloader_idx: int = 0):
+        return self._model_predict(batch["inputs"][self._model.item_feature_name], batch["pad_mask"], batch["token_mask"])
 
     def predict_step(self, batch: dict, batch_idx: int = 0, dataloader_idx: int = 0):
-        ids, pm, tm = self._shifted(batch)
-        return self._model.core.logits(ids, pm, tm, self._candidates_to_score)
+        return self._model_predict(*self._prepared(batch))
 
     def predict(self, batch: dict, candidates_to_score=None):
-        ids, pm, tm = self._shifted(batch)
-        return self._model.core.logits(ids, pm, tm, candidates_to_score)
+        return self._model_predict(*self._prepared(batch), candidates_to_score)
 
     def predict_topk(self, batch: dict, k: int, seen_ids=None, candidates_to_score=None):
-        ids, pm, tm = self._shifted(batch)
-        return self._model.core.predict_topk(ids, pm, tm, k, seen_ids, candidates_to_score)
+        ids, pm, tm = self._prepared(batch)
+        cands = self._candidates_to_score if candidates_to_score is None else candidates_to_score
+        return self._model.core.predict_topk(ids, pm, tm, k, seen_ids, cands)
 
     def configure_optimizers(self):
         params = [self._model.core.flat]

@@ -118,8 +118,23 @@ def test_bert4rec_lightning_mirror(golden_dir, cuda):
     assert abs(float(loss) - float(z["train_loss"])) < 5e-3 * float(z["train_loss"])
     sd2 = m.state_dict()
     assert set(sd2) == set(sd)
+    # prediction batches arrive already shifted from the reference's Bert4RecPredictionDataset (full length: taken as is)
+    from replay_b200.models.nn.sequential.bert4rec import shift_features
+    sids, spm, stm = shift_features(ids, pm, pm, 0)
+    batch = {"query_id": batch["query_id"], "inputs": {"item_id": sids}, "pad_mask": spm, "token_mask": stm}
     scores = m.predict(batch)
     assert scores.shape == (ids.shape[0], n_items) and torch.isfinite(scores).all()
+    torch.testing.assert_close(m.validation_step(batch, 0), scores)
+    torch.testing.assert_close(m(batch["inputs"], spm, stm), scores)
+    # a shorter (un-shifted) window is left-padded and shifted by the module (bert4rec/lightning.py:660-682)
+    short = {"inputs": {"item_id": ids[:, 4:]}, "pad_mask": pm[:, 4:], "token_mask": pm[:, 4:]}
+    sc_short = m.predict(short)
+    keep = ~pm[:, :4].any(1)                       # rows whose 4 dropped positions were padding anyway
+    assert keep.any()
+    torch.testing.assert_close(sc_short[keep], scores[keep])
+    with pytest.raises(ValueError):
+        m.predict({"inputs": {"item_id": torch.cat([ids, ids[:, :1]], 1)}, "pad_mask": torch.cat([pm, pm[:, :1]], 1),
+                   "token_mask": torch.cat([pm, pm[:, :1]], 1)})
     cands = torch.arange(5, 200, 3).cuda()
     top_ids, top_sc = m.predict_topk(batch, 7, seen_ids=ids, candidates_to_score=cands)
     assert set(top_ids.flatten().tolist()) <= set(cands.tolist())

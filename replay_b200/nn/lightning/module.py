@@ -48,8 +48,12 @@ class LightningModule(LightningModuleBase):
             lab, tm = batch["positive_labels"], batch["target_padding_mask"]
             lab = lab[..., 0] if lab.dim() == 3 else lab
             tm = tm[..., 0] if tm.dim() == 3 else tm
+            spec = getattr(self.model, "loss", None)
+            neg = batch.get("negative_labels") if getattr(spec, "needs_negatives", False) else None
+            if getattr(spec, "needs_negatives", False) and neg is None:
+                raise ValueError(f"{type(spec).__name__} needs `negative_labels` in the batch")
             loss = core.fused_step(batch["feature_tensors"][core.item_feature], batch["padding_mask"], lab, tm,
-                                   lr=self._optimizer_factory.learning_rate)
+                                   lr=self._optimizer_factory.learning_rate, negatives=neg)
         else:
             loss = self(batch)["loss"]
         self.log("train_loss", loss, on_step=True, on_epoch=True, prog_bar=True, sync_dist=True)

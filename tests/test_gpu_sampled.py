@@ -158,6 +158,17 @@ def test_api_mirrors_select_the_sampled_heads(golden_dir, cuda):
         model.core.flat.grad = None
     with pytest.raises(ValueError):
         model(feature_tensors={"item_id": ids}, padding_mask=pm, positive_labels=lab.unsqueeze(-1), target_padding_mask=tm.unsqueeze(-1))
+    # Lightning mirror, fused forward+backward+Adam with per-batch shared negatives
+    from replay_b200.nn.lightning import LightningModule, OptimizerFactory
+    model.loss = CESampled()
+    lm = LightningModule(model, optimizer_factory=OptimizerFactory(learning_rate=3e-3))
+    g = torch.Generator().manual_seed(1)
+    b = {"feature_tensors": {"item_id": ids}, "padding_mask": pm, "positive_labels": lab.unsqueeze(-1),
+         "target_padding_mask": tm.unsqueeze(-1)}
+    ls = [float(lm.training_step({**b, "negative_labels": torch.randint(0, n_items, (50,), generator=g).cuda()}, i)) for i in range(40)]
+    assert ls[-1] < ls[0] - 0.5, (ls[0], ls[-1])
+    with pytest.raises(ValueError):
+        lm.training_step(b, 0)
     # legacy module: CE with 64 sampled negatives per position / shared BCE negatives
     for kw in (dict(loss_type="CE", loss_sample_count=64), dict(loss_type="BCE", loss_sample_count=32, negatives_sharing=True)):
         torch.manual_seed(0)

@@ -281,6 +281,8 @@ int rp_sampled_head_bwd(const rp_sampled_desc* s, void* d_hc, float* d_table, vo
  *   SasRecTrainingDataset.__getitem__ (window L+1, inputs [:-1], labels [1:])  replay/models/nn/sequential/sasrec/dataset.py:104-126
  *   Bert4RecUniformMasker.mask + Bert4RecTrainingDataset.__getitem__          .../bert4rec/dataset.py:71-92,163-177
  *   _shift_features (predict: roll left, last = pad, token/pad masks)         .../bert4rec/dataset.py:322-351
+ *   Array1DColumn.__getitem__ + NextTokenTransform (new path, torch ops)     replay/data/nn/parquet/impl/array_1d_column.py:70-84,
+ *                                                                            impl/indexing.py:42-78, replay/nn/transform/next_token.py:65-96
  * and the default collate.  mode: RP_BATCH_SASREC_TRAIN -> ids, pad_mask, labels, aux_mask = target_padding_mask;
  * RP_BATCH_PREDICT -> ids, pad_mask; RP_BATCH_BERT_TRAIN -> ids (= inputs), pad_mask, labels (= positive_labels),
  * aux_mask = token_mask (0 = masked) drawn as (u * pad) >= mask_prob with the reference's two corner-case fix-ups, u from

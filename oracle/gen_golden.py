@@ -286,6 +286,18 @@ def gen_dataset_layout():
     out["bertpred_ids"] = stack(smp, ["inputs", "item_id"])
     out["bertpred_pad"] = stack(smp, ["pad_mask"])
     out["bertpred_tok"] = stack(smp, ["token_mask"])
+    # ---- new path: Array1DColumn.__getitem__ (left-padded gather of the LAST shape elements from flat values + offsets,
+    # replay/data/nn/parquet/impl/array_1d_column.py:70-84, indexing.py:42-78) followed by NextTokenTransform(shift=1)
+    from replay.data.nn.parquet.impl.array_1d_column import Array1DColumn
+    from replay.nn.transform.next_token import NextTokenTransform
+    col = Array1DColumn(data=torch.from_numpy(np.concatenate(seqs)), lengths=torch.tensor(lens, dtype=torch.int64), shape=L + 1,
+                        padding=n_items)
+    order = torch.tensor([3, 0, 11, 7, 7, 2, 10, 5, 1, 4, 6, 8, 9])
+    mask, vals = col[order]
+    nt = NextTokenTransform(label_name="item_id", shift=1, ignore="query_id")({"query_id": order.clone(), "item_id": vals,
+                                                                               "item_id_mask": mask})
+    out.update(newpath_order=order.numpy(), newpath_ids=nt["item_id"].numpy(), newpath_pad=nt["item_id_mask"].numpy(),
+               newpath_labels=nt["positive_labels"].numpy(), newpath_tmask=nt["positive_labels_mask"].numpy())
     np.savez_compressed(os.path.join(OUT, "dataset_layout.npz"), **out)
     print("wrote dataset_layout", {k: np.asarray(v).shape for k, v in out.items() if k.endswith("_ids")})
 

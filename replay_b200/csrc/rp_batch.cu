@@ -4,7 +4,9 @@
 // (replay/data/nn/torch_sequential_dataset.py:69-136), SasRecTrainingDataset.__getitem__
 // (replay/models/nn/sequential/sasrec/dataset.py:104-126), Bert4RecUniformMasker.mask + Bert4RecTrainingDataset.__getitem__
 // (replay/models/nn/sequential/bert4rec/dataset.py:71-92,163-177), _shift_features (bert4rec/dataset.py:322-351) and the
-// default collate that stacks the samples.
+// default collate that stacks the samples; and the new path's torch-op version of the same thing: Array1DColumn.__getitem__
+// (replay/data/nn/parquet/impl/array_1d_column.py:70-84, indexing.py:42-78) + NextTokenTransform
+// (replay/nn/transform/next_token.py:65-96), ~10 small kernels there.
 //
 // HBM-bound integer work: per row one CSR offset pair + <= W item ids are read (coalesced along the window) and W x
 // (8 + 1 [+ 8 + 1]) bytes are written; one CTA per batch row so the BERT masker's row-wide all()/any() fix-ups are block

@@ -58,11 +58,11 @@ class DeviceSequenceStore:
         self.device = torch.device(device)
         self.lengths = np.diff(offsets)
         self.n_seq = len(self.lengths)
-        self.offsets = torch.from_numpy(offsets).to(self.device)
+        self.offsets = torch.from_numpy(np.array(offsets, dtype=np.int64)).to(self.device)
         self.items = torch.from_numpy(items.astype(np.int32)).to(self.device)
         if len(items) == 0:  # keep a valid pointer
             self.items = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.query_ids = None if query_ids is None else torch.as_tensor(np.asarray(query_ids, dtype=np.int64)).to(self.device)
+        self.query_ids = None if query_ids is None else torch.from_numpy(np.array(query_ids, dtype=np.int64)).to(self.device)
 
     @classmethod
     def from_sequential_dataset(cls, sequential, feature_name: str | None = None, device="cuda"):
@@ -72,6 +72,35 @@ class DeviceSequenceStore:
         n = len(sequential)
         return cls([np.asarray(sequential.get_sequence(i, name)) for i in range(n)],
                    query_ids=[sequential.get_query_id(i) for i in range(n)], device=device)
+
+    @classmethod
+    def from_parquet(cls, source, item_column: str = "item_id", query_column: str | None = None, device="cuda"):
+        """Sequence-per-row parquet (the layout the reference's ParquetDataset / ParquetModule reads: one row per query, the
+        item ids in a list<int> column; replay/data/nn/parquet/impl/array_1d_column.py:87-140): the list column's offsets and
+        flat values become the CSR store without a Python loop (null lists count as empty).  ``source``: a path, a list of
+        paths or a ``pyarrow.Table``."""
+        import pyarrow as pa
+        import pyarrow.compute as pc
+        import pyarrow.parquet as pq
+
+        cols = [item_column] + ([query_column] if query_column else [])
+        if isinstance(source, pa.Table):
+            table = source.select(cols)
+        elif isinstance(source, (list, tuple)):
+            table = pa.concat_tables([pq.read_table(p, columns=cols) for p in source])
+        else:
+            table = pq.read_table(source, columns=cols)
+        col = table.column(item_column).combine_chunks()
+        if not (pa.types.is_list(col.type) or pa.types.is_large_list(col.type)):
+            raise ValueError(f"column {item_column!r} must be a list column, got {col.type}")
+        lengths = pc.fill_null(pc.list_value_length(col), 0).to_numpy(zero_copy_only=False).astype(np.int64)
+        values = pc.list_flatten(col)
+        if values.null_count:
+            raise ValueError(f"column {item_column!r} holds null item ids")
+        offsets = np.zeros(len(lengths) + 1, dtype=np.int64)
+        np.cumsum(lengths, out=offsets[1:])
+        q = table.column(query_column).combine_chunks().to_numpy(zero_copy_only=False) if query_column else None
+        return cls(offsets=offsets, items=values.to_numpy(zero_copy_only=False), query_ids=q, device=device)
 
     def __len__(self):
         return self.n_seq
@@ -109,6 +138,19 @@ class DeviceSequenceStore:
                                                  with_aux=True)
         return {"query_id": q, "feature_tensor": {feature_name: ids}, "padding_mask": pad, "positive_labels": labels,
                 "target_padding_mask": tmask}
+
+    def sasrec_new_path_batch(self, seq_index, max_len: int, pad_value: int, feature_name="item_id", with_seen: bool = True):
+        """The new path's model inputs: Array1DColumn.__getitem__ with shape max_len + 1 (left-padded gather of the last
+        elements, parquet/impl/indexing.py:42-78) + NextTokenTransform(shift=1) (nn/transform/next_token.py:65-96) +
+        the unsqueeze of the default SASRec transform template -> feature_tensors, padding_mask, positive_labels [B,L,1],
+        target_padding_mask [B,L,1] (+ seen_ids = the window)."""
+        ids, pad, labels, tmask, q = self._build(SASREC_TRAIN, seq_index, None, max_len, pad_value, with_labels=True,
+                                                 with_aux=True)
+        out = {"query_id": q, "feature_tensors": {feature_name: ids}, "padding_mask": pad,
+               "positive_labels": labels.unsqueeze(-1), "target_padding_mask": tmask.unsqueeze(-1)}
+        if with_seen:
+            out["seen_ids"] = ids
+        return out
 
     def sasrec_prediction_batch(self, seq_index, max_len: int, pad_value: int, feature_name="item_id"):
         ids, pad, _, _, q = self._build(PREDICT, seq_index, None, max_len, pad_value)

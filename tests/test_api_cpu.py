@@ -209,3 +209,27 @@ def test_window_index_vectorised_matches_reference_order():
             s, o = window_index(lens, window, st)
             ref = np.asarray(od.window_index(lens, window, st)).reshape(-1, 2)
             assert np.array_equal(np.stack([s, o], 1), ref)
+
+
+def test_parquet_to_csr_store(tmp_path):
+    """DeviceSequenceStore.from_parquet: list<int> column -> offsets / flat values without a Python loop (multiple files,
+    empty and null lists, int32 / int64 item types); no kernel is involved, so this runs on the CPU."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from replay_b200.device_data import DeviceSequenceStore
+    seqs = [[3, 1, 2], [], [7], None, [5, 5, 5, 9]]
+    t1 = pa.table({"user": pa.array([10, 11, 12, 13, 14], pa.int64()), "item_id": pa.array(seqs, pa.list_(pa.int64()))})
+    t2 = pa.table({"user": pa.array([20, 21], pa.int64()), "item_id": pa.array([[4, 4], [0]], pa.list_(pa.int64()))})
+    p1, p2 = str(tmp_path / "a.parquet"), str(tmp_path / "b.parquet")
+    pq.write_table(t1, p1, row_group_size=2)
+    pq.write_table(t2, p2)
+    st = DeviceSequenceStore.from_parquet([p1, p2], "item_id", query_column="user", device="cpu")
+    assert st.offsets.tolist() == [0, 3, 3, 4, 4, 8, 10, 11]
+    assert st.items.tolist() == [3, 1, 2, 7, 5, 5, 5, 9, 4, 4, 0] and st.items.dtype == torch.int32
+    assert st.query_ids.tolist() == [10, 11, 12, 13, 14, 20, 21] and len(st) == 7
+    st32 = DeviceSequenceStore.from_parquet(pa.table({"item_id": pa.array([[1, 2], [3]], pa.list_(pa.int32()))}), device="cpu")
+    assert st32.offsets.tolist() == [0, 2, 3] and st32.query_ids is None
+    with pytest.raises(ValueError):
+        DeviceSequenceStore.from_parquet(pa.table({"item_id": pa.array([1, 2, 3])}), device="cpu")
+    with pytest.raises(ValueError):
+        DeviceSequenceStore(offsets=[0, 2, 1], items=[1, 2], device="cpu")

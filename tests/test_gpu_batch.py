@@ -57,6 +57,13 @@ def test_golden_samples_of_the_reference_datasets(golden_dir, cuda):
     assert np.array_equal(_np(bp["inputs"]["item_id"]), z["bertpred_ids"])
     assert np.array_equal(_np(bp["pad_mask"]), z["bertpred_pad"])
     assert np.array_equal(_np(bp["token_mask"]), z["bertpred_tok"])
+    # new path: Array1DColumn gather + NextTokenTransform of the reference on an arbitrary (repeating) row order
+    nb = st.sasrec_new_path_batch(z["newpath_order"], L, pad)
+    assert np.array_equal(_np(nb["feature_tensors"]["item_id"]), z["newpath_ids"])
+    assert np.array_equal(_np(nb["padding_mask"]), z["newpath_pad"])
+    assert np.array_equal(_np(nb["positive_labels"])[..., 0], z["newpath_labels"])
+    assert np.array_equal(_np(nb["target_padding_mask"])[..., 0], z["newpath_tmask"])
+    assert np.array_equal(_np(nb["seen_ids"]), z["newpath_ids"])
     # masker corner cases (draw independent)
     for tag, pr in (("p0", 0.0), ("p2", 2.0)):
         bb = st.bert4rec_training_batch(np.arange(len(seqs)), L, pad, pr, seed=5)

@@ -110,6 +110,29 @@ def cpu_train_seq_per_s(batch=8, steps=3, warmup=1):
     return batch / med, med, float(loss.detach())
 
 
+def cpu_predict_users_per_s(users=64, reps=3):
+    """Reference predict path on the host cores (oracle port): body forward (eval) -> last hidden -> [U, |I|] logits ->
+    SeenItemsFilter (clone + scatter -inf) -> torch.topk(10), fp32, at the scoring leg's shape (|I| = 500K, L = 200, d = 128)."""
+    from oracle import sasrec as osr
+    from replay_b200.synthetic import make_sequences
+
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
+    sc = SCORE_CFG
+    P = osr.random_params(sc["n_items"], sc["d"], sc["seq_len"], 2, seed=7)
+    ids, pm, _, _ = make_sequences(users, sc["n_items"], sc["seq_len"], seed=7)
+    ts = []
+    with torch.no_grad():
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            h = osr.sasrec_body(P, ids, pm, 2, "new", mode="eval")[:, -1]
+            scores = h @ P["item_emb"][: sc["n_items"]].T
+            scores = osr.seen_filter(scores, ids, sc["n_items"])
+            torch.topk(scores, sc["k"], dim=1)
+            ts.append(time.perf_counter() - t0)
+    ts = sorted(ts[1:])
+    return users / ts[len(ts) // 2]
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -304,6 +327,9 @@ def run_ours(args):
                 "config": {"workload": "SASRec predict(): body fwd + fused score+seen-filter+top-10, users sharded over the GPUs",
                            **sc},
                 "ms_per_call": ms_p,
+                "cpu_baseline": None if args.no_cpu else {
+                    "value": cpu_predict_users_per_s(), "unit": "users/s", "cores": torch.get_num_threads(), "kind": "port",
+                    "sample": "64 users, 3 timed calls: oracle body + full logits + seen filter + torch.topk, torch fp32 CPU"},
                 "roofline": {"bound": "tensor", "kernel": "score_topk_kernel", "achieved": head_flops / (t_head * 1e-3) / 1e12,
                              "peak": PK["tc_burst"], "unit": "TFLOP/s", "frac": head_flops / (t_head * 1e-3) / 1e12 / PK["tc_burst"],
                              "head_ms": t_head, "head_users_per_s": Bu / t_head * 1e3, "traffic": None},

@@ -174,7 +174,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    c = CFG
+    c = dict(CFG)
+    if args.dropout is not None:
+        c["dropout"] = args.dropout
     B, L, d, I = c["per_gpu_batch"], c["seq_len"], c["d"], c["n_items"]
     cfg = EncoderConfig(n_items=I, d=d, n_heads=c["heads"], n_blocks=c["blocks"], max_len=L, dropout=c["dropout"], variant="new")
     eng = SasRecEngine(cfg, B, L, dev, seed=1234)
@@ -378,7 +380,7 @@ def run_ours(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": "BASELINE configs[1]: SASRec L=200 d=128 H=2 blocks=2 |I|=50K, full-catalog CE + Adam, "
-                               "dropout 0.2, MovieLens-shaped synthetic windows (inputs > L2: ~1 GB of activations per step)",
+                               f"dropout {c['dropout']}, MovieLens-shaped synthetic windows (inputs > L2: ~1 GB of activations per step)",
                    "global_batch": world * B, "per_gpu_batch": B, "seq_len": L, "d": d, "n_items": I,
                    "parallelism": f"dp{world}", "valid_targets_per_seq": valid_per_seq, "cuda_graph": not args.no_graph},
         "e2e": {"value": seq_s_e2e, "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -409,6 +411,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-scoring", action="store_true")
     ap.add_argument("--no-device-batches", action="store_true", help="skip the device-side batch construction leg")
+    ap.add_argument("--dropout", type=float, default=None, help="diagnostic override of the workload's dropout (0.2); "
+                    "a run with this flag is not the benchmark configuration")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

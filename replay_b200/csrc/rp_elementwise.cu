@@ -190,7 +190,7 @@ __global__ void embed_bwd_pos_kernel(const __nv_bfloat16* __restrict__ dx, const
     const float2 a = __bfloat1622float2(h[0]), c = __bfloat1622float2(h[1]);
     float v[4] = {a.x, a.y, c.x, c.y};
     if (drop_p > 0.f) {
-      const uint4 r = philox4x32(seed, (drop_off + (unsigned long long)t * D + cg * 4) >> 2);
+      const uint4 r = rng4x32(seed, (drop_off + (unsigned long long)t * D + cg * 4) >> 2);
       v[0] = r.x >= thr ? v[0] * ks : 0.f;
       v[1] = r.y >= thr ? v[1] * ks : 0.f;
       v[2] = r.z >= thr ? v[2] * ks : 0.f;
@@ -360,7 +360,7 @@ __global__ void dropout_bwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bf
     float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
     float v[4] = {a.x, a.y, b.x, b.y};
     if (drop_p > 0.f) {
-      const uint4 r = philox4x32(seed, (drop_off + (unsigned long long)i) >> 2);
+      const uint4 r = rng4x32(seed, (drop_off + (unsigned long long)i) >> 2);
       v[0] = r.x >= thr ? v[0] * ks : 0.f;
       v[1] = r.y >= thr ? v[1] * ks : 0.f;
       v[2] = r.z >= thr ? v[2] * ks : 0.f;

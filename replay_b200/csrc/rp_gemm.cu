@@ -99,7 +99,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const f
         const unsigned long long e0 = p.drop_offset + (unsigned long long)(c_base + n0 + c);
 #pragma unroll
         for (int q = 0; q < 32; q += 4) {
-          const uint4 r = philox4x32(seed_eff, (e0 + q) >> 2);
+          const uint4 r = rng4x32(seed_eff, (e0 + q) >> 2);
           x[q + 0] = (r.x >= drop_thr) ? x[q + 0] * keep_scale : 0.f;
           x[q + 1] = (r.y >= drop_thr) ? x[q + 1] * keep_scale : 0.f;
           x[q + 2] = (r.z >= drop_thr) ? x[q + 2] * keep_scale : 0.f;
@@ -148,7 +148,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const f
         const unsigned long long e0 = p.post_drop_offset + (unsigned long long)(c_base + n0 + c);
 #pragma unroll
         for (int q = 0; q < 32; q += 4) {
-          const uint4 r = philox4x32(p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull), (e0 + q) >> 2);
+          const uint4 r = rng4x32(p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull), (e0 + q) >> 2);
           x[q + 0] = (r.x >= thr2) ? x[q + 0] * ks2 : 0.f;
           x[q + 1] = (r.y >= thr2) ? x[q + 1] * ks2 : 0.f;
           x[q + 2] = (r.z >= thr2) ? x[q + 2] * ks2 : 0.f;

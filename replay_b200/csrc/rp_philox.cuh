@@ -1,5 +1,5 @@
-// rp_philox.cuh - counter-based RNG (Philox4x32-10) for dropout masks: the forward and the backward regenerate the same
-// mask from (seed, element index / 4) instead of storing it.  Element e uses word (e & 3) of philox4x32(seed, e >> 2).
+// rp_philox.cuh - counter-based RNGs: the forward and the backward regenerate the same dropout mask from
+// (seed, element index / 4) instead of storing it.  Element e uses word (e & 3) of rng4x32(seed, e >> 2).
 #pragma once
 #include <stdint.h>
 
@@ -25,9 +25,29 @@ __host__ __device__ __forceinline__ uint4 philox4x32(unsigned long long seed, un
   return make_uint4(c0, c1, c2, c3);
 }
 
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {  // murmur3 finaliser: full avalanche in 5 steps
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+
+// Activation-dropout generator: four 32-bit words for the 4 consecutive elements of counter `ctr` (= element index / 4).
+// Dropout only needs independent-looking Bernoulli draws that the backward can regenerate; Philox4x32-10 costs ~110
+// integer instructions per call and showed up as ~5 % of the training step, this counter hash (one mixed 32-bit key per
+// (seed, ctr), four finalisers on a Weyl sequence) costs ~30.  Philox stays in use where a reference-grade stream matters
+// (the BERT4Rec token masker).
+__host__ __device__ __forceinline__ uint4 rng4x32(unsigned long long seed, unsigned long long ctr) {
+  const uint32_t key = fmix32((uint32_t)ctr * 0x9E3779B1u ^ (uint32_t)seed) ^
+                       fmix32((uint32_t)(ctr >> 32) * 0x85EBCA77u + (uint32_t)(seed >> 32) + 0x27D4EB2Fu);
+  return make_uint4(fmix32(key), fmix32(key + 0x9E3779B9u), fmix32(key + 0x3C6EF372u), fmix32(key + 0xDAA66D2Bu));
+}
+
 // keep decision for element e with drop threshold thr = p * 2^32
 __device__ __forceinline__ bool philox_keep(unsigned long long seed, unsigned long long e, uint32_t thr) {
-  const uint4 r = philox4x32(seed, e >> 2);
+  const uint4 r = rng4x32(seed, e >> 2);
   const uint32_t w = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
   return w >= thr;
 }

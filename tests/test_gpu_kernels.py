@@ -244,3 +244,33 @@ def test_ce_head_wide_hidden_matches_oracle(ops, T, n_valid, I, budget, monkeypa
     ee = (d_tab[:I].cpu().double() - e64.grad).norm() / e64.grad.norm()
     assert eh < 1e-2 and ee < 1e-2, (eh, ee)
     assert (d_tab[I] == 7.0).all()
+
+
+def test_activation_dropout_generator_statistics(ops):
+    """The counter hash behind the activation dropout (rp_philox.cuh rng4x32), observed through rp_dropout_bwd on an all-ones
+    input: keep rate, no row / column / lag structure, different masks for different sites, seeds and step counters."""
+    from replay_b200._lib import check, lib
+    rows, cols, p = 8192, 128, 0.2
+    x = torch.ones(rows, cols, device="cuda", dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def mask(seed, off, counter=None):
+        out = torch.empty_like(x)
+        cptr = None if counter is None else counter.data_ptr()
+        check(lib().rp_dropout_bwd(x.data_ptr(), out.data_ptr(), rows, cols, None, p, seed, off, cptr, st), "rp_dropout_bwd")
+        return (out.float() > 0)
+
+    m = mask(1234, 3 << 40)
+    n = rows * cols
+    sig = (p * (1 - p) / n) ** 0.5
+    assert abs(m.float().mean().item() - (1 - p)) < 5 * sig
+    assert (m.float().mean(0) - (1 - p)).abs().max() < 6 * (p * (1 - p) / rows) ** 0.5      # columns
+    assert (m.float().mean(1) - (1 - p)).abs().max() < 6 * (p * (1 - p) / cols) ** 0.5      # rows
+    f = m.float().flatten() - (1 - p)
+    for lag in (1, 2, 3, 4, 5, 8, 128, 129):                                                 # serial correlation
+        c = (f[:-lag] * f[lag:]).mean().item() / (p * (1 - p))
+        assert abs(c) < 6 / n ** 0.5, (lag, c)
+    assert torch.equal(m, mask(1234, 3 << 40))                                               # regenerable
+    for other in (mask(1235, 3 << 40), mask(1234, 4 << 40), mask(1234, 3 << 40, torch.tensor([7], device="cuda", dtype=torch.int64))):
+        agree = (m == other).float().mean().item()                                           # independent masks agree 68 %
+        assert abs(agree - (p * p + (1 - p) ** 2)) < 0.005, agree

@@ -606,22 +606,50 @@ __global__ void ce_label_scatter_kernel(const __nv_bfloat16* __restrict__ hc, co
 __global__ void ce_bound_kernel(const __nv_bfloat16* __restrict__ hc, const __nv_bfloat16* __restrict__ table,
                                 const float* __restrict__ bias, const int32_t* __restrict__ n_valid_ptr, int n_items, int d,
                                 unsigned int* __restrict__ bound /* [3] float bits, zeroed */) {
+  // G = min(32, d/8) lanes share one row with 16-byte loads (d/8 chunks per row, d in {64,128,256,512}); every thread keeps
+  // 4 rows in flight, so the 20 MB of operands stream instead of waiting on one shuffle chain per row.
   const int n_valid = *n_valid_ptr;
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cpr = d >> 3, G = cpr < 32 ? cpr : 32, per_lane = cpr / G;     // chunks per row / lanes per row / chunks per lane
+  const int rows_per_warp = 32 / G;
+  const int sub = lane / G, gl = lane % G;
+  const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
   const int total = n_valid + n_items;
   float mh = 0.f, me = 0.f, mb = 0.f;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < total; r += gridDim.x * wpb) {
-    const bool is_h = r < n_valid;
-    const __nv_bfloat16* row = is_h ? hc + (size_t)r * d : table + (size_t)(r - n_valid) * d;
-    float ss = 0.f;
-    for (int c = lane * 2; c < d; c += 64) {
-      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + c));
-      ss = fmaf(v.x, v.x, fmaf(v.y, v.y, ss));
+  for (long long r0 = warp_id * rows_per_warp * 4; r0 < total; r0 += n_warps * rows_per_warp * 4) {
+    float ss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + u * rows_per_warp + sub;
+      if (r < total) {
+        const __nv_bfloat16* row = r < n_valid ? hc + (size_t)r * d : table + (size_t)(r - n_valid) * d;
+        for (int k = 0; k < per_lane; ++k) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + gl + k * G);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __bfloat1622float2(h2[q]);
+            ss[u] = fmaf(f.x, f.x, fmaf(f.y, f.y, ss[u]));
+          }
+        }
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (is_h) mh = fmaxf(mh, ss); else me = fmaxf(me, ss);
-    if (!is_h && bias && lane == 0) mb = fmaxf(mb, fabsf(bias[r - n_valid]));
+    for (int u = 0; u < 4; ++u) {
+      for (int o = G >> 1; o > 0; o >>= 1) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
+      const long long r = r0 + u * rows_per_warp + sub;
+      if (r < total) {
+        if (r < n_valid) mh = fmaxf(mh, ss[u]); else me = fmaxf(me, ss[u]);
+        if (r >= n_valid && bias && gl == 0) mb = fmaxf(mb, fabsf(bias[r - n_valid]));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, o));
+    me = fmaxf(me, __shfl_xor_sync(0xffffffffu, me, o));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
   }
   if (lane == 0) {  // non-negative floats order like their bit patterns
     atomicMax(bound + 0, __float_as_uint(mh));
@@ -666,17 +694,23 @@ __global__ void ce_fused_finalize_kernel(const float* __restrict__ part_dh, cons
     const __nv_bfloat16* er = table + (size_t)y * d;
     const float scale = inv_n / z;
     float dot = 0.f;
-    for (int c = lane * 2; c < d; c += 64) {
-      const float2 h2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hr + c));
-      const float2 e2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(er + c));
-      dot = fmaf(h2.x, e2.x, fmaf(h2.y, e2.y, dot));
-      float a0 = 0.f, a1 = 0.f;
+    for (int c = lane * 4; c < d; c += 128) {  // 16-byte loads of the partials, all splits in flight
+      const uint2 hraw = *reinterpret_cast<const uint2*>(hr + c), eraw = *reinterpret_cast<const uint2*>(er + c);
+      const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hraw.x));
+      const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hraw.y));
+      const float2 e0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&eraw.x));
+      const float2 e1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&eraw.y));
+      dot = fmaf(h0.x, e0.x, fmaf(h0.y, e0.y, fmaf(h1.x, e1.x, fmaf(h1.y, e1.y, dot))));
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
       for (int p = 0; p < n_splits; ++p) {
-        const float2 v = *reinterpret_cast<const float2*>(part_dh + ((size_t)p * capacity + t) * d + c);
-        a0 += v.x;
-        a1 += v.y;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(part_dh + ((size_t)p * capacity + t) * d + c));
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
       }
-      *reinterpret_cast<uint32_t*>(d_hc + (size_t)t * d + c) = pack_bf16(a0 * scale - inv_n * e2.x, a1 * scale - inv_n * e2.y);
+      uint2 o;
+      o.x = pack_bf16(a.x * scale - inv_n * e0.x, a.y * scale - inv_n * e0.y);
+      o.y = pack_bf16(a.z * scale - inv_n * e1.x, a.w * scale - inv_n * e1.y);
+      *reinterpret_cast<uint2*>(d_hc + (size_t)t * d + c) = o;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);

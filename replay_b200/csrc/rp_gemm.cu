@@ -499,6 +499,167 @@ static int launch_gemm_ws(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   return RP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent streaming variant for mid-size and large single GEMMs (BERT4Rec's d -> 4d FFN, the d = 512 CE backward,
+// predict-sized projections): one CTA per SM walks 128 x 128 output tiles (n fastest, so that CTAs running side by side
+// share the A rows in L2); A and B k-chunks stream through an NSTAGE-deep TMA ring; FOUR accumulator stages in TMEM
+// (4 x 128 = 512 columns) let the 8 epilogue warps trail the tensor core by up to three tiles, so short-K tiles with heavy
+// epilogues (bias + GELU + dropout) and long-K tiles both keep the MMA pipe fed.  batch == 1, split_k == 1.
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr int kPsEpiWarps = 8;
+static constexpr int kPsThreads = 64 + kPsEpiWarps * 32;
+
+// BN = 128: four accumulator stages; BN = 256 (wide outputs): two stages, and an M=128 x N=256 MMA reads 12 KB of shared
+// memory per 128 tensor-core cycles instead of 8 KB per 64, i.e. it is no longer shared-memory-bandwidth bound.
+template <int BN, bool A_MN, bool B_MN, int NSTAGE>
+__global__ void __launch_bounds__(kPsThreads, 1)
+gemm_ps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int kPsAcc = 512 / BN;
+  constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_tfull[kPsAcc], bar_tempty[kPsAcc];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int m_eff = p.M, k_eff = p.K;
+  if (p.m_limit_dev != nullptr) m_eff = max(0, min(p.M, *p.m_limit_dev - p.m_limit_base));
+  if (p.k_limit_dev != nullptr) k_eff = max(0, min(p.K, *p.k_limit_dev - p.k_limit_base));
+  const int m_tiles = (m_eff + 127) / 128, n_tiles = (p.N + BN - 1) / BN;
+  const int k_chunks = (k_eff + 63) / 64;
+  const long long total = (long long)m_tiles * n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < kPsAcc; ++i) {
+      mbar_init(&bar_tfull[i], 1);
+      mbar_init(&bar_tempty[i], kPsEpiWarps);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, kPsAcc * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+        const int m0 = (int)(t / n_tiles) * 128, n0 = (int)(t % n_tiles) * BN;
+        for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+          const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
+          mbar_wait(&bar_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&bar_full[s], STAGE);
+          uint8_t* sa = smem + s * STAGE;
+          uint8_t* sb = sa + A_BYTES;
+          if (A_MN) {
+            tma_load_2d(sa, &tmA, &bar_full[s], p.a_c0 + m0, p.a_r0 + kc * 64);
+            tma_load_2d(sa + 8192, &tmA, &bar_full[s], p.a_c0 + m0 + 64, p.a_r0 + kc * 64);
+          } else {
+            tma_load_2d(sa, &tmA, &bar_full[s], p.a_c0 + kc * 64, p.a_r0 + m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sb + c * 8192, &tmB, &bar_full[s], p.b_c0 + n0 + c * 64, p.b_r0 + kc * 64);
+          } else {
+            tma_load_2d(sb, &tmB, &bar_full[s], p.b_c0 + kc * 64, p.b_r0 + n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, A_MN, B_MN);
+      uint32_t it = 0, tile = 0;
+      for (long long t = blockIdx.x; t < total; t += gridDim.x, ++tile) {
+        const uint32_t as = tile % kPsAcc, aph = (tile / kPsAcc) & 1;
+        mbar_wait(&bar_tempty[as], aph ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+          const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
+          mbar_wait(&bar_full[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + s * STAGE), b0 = a0 + A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = A_MN ? umma_desc_sw128(a0 + ks * 2048, 8192, 1024) : umma_desc_sw128(a0 + ks * 32, 16, 1024);
+            const uint64_t bd = B_MN ? umma_desc_sw128(b0 + ks * 2048, 8192, 1024) : umma_desc_sw128(b0 + ks * 32, 16, 1024);
+            umma_ss(tmem + as * BN, ad, bd, idesc, (kc | ks) != 0);
+          }
+          umma_commit(&bar_empty[s]);
+        }
+        umma_commit(&bar_tfull[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue: 8 warps, warp%4 = lane quarter, (warp-2)/4 = column half
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    const int row = quarter * 32 + lane;
+    constexpr int HALF = BN / 2;
+    EpiRow er;
+    er.keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    er.drop_thr = p.drop_p > 0.f ? (uint32_t)(p.drop_p * 4294967296.0) : 0u;
+    er.seed_eff = p.seed + ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
+    uint32_t tile = 0;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++tile) {
+      const uint32_t as = tile % kPsAcc, aph = (tile / kPsAcc) & 1;
+      const int m = (int)(t / n_tiles) * 128 + row, n0 = (int)(t % n_tiles) * BN;
+      const bool row_ok = m < p.M;
+      er.c_base = p.c_off0 + (long long)m * p.ldc;
+      er.rm = 1.f;
+      if (p.rowmask && row_ok) er.rm = p.rowmask[p.rowmask_off0 + m] ? 1.f : 0.f;
+      er.exp_off = (p.act == 3 && row_ok) ? p.row_exp2_offset[m] : 0.f;
+      mbar_wait(&bar_tfull[as], aph);
+      tc_fence_after();
+      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + as * BN + half * HALF;
+      const float* bias_n0 = p.bias ? p.bias + n0 : nullptr;  // N % 32 == 0 is required with a bias (launcher)
+#pragma unroll 1
+      for (int c0 = 0; c0 < HALF; c0 += 64) {  // 64 columns per round
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tbase + c0, r0);
+        tmem_ld32(tbase + c0 + 32, r1);
+        tmem_ld_wait();
+        if (c0 + 64 == HALF) {  // accumulator stage is free once its last values sit in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_tempty[as]);
+        }
+        if (k_chunks == 0) {  // empty contraction (dynamic K limit): the accumulator was never written
+#pragma unroll
+          for (int q = 0; q < 32; ++q) r0[q] = r1[q] = 0u;
+        }
+        const int c = half * HALF + c0;
+        if (row_ok && n0 + c < p.N) gemm_epilogue_chunk(p, bias_n0, er, r0, n0, c);
+        if (row_ok && n0 + c + 32 < p.N) gemm_epilogue_chunk(p, bias_n0, er, r1, n0, c + 32);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, kPsAcc * BN);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm_ps(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  constexpr int NSTAGE = BN == 128 ? 6 : 4;
+  const int smem = NSTAGE * (128 * 128 + BN * 128) + 1024;
+  auto kern = gemm_ps_kernel<BN, A_MN, B_MN, NSTAGE>;
+  RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const long long tiles = (long long)((p.M + 127) / 128) * ((p.N + BN - 1) / BN);
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  kern<<<grid, kPsThreads, smem, st>>>(tmA, tmB, p);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
 // short-K problems (the body's d x d projections) use 2 stages so that 3 CTAs share an SM and their prologues,
 // main loops and epilogues overlap; long-K problems (weight gradients) use a 4-deep ring.
 template <int BN, bool A_MN, bool B_MN>
@@ -556,6 +717,32 @@ RP_API int rp_gemm(const rp_gemm_desc* g, void* stream_) {
     if (g->K == 128) { RP_WS_CASE(2); }
     RP_WS_CASE(4);
 #undef RP_WS_CASE
+  }
+  // persistent streaming kernel: single GEMMs with enough tiles for every SM and a contraction / width beyond the body's
+  // d x d projections (those are launch/latency-bound and stay on the tile kernel, which co-schedules 3 CTAs per SM)
+  static const long long ps_min_flop = getenv("RP_GEMM_PS_MIN_FLOP") ? atoll(getenv("RP_GEMM_PS_MIN_FLOP")) : 4000000000ll;
+  const long long tiles = (long long)((g->M + 127) / 128) * ((g->N + 127) / 128);
+  const bool ps_ok = g->batch == 1 && g->split_k == 1 && g->out_mode != 1 && g->out_mode != 3 && bn == 128 &&
+                     tiles >= sm_count() && 2ll * g->M * g->N * g->K >= ps_min_flop && (g->K > 128 || g->N > 128) &&
+                     (!g->bias || g->N % 32 == 0) && g->a_ro == 0 && g->a_ri == 0 && g->b_ro == 0 && g->b_ri == 0 &&
+                     g->a_co == 0 && g->a_ci == 0 && g->b_co == 0 && g->b_ci == 0 && g->c_oo == 0 && g->c_oi == 0 &&
+                     g->rowmask_oo == 0;
+  if (ps_ok) {
+    // wide outputs: 128 x 256 tiles when they still give every SM a tile
+    const bool wide = g->N >= 256 && (long long)((g->M + 127) / 128) * ((g->N + 255) / 256) >= sm_count();
+    if (wide && !g->b_mn) {  // K-major B: the TMA box grows to 256 rows
+      if ((rc = make_tmap_bf16(&tmB, g->B, g->b_rows, g->b_cols, g->ldb, 256)) != RP_OK) return rc;
+    }
+#define RP_PS_CASE(BN_)                                                                                  \
+  do {                                                                                                   \
+    if (!g->a_mn && !g->b_mn) return launch_gemm_ps<BN_, false, false>(tmA, tmB, p, stream);             \
+    if (!g->a_mn && g->b_mn) return launch_gemm_ps<BN_, false, true>(tmA, tmB, p, stream);               \
+    if (g->a_mn && !g->b_mn) return launch_gemm_ps<BN_, true, false>(tmA, tmB, p, stream);               \
+    return launch_gemm_ps<BN_, true, true>(tmA, tmB, p, stream);                                         \
+  } while (0)
+    if (wide) RP_PS_CASE(256);
+    RP_PS_CASE(128);
+#undef RP_PS_CASE
   }
 #define RP_GEMM_CASE(BN_, AMN_, BMN_) return launch_gemm<BN_, AMN_, BMN_>(tmA, tmB, p, g->batch, stream)
   if (bn == 64) {

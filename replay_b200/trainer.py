@@ -33,10 +33,12 @@ class Trainer:
         e.forward_train()
         e.backward()
 
-    def step(self, ids, pad_mask, labels, target_mask):
-        """One optimisation step on this rank's shard.  Returns the device loss tensor fp32 [2] (mean CE, 1/n_valid)."""
+    def step(self, *batch):
+        """One optimisation step on this rank's shard; ``batch`` is what the engine's ``set_batch`` takes (SASRec: ids,
+        pad_mask, labels, target_mask; BERT4Rec: ids, pad_mask, token_mask, labels).  Returns the device loss tensor fp32 [2]
+        (mean CE, 1/n_valid)."""
         e = self.engine
-        e.set_batch(ids, pad_mask, labels, target_mask)
+        e.set_batch(*batch)
         if not self.use_graph:
             c0 = e.lib.count
             self._fwd_bwd()

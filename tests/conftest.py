@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 # exercise the weight-stationary persistent GEMM on the small test shapes too (its production threshold is M >= 131072)
 os.environ.setdefault("RP_GEMM_WS_MIN_M", "1024")
+os.environ.setdefault("RP_GEMM_PS_MIN_FLOP", "50000000")  # route mid-size test GEMMs through the persistent streaming kernel
 
 
 def pytest_configure(config):

@@ -274,3 +274,65 @@ def test_activation_dropout_generator_statistics(ops):
     for other in (mask(1235, 3 << 40), mask(1234, 4 << 40), mask(1234, 3 << 40, torch.tensor([7], device="cuda", dtype=torch.int64))):
         agree = (m == other).float().mean().item()                                           # independent masks agree 68 %
         assert abs(agree - (p * p + (1 - p) ** 2)) < 0.005, agree
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+def test_persistent_streaming_gemm(ops, a_mn, b_mn):
+    """gemm_ps_kernel (tiles >= #SMs, K = 512 so the weight-stationary kernel does not take it): all four operand layouts,
+    fused epilogue (bias + GELU + residual, bf16 out), fp32 store and accumulate, N not a multiple of the tile."""
+    g = torch.Generator().manual_seed(int(a_mn) * 2 + int(b_mn))
+    M, N, K = 2504, 1184, 512          # 20 x 10 tiles, ragged last M and N tile (pitches stay 16-byte multiples)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.1).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    R = torch.randn(M, N, generator=g).to(torch.bfloat16)
+    Aop = (A.T.contiguous() if a_mn else A).cuda()
+    Bop = (W.T.contiguous() if b_mn else W).cuda()
+    z = A.double() @ W.double().T
+    ref = torch.nn.functional.gelu(z + bias.double()) + R.double()
+    C = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(Aop, Bop, C, M, N, K, a_mn=a_mn, b_mn=b_mn, bias=bias.cuda(), act=2, residual=R.cuda())
+    torch.cuda.synchronize()
+    assert (C.cpu().double() - ref).abs().max().item() < 0.06
+    C32 = torch.full((M, N), 1.5, device="cuda")
+    ops.gemm(Aop, Bop, C32, M, N, K, a_mn=a_mn, b_mn=b_mn, out_mode=2)
+    ops.gemm(Aop, Bop, C32, M, N, K, a_mn=a_mn, b_mn=b_mn, out_mode=4, alpha=0.5)
+    torch.cuda.synchronize()
+    assert (C32.cpu().double() - 1.5 * z).abs().max().item() < 5e-3
+    # dynamic limits on the device
+    lim = torch.tensor([1000], dtype=torch.int32, device="cuda")
+    Cm = torch.full((M, N), 9.0, device="cuda")
+    ops.gemm(Aop, Bop, Cm, M, N, K, a_mn=a_mn, b_mn=b_mn, out_mode=2, m_limit=lim)
+    klim = torch.tensor([200], dtype=torch.int32, device="cuda")
+    Ck = torch.full((M, N), 9.0, device="cuda")
+    ops.gemm(Aop, Bop, Ck, M, N, K, a_mn=a_mn, b_mn=b_mn, out_mode=2, k_limit=klim)
+    torch.cuda.synchronize()
+    assert (Cm[:1000].cpu().double() - z[:1000]).abs().max().item() < 5e-3 and (Cm[1024:] == 9.0).all()
+    zk = A[:, :256].double() @ W[:, :256].double().T      # the limit acts on whole 64-element chunks: 200 -> 256
+    assert (Ck.cpu().double() - zk).abs().max().item() < 5e-3
+
+
+def test_ce_head_wide_hidden_large_enough_for_the_persistent_gemm(ops):
+    """d = 512 CE backward at a size whose G / dE GEMMs run on gemm_ps_kernel (exp2 epilogue + device-side row limit, MN-major
+    operands + device-side contraction limit)."""
+    T, n_valid, I, d = 1536, 1300, 5000, 512
+    g = torch.Generator().manual_seed(11)
+    hc = (torch.randn(T, d, generator=g) * 0.7).to(torch.bfloat16)
+    hc[n_valid:] = 0
+    table = (torch.randn(I, d, generator=g) * 0.15).to(torch.bfloat16)
+    labels = torch.randint(0, I, (T,), generator=g, dtype=torch.int64)
+    st = ops.CEHeadState(T, I, d, "cuda")
+    nv = torch.tensor([n_valid], dtype=torch.int32, device="cuda")
+    d_hc = torch.zeros(T, d, device="cuda", dtype=torch.bfloat16)
+    d_tab = torch.full((I + 1, d), 7.0, device="cuda", dtype=torch.float32)
+    out = ops.ce_head_fwd(st, hc.cuda(), table.cuda(), labels.int().cuda(), nv, d_hc=d_hc, n_valid_hint=n_valid)
+    ops.ce_head_bwd(st, hc.cuda(), table.cuda(), labels.int().cuda(), nv, d_hc, d_tab, n_valid_hint=n_valid)
+    torch.cuda.synchronize()
+    h64, e64 = hc[:n_valid].double().requires_grad_(True), table.double().requires_grad_(True)
+    logits = h64 @ e64.T
+    loss = (torch.logsumexp(logits, -1) - logits.gather(1, labels[:n_valid, None])[:, 0]).mean()
+    loss.backward()
+    assert abs(out[0].item() - loss.item()) < 2e-4 * abs(loss.item())
+    eh = (d_hc[:n_valid].cpu().double() - h64.grad).norm() / h64.grad.norm()
+    ee = (d_tab[:I].cpu().double() - e64.grad).norm() / e64.grad.norm()
+    assert eh < 1e-2 and ee < 1e-2, (eh, ee)

@@ -22,4 +22,17 @@ for i in range(n):
     eng.train_step()
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / n
+from replay_b200.trainer import Trainer
+tr = Trainer(eng)
+for i in range(6):
+    tr.step(ids, pm, tok, ids)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for i in range(50):
+    loss = tr.step(ids, pm, tok, ids)
+b.record()
+torch.cuda.synchronize()
+ms = a.elapsed_time(b) / 50
+print(f"bert4rec c3 under a CUDA graph: {ms:.2f} ms/step -> {B / ms * 1e3:.0f} seq/s, loss {float(loss[0]):.3f}")
 print("bert4rec c3: n_valid", int(eng.n_valid), "losses", [round(x, 3) for x in losses], f"eager {dt*1e3:.2f} ms/step -> {B/dt:.0f} seq/s", "launches/step", eng.lib.count // 18)

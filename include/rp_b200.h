@@ -305,6 +305,10 @@ int rp_build_batch(const int64_t* offsets, const int32_t* items, long long n_seq
  * bit2: A given as At[K,M].  D = A . B^T in every mode.
  * ------------------------------------------------------------------------------------------------------------- */
 int rp_selftest_umma(int mode, const void* A, const void* B, float* D, void* stream);
+/* TMA feed-rate probe (tools/probe_tma.py): every CTA streams `tiles` [box_rows x d] row tiles of a K-major bf16 table through
+ * an 8-stage ring with no consumer. */
+int rp_selftest_tma_probe(const void* table, long long rows, int d, int box_rows, int tiles, int same_tile, int grid,
+                          void* stream);
 
 #ifdef __cplusplus
 }

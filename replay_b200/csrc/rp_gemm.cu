@@ -721,9 +721,10 @@ RP_API int rp_gemm(const rp_gemm_desc* g, void* stream_) {
   // persistent streaming kernel: single GEMMs with enough tiles for every SM and a contraction / width beyond the body's
   // d x d projections (those are launch/latency-bound and stay on the tile kernel, which co-schedules 3 CTAs per SM)
   static const long long ps_min_flop = getenv("RP_GEMM_PS_MIN_FLOP") ? atoll(getenv("RP_GEMM_PS_MIN_FLOP")) : 4000000000ll;
+  static const bool ps_small = getenv("RP_GEMM_PS_SMALL") && atoi(getenv("RP_GEMM_PS_SMALL")) != 0;  // experiment: d x d projections too
   const long long tiles = (long long)((g->M + 127) / 128) * ((g->N + 127) / 128);
   const bool ps_ok = g->batch == 1 && g->split_k == 1 && g->out_mode != 1 && g->out_mode != 3 && bn == 128 &&
-                     tiles >= sm_count() && 2ll * g->M * g->N * g->K >= ps_min_flop && (g->K > 128 || g->N > 128) &&
+                     tiles >= sm_count() && 2ll * g->M * g->N * g->K >= ps_min_flop && (g->K > 128 || g->N > 128 || ps_small) &&
                      (!g->bias || g->N % 32 == 0) && g->a_ro == 0 && g->a_ri == 0 && g->b_ro == 0 && g->b_ri == 0 &&
                      g->a_co == 0 && g->a_ci == 0 && g->b_co == 0 && g->b_ci == 0 && g->c_oo == 0 && g->c_oi == 0 &&
                      g->rowmask_oo == 0;

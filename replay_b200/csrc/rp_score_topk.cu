@@ -61,8 +61,58 @@ __device__ __forceinline__ float key2f(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-static constexpr int kEpiWarps = 8;
+static constexpr int kEpiWarps = 16;   // lane quarter x 32-column part of the 128-column tile: 4 warps per SM sub-partition hide the
+                                       // tcgen05.ld / shared-memory / insert-chain latencies of each other (measured: the epilogue,
+                                       // not the MMA or the TMA feed, bounds this kernel)
+static constexpr int kColParts = kEpiWarps / 4;
+static constexpr int kAcc = 4;       // accumulator stages in TMEM (4 x 128 = all 512 columns): the epilogue may trail by 3 tiles
 static constexpr int kThreads = 64 + kEpiWarps * 32;
+
+// One 32-column chunk of one row (thread).  FAST PATH: the maxima of the four 8-column groups against the admission threshold -
+// the values are never modified or copied (they stay in the registers tcgen05.ld filled).  Seen / out-of-catalog columns are
+// NOT masked here: a masked column only matters if it would be admitted, and then the slow path drops it from the hit mask (a
+// spurious slow-path entry costs about what masking every chunk that holds a seen item would).  SLOW PATH (a group maximum
+// beats the threshold): stage that group's 8 values in shared memory so that ONE insert site serves a runtime column index,
+// build the hit mask, drop masked columns, insert.
+template <int KMAX>
+__device__ __forceinline__ void score_chunk(const uint32_t (&raw)[32], uint32_t kill, float thr, float gthr, int col0,
+                                            TopK<KMAX>& top, float* sc, bool live, uint32_t* row_thr_u) {
+  // maxima of the four 8-column groups: the slow path then stages and scans only the group(s) that hold a candidate
+  float g[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float a = fmaxf(__uint_as_float(raw[8 * k]), __uint_as_float(raw[8 * k + 1]));
+    const float b = fmaxf(__uint_as_float(raw[8 * k + 2]), __uint_as_float(raw[8 * k + 3]));
+    const float c = fmaxf(__uint_as_float(raw[8 * k + 4]), __uint_as_float(raw[8 * k + 5]));
+    const float d = fmaxf(__uint_as_float(raw[8 * k + 6]), __uint_as_float(raw[8 * k + 7]));
+    g[k] = fmaxf(fmaxf(a, b), fmaxf(c, d));
+  }
+  const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+  if (m > thr) {
+    const float before = top.thr();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (g[k] > thr) {  // stage this group's 8 values so that ONE insert site serves a runtime column index
+        uint32_t hit = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          sc[i * (kEpiWarps * 32)] = __uint_as_float(raw[8 * k + i]);
+          hit |= (__uint_as_float(raw[8 * k + i]) > thr) ? (1u << i) : 0u;
+        }
+        hit &= ~(kill >> (8 * k));
+        while (hit) {
+          const int i = __ffs(hit) - 1;
+          hit &= hit - 1;
+          const float val = sc[i * (kEpiWarps * 32)];
+          if (val > fmaxf(top.thr(), gthr)) top.insert(val, col0 + 8 * k + i);
+        }
+      }
+    }
+    // publish an improved K-th best (only once the list holds K real entries, i.e. its last slot is finite)
+    if (live && top.thr() > before && top.thr() > -INFINITY) atomicMax(row_thr_u, f2key(top.thr()));
+  }
+}
+
 
 template <int KCH /* d / 64 */, int NSTAGE, int KMAX>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -74,9 +124,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                          // KCH chunks of 16 KB
   uint8_t* sB = smem + KCH * kChunkBytes;      // NSTAGE chunks of 16 KB
-  __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_tfull[2], bar_tempty[2];
+  __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_tfull[kAcc], bar_tempty[kAcc];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_scratch[32 * kEpiWarps * 32];  // [q][epilogue thread]: chunk values for the rare insert path
+  __shared__ float s_scratch[8 * kEpiWarps * 32];  // [i][epilogue thread]: one 8-column group staged for the insert path
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int user_tile = blockIdx.x / n_splits, split = blockIdx.x % n_splits;
@@ -84,6 +134,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int n_tiles_total = (n_items + kTileN - 1) / kTileN;
   const int t_begin = (int)(((long long)n_tiles_total * split) / n_splits);
   const int t_end = (int)(((long long)n_tiles_total * (split + 1)) / n_splits);
+  const int n_ct = t_end - t_begin;
 
   if (threadIdx.x == 0) {
     mbar_init(&bar_a, 1);
@@ -91,7 +142,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAcc; ++i) {
       mbar_init(&bar_tfull[i], 1);
       mbar_init(&bar_tempty[i], kEpiWarps);  // one arrive per epilogue warp
     }
@@ -99,7 +150,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1) tmem_alloc(&tmem_slot, 256);
+  if (warp == 1) tmem_alloc(&tmem_slot, kAcc * kTileN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -127,8 +178,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&bar_a, 0);
       tc_fence_after();
       uint32_t it = 0;
-      for (int t = t_begin, j = 0; t < t_end; ++t, ++j) {
-        const uint32_t as = j & 1, aph = (j >> 1) & 1;
+      for (int j = 0; j < n_ct; ++j) {
+        const uint32_t as = j % kAcc, aph = (j / kAcc) & 1;
         mbar_wait(&bar_tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t dcol = tmem + as * kTileN;
@@ -147,8 +198,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------ epilogue: 8 warps; warp%4 = TMEM lane quarter, (warp-2)/4 = column half
-    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    // ------------------------------------------------ epilogue: 16 warps; warp%4 = TMEM lane quarter, (warp-2)/4 = 32-column part
+    const int ew = warp - 2, quarter = warp & 3, part = ew >> 2;
     const int row = quarter * 32 + lane;
     const int u = u0 + row;
     const bool live = u < n_users;
@@ -171,87 +222,57 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       next_seen = ci < S ? sp[ci] : kNoId;
       pre_seen = ci + 1 < S ? sp[ci + 1] : kNoId;
     }
+    // K-th best already secured for this row by ANY thread / CTA working on it (other column halves and item splits):
+    // anything strictly below it cannot reach the final top-K, so it never enters the insert path.  The shared value is
+    // read one tile AHEAD (a stale threshold is only weaker, never wrong), so its L2 round trip is off the per-tile path.
+    uint32_t gk = live ? *reinterpret_cast<volatile uint32_t*>(row_thr + u) : 0u;
+    float gthr = -INFINITY;
     for (int t = t_begin, j = 0; t < t_end; ++t, ++j) {
-      const uint32_t as = j & 1, aph = (j >> 1) & 1;
+      const uint32_t as = j % kAcc, aph = (j / kAcc) & 1;
+      if ((j & 3) == 0) {  // refresh every 4th tile: the shared threshold moves slowly once the lists are full
+        gthr = gk != 0u ? key2f(gk - 1u) : -INFINITY;  // largest value strictly below the shared K-th best
+        if (live) gk = *reinterpret_cast<volatile uint32_t*>(row_thr + u);  // lands long before its use 4 tiles later
+      }
       mbar_wait(&bar_tfull[as], aph);
       tc_fence_after();
-      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + as * kTileN + half * 64;
-      // K-th best already secured for this row by ANY thread / CTA working on it (other column halves and item splits):
-      // anything strictly below it cannot reach the final top-K, so it never enters the insert path
-      float gthr = -INFINITY;
-      if (live) {
-        const uint32_t gk = *reinterpret_cast<volatile uint32_t*>(row_thr + u);
-        if (gk != 0u) gthr = key2f(gk - 1u);  // largest value strictly below the shared K-th best: x > gthr <=> x >= shared
-      }
-      uint32_t raw0[32], raw1[32];
-      tmem_ld32(tbase, raw0);
-      tmem_ld32(tbase + 32, raw1);
+      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + as * kTileN + part * 32;
+      uint32_t raw[32];
+      tmem_ld32(tbase, raw);
       tmem_ld_wait();
       // the accumulator stage can be reused as soon as its values sit in registers
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[as]);
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        const int col0 = t * kTileN + half * 64 + c;
-        float x[32];
-#pragma unroll
-        for (int q = 0; q < 32; ++q) x[q] = __uint_as_float(c == 0 ? raw0[q] : raw1[q]);
-        if (bias) {  // biased head (BERT4Rec): warp-uniform 16-byte loads, bias padded to a multiple of 128 entries
-#pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
-            x[q] += b4.x; x[q + 1] += b4.y; x[q + 2] += b4.z; x[q + 3] += b4.w;
-          }
-        }
-        if (col0 + 32 > n_items) {  // ragged last tile: columns beyond the catalog do not exist
-#pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if (col0 + q >= n_items) x[q] = -INFINITY;
-        }
-        // seen items of this 32-column chunk as a bit mask (also skips entries that belong to the other column half)
-        uint32_t kill = 0;
-        while (next_seen < col0 + 32) {
-          if (next_seen >= col0) kill |= 1u << (next_seen - col0);
-          next_seen = pre_seen;
-          ++ci;
-          pre_seen = ci + 1 < S ? sp[ci + 1] : kNoId;
-        }
-        if (kill) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if ((kill >> q) & 1u) x[q] = -INFINITY;
-        }
-        const float thr = fmaxf(top.thr(), gthr);
-        bool a0 = false, a1 = false, a2 = false, a3 = false;  // four independent compare chains
+      const int col0 = t * kTileN + part * 32;
+      // seen items of this 32-column chunk as a bit mask (also skips entries that belong to the other column parts);
+      // columns beyond the catalog (ragged last tile) are "seen" too
+      uint32_t kill = 0;
+      while (next_seen < col0 + 32) {
+        if (next_seen >= col0) kill |= 1u << (next_seen - col0);
+        next_seen = pre_seen;
+        ++ci;
+        pre_seen = ci + 1 < S ? sp[ci + 1] : kNoId;
+      }
+      if (col0 + 32 > n_items) kill |= (col0 >= n_items) ? 0xffffffffu : (0xffffffffu << (n_items - col0));
+      const float thr = live ? fmaxf(top.thr(), gthr) : INFINITY;  // rows beyond the batch never enter the insert path
+      if (bias == nullptr) {
+        score_chunk(raw, kill, thr, gthr, col0, top, sc, live, row_thr + u);
+      } else {  // biased head (BERT4Rec): warp-uniform 16-byte loads, bias padded to a multiple of 128 entries
+        uint32_t xb[32];
 #pragma unroll
         for (int q = 0; q < 32; q += 4) {
-          a0 |= (x[q] > thr);
-          a1 |= (x[q + 1] > thr);
-          a2 |= (x[q + 2] > thr);
-          a3 |= (x[q + 3] > thr);
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
+          xb[q] = __float_as_uint(__uint_as_float(raw[q]) + b4.x);
+          xb[q + 1] = __float_as_uint(__uint_as_float(raw[q + 1]) + b4.y);
+          xb[q + 2] = __float_as_uint(__uint_as_float(raw[q + 2]) + b4.z);
+          xb[q + 3] = __float_as_uint(__uint_as_float(raw[q + 3]) + b4.w);
         }
-        if (a0 | a1 | a2 | a3) {  // some lane of the warp has a candidate: stage the chunk, then walk only the set bits
-#pragma unroll
-          for (int q = 0; q < 32; ++q) sc[q * (kEpiWarps * 32)] = x[q];
-          uint32_t hit = 0;
-#pragma unroll
-          for (int q = 0; q < 32; ++q) hit |= (x[q] > thr) ? (1u << q) : 0u;
-          const float before = top.thr();
-          while (hit) {
-            const int q = __ffs(hit) - 1;
-            hit &= hit - 1;
-            const float val = sc[q * (kEpiWarps * 32)];
-            if (val > fmaxf(top.thr(), gthr)) top.insert(val, col0 + q);
-          }
-          // publish an improved K-th best (only once the list holds K real entries, i.e. its last slot is finite)
-          if (live && top.thr() > before && top.thr() > -INFINITY) atomicMax(row_thr + u, f2key(top.thr()));
-        }
+        score_chunk(xb, kill, thr, gthr, col0, top, sc, live, row_thr + u);
       }
     }
     if (live) {
-      float* pv = part_vals + (((size_t)u * n_splits + split) * 2 + half) * K;
-      int32_t* pi = part_ids + (((size_t)u * n_splits + split) * 2 + half) * K;
+      float* pv = part_vals + (((size_t)u * n_splits + split) * kColParts + part) * K;
+      int32_t* pi = part_ids + (((size_t)u * n_splits + split) * kColParts + part) * K;
 #pragma unroll
       for (int i = 0; i < KMAX; ++i)
         if (i >= KMAX - K) {
@@ -262,7 +283,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, kAcc * kTileN);
 }
 
 // one warp per user: merge n_splits sorted partial lists -> final top-K; ties: smaller column first.
@@ -415,7 +436,7 @@ RP_API size_t rp_score_topk_workspace(int n_users, int n_items, int d, int K) {
   if (n_users <= 0 || n_items <= 0 || K <= 0) return 0;
   const int ut = (n_users + rp::kTileM - 1) / rp::kTileM, it = (n_items + rp::kTileN - 1) / rp::kTileN;
   const int p = rp::choose_splits(ut, it);
-  return (size_t)n_users * p * 2 * K * 8 + (size_t)n_users * 4 + 256;
+  return (size_t)n_users * p * rp::kColParts * K * 8 + (size_t)n_users * 4 + 256;
 }
 
 RP_API int rp_seen_prepare(const int64_t* seen_ids, int n_users, int S, int item_count, const int32_t* inv_map,
@@ -445,8 +466,8 @@ RP_API int rp_score_topk(const void* hq, const void* table, const float* bias, c
   const int ut = (n_users + kTileM - 1) / kTileM, it = (n_items + kTileN - 1) / kTileN;
   const int p = choose_splits(ut, it);
   float* pv = reinterpret_cast<float*>(workspace);
-  int32_t* pi = reinterpret_cast<int32_t*>(pv + (size_t)n_users * p * 2 * K);
-  uint32_t* row_thr = reinterpret_cast<uint32_t*>(pi + (size_t)n_users * p * 2 * K);
+  int32_t* pi = reinterpret_cast<int32_t*>(pv + (size_t)n_users * p * kColParts * K);
+  uint32_t* row_thr = reinterpret_cast<uint32_t*>(pi + (size_t)n_users * p * kColParts * K);
   RP_CUDA_CHECK(cudaMemsetAsync(row_thr, 0, (size_t)n_users * 4, stream));
   CUtensorMap tmA, tmB;
   int rc;
@@ -461,7 +482,7 @@ RP_API int rp_score_topk(const void* hq, const void* table, const float* bias, c
   if (rc != RP_OK) return rc;
   const int threads = 128;
   const int blocks = (n_users * 32 + threads - 1) / threads;
-  topk_merge_kernel<<<blocks, threads, 0, stream>>>(pv, pi, seen_sorted, S, n_users, n_items, K, p * 2, candidates, out_ids,
+  topk_merge_kernel<<<blocks, threads, 0, stream>>>(pv, pi, seen_sorted, S, n_users, n_items, K, p * kColParts, candidates, out_ids,
                                                     out_scores);
   RP_LAUNCH_CHECK();
   return RP_OK;

@@ -107,7 +107,52 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// Probe (tools/probe_tma.py): how fast can ONE SM pull [box_rows x 64] bf16 boxes of a K-major [rows, d] table through TMA
+// into a 6-stage ring when nothing consumes them?  Every CTA streams `tiles` row tiles (all d/64 chunks each), CTAs start
+// at different tiles.  The ceiling this gives bounds the B-operand feed of score_topk / CE kernels (32 KB per 128x128 tile).
+__global__ void __launch_bounds__(64, 1) tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int n_row_tiles, int kch,
+                                                          int tiles, int box_bytes, int same_tile) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NST = 6;
+  __shared__ uint64_t bar_full[NST];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST; ++i) mbar_init(&bar_full[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t it = 0;
+    for (int t = 0; t < tiles; ++t) {
+      const int rt = same_tile ? (int)(blockIdx.x % n_row_tiles) : (int)((blockIdx.x * 7 + t) % n_row_tiles);
+      for (int kc = 0; kc < kch; ++kc, ++it) {
+        const uint32_t s = it % NST;
+        if (it >= NST) mbar_wait(&bar_full[s], ((it / NST) - 1) & 1);  // the previous load into this slot has landed
+        mbar_arrive_expect_tx(&bar_full[s], box_bytes);
+        tma_load_2d(smem + s * 32768, &tm, &bar_full[s], kc * 64, rt * (box_bytes / 128));
+      }
+    }
+    for (uint32_t k = (it > NST ? it - NST : 0); k < it; ++k) mbar_wait(&bar_full[k % NST], (k / NST) & 1);
+  }
+  __syncthreads();
+}
+
 }  // namespace rp
+
+RP_API int rp_selftest_tma_probe(const void* table, long long rows, int d, int box_rows, int tiles, int same_tile, int grid,
+                                 void* stream_) {
+  using namespace rp;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CUtensorMap tm;
+  int rc;
+  if (!table || rows <= 0 || d % 64 || (box_rows != 64 && box_rows != 128 && box_rows != 256)) return RP_EINVAL;
+  if ((rc = make_tmap_bf16(&tm, table, rows, d, d, box_rows)) != RP_OK) return rc;
+  const int smem = 6 * 32768 + 1024;
+  RP_CUDA_CHECK(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tma_probe_kernel<<<grid, 64, smem, stream>>>(tm, (int)(rows / box_rows), d / 64, tiles, box_rows * 128, same_tile);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
 
 RP_API int rp_selftest_umma(int mode, const void* A, const void* B, float* D, void* stream_) {
   using namespace rp;

@@ -238,6 +238,13 @@ int rp_bert_embed_bwd(const void* dx, const int32_t* ids, const uint8_t* pad_mas
 int rp_gather_rows(const void* src, const int32_t* idx, int n_max, const int32_t* n_dev, int d, void* dst, int scatter,
                    void* stream);
 
+/* Inference / predict(): the whole point-wise FFN in one pass  out = relu(y W1^T + b1) W2^T + b2 + y  (weights resident in shared
+ * memory, hidden activation kept in TMEM, residual read from the staged y tile): y is read once and out written once.
+ *   replaces (eval)  SasRecPointWiseFeedForward.forward  replay/models/nn/sequential/sasrec/model.py:496-506 ; replay/nn/ffn.py:43-57
+ * y, out bf16 [T, d] (no aliasing), w1 / w2 bf16 [d, d], b1 / b2 fp32 [d], rowmask optional uint8 [T] (0 -> zero row), d in {64,128}. */
+int rp_ffn_fused(const void* y, const void* w1, const float* b1, const void* w2, const float* b2, const uint8_t* rowmask, int T,
+                 int d, void* out, void* stream);
+
 int rp_adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, long long n, const float* lr_dev,
                  int32_t* step_dev, float beta1, float beta2, float eps, float grad_scale, const uint8_t* frozen,
                  int zero_grad, void* stream);

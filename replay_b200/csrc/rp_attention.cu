@@ -354,28 +354,50 @@ __global__ void attn_last_kernel(const __nv_bfloat16* __restrict__ q, const __nv
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float inv = sum > 0.f ? 1.f / sum : 0.f;  // no visible key -> zero output (safe-softmax semantics)
-  float acc[PER];
+  // P.V: every lane accumulates the value rows of ITS keys (independent 16-byte loads, nothing serialised on a broadcast of
+  // p_j), then a reduce-scatter butterfly over the lanes leaves HD/32 finished output columns per lane
+  float o[HD];
 #pragma unroll
-  for (int c = 0; c < PER; ++c) acc[c] = 0.f;
+  for (int c = 0; c < HD; ++c) o[c] = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const int jmax = min(32, L - i * 32);
-    for (int jj = 0; jj < jmax; ++jj) {
-      const float pj = __shfl_sync(0xffffffffu, sc[i], jj);
-      if (pj != 0.f) {
-        const __nv_bfloat16* vr = v + ((size_t)b * L + i * 32 + jj) * ldv + v_c0 + h * HD + lane * PER;
+    const int j = i * 32 + lane;
+    if (j < L && sc[i] != 0.f) {
+      const uint4* vr = reinterpret_cast<const uint4*>(v + ((size_t)b * L + j) * ldv + v_c0 + h * HD);
+      const float pj = sc[i];
 #pragma unroll
-        for (int c = 0; c < PER; c += 2) {
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vr + c));
-          acc[c] = fmaf(pj, f.x, acc[c]);
-          acc[c + 1] = fmaf(pj, f.y, acc[c + 1]);
+      for (int c8 = 0; c8 < HD / 8; ++c8) {
+        const uint4 raw = vr[c8];
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __bfloat1622float2(h2[t]);
+          o[c8 * 8 + 2 * t] = fmaf(pj, f.x, o[c8 * 8 + 2 * t]);
+          o[c8 * 8 + 2 * t + 1] = fmaf(pj, f.y, o[c8 * 8 + 2 * t + 1]);
         }
       }
     }
   }
-  __nv_bfloat16* o = out + (size_t)b * H * HD + h * HD + lane * PER;
+  int base = 0;
+#define RP_RS_STEP(OFF, N)                                                     \
+  {                                                                            \
+    const bool up = (lane & OFF) != 0;                                         \
+    _Pragma("unroll") for (int c = 0; c < N; ++c) {                            \
+      const float send = up ? o[c] : o[c + N];                                 \
+      const float recv = __shfl_xor_sync(0xffffffffu, send, OFF);              \
+      o[c] = (up ? o[c + N] : o[c]) + recv;                                    \
+    }                                                                          \
+    base += up ? N : 0;                                                        \
+  }
+  RP_RS_STEP(16, HD / 2)
+  RP_RS_STEP(8, HD / 4)
+  RP_RS_STEP(4, HD / 8)
+  RP_RS_STEP(2, HD / 16)
+  RP_RS_STEP(1, HD / 32)
+#undef RP_RS_STEP
+  __nv_bfloat16* op = out + (size_t)b * H * HD + h * HD + base;
 #pragma unroll
-  for (int c = 0; c < PER; c += 2) *reinterpret_cast<uint32_t*>(o + c) = pack_bf16(acc[c] * inv, acc[c + 1] * inv);
+  for (int c = 0; c < PER; c += 2) *reinterpret_cast<uint32_t*>(op + c) = pack_bf16(o[c] * inv, o[c + 1] * inv);
 }
 
 }  // namespace rp

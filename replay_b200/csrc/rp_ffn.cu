@@ -1,0 +1,245 @@
+// rp_ffn.cu - fused point-wise feed-forward for inference / predict():  out = relu(y W1^T + b1) W2^T + b2 + y  in ONE pass.
+//   replaces  SasRecPointWiseFeedForward.forward (eval)   replay/models/nn/sequential/sasrec/model.py:496-506
+//             PointWiseFeedForward.forward (eval)          replay/nn/ffn.py:43-57
+// predict() is HBM-bound on [T, d] activation passes (T = users x L tokens); two GEMM launches read y, write u, read u, read y
+// again (residual) and write the result.  Here both d x d weights stay resident in shared memory, a persistent CTA streams
+// 128-token tiles of y through a TMA ring, the hidden activation u never leaves the SM (bf16 written back into TMEM over the
+// first accumulator and consumed from there as the A operand of the second MMA) and the residual is read from the y tile that
+// is already in shared memory: y is read once, the result written once.  d in {64, 128}.
+#include "rp_host.h"
+#include "rp_sm100.cuh"
+
+namespace rp {
+
+static constexpr int kFfnEpiWarps = 8;
+static constexpr int kFfnThreads = 64 + kFfnEpiWarps * 32;
+
+struct FfnParams {
+  const float* b1;
+  const float* b2;
+  const uint8_t* rowmask;   // optional [T]: rows with 0 are written as zeros (legacy SASRec pad rows)
+  __nv_bfloat16* out;       // [T, d]
+  int T;
+};
+
+template <int KCH /* d / 64 */, int NA>
+__global__ void __launch_bounds__(kFfnThreads, 1)
+ffn_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const FfnParams p) {
+  constexpr int D = KCH * 64;
+  constexpr int W_BYTES = KCH * D * 128;      // [D x D] bf16 as KCH chunks of [D rows x 64]
+  constexpr int Y_STAGE = KCH * 128 * 128;    // [128 x D]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW1 = smem;
+  uint8_t* sW2 = smem + W_BYTES;
+  uint8_t* sY = smem + 2 * W_BYTES;
+  __shared__ uint64_t bar_w, y_full[NA], y_empty[NA], s1_full[2], u_ready[2], acc2_full[2], acc2_free[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_b1[D], s_b2[D];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.T + 127) / 128;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_w, 1);
+    for (int i = 0; i < NA; ++i) {
+      mbar_init(&y_full[i], 1);
+      mbar_init(&y_empty[i], kFfnEpiWarps);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s1_full[i], 1);
+      mbar_init(&u_ready[i], kFfnEpiWarps);
+      mbar_init(&acc2_full[i], 1);
+      mbar_init(&acc2_free[i], kFfnEpiWarps);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  if (threadIdx.x >= 64)
+    for (int i = threadIdx.x - 64; i < D; i += kFfnEpiWarps * 32) {
+      s_b1[i] = p.b1[i];
+      s_b2[i] = p.b2[i];
+    }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  // TMEM columns: acc1[p] at p*128 (its first D/2 columns per 64-wide half later hold u as packed bf16), acc2[p] at 256+p*128
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bar_w, 2 * W_BYTES);
+      for (int kc = 0; kc < KCH; ++kc) {
+        tma_load_2d(sW1 + kc * (D * 128), &tmW1, &bar_w, kc * 64, 0);
+        tma_load_2d(sW2 + kc * (D * 128), &tmW2, &bar_w, kc * 64, 0);
+      }
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const uint32_t s = it % NA, ph = (it / NA) & 1;
+        mbar_wait(&y_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&y_full[s], Y_STAGE);
+        for (int kc = 0; kc < KCH; ++kc) tma_load_2d(sY + s * Y_STAGE + kc * 16384, &tmY, &y_full[s], kc * 64, t * 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, D);
+      mbar_wait(&bar_w, 0);
+      tc_fence_after();
+      const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      for (int it = 0; it <= my_tiles; ++it) {
+        if (it < my_tiles) {  // first GEMM of tile `it`:  acc1 = y . W1^T
+          const uint32_t s = it % NA, ph = (it / NA) & 1, pp = it & 1;
+          mbar_wait(&y_full[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sY + s * Y_STAGE), b0 = smem_u32(sW1);
+#pragma unroll
+          for (int kc = 0; kc < KCH; ++kc)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss(tmem + pp * 128, umma_desc_sw128(a0 + kc * 16384 + ks * 32, 16, 1024),
+                      umma_desc_sw128(b0 + kc * (D * 128) + ks * 32, 16, 1024), idesc, (kc | ks) != 0);
+          umma_commit(&s1_full[pp]);
+        }
+        if (it >= 1) {  // second GEMM of tile `it - 1`:  acc2 = u . W2^T, u read from TMEM
+          const int jt = it - 1;
+          const uint32_t q = jt & 1, qph = (jt >> 1) & 1;
+          mbar_wait(&u_ready[q], qph);
+          mbar_wait(&acc2_free[q], qph ^ 1);
+          tc_fence_after();
+          const uint32_t b0 = smem_u32(sW2);
+#pragma unroll
+          for (int kc = 0; kc < KCH; ++kc)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)  // K step kc*64 + ks*16: packed pairs at column kc*64 + ks*8 of acc1[q]
+              umma_ts(tmem + 256 + q * 128, tmem + q * 128 + kc * 64 + ks * 8,
+                      umma_desc_sw128(b0 + kc * (D * 128) + ks * 32, 16, 1024), idesc, (kc | ks) != 0);
+          umma_commit(&acc2_full[q]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue warps: warp%4 = lane quarter, (warp-2)/4 = 64-column half
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const bool has_half = half * 64 < D;  // d = 64: only half 0 carries columns
+    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    for (int it = 0; it <= my_tiles; ++it) {
+      if (it < my_tiles) {  // u = relu(acc1 + b1) -> bf16, packed in place over this warp's own (already read) columns
+        const uint32_t pp = it & 1, pph = (it >> 1) & 1;
+        mbar_wait(&s1_full[pp], pph);
+        tc_fence_after();
+        if (has_half) {
+          const uint32_t base = tmem + lane_base + pp * 128 + half * 64;
+          uint32_t r0[32], r1[32];
+          tmem_ld32(base, r0);
+          tmem_ld32(base + 32, r1);
+          tmem_ld_wait();
+          uint32_t pk[32];
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) {
+            const float a0 = fmaxf(__uint_as_float(r0[q]) + s_b1[half * 64 + q], 0.f);
+            const float a1 = fmaxf(__uint_as_float(r0[q + 1]) + s_b1[half * 64 + q + 1], 0.f);
+            const float c0 = fmaxf(__uint_as_float(r1[q]) + s_b1[half * 64 + 32 + q], 0.f);
+            const float c1 = fmaxf(__uint_as_float(r1[q + 1]) + s_b1[half * 64 + 32 + q + 1], 0.f);
+            pk[q >> 1] = pack_bf16(a0, a1);
+            pk[16 + (q >> 1)] = pack_bf16(c0, c1);
+          }
+          tmem_st16(base, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+          tmem_st16(base + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&u_ready[pp]);
+      }
+      if (it >= 1) {  // out = acc2 + b2 + y  (y from the shared-memory tile), rows >= T are not stored
+        const int jt = it - 1;
+        const uint32_t q = jt & 1, qph = (jt >> 1) & 1, s = jt % NA;
+        const int t = (int)blockIdx.x + jt * (int)gridDim.x;
+        const int m = t * 128 + row;
+        mbar_wait(&acc2_full[q], qph);
+        tc_fence_after();
+        if (has_half) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(tmem + lane_base + 256 + q * 128 + half * 64, r0);
+          tmem_ld32(tmem + lane_base + 256 + q * 128 + half * 64 + 32, r1);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc2_free[q]);
+          const uint8_t* ytile = sY + s * Y_STAGE + half * 16384;  // 64-column chunk `half` of the y tile
+          const float keep = (p.rowmask == nullptr || (m < p.T && p.rowmask[m])) ? 1.f : 0.f;
+          if (m < p.T) {
+            __nv_bfloat16* o = p.out + (size_t)m * D + half * 64;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {  // 8 columns (16 bytes) per step
+              const uint4 yv = *reinterpret_cast<const uint4*>(ytile + sw128_off((uint32_t)row, (uint32_t)c8));
+              const __nv_bfloat162* y2 = reinterpret_cast<const __nv_bfloat162*>(&yv);
+              uint4 w;
+              uint32_t* w32 = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int col = c8 * 8 + 2 * e;
+                const float2 yf = __bfloat1622float2(y2[e]);
+                const float v0 = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + s_b2[half * 64 + col] + yf.x;
+                const float v1 = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + s_b2[half * 64 + col + 1] + yf.y;
+                w32[e] = pack_bf16(v0 * keep, v1 * keep);
+              }
+              *reinterpret_cast<uint4*>(o + c8 * 8) = w;
+            }
+          }
+        } else {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc2_free[q]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&y_empty[s]);  // the y tile (A operand of GEMM 1 and residual) is no longer needed
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int KCH>
+static int launch_ffn(const CUtensorMap& tmY, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const FfnParams& p,
+                      cudaStream_t st) {
+  constexpr int NA = 3;
+  constexpr int D = KCH * 64;
+  const int smem = 2 * KCH * D * 128 + NA * KCH * 128 * 128 + 1024;
+  auto kern = ffn_fused_kernel<KCH, NA>;
+  RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int n_tiles = (p.T + 127) / 128;
+  const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+  kern<<<grid, kFfnThreads, smem, st>>>(tmY, tmW1, tmW2, p);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+}  // namespace rp
+
+using namespace rp;
+
+// y, out bf16 [T, d] (out may not alias y); w1, w2 bf16 [d, d] (row = output feature, as torch Linear / Conv1d(k=1) weights);
+// b1, b2 fp32 [d]; rowmask optional uint8 [T].  d in {64, 128}.
+RP_API int rp_ffn_fused(const void* y, const void* w1, const float* b1, const void* w2, const float* b2,
+                        const uint8_t* rowmask, int T, int d, void* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!y || !w1 || !b1 || !w2 || !b2 || !out || T <= 0) return RP_EINVAL;
+  if (d != 64 && d != 128) return RP_ESHAPE;
+  if (y == out) return RP_EINVAL;
+  CUtensorMap tmY, tmW1, tmW2;
+  int rc;
+  if ((rc = make_tmap_bf16(&tmY, y, T, d, d, 128)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmW1, w1, d, d, d, d)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmW2, w2, d, d, d, d)) != RP_OK) return rc;
+  FfnParams p;
+  p.b1 = b1; p.b2 = b2; p.rowmask = rowmask; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.T = T;
+  return d == 64 ? launch_ffn<1>(tmY, tmW1, tmW2, p, stream) : launch_ffn<2>(tmY, tmW1, tmW2, p, stream);
+}

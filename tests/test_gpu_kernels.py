@@ -336,3 +336,29 @@ def test_ce_head_wide_hidden_large_enough_for_the_persistent_gemm(ops):
     eh = (d_hc[:n_valid].cpu().double() - h64.grad).norm() / h64.grad.norm()
     ee = (d_tab[:I].cpu().double() - e64.grad).norm() / e64.grad.norm()
     assert eh < 1e-2 and ee < 1e-2, (eh, ee)
+
+
+@pytest.mark.parametrize("T,d,mask", [(3000, 128, False), (20000, 128, True), (777, 64, True), (40000, 64, False)])
+def test_fused_ffn_matches_reference_formula(ops, T, d, mask):
+    """rp_ffn_fused (inference): relu(y W1^T + b1) W2^T + b2 + y in one pass, ragged last tile, optional row mask."""
+    from replay_b200._lib import check, lib
+    g = torch.Generator().manual_seed(T + d)
+    y = torch.randn(T, d, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(d, d, generator=g) * 0.15).to(torch.bfloat16)
+    w2 = (torch.randn(d, d, generator=g) * 0.15).to(torch.bfloat16)
+    b1, b2 = torch.randn(d, generator=g) * 0.3, torch.randn(d, generator=g) * 0.3
+    rm = (torch.rand(T, generator=g) > 0.3) if mask else None
+    u = torch.relu(y.double() @ w1.double().T + b1.double()).to(torch.bfloat16).double()   # the hidden activation is bf16
+    ref = u @ w2.double().T + b2.double() + y.double()
+    if mask:
+        ref = ref * rm[:, None].double()
+    out = torch.full((T + 5, d), 3.0, device="cuda", dtype=torch.bfloat16)
+    yc, w1c, w2c, b1c, b2c = y.cuda(), w1.cuda(), w2.cuda(), b1.cuda(), b2.cuda()
+    rmc = rm.to(torch.uint8).cuda() if mask else None
+    check(lib().rp_ffn_fused(yc.data_ptr(), w1c.data_ptr(), b1c.data_ptr(), w2c.data_ptr(), b2c.data_ptr(),
+                             None if rmc is None else rmc.data_ptr(), T, d, out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+          "rp_ffn_fused")
+    torch.cuda.synchronize()
+    err = (out[:T].cpu().double() - ref).abs().max().item()
+    assert err < 0.06, err            # bf16 output rounding of O(5) values
+    assert (out[T:] == 3.0).all()     # nothing written beyond T

@@ -224,6 +224,8 @@ int rp_layernorm_bwd(const void* dy, const void* x, const float* w, const float*
 int rp_dropout_bwd(const void* in, void* out, long long rows, int cols, const uint8_t* rowmask, float drop_p,
                    unsigned long long seed, unsigned long long drop_off, const unsigned long long* seed_ptr, void* stream);
 int rp_colsum(const void* dy, int rows, int cols, long long ld, float* db, void* stream);
+/* the same for n <= 6 tensors sharing the row count, one launch (the bias gradients of one block's backward) */
+int rp_colsum_multi(int n, const void* const* dy, const int* cols, const long long* ld, float* const* db, int rows, void* stream);
 
 /* torch.optim.Adam (models/nn/optimizer_utils/optimizer_factory.py:71-87; no weight decay) on flat fp32 buffers; refreshes
  * the bf16 shadow, optionally zeroes the gradient; lr and the step counter live in device memory. */

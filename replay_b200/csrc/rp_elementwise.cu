@@ -413,6 +413,56 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, int rows, in
   }
 }
 
+// Several column sums in ONE launch (blockIdx.y selects the tensor): the five bias gradients of a transformer block's
+// backward are small, independent reductions whose launch / drain overhead would otherwise be paid five times.
+struct ColsumBatch {
+  const __nv_bfloat16* dy[6];
+  float* db[6];
+  long long ld[6];
+  int cols[6];
+  int rows;
+};
+__global__ void colsum_multi_kernel(const ColsumBatch b) {
+  extern __shared__ float red4[];  // [rlanes][cols]
+  const int which = blockIdx.y;
+  const __nv_bfloat16* __restrict__ dy = b.dy[which];
+  float* __restrict__ db = b.db[which];
+  const int cols = b.cols[which], rows = b.rows;
+  const long long ld = b.ld[which];
+  const int tpr = cols / 4, rlanes = blockDim.x / tpr;
+  const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rl < rlanes) {
+    const int stride = gridDim.x * rlanes;
+    int r = blockIdx.x * rlanes + rl;
+    for (; r + 3 * stride < rows; r += 4 * stride) {
+      uint2 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) raw[u] = *reinterpret_cast<const uint2*>(dy + (size_t)(r + u * stride) * ld + cg * 4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+        const float2 a = __bfloat1622float2(h[0]), c = __bfloat1622float2(h[1]);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += c.x; acc[3] += c.y;
+      }
+    }
+    for (; r < rows; r += stride) {
+      const uint2 raw = *reinterpret_cast<const uint2*>(dy + (size_t)r * ld + cg * 4);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      const float2 a = __bfloat1622float2(h[0]), c = __bfloat1622float2(h[1]);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += c.x; acc[3] += c.y;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red4[rl * cols + cg * 4 + k] = acc[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float sum = 0.f;
+    for (int r = 0; r < rlanes; ++r) sum += red4[r * cols + c];
+    atomicAdd(db + c, sum);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam, no weight decay / amsgrad) over one flat fp32 parameter buffer; also refreshes the bf16 shadow
 // copy the kernels consume and zeroes the gradient for the next step.  The step counter and lr live in device memory so
@@ -591,6 +641,34 @@ RP_API int rp_colsum(const void* dy, int rows, int cols, long long ld, float* db
   if (grid > (rows + rlanes - 1) / rlanes) grid = (rows + rlanes - 1) / rlanes;
   colsum_kernel<<<grid, 256, (size_t)rlanes * cols * sizeof(float), stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), rows,
                                                                              cols, ld, db);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
+// db[i][c] += sum_r dy[i][r, c] for n <= 6 tensors that share the row count (one launch)
+RP_API int rp_colsum_multi(int n, const void* const* dy, const int* cols, const long long* ld, float* const* db, int rows,
+                           void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (n <= 0 || n > 6 || !dy || !cols || !ld || !db || rows <= 0) return RP_EINVAL;
+  ColsumBatch b;
+  int max_cols = 0, min_cols = 1 << 30;
+  for (int i = 0; i < n; ++i) {
+    if (!dy[i] || !db[i] || cols[i] <= 0 || (cols[i] & 3) || cols[i] > 1024 || (ld[i] & 3)) return RP_EINVAL;
+    b.dy[i] = reinterpret_cast<const __nv_bfloat16*>(dy[i]);
+    b.db[i] = db[i];
+    b.ld[i] = ld[i];
+    b.cols[i] = cols[i];
+    max_cols = cols[i] > max_cols ? cols[i] : max_cols;
+    min_cols = cols[i] < min_cols ? cols[i] : min_cols;
+  }
+  b.rows = rows;
+  const int rlanes_max = 256 / (min_cols / 4), rlanes_min = 256 / (max_cols / 4);
+  if (rlanes_min < 1) return RP_ESHAPE;
+  int gx = sm_count() * 4 / n;
+  if (gx < 1) gx = 1;
+  if (gx > (rows + rlanes_min - 1) / rlanes_min) gx = (rows + rlanes_min - 1) / rlanes_min;
+  const size_t smem = (size_t)(rlanes_max > rlanes_min ? rlanes_max : rlanes_min) * max_cols * sizeof(float);
+  colsum_multi_kernel<<<dim3(gx, n), 256, smem, stream>>>(b);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }

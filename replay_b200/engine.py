@@ -61,7 +61,7 @@ class _CountingLib:
     """Proxy over the ctypes library that counts the sm_100a kernel launches issued through it (bench.py reports them)."""
 
     KERNELS = {"rp_gemm": 1, "rp_attn_fwd": 1, "rp_attn_bwd": 1, "rp_attn_last": 1, "rp_attn_softmax_bwd": 1, "rp_prepare_batch": 2, "rp_embed_fwd": 1,
-               "rp_embed_bwd": 2, "rp_layernorm_fwd": 1, "rp_layernorm_bwd": 1, "rp_dropout_bwd": 1, "rp_colsum": 1,
+               "rp_embed_bwd": 2, "rp_layernorm_fwd": 1, "rp_layernorm_bwd": 1, "rp_dropout_bwd": 1, "rp_colsum": 1, "rp_colsum_multi": 1,
                "rp_adam_step": 2, "rp_cast_bf16": 1, "rp_counter_add": 1, "rp_reduce_splits": 1, "rp_ce_head_fwd": 2, "rp_ce_head_bwd": 3,
                "rp_score_topk": 2, "rp_seen_prepare": 1, "rp_sampled_head_fwd": 4, "rp_sampled_head_bwd": 4, "rp_ffn_fused": 1}
 
@@ -291,6 +291,15 @@ class SasRecEngine:
         check(self.lib.rp_colsum(dY.data_ptr(), dY.shape[0], dY.shape[1], dY.stride(0), db.data_ptr(), self._stream()),
               "rp_colsum")
 
+    def _colsum_multi(self, pairs):
+        """[(dY bf16 [T, cols], db fp32 [cols]), ...] (<= 6) in one launch: the bias gradients of one block."""
+        n = len(pairs)
+        dy = (ctypes.c_void_p * n)(*[a.data_ptr() for a, _ in pairs])
+        db = (ctypes.c_void_p * n)(*[b.data_ptr() for _, b in pairs])
+        cols = (ctypes.c_int * n)(*[a.shape[1] for a, _ in pairs])
+        ld = (ctypes.c_longlong * n)(*[a.stride(0) for a, _ in pairs])
+        check(self.lib.rp_colsum_multi(n, dy, cols, ld, db, pairs[0][0].shape[0], self._stream()), "rp_colsum_multi")
+
     def _ln_fwd(self, x, w, b, eps, y, mean, rstd, n_rows, gather=None, n_rows_dev=None):
         check(self.lib.rp_layernorm_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), eps, n_rows, self.cfg.d,
                                         None if n_rows_dev is None else n_rows_dev.data_ptr(),
@@ -497,16 +506,16 @@ class SasRecEngine:
                 d_t = dz
             # ---- FFN backward
             self._wgrad(d_t, a["u"], g("w2"), d, d)
-            self._colsum(d_t, g("b2"))
+            bias_grads = [(d_t, g("b2"))]  # column sums of this block, one launch at the end of its backward
             self._gemm(d_t, w("w2"), s["du"], T, d, d, b_mn=True, gate=a["u"], gate_scale=ks)
             self._wgrad(s["du"], a["y"], g("w1"), d, d)
-            self._colsum(s["du"], g("b1"))
+            bias_grads.append((s["du"], g("b1")))
             self._gemm(s["du"], w("w1"), s["dy"], T, d, d, b_mn=True, residual=dz)
             self._ln_bwd(s["dy"], a["h"], f("ln2_w"), a["mean2"], a["rstd2"], s["dh"], g("ln2_w"), g("ln2_b"), T)
             # ---- out projection
             self._gemm(s["dh"], w("out_w"), s["d_o"], T, d, d, b_mn=True)
             self._wgrad(s["dh"], a["O"], g("out_w"), d, d)
-            self._colsum(s["dh"], g("out_b"))
+            bias_grads.append((s["dh"], g("out_b")))
             # ---- attention backward
             KV, Q = a["KV"], a["Q"]
             if self.fused_attn_bwd:
@@ -546,11 +555,12 @@ class SasRecEngine:
             in_w = w("in_w")
             self._gemm(s["dQ"], in_w[:d], s["dq_in"], T, d, d, b_mn=True, residual=s["dh"])
             self._wgrad(s["dQ"], a["q_in"], g("in_w")[:d], d, d)
-            self._colsum(s["dQ"], g("in_b")[:d])
+            bias_grads.append((s["dQ"], g("in_b")[:d]))
             self._ln_bwd(s["dq_in"], x, f("ln1_w"), a["mean1"], a["rstd1"], s["tmp"], g("ln1_w"), g("ln1_b"), T)
             self._gemm(s["dKV"], in_w[d:], other, T, d, 2 * d, b_mn=True, residual=s["tmp"])
             self._wgrad(s["dKV"], x, g("in_w")[d:], 2 * d, d)
-            self._colsum(s["dKV"], g("in_b")[d:])
+            bias_grads.append((s["dKV"], g("in_b")[d:]))
+            self._colsum_multi(bias_grads)
             dx, other = other, dx
         pos0 = 0 if legacy else cfg.max_len - L
         check(self.lib.rp_embed_bwd(dx.data_ptr(), self.ids32.data_ptr(), self.in_pad.data_ptr(), self.B, L, d, cfg.pad_id,

@@ -316,6 +316,9 @@ int rp_build_batch(const int64_t* offsets, const int32_t* items, long long n_seq
 int rp_selftest_umma(int mode, const void* A, const void* B, float* D, void* stream);
 /* TMA feed-rate probe (tools/probe_tma.py): every CTA streams `tiles` [box_rows x d] row tiles of a K-major bf16 table through
  * an 8-stage ring with no consumer. */
+/* tcgen05.mma issue-rate probe (tools/probe_mma.py): mode bit0 B MN-major, bit1 A from TMEM, bit2 A MN-major; every CTA issues
+ * iters x 8 MMAs (128x128x16 bf16) and writes its elapsed SM cycles to cycles_out[blockIdx.x]. */
+int rp_selftest_mma_probe(int mode, int iters, int grid, long long* cycles_out, void* stream);
 int rp_selftest_tma_probe(const void* table, long long rows, int d, int box_rows, int tiles, int same_tile, int grid,
                           void* stream);
 

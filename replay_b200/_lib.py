@@ -77,6 +77,7 @@ def lib():
     _sig(L.rp_sampled_head_workspace, c_size_t, [c_int, c_int, c_int, c_int])
     _sig(L.rp_sampled_head_fwd, c_int, [P, P])
     _sig(L.rp_sampled_head_bwd, c_int, [P, P, P, P])
+    _sig(L.rp_selftest_mma_probe, c_int, [c_int, c_int, c_int, P, P])
     _sig(L.rp_selftest_tma_probe, c_int, [P, LL, c_int, c_int, c_int, c_int, c_int, P])
     _sig(L.rp_colsum_multi, c_int, [c_int, P, P, P, P, c_int, P])
     _sig(L.rp_ffn_fused, c_int, [P, P, P, P, P, P, c_int, c_int, P, P])

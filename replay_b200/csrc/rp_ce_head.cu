@@ -34,6 +34,9 @@ static constexpr int kThreads = 64 + kEpiWarps * 32;
 #ifndef RP_CE_BWD_CG
 #define RP_CE_BWD_CG 2
 #endif
+#ifndef RP_CE_ABLATE
+#define RP_CE_ABLATE 0
+#endif
 static constexpr int kBwdCG = RP_CE_BWD_CG;
 static constexpr int kBwdEpiWarps = 4 * kBwdCG;
 static constexpr int kBwdThreads = 64 + kBwdEpiWarps * 32;
@@ -446,6 +449,12 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       mbar_wait(&bar_sfull[b], (j / NBUF) & 1);
       tc_fence_after();
       const uint32_t sbase = tmem + lane_base + b * kT + cg * kW;
+#if RP_CE_ABLATE == 2  // diagnostic build (tools/ce_variants.sh): no epilogue work at all -> MMA + TMA pipeline alone
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_pfull[b]);
+      continue;
+#endif
       uint32_t raw[kW];
 #pragma unroll
       for (int c = 0; c < kW; c += 32) tmem_ld32(sbase + c, *reinterpret_cast<uint32_t(*)[32]>(&raw[c]));
@@ -489,6 +498,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           pk[q >> 1] = pack_bf16(g0, g1);
         }
       }
+#if RP_CE_ABLATE == 1  // diagnostic build: keep the TMEM traffic, drop the exponentials (G = bf16(S))
+#pragma unroll
+      for (int q = 0; q < kW; q += 2) pk[q >> 1] = pack_bf16(__uint_as_float(raw[q]), __uint_as_float(raw[q + 1]));
+#endif
       // in place over this warp's own (already consumed) S columns: kW fp32 columns -> kW/2 packed columns
 #pragma unroll
       for (int c = 0; c < kW / 2; c += 16) tmem_st16(sbase + c, *reinterpret_cast<uint32_t(*)[16]>(&pk[c]));

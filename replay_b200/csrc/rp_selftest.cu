@@ -137,7 +137,64 @@ __global__ void __launch_bounds__(64, 1) tma_probe_kernel(const __grid_constant_
   __syncthreads();
 }
 
+// Probe (tools/probe_mma.py): issue rate of tcgen05.mma 128x128x16 bf16 for the operand forms the kernels use, with nothing
+// else going on: one elected thread issues `iters` groups of 8 MMAs (K = 128) on fixed shared-memory / TMEM operands
+// (contents irrelevant) and the CTA reports elapsed SM cycles.  mode bit0: B MN-major, bit1: A from TMEM, bit2: A MN-major,
+// bits 3-4: N = 128 / 256 / 64.
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int mode, int iters, long long* cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 98304 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0 && elect_one()) {
+    const bool b_mn = mode & 1, a_tmem = mode & 2, a_mn = mode & 4;
+    const int nsel = (mode >> 3) & 3, N = nsel == 1 ? 256 : (nsel == 2 ? 64 : 128);
+    const uint32_t idesc = umma_idesc_bf16(128, N, a_mn, b_mn);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 32768);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t ad = a_mn ? umma_desc_sw128(a0 + ks * 2048, 16384, 1024) : umma_desc_sw128(a0 + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+        const uint64_t bd = b_mn ? umma_desc_sw128(b0 + ks * 2048, 16384, 1024) : umma_desc_sw128(b0 + (ks >> 2) * (N * 128) + (ks & 3) * 32, 16, 1024);
+        if (a_tmem) umma_ts(tmem + (N == 256 ? 0 : (it & 1) * 128), tmem + 256 + ks * 8, bd, idesc, ks != 0);
+        else umma_ss(tmem + (N == 256 ? 0 : (it & 1) * 128), ad, bd, idesc, ks != 0);
+      }
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    cycles_out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace rp
+
+RP_API int rp_selftest_mma_probe(int mode, int iters, int grid, long long* cycles_out, void* stream_) {
+  using namespace rp;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (mode < 0 || mode > 31 || iters <= 0 || grid <= 0 || !cycles_out) return RP_EINVAL;
+  const int smem = 98304 + 1024;
+  RP_CUDA_CHECK(cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mma_probe_kernel<<<grid, 128, smem, stream>>>(mode, iters, cycles_out);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
 
 RP_API int rp_selftest_tma_probe(const void* table, long long rows, int d, int box_rows, int tiles, int same_tile, int grid,
                                  void* stream_) {

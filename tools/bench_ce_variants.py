@@ -17,7 +17,7 @@ for path in sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file
     L = ctypes.CDLL(path)
     L.rp_ce_head_workspace.restype = sz; L.rp_ce_head_workspace.argtypes = [ci, ci, ci]
     L.rp_ce_head_fwd.argtypes = [P, P, P, P, P, ci, ci, ci, P, P, P, P, ci, P, sz, P]
-    L.rp_ce_head_bwd.argtypes = [P, P, P, P, P, ci, ci, ci, P, P, P, P, P, ci, P, sz, P]
+    L.rp_ce_head_bwd.argtypes = [P, P, P, P, P, ci, ci, ci, P, P, P, P, P, ci, ci, P, sz, P]
     wsb = L.rp_ce_head_workspace(T, I, d); ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
     fwd = lambda: L.rp_ce_head_fwd(hc.data_ptr(), table.data_ptr(), None, labels.data_ptr(), nv.data_ptr(), T, I, d, loss.data_ptr(), lse.data_ptr(), cvec.data_ptr(), d_hc.data_ptr(), nv_, ws.data_ptr(), wsb, st)
     bwd = lambda: L.rp_ce_head_bwd(hc.data_ptr(), table.data_ptr(), None, labels.data_ptr(), nv.data_ptr(), T, I, d, loss.data_ptr(), cvec.data_ptr(), d_hc.data_ptr(), d_tab.data_ptr(), None, 1, 0, ws.data_ptr(), wsb, st)

@@ -37,6 +37,9 @@ static constexpr int kThreads = 64 + kEpiWarps * 32;
 #ifndef RP_CE_ABLATE
 #define RP_CE_ABLATE 0
 #endif
+#ifndef RP_CE_NSTAGE_D128
+#define RP_CE_NSTAGE_D128 4   // B-tile ring depth of the backward / fused kernels at d = 128 (32 KB per stage)
+#endif
 static constexpr int kBwdCG = RP_CE_BWD_CG;
 static constexpr int kBwdEpiWarps = 4 * kBwdCG;
 static constexpr int kBwdThreads = 64 + kBwdEpiWarps * 32;
@@ -906,7 +909,7 @@ static int dispatch_ce_bwd(int d, const CUtensorMap& tmA, const CUtensorMap& tmB
       return launch_ce_bwd<1, 6, MODE>(tmA, tmB, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
                                        safe_flag, run_if_safe, n_splits, capacity, zpart, stream);
     case 128:
-      return launch_ce_bwd<2, 4, MODE>(tmA, tmB, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
+      return launch_ce_bwd<2, RP_CE_NSTAGE_D128, MODE>(tmA, tmB, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
                                        safe_flag, run_if_safe, n_splits, capacity, zpart, stream);
     case 256:
       return launch_ce_bwd<4, 2, MODE>(tmA, tmB, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,

@@ -207,6 +207,283 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Inference: everything after the attention of one SASRec block in ONE pass over the tokens:
+//   h = O Wo^T + bo + q_in ;  y = LayerNorm(h) ;  out = relu(y W1^T + b1) W2^T + b2 + y
+// (replaces out-projection GEMM + LayerNorm + the FFN above: h and y never reach HBM - 3 tensors move instead of 7).
+// Per 128-token tile three chained MMAs; y and u live in TMEM as packed bf16 over their own accumulators and feed the next MMA
+// as its A operand; LayerNorm statistics of a row are split over the two column-half threads and exchanged through shared
+// memory.  One tile in flight per CTA (3 x 128 accumulator columns), O tiles prefetched through a TMA ring: the kernel is
+// HBM-bound (3 x [T, d] bf16), the serial MMA chain is well below the memory time.
+// ------------------------------------------------------------------------------------------------------------------
+struct PostAttnParams {
+  const float* bo;
+  const float* ln_w;
+  const float* ln_b;
+  const float* b1;
+  const float* b2;
+  const __nv_bfloat16* q_in;   // residual of the out-projection, [T, d]
+  const uint8_t* rowmask;
+  __nv_bfloat16* out;
+  float eps;
+  int T;
+};
+
+template <int KCH, int NA>
+__global__ void __launch_bounds__(kFfnThreads, 1)
+post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWo,
+                       const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                       const PostAttnParams p) {
+  constexpr int D = KCH * 64;
+  constexpr int W_BYTES = KCH * D * 128;
+  constexpr int O_STAGE = KCH * 128 * 128;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sWo = smem;
+  uint8_t* sW1 = smem + W_BYTES;
+  uint8_t* sW2 = smem + 2 * W_BYTES;
+  uint8_t* sO = smem + 3 * W_BYTES;
+  __shared__ uint64_t bar_w, o_full[NA], o_empty[NA], g0_full, y_ready, g1_full, u_ready, g2_full, tile_done;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_vec[5][D];     // bo, ln_w, ln_b, b1, b2
+  __shared__ float2 s_stat[2][128];               // (sum, sum of squares) of each row's column half
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.T + 127) / 128;
+  const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_w, 1);
+    for (int i = 0; i < NA; ++i) {
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], 1);
+    }
+    mbar_init(&g0_full, 1);
+    mbar_init(&y_ready, kFfnEpiWarps);
+    mbar_init(&g1_full, 1);
+    mbar_init(&u_ready, kFfnEpiWarps);
+    mbar_init(&g2_full, 1);
+    mbar_init(&tile_done, kFfnEpiWarps);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmO);
+    tma_prefetch_desc(&tmWo);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  if (threadIdx.x >= 64)
+    for (int i = threadIdx.x - 64; i < D; i += kFfnEpiWarps * 32) {
+      s_vec[0][i] = p.bo[i];
+      s_vec[1][i] = p.ln_w[i];
+      s_vec[2][i] = p.ln_b[i];
+      s_vec[3][i] = p.b1[i];
+      s_vec[4][i] = p.b2[i];
+    }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_acc0 = tmem, t_acc1 = tmem + 128, t_acc2 = tmem + 256;  // y packed over acc0, u packed over acc1
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bar_w, 3 * W_BYTES);
+      for (int kc = 0; kc < KCH; ++kc) {
+        tma_load_2d(sWo + kc * (D * 128), &tmWo, &bar_w, kc * 64, 0);
+        tma_load_2d(sW1 + kc * (D * 128), &tmW1, &bar_w, kc * 64, 0);
+        tma_load_2d(sW2 + kc * (D * 128), &tmW2, &bar_w, kc * 64, 0);
+      }
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const uint32_t s = it % NA, ph = (it / NA) & 1;
+        mbar_wait(&o_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&o_full[s], O_STAGE);
+        for (int kc = 0; kc < KCH; ++kc) tma_load_2d(sO + s * O_STAGE + kc * 16384, &tmO, &o_full[s], kc * 64, t * 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, D);
+      mbar_wait(&bar_w, 0);
+      tc_fence_after();
+      for (int it = 0; it < my_tiles; ++it) {
+        const uint32_t s = it % NA, ph = (it / NA) & 1, tp = it & 1;
+        if (it > 0) mbar_wait(&tile_done, tp ^ 1);  // the previous tile's accumulators (and its y in TMEM) are drained
+        mbar_wait(&o_full[s], ph);
+        tc_fence_after();
+        {  // h~ = O . Wo^T
+          const uint32_t a0 = smem_u32(sO + s * O_STAGE), b0 = smem_u32(sWo);
+#pragma unroll
+          for (int kc = 0; kc < KCH; ++kc)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss(t_acc0, umma_desc_sw128(a0 + kc * 16384 + ks * 32, 16, 1024),
+                      umma_desc_sw128(b0 + kc * (D * 128) + ks * 32, 16, 1024), idesc, (kc | ks) != 0);
+          umma_commit(&o_empty[s]);
+          umma_commit(&g0_full);
+        }
+        mbar_wait(&y_ready, tp);
+        tc_fence_after();
+        {  // y . W1^T, y read from TMEM
+          const uint32_t b0 = smem_u32(sW1);
+#pragma unroll
+          for (int kc = 0; kc < KCH; ++kc)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ts(t_acc1, t_acc0 + kc * 64 + ks * 8, umma_desc_sw128(b0 + kc * (D * 128) + ks * 32, 16, 1024), idesc,
+                      (kc | ks) != 0);
+          umma_commit(&g1_full);
+        }
+        mbar_wait(&u_ready, tp);
+        tc_fence_after();
+        {  // u . W2^T, u read from TMEM
+          const uint32_t b0 = smem_u32(sW2);
+#pragma unroll
+          for (int kc = 0; kc < KCH; ++kc)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ts(t_acc2, t_acc1 + kc * 64 + ks * 8, umma_desc_sw128(b0 + kc * (D * 128) + ks * 32, 16, 1024), idesc,
+                      (kc | ks) != 0);
+          umma_commit(&g2_full);
+        }
+      }
+    }
+  } else {
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const bool has_half = half * 64 < D;
+    const int c0 = half * 64;
+    for (int it = 0; it < my_tiles; ++it) {
+      const uint32_t tp = it & 1;
+      const int t = (int)blockIdx.x + it * (int)gridDim.x;
+      const int m = t * 128 + row;
+      const bool row_ok = m < p.T;
+      // ---- h = O Wo^T + bo + q_in ; LayerNorm ; y -> TMEM (bf16, over this warp's own accumulator columns)
+      mbar_wait(&g0_full, tp);
+      tc_fence_after();
+      float hv[64];
+      float sum = 0.f, sq = 0.f;
+      if (has_half) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(t_acc0 + lane_base + c0, r0);
+        tmem_ld32(t_acc0 + lane_base + c0 + 32, r1);
+        tmem_ld_wait();
+        const uint4* qrow = reinterpret_cast<const uint4*>(p.q_in + (size_t)(row_ok ? m : 0) * D + c0);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const uint4 qv = row_ok ? __ldg(qrow + c8) : make_uint4(0u, 0u, 0u, 0u);
+          const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = c8 * 8 + 2 * e;
+            const float2 qf = __bfloat1622float2(q2[e]);
+            const float v0 = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + s_vec[0][c0 + col] + qf.x;
+            const float v1 = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + s_vec[0][c0 + col + 1] + qf.y;
+            hv[col] = v0;
+            hv[col + 1] = v1;
+            sum += v0 + v1;
+            sq = fmaf(v0, v0, fmaf(v1, v1, sq));
+          }
+        }
+      }
+      s_stat[half][row] = make_float2(sum, sq);
+      asm volatile("bar.sync 1, %0;" ::"r"(kFfnEpiWarps * 32) : "memory");
+      const float2 sa = s_stat[0][row], sb = (D > 64) ? s_stat[1][row] : make_float2(0.f, 0.f);
+      const float mean = (sa.x + sb.x) * (1.f / D);
+      const float var = fmaxf((sa.y + sb.y) * (1.f / D) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + p.eps);
+      asm volatile("bar.sync 1, %0;" ::"r"(kFfnEpiWarps * 32) : "memory");  // s_stat is rewritten by the next tile
+      if (has_half) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int q = 0; q < 64; q += 2) {
+          const float y0 = (hv[q] - mean) * rstd * s_vec[1][c0 + q] + s_vec[2][c0 + q];
+          const float y1 = (hv[q + 1] - mean) * rstd * s_vec[1][c0 + q + 1] + s_vec[2][c0 + q + 1];
+          pk[q >> 1] = pack_bf16(y0, y1);
+        }
+        tmem_st16(t_acc0 + lane_base + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+        tmem_st16(t_acc0 + lane_base + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&y_ready);
+      // ---- u = relu(y W1^T + b1) -> TMEM
+      mbar_wait(&g1_full, tp);
+      tc_fence_after();
+      if (has_half) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(t_acc1 + lane_base + c0, r0);
+        tmem_ld32(t_acc1 + lane_base + c0 + 32, r1);
+        tmem_ld_wait();
+        uint32_t pk[32];
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) {
+          pk[q >> 1] = pack_bf16(fmaxf(__uint_as_float(r0[q]) + s_vec[3][c0 + q], 0.f),
+                                 fmaxf(__uint_as_float(r0[q + 1]) + s_vec[3][c0 + q + 1], 0.f));
+          pk[16 + (q >> 1)] = pack_bf16(fmaxf(__uint_as_float(r1[q]) + s_vec[3][c0 + 32 + q], 0.f),
+                                        fmaxf(__uint_as_float(r1[q + 1]) + s_vec[3][c0 + 32 + q + 1], 0.f));
+        }
+        tmem_st16(t_acc1 + lane_base + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+        tmem_st16(t_acc1 + lane_base + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&u_ready);
+      // ---- out = u W2^T + b2 + y   (y re-read from TMEM as packed bf16)
+      mbar_wait(&g2_full, tp);
+      tc_fence_after();
+      if (has_half) {
+        uint32_t r0[32], r1[32], yk[32];
+        tmem_ld32(t_acc2 + lane_base + c0, r0);
+        tmem_ld32(t_acc2 + lane_base + c0 + 32, r1);
+        tmem_ld32(t_acc0 + lane_base + c0, yk);
+        tmem_ld_wait();
+        const float keep = (p.rowmask == nullptr || (row_ok && p.rowmask[m])) ? 1.f : 0.f;
+        if (row_ok) {
+          __nv_bfloat16* o = p.out + (size_t)m * D + c0;
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            uint4 w;
+            uint32_t* w32 = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int col = c8 * 8 + 2 * e;
+              const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yk[col >> 1]));
+              const float v0 = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + s_vec[4][c0 + col] + yf.x;
+              const float v1 = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + s_vec[4][c0 + col + 1] + yf.y;
+              w32[e] = pack_bf16(v0 * keep, v1 * keep);
+            }
+            *reinterpret_cast<uint4*>(o + c8 * 8) = w;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tile_done);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int KCH>
+static int launch_post_attn(const CUtensorMap& tmO, const CUtensorMap& tmWo, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
+                            const PostAttnParams& p, cudaStream_t st) {
+  constexpr int D = KCH * 64;
+  constexpr int NA = KCH == 1 ? 4 : 2;
+  const int smem = 3 * KCH * D * 128 + NA * KCH * 128 * 128 + 1024;
+  auto kern = post_attn_fused_kernel<KCH, NA>;
+  RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int n_tiles = (p.T + 127) / 128;
+  const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+  kern<<<grid, kFfnThreads, smem, st>>>(tmO, tmWo, tmW1, tmW2, p);
+  RP_LAUNCH_CHECK();
+  return RP_OK;
+}
+
 template <int KCH>
 static int launch_ffn(const CUtensorMap& tmY, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const FfnParams& p,
                       cudaStream_t st) {
@@ -242,4 +519,28 @@ RP_API int rp_ffn_fused(const void* y, const void* w1, const float* b1, const vo
   FfnParams p;
   p.b1 = b1; p.b2 = b2; p.rowmask = rowmask; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.T = T;
   return d == 64 ? launch_ffn<1>(tmY, tmW1, tmW2, p, stream) : launch_ffn<2>(tmY, tmW1, tmW2, p, stream);
+}
+
+// Inference: out-projection + residual + LayerNorm + FFN of one SASRec block in one pass (see post_attn_fused_kernel).
+//   o, q_in, out bf16 [T, d] (out may not alias o / q_in); wo, w1, w2 bf16 [d, d]; bo, ln_w, ln_b, b1, b2 fp32 [d]; d in {64,128}.
+//   replaces (eval)  out_proj + "x = q + a" + LayerNorm + FFN   replay/nn/sequential/sasrec/transformer.py:99-110 ;
+//                                                              replay/models/nn/sequential/sasrec/model.py:435-441
+RP_API int rp_post_attn_fused(const void* o, const void* q_in, const void* wo, const float* bo, const float* ln_w,
+                              const float* ln_b, float eps, const void* w1, const float* b1, const void* w2, const float* b2,
+                              const uint8_t* rowmask, int T, int d, void* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!o || !q_in || !wo || !bo || !ln_w || !ln_b || !w1 || !b1 || !w2 || !b2 || !out || T <= 0) return RP_EINVAL;
+  if (d != 64 && d != 128) return RP_ESHAPE;
+  if (out == o || out == q_in) return RP_EINVAL;
+  CUtensorMap tmO, tmWo, tmW1, tmW2;
+  int rc;
+  if ((rc = make_tmap_bf16(&tmO, o, T, d, d, 128)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmWo, wo, d, d, d, d)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmW1, w1, d, d, d, d)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmW2, w2, d, d, d, d)) != RP_OK) return rc;
+  PostAttnParams p;
+  p.bo = bo; p.ln_w = ln_w; p.ln_b = ln_b; p.b1 = b1; p.b2 = b2;
+  p.q_in = reinterpret_cast<const __nv_bfloat16*>(q_in); p.rowmask = rowmask;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out); p.eps = eps; p.T = T;
+  return d == 64 ? launch_post_attn<1>(tmO, tmWo, tmW1, tmW2, p, stream) : launch_post_attn<2>(tmO, tmWo, tmW1, tmW2, p, stream);
 }

@@ -63,7 +63,7 @@ class _CountingLib:
     KERNELS = {"rp_gemm": 1, "rp_attn_fwd": 1, "rp_attn_bwd": 1, "rp_attn_last": 1, "rp_attn_softmax_bwd": 1, "rp_prepare_batch": 2, "rp_embed_fwd": 1,
                "rp_embed_bwd": 2, "rp_layernorm_fwd": 1, "rp_layernorm_bwd": 1, "rp_dropout_bwd": 1, "rp_colsum": 1, "rp_colsum_multi": 1,
                "rp_adam_step": 2, "rp_cast_bf16": 1, "rp_counter_add": 1, "rp_reduce_splits": 1, "rp_ce_head_fwd": 2, "rp_ce_head_bwd": 3,
-               "rp_score_topk": 2, "rp_seen_prepare": 1, "rp_sampled_head_fwd": 4, "rp_sampled_head_bwd": 4, "rp_ffn_fused": 1}
+               "rp_score_topk": 2, "rp_seen_prepare": 1, "rp_sampled_head_fwd": 4, "rp_sampled_head_bwd": 4, "rp_ffn_fused": 1, "rp_post_attn_fused": 1}
 
     def __init__(self, L):
         self._L = L
@@ -133,6 +133,7 @@ class SasRecEngine:
         self.fused_attn_bwd = (cfg.d // cfg.n_heads) == 64 and seq_len <= 256
         self.sampled = None       # full-catalog CE unless set_loss() selects a sampled head
         self.fused_ffn_eval = True  # eval / predict: one-pass FFN kernel for d <= 128
+        self.fused_post_attn_eval = True  # eval / predict: out-projection + LayerNorm + FFN in one kernel for d <= 128
         self.fused_ce = True      # single-pass CE forward + dH (guarded on the device by a bound on |logit|)
         self.n_valid_hint = 0     # host estimate of the number of valid targets per step (load balance of the CE head only)
         self._alloc_workspace()
@@ -436,6 +437,14 @@ class SasRecEngine:
                 ad.p_save, ad.inv_sum, ad.m_save = None, None, None
             ad.drop_p, ad.seed, ad.drop_off, ad.seed_ptr = drop, self.seed, self._site(i, 0) << 40, self.rng_counter.data_ptr()
             check(self.lib.rp_attn_fwd(ctypes.byref(ad), self._stream()), "rp_attn_fwd")
+            if not training and d <= 128 and self.fused_post_attn_eval:
+                # inference: out-projection + residual + LayerNorm + FFN in one pass over the tokens (csrc/rp_ffn.cu)
+                check(self.lib.rp_post_attn_fused(a["O"].data_ptr(), a["q_in"].data_ptr(), w("out_w").data_ptr(),
+                                                  f("out_b").data_ptr(), f("ln2_w").data_ptr(), f("ln2_b").data_ptr(), 1e-8,
+                                                  w("w1").data_ptr(), f("b1").data_ptr(), w("w2").data_ptr(), f("b2").data_ptr(),
+                                                  pad.data_ptr() if legacy else None, T, d, self.x[i + 1].data_ptr(),
+                                                  self._stream()), "rp_post_attn_fused")
+                continue
             self._gemm(a["O"], w("out_w"), a["h"], T, d, d, bias=f("out_b"), residual=a["q_in"])
             self._ln_fwd(a["h"], f("ln2_w"), f("ln2_b"), 1e-8, a["y"], a["mean2"], a["rstd2"], T)
             if not training and d <= 128 and self.fused_ffn_eval:

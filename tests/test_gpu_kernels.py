@@ -362,3 +362,34 @@ def test_fused_ffn_matches_reference_formula(ops, T, d, mask):
     err = (out[:T].cpu().double() - ref).abs().max().item()
     assert err < 0.06, err            # bf16 output rounding of O(5) values
     assert (out[T:] == 3.0).all()     # nothing written beyond T
+
+
+@pytest.mark.parametrize("T,d,mask", [(3000, 128, False), (20000, 128, True), (777, 64, True), (33000, 64, False)])
+def test_fused_post_attention_block_matches_reference_formula(ops, T, d, mask):
+    """rp_post_attn_fused (inference): h = o Wo^T + bo + q ; y = LN(h) ; out = relu(y W1^T + b1) W2^T + b2 + y."""
+    from replay_b200._lib import check, lib
+    g = torch.Generator().manual_seed(T * 3 + d)
+    o = torch.randn(T, d, generator=g).to(torch.bfloat16)
+    qin = torch.randn(T, d, generator=g).to(torch.bfloat16)
+    wo, w1, w2 = ((torch.randn(d, d, generator=g) * 0.15).to(torch.bfloat16) for _ in range(3))
+    bo, b1, b2, lb = (torch.randn(d, generator=g) * 0.3 for _ in range(4))
+    lw = 1 + torch.randn(d, generator=g) * 0.1
+    rm = (torch.rand(T, generator=g) > 0.3) if mask else None
+    h = o.double() @ wo.double().T + bo.double() + qin.double()
+    y = torch.nn.functional.layer_norm(h, (d,), lw.double(), lb.double(), 1e-8)
+    yb = y.to(torch.bfloat16).double()                          # y feeds the FFN (and its residual) as bf16
+    u = torch.relu(yb @ w1.double().T + b1.double()).to(torch.bfloat16).double()
+    ref = u @ w2.double().T + b2.double() + yb
+    if mask:
+        ref = ref * rm[:, None].double()
+    out = torch.full((T + 3, d), 3.0, device="cuda", dtype=torch.bfloat16)
+    t = [x.cuda() for x in (o, qin, wo, bo, lw, lb, w1, b1, w2, b2)]
+    rmc = rm.to(torch.uint8).cuda() if mask else None
+    check(lib().rp_post_attn_fused(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), t[5].data_ptr(),
+                                   1e-8, t[6].data_ptr(), t[7].data_ptr(), t[8].data_ptr(), t[9].data_ptr(),
+                                   None if rmc is None else rmc.data_ptr(), T, d, out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+          "rp_post_attn_fused")
+    torch.cuda.synchronize()
+    err = (out[:T].cpu().double() - ref).abs().max().item()
+    assert err < 0.08, err
+    assert (out[T:] == 3.0).all()

@@ -5,7 +5,8 @@ import torch
 from replay_b200.engine_bert import Bert4RecEngine, BertConfig
 from replay_b200.models.nn.sequential import uniform_masker
 from replay_b200.synthetic import make_sequences
-B, L, d, I = 128, 200, 256, 100_000
+import sys as _s
+B, L, d, I = (int(_s.argv[1]) if len(_s.argv) > 1 else 128), 200, 256, 100_000
 cfg = BertConfig(n_items=I, d=d, n_heads=4, n_blocks=2, max_len=L, dropout=0.1)
 eng = Bert4RecEngine(cfg, B, L, "cuda", seed=1)
 ids, pm, _, _ = make_sequences(B, I, L, seed=3, pad_value=0)

@@ -6,7 +6,8 @@
 
 Workload (BASELINE.json configs[1]): SASRec seq_len=200 d=128 H=2 2 blocks |items|=50 000, full-catalog CE, Adam,
 dropout 0.2, bf16 compute / fp32 master, MovieLens-shaped synthetic sequences (replay_b200/synthetic.py, seed 1234),
-data parallel over N GPUs (weak scaling: 256 sequences per GPU per step).  One step = forward + backward + gradient
+data parallel over N GPUs (weak scaling: 512 sequences per GPU per step; 128 / 256 / 512 / 1024 give 92 / 109 / 124 / 130 k
+seq/s on one B200, profiles/README.md).  One step = forward + backward + gradient
 all-reduce + Adam over one batch.  Metric: training sequences/s (whole job).  The same JSON line also carries the scoring
 leg of BASELINE's metric (users/s, top-K@10 with seen-item filter, |items| = 500 000) under "scoring".
 """
@@ -25,7 +26,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(model="SASRec(new path)", seq_len=200, d=128, heads=2, blocks=2, n_items=50_000, dropout=0.2, per_gpu_batch=256)
+CFG = dict(model="SASRec(new path)", seq_len=200, d=128, heads=2, blocks=2, n_items=50_000, dropout=0.2, per_gpu_batch=512)
 SCORE_CFG = dict(n_items=500_000, d=128, seq_len=200, k=10, users_per_call=4096)
 
 
@@ -177,6 +178,8 @@ def run_ours(args):
     c = dict(CFG)
     if args.dropout is not None:
         c["dropout"] = args.dropout
+    if args.batch is not None:
+        c["per_gpu_batch"] = args.batch
     B, L, d, I = c["per_gpu_batch"], c["seq_len"], c["d"], c["n_items"]
     cfg = EncoderConfig(n_items=I, d=d, n_heads=c["heads"], n_blocks=c["blocks"], max_len=L, dropout=c["dropout"], variant="new")
     eng = SasRecEngine(cfg, B, L, dev, seed=1234)
@@ -380,7 +383,7 @@ def run_ours(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": "BASELINE configs[1]: SASRec L=200 d=128 H=2 blocks=2 |I|=50K, full-catalog CE + Adam, "
-                               f"dropout {c['dropout']}, MovieLens-shaped synthetic windows (inputs > L2: ~1 GB of activations per step)",
+                               f"dropout {c['dropout']}, MovieLens-shaped synthetic windows (inputs > L2: ~2 GB of activations per step)",
                    "global_batch": world * B, "per_gpu_batch": B, "seq_len": L, "d": d, "n_items": I,
                    "parallelism": f"dp{world}", "valid_targets_per_seq": valid_per_seq, "cuda_graph": not args.no_graph},
         "e2e": {"value": seq_s_e2e, "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -411,6 +414,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-scoring", action="store_true")
     ap.add_argument("--no-device-batches", action="store_true", help="skip the device-side batch construction leg")
+    ap.add_argument("--batch", type=int, default=None, help="sequences per GPU and step (default 512; SURVEY 8d sweeps {128, 256, 512})")
     ap.add_argument("--dropout", type=float, default=None, help="diagnostic override of the workload's dropout (0.2); "
                     "a run with this flag is not the benchmark configuration")
     args = ap.parse_args()

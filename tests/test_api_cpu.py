@@ -233,3 +233,45 @@ def test_parquet_to_csr_store(tmp_path):
         DeviceSequenceStore.from_parquet(pa.table({"item_id": pa.array([1, 2, 3])}), device="cpu")
     with pytest.raises(ValueError):
         DeviceSequenceStore(offsets=[0, 2, 1], items=[1, 2], device="cpu")
+
+
+def test_c_abi_argument_errors_without_a_gpu():
+    """include/rp_b200.h error convention: < 0 for argument / shape errors, decided before any CUDA call - so it can be checked
+    on a machine without a GPU (no kernel is launched here).  Workspace queries are pure host functions."""
+    import ctypes
+    from replay_b200._lib import AttnBwdDesc, AttnDesc, GemmDesc, SampledDesc, lib
+    L = lib()
+    EINVAL, ESHAPE = -1, -2
+    assert L.rp_version().decode().startswith("rp_b200")
+    # workspace sizes: positive, monotone in the problem size, 0 for nonsense
+    a, b = L.rp_score_topk_workspace(4096, 500_000, 128, 10), L.rp_score_topk_workspace(8192, 500_000, 128, 10)
+    assert 0 < a < b and L.rp_score_topk_workspace(0, 10, 128, 10) == 0
+    assert 0 < L.rp_ce_head_workspace(1024, 5000, 128) < L.rp_ce_head_workspace(2048, 5000, 128)
+    assert L.rp_ce_head_workspace(1024, 5000, 512) > L.rp_ce_head_workspace(1024, 5000, 256)      # d = 512 holds a G chunk
+    assert 0 < L.rp_sampled_head_workspace(1024, 128, 100, 1) < L.rp_sampled_head_workspace(1024, 128, 100, 0)
+    assert L.rp_sampled_head_workspace(0, 128, 100, 0) == 0
+    # NULL / malformed arguments
+    assert L.rp_gemm(None, None) == EINVAL
+    g = GemmDesc()
+    assert L.rp_gemm(ctypes.byref(g), None) == EINVAL                      # NULL operands
+    assert L.rp_attn_fwd(None, None) == EINVAL and L.rp_attn_fwd(ctypes.byref(AttnDesc()), None) == EINVAL
+    assert L.rp_attn_bwd(None, None) == EINVAL and L.rp_attn_bwd(ctypes.byref(AttnBwdDesc()), None) == EINVAL
+    assert L.rp_sampled_head_fwd(None, None) == EINVAL and L.rp_sampled_head_fwd(ctypes.byref(SampledDesc()), None) == EINVAL
+    assert L.rp_sampled_head_bwd(ctypes.byref(SampledDesc()), None, None, None) == EINVAL
+    assert L.rp_seen_prepare(None, 1, 1, 1, None, None, None) != 0
+    assert L.rp_score_topk(None, None, None, None, 0, 1, 1, 128, 10, None, None, None, None, 0, None) != 0
+    assert L.rp_ce_head_fwd(None, None, None, None, None, 1, 1, 128, None, None, None, None, 0, None, 0, None) == EINVAL
+    assert L.rp_ce_head_bwd(None, None, None, None, None, 1, 1, 128, None, None, None, None, None, 0, 0, None, 0, None) == EINVAL
+    assert L.rp_ffn_fused(None, None, None, None, None, None, 1, 128, None, None) == EINVAL
+    assert L.rp_post_attn_fused(None, None, None, None, None, None, 1e-8, None, None, None, None, None, 1, 128, None, None) == EINVAL
+    assert L.rp_build_batch(None, None, 1, None, None, 1, 1, 0, 0, 0.0, None, 0, 0, None, None, None, None, None, None, None) == EINVAL
+    assert L.rp_reduce_splits(None, 1, 4, 4, None, 0, None) == EINVAL
+    assert L.rp_colsum(None, 1, 4, 4, None, None) == EINVAL
+    assert L.rp_colsum_multi(0, None, None, None, None, 1, None) == EINVAL
+    assert L.rp_adam_step(None, None, None, None, None, 4, None, None, 0.9, 0.98, 1e-8, 1.0, None, 1, None) == EINVAL
+    assert L.rp_selftest_mma_probe(99, 1, 1, None, None) == EINVAL
+    # shape errors with non-NULL dummies (no memory is touched before the shape check)
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert L.rp_ffn_fused(p, p, p, p, p, None, 10, 96, ctypes.cast(ctypes.create_string_buffer(8), ctypes.c_void_p), None) == ESHAPE
+    assert L.rp_ce_head_fwd(p, p, None, p, p, 128, 100, 96, p, p, p, None, 0, p, 1 << 40, None) == ESHAPE

@@ -7,7 +7,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librp_b200.so")
+# RP_B200_LIB: load another build of the SAME C ABI (A/B timing of kernel variants inside one GPU call, tools/ab_env.sh)
+LIB_PATH = os.environ.get("RP_B200_LIB") or os.path.join(_HERE, "librp_b200.so")
 
 _lib = None
 

@@ -149,9 +149,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld32(tmem + lane_base + c * 32, raw);
       tmem_ld_wait();
       const uint32_t vm = vis_mask(c);
+      if (vm == 0xffffffffu) {  // chunk entirely visible (the common case below the diagonal): no per-element selects
+        float m0 = __uint_as_float(raw[0]), m1 = __uint_as_float(raw[1]), m2 = __uint_as_float(raw[2]), m3 = __uint_as_float(raw[3]);
 #pragma unroll
-      for (int q = 0; q < 32; ++q)
-        if (vm & (1u << q)) mx = fmaxf(mx, __uint_as_float(raw[q]));
+        for (int q = 4; q < 32; q += 4) {
+          m0 = fmaxf(m0, __uint_as_float(raw[q]));
+          m1 = fmaxf(m1, __uint_as_float(raw[q + 1]));
+          m2 = fmaxf(m2, __uint_as_float(raw[q + 2]));
+          m3 = fmaxf(m3, __uint_as_float(raw[q + 3]));
+        }
+        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+      } else if (vm != 0u) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          if (vm & (1u << q)) mx = fmaxf(mx, __uint_as_float(raw[q]));
+      }
     }
     const float moff = (mx == -INFINITY) ? 0.f : mx * sl2;
     // pass 2: exponentials, row sum, P (bf16) back into TMEM over S, optional copy of the un-dropped P to global
@@ -164,11 +176,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld_wait();
       const uint32_t vm = vis_mask(c);
       float e[32];
+      if (vm == 0xffffffffu) {
 #pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        const float v = ex2f(fmaf(__uint_as_float(raw[q]), sl2, -moff));
-        e[q] = (vm & (1u << q)) ? v : 0.f;
-        sum += e[q];
+        for (int q = 0; q < 32; ++q) {
+          e[q] = ex2f(fmaf(__uint_as_float(raw[q]), sl2, -moff));
+          sum += e[q];
+        }
+      } else if (vm == 0u) {  // chunk entirely masked (left padding, or beyond the diagonal): no exponentials at all
+#pragma unroll
+        for (int q = 0; q < 32; ++q) e[q] = 0.f;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const float v = ex2f(fmaf(__uint_as_float(raw[q]), sl2, -moff));
+          e[q] = (vm & (1u << q)) ? v : 0.f;
+          sum += e[q];
+        }
       }
       if (prow) {
 #pragma unroll

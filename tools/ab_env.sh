@@ -1,4 +1,5 @@
 #!/bin/bash
+# A/B of an environment knob inside ONE gpurun call (for two BUILDS of the library: RP_B200_LIB=<path to the other .so> vs "")
 # A/B of an environment knob inside ONE gpurun call (box-to-box variance is ~2-3 %): tools/ab_env.sh VAR "v1 v2 v1 v2" [bench args]
 VAR=$1; VALS=$2; shift 2
 for v in $VALS; do

@@ -197,7 +197,9 @@ class DeviceBatchLoader:
     def __len__(self):
         return self.per_rank // self.bs if self.drop_last else -(-self.per_rank // self.bs)
 
-    def __iter__(self):
+    def epoch_indices(self) -> torch.Tensor:
+        """This rank's window indices for the current epoch (on the store's device): seeded permutation shared by all ranks,
+        wrap-around padding to a multiple of the world size, strided over the ranks (DistributedSampler semantics)."""
         dev = self.store.device
         if self.shuffle:
             g = torch.Generator(device="cpu").manual_seed(self.seed + self.epoch)
@@ -207,7 +209,10 @@ class DeviceBatchLoader:
         total = self.per_rank * self.world
         if total > self.n:  # wrap-around padding
             order = torch.cat([order, order[: total - self.n]])
-        mine = order[self.rank: total: self.world]
+        return order[self.rank: total: self.world]
+
+    def __iter__(self):
+        mine = self.epoch_indices()
         for i in range(len(self)):
             idx = mine[i * self.bs: (i + 1) * self.bs]
             s, o = self.win_seq[idx], self.win_off[idx]

@@ -275,3 +275,24 @@ def test_c_abi_argument_errors_without_a_gpu():
     p = ctypes.cast(buf, ctypes.c_void_p)
     assert L.rp_ffn_fused(p, p, p, p, p, None, 10, 96, ctypes.cast(ctypes.create_string_buffer(8), ctypes.c_void_p), None) == ESHAPE
     assert L.rp_ce_head_fwd(p, p, None, p, p, 128, 100, 96, p, p, p, None, 0, p, 1 << 40, None) == ESHAPE
+
+
+def test_device_loader_sharding_covers_every_window_once():
+    """Host-side index logic of DeviceBatchLoader (no kernel involved: the store may live on the CPU for this): for every world
+    size the ranks' shards are disjoint up to the wrap-around padding and cover all windows; every epoch reshuffles."""
+    from replay_b200.device_data import DeviceBatchLoader, DeviceSequenceStore
+    rng = np.random.default_rng(0)
+    seqs = [rng.integers(0, 50, n) for n in rng.integers(1, 40, 101)]
+    st = DeviceSequenceStore(seqs, device="cpu")
+    for world in (1, 2, 3, 8):
+        loaders = [DeviceBatchLoader(st, 8, 16, 50, sliding_window_step=3, seed=5, rank=r, world_size=world) for r in range(world)]
+        n = loaders[0].n
+        shards = [ld.epoch_indices() for ld in loaders]
+        assert all(len(s) == -(-n // world) for s in shards)
+        allidx = torch.cat(shards)
+        assert set(allidx.tolist()) == set(range(n)) and len(allidx) - n < world      # only the wrap-around duplicates
+        assert len(loaders[0]) == -(-len(shards[0]) // 16)
+        loaders[0].set_epoch(1)
+        assert not torch.equal(loaders[0].epoch_indices(), shards[0])
+    fixed = DeviceBatchLoader(st, 8, 16, 50, shuffle=False)
+    assert torch.equal(fixed.epoch_indices(), torch.arange(fixed.n))

@@ -65,7 +65,7 @@ static constexpr int kEpiWarps = 16;   // lane quarter x 32-column part of the 1
                                        // tcgen05.ld / shared-memory / insert-chain latencies of each other (measured: the epilogue,
                                        // not the MMA or the TMA feed, bounds this kernel)
 static constexpr int kColParts = kEpiWarps / 4;
-static constexpr int kAcc = 4;       // accumulator stages in TMEM (4 x 128 = all 512 columns): the epilogue may trail by 3 tiles
+static constexpr int kAccMax = 4;    // accumulator stages in TMEM: 4 x 128 columns, or 3 when the user tile itself lives in TMEM
 static constexpr int kThreads = 64 + kEpiWarps * 32;
 
 // One 32-column chunk of one row (thread).  FAST PATH: the maxima of the four 8-column groups against the admission threshold -
@@ -119,12 +119,17 @@ __global__ void __launch_bounds__(kThreads, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const int32_t* __restrict__ seen_sorted, int S, int n_users, int n_items, int K, int n_splits,
                   const float* __restrict__ bias, float* __restrict__ part_vals, int32_t* __restrict__ part_ids,
-                  uint32_t* __restrict__ row_thr /* [n_users] shared K-th-best keys, zero-filled */) {
+                  uint32_t* __restrict__ row_thr /* [n_users] shared K-th-best keys, zero-filled */,
+                  const __nv_bfloat16* __restrict__ hq_rows /* the user matrix as a plain pointer (A_TMEM) */) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                          // KCH chunks of 16 KB
   uint8_t* sB = smem + KCH * kChunkBytes;      // NSTAGE chunks of 16 KB
-  __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_tfull[kAcc], bar_tempty[kAcc];
+  // d = 128 / 256: the resident user tile Hq goes to TMEM (packed bf16, d/2 columns) and the MMA takes its A operand from
+  // there: 73 instead of 102 cycles per 128x128x16 MMA (profiles/r1_mma_probe.md); three accumulator stages remain
+  constexpr bool A_TMEM = (KCH == 2 || KCH == 4);
+  constexpr int kAcc = A_TMEM ? 3 : 4;
+  __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_tfull[kAccMax], bar_tempty[kAccMax];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_scratch[8 * kEpiWarps * 32];  // [i][epilogue thread]: one 8-column group staged for the insert path
 
@@ -137,7 +142,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int n_ct = t_end - t_begin;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bar_a, 1);
+    mbar_init(&bar_a, A_TMEM ? kEpiWarps : 1);
     for (int i = 0; i < NSTAGE; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
@@ -150,7 +155,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1) tmem_alloc(&tmem_slot, kAcc * kTileN);
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -159,8 +164,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
     if (elect_one()) {
-      mbar_arrive_expect_tx(&bar_a, KCH * kChunkBytes);
-      for (int kc = 0; kc < KCH; ++kc) tma_load_2d(sA + kc * kChunkBytes, &tmA, &bar_a, kc * 64, u0);
+      if (!A_TMEM) {
+        mbar_arrive_expect_tx(&bar_a, KCH * kChunkBytes);
+        for (int kc = 0; kc < KCH; ++kc) tma_load_2d(sA + kc * kChunkBytes, &tmA, &bar_a, kc * 64, u0);
+      }
       uint32_t it = 0;
       for (int t = t_begin; t < t_end; ++t) {
         for (int kc = 0; kc < KCH; ++kc, ++it) {
@@ -189,9 +196,13 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
           const uint32_t a0 = smem_u32(sA + kc * kChunkBytes), b0 = smem_u32(sB + s * kChunkBytes);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ss(dcol, umma_desc_sw128(a0 + ks * 32, 16, 1024), umma_desc_sw128(b0 + ks * 32, 16, 1024), idesc,
-                    (kc | ks) != 0);
+          for (int ks = 0; ks < 4; ++ks) {
+            if (A_TMEM)
+              umma_ts(dcol, tmem + kAcc * kTileN + kc * 32 + ks * 8, umma_desc_sw128(b0 + ks * 32, 16, 1024), idesc, (kc | ks) != 0);
+            else
+              umma_ss(dcol, umma_desc_sw128(a0 + ks * 32, 16, 1024), umma_desc_sw128(b0 + ks * 32, 16, 1024), idesc,
+                      (kc | ks) != 0);
+          }
           umma_commit(&bar_empty[s]);
         }
         umma_commit(&bar_tfull[as]);
@@ -204,6 +215,25 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int u = u0 + row;
     const bool live = u < n_users;
     float* sc = s_scratch + ew * 32 + lane;  // element q of this thread at sc[q * (kEpiWarps*32)]
+    if (A_TMEM) {
+      // thread (row, part) copies K elements [part*D/4, (part+1)*D/4) of its user row from global memory into TMEM
+      constexpr int D = KCH * 64, WORDS = D / 8;   // 32-bit words (bf16 pairs) per thread
+      const uint4* src = reinterpret_cast<const uint4*>(hq_rows + (size_t)(live ? u : 0) * D + part * (D / 4));
+#pragma unroll
+      for (int c = 0; c < WORDS; c += 16) {
+        uint32_t v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+          const uint4 t4 = live ? __ldg(src + ((c + q) >> 2)) : make_uint4(0u, 0u, 0u, 0u);
+          v[q] = t4.x; v[q + 1] = t4.y; v[q + 2] = t4.z; v[q + 3] = t4.w;
+        }
+        tmem_st16(tmem + ((uint32_t)(quarter * 32) << 16) + kAcc * kTileN + part * WORDS + c, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_a);
+    }
     TopK<KMAX> top;
     top.init(K);
     // cursor into this user's sorted seen list (ascending, kNoId = padding).  The next entry is prefetched one step ahead
@@ -283,7 +313,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, kAcc * kTileN);
+  if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 // one warp per user: merge n_splits sorted partial lists -> final top-K; ties: smaller column first.
@@ -409,21 +439,21 @@ static int choose_splits(int n_user_tiles, int n_item_tiles) {
 template <int KCH, int NSTAGE>
 static int launch_score_topk(const CUtensorMap& tmA, const CUtensorMap& tmB, const int32_t* seen_sorted, int S, int B,
                              int I, int K, int n_splits, const float* bias, float* pv, int32_t* pi, uint32_t* row_thr,
-                             cudaStream_t stream) {
+                             const __nv_bfloat16* hq_rows, cudaStream_t stream) {
   const int smem = (KCH + NSTAGE) * kChunkBytes + 1024;
   const int grid = ((B + kTileM - 1) / kTileM) * n_splits;
   if (K <= 10) {
     auto kern = score_topk_kernel<KCH, NSTAGE, 10>;
     RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, bias, pv, pi, row_thr);
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, bias, pv, pi, row_thr, hq_rows);
   } else if (K <= 16) {
     auto kern = score_topk_kernel<KCH, NSTAGE, 16>;
     RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, bias, pv, pi, row_thr);
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, bias, pv, pi, row_thr, hq_rows);
   } else {
     auto kern = score_topk_kernel<KCH, NSTAGE, 32>;
     RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, bias, pv, pi, row_thr);
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, seen_sorted, S, B, I, K, n_splits, bias, pv, pi, row_thr, hq_rows);
   }
   RP_LAUNCH_CHECK();
   return RP_OK;
@@ -474,10 +504,14 @@ RP_API int rp_score_topk(const void* hq, const void* table, const float* bias, c
   if ((rc = make_tmap_bf16(&tmA, hq, n_users, d, d, 128)) != RP_OK) return rc;
   if ((rc = make_tmap_bf16(&tmB, table, n_items, d, d, 128)) != RP_OK) return rc;
   switch (d) {
-    case 64: rc = launch_score_topk<1, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, row_thr, stream); break;
-    case 128: rc = launch_score_topk<2, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, row_thr, stream); break;
-    case 256: rc = launch_score_topk<4, 6>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, row_thr, stream); break;
-    default: rc = launch_score_topk<8, 3>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, row_thr, stream); break;
+    case 64: rc = launch_score_topk<1, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, row_thr,
+                                            reinterpret_cast<const __nv_bfloat16*>(hq), stream); break;
+    case 128: rc = launch_score_topk<2, 8>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, row_thr,
+                                            reinterpret_cast<const __nv_bfloat16*>(hq), stream); break;
+    case 256: rc = launch_score_topk<4, 6>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, row_thr,
+                                            reinterpret_cast<const __nv_bfloat16*>(hq), stream); break;
+    default: rc = launch_score_topk<8, 3>(tmA, tmB, seen_sorted, S, n_users, n_items, K, p, bias, pv, pi, row_thr,
+                                            reinterpret_cast<const __nv_bfloat16*>(hq), stream); break;
   }
   if (rc != RP_OK) return rc;
   const int threads = 128;

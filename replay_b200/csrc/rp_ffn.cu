@@ -213,8 +213,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 // (replaces out-projection GEMM + LayerNorm + the FFN above: h and y never reach HBM - 3 tensors move instead of 7).
 // Per 128-token tile three chained MMAs; y and u live in TMEM as packed bf16 over their own accumulators and feed the next MMA
 // as its A operand; LayerNorm statistics of a row are split over the two column-half threads and exchanged through shared
-// memory.  One tile in flight per CTA (3 x 128 accumulator columns), O tiles prefetched through a TMA ring: the kernel is
-// HBM-bound (3 x [T, d] bf16), the serial MMA chain is well below the memory time.
+// memory.  Two tiles are in flight per CTA (2 x 256 TMEM columns: the third accumulator reuses the first one's columns once y
+// has been copied next to u), their MMAs and epilogues interleave; O tiles are prefetched through a TMA ring.
 // ------------------------------------------------------------------------------------------------------------------
 struct PostAttnParams {
   const float* bo;
@@ -243,7 +243,9 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
   uint8_t* sW1 = smem + W_BYTES;
   uint8_t* sW2 = smem + 2 * W_BYTES;
   uint8_t* sO = smem + 3 * W_BYTES;
-  __shared__ uint64_t bar_w, o_full[NA], o_empty[NA], g0_full, y_ready, g1_full, u_ready, g2_full, tile_done;
+  // TWO tiles in flight per CTA (parity p = tile & 1): the three MMAs of one tile alternate with those of the other, so every
+  // epilogue (LayerNorm, ReLU, output) overlaps an MMA of the other tile instead of sitting on a serial chain.
+  __shared__ uint64_t bar_w, o_full[NA], o_empty[NA], g0_full[2], y_ready[2], g1_full[2], u_ready[2], g2_full[2], tile_done[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_vec[5][D];     // bo, ln_w, ln_b, b1, b2
   __shared__ float2 s_stat[2][128];               // (sum, sum of squares) of each row's column half
@@ -251,18 +253,21 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.T + 127) / 128;
   const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_pairs = (my_tiles + 1) / 2;
   if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
     for (int i = 0; i < NA; ++i) {
       mbar_init(&o_full[i], 1);
       mbar_init(&o_empty[i], 1);
     }
-    mbar_init(&g0_full, 1);
-    mbar_init(&y_ready, kFfnEpiWarps);
-    mbar_init(&g1_full, 1);
-    mbar_init(&u_ready, kFfnEpiWarps);
-    mbar_init(&g2_full, 1);
-    mbar_init(&tile_done, kFfnEpiWarps);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&g0_full[i], 1);
+      mbar_init(&y_ready[i], kFfnEpiWarps);
+      mbar_init(&g1_full[i], 1);
+      mbar_init(&u_ready[i], kFfnEpiWarps);
+      mbar_init(&g2_full[i], 1);
+      mbar_init(&tile_done[i], kFfnEpiWarps);
+    }
     fence_barrier_init();
     tma_prefetch_desc(&tmO);
     tma_prefetch_desc(&tmWo);
@@ -282,7 +287,8 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t t_acc0 = tmem, t_acc1 = tmem + 128, t_acc2 = tmem + 256;  // y packed over acc0, u packed over acc1
+  // TMEM per parity p (256 columns): R0 = p*256 holds acc0, then y (packed bf16 in the first 32 columns of each 64-wide half),
+  // finally acc2; R1 = p*256 + 128 holds acc1, then u (packed, first 32 columns of each half) and a copy of y (next 32 columns)
 
   if (warp == 0) {
     if (elect_one()) {
@@ -305,45 +311,51 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
       constexpr uint32_t idesc = umma_idesc_bf16(128, D);
       mbar_wait(&bar_w, 0);
       tc_fence_after();
-      for (int it = 0; it < my_tiles; ++it) {
-        const uint32_t s = it % NA, ph = (it / NA) & 1, tp = it & 1;
-        if (it > 0) mbar_wait(&tile_done, tp ^ 1);  // the previous tile's accumulators (and its y in TMEM) are drained
-        mbar_wait(&o_full[s], ph);
-        tc_fence_after();
-        {  // h~ = O . Wo^T
-          const uint32_t a0 = smem_u32(sO + s * O_STAGE), b0 = smem_u32(sWo);
+      for (int pi = 0; pi < n_pairs; ++pi) {
+        const uint32_t pph = pi & 1;
+#pragma unroll 1
+        for (int stage = 0; stage < 3; ++stage) {
+#pragma unroll 1
+          for (int pp = 0; pp < 2; ++pp) {
+            const int it = 2 * pi + pp;
+            if (it >= my_tiles) continue;
+            const uint32_t R0 = tmem + pp * 256, R1 = R0 + 128;
+            if (stage == 0) {  // h~ = O . Wo^T
+              const uint32_t s = it % NA, ph = (it / NA) & 1;
+              if (pi > 0) mbar_wait(&tile_done[pp], pph ^ 1);  // tile it-2 has left R0 / R1
+              mbar_wait(&o_full[s], ph);
+              tc_fence_after();
+              const uint32_t a0 = smem_u32(sO + s * O_STAGE), b0 = smem_u32(sWo);
 #pragma unroll
-          for (int kc = 0; kc < KCH; ++kc)
+              for (int kc = 0; kc < KCH; ++kc)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_ss(t_acc0, umma_desc_sw128(a0 + kc * 16384 + ks * 32, 16, 1024),
-                      umma_desc_sw128(b0 + kc * (D * 128) + ks * 32, 16, 1024), idesc, (kc | ks) != 0);
-          umma_commit(&o_empty[s]);
-          umma_commit(&g0_full);
-        }
-        mbar_wait(&y_ready, tp);
-        tc_fence_after();
-        {  // y . W1^T, y read from TMEM
-          const uint32_t b0 = smem_u32(sW1);
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_ss(R0, umma_desc_sw128(a0 + kc * 16384 + ks * 32, 16, 1024),
+                          umma_desc_sw128(b0 + kc * (D * 128) + ks * 32, 16, 1024), idesc, (kc | ks) != 0);
+              umma_commit(&o_empty[s]);
+              umma_commit(&g0_full[pp]);
+            } else if (stage == 1) {  // y . W1^T, y read from TMEM (R0)
+              mbar_wait(&y_ready[pp], pph);
+              tc_fence_after();
+              const uint32_t b0 = smem_u32(sW1);
 #pragma unroll
-          for (int kc = 0; kc < KCH; ++kc)
+              for (int kc = 0; kc < KCH; ++kc)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_ts(t_acc1, t_acc0 + kc * 64 + ks * 8, umma_desc_sw128(b0 + kc * (D * 128) + ks * 32, 16, 1024), idesc,
-                      (kc | ks) != 0);
-          umma_commit(&g1_full);
-        }
-        mbar_wait(&u_ready, tp);
-        tc_fence_after();
-        {  // u . W2^T, u read from TMEM
-          const uint32_t b0 = smem_u32(sW2);
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_ts(R1, R0 + kc * 64 + ks * 8, umma_desc_sw128(b0 + kc * (D * 128) + ks * 32, 16, 1024), idesc, (kc | ks) != 0);
+              umma_commit(&g1_full[pp]);
+            } else {  // u . W2^T, u read from TMEM (R1); the result goes to R0, whose y has been copied to R1 by then
+              mbar_wait(&u_ready[pp], pph);
+              tc_fence_after();
+              const uint32_t b0 = smem_u32(sW2);
 #pragma unroll
-          for (int kc = 0; kc < KCH; ++kc)
+              for (int kc = 0; kc < KCH; ++kc)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_ts(t_acc2, t_acc1 + kc * 64 + ks * 8, umma_desc_sw128(b0 + kc * (D * 128) + ks * 32, 16, 1024), idesc,
-                      (kc | ks) != 0);
-          umma_commit(&g2_full);
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_ts(R0, R1 + kc * 64 + ks * 8, umma_desc_sw128(b0 + kc * (D * 128) + ks * 32, 16, 1024), idesc, (kc | ks) != 0);
+              umma_commit(&g2_full[pp]);
+            }
+          }
         }
       }
     }
@@ -353,115 +365,135 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const bool has_half = half * 64 < D;
     const int c0 = half * 64;
-    for (int it = 0; it < my_tiles; ++it) {
-      const uint32_t tp = it & 1;
-      const int t = (int)blockIdx.x + it * (int)gridDim.x;
-      const int m = t * 128 + row;
-      const bool row_ok = m < p.T;
-      // ---- h = O Wo^T + bo + q_in ; LayerNorm ; y -> TMEM (bf16, over this warp's own accumulator columns)
-      mbar_wait(&g0_full, tp);
-      tc_fence_after();
-      float hv[64];
-      float sum = 0.f, sq = 0.f;
-      if (has_half) {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(t_acc0 + lane_base + c0, r0);
-        tmem_ld32(t_acc0 + lane_base + c0 + 32, r1);
-        tmem_ld_wait();
-        const uint4* qrow = reinterpret_cast<const uint4*>(p.q_in + (size_t)(row_ok ? m : 0) * D + c0);
+    for (int pi = 0; pi < n_pairs; ++pi) {
+      const uint32_t pph = pi & 1;
+#pragma unroll 1
+      for (int stage = 0; stage < 3; ++stage) {
+#pragma unroll 1
+        for (int pp = 0; pp < 2; ++pp) {
+          const int it = 2 * pi + pp;
+          if (it >= my_tiles) continue;
+          const uint32_t R0 = tmem + lane_base + pp * 256, R1 = R0 + 128;
+          const int t = (int)blockIdx.x + it * (int)gridDim.x;
+          const int m = t * 128 + row;
+          const bool row_ok = m < p.T;
+          if (stage == 0) {
+            // ---- h = O Wo^T + bo + q_in ; LayerNorm ; y -> TMEM (bf16, over this warp's own accumulator columns)
+            mbar_wait(&g0_full[pp], pph);
+            tc_fence_after();
+            float hv[64];
+            float sum = 0.f, sq = 0.f;
+            if (has_half) {
+              uint32_t r0[32], r1[32];
+              tmem_ld32(R0 + c0, r0);
+              tmem_ld32(R0 + c0 + 32, r1);
+              tmem_ld_wait();
+              const uint4* qrow = reinterpret_cast<const uint4*>(p.q_in + (size_t)(row_ok ? m : 0) * D + c0);
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          const uint4 qv = row_ok ? __ldg(qrow + c8) : make_uint4(0u, 0u, 0u, 0u);
-          const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
+              for (int c8 = 0; c8 < 8; ++c8) {
+                const uint4 qv = row_ok ? __ldg(qrow + c8) : make_uint4(0u, 0u, 0u, 0u);
+                const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = c8 * 8 + 2 * e;
-            const float2 qf = __bfloat1622float2(q2[e]);
-            const float v0 = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + s_vec[0][c0 + col] + qf.x;
-            const float v1 = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + s_vec[0][c0 + col + 1] + qf.y;
-            hv[col] = v0;
-            hv[col + 1] = v1;
-            sum += v0 + v1;
-            sq = fmaf(v0, v0, fmaf(v1, v1, sq));
-          }
-        }
-      }
-      s_stat[half][row] = make_float2(sum, sq);
-      asm volatile("bar.sync 1, %0;" ::"r"(kFfnEpiWarps * 32) : "memory");
-      const float2 sa = s_stat[0][row], sb = (D > 64) ? s_stat[1][row] : make_float2(0.f, 0.f);
-      const float mean = (sa.x + sb.x) * (1.f / D);
-      const float var = fmaxf((sa.y + sb.y) * (1.f / D) - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + p.eps);
-      asm volatile("bar.sync 1, %0;" ::"r"(kFfnEpiWarps * 32) : "memory");  // s_stat is rewritten by the next tile
-      if (has_half) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int q = 0; q < 64; q += 2) {
-          const float y0 = (hv[q] - mean) * rstd * s_vec[1][c0 + q] + s_vec[2][c0 + q];
-          const float y1 = (hv[q + 1] - mean) * rstd * s_vec[1][c0 + q + 1] + s_vec[2][c0 + q + 1];
-          pk[q >> 1] = pack_bf16(y0, y1);
-        }
-        tmem_st16(t_acc0 + lane_base + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
-        tmem_st16(t_acc0 + lane_base + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
-        tmem_st_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&y_ready);
-      // ---- u = relu(y W1^T + b1) -> TMEM
-      mbar_wait(&g1_full, tp);
-      tc_fence_after();
-      if (has_half) {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(t_acc1 + lane_base + c0, r0);
-        tmem_ld32(t_acc1 + lane_base + c0 + 32, r1);
-        tmem_ld_wait();
-        uint32_t pk[32];
-#pragma unroll
-        for (int q = 0; q < 32; q += 2) {
-          pk[q >> 1] = pack_bf16(fmaxf(__uint_as_float(r0[q]) + s_vec[3][c0 + q], 0.f),
-                                 fmaxf(__uint_as_float(r0[q + 1]) + s_vec[3][c0 + q + 1], 0.f));
-          pk[16 + (q >> 1)] = pack_bf16(fmaxf(__uint_as_float(r1[q]) + s_vec[3][c0 + 32 + q], 0.f),
-                                        fmaxf(__uint_as_float(r1[q + 1]) + s_vec[3][c0 + 32 + q + 1], 0.f));
-        }
-        tmem_st16(t_acc1 + lane_base + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
-        tmem_st16(t_acc1 + lane_base + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
-        tmem_st_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&u_ready);
-      // ---- out = u W2^T + b2 + y   (y re-read from TMEM as packed bf16)
-      mbar_wait(&g2_full, tp);
-      tc_fence_after();
-      if (has_half) {
-        uint32_t r0[32], r1[32], yk[32];
-        tmem_ld32(t_acc2 + lane_base + c0, r0);
-        tmem_ld32(t_acc2 + lane_base + c0 + 32, r1);
-        tmem_ld32(t_acc0 + lane_base + c0, yk);
-        tmem_ld_wait();
-        const float keep = (p.rowmask == nullptr || (row_ok && p.rowmask[m])) ? 1.f : 0.f;
-        if (row_ok) {
-          __nv_bfloat16* o = p.out + (size_t)m * D + c0;
-#pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
-            uint4 w;
-            uint32_t* w32 = reinterpret_cast<uint32_t*>(&w);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int col = c8 * 8 + 2 * e;
-              const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yk[col >> 1]));
-              const float v0 = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + s_vec[4][c0 + col] + yf.x;
-              const float v1 = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + s_vec[4][c0 + col + 1] + yf.y;
-              w32[e] = pack_bf16(v0 * keep, v1 * keep);
+                for (int e = 0; e < 4; ++e) {
+                  const int col = c8 * 8 + 2 * e;
+                  const float2 qf = __bfloat1622float2(q2[e]);
+                  const float v0 = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + s_vec[0][c0 + col] + qf.x;
+                  const float v1 = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + s_vec[0][c0 + col + 1] + qf.y;
+                  hv[col] = v0;
+                  hv[col + 1] = v1;
+                  sum += v0 + v1;
+                  sq = fmaf(v0, v0, fmaf(v1, v1, sq));
+                }
+              }
             }
-            *reinterpret_cast<uint4*>(o + c8 * 8) = w;
+            s_stat[half][row] = make_float2(sum, sq);
+            asm volatile("bar.sync 1, %0;" ::"r"(kFfnEpiWarps * 32) : "memory");
+            const float2 sa = s_stat[0][row], sb = (D > 64) ? s_stat[1][row] : make_float2(0.f, 0.f);
+            const float mean = (sa.x + sb.x) * (1.f / D);
+            const float var = fmaxf((sa.y + sb.y) * (1.f / D) - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + p.eps);
+            asm volatile("bar.sync 1, %0;" ::"r"(kFfnEpiWarps * 32) : "memory");  // s_stat is rewritten by the next tile
+            if (has_half) {
+              uint32_t pk[32];
+#pragma unroll
+              for (int q = 0; q < 64; q += 2) {
+                const float y0 = (hv[q] - mean) * rstd * s_vec[1][c0 + q] + s_vec[2][c0 + q];
+                const float y1 = (hv[q + 1] - mean) * rstd * s_vec[1][c0 + q + 1] + s_vec[2][c0 + q + 1];
+                pk[q >> 1] = pack_bf16(y0, y1);
+              }
+              tmem_st16(R0 + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+              tmem_st16(R0 + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+              tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&y_ready[pp]);
+          } else if (stage == 1) {
+            // ---- u = relu(y W1^T + b1) -> TMEM (R1, first 32 columns of the half); y copied next to it, R0 becomes free
+            mbar_wait(&g1_full[pp], pph);
+            tc_fence_after();
+            if (has_half) {
+              uint32_t r0[32], r1[32], yk[32];
+              tmem_ld32(R1 + c0, r0);
+              tmem_ld32(R1 + c0 + 32, r1);
+              tmem_ld32(R0 + c0, yk);
+              tmem_ld_wait();
+              uint32_t pk[32];
+#pragma unroll
+              for (int q = 0; q < 32; q += 2) {
+                pk[q >> 1] = pack_bf16(fmaxf(__uint_as_float(r0[q]) + s_vec[3][c0 + q], 0.f),
+                                       fmaxf(__uint_as_float(r0[q + 1]) + s_vec[3][c0 + q + 1], 0.f));
+                pk[16 + (q >> 1)] = pack_bf16(fmaxf(__uint_as_float(r1[q]) + s_vec[3][c0 + 32 + q], 0.f),
+                                              fmaxf(__uint_as_float(r1[q + 1]) + s_vec[3][c0 + 32 + q + 1], 0.f));
+              }
+              tmem_st16(R1 + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+              tmem_st16(R1 + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+              tmem_st16(R1 + c0 + 32, *reinterpret_cast<uint32_t(*)[16]>(&yk[0]));
+              tmem_st16(R1 + c0 + 48, *reinterpret_cast<uint32_t(*)[16]>(&yk[16]));
+              tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&u_ready[pp]);
+          } else {
+            // ---- out = u W2^T + b2 + y   (acc2 in R0, y re-read from its copy in R1)
+            mbar_wait(&g2_full[pp], pph);
+            tc_fence_after();
+            if (has_half) {
+              uint32_t r0[32], r1[32], yk[32];
+              tmem_ld32(R0 + c0, r0);
+              tmem_ld32(R0 + c0 + 32, r1);
+              tmem_ld32(R1 + c0 + 32, yk);
+              tmem_ld_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tile_done[pp]);  // everything of this tile is in registers
+              const float keep = (p.rowmask == nullptr || (row_ok && p.rowmask[m])) ? 1.f : 0.f;
+              if (row_ok) {
+                __nv_bfloat16* o = p.out + (size_t)m * D + c0;
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                  uint4 w;
+                  uint32_t* w32 = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int col = c8 * 8 + 2 * e;
+                    const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yk[col >> 1]));
+                    const float v0 = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + s_vec[4][c0 + col] + yf.x;
+                    const float v1 = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + s_vec[4][c0 + col + 1] + yf.y;
+                    w32[e] = pack_bf16(v0 * keep, v1 * keep);
+                  }
+                  *reinterpret_cast<uint4*>(o + c8 * 8) = w;
+                }
+              }
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tile_done[pp]);
+            }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tile_done);
     }
   }
   tc_fence_before();

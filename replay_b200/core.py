@@ -58,6 +58,24 @@ class _EngineLoss(torch.autograd.Function):
         return eng.g32 * grad_out, None
 
 
+def dist_grad_all_reduce():
+    """Gradient exchange of the fused training step when ``torch.distributed`` is initialised with more than one rank (what
+    Lightning's DDP hooks do for the reference's autograd ``training_step``; here there is no autograd backward for them to
+    fire on): returns the ``all_reduce`` callback of ``SasRecEngine.train_step`` - one sum-all-reduce of the flat fp32
+    gradient, Adam then applies it scaled by 1/world - or None for a single process."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+    world = dist.get_world_size()
+
+    def _all_reduce(g32):
+        dist.all_reduce(g32, op=dist.ReduceOp.SUM)
+        return 1.0 / world
+
+    return _all_reduce
+
+
 class SasRecCore(torch.nn.Module):
     def __init__(self, cfg: EncoderConfig, item_feature: str = "item_id", device=None, seed: int = 0):
         super().__init__()
@@ -69,23 +87,41 @@ class SasRecCore(torch.nn.Module):
         self.flat: torch.nn.Parameter | None = None
         self._pending_state = None
         self._shadow_dirty = True
+        self.adam_betas = (0.9, 0.98)  # optimizer_factory.py:56-63 / nn/lightning/optimizer.py:44-60
         self._keymap = reference_key_map(cfg.variant, cfg.n_blocks, item_feature)
+        self._materialise()
 
-    # ---- engine lifetime: created on first use for the batch geometry it sees (re-created if a larger batch arrives)
+    def _materialise(self):
+        """Parameters exist from construction on (their layout depends on the configuration only), so ``parameters()``,
+        ``configure_optimizers`` and DDP wrapping work before the first batch.  Skipped where there is no GPU (the CPU-side
+        tests construct the mirrors for their key maps and error behaviour only)."""
+        if self._device.type == "cuda" and torch.cuda.is_available():
+            self.ensure_engine(1, self._initial_seq_len(), with_grad=False)
+
+    def _initial_seq_len(self) -> int:
+        return self.cfg.max_len if self.cfg.variant == "legacy" else min(self.cfg.max_len, 64)
+
+    def _make_engine(self, batch: int, seq_len: int, with_grad: bool):
+        return SasRecEngine(self.cfg, batch, seq_len, self._device, seed=self._seed, with_grad=with_grad)
+
+    # ---- engine lifetime: the engine (parameters, gradients, Adam state, lr, RNG counter) is created ONCE; a larger batch or
+    # another sequence length only re-allocates its activation workspace (SasRecEngine.resize), so ``flat`` keeps its identity
     def ensure_engine(self, batch: int, seq_len: int, with_grad: bool = True) -> SasRecEngine:
         e = self.engine
-        if e is None or batch > e.B or seq_len != e.L or (with_grad and not e.with_grad):
-            state = self._export() if e is not None else self._pending_state
-            opt = (e.adam_m.clone(), e.adam_v.clone(), e.step_count.clone()) if (e is not None and e.with_grad) else None
-            self.engine = SasRecEngine(self.cfg, batch, seq_len, self._device, seed=self._seed, with_grad=with_grad)
-            if state is not None:
-                self._import(state)
-            if opt is not None and self.engine.with_grad:
-                self.engine.adam_m.copy_(opt[0]); self.engine.adam_v.copy_(opt[1]); self.engine.step_count.copy_(opt[2])
-            self.flat = torch.nn.Parameter(self.engine.p32, requires_grad=with_grad)
-            self._pending_state = None
+        if e is None:
+            e = self.engine = self._make_engine(batch, seq_len, with_grad)
+            if self._pending_state is not None:
+                self._import(self._pending_state)
+                self._pending_state = None
+            self.flat = torch.nn.Parameter(e.p32, requires_grad=True)
             self._shadow_dirty = True
-        return self.engine
+            spec = getattr(self, "_loss_spec", None)
+            if spec is not None and spec[0] == "ce":
+                e.set_loss("ce")
+        elif batch > e.B or seq_len != e.L or (with_grad and not e.with_grad):
+            e.resize(max(batch, e.B) if seq_len == e.L else batch, seq_len, with_grad or e.with_grad)
+            e._loss_applied = None
+        return e
 
     def _export(self) -> dict:
         return {self._keymap[k]: self._to_ref(k, v.detach().clone()) for k, v in self.engine.params.items()}
@@ -163,19 +199,26 @@ class SasRecCore(torch.nn.Module):
         self._stage(eng, ids, pad_mask, labels, target_mask, negatives)
         return _EngineLoss.apply(self.flat, self)
 
-    def fused_step(self, ids, pad_mask, labels, target_mask, all_reduce=None, lr: float | None = None,
+    def fused_step(self, ids, pad_mask, labels, target_mask, all_reduce="auto", lr: float | None = None,
                    negatives=None) -> torch.Tensor:
-        """forward + backward + Adam entirely inside the engine (no autograd, no torch optimizer)."""
+        """forward + backward + Adam entirely inside the engine (no autograd, no torch optimizer).  ``all_reduce="auto"``
+        exchanges the gradient over ``torch.distributed`` whenever a process group with more than one rank is initialised
+        (Lightning ``strategy="ddp"``): this path has no autograd backward for DDP's hooks to fire on."""
         B, L = ids.shape
         eng = self.ensure_engine(B, L, with_grad=True)
         if self._shadow_dirty:
             eng.refresh_shadow()
             self._shadow_dirty = False
-        if lr is not None and lr != getattr(self, "_lr_set", None):
-            eng.lr.fill_(lr)
-            self._lr_set = lr
+        self._set_lr(eng, lr)
         self._stage(eng, ids, pad_mask, labels, target_mask, negatives)
-        return eng.train_step(all_reduce)[0]
+        if isinstance(all_reduce, str):
+            all_reduce = dist_grad_all_reduce()
+        return eng.train_step(all_reduce, betas=self.adam_betas)[0]
+
+    def _set_lr(self, eng, lr):
+        if lr is not None and lr != getattr(eng, "_lr_host", None):
+            eng.lr.fill_(lr)
+            eng._lr_host = lr
 
     def mark_params_updated(self):
         """Call after an external optimizer changed ``flat`` (done automatically by the API mirrors)."""

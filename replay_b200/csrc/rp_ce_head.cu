@@ -58,6 +58,16 @@ static constexpr int kBwdThreads = 64 + kBwdEpiWarps * 32;
 #ifndef RP_CE_A_TMEM
 #define RP_CE_A_TMEM 1
 #endif
+// MMA issue order of the backward / fused kernels (profiles/r2_ce_issue_order.md):
+//   0  round-1 order: S tile j+NBUF-1 is issued right behind the second GEMM of tile j-1 and has to wait for it (its TMEM
+//      buffer is the one that GEMM reads G from): the tensor pipe drains once per tile
+//   1  (d <= 128) two S buffers, row tile in TMEM, S tile j+2 issued right BEHIND the second GEMM of tile j without a
+//      barrier in between: tcgen05.mma instructions of one CTA execute in issue order, so the overwrite of the buffer cannot
+//      overtake the reads of G; the issuing thread never waits on work it has just queued
+//   2  three S buffers (row tile in shared memory), prefetch distance 1: every wait is for a GEMM issued two groups earlier
+#ifndef RP_CE_ORDER
+#define RP_CE_ORDER 1
+#endif
 template <int DEG, int EVERY>
 __device__ __forceinline__ float ce_ex2(float x, int q) {
   if (EVERY > 0 && (q % (EVERY > 0 ? EVERY : 1)) == 1) return ex2_poly<DEG>(x);
@@ -291,7 +301,7 @@ __global__ void ce_finalize_kernel(const float2* __restrict__ part, const __nv_b
 // MODE 2: rows = tokens, FUSED forward+backward: G~ = exp(s + b) with reference max 0 (valid while |s| is bounded, see
 //         ce_bound_kernel), per-row sum of G~ and un-normalised dH~ = sum_i G~ E_i over this CTA's column split
 //                                                                                      -> out = partial dH~ fp32, zpart
-template <int KCH, int NSTAGE, int MODE, int NBUF, bool A_TMEM>
+template <int KCH, int NSTAGE, int MODE, int NBUF, bool A_TMEM, bool INORDER>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __nv_bfloat16* __restrict__ a_rows /* the row-side matrix (tmA) as a plain pointer, for A_TMEM */,
@@ -382,7 +392,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       auto issue_mma1 = [&](int j) {
         const uint32_t s = j % NSTAGE, ph = (j / NSTAGE) & 1;
         mbar_wait(&bar_full[s], ph);
-        if (j >= NBUF) mbar_wait(&bar_sfree[j % NBUF], ((j / NBUF) - 1) & 1);
+        if (!INORDER && j >= NBUF) mbar_wait(&bar_sfree[j % NBUF], ((j / NBUF) - 1) & 1);
         tc_fence_after();
         const uint32_t dcol = tmem + (j % NBUF) * kT;
 #pragma unroll
@@ -399,9 +409,13 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
         umma_commit(&bar_sfull[j % NBUF]);
       };
-      for (int j = 0; j < NBUF - 1 && j < n_ct; ++j) issue_mma1(j);
+      // PRE S tiles are in flight ahead of the second GEMM.  INORDER: tile j+NBUF follows the second GEMM of tile j through
+      // the in-order tensor pipe (no barrier); otherwise tile j+PRE is issued before it and waits for the second GEMM of
+      // tile j+PRE-NBUF (RP_CE_ORDER 0: the one issued last -> pipe drain; 2: two groups back)
+      constexpr int PRE = INORDER ? NBUF : ((RP_CE_ORDER == 2 && NBUF >= 3) ? NBUF - 2 : NBUF - 1);
+      for (int j = 0; j < PRE && j < n_ct; ++j) issue_mma1(j);
       for (int j = 0; j < n_ct; ++j) {
-        if (j + NBUF - 1 < n_ct) issue_mma1(j + NBUF - 1);
+        if (!INORDER && j + PRE < n_ct) issue_mma1(j + PRE);
         const uint32_t s = j % NSTAGE;
         mbar_wait(&bar_pfull[j % NBUF], (j / NBUF) & 1);
         tc_fence_after();
@@ -412,7 +426,11 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           umma_ts(tmem_acc, pcol + ((ks * 16) / kW) * kW + ((ks * 16) % kW) / 2, umma_desc_sw128(b0 + ks * 2048, kChunk, 1024),
                   idesc2, (j | ks) != 0);
         umma_commit(&bar_empty[s]);
-        umma_commit(&bar_sfree[j % NBUF]);
+        if (INORDER) {
+          if (j + PRE < n_ct) issue_mma1(j + PRE);
+        } else {
+          umma_commit(&bar_sfree[j % NBUF]);
+        }
       }
       umma_commit(&bar_acc);
     }
@@ -886,10 +904,13 @@ static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const v
                          int capacity, float* zpart, cudaStream_t stream) {
   // d <= 128: the row tile goes to TMEM (2 S buffers + accumulator + operand = 448 columns) and its 32 KB of smem become
   // an extra pipeline stage; d = 256: row tile in smem, 2 S buffers + accumulator = 512 columns
-  constexpr bool A_TMEM = (RP_CE_A_TMEM != 0) && KCH <= 2 && MODE == 1;  // measured: pays for the dE pass only
+  // RP_CE_ORDER 1: both directions keep the row tile in TMEM (two S buffers suffice once the issue order no longer drains the
+  // pipe); otherwise round 1's choice (measured then: the TMEM row tile paid for the dE pass only, because it forces 2 buffers)
+  constexpr bool A_TMEM = (RP_CE_A_TMEM != 0) && KCH <= 2 && (MODE == 1 || RP_CE_ORDER == 1);
   constexpr int NBUF = A_TMEM ? 2 : ((RP_CE_NBUF3 && KCH <= 2) ? 3 : 2);
+  constexpr bool INORDER = (RP_CE_ORDER == 1) && NBUF == 2;
   const int smem = ((A_TMEM ? 0 : 1) + NSTAGE + (A_TMEM ? 1 : 0)) * KCH * kChunk + 1024;
-  auto kern = ce_bwd_kernel<KCH, NSTAGE + (A_TMEM ? 1 : 0), MODE, NBUF, A_TMEM>;
+  auto kern = ce_bwd_kernel<KCH, NSTAGE + (A_TMEM ? 1 : 0), MODE, NBUF, A_TMEM, INORDER>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, kBwdThreads, smem, stream>>>(tmA, tmB, reinterpret_cast<const __nv_bfloat16*>(a_rows), cvec, labels,
                                             reinterpret_cast<const __nv_bfloat16*>(table), loss_inv,
@@ -965,7 +986,12 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, 
     RP_LAUNCH_CHECK();
     skip = ws.flag;
   }
-  const int P2 = pick_splits(hint_tiles, n_item_tiles, kMaxSplitsFwd);
+  int P2 = pick_splits(hint_tiles, n_item_tiles, kMaxSplitsFwd);
+  if (fused) {  // two-pass fallback behind the fused pass: it only runs when the bound failed; launching (and retiring) tens of
+                // thousands of CTAs that exit at once cost ~40 us per step, so keep it at about two waves
+    const int cap = (2 * sm_count() + n_tok_tiles - 1) / n_tok_tiles;
+    if (P2 > cap) P2 = cap;
+  }
   switch (d) {
     case 64: rc = launch_ce_fwd<1, 8>(tmA, tmB, n_valid, n_items, P2, n_tok_tiles, bias, ws.part, skip, stream); break;
     case 128: rc = launch_ce_fwd<2, 8>(tmA, tmB, n_valid, n_items, P2, n_tok_tiles, bias, ws.part, skip, stream); break;

@@ -89,12 +89,7 @@ class SasRecEngine:
         self.cfg = cfg
         self.dev = torch.device(device)
         self.B, self.L = max_batch, seq_len
-        if seq_len > cfg.max_len:
-            raise ValueError(f"sequence length {seq_len} exceeds max_len {cfg.max_len}")
-        if cfg.variant == "legacy" and seq_len != cfg.max_len:
-            raise ValueError("legacy SASRec needs seq_len == max_len (sasrec/model.py:528-529)")
-        if seq_len > 512 or (seq_len > 256 and cfg.d // cfg.n_heads != 64):
-            raise ValueError("attention kernels support seq_len <= 256 (head_dim 128) / <= 512 (head_dim 64)")
+        self._check_geometry(seq_len)
         self.T = max_batch * seq_len
         self.Lp = _ru(seq_len, 64)
         self.with_grad = with_grad
@@ -120,24 +115,64 @@ class SasRecEngine:
         self.params = {k: self.p32[o:o + math.prod(s)].view(s) for k, (o, s) in self.layout.items()}
         self.params16 = {k: self.p16[o:o + math.prod(s)].view(s) for k, (o, s) in self.layout.items()}
         if with_grad:
-            self.g32 = torch.zeros(off, **f32)
-            self.adam_m = torch.zeros(off, **f32)
-            self.adam_v = torch.zeros(off, **f32)
-            self.grads = {k: self.g32[o:o + math.prod(s)].view(s) for k, (o, s) in self.layout.items()}
-            self.lr = torch.full((1,), 1e-3, **f32)
-            self.step_count = torch.zeros(1, device=self.dev, dtype=torch.int32)
+            self._alloc_grad_state()
         self.rng_counter = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self.seed = seed & 0xFFFFFFFFFFFF
         self.training = with_grad
         # fused tcgen05 attention backward: head_dim 64, L <= 256; otherwise saved probabilities + batched GEMMs
         self.fused_attn_bwd = (cfg.d // cfg.n_heads) == 64 and seq_len <= 256
         self.sampled = None       # full-catalog CE unless set_loss() selects a sampled head
+        self._loss_args = None
         self.fused_ffn_eval = True  # eval / predict: one-pass FFN kernel for d <= 128
         self.fused_post_attn_eval = True  # eval / predict: out-projection + LayerNorm + FFN in one kernel for d <= 128
         self.fused_ce = True      # single-pass CE forward + dH (guarded on the device by a bound on |logit|)
         self.n_valid_hint = 0     # host estimate of the number of valid targets per step (load balance of the CE head only)
         self._alloc_workspace()
         self.init_parameters(seed)
+
+    # ------------------------------------------------------------------------------------------------ state that outlives a batch geometry
+    def _alloc_grad_state(self):
+        """Flat gradient, Adam moments, learning rate and step counter: sized by the configuration only, allocated once."""
+        f32 = dict(device=self.dev, dtype=torch.float32)
+        n = self.n_flat
+        self.g32 = torch.zeros(n, **f32)
+        self.adam_m = torch.zeros(n, **f32)
+        self.adam_v = torch.zeros(n, **f32)
+        self.grads = {k: self.g32[o:o + math.prod(s)].view(s) for k, (o, s) in self.layout.items()}
+        self.lr = torch.full((1,), 1e-3, **f32)
+        self.step_count = torch.zeros(1, device=self.dev, dtype=torch.int32)
+
+    def _check_geometry(self, seq_len: int):
+        cfg = self.cfg
+        if seq_len > cfg.max_len:
+            raise ValueError(f"sequence length {seq_len} exceeds max_len {cfg.max_len}")
+        if cfg.variant == "legacy" and seq_len != cfg.max_len:
+            raise ValueError("legacy SASRec needs seq_len == max_len (sasrec/model.py:528-529)")
+        if seq_len > 512 or (seq_len > 256 and cfg.d // cfg.n_heads != 64):
+            raise ValueError("attention kernels support seq_len <= 256 (head_dim 128) / <= 512 (head_dim 64)")
+
+    def resize(self, max_batch: int, seq_len: int, with_grad: bool | None = None):
+        """New batch geometry (a larger validation / predict batch, another sequence length): ONLY the activation workspace is
+        re-allocated.  Parameters, the bf16 shadow, gradients, Adam moments, the learning rate, the step counter and the
+        dropout counter keep their buffers - and their addresses, so an ``nn.Parameter`` / optimizer / CUDA pointer that
+        refers to them stays valid."""
+        self._check_geometry(seq_len)
+        if with_grad and not self.with_grad:
+            self.with_grad = True
+            self._alloc_grad_state()
+        self.B, self.L = max_batch, seq_len
+        self.T = max_batch * seq_len
+        self.Lp = _ru(seq_len, 64)
+        self.fused_attn_bwd = (self.cfg.d // self.cfg.n_heads) == 64 and seq_len <= 256
+        self._realloc_workspace()
+        if self._loss_args is not None and self._loss_args[0] != "ce":  # sampled-head buffers are sized by (B, T)
+            self.sampled = None
+            if self.with_grad:
+                self.set_loss(*self._loss_args[:1], **self._loss_args[1])
+        return self
+
+    def _realloc_workspace(self):
+        self._alloc_workspace()
 
     # ------------------------------------------------------------------------------------------------ parameters
     def init_parameters(self, seed: int = 0):
@@ -342,6 +377,7 @@ class SasRecEngine:
         """``"ce"`` = full-catalog CE (default).  Sampled heads: ``ce_sampled`` / ``bce_sampled`` (new path,
         replay/nn/loss/ce.py:146, bce.py:98) and ``legacy_ce_sampled`` / ``legacy_bce_sampled`` (sasrec/lightning.py:310-376)
         with ``n_neg`` negatives per target, ``neg_shape`` in shared [N] / perseq [B, N] / perpos [B, L, N]."""
+        self._loss_args = (kind, dict(n_neg=n_neg, neg_shape=neg_shape, ignore_index=ignore_index, log_eps=log_eps, clamp=clamp))
         if kind == "ce":
             self.sampled = None
             return
@@ -587,7 +623,7 @@ class SasRecEngine:
         check(self.lib.rp_counter_add(self.rng_counter.data_ptr(), 0x9E3779B97F4A7C15 & 0xFFFFFFFFFFFF, self._stream()),
               "rp_counter_add")
 
-    def train_step(self, all_reduce=None):
+    def train_step(self, all_reduce=None, betas=(0.9, 0.98)):
         """forward + backward + (optional gradient all-reduce callback on the flat fp32 gradient) + Adam."""
         self.tick_rng()
         loss = self.forward_train()
@@ -595,7 +631,7 @@ class SasRecEngine:
         scale = 1.0
         if all_reduce is not None:
             scale = all_reduce(self.g32)
-        self.optimizer_step(grad_scale=scale)
+        self.optimizer_step(grad_scale=scale, beta1=betas[0], beta2=betas[1])
         return loss
 
     # ------------------------------------------------------------------------------------------------ inference

@@ -73,12 +73,8 @@ class Bert4RecEngine(SasRecEngine):
         self.params = {k: self.p32[o:o + math.prod(s)].view(s) for k, (o, s) in self.layout.items()}
         self.params16 = {k: self.p16[o:o + math.prod(s)].view(s) for k, (o, s) in self.layout.items()}
         if with_grad:
-            self.g32 = torch.zeros(off, **f32)
-            self.adam_m = torch.zeros(off, **f32)
-            self.adam_v = torch.zeros(off, **f32)
-            self.grads = {k: self.g32[o:o + math.prod(s)].view(s) for k, (o, s) in self.layout.items()}
-            self.lr = torch.full((1,), 1e-3, **f32)
-            self.step_count = torch.zeros(1, device=self.dev, dtype=torch.int32)
+            self._alloc_grad_state()
+        self.sampled, self._loss_args = None, None
         self.rng_counter = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self.seed = seed & 0xFFFFFFFFFFFF
         self.fused_attn_bwd = (cfg.d // cfg.n_heads) == 64 and seq_len <= 256
@@ -133,6 +129,15 @@ class Bert4RecEngine(SasRecEngine):
         return P
 
     # ------------------------------------------------------------------------------------------------ workspace
+    def _check_geometry(self, seq_len: int):
+        if seq_len != self.cfg.max_len:
+            raise ValueError("BERT4Rec needs seq_len == max_len (bert4rec/model.py:276)")
+        if seq_len > 512 or (seq_len > 256 and self.cfg.d // self.cfg.n_heads != 64):
+            raise ValueError("attention kernels support seq_len <= 256 (head_dim 128) / <= 512 (head_dim 64)")
+
+    def _realloc_workspace(self):
+        self._alloc_bert_workspace()
+
     def _alloc_bert_workspace(self):
         cfg, T, d, dev = self.cfg, self.T, self.cfg.d, self.dev
         bf = dict(device=dev, dtype=torch.bfloat16)

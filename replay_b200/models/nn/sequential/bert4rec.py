@@ -6,7 +6,7 @@ from __future__ import annotations
 import torch
 
 from ....compat import LightningModuleBase
-from ....core import SasRecCore, _EngineLoss
+from ....core import SasRecCore, _EngineLoss, dist_grad_all_reduce
 from ....engine_bert import _BERT_BLOCK, Bert4RecEngine, BertConfig
 from ....schema import item_feature_of
 
@@ -59,18 +59,15 @@ class _BertCore(SasRecCore):
         self.cfg, self.item_feature = cfg, item_feature
         self._device = torch.device(device) if device is not None else torch.device("cuda")
         self._seed, self.engine, self.flat, self._pending_state, self._shadow_dirty = seed, None, None, None, True
+        self.adam_betas = (0.9, 0.98)
         self._keymap = bert_key_map(cfg.n_blocks, cfg.tying, item_feature)
+        self._materialise()
 
-    def ensure_engine(self, batch, seq_len, with_grad=True):
-        e = self.engine
-        if e is None or batch > e.B or (with_grad and not e.with_grad):
-            state = self._export() if e is not None else self._pending_state
-            self.engine = Bert4RecEngine(self.cfg, batch, seq_len, self._device, seed=self._seed, with_grad=with_grad)
-            if state is not None:
-                self._import(state)
-            self.flat = torch.nn.Parameter(self.engine.p32, requires_grad=with_grad)
-            self._pending_state, self._shadow_dirty = None, True
-        return self.engine
+    def _initial_seq_len(self):
+        return self.cfg.max_len
+
+    def _make_engine(self, batch, seq_len, with_grad):
+        return Bert4RecEngine(self.cfg, batch, seq_len, self._device, seed=self._seed, with_grad=with_grad)
 
     def _to_ref(self, k, v):
         return v[: self.cfg.n_items] if k == "head_b" else v
@@ -105,14 +102,15 @@ class _BertCore(SasRecCore):
         eng.set_batch(ids, pad_mask, token_mask, labels)
         return _EngineLoss.apply(self.flat, self)
 
-    def fused_step(self, ids, pad_mask, token_mask, labels, all_reduce=None, lr=None):
+    def fused_step(self, ids, pad_mask, token_mask, labels, all_reduce="auto", lr=None):
         eng = self.ensure_engine(*ids.shape, with_grad=True)
         if self._shadow_dirty:
             eng.refresh_shadow(); self._shadow_dirty = False
-        if lr is not None and lr != getattr(self, "_lr_set", None):
-            eng.lr.fill_(lr); self._lr_set = lr
+        self._set_lr(eng, lr)
         eng.set_batch(ids, pad_mask, token_mask, labels)
-        return eng.train_step(all_reduce)[0]
+        if isinstance(all_reduce, str):
+            all_reduce = dist_grad_all_reduce()
+        return eng.train_step(all_reduce, betas=self.adam_betas)[0]
 
     @torch.no_grad()
     def query_embeddings(self, ids, pad_mask, token_mask):
@@ -198,6 +196,7 @@ class Bert4Rec(LightningModuleBase):
         if fused_optimizer:
             self.automatic_optimization = False
         self._lr = getattr(optimizer_factory, "learning_rate", 1e-3)
+        self._model.core.adam_betas = tuple(getattr(optimizer_factory, "betas", (0.9, 0.98)))
 
     def state_dict(self, *a, prefix="", **k):
         return {prefix + "_model." + key: v for key, v in self._model.state_dict().items()}
@@ -210,7 +209,7 @@ class Bert4Rec(LightningModuleBase):
         ids = batch["inputs"][self._model.item_feature_name]
         args = (ids, batch["pad_mask"], batch["token_mask"], batch["positive_labels"])
         core = self._model.core
-        loss = core.fused_step(*args, lr=self._lr) if self.fused_optimizer else core.loss(*args)
+        loss = core.fused_step(*args, lr=self._fused_lr()) if self.fused_optimizer else core.loss(*args)
         self.log("train_loss", loss, on_step=True, on_epoch=True, prog_bar=True, sync_dist=True)
         return loss
 
@@ -251,6 +250,27 @@ class Bert4Rec(LightningModuleBase):
         ids, pm, tm = self._prepared(batch)
         cands = self._candidates_to_score if candidates_to_score is None else candidates_to_score
         return self._model.core.predict_topk(ids, pm, tm, k, seen_ids, cands)
+
+    def _fused_lr(self) -> float:
+        try:
+            opt = self.optimizers()
+        except Exception:  # noqa: BLE001 - no trainer attached
+            opt = None
+        if isinstance(opt, (list, tuple)):
+            opt = opt[0] if opt else None
+        if opt is not None and getattr(opt, "param_groups", None):
+            return float(opt.param_groups[0]["lr"])
+        return float(self._lr)
+
+    def on_train_epoch_end(self):
+        if self.fused_optimizer and self._lr_scheduler_factory is not None:
+            try:
+                sch = self.lr_schedulers()
+            except Exception:  # noqa: BLE001
+                sch = None
+            for s_ in (sch if isinstance(sch, (list, tuple)) else [sch]):
+                if s_ is not None:
+                    s_.step()
 
     def configure_optimizers(self):
         params = [self._model.core.flat]

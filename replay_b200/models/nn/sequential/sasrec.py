@@ -123,6 +123,7 @@ class SasRec(LightningModuleBase):
         if fused_optimizer:
             self.automatic_optimization = False
         self._lr = getattr(optimizer_factory, "learning_rate", 1e-3)
+        self._model.core.adam_betas = tuple(getattr(optimizer_factory, "betas", (0.9, 0.98)))
 
     def state_dict(self, *a, prefix="", **k):
         return {prefix + "_model." + key: v for key, v in self._model.state_dict().items()}
@@ -144,7 +145,7 @@ class SasRec(LightningModuleBase):
         core = self._model.core
         neg = self._sample_negatives(ids) if self._loss_sample_count is not None else None
         if self.fused_optimizer:
-            loss = core.fused_step(*args, lr=self._lr, negatives=neg)
+            loss = core.fused_step(*args, lr=self._fused_lr(), negatives=neg)  # all_reduce="auto": DDP exchange inside
         else:
             loss = core.loss(*args, negatives=neg)
         self.log("train_loss", loss, on_step=True, on_epoch=True, prog_bar=True, sync_dist=True)
@@ -166,6 +167,28 @@ class SasRec(LightningModuleBase):
         batch = _prepare_prediction_batch(self._schema, self._model.max_len, batch)
         ids = batch["feature_tensor"][self._model.item_feature_name]
         return self._model.core.predict_topk(ids, batch["padding_mask"], k, seen_ids, candidates_to_score)
+
+    def _fused_lr(self) -> float:
+        """learning rate of this step: the (possibly scheduled) optimizer Lightning holds, else the factory's."""
+        try:
+            opt = self.optimizers()
+        except Exception:  # noqa: BLE001 - no trainer attached
+            opt = None
+        if isinstance(opt, (list, tuple)):
+            opt = opt[0] if opt else None
+        if opt is not None and getattr(opt, "param_groups", None):
+            return float(opt.param_groups[0]["lr"])
+        return float(self._lr)
+
+    def on_train_epoch_end(self):
+        if self.fused_optimizer and self._lr_scheduler_factory is not None:  # manual optimisation: step the scheduler here
+            try:
+                sch = self.lr_schedulers()
+            except Exception:  # noqa: BLE001
+                sch = None
+            for s_ in (sch if isinstance(sch, (list, tuple)) else [sch]):
+                if s_ is not None:
+                    s_.step()
 
     def configure_optimizers(self):
         params = [self._model.core.flat]
@@ -246,6 +269,7 @@ class SasRec(LightningModuleBase):
             raise ValueError(f"Expected optimizer_factory of type OptimizerFactory, got {type(optimizer_factory)}")
         self._optimizer_factory = optimizer_factory
         self._lr = getattr(optimizer_factory, "learning_rate", 1e-3)
+        self._model.core.adam_betas = tuple(getattr(optimizer_factory, "betas", (0.9, 0.98)))
 
     @property
     def candidates_to_score(self):

@@ -24,7 +24,10 @@ class TopItemsCallbackBase(CallbackBase):
 
     def on_predict_batch_end(self, trainer, pl_module, outputs, batch, batch_idx, dataloader_idx=0):
         model = getattr(pl_module, "model", None)
-        fusable = hasattr(model, "core") and all(isinstance(p, SeenItemsFilter) for p in self._postprocessors)
+        from ...ops import MAX_FUSED_K
+
+        fusable = (hasattr(model, "core") and self._top_k <= MAX_FUSED_K
+                   and all(isinstance(p, SeenItemsFilter) for p in self._postprocessors))
         if fusable:
             seen = batch[self._postprocessors[0].seen_items_column] if self._postprocessors else None
             ids, scores = model.predict_topk(batch["feature_tensors"], batch["padding_mask"], self._top_k, seen,

@@ -12,7 +12,7 @@ import torch
 from ...compat import CallbackBase
 from .postprocessor import SeenItemsFilter
 
-_ALL = ("recall", "precision", "ndcg", "map", "mrr")
+_ALL = ("recall", "precision", "ndcg", "map", "mrr", "hitrate")
 
 
 class RankingMetrics:
@@ -49,6 +49,8 @@ class RankingMetrics:
                     v = (h * w_ndcg[:k]).sum(1) / idcg[gk]
                 elif m == "map":
                     v = (h * h.cumsum(1) * w_map[:k]).sum(1) / gk
+                elif m == "hitrate":
+                    v = (h.sum(1) > 0).float()
                 else:  # mrr
                     ih = h * torch.arange(k, 0, -1, device=dev)
                     vals, idx = ih.max(dim=1)
@@ -77,7 +79,9 @@ class ComputeMetricsCallback(CallbackBase):
     def on_validation_batch_end(self, trainer, pl_module, outputs, batch, batch_idx, dataloader_idx=0):
         model = getattr(pl_module, "model", None)
         k = self._builder.max_k
-        if hasattr(model, "core") and all(isinstance(p, SeenItemsFilter) for p in self._postprocessors):
+        from ...ops import MAX_FUSED_K
+
+        if hasattr(model, "core") and k <= MAX_FUSED_K and all(isinstance(p, SeenItemsFilter) for p in self._postprocessors):
             seen = batch[self._postprocessors[0].seen_items_column] if self._postprocessors else None
             ids, _ = model.predict_topk(batch["feature_tensors"], batch["padding_mask"], k, seen, pl_module.candidates_to_score)
         else:

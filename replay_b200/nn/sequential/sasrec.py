@@ -14,6 +14,22 @@ from ...engine import EncoderConfig
 from ...schema import item_feature_of
 
 
+class _InferenceOutput(dict):
+    """``InferenceOutput`` with a lazily evaluated ``hidden_states`` entry."""
+
+    def __init__(self, logits, hidden_fn):
+        super().__init__(logits=logits)
+        self._hidden_fn = hidden_fn
+
+    def __getitem__(self, k):
+        if k == "hidden_states" and not super().__contains__(k):
+            super().__setitem__(k, self._hidden_fn())
+        return super().__getitem__(k)
+
+    def __contains__(self, k):
+        return k == "hidden_states" or super().__contains__(k)
+
+
 class SasRec(torch.nn.Module):
     def __init__(self, core: SasRecCore, loss=None):
         super().__init__()
@@ -59,7 +75,7 @@ class SasRec(torch.nn.Module):
 
     def parameters(self, recurse=True):
         if self.core.flat is None:
-            raise RuntimeError("parameters are materialised on the first batch (engine geometry); call warm_up(B, L) first")
+            raise RuntimeError("no CUDA device: the parameters live in the engine's flat device buffer (replay_b200 has no CPU path)")
         return iter([self.core.flat])
 
     def warm_up(self, batch_size: int, seq_len: int, with_grad: bool = True):
@@ -89,9 +105,12 @@ class SasRec(torch.nn.Module):
         return {"loss": loss, "hidden_states": ()}
 
     def forward_inference(self, feature_tensors, padding_mask, candidates_to_score=None):
+        """model.py:292-307: ``logits`` = scores of the LAST position [B, |I|] (or [B, |C|]); ``hidden_states`` = ([B, L, d],).
+        The scores come from the last-position shortcut of the engine; the all-position hidden states (a second, full pass over
+        the body) are only computed if that key is actually read."""
         ids = feature_tensors[self.core.item_feature]
         logits = self.core.logits(ids, padding_mask, candidates_to_score)
-        return {"logits": logits, "hidden_states": (self.core.engine.hq[: ids.shape[0]].float(),)}
+        return _InferenceOutput(logits, lambda: (self.core.hidden_states(ids, padding_mask).float(),))
 
     def forward(self, feature_tensors, padding_mask, candidates_to_score=None, positive_labels=None, negative_labels=None,
                 target_padding_mask=None):

@@ -41,6 +41,9 @@ def seen_prepare(seen_ids: torch.Tensor, item_count: int, inv_map: torch.Tensor 
     return out
 
 
+MAX_FUSED_K = 32  # rp_score_topk keeps per-thread sorted lists of K entries (include/rp_b200.h); larger K: logits + torch.topk
+
+
 def score_topk(hq: torch.Tensor, table: torch.Tensor, k: int, seen_sorted: torch.Tensor | None = None,
                candidates: torch.Tensor | None = None, bias: torch.Tensor | None = None):
     """Fused scores -> seen mask -> top-k.  hq bf16 [B,d], table bf16 [I,d].  Returns (ids int64 [B,k], scores fp32 [B,k])."""

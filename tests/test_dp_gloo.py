@@ -52,6 +52,13 @@ def _worker(rank, world, port, q):
     tr = Trainer(eng, use_graph=False)
     assert tr.world == world
     tr.step(None, None, None, None)
+    # the callback the Lightning mirrors' fused training_step hands to the engine (replay_b200/core.py): sum + 1/world
+    from replay_b200.core import dist_grad_all_reduce
+
+    cb = dist_grad_all_reduce()
+    g = torch.arange(4, dtype=torch.float32) + 10 * rank
+    scale = cb(g)
+    assert scale == 0.5 and g.tolist() == [10.0, 12.0, 14.0, 16.0], (scale, g)
     q.put((rank, eng.seen_scale, eng.seen_grad.tolist()))
     dist.destroy_process_group()
 
@@ -84,3 +91,9 @@ def test_user_shard_is_exact_partition():
             assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
             sizes = [hi - lo for lo, hi in cuts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_grad_all_reduce_callback_is_none_without_a_process_group():
+    from replay_b200.core import dist_grad_all_reduce
+
+    assert dist_grad_all_reduce() is None

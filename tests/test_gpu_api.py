@@ -260,3 +260,69 @@ def test_legacy_vocabulary_growth_like_reference_tests(golden_dir, cuda):
         model.append_item_embeddings(torch.rand(1, 1))
     with pytest.raises(ValueError):
         model.optimizer_factory = object()
+
+
+def test_lightning_module_checkpoint_optimizer_and_lazy_predict(golden_dir, cuda):
+    """ADVICE r1: (1) LightningModule-level state_dict / load_state_dict carry the reference's ``model.``-prefixed keys;
+    (2) parameters exist at construction, so configure_optimizers (and DDP wrapping) work before the first batch;
+    (3) predict_step does not run the body / materialise [B, |I|] logits when the fused callback consumes the batch;
+    (4) top_k beyond the fused kernel's limit falls back to logits + torch.topk instead of failing."""
+    from replay_b200.nn.lightning import LightningModule, OptimizerFactory, SeenItemsFilter, TorchTopItemsCallback
+    from replay_b200.nn.lightning.module import LazyInferenceOutput
+    from replay_b200.nn.sequential import SasRec
+    from replay_b200.schema import TensorFeatureInfo, TensorSchema
+
+    z, sd = _golden(golden_dir, "sasrec_new_small.npz")
+    n_items, d, H, L = int(z["n_items"]), int(z["d"]), int(z["H"]), int(z["L"])
+    schema = TensorSchema(TensorFeatureInfo("item_id", n_items, n_items, d))
+    mk = lambda: SasRec.from_params(schema, embedding_dim=d, num_heads=H, num_blocks=int(z["n_blocks"]),  # noqa: E731
+                                    max_sequence_length=L, dropout=0.0)
+    lm = LightningModule(mk(), optimizer_factory=OptimizerFactory(learning_rate=3e-3, betas=(0.8, 0.95)))
+    # (2)
+    opt = lm.configure_optimizers()
+    assert len(opt.param_groups[0]["params"]) == 1 and opt.param_groups[0]["params"][0] is lm.model.core.flat
+    assert lm.model.core.adam_betas == (0.8, 0.95)
+    # (1) load the reference's Lightning checkpoint layout, save it back
+    ref_ckpt = {"model." + k: v for k, v in sd.items()}
+    res = lm.load_state_dict(ref_ckpt)
+    assert not res.missing_keys and not res.unexpected_keys
+    out = lm.state_dict()
+    assert set(out) == set(ref_ckpt)
+    for k in ref_ckpt:
+        torch.testing.assert_close(out[k].cpu(), ref_ckpt[k], rtol=0, atol=0)
+    lm2 = LightningModule(mk())
+    lm2.load_state_dict(out)
+    torch.testing.assert_close(lm2.model.core.flat.detach(), lm.model.core.flat.detach(), rtol=0, atol=0)
+    with pytest.raises(RuntimeError):
+        lm2.load_state_dict({k: v for k, v in out.items() if "pe.weight" not in k})  # strict: missing key
+    # fused step uses the factory's lr and betas
+    ids, pm = torch.from_numpy(z["ids"]).cuda(), torch.from_numpy(z["pad_mask"]).cuda()
+    lab, tm = torch.from_numpy(z["labels"]).cuda(), torch.from_numpy(z["target_mask"]).cuda()
+    batch = {"query_id": torch.arange(ids.shape[0]).cuda(), "feature_tensors": {"item_id": ids}, "padding_mask": pm,
+             "positive_labels": lab.unsqueeze(-1), "target_padding_mask": tm.unsqueeze(-1), "seen_ids": ids}
+    loss = lm.training_step(batch, 0)
+    assert abs(float(loss) - float(z["train_loss"])) < 5e-3 * float(z["train_loss"])
+    assert float(lm.model.core.engine.lr.item()) == pytest.approx(3e-3)
+    assert lm.logged["learning_rate"] == pytest.approx(3e-3)
+    # (3)
+    cb = TorchTopItemsCallback(top_k=10, query_column="query_id", item_column="item_id",
+                               postprocessors=[SeenItemsFilter(item_count=n_items, seen_items_column="seen_ids")])
+    cb.on_predict_epoch_start(None, lm2)
+    n0 = lm2.model.core.engine.lib.count
+    outputs = lm2.predict_step(batch, 0)
+    assert isinstance(outputs, LazyInferenceOutput) and lm2.model.core.engine.lib.count == n0  # nothing ran yet
+    cb.on_predict_batch_end(None, lm2, outputs, batch, 0)
+    assert not outputs.materialised  # the fused callback never asked for the logits
+    _, items10, scores10 = cb.get_result()
+    logits = outputs["logits"]  # a callback that does want them gets the reference's tensor
+    assert outputs.materialised and logits.shape == (ids.shape[0], n_items)
+    assert outputs["hidden_states"][0].shape == (ids.shape[0], L, d)
+    # (4) K = 50 > 32: logits + SeenItemsFilter.on_prediction + torch.topk; its first 10 columns agree with the fused head
+    cb50 = TorchTopItemsCallback(top_k=50, query_column="query_id", item_column="item_id",
+                                 postprocessors=[SeenItemsFilter(item_count=n_items, seen_items_column="seen_ids")])
+    cb50.on_predict_epoch_start(None, lm2)
+    cb50.on_predict_batch_end(None, lm2, lm2.predict_step(batch, 0), batch, 0)
+    _, items50, scores50 = cb50.get_result()
+    assert items50.shape == (ids.shape[0], 50)
+    torch.testing.assert_close(scores50[:, :10], scores10, rtol=1e-3, atol=1e-3)
+    assert (items50[:, :10] == items10).float().mean() > 0.98

@@ -2,7 +2,7 @@
 import ctypes, glob, os, sys, json
 import torch
 P, ci, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
-T, nv_, I, d = 51200, 26263, 50000, 128
+T, nv_, I, d = (102400, 55574, 50000, 128) if "--b256" not in sys.argv else (51200, 26263, 50000, 128)
 g = torch.Generator(device="cuda").manual_seed(0)
 hc = torch.randn(T, d, device="cuda", generator=g).bfloat16(); hc[nv_:] = 0
 table = (torch.randn(I, d, device="cuda", generator=g) * 0.3).bfloat16()
@@ -29,5 +29,9 @@ for path in sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file
         for _ in range(n): fn()
         b.record(); torch.cuda.synchronize()
         return a.elapsed_time(b) / n
-    res[os.path.basename(path)] = dict(fwd_ms=round(t(fwd), 4), bwd_ms=round(t(bwd), 4), loss=float(loss[0]))
+    r = dict(fwd_ms=round(t(fwd), 4), bwd_ms=round(t(bwd), 4), loss=float(loss[0]))
+    # checksums of both gradients: every variant must agree with the round-1 issue order to accumulation noise
+    r["dh_abs_sum"] = float(d_hc[:nv_].float().abs().sum()); r["de_abs_sum"] = float(d_tab[:I].abs().sum())
+    r["dh_probe"] = float(d_hc[nv_ // 2].float().sum()); r["de_probe"] = float(d_tab[I // 3].sum())
+    res[os.path.basename(path)] = r
 print(json.dumps(res, indent=1))

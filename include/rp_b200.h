@@ -254,6 +254,36 @@ int rp_post_attn_fused(const void* o, const void* q_in, const void* wo, const fl
                        float eps, const void* w1, const float* b1, const void* w2, const float* b2, const uint8_t* rowmask, int T,
                        int d, void* out, void* stream);
 
+/* Training forward of everything after the attention of one SASRec block in one pass over the tokens:
+ *   h = o Wo^T + bo + q_in ; y = LN(h) ; u = dropout1(relu(y W1^T + b1)) ; out = (y + dropout2(u W2^T + b2)) [* rowmask]
+ * writing the activations the backward needs on the way (h, y, u bf16 [T, d]; LayerNorm mean / rstd fp32 [T]): 2 tensors read
+ * and 4 written instead of the 14 [T, d] passes of out-projection GEMM + LayerNorm + two FFN GEMMs.  Dropout element e of a site
+ * uses word (e & 3) of rng4x32(seed + *seed_ptr, (drop_off + e) >> 2), e = row * d + column - the stream of rp_gemm's epilogue
+ * and rp_dropout_bwd, so the un-fused backward applies unchanged.  d in {64,128}; out may not alias o / q_in.
+ *   replaces (train)  replay/nn/sequential/sasrec/transformer.py:99-110 ; replay/nn/ffn.py:43-57 ;
+ *                     replay/models/nn/sequential/sasrec/model.py:435-441,496-506 */
+int rp_post_attn_train(const void* o, const void* q_in, const void* wo, const float* bo, const float* ln_w, const float* ln_b,
+                       float eps, const void* w1, const float* b1, const void* w2, const float* b2, const uint8_t* rowmask, int T,
+                       int d, float drop_p, unsigned long long seed, unsigned long long drop_off1, unsigned long long drop_off2,
+                       const unsigned long long* seed_ptr, void* h_save, void* y_save, void* u_save, float* mean_out,
+                       float* rstd_out, void* out, void* stream);
+
+/* ALL weight and bias gradients of one transformer block in one launch (+ one deterministic reduction launch):
+ *   dW_i[n_out_i, n_in_i] (+)= dY_i[T, n_out_i]^T . X_i[T, n_in_i] ;  db_i[n_out_i] (+)= column sums of dY_i      i < n_pairs <= 8
+ * dY_i / X_i are read in place (MN-major tcgen05 operands, contraction over the tokens); the bias gradient is one extra N = 16
+ * MMA per k-step against a tile of ones.  n_out, n_in multiples of 64; at most 48 output tiles of 128 x 128 in one call.
+ *   replaces  autograd's weight / bias gradients of  replay/nn/sequential/sasrec/transformer.py:36-46,99-110 ;
+ *             replay/nn/ffn.py:43-57 ; replay/models/nn/sequential/sasrec/model.py:407-414,490-506 ; bert4rec/model.py:471-527 */
+typedef struct rp_wgrad_pair {
+  const void* dY; long long dy_ld; int n_out;   /* bf16 [T, n_out], row pitch dy_ld elements */
+  const void* X; long long x_ld; int n_in;      /* bf16 [T, n_in],  row pitch x_ld */
+  float* dW; long long dw_ld;                   /* fp32 [n_out, n_in], row pitch dw_ld (multiple of 4) */
+  float* db;                                    /* fp32 [n_out] or NULL */
+} rp_wgrad_pair;
+size_t rp_wgrad_group_workspace(const rp_wgrad_pair* pairs, int n_pairs);
+int rp_wgrad_group(const rp_wgrad_pair* pairs, int n_pairs, int T, int accumulate, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
 int rp_adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, long long n, const float* lr_dev,
                  int32_t* step_dev, float beta1, float beta2, float eps, float grad_scale, const uint8_t* frozen,
                  int zero_grad, void* stream);

@@ -84,6 +84,10 @@ def lib():
     _sig(L.rp_post_attn_fused, c_int, [P, P, P, P, P, P, c_float, P, P, P, P, P, c_int, c_int, P, P])
     _sig(L.rp_ffn_fused, c_int, [P, P, P, P, P, P, c_int, c_int, P, P])
     _sig(L.rp_build_batch, c_int, [P, P, LL, P, P, c_int, c_int, c_int, c_int, c_float, P, U64, U64, P, P, P, P, P, P, P])
+    _sig(L.rp_post_attn_train, c_int, [P, P, P, P, P, P, c_float, P, P, P, P, P, c_int, c_int, c_float, U64, U64, U64, P,
+                                       P, P, P, P, P, P, P])
+    _sig(L.rp_wgrad_group_workspace, c_size_t, [ctypes.POINTER(WgradPair), c_int])
+    _sig(L.rp_wgrad_group, c_int, [ctypes.POINTER(WgradPair), c_int, c_int, c_int, P, c_size_t, P])
     for name, restype, argtypes in _EXTRA_SIGS:
         _sig(getattr(L, name), restype, argtypes)
     _lib = L
@@ -110,6 +114,17 @@ class GemmDesc(ctypes.Structure):
         ("c_split_stride", ctypes.c_longlong),
         ("row_exp2_offset", c_void_p), ("m_limit_dev", c_void_p), ("m_limit_base", c_int),
         ("k_limit_dev", c_void_p), ("k_limit_base", c_int),
+    ]
+
+
+class WgradPair(ctypes.Structure):
+    """Mirror of ``struct rp_wgrad_pair`` (include/rp_b200.h)."""
+
+    _fields_ = [
+        ("dY", c_void_p), ("dy_ld", ctypes.c_longlong), ("n_out", c_int),
+        ("X", c_void_p), ("x_ld", ctypes.c_longlong), ("n_in", c_int),
+        ("dW", c_void_p), ("dw_ld", ctypes.c_longlong),
+        ("db", c_void_p),
     ]
 
 
@@ -166,4 +181,4 @@ class AttnBwdDesc(ctypes.Structure):
 
 _EXTRA_SIGS: list = []
 
-__all__ = ["GemmDesc", "AttnDesc", "AttnBwdDesc", "lib", "check", "RpError", "LIB_PATH", "c_float", "c_int", "c_int32", "c_int64", "c_size_t", "c_void_p"]
+__all__ = ["GemmDesc", "AttnDesc", "AttnBwdDesc", "WgradPair", "lib", "check", "RpError", "LIB_PATH", "c_float", "c_int", "c_int32", "c_int64", "c_size_t", "c_void_p"]

@@ -7,6 +7,7 @@
 // first accumulator and consumed from there as the A operand of the second MMA) and the residual is read from the y tile that
 // is already in shared memory: y is read once, the result written once.  d in {64, 128}.
 #include "rp_host.h"
+#include "rp_philox.cuh"
 #include "rp_sm100.cuh"
 
 namespace rp {
@@ -227,9 +228,29 @@ struct PostAttnParams {
   __nv_bfloat16* out;
   float eps;
   int T;
+  // TRAIN: activations saved for the backward (bf16 [T, d]; u is stored AFTER its dropout, as the un-fused path does) and
+  // the two dropouts of the FFN (replay/nn/ffn.py:49-55), regenerated in the backward from (seed, site offset, element index)
+  __nv_bfloat16* h_save;
+  __nv_bfloat16* y_save;
+  __nv_bfloat16* u_save;
+  float* mean_out;
+  float* rstd_out;
+  float drop_p;
+  unsigned long long seed, off1, off2;
+  const unsigned long long* seed_ptr;
 };
 
-template <int KCH, int NA>
+// keep/scale 4 consecutive elements starting at element index e (e % 4 == 0)
+__device__ __forceinline__ void drop4(float& a, float& b, float& c, float& d, unsigned long long seed, unsigned long long e,
+                                      uint32_t thr, float ks) {
+  const uint4 r = rng4x32(seed, e >> 2);
+  a = r.x >= thr ? a * ks : 0.f;
+  b = r.y >= thr ? b * ks : 0.f;
+  c = r.z >= thr ? c * ks : 0.f;
+  d = r.w >= thr ? d * ks : 0.f;
+}
+
+template <int KCH, int NA, bool TRAIN>
 __global__ void __launch_bounds__(kFfnThreads, 1)
 post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWo,
                        const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
@@ -365,6 +386,9 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const bool has_half = half * 64 < D;
     const int c0 = half * 64;
+    const float keep_scale = (TRAIN && p.drop_p > 0.f) ? 1.f / (1.f - p.drop_p) : 1.f;
+    const uint32_t drop_thr = (TRAIN && p.drop_p > 0.f) ? (uint32_t)(p.drop_p * 4294967296.0) : 0u;
+    const unsigned long long seed_eff = TRAIN ? p.seed + ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull) : 0ull;
     for (int pi = 0; pi < n_pairs; ++pi) {
       const uint32_t pph = pi & 1;
 #pragma unroll 1
@@ -397,13 +421,24 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
                 for (int e = 0; e < 4; ++e) {
                   const int col = c8 * 8 + 2 * e;
                   const float2 qf = __bfloat1622float2(q2[e]);
-                  const float v0 = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + s_vec[0][c0 + col] + qf.x;
-                  const float v1 = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + s_vec[0][c0 + col + 1] + qf.y;
+                  float v0 = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + s_vec[0][c0 + col] + qf.x;
+                  float v1 = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + s_vec[0][c0 + col + 1] + qf.y;
+                  if (TRAIN) {  // the statistics describe exactly the bf16 h the backward will read
+                    v0 = __bfloat162float(__float2bfloat16(v0));
+                    v1 = __bfloat162float(__float2bfloat16(v1));
+                  }
                   hv[col] = v0;
                   hv[col + 1] = v1;
                   sum += v0 + v1;
                   sq = fmaf(v0, v0, fmaf(v1, v1, sq));
                 }
+              }
+              if (TRAIN && row_ok) {
+                uint4* hs = reinterpret_cast<uint4*>(p.h_save + (size_t)m * D + c0);
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8)
+                  hs[c8] = make_uint4(pack_bf16(hv[c8 * 8], hv[c8 * 8 + 1]), pack_bf16(hv[c8 * 8 + 2], hv[c8 * 8 + 3]),
+                                      pack_bf16(hv[c8 * 8 + 4], hv[c8 * 8 + 5]), pack_bf16(hv[c8 * 8 + 6], hv[c8 * 8 + 7]));
               }
             }
             s_stat[half][row] = make_float2(sum, sq);
@@ -423,6 +458,15 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
               }
               tmem_st16(R0 + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
               tmem_st16(R0 + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+              if (TRAIN && row_ok) {
+                uint4* ys = reinterpret_cast<uint4*>(p.y_save + (size_t)m * D + c0);
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) ys[c8] = make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
+                if (half == 0) {
+                  p.mean_out[m] = mean;
+                  p.rstd_out[m] = rstd;
+                }
+              }
               tmem_st_wait();
             }
             tc_fence_before();
@@ -439,12 +483,34 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
               tmem_ld32(R0 + c0, yk);
               tmem_ld_wait();
               uint32_t pk[32];
+              if (TRAIN && p.drop_p > 0.f) {
+                const unsigned long long e0 = p.off1 + (unsigned long long)m * D + c0;
 #pragma unroll
-              for (int q = 0; q < 32; q += 2) {
-                pk[q >> 1] = pack_bf16(fmaxf(__uint_as_float(r0[q]) + s_vec[3][c0 + q], 0.f),
-                                       fmaxf(__uint_as_float(r0[q + 1]) + s_vec[3][c0 + q + 1], 0.f));
-                pk[16 + (q >> 1)] = pack_bf16(fmaxf(__uint_as_float(r1[q]) + s_vec[3][c0 + 32 + q], 0.f),
-                                              fmaxf(__uint_as_float(r1[q + 1]) + s_vec[3][c0 + 32 + q + 1], 0.f));
+                for (int q = 0; q < 32; q += 4) {
+                  float a0 = fmaxf(__uint_as_float(r0[q]) + s_vec[3][c0 + q], 0.f), a1 = fmaxf(__uint_as_float(r0[q + 1]) + s_vec[3][c0 + q + 1], 0.f);
+                  float a2 = fmaxf(__uint_as_float(r0[q + 2]) + s_vec[3][c0 + q + 2], 0.f), a3 = fmaxf(__uint_as_float(r0[q + 3]) + s_vec[3][c0 + q + 3], 0.f);
+                  float b0 = fmaxf(__uint_as_float(r1[q]) + s_vec[3][c0 + 32 + q], 0.f), b1 = fmaxf(__uint_as_float(r1[q + 1]) + s_vec[3][c0 + 32 + q + 1], 0.f);
+                  float b2 = fmaxf(__uint_as_float(r1[q + 2]) + s_vec[3][c0 + 32 + q + 2], 0.f), b3 = fmaxf(__uint_as_float(r1[q + 3]) + s_vec[3][c0 + 32 + q + 3], 0.f);
+                  drop4(a0, a1, a2, a3, seed_eff, e0 + q, drop_thr, keep_scale);
+                  drop4(b0, b1, b2, b3, seed_eff, e0 + 32 + q, drop_thr, keep_scale);
+                  pk[q >> 1] = pack_bf16(a0, a1);
+                  pk[(q >> 1) + 1] = pack_bf16(a2, a3);
+                  pk[16 + (q >> 1)] = pack_bf16(b0, b1);
+                  pk[16 + (q >> 1) + 1] = pack_bf16(b2, b3);
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 32; q += 2) {
+                  pk[q >> 1] = pack_bf16(fmaxf(__uint_as_float(r0[q]) + s_vec[3][c0 + q], 0.f),
+                                         fmaxf(__uint_as_float(r0[q + 1]) + s_vec[3][c0 + q + 1], 0.f));
+                  pk[16 + (q >> 1)] = pack_bf16(fmaxf(__uint_as_float(r1[q]) + s_vec[3][c0 + 32 + q], 0.f),
+                                                fmaxf(__uint_as_float(r1[q + 1]) + s_vec[3][c0 + 32 + q + 1], 0.f));
+                }
+              }
+              if (TRAIN && row_ok) {
+                uint4* us = reinterpret_cast<uint4*>(p.u_save + (size_t)m * D + c0);
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) us[c8] = make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
               }
               tmem_st16(R1 + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
               tmem_st16(R1 + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
@@ -479,9 +545,15 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
                   for (int e = 0; e < 4; ++e) {
                     const int col = c8 * 8 + 2 * e;
                     const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yk[col >> 1]));
-                    const float v0 = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + s_vec[4][c0 + col] + yf.x;
-                    const float v1 = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + s_vec[4][c0 + col + 1] + yf.y;
-                    w32[e] = pack_bf16(v0 * keep, v1 * keep);
+                    float f0 = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + s_vec[4][c0 + col];
+                    float f1 = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + s_vec[4][c0 + col + 1];
+                    if (TRAIN && p.drop_p > 0.f) {  // element pair (col, col+1) of the 4-group starting at col & ~3
+                      const uint4 rr = rng4x32(seed_eff, (p.off2 + (unsigned long long)m * D + c0 + col) >> 2);
+                      const uint32_t w0 = (col & 2) ? rr.z : rr.x, w1 = (col & 2) ? rr.w : rr.y;
+                      f0 = w0 >= drop_thr ? f0 * keep_scale : 0.f;
+                      f1 = w1 >= drop_thr ? f1 * keep_scale : 0.f;
+                    }
+                    w32[e] = pack_bf16((f0 + yf.x) * keep, (f1 + yf.y) * keep);
                   }
                   *reinterpret_cast<uint4*>(o + c8 * 8) = w;
                 }
@@ -501,13 +573,13 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-template <int KCH>
+template <int KCH, bool TRAIN>
 static int launch_post_attn(const CUtensorMap& tmO, const CUtensorMap& tmWo, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
                             const PostAttnParams& p, cudaStream_t st) {
   constexpr int D = KCH * 64;
   constexpr int NA = KCH == 1 ? 4 : 2;
   const int smem = 3 * KCH * D * 128 + NA * KCH * 128 * 128 + 1024;
-  auto kern = post_attn_fused_kernel<KCH, NA>;
+  auto kern = post_attn_fused_kernel<KCH, NA, TRAIN>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int n_tiles = (p.T + 127) / 128;
   const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
@@ -574,5 +646,45 @@ RP_API int rp_post_attn_fused(const void* o, const void* q_in, const void* wo, c
   p.bo = bo; p.ln_w = ln_w; p.ln_b = ln_b; p.b1 = b1; p.b2 = b2;
   p.q_in = reinterpret_cast<const __nv_bfloat16*>(q_in); p.rowmask = rowmask;
   p.out = reinterpret_cast<__nv_bfloat16*>(out); p.eps = eps; p.T = T;
-  return d == 64 ? launch_post_attn<1>(tmO, tmWo, tmW1, tmW2, p, stream) : launch_post_attn<2>(tmO, tmWo, tmW1, tmW2, p, stream);
+  p.h_save = p.y_save = p.u_save = nullptr; p.mean_out = p.rstd_out = nullptr;
+  p.drop_p = 0.f; p.seed = p.off1 = p.off2 = 0ull; p.seed_ptr = nullptr;
+  return d == 64 ? launch_post_attn<1, false>(tmO, tmWo, tmW1, tmW2, p, stream)
+                 : launch_post_attn<2, false>(tmO, tmWo, tmW1, tmW2, p, stream);
+}
+
+// Training forward of everything after the attention of one SASRec block, one pass over the tokens:
+//   h = O Wo^T + bo + q_in ; y = LayerNorm(h) ; u = dropout1(relu(y W1^T + b1)) ; out = (y + dropout2(u W2^T + b2)) [* rowmask]
+// and the activations the backward needs are written on the way: h, y, u (bf16 [T, d]) and the LayerNorm statistics
+// (fp32 [T]) - 2 tensors read, 4 written, against 14 [T, d] passes of the four separate launches
+// (out-projection GEMM, LayerNorm, two FFN GEMMs).  Dropout element e of site s uses word (e & 3) of
+// rng4x32(seed + *seed_ptr, (off_s + e) >> 2), e = row * d + column: the same stream rp_gemm's epilogue and rp_dropout_bwd use.
+//   replaces (train)  replay/nn/sequential/sasrec/transformer.py:99-110 ; replay/nn/ffn.py:43-57 ;
+//                     replay/models/nn/sequential/sasrec/model.py:435-441,496-506
+RP_API int rp_post_attn_train(const void* o, const void* q_in, const void* wo, const float* bo, const float* ln_w,
+                              const float* ln_b, float eps, const void* w1, const float* b1, const void* w2, const float* b2,
+                              const uint8_t* rowmask, int T, int d, float drop_p, unsigned long long seed,
+                              unsigned long long drop_off1, unsigned long long drop_off2, const unsigned long long* seed_ptr,
+                              void* h_save, void* y_save, void* u_save, float* mean_out, float* rstd_out, void* out,
+                              void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!o || !q_in || !wo || !bo || !ln_w || !ln_b || !w1 || !b1 || !w2 || !b2 || !out || T <= 0) return RP_EINVAL;
+  if (!h_save || !y_save || !u_save || !mean_out || !rstd_out) return RP_EINVAL;
+  if (d != 64 && d != 128) return RP_ESHAPE;
+  if (drop_p < 0.f || drop_p >= 1.f || (drop_off1 & 3) || (drop_off2 & 3)) return RP_EINVAL;
+  if (out == o || out == q_in) return RP_EINVAL;
+  CUtensorMap tmO, tmWo, tmW1, tmW2;
+  int rc;
+  if ((rc = make_tmap_bf16(&tmO, o, T, d, d, 128)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmWo, wo, d, d, d, d)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmW1, w1, d, d, d, d)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmW2, w2, d, d, d, d)) != RP_OK) return rc;
+  PostAttnParams p;
+  p.bo = bo; p.ln_w = ln_w; p.ln_b = ln_b; p.b1 = b1; p.b2 = b2;
+  p.q_in = reinterpret_cast<const __nv_bfloat16*>(q_in); p.rowmask = rowmask;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out); p.eps = eps; p.T = T;
+  p.h_save = reinterpret_cast<__nv_bfloat16*>(h_save); p.y_save = reinterpret_cast<__nv_bfloat16*>(y_save);
+  p.u_save = reinterpret_cast<__nv_bfloat16*>(u_save); p.mean_out = mean_out; p.rstd_out = rstd_out;
+  p.drop_p = drop_p; p.seed = seed; p.off1 = drop_off1; p.off2 = drop_off2; p.seed_ptr = seed_ptr;
+  return d == 64 ? launch_post_attn<1, true>(tmO, tmWo, tmW1, tmW2, p, stream)
+                 : launch_post_attn<2, true>(tmO, tmWo, tmW1, tmW2, p, stream);
 }

@@ -18,7 +18,7 @@ from dataclasses import dataclass
 
 import torch
 
-from ._lib import SampledDesc, AttnBwdDesc, AttnDesc, GemmDesc, check, lib
+from ._lib import SampledDesc, AttnBwdDesc, AttnDesc, GemmDesc, WgradPair, check, lib
 
 
 @dataclass
@@ -63,7 +63,8 @@ class _CountingLib:
     KERNELS = {"rp_gemm": 1, "rp_attn_fwd": 1, "rp_attn_bwd": 1, "rp_attn_last": 1, "rp_attn_softmax_bwd": 1, "rp_prepare_batch": 2, "rp_embed_fwd": 1,
                "rp_embed_bwd": 2, "rp_layernorm_fwd": 1, "rp_layernorm_bwd": 1, "rp_dropout_bwd": 1, "rp_colsum": 1, "rp_colsum_multi": 1,
                "rp_adam_step": 2, "rp_cast_bf16": 1, "rp_counter_add": 1, "rp_reduce_splits": 1, "rp_ce_head_fwd": 2, "rp_ce_head_bwd": 3,
-               "rp_score_topk": 2, "rp_seen_prepare": 1, "rp_sampled_head_fwd": 4, "rp_sampled_head_bwd": 4, "rp_ffn_fused": 1, "rp_post_attn_fused": 1}
+               "rp_score_topk": 2, "rp_seen_prepare": 1, "rp_sampled_head_fwd": 4, "rp_sampled_head_bwd": 4, "rp_ffn_fused": 1, "rp_post_attn_fused": 1,
+               "rp_post_attn_train": 1, "rp_wgrad_group": 2}
 
     def __init__(self, L):
         self._L = L
@@ -125,6 +126,11 @@ class SasRecEngine:
         self._loss_args = None
         self.fused_ffn_eval = True  # eval / predict: one-pass FFN kernel for d <= 128
         self.fused_post_attn_eval = True  # eval / predict: out-projection + LayerNorm + FFN in one kernel for d <= 128
+        # training: out-projection + LayerNorm + FFN (+ dropouts, saved activations) in one pass for d <= 128; all weight / bias
+        # gradients of a block in one grouped launch (RP_FUSED_BODY=0 restores round 1's launch-per-GEMM body for A/B runs)
+        fused_body = os.environ.get("RP_FUSED_BODY", "1") != "0"
+        self.fused_post_attn_train = fused_body
+        self.fused_wgrad = fused_body
         self.fused_ce = True      # single-pass CE forward + dH (guarded on the device by a bound on |logit|)
         self.n_valid_hint = 0     # host estimate of the number of valid targets per step (load balance of the CE head only)
         self._alloc_workspace()
@@ -269,6 +275,7 @@ class SasRecEngine:
             if not self.fused_attn_bwd:
                 self.s["dpd"] = torch.zeros(BH, self.Lp, self.Lp, **bf)
             self.wg_ws = torch.zeros(148 * 4 * d * d, **f32)  # split-K partials of the weight-gradient GEMMs
+            self._wgrad_ws = None  # workspace of rp_wgrad_group, sized on first use
 
     def _stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
@@ -322,6 +329,25 @@ class SasRecEngine:
         self._gemm(dY, X, self.wg_ws, n_out, n_in, self.T, a_mn=True, b_mn=True, out_mode=3, split_k=split,
                    c_geom=(n_in, 0, 0, 0), c_split_stride=n)
         check(self.lib.rp_reduce_splits(self.wg_ws.data_ptr(), split, n, n, dW.data_ptr(), 1, self._stream()), "rp_reduce_splits")
+
+    def _wgrad_group(self, pairs):
+        """[(dY bf16 [T, n_out], X bf16 [T, n_in], dW fp32 [n_out, n_in], db fp32 [n_out] | None), ...]: every weight and bias
+        gradient of a block in one tcgen05 launch + one deterministic reduction launch (csrc/rp_wgrad.cu).  Gradients are
+        accumulated (+=) like the un-fused path does."""
+        n = len(pairs)
+        arr = (WgradPair * n)()
+        for k, (dY, X, dW, db) in enumerate(pairs):
+            arr[k].dY, arr[k].dy_ld, arr[k].n_out = dY.data_ptr(), dY.stride(0), dW.shape[0]
+            arr[k].X, arr[k].x_ld, arr[k].n_in = X.data_ptr(), X.stride(0), dW.shape[1]
+            arr[k].dW, arr[k].dw_ld = dW.data_ptr(), dW.stride(0)
+            arr[k].db = None if db is None else db.data_ptr()
+        need = self.lib.rp_wgrad_group_workspace(arr, n)
+        if need == 0:
+            raise ValueError("rp_wgrad_group: unsupported gradient shapes")
+        if self._wgrad_ws is None or self._wgrad_ws.numel() < need:
+            self._wgrad_ws = torch.zeros(need, device=self.dev, dtype=torch.uint8)
+        check(self.lib.rp_wgrad_group(arr, n, self.T, 1, self._wgrad_ws.data_ptr(), self._wgrad_ws.numel(), self._stream()),
+              "rp_wgrad_group")
 
     def _colsum(self, dY, db):
         check(self.lib.rp_colsum(dY.data_ptr(), dY.shape[0], dY.shape[1], dY.stride(0), db.data_ptr(), self._stream()),
@@ -481,6 +507,17 @@ class SasRecEngine:
                                                   pad.data_ptr() if legacy else None, T, d, self.x[i + 1].data_ptr(),
                                                   self._stream()), "rp_post_attn_fused")
                 continue
+            if training and d <= 128 and self.fused_post_attn_train:
+                # training: the same chain in one pass, saving h / y / u and the LayerNorm statistics for the backward
+                check(self.lib.rp_post_attn_train(a["O"].data_ptr(), a["q_in"].data_ptr(), w("out_w").data_ptr(),
+                                                  f("out_b").data_ptr(), f("ln2_w").data_ptr(), f("ln2_b").data_ptr(), 1e-8,
+                                                  w("w1").data_ptr(), f("b1").data_ptr(), w("w2").data_ptr(), f("b2").data_ptr(),
+                                                  pad.data_ptr() if legacy else None, T, d, drop, self.seed,
+                                                  self._site(i, 1) << 40, self._site(i, 2) << 40, self.rng_counter.data_ptr(),
+                                                  a["h"].data_ptr(), a["y"].data_ptr(), a["u"].data_ptr(),
+                                                  a["mean2"].data_ptr(), a["rstd2"].data_ptr(), self.x[i + 1].data_ptr(),
+                                                  self._stream()), "rp_post_attn_train")
+                continue
             self._gemm(a["O"], w("out_w"), a["h"], T, d, d, bias=f("out_b"), residual=a["q_in"])
             self._ln_fwd(a["h"], f("ln2_w"), f("ln2_b"), 1e-8, a["y"], a["mean2"], a["rstd2"], T)
             if not training and d <= 128 and self.fused_ffn_eval:
@@ -550,16 +587,23 @@ class SasRecEngine:
             else:
                 d_t = dz
             # ---- FFN backward
-            self._wgrad(d_t, a["u"], g("w2"), d, d)
+            fw = self.fused_wgrad
+            wpairs = [(d_t, a["u"], g("w2"), g("b2"))]  # (dY, X, dW, db): weight + bias gradients, one grouped launch per block
+            if not fw:
+                self._wgrad(d_t, a["u"], g("w2"), d, d)
             bias_grads = [(d_t, g("b2"))]  # column sums of this block, one launch at the end of its backward
             self._gemm(d_t, w("w2"), s["du"], T, d, d, b_mn=True, gate=a["u"], gate_scale=ks)
-            self._wgrad(s["du"], a["y"], g("w1"), d, d)
+            wpairs.append((s["du"], a["y"], g("w1"), g("b1")))
+            if not fw:
+                self._wgrad(s["du"], a["y"], g("w1"), d, d)
             bias_grads.append((s["du"], g("b1")))
             self._gemm(s["du"], w("w1"), s["dy"], T, d, d, b_mn=True, residual=dz)
             self._ln_bwd(s["dy"], a["h"], f("ln2_w"), a["mean2"], a["rstd2"], s["dh"], g("ln2_w"), g("ln2_b"), T)
             # ---- out projection
             self._gemm(s["dh"], w("out_w"), s["d_o"], T, d, d, b_mn=True)
-            self._wgrad(s["dh"], a["O"], g("out_w"), d, d)
+            wpairs.append((s["dh"], a["O"], g("out_w"), g("out_b")))
+            if not fw:
+                self._wgrad(s["dh"], a["O"], g("out_w"), d, d)
             bias_grads.append((s["dh"], g("out_b")))
             # ---- attention backward
             KV, Q = a["KV"], a["Q"]
@@ -599,13 +643,19 @@ class SasRecEngine:
             # ---- projections
             in_w = w("in_w")
             self._gemm(s["dQ"], in_w[:d], s["dq_in"], T, d, d, b_mn=True, residual=s["dh"])
-            self._wgrad(s["dQ"], a["q_in"], g("in_w")[:d], d, d)
+            wpairs.append((s["dQ"], a["q_in"], g("in_w")[:d], g("in_b")[:d]))
+            if not fw:
+                self._wgrad(s["dQ"], a["q_in"], g("in_w")[:d], d, d)
             bias_grads.append((s["dQ"], g("in_b")[:d]))
             self._ln_bwd(s["dq_in"], x, f("ln1_w"), a["mean1"], a["rstd1"], s["tmp"], g("ln1_w"), g("ln1_b"), T)
             self._gemm(s["dKV"], in_w[d:], other, T, d, 2 * d, b_mn=True, residual=s["tmp"])
-            self._wgrad(s["dKV"], x, g("in_w")[d:], 2 * d, d)
-            bias_grads.append((s["dKV"], g("in_b")[d:]))
-            self._colsum_multi(bias_grads)
+            wpairs.append((s["dKV"], x, g("in_w")[d:], g("in_b")[d:]))
+            if fw:
+                self._wgrad_group(wpairs)
+            else:
+                self._wgrad(s["dKV"], x, g("in_w")[d:], 2 * d, d)
+                bias_grads.append((s["dKV"], g("in_b")[d:]))
+                self._colsum_multi(bias_grads)
             dx, other = other, dx
         pos0 = 0 if legacy else cfg.max_len - L
         check(self.lib.rp_embed_bwd(dx.data_ptr(), self.ids32.data_ptr(), self.in_pad.data_ptr(), self.B, L, d, cfg.pad_id,

@@ -32,11 +32,13 @@ class LazyInferenceOutput(dict):
 
     def _fill(self):
         if self._compute is not None:
-            out, self._compute = self._compute(), None
-            super().update(out)
+            self._inner, self._compute = self._compute(), None
+            super().update(self._inner)
 
     def __getitem__(self, k):
         self._fill()
+        if not super().__contains__(k):  # the model's own output may compute entries lazily as well (hidden_states)
+            super().__setitem__(k, self._inner[k])
         return super().__getitem__(k)
 
     def __contains__(self, k):

@@ -39,7 +39,7 @@ def _worker(rank, world, port, backend, q):
             mod.training_step({"feature_tensors": {"item_id": ids}, "padding_mask": pm, "positive_labels": lab.unsqueeze(-1),
                                "target_padding_mask": tm.unsqueeze(-1)}, step)
         torch.cuda.synchronize()
-        out["new"] = model.core.flat.detach().cpu()
+        out["new"] = model.core.flat.detach().cpu().numpy()
         out["new_moved"] = float((model.core.flat.detach() - p_init).abs().max())
         # same data WITHOUT the exchange (explicit all_reduce=None): replicas must then differ, i.e. the test can fail
         model2 = SasRec.from_params(schema, embedding_dim=64, num_heads=1, num_blocks=1, max_sequence_length=L, dropout=0.0,
@@ -48,7 +48,7 @@ def _worker(rank, world, port, backend, q):
             ids, pm, lab, tm = [t.to(dev) for t in make_sequences(8, n_items, L, seed=1000 * rank + step)]
             model2.core.fused_step(ids, pm, lab, tm, all_reduce=None, lr=1e-3)
         torch.cuda.synchronize()
-        out["local_only"] = model2.core.flat.detach().cpu()
+        out["local_only"] = model2.core.flat.detach().cpu().numpy()
         # ---- legacy Lightning mirror
         leg = LegacySasRec(schema, block_count=1, head_count=1, hidden_size=64, max_seq_len=L, dropout_rate=0.0, device=dev)
         for step in range(3):
@@ -56,8 +56,8 @@ def _worker(rank, world, port, backend, q):
             leg.training_step({"feature_tensor": {"item_id": ids}, "padding_mask": pm, "positive_labels": lab,
                                "target_padding_mask": tm}, step)
         torch.cuda.synchronize()
-        out["legacy"] = leg._model.core.flat.detach().cpu()
-        q.put((rank, out))
+        out["legacy"] = leg._model.core.flat.detach().cpu().numpy()
+        q.put((rank, out))  # numpy arrays: pickled by value (torch tensors would travel as shared-memory handles that die with the worker)
     finally:
         dist.destroy_process_group()
 
@@ -82,8 +82,10 @@ def test_lightning_training_step_two_ranks_keeps_replicas_identical():
         p.join(timeout=120)
         assert p.exitcode == 0
     a, b = res[0], res[1]
+    import numpy as np
+
     assert a["new_moved"] > 0
-    assert torch.equal(a["new"], b["new"]), "new-path LightningModule: replicas diverged (no gradient exchange?)"
-    assert torch.equal(a["legacy"], b["legacy"]), "legacy SasRec module: replicas diverged"
-    assert not torch.equal(a["local_only"], b["local_only"])  # different data per rank really gives different local updates
-    assert not torch.equal(a["new"], a["local_only"])
+    assert np.array_equal(a["new"], b["new"]), "new-path LightningModule: replicas diverged (no gradient exchange?)"
+    assert np.array_equal(a["legacy"], b["legacy"]), "legacy SasRec module: replicas diverged"
+    assert not np.array_equal(a["local_only"], b["local_only"])  # different data per rank really gives different local updates
+    assert not np.array_equal(a["new"], a["local_only"])

@@ -247,3 +247,49 @@ def test_config5_shape_train_step_matches_oracle(cuda):
     hq = eng.forward_last_hidden().float().cpu()
     ref_e = osr.sasrec_body(P, ids, pm, H, "new", mode="eval")[:, -1]
     assert (hq - ref_e).abs().max() < 8e-2
+
+
+@pytest.mark.parametrize("variant,drop", [("new", 0.0), ("new", 0.2), ("legacy", 0.2)])
+def test_fused_training_body_equals_unfused(cuda, variant, drop, monkeypatch):
+    """The fused training kernels (rp_post_attn_train: out-projection + LayerNorm + FFN + dropouts in one pass; rp_wgrad_group:
+    all weight / bias gradients of a block in one launch) against round 1's launch-per-GEMM body on the same weights, batch and
+    dropout stream: saved activations, loss and every gradient agree to bf16 rounding."""
+    from replay_b200.engine import EncoderConfig, SasRecEngine
+    from replay_b200.synthetic import make_sequences
+
+    B, L, d, H, I = 24, 64, 128, 2, 3000
+    cfg = EncoderConfig(n_items=I, d=d, n_heads=H, n_blocks=2, max_len=L, dropout=drop, variant=variant)
+    ids, pm, lab, tm = [t.cuda() for t in make_sequences(B, I, L, seed=5)]
+    engs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("RP_FUSED_BODY", flag)
+        e = SasRecEngine(cfg, B, L, cuda, seed=7)
+        assert e.fused_wgrad == (flag == "1")
+        e.set_batch(ids, pm, lab, tm)
+        e.tick_rng()
+        loss = e.forward_train()
+        e.g32.zero_()
+        e.backward()
+        torch.cuda.synchronize()
+        engs.append((e, float(loss[0])))
+    (e0, l0), (e1, l1) = engs
+    assert abs(l0 - l1) < 2e-3 * abs(l0), (l0, l1)
+    for i in range(2):
+        for k in ("h", "y", "u"):
+            a, b = e0.act[i][k].float(), e1.act[i][k].float()
+            assert (a - b).abs().max() < 0.08 and (a - b).abs().mean() < 2e-3, (i, k, float((a - b).abs().max()))
+        # identical dropout decisions: the zero pattern of u (ReLU and dropout zeros) agrees except where relu's input is ~0
+        z0, z1 = e0.act[i]["u"] == 0, e1.act[i]["u"] == 0
+        assert (z0 != z1).float().mean() < 2e-3
+        torch.testing.assert_close(e0.act[i]["mean2"], e1.act[i]["mean2"], rtol=0, atol=2e-2)
+    assert (e0.x[-1].float() - e1.x[-1].float()).abs().max() < 0.1
+    bad = []
+    for name in e0.grads:
+        a, b = e0.grads[name].double().flatten(), e1.grads[name].double().flatten()
+        if b.norm() < 1e-12:
+            continue
+        cos = float(a @ b / (a.norm() * b.norm() + 1e-30))
+        ratio = float(a.norm() / b.norm())
+        if cos < 0.998 or abs(ratio - 1) > 0.02:
+            bad.append((name, round(cos, 5), round(ratio, 4)))
+    assert not bad, bad

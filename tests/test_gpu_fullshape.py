@@ -285,6 +285,12 @@ def test_training_trajectory_10_steps_vs_oracle_adam(cuda):
     for nm, p0, p1, pr in zip(names, osr.flat_param_list(P0), osr.flat_param_list(P1), ref_params):
         du, dr = (p1 - p0).double().flatten(), (pr.detach() - p0).double().flatten()
         assert du.abs().max() <= 10 * 1.001e-3 + 1e-6, nm  # |Adam step| <= lr
+        if nm.endswith("in_b"):
+            # the key bias has an exactly-zero true gradient (softmax is invariant to a per-query constant): both sides hold
+            # pure rounding noise there, which Adam normalises to +-lr - compare the query and value thirds only
+            keep = torch.ones(3 * d, dtype=torch.bool)
+            keep[d:2 * d] = False
+            du, dr = du[keep], dr[keep]
         if dr.norm() < 1e-9:
             continue
         cos = float(du @ dr / (du.norm() * dr.norm() + 1e-30))

@@ -393,3 +393,53 @@ def test_fused_post_attention_block_matches_reference_formula(ops, T, d, mask):
     err = (out[:T].cpu().double() - ref).abs().max().item()
     assert err < 0.08, err
     assert (out[T:] == 3.0).all()
+
+
+@pytest.mark.parametrize("T,shapes", [(1000, [(128, 128), (128, 128), (256, 128)]), (4096 + 37, [(64, 64), (128, 64)]),
+                                      (700, [(1024, 256), (256, 1024), (768, 256)])])
+def test_wgrad_group_matches_matmul(ops, T, shapes):
+    """rp_wgrad_group: every dW_i (+)= dY_i^T X_i and db_i (+)= colsum(dY_i) of a block in one launch, operands read in place
+    (column views with a row pitch), against fp64 matmuls; accumulate semantics; bit-identical across runs (no float atomics)."""
+    import ctypes
+
+    from replay_b200._lib import WgradPair, check, lib
+
+    g = torch.Generator().manual_seed(T)
+    L = lib()
+    pairs, keep = [], []
+    arr = (WgradPair * len(shapes))()
+    for k, (n_out, n_in) in enumerate(shapes):
+        # dY is a column view of a wider array (as dK / dV inside dKV), X has its natural pitch
+        wide = (torch.randn(T, n_out + 64, generator=g) * 0.5).to(torch.bfloat16).cuda()
+        dY = wide[:, 64:]
+        X = (torch.randn(T, n_in, generator=g) * 0.5).to(torch.bfloat16).cuda()
+        dW = torch.full((n_out, n_in), 0.25, device="cuda")
+        db = torch.full((n_out,), -1.0, device="cuda")
+        arr[k].dY, arr[k].dy_ld, arr[k].n_out = dY.data_ptr(), dY.stride(0), n_out
+        arr[k].X, arr[k].x_ld, arr[k].n_in = X.data_ptr(), X.stride(0), n_in
+        arr[k].dW, arr[k].dw_ld, arr[k].db = dW.data_ptr(), dW.stride(0), db.data_ptr()
+        pairs.append((dY, X, dW, db))
+        keep.append(wide)
+    need = L.rp_wgrad_group_workspace(arr, len(shapes))
+    assert need > 0
+    ws = torch.zeros(need, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    check(L.rp_wgrad_group(arr, len(shapes), T, 1, ws.data_ptr(), need, st), "rp_wgrad_group")
+    torch.cuda.synchronize()
+    first = [(dW.clone(), db.clone()) for _, _, dW, db in pairs]
+    for (dY, X, dW, db) in pairs:
+        ref = dY.double().T @ X.double() + 0.25
+        refb = dY.double().sum(0) - 1.0
+        assert (dW.double() - ref).abs().max() < 2e-3 * max(1.0, ref.abs().max().item())
+        assert (db.double() - refb).abs().max() < 2e-3 * max(1.0, refb.abs().max().item())
+    # overwrite mode + determinism
+    check(L.rp_wgrad_group(arr, len(shapes), T, 0, ws.data_ptr(), need, st), "rp_wgrad_group")
+    torch.cuda.synchronize()
+    for (dY, X, dW, db), (w1, b1) in zip(pairs, first):
+        assert torch.equal(dW + 0.25, w1) or (dW + 0.25 - w1).abs().max() < 1e-5  # same partial sums, only the +0.25 differs
+        torch.testing.assert_close(db - 1.0, b1, rtol=0, atol=1e-5)
+    again = [(dW.clone(), db.clone()) for _, _, dW, db in pairs]
+    check(L.rp_wgrad_group(arr, len(shapes), T, 0, ws.data_ptr(), need, st), "rp_wgrad_group")
+    torch.cuda.synchronize()
+    for (_, _, dW, db), (w2, b2) in zip(pairs, again):
+        assert torch.equal(dW, w2) and torch.equal(db, b2)

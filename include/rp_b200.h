@@ -268,6 +268,18 @@ int rp_post_attn_train(const void* o, const void* q_in, const void* wo, const fl
                        const unsigned long long* seed_ptr, void* h_save, void* y_save, void* u_save, float* mean_out,
                        float* rstd_out, void* out, void* stream);
 
+/* Everything BEFORE the attention of one SASRec block in one pass over the tokens (training and inference):
+ *   q_in = LayerNorm(x) ;  Q = q_in Wq^T + bq ;  [K | V] = x [Wk | Wv]^T + [bk | bv]      (K, V from the un-normalised x)
+ * x is read once; q_in (the block's residual), Q, KV and the LayerNorm statistics are written once (LayerNorm + two GEMM
+ * launches read x / q_in three times).  w_in bf16 [3d, d] = packed in_proj_weight, b_in fp32 [3d]; d in {64,128}.
+ *   replaces  replay/nn/sequential/sasrec/transformer.py:99-106 ; replay/models/nn/sequential/sasrec/model.py:434-435 */
+int rp_ln_qkv_fused(const void* x, const float* ln_w, const float* ln_b, float eps, const void* w_in, const float* b_in, int T,
+                    int d, void* q_in, void* Q, void* KV, float* mean_out, float* rstd_out, void* stream);
+/* Its backward in one pass:  dq_in = dQ Wq + dh ;  t = LayerNorm-backward(dq_in; x, mean, rstd, ln_w) ;  dx = [dK | dV] Wkv + t.
+ * dln_w / dln_b fp32 [d] are ACCUMULATED (one fp32 atomic per column and CTA).  dx may not alias an input; d in {64,128}. */
+int rp_pre_attn_bwd(const void* dQ, const void* dKV, const void* dh, const void* x, const float* mean, const float* rstd,
+                    const float* ln_w, const void* w_in, int T, int d, void* dx, float* dln_w, float* dln_b, void* stream);
+
 /* ALL weight and bias gradients of one transformer block in one launch (+ one deterministic reduction launch):
  *   dW_i[n_out_i, n_in_i] (+)= dY_i[T, n_out_i]^T . X_i[T, n_in_i] ;  db_i[n_out_i] (+)= column sums of dY_i      i < n_pairs <= 8
  * dY_i / X_i are read in place (MN-major tcgen05 operands, contraction over the tokens); the bias gradient is one extra N = 16

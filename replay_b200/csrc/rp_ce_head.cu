@@ -301,7 +301,7 @@ __global__ void ce_finalize_kernel(const float2* __restrict__ part, const __nv_b
 // MODE 2: rows = tokens, FUSED forward+backward: G~ = exp(s + b) with reference max 0 (valid while |s| is bounded, see
 //         ce_bound_kernel), per-row sum of G~ and un-normalised dH~ = sum_i G~ E_i over this CTA's column split
 //                                                                                      -> out = partial dH~ fp32, zpart
-template <int KCH, int NSTAGE, int MODE, int NBUF, bool A_TMEM, bool INORDER>
+template <int KCH, int NSTAGE, int MODE, int NBUF, bool A_TMEM, bool INORDER, bool HAS_BIAS>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __nv_bfloat16* __restrict__ a_rows /* the row-side matrix (tmA) as a plain pointer, for A_TMEM */,
@@ -492,12 +492,12 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const float g1 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 1]), kLog2e, o.y), q + 1);
           const float g2 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 2]), kLog2e, o.z), q + 2);
           const float g3 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 3]), kLog2e, o.w), q + 3);
-          if (d_bias) gsum += (g0 + g1) + (g2 + g3);
+          if (HAS_BIAS) gsum += (g0 + g1) + (g2 + g3);
           pk[(q >> 1) + 0] = pack_bf16(g0, g1);
           pk[(q >> 1) + 1] = pack_bf16(g2, g3);
         }
       } else {
-        if (bias) {  // per-column bias: s + b before the exponential (warp-uniform 16-byte loads)
+        if (HAS_BIAS) {  // per-column bias: s + b before the exponential (warp-uniform 16-byte loads)
 #pragma unroll
           for (int q = 0; q < kW; q += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
@@ -540,8 +540,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (COLCONST) {
       float* o = reinterpret_cast<float*>(out);
       // biased head: G carries a per-item factor e^{b_i}; it was left out of the loop and is applied to the row here
-      const float rs = (bias && r < n_items) ? __expf(bias[r]) : 1.f;
-      if (d_bias) {
+      const float rs = (HAS_BIAS && r < n_items) ? __expf(bias[r]) : 1.f;
+      if (HAS_BIAS) {
         s_gsum[cg][row] = gsum;
         asm volatile("bar.sync 1, %0;" ::"r"(kBwdEpiWarps * 32) : "memory");  // epilogue warps only
         if (cg == 0 && r < n_items) {
@@ -910,7 +910,9 @@ static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const v
   constexpr int NBUF = A_TMEM ? 2 : ((RP_CE_NBUF3 && KCH <= 2) ? 3 : 2);
   constexpr bool INORDER = (RP_CE_ORDER == 1) && NBUF == 2;
   const int smem = ((A_TMEM ? 0 : 1) + NSTAGE + (A_TMEM ? 1 : 0)) * KCH * kChunk + 1024;
-  auto kern = ce_bwd_kernel<KCH, NSTAGE + (A_TMEM ? 1 : 0), MODE, NBUF, A_TMEM, INORDER>;
+  // the biased head (BERT4Rec) is a separate instantiation: its per-column adds / row sums cost an instruction per logit
+  auto kern = bias ? ce_bwd_kernel<KCH, NSTAGE + (A_TMEM ? 1 : 0), MODE, NBUF, A_TMEM, INORDER, true>
+                   : ce_bwd_kernel<KCH, NSTAGE + (A_TMEM ? 1 : 0), MODE, NBUF, A_TMEM, INORDER, false>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, kBwdThreads, smem, stream>>>(tmA, tmB, reinterpret_cast<const __nv_bfloat16*>(a_rows), cvec, labels,
                                             reinterpret_cast<const __nv_bfloat16*>(table), loss_inv,

@@ -64,7 +64,7 @@ class _CountingLib:
                "rp_embed_bwd": 2, "rp_layernorm_fwd": 1, "rp_layernorm_bwd": 1, "rp_dropout_bwd": 1, "rp_colsum": 1, "rp_colsum_multi": 1,
                "rp_adam_step": 2, "rp_cast_bf16": 1, "rp_counter_add": 1, "rp_reduce_splits": 1, "rp_ce_head_fwd": 2, "rp_ce_head_bwd": 3,
                "rp_score_topk": 2, "rp_seen_prepare": 1, "rp_sampled_head_fwd": 4, "rp_sampled_head_bwd": 4, "rp_ffn_fused": 1, "rp_post_attn_fused": 1,
-               "rp_post_attn_train": 1, "rp_wgrad_group": 2}
+               "rp_post_attn_train": 1, "rp_wgrad_group": 2, "rp_ln_qkv_fused": 1, "rp_pre_attn_bwd": 1}
 
     def __init__(self, L):
         self._L = L
@@ -130,7 +130,8 @@ class SasRecEngine:
         # gradients of a block in one grouped launch (RP_FUSED_BODY=0 restores round 1's launch-per-GEMM body for A/B runs)
         fused_body = os.environ.get("RP_FUSED_BODY", "1") != "0"
         self.fused_post_attn_train = fused_body
-        self.fused_wgrad = fused_body
+        self.fused_wgrad = fused_body and d <= 256          # rp_wgrad_group: at most 48 output tiles per block
+        self.fused_pre_attn = fused_body and d <= 128       # LN1 + Q / KV projections in one pass (forward and backward)
         self.fused_ce = True      # single-pass CE forward + dH (guarded on the device by a bound on |logit|)
         self.n_valid_hint = 0     # host estimate of the number of valid targets per step (load balance of the CE head only)
         self._alloc_workspace()
@@ -480,10 +481,16 @@ class SasRecEngine:
                 self._gemm(lb["u"], w("w2"), self.last_rows, Bq, d, d, bias=f("b2"), residual=lb["y"],
                            rowmask=self.last_pad if legacy else None)
                 return
-            self._ln_fwd(x, f("ln1_w"), f("ln1_b"), 1e-8, a["q_in"], a["mean1"], a["rstd1"], T)
             in_w, in_b = w("in_w"), f("in_b")
-            self._gemm(a["q_in"], in_w[:d], a["Q"], T, d, d, bias=in_b[:d])
-            self._gemm(x, in_w[d:], a["KV"], T, 2 * d, d, bias=in_b[d:])
+            if self.fused_pre_attn:
+                check(self.lib.rp_ln_qkv_fused(x.data_ptr(), f("ln1_w").data_ptr(), f("ln1_b").data_ptr(), 1e-8,
+                                               in_w.data_ptr(), in_b.data_ptr(), T, d, a["q_in"].data_ptr(), a["Q"].data_ptr(),
+                                               a["KV"].data_ptr(), a["mean1"].data_ptr(), a["rstd1"].data_ptr(), self._stream()),
+                      "rp_ln_qkv_fused")
+            else:
+                self._ln_fwd(x, f("ln1_w"), f("ln1_b"), 1e-8, a["q_in"], a["mean1"], a["rstd1"], T)
+                self._gemm(a["q_in"], in_w[:d], a["Q"], T, d, d, bias=in_b[:d])
+                self._gemm(x, in_w[d:], a["KV"], T, 2 * d, d, bias=in_b[d:])
             ad = AttnDesc()
             ad.q, ad.q_rows, ad.q_cols, ad.ldq, ad.q_c0 = a["Q"].data_ptr(), T, d, d, 0
             ad.k, ad.k_rows, ad.k_cols, ad.ldk, ad.k_c0 = a["KV"].data_ptr(), T, 2 * d, 2 * d, 0
@@ -642,13 +649,19 @@ class SasRecEngine:
                            a_off=(0, H * Lp, Lp, 0, 0, 0), b_off=(0, L, 0, 0, 0, hd), c_geom=(2 * d, d, L * 2 * d, hd))
             # ---- projections
             in_w = w("in_w")
-            self._gemm(s["dQ"], in_w[:d], s["dq_in"], T, d, d, b_mn=True, residual=s["dh"])
+            if self.fused_pre_attn:
+                check(self.lib.rp_pre_attn_bwd(s["dQ"].data_ptr(), s["dKV"].data_ptr(), s["dh"].data_ptr(), x.data_ptr(),
+                                               a["mean1"].data_ptr(), a["rstd1"].data_ptr(), f("ln1_w").data_ptr(),
+                                               in_w.data_ptr(), T, d, other.data_ptr(), g("ln1_w").data_ptr(),
+                                               g("ln1_b").data_ptr(), st()), "rp_pre_attn_bwd")
+            else:
+                self._gemm(s["dQ"], in_w[:d], s["dq_in"], T, d, d, b_mn=True, residual=s["dh"])
+                self._ln_bwd(s["dq_in"], x, f("ln1_w"), a["mean1"], a["rstd1"], s["tmp"], g("ln1_w"), g("ln1_b"), T)
+                self._gemm(s["dKV"], in_w[d:], other, T, d, 2 * d, b_mn=True, residual=s["tmp"])
             wpairs.append((s["dQ"], a["q_in"], g("in_w")[:d], g("in_b")[:d]))
             if not fw:
                 self._wgrad(s["dQ"], a["q_in"], g("in_w")[:d], d, d)
             bias_grads.append((s["dQ"], g("in_b")[:d]))
-            self._ln_bwd(s["dq_in"], x, f("ln1_w"), a["mean1"], a["rstd1"], s["tmp"], g("ln1_w"), g("ln1_b"), T)
-            self._gemm(s["dKV"], in_w[d:], other, T, d, 2 * d, b_mn=True, residual=s["tmp"])
             wpairs.append((s["dKV"], x, g("in_w")[d:], g("in_b")[d:]))
             if fw:
                 self._wgrad_group(wpairs)

@@ -443,3 +443,68 @@ def test_wgrad_group_matches_matmul(ops, T, shapes):
     torch.cuda.synchronize()
     for (_, _, dW, db), (w2, b2) in zip(pairs, again):
         assert torch.equal(dW, w2) and torch.equal(db, b2)
+
+
+@pytest.mark.parametrize("T,d", [(1000, 128), (517, 64), (128 * 150 + 5, 128)])
+def test_ln_qkv_fused_matches_formula(ops, T, d):
+    """rp_ln_qkv_fused: q_in = LN(x), Q = q_in Wq^T + bq, [K|V] = x Wkv^T + bkv in one pass, vs fp64 on the same bf16 inputs
+    (transformer.py:99-106: the query is the NORMALISED x, keys / values the un-normalised one)."""
+    from replay_b200._lib import check, lib
+
+    g = torch.Generator().manual_seed(T + d)
+    x = (torch.randn(T, d, generator=g) * 1.3 + 0.2).to(torch.bfloat16)
+    w_in = (torch.randn(3 * d, d, generator=g) / d ** 0.5).to(torch.bfloat16)
+    b_in = torch.randn(3 * d, generator=g) * 0.1
+    ln_w, ln_b = 1 + 0.1 * torch.randn(d, generator=g), 0.1 * torch.randn(d, generator=g)
+    xd = x.double()
+    mean, var = xd.mean(-1, keepdim=True), xd.var(-1, unbiased=False, keepdim=True)
+    q_ref = (xd - mean) / torch.sqrt(var + 1e-8) * ln_w.double() + ln_b.double()
+    dev = dict(device="cuda")
+    q_in, Q = torch.zeros(T, d, dtype=torch.bfloat16, **dev), torch.zeros(T, d, dtype=torch.bfloat16, **dev)
+    KV = torch.zeros(T, 2 * d, dtype=torch.bfloat16, **dev)
+    mo, ro = torch.zeros(T, **dev), torch.zeros(T, **dev)
+    xc, wc, bc, lw, lb = x.cuda(), w_in.cuda(), b_in.cuda(), ln_w.cuda(), ln_b.cuda()
+    check(lib().rp_ln_qkv_fused(xc.data_ptr(), lw.data_ptr(), lb.data_ptr(), 1e-8, wc.data_ptr(), bc.data_ptr(), T, d,
+                                q_in.data_ptr(), Q.data_ptr(), KV.data_ptr(), mo.data_ptr(), ro.data_ptr(),
+                                torch.cuda.current_stream().cuda_stream), "rp_ln_qkv_fused")
+    torch.cuda.synchronize()
+    assert (q_in.cpu().double() - q_ref).abs().max() < 3e-2
+    torch.testing.assert_close(mo.cpu().double(), mean[:, 0], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(ro.cpu().double(), 1 / torch.sqrt(var[:, 0] + 1e-8), rtol=1e-3, atol=1e-4)
+    q16 = q_in.cpu().double()  # the Q GEMM consumes the bf16 q_in the kernel itself produced
+    Q_ref = q16 @ w_in[:d].double().T + b_in[:d].double()
+    KV_ref = xd @ w_in[d:].double().T + b_in[d:].double()
+    assert (Q.cpu().double() - Q_ref).abs().max() < 3e-2 * max(1.0, Q_ref.abs().max().item())
+    assert (KV.cpu().double() - KV_ref).abs().max() < 3e-2 * max(1.0, KV_ref.abs().max().item())
+    assert (Q.cpu().double() - Q_ref).norm() / Q_ref.norm() < 5e-3 and (KV.cpu().double() - KV_ref).norm() / KV_ref.norm() < 5e-3
+
+
+@pytest.mark.parametrize("T,d", [(1000, 128), (517, 64), (128 * 150 + 5, 128)])
+def test_pre_attn_bwd_matches_formula(ops, T, d):
+    """rp_pre_attn_bwd: dq_in = dQ Wq + dh ; LayerNorm backward ; dx = dKV Wkv + t ; dln_w, dln_b - vs fp64 autograd-free formulas."""
+    from replay_b200._lib import check, lib
+
+    g = torch.Generator().manual_seed(T * 3 + d)
+    bf = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(torch.bfloat16)  # noqa: E731
+    dQ, dKV, dh, x = bf(T, d, sc=0.3), bf(T, 2 * d, sc=0.3), bf(T, d, sc=0.3), bf(T, d, sc=1.2)
+    w_in = bf(3 * d, d, sc=1 / d ** 0.5)
+    ln_w = 1 + 0.1 * torch.randn(d, generator=g)
+    xd = x.double()
+    mean, var = xd.mean(-1), xd.var(-1, unbiased=False)
+    rstd = 1 / torch.sqrt(var + 1e-8)
+    xhat = (xd - mean[:, None]) * rstd[:, None]
+    dq = dQ.double() @ w_in[:d].double() + dh.double()
+    gg = dq * ln_w.double()
+    t = rstd[:, None] * (gg - gg.mean(-1, keepdim=True) - xhat * (gg * xhat).mean(-1, keepdim=True))
+    dx_ref = dKV.double() @ w_in[d:].double() + t
+    dw_ref, db_ref = (dq * xhat).sum(0), dq.sum(0)
+    dx = torch.zeros(T, d, dtype=torch.bfloat16, device="cuda")
+    dw, db = torch.full((d,), 2.0, device="cuda"), torch.full((d,), -3.0, device="cuda")
+    args = [t_.cuda() for t_ in (dQ, dKV, dh, x, mean.float(), rstd.float(), ln_w, w_in)]
+    check(lib().rp_pre_attn_bwd(*[a.data_ptr() for a in args], T, d, dx.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                                torch.cuda.current_stream().cuda_stream), "rp_pre_attn_bwd")
+    torch.cuda.synchronize()
+    assert (dx.cpu().double() - dx_ref).norm() / dx_ref.norm() < 6e-3
+    assert (dx.cpu().double() - dx_ref).abs().max() < 3e-2 * max(1.0, dx_ref.abs().max().item())
+    assert ((dw.cpu().double() - 2.0) - dw_ref).norm() / dw_ref.norm() < 5e-3   # accumulated on top of the preset values
+    assert ((db.cpu().double() + 3.0) - db_ref).norm() / db_ref.norm() < 5e-3

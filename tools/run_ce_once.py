@@ -2,7 +2,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from replay_b200 import ops
-T, nv_, I, d = 51200, 26263, 50000, 128
+T, nv_, I, d = 102400, 55574, 50000, 128  # bench default: 512 sequences per step
 g = torch.Generator(device="cuda").manual_seed(0)
 hc = torch.randn(T, d, device="cuda", generator=g).bfloat16(); hc[nv_:] = 0
 table = (torch.randn(I, d, device="cuda", generator=g) * 0.3).bfloat16()

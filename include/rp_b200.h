@@ -268,6 +268,18 @@ int rp_post_attn_train(const void* o, const void* q_in, const void* wo, const fl
                        const unsigned long long* seed_ptr, void* h_save, void* y_save, void* u_save, float* mean_out,
                        float* rstd_out, void* out, void* stream);
 
+/* Backward of rp_post_attn_train in one pass over the tokens.  Given dz = d loss / d out:
+ *   dzm = dz [* rowmask] ;  d_t = dropout2'(dzm) ;  du = (d_t W2) * [u != 0] / keep ;  dy = du W1 + dzm ;
+ *   dh = LayerNorm-backward(dy ; h, mean, rstd, ln_w) ;  d_o = dh Wo ;  dln_w / dln_b += column sums (fp32 atomics, one per column and CTA)
+ * d_t, du, dh (bf16 [T, d]) are the dY operands of rp_wgrad_group for W2 / W1 / Wo (X = u, y, o); dh is also the residual gradient
+ * into the pre-attention part; d_o feeds rp_attn_bwd.  d_t may be NULL when drop_p == 0 and rowmask == NULL (then d_t == dz).
+ *   replaces autograd's backward of  replay/nn/sequential/sasrec/transformer.py:107-110 ; replay/nn/ffn.py:43-57 ;
+ *                                    replay/models/nn/sequential/sasrec/model.py:436-441,496-506 */
+int rp_post_attn_bwd(const void* dz, const void* u, const void* h, const float* mean, const float* rstd, const float* ln_w,
+                     const void* w2, const void* w1, const void* wo, const uint8_t* rowmask, int T, int d, float drop_p,
+                     unsigned long long seed, unsigned long long drop_off2, const unsigned long long* seed_ptr, void* d_t, void* du,
+                     void* dh, void* d_o, float* dln_w, float* dln_b, void* stream);
+
 /* Everything BEFORE the attention of one SASRec block in one pass over the tokens (training and inference):
  *   q_in = LayerNorm(x) ;  Q = q_in Wq^T + bq ;  [K | V] = x [Wk | Wv]^T + [bk | bv]      (K, V from the un-normalised x)
  * x is read once; q_in (the block's residual), Q, KV and the LayerNorm statistics are written once (LayerNorm + two GEMM

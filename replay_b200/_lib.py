@@ -86,6 +86,7 @@ def lib():
     _sig(L.rp_build_batch, c_int, [P, P, LL, P, P, c_int, c_int, c_int, c_int, c_float, P, U64, U64, P, P, P, P, P, P, P])
     _sig(L.rp_post_attn_train, c_int, [P, P, P, P, P, P, c_float, P, P, P, P, P, c_int, c_int, c_float, U64, U64, U64, P,
                                        P, P, P, P, P, P, P])
+    _sig(L.rp_post_attn_bwd, c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_float, U64, U64, P, P, P, P, P, P, P, P])
     _sig(L.rp_ln_qkv_fused, c_int, [P, P, P, c_float, P, P, c_int, c_int, P, P, P, P, P, P])
     _sig(L.rp_pre_attn_bwd, c_int, [P, P, P, P, P, P, P, P, c_int, c_int, P, P, P, P])
     _sig(L.rp_wgrad_group_workspace, c_size_t, [ctypes.POINTER(WgradPair), c_int])

@@ -50,7 +50,7 @@ static constexpr int kBwdThreads = 64 + kBwdEpiWarps * 32;
 #define RP_CE_POLY_EVERY 4   /* forward: 25 % of the exponentials on the FMA pipe (measured best, profiles/r1_ce_variants.md) */
 #endif
 #ifndef RP_CE_POLY_EVERY_BWD
-#define RP_CE_POLY_EVERY_BWD 8   /* backward: 12.5 % */
+#define RP_CE_POLY_EVERY_BWD 0   /* backward / fused passes: MUFU only (r2 A/B with the in-order issue: 0 beats 12.5 % by 2-8 %, profiles/r2_ce_variants.md) */
 #endif
 #ifndef RP_CE_NBUF3
 #define RP_CE_NBUF3 1
@@ -507,16 +507,29 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             raw[q + 3] = __float_as_uint(__uint_as_float(raw[q + 3]) + b4.w);
           }
         }
+        if (col0 + kW <= n_items) {  // (warp-uniform) every column of this part exists: no per-element masking in the hot loop
+          float z0 = 0.f, z1 = 0.f;
 #pragma unroll
-        for (int q = 0; q < kW; q += 2) {
-          float g0 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 0]), kLog2e, crow), q + 0);
-          float g1 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 1]), kLog2e, crow), q + 1);
-          if (col0 + kW > n_items) {  // columns beyond the catalog do not exist
+          for (int q = 0; q < kW; q += 2) {
+            const float g0 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 0]), kLog2e, crow), q + 0);
+            const float g1 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 1]), kLog2e, crow), q + 1);
+            if (FUSED) {
+              z0 += g0;
+              z1 += g1;
+            }
+            pk[q >> 1] = pack_bf16(g0, g1);
+          }
+          if (FUSED) zacc += z0 + z1;
+        } else {  // ragged last tile of the catalog: columns beyond it do not exist
+#pragma unroll
+          for (int q = 0; q < kW; q += 2) {
+            float g0 = ex2f(fmaf(__uint_as_float(raw[q + 0]), kLog2e, crow));
+            float g1 = ex2f(fmaf(__uint_as_float(raw[q + 1]), kLog2e, crow));
             if (col0 + q >= n_items) g0 = 0.f;
             if (col0 + q + 1 >= n_items) g1 = 0.f;
+            if (FUSED) zacc += g0 + g1;
+            pk[q >> 1] = pack_bf16(g0, g1);
           }
-          if (FUSED) zacc += g0 + g1;
-          pk[q >> 1] = pack_bf16(g0, g1);
         }
       }
 #if RP_CE_ABLATE == 1  // diagnostic build: keep the TMEM traffic, drop the exponentials (G = bf16(S))

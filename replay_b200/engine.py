@@ -64,7 +64,8 @@ class _CountingLib:
                "rp_embed_bwd": 2, "rp_layernorm_fwd": 1, "rp_layernorm_bwd": 1, "rp_dropout_bwd": 1, "rp_colsum": 1, "rp_colsum_multi": 1,
                "rp_adam_step": 2, "rp_cast_bf16": 1, "rp_counter_add": 1, "rp_reduce_splits": 1, "rp_ce_head_fwd": 2, "rp_ce_head_bwd": 3,
                "rp_score_topk": 2, "rp_seen_prepare": 1, "rp_sampled_head_fwd": 4, "rp_sampled_head_bwd": 4, "rp_ffn_fused": 1, "rp_post_attn_fused": 1,
-               "rp_post_attn_train": 1, "rp_wgrad_group": 2, "rp_ln_qkv_fused": 1, "rp_pre_attn_bwd": 1}
+               "rp_post_attn_train": 1, "rp_wgrad_group": 2, "rp_ln_qkv_fused": 1, "rp_pre_attn_bwd": 1,
+               "rp_post_attn_bwd": 1}
 
     def __init__(self, L):
         self._L = L
@@ -132,6 +133,7 @@ class SasRecEngine:
         self.fused_post_attn_train = fused_body
         self.fused_wgrad = fused_body and d <= 256          # rp_wgrad_group: at most 48 output tiles per block
         self.fused_pre_attn = fused_body and d <= 128       # LN1 + Q / KV projections in one pass (forward and backward)
+        self.fused_post_attn_bwd = fused_body and d <= 128  # dropout' + FFN + LN2 + out-projection backward in one pass
         self.fused_ce = True      # single-pass CE forward + dH (guarded on the device by a bound on |logit|)
         self.n_valid_hint = 0     # host estimate of the number of valid targets per step (load balance of the CE head only)
         self._alloc_workspace()
@@ -584,34 +586,54 @@ class SasRecEngine:
             f = lambda k: prm[f"b{i}.{k}"]  # noqa: E731
             g = lambda k: G[f"b{i}.{k}"]  # noqa: E731
             dz = dx
-            if legacy:  # x_next = (...) * pad   (sasrec/model.py:441)
+            if self.fused_post_attn_bwd:
+                # one pass: d_t, du, dh (operands of the grouped weight gradients), d_o (into the attention backward), dLN2
+                masked = legacy or drop > 0
+                check(self.lib.rp_post_attn_bwd(dz.data_ptr(), a["u"].data_ptr(), a["h"].data_ptr(), a["mean2"].data_ptr(),
+                                                a["rstd2"].data_ptr(), f("ln2_w").data_ptr(), w("w2").data_ptr(),
+                                                w("w1").data_ptr(), w("out_w").data_ptr(),
+                                                self.in_pad.data_ptr() if legacy else None, T, d, drop, self.seed,
+                                                self._site(i, 2) << 40, self.rng_counter.data_ptr(),
+                                                s["d_t"].data_ptr() if masked else None, s["du"].data_ptr(), s["dh"].data_ptr(),
+                                                s["d_o"].data_ptr(), g("ln2_w").data_ptr(), g("ln2_b").data_ptr(), st()),
+                      "rp_post_attn_bwd")
+                d_t = s["d_t"] if masked else dz
+                fw = self.fused_wgrad
+                wpairs = [(d_t, a["u"], g("w2"), g("b2")), (s["du"], a["y"], g("w1"), g("b1")), (s["dh"], a["O"], g("out_w"), g("out_b"))]
+                bias_grads = [(d_t, g("b2")), (s["du"], g("b1")), (s["dh"], g("out_b"))]
+                if not fw:
+                    self._wgrad(d_t, a["u"], g("w2"), d, d)
+                    self._wgrad(s["du"], a["y"], g("w1"), d, d)
+                    self._wgrad(s["dh"], a["O"], g("out_w"), d, d)
+            if not self.fused_post_attn_bwd and legacy:  # x_next = (...) * pad   (sasrec/model.py:441)
                 check(self.lib.rp_dropout_bwd(dz.data_ptr(), dz.data_ptr(), T, d, self.in_pad.data_ptr(), 0.0, 0, 0, None, st()),
                       "rp_dropout_bwd")
-            if drop > 0:
-                check(self.lib.rp_dropout_bwd(dz.data_ptr(), s["d_t"].data_ptr(), T, d, None, drop, self.seed,
-                                              self._site(i, 2) << 40, self.rng_counter.data_ptr(), st()), "rp_dropout_bwd")
-                d_t = s["d_t"]
-            else:
-                d_t = dz
-            # ---- FFN backward
-            fw = self.fused_wgrad
-            wpairs = [(d_t, a["u"], g("w2"), g("b2"))]  # (dY, X, dW, db): weight + bias gradients, one grouped launch per block
-            if not fw:
-                self._wgrad(d_t, a["u"], g("w2"), d, d)
-            bias_grads = [(d_t, g("b2"))]  # column sums of this block, one launch at the end of its backward
-            self._gemm(d_t, w("w2"), s["du"], T, d, d, b_mn=True, gate=a["u"], gate_scale=ks)
-            wpairs.append((s["du"], a["y"], g("w1"), g("b1")))
-            if not fw:
-                self._wgrad(s["du"], a["y"], g("w1"), d, d)
-            bias_grads.append((s["du"], g("b1")))
-            self._gemm(s["du"], w("w1"), s["dy"], T, d, d, b_mn=True, residual=dz)
-            self._ln_bwd(s["dy"], a["h"], f("ln2_w"), a["mean2"], a["rstd2"], s["dh"], g("ln2_w"), g("ln2_b"), T)
-            # ---- out projection
-            self._gemm(s["dh"], w("out_w"), s["d_o"], T, d, d, b_mn=True)
-            wpairs.append((s["dh"], a["O"], g("out_w"), g("out_b")))
-            if not fw:
-                self._wgrad(s["dh"], a["O"], g("out_w"), d, d)
-            bias_grads.append((s["dh"], g("out_b")))
+            if not self.fused_post_attn_bwd:
+                if drop > 0:
+                    check(self.lib.rp_dropout_bwd(dz.data_ptr(), s["d_t"].data_ptr(), T, d, None, drop, self.seed,
+                                                  self._site(i, 2) << 40, self.rng_counter.data_ptr(), st()), "rp_dropout_bwd")
+                    d_t = s["d_t"]
+                else:
+                    d_t = dz
+                # ---- FFN backward
+                fw = self.fused_wgrad
+                wpairs = [(d_t, a["u"], g("w2"), g("b2"))]  # (dY, X, dW, db): weight + bias gradients, one grouped launch per block
+                if not fw:
+                    self._wgrad(d_t, a["u"], g("w2"), d, d)
+                bias_grads = [(d_t, g("b2"))]  # column sums of this block, one launch at the end of its backward
+                self._gemm(d_t, w("w2"), s["du"], T, d, d, b_mn=True, gate=a["u"], gate_scale=ks)
+                wpairs.append((s["du"], a["y"], g("w1"), g("b1")))
+                if not fw:
+                    self._wgrad(s["du"], a["y"], g("w1"), d, d)
+                bias_grads.append((s["du"], g("b1")))
+                self._gemm(s["du"], w("w1"), s["dy"], T, d, d, b_mn=True, residual=dz)
+                self._ln_bwd(s["dy"], a["h"], f("ln2_w"), a["mean2"], a["rstd2"], s["dh"], g("ln2_w"), g("ln2_b"), T)
+                # ---- out projection
+                self._gemm(s["dh"], w("out_w"), s["d_o"], T, d, d, b_mn=True)
+                wpairs.append((s["dh"], a["O"], g("out_w"), g("out_b")))
+                if not fw:
+                    self._wgrad(s["dh"], a["O"], g("out_w"), d, d)
+                bias_grads.append((s["dh"], g("out_b")))
             # ---- attention backward
             KV, Q = a["KV"], a["Q"]
             if self.fused_attn_bwd:

@@ -508,3 +508,61 @@ def test_pre_attn_bwd_matches_formula(ops, T, d):
     assert (dx.cpu().double() - dx_ref).abs().max() < 3e-2 * max(1.0, dx_ref.abs().max().item())
     assert ((dw.cpu().double() - 2.0) - dw_ref).norm() / dw_ref.norm() < 5e-3   # accumulated on top of the preset values
     assert ((db.cpu().double() + 3.0) - db_ref).norm() / db_ref.norm() < 5e-3
+
+
+@pytest.mark.parametrize("T,d,drop,masked", [(1000, 128, 0.0, False), (900, 128, 0.25, True), (517, 64, 0.1, False),
+                                             (128 * 150 + 5, 128, 0.2, False)])
+def test_post_attn_bwd_matches_formula(ops, T, d, drop, masked):
+    """rp_post_attn_bwd (dropout' -> FFN backward -> LayerNorm2 backward -> out-projection backward in one pass) vs fp64
+    formulas; the site-2 dropout mask is taken from rp_dropout_bwd (the same stream), site 1 is encoded in the zeros of u."""
+    from replay_b200._lib import check, lib
+
+    L = lib()
+    g = torch.Generator().manual_seed(T * 7 + d)
+    bf = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(torch.bfloat16)  # noqa: E731
+    dz, h = bf(T, d, sc=0.5), bf(T, d, sc=1.5)
+    u = torch.relu(bf(T, d))  # ~half zeros, like relu + dropout output
+    w2, w1, wo = bf(d, d, sc=1 / d ** 0.5), bf(d, d, sc=1 / d ** 0.5), bf(d, d, sc=1 / d ** 0.5)
+    ln_w = 1 + 0.1 * torch.randn(d, generator=g)
+    rowmask = (torch.rand(T, generator=g) > 0.3).to(torch.uint8) if masked else None
+    seed, off2 = 1234567, 5 << 40
+    st = torch.cuda.current_stream().cuda_stream
+    ctr = torch.tensor([99], dtype=torch.int64, device="cuda")
+    # reference mask of site 2: d_t_ref = dropout_bwd(dz * rowmask)
+    dzc = dz.cuda()
+    ones = torch.ones(T, d, dtype=torch.bfloat16, device="cuda")
+    keep = torch.empty_like(ones)
+    check(L.rp_dropout_bwd(ones.data_ptr(), keep.data_ptr(), T, d, None, drop, seed, off2, ctr.data_ptr(), st), "rp_dropout_bwd")
+    keep = keep.cpu().double()  # 0 or 1/(1-p) (bf16-rounded scale: divide it out)
+    keep = (keep > 0).double() / (1.0 - drop)
+    rm = rowmask.double()[:, None] if masked else 1.0
+    dzm = dz.double() * rm
+    d_t = dzm * keep
+    hd = h.double()
+    mean, var = hd.mean(-1), hd.var(-1, unbiased=False)
+    rstd = 1 / torch.sqrt(var + 1e-8)
+    xhat = (hd - mean[:, None]) * rstd[:, None]
+    d_t16 = d_t.to(torch.bfloat16).double()
+    du = (d_t16 @ w2.double()) * (u.double() != 0) / (1.0 - drop)
+    du16 = du.to(torch.bfloat16).double()
+    dy = du16 @ w1.double() + dzm
+    gg = dy * ln_w.double()
+    dh = rstd[:, None] * (gg - gg.mean(-1, keepdim=True) - xhat * (gg * xhat).mean(-1, keepdim=True))
+    d_o = dh.to(torch.bfloat16).double() @ wo.double()
+    o = {k: torch.zeros(T, d, dtype=torch.bfloat16, device="cuda") for k in ("d_t", "du", "dh", "d_o")}
+    dw, db = torch.full((d,), 1.0, device="cuda"), torch.full((d,), -1.0, device="cuda")
+    need_dt = masked or drop > 0
+    args = [dzc, u.cuda(), h.cuda(), mean.float().cuda(), rstd.float().cuda(), ln_w.cuda(), w2.cuda(), w1.cuda(), wo.cuda()]
+    rmc = rowmask.cuda() if masked else None
+    check(L.rp_post_attn_bwd(*[a.data_ptr() for a in args], None if rmc is None else rmc.data_ptr(), T, d, drop, seed, off2,
+                             ctr.data_ptr(), o["d_t"].data_ptr() if need_dt else None, o["du"].data_ptr(), o["dh"].data_ptr(),
+                             o["d_o"].data_ptr(), dw.data_ptr(), db.data_ptr(), st), "rp_post_attn_bwd")
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a.cpu().double() - b).norm() / b.norm())  # noqa: E731
+    if need_dt:
+        assert rel(o["d_t"], d_t) < 5e-3
+    assert rel(o["du"], du) < 8e-3, rel(o["du"], du)
+    assert rel(o["dh"], dh) < 1e-2, rel(o["dh"], dh)
+    assert rel(o["d_o"], d_o) < 1.2e-2, rel(o["d_o"], d_o)
+    assert float(((dw.cpu().double() - 1.0) - (dy * xhat).sum(0)).norm() / (dy * xhat).sum(0).norm()) < 1e-2
+    assert float(((db.cpu().double() + 1.0) - dy.sum(0)).norm() / dy.sum(0).norm()) < 1e-2

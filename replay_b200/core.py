@@ -8,6 +8,8 @@
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .engine import _BLOCK_PARAMS, EncoderConfig, SasRecEngine
@@ -121,7 +123,28 @@ class SasRecCore(torch.nn.Module):
         elif batch > e.B or seq_len != e.L or (with_grad and not e.with_grad):
             e.resize(max(batch, e.B) if seq_len == e.L else batch, seq_len, with_grad or e.with_grad)
             e._loss_applied = None
+            self._drop_graphs()
         return e
+
+    # ---- the fused step replays two CUDA graphs (forward + backward | Adam) around the gradient exchange, exactly like
+    # replay_b200.trainer.Trainer: ~40 launches per step would otherwise cost their launch latency on every training_step
+    use_cuda_graph = os.environ.get("RP_NO_GRAPH", "0") == "0"
+
+    def _drop_graphs(self):
+        tr = getattr(self, "_trainer", None)
+        if tr is not None:
+            tr.invalidate()
+
+    def _graph_trainer(self, eng):
+        from .trainer import Trainer
+
+        tr = getattr(self, "_trainer", None)
+        if tr is None or tr.engine is not eng:
+            tr = self._trainer = Trainer(eng, use_graph=self.use_cuda_graph, betas=self.adam_betas)
+        if tr.betas != tuple(self.adam_betas):
+            tr.betas = tuple(self.adam_betas)
+            tr.invalidate()
+        return tr
 
     def _export(self) -> dict:
         return {self._keymap[k]: self._to_ref(k, v.detach().clone()) for k, v in self.engine.params.items()}
@@ -210,9 +233,12 @@ class SasRecCore(torch.nn.Module):
             eng.refresh_shadow()
             self._shadow_dirty = False
         self._set_lr(eng, lr)
+        loss_before = getattr(eng, "_loss_applied", None), eng.sampled is None
         self._stage(eng, ids, pad_mask, labels, target_mask, negatives)
-        if isinstance(all_reduce, str):
-            all_reduce = dist_grad_all_reduce()
+        if (getattr(eng, "_loss_applied", None), eng.sampled is None) != loss_before:
+            self._drop_graphs()  # another loss head: different kernels / buffers
+        if isinstance(all_reduce, str):  # "auto": torch.distributed when initialised (inside Trainer.run)
+            return self._graph_trainer(eng).run()[0]
         return eng.train_step(all_reduce, betas=self.adam_betas)[0]
 
     def _set_lr(self, eng, lr):

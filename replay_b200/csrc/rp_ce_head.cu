@@ -43,6 +43,14 @@ static constexpr int kThreads = 64 + kEpiWarps * 32;
 static constexpr int kBwdCG = RP_CE_BWD_CG;
 static constexpr int kBwdEpiWarps = 4 * kBwdCG;
 static constexpr int kBwdThreads = 64 + kBwdEpiWarps * 32;
+// RP_CE_GROUPS = 2 (d = 128): TWO such sets of epilogue warps, one per S buffer (even / odd column tiles).  One set works in
+// lock step - wait, tcgen05.ld, 64 exponentials per thread, tcgen05.st, arrive - so the MUFU pipe (the 16 384 exponentials of
+// a tile need >= 1024 of the ~1170 tensor cycles of the tile) idles through every load / store / barrier phase; two sets on
+// different tiles fill each other's gaps (r2 ncu: MUFU 61-65 % and tensor 69-74 % busy with one set).
+#ifndef RP_CE_GROUPS
+#define RP_CE_GROUPS 2
+#endif
+static constexpr int kCeMaxGroups = 2;
 
 // tuning knobs (measured on B200, see profiles/): every RP_CE_POLY_EVERY-th exponential goes to the FMA-pipe polynomial
 // instead of MUFU.EX2 (0 = MUFU only); RP_CE_NBUF3 = 1 triple-buffers S in TMEM for d <= 128.
@@ -301,8 +309,8 @@ __global__ void ce_finalize_kernel(const float2* __restrict__ part, const __nv_b
 // MODE 2: rows = tokens, FUSED forward+backward: G~ = exp(s + b) with reference max 0 (valid while |s| is bounded, see
 //         ce_bound_kernel), per-row sum of G~ and un-normalised dH~ = sum_i G~ E_i over this CTA's column split
 //                                                                                      -> out = partial dH~ fp32, zpart
-template <int KCH, int NSTAGE, int MODE, int NBUF, bool A_TMEM, bool INORDER, bool HAS_BIAS>
-__global__ void __launch_bounds__(kBwdThreads, 1)
+template <int KCH, int NSTAGE, int MODE, int NBUF, bool A_TMEM, bool INORDER, bool HAS_BIAS, int GROUPS>
+__global__ void __launch_bounds__(64 + GROUPS * kBwdEpiWarps * 32, 1)
 ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __nv_bfloat16* __restrict__ a_rows /* the row-side matrix (tmA) as a plain pointer, for A_TMEM */,
               const float* __restrict__ cvec /* [T] exponent offsets per token */, const int32_t* __restrict__ labels,
@@ -313,6 +321,9 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   constexpr bool COLCONST = (MODE == 1);
   constexpr bool FUSED = (MODE == 2);
   constexpr int kW = kT / kBwdCG;  // S columns owned by one epilogue warp (its bf16 G lands in the first kW/2 of them)
+  constexpr int kEW = kBwdEpiWarps * GROUPS;   // epilogue warps in total
+  constexpr int kSlots = kBwdCG * GROUPS;      // column slots of the accumulator read-out / of the row-sum partials
+  static_assert(GROUPS == 1 || (GROUPS == 2 && NBUF == 2), "one epilogue warp set per S buffer");
   constexpr int D = KCH * 64;
   if (safe_flag && (*safe_flag != 0) != (run_if_safe != 0)) return;  // fused path vs two-pass fallback (uniform)
   constexpr int kStage = KCH * kChunk;
@@ -323,7 +334,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint8_t* sA = smem;
   uint8_t* sB = smem + (A_TMEM ? 0 : kStage);
   __shared__ __align__(16) float s_cc[NSTAGE][kT];
-  __shared__ float s_gsum[kBwdCG][kT];
+  __shared__ float s_gsum[kSlots][kT];
   __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_sfull[NBUF], bar_sfree[NBUF], bar_pfull[NBUF], bar_acc;
   __shared__ uint32_t tmem_slot;
 
@@ -339,7 +350,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int n_ct = FUSED ? (int)(((long long)n_ct_all * (split + 1)) / n_splits) - jg0 : n_ct_all;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bar_a, A_TMEM ? kBwdEpiWarps : 1);
+    mbar_init(&bar_a, A_TMEM ? kEW : 1);
     for (int i = 0; i < NSTAGE; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
@@ -435,7 +446,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       umma_commit(&bar_acc);
     }
   } else {
-    const int ew = warp - 2, quarter = warp & 3, cg = ew >> 2;   // lane quarter, column group
+    const int ew = warp - 2, quarter = warp & 3;                 // lane quarter
+    const int grp = ew / kBwdEpiWarps, cg = (ew % kBwdEpiWarps) >> 2, slot = grp * kBwdCG + cg;   // warp set, column group
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     float crow = 0.f;
@@ -446,9 +458,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (A_TMEM) {
       // thread (row, column group) copies its slice of the row tile from global memory into TMEM: K elements
       // [cg*D/CG, (cg+1)*D/CG) of row r0+row -> packed columns [cg*D/(2CG), ...); rows beyond the matrix read as zero
-      constexpr int WORDS = D / 2 / kBwdCG;  // 32-bit words per thread
+      constexpr int WORDS = D / 2 / kSlots;  // 32-bit words per thread
+      static_assert(WORDS % 16 == 0, "row-tile copy works in 16-word TMEM stores");
       const bool in = (r0 + row) < n_rows;
-      const uint4* src = reinterpret_cast<const uint4*>(a_rows + (size_t)(in ? r0 + row : 0) * D + cg * (D / kBwdCG));
+      const uint4* src = reinterpret_cast<const uint4*>(a_rows + (size_t)(in ? r0 + row : 0) * D + slot * (D / kSlots));
 #pragma unroll
       for (int c = 0; c < WORDS; c += 16) {
         uint32_t v[16];
@@ -457,14 +470,14 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const uint4 t4 = in ? __ldg(src + ((c + q) >> 2)) : make_uint4(0u, 0u, 0u, 0u);
           v[q] = t4.x; v[q + 1] = t4.y; v[q + 2] = t4.z; v[q + 3] = t4.w;
         }
-        tmem_st16(tmem_a + lane_base + cg * WORDS + c, v);
+        tmem_st16(tmem_a + lane_base + slot * WORDS + c, v);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_a);
     }
-    for (int j = 0; j < n_ct; ++j) {
+    for (int j = grp; j < n_ct; j += GROUPS) {   // two warp sets: this one owns every GROUPS-th column tile (= one S buffer)
       const uint32_t b = j % NBUF, s = j % NSTAGE;
       if (COLCONST) mbar_wait(&bar_full[s], (j / NSTAGE) & 1);  // s_cc[s] was written by the async proxy
       mbar_wait(&bar_sfull[b], (j / NBUF) & 1);
@@ -548,19 +561,19 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     mbar_wait(&bar_acc, 0);
     tc_fence_after();
     const int r = r0 + row;
-    constexpr int DW = D / kBwdCG;
-    const uint32_t abase = tmem_acc + lane_base + cg * DW;
+    constexpr int DW = D / kSlots;
+    const uint32_t abase = tmem_acc + lane_base + slot * DW;
     if (COLCONST) {
       float* o = reinterpret_cast<float*>(out);
       // biased head: G carries a per-item factor e^{b_i}; it was left out of the loop and is applied to the row here
       const float rs = (HAS_BIAS && r < n_items) ? __expf(bias[r]) : 1.f;
       if (HAS_BIAS) {
-        s_gsum[cg][row] = gsum;
-        asm volatile("bar.sync 1, %0;" ::"r"(kBwdEpiWarps * 32) : "memory");  // epilogue warps only
-        if (cg == 0 && r < n_items) {
+        s_gsum[slot][row] = gsum;
+        asm volatile("bar.sync 1, %0;" ::"r"(kEW * 32) : "memory");  // epilogue warps only
+        if (slot == 0 && r < n_items) {
           float tot = 0.f;
 #pragma unroll
-          for (int k = 0; k < kBwdCG; ++k) tot += s_gsum[k][row];
+          for (int k = 0; k < kSlots; ++k) tot += s_gsum[k][row];
           d_bias[r] = tot * rs;
         }
       }
@@ -570,7 +583,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tmem_ld16(abase + c, a16);
         tmem_ld_wait();
         if (r < n_items) {
-          float4* dst = reinterpret_cast<float4*>(o + (size_t)r * D + cg * DW + c);
+          float4* dst = reinterpret_cast<float4*>(o + (size_t)r * D + slot * DW + c);
 #pragma unroll
           for (int q = 0; q < 16; q += 4)
             dst[q >> 2] = make_float4(__uint_as_float(a16[q]) * rs, __uint_as_float(a16[q + 1]) * rs,
@@ -580,14 +593,14 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     } else if (FUSED) {
       // partial (this column split) un-normalised gradient and row sums; ce_fused_finalize_kernel reduces the splits
       float* o = reinterpret_cast<float*>(out) + (size_t)split * capacity * D;
-      if (r < n_valid) zpart[((size_t)split * kBwdCG + cg) * capacity + r] = zacc;
+      if (r < n_valid) zpart[((size_t)split * kSlots + slot) * capacity + r] = zacc;
 #pragma unroll 1
       for (int c = 0; c < DW; c += 16) {
         uint32_t a16[16];
         tmem_ld16(abase + c, a16);
         tmem_ld_wait();
         if (r < n_valid) {
-          float4* dst = reinterpret_cast<float4*>(o + (size_t)r * D + cg * DW + c);
+          float4* dst = reinterpret_cast<float4*>(o + (size_t)r * D + slot * DW + c);
 #pragma unroll
           for (int q = 0; q < 16; q += 4)
             dst[q >> 2] = make_float4(__uint_as_float(a16[q]), __uint_as_float(a16[q + 1]), __uint_as_float(a16[q + 2]),
@@ -604,8 +617,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tmem_ld16(abase + c, a16);
         tmem_ld_wait();
         if (r < n_valid) {
-          const uint4* ey = reinterpret_cast<const uint4*>(table + (size_t)y * D + cg * DW + c);
-          uint4* dst = reinterpret_cast<uint4*>(o + (size_t)r * D + cg * DW + c);
+          const uint4* ey = reinterpret_cast<const uint4*>(table + (size_t)y * D + slot * DW + c);
+          uint4* dst = reinterpret_cast<uint4*>(o + (size_t)r * D + slot * DW + c);
 #pragma unroll
           for (int q = 0; q < 16; q += 8) {
             const uint4 e = ey[q >> 3];
@@ -717,7 +730,7 @@ __global__ void ce_fused_finalize_kernel(const float* __restrict__ part_dh, cons
                                          const __nv_bfloat16* __restrict__ hc, const __nv_bfloat16* __restrict__ table,
                                          const int32_t* __restrict__ labels, const float* __restrict__ bias,
                                          const int32_t* __restrict__ n_valid_ptr, const int32_t* __restrict__ safe_flag,
-                                         int n_splits, int capacity, int d, float* __restrict__ lse_out,
+                                         int n_splits, int z_slots, int capacity, int d, float* __restrict__ lse_out,
                                          float* __restrict__ cvec, __nv_bfloat16* __restrict__ d_hc,
                                          float* __restrict__ block_sums, unsigned int* __restrict__ ticket,
                                          float* __restrict__ loss_out) {
@@ -733,7 +746,7 @@ __global__ void ce_fused_finalize_kernel(const float* __restrict__ part_dh, cons
       continue;
     }
     float z = 0.f;
-    for (int i = lane; i < n_splits * kBwdCG; i += 32) z += zpart[(size_t)i * capacity + t];
+    for (int i = lane; i < n_splits * z_slots; i += 32) z += zpart[(size_t)i * capacity + t];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
     const int y = labels[t];
@@ -862,7 +875,7 @@ static const int kMaxSplitsFwd = 32;   // two-pass forward: only (max, sum) pair
 static const int kWideSplitK = 16;     // d = 512 backward: split-K partials of the dH GEMM
 
 static size_t ce_ws_base_bytes(int cap, int d) {
-  return (size_t)cap * kMaxSplitsFwd * 2 * sizeof(float2) + 4096 + 64 + (size_t)kMaxSplits * kBwdCG * cap * 4 +
+  return (size_t)cap * kMaxSplitsFwd * 2 * sizeof(float2) + 4096 + 64 + (size_t)kMaxSplits * kBwdCG * kCeMaxGroups * cap * 4 +
          (d <= 256 ? (size_t)kMaxSplits * cap * d * 4 : 0) + 256;
 }
 static size_t ce_ws_bytes(int cap, int n_items, int d) {
@@ -886,7 +899,7 @@ static CeWs ce_ws(void* workspace, int cap, int d) {
   r.flag = reinterpret_cast<int32_t*>(r.ticket + 4);
   w += 64;
   r.zpart = reinterpret_cast<float*>(w);
-  w += (size_t)kMaxSplits * kBwdCG * cap * 4;
+  w += (size_t)kMaxSplits * kBwdCG * kCeMaxGroups * cap * 4;
   r.part_dh = reinterpret_cast<float*>(w);
   (void)d;
   return r;
@@ -909,6 +922,14 @@ static int launch_ce_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const i
   return RP_OK;
 }
 
+// two epilogue warp sets: d = 128 with two S buffers (the row-tile copy and the accumulator read-out split 4 ways there)
+constexpr int ce_groups_of(int kch, int nbuf) { return (RP_CE_GROUPS == 2 && kch == 2 && nbuf == 2) ? 2 : 1; }
+static int ce_z_slots(int d) {
+  constexpr bool a_tmem = (RP_CE_A_TMEM != 0) && (RP_CE_ORDER == 1);
+  const int nbuf = (d <= 128 && a_tmem) ? 2 : ((RP_CE_NBUF3 && d <= 128) ? 3 : 2);
+  return kBwdCG * ce_groups_of(d / 64, nbuf);
+}
+
 template <int KCH, int NSTAGE, int MODE>
 static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const void* a_rows, const float* cvec,
                          const int32_t* labels,
@@ -924,10 +945,11 @@ static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const v
   constexpr bool INORDER = (RP_CE_ORDER == 1) && NBUF == 2;
   const int smem = ((A_TMEM ? 0 : 1) + NSTAGE + (A_TMEM ? 1 : 0)) * KCH * kChunk + 1024;
   // the biased head (BERT4Rec) is a separate instantiation: its per-column adds / row sums cost an instruction per logit
-  auto kern = bias ? ce_bwd_kernel<KCH, NSTAGE + (A_TMEM ? 1 : 0), MODE, NBUF, A_TMEM, INORDER, true>
-                   : ce_bwd_kernel<KCH, NSTAGE + (A_TMEM ? 1 : 0), MODE, NBUF, A_TMEM, INORDER, false>;
+  constexpr int GROUPS = ce_groups_of(KCH, NBUF);
+  auto kern = bias ? ce_bwd_kernel<KCH, NSTAGE + (A_TMEM ? 1 : 0), MODE, NBUF, A_TMEM, INORDER, true, GROUPS>
+                   : ce_bwd_kernel<KCH, NSTAGE + (A_TMEM ? 1 : 0), MODE, NBUF, A_TMEM, INORDER, false, GROUPS>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, kBwdThreads, smem, stream>>>(tmA, tmB, reinterpret_cast<const __nv_bfloat16*>(a_rows), cvec, labels,
+  kern<<<grid, 64 + GROUPS * kBwdEpiWarps * 32, smem, stream>>>(tmA, tmB, reinterpret_cast<const __nv_bfloat16*>(a_rows), cvec, labels,
                                             reinterpret_cast<const __nv_bfloat16*>(table), loss_inv,
                                          n_valid, n_items, bias, d_bias, out, safe_flag, run_if_safe, n_splits, capacity, zpart);
   RP_LAUNCH_CHECK();
@@ -996,7 +1018,7 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, 
     if (rc != RP_OK) return rc;
     ce_fused_finalize_kernel<<<blocks, 256, 0, stream>>>(ws.part_dh, ws.zpart, reinterpret_cast<const __nv_bfloat16*>(hc),
                                                          reinterpret_cast<const __nv_bfloat16*>(table), labels, bias, n_valid,
-                                                         ws.flag, P, capacity, d, lse, cvec,
+                                                         ws.flag, P, ce_z_slots(d), capacity, d, lse, cvec,
                                                          reinterpret_cast<__nv_bfloat16*>(d_hc), ws.block_sums, ws.ticket, loss_out);
     RP_LAUNCH_CHECK();
     skip = ws.flag;

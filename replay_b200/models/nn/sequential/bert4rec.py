@@ -109,7 +109,7 @@ class _BertCore(SasRecCore):
         self._set_lr(eng, lr)
         eng.set_batch(ids, pad_mask, token_mask, labels)
         if isinstance(all_reduce, str):
-            all_reduce = dist_grad_all_reduce()
+            return self._graph_trainer(eng).run()[0]
         return eng.train_step(all_reduce, betas=self.adam_betas)[0]
 
     @torch.no_grad()

@@ -12,14 +12,19 @@ from .engine import SasRecEngine
 
 
 class Trainer:
-    def __init__(self, engine: SasRecEngine, use_graph: bool = True):
+    def __init__(self, engine: SasRecEngine, use_graph: bool = True, betas=(0.9, 0.98)):
         self.engine = engine
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.use_graph = use_graph
+        self.betas = tuple(betas)
+        self.launches_per_step = None
+        self.invalidate()
+
+    def invalidate(self):
+        """Drop the captured graphs (the engine's workspace was re-allocated, the loss head or the Adam betas changed)."""
         self._g_fb = None
         self._g_opt = None
         self._warm = 0
-        self.launches_per_step = None
 
     # gradient exchange: one flat fp32 bucket (the CE backward finishes the big item-table gradient first)
     def _all_reduce(self):
@@ -33,24 +38,31 @@ class Trainer:
         e.forward_train()
         e.backward()
 
+    def _opt(self, scale):
+        self.engine.optimizer_step(grad_scale=scale, beta1=self.betas[0], beta2=self.betas[1])
+
     def step(self, *batch):
         """One optimisation step on this rank's shard; ``batch`` is what the engine's ``set_batch`` takes (SASRec: ids,
         pad_mask, labels, target_mask; BERT4Rec: ids, pad_mask, token_mask, labels).  Returns the device loss tensor fp32 [2]
         (mean CE, 1/n_valid)."""
+        self.engine.set_batch(*batch)
+        return self.run()
+
+    def run(self):
+        """The step on the batch already staged in the engine's static input buffers (``set_batch`` / ``set_negatives``)."""
         e = self.engine
-        e.set_batch(*batch)
         if not self.use_graph:
             c0 = e.lib.count
             self._fwd_bwd()
-            e.optimizer_step(self._all_reduce())
+            self._opt(self._all_reduce())
             self.launches_per_step = e.lib.count - c0
             return e.ce.loss
         if self._g_fb is None:
-            if self._warm < 2:  # eager warm-up (lazy module load, func attributes) before capture
+            if self._warm < 2:  # eager warm-up (lazy module load, func attributes, workspaces) before capture
                 self._warm += 1
                 c0 = e.lib.count
                 self._fwd_bwd()
-                e.optimizer_step(self._all_reduce())
+                self._opt(self._all_reduce())
                 self.launches_per_step = e.lib.count - c0
                 return e.ce.loss
             torch.cuda.synchronize()
@@ -59,12 +71,8 @@ class Trainer:
                 self._fwd_bwd()
             self._g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._g_opt):
-                e.optimizer_step(1.0 / self.world)
+                self._opt(1.0 / self.world)
             # capture does not execute: run the captured work once so this call is a real step
-            self._g_fb.replay()
-            self._all_reduce()
-            self._g_opt.replay()
-            return e.ce.loss
         self._g_fb.replay()
         self._all_reduce()
         self._g_opt.replay()

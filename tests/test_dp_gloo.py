@@ -39,7 +39,7 @@ class FakeEngine:
     def backward(self):
         self.g32 = torch.arange(8, dtype=torch.float32) * (self.rank + 1)
 
-    def optimizer_step(self, grad_scale=1.0):
+    def optimizer_step(self, grad_scale=1.0, **kw):
         self.seen_scale, self.seen_grad = grad_scale, self.g32.clone()
 
 

@@ -299,6 +299,37 @@ __global__ void ce_finalize_kernel(const float2* __restrict__ part, const __nv_b
   }
 }
 
+// Direct completion of the fused pass when the catalog is NOT split over CTAs (n_splits == 1: the CTA has seen every item of
+// its 128 tokens): lse, exponent offsets, per-row loss terms and the final bf16 dH are written from the accumulator itself, so
+// the partial-gradient round trip through HBM (2 x T_v x d fp32) and ce_fused_finalize_kernel disappear.
+struct CeDirect {
+  __nv_bfloat16* d_hc;   // null: column-split mode (partials + ce_fused_finalize_kernel)
+  float* lse;
+  float* cvec;
+  float* row_loss;       // [capacity] lse_t - z_{t, y_t}; summed in a fixed order by ce_loss_reduce_kernel
+};
+
+// loss = mean over the valid targets of row_loss, deterministic (fixed partition + tree); also publishes 1 / T_v
+__global__ void __launch_bounds__(1024) ce_loss_reduce_kernel(const float* __restrict__ row_loss, const int32_t* __restrict__ n_valid_ptr,
+                                                              const int32_t* __restrict__ safe_flag, float* __restrict__ loss_out) {
+  if (safe_flag && *safe_flag == 0) return;  // the two-pass fallback computes the loss itself
+  __shared__ float red[1024];
+  const int n_valid = *n_valid_ptr;
+  float a = 0.f;
+  for (int i = threadIdx.x; i < n_valid; i += 1024) a += row_loss[i];
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float inv_n = n_valid > 0 ? 1.f / (float)n_valid : 0.f;
+    loss_out[0] = red[0] * inv_n;
+    loss_out[1] = inv_n;
+  }
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // backward (both directions share one kernel)
 //   COLCONST = false : rows = tokens (A = Hc tile), columns = items  -> acc = dHc tile [128, d]
@@ -317,7 +348,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               const __nv_bfloat16* __restrict__ table, const float* __restrict__ loss_inv /* [1] = 1/T_v */,
               const int32_t* __restrict__ n_valid_ptr, int n_items, const float* __restrict__ bias,
               float* __restrict__ d_bias, void* __restrict__ out, const int32_t* __restrict__ safe_flag, int run_if_safe,
-              int n_splits, int capacity, float* __restrict__ zpart) {
+              int n_splits, int capacity, float* __restrict__ zpart, const CeDirect direct) {
   constexpr bool COLCONST = (MODE == 1);
   constexpr bool FUSED = (MODE == 2);
   constexpr int kW = kT / kBwdCG;  // S columns owned by one epilogue warp (its bf16 G lands in the first kW/2 of them)
@@ -335,6 +366,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint8_t* sB = smem + (A_TMEM ? 0 : kStage);
   __shared__ __align__(16) float s_cc[NSTAGE][kT];
   __shared__ float s_gsum[kSlots][kT];
+  __shared__ float s_dot[FUSED ? kSlots : 1][kT];
   __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_sfull[NBUF], bar_sfree[NBUF], bar_pfull[NBUF], bar_acc;
   __shared__ uint32_t tmem_slot;
 
@@ -588,6 +620,61 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           for (int q = 0; q < 16; q += 4)
             dst[q >> 2] = make_float4(__uint_as_float(a16[q]) * rs, __uint_as_float(a16[q + 1]) * rs,
                                       __uint_as_float(a16[q + 2]) * rs, __uint_as_float(a16[q + 3]) * rs);
+        }
+      }
+    } else if (FUSED && direct.d_hc != nullptr) {
+      // ---- no column splits: finish here.  z_t = sum of the four slots' row sums; dH = acc / (z T_v) - E[y] / T_v
+      s_gsum[slot][row] = zacc;
+      asm volatile("bar.sync 1, %0;" ::"r"(kEW * 32) : "memory");
+      float z = 0.f;
+#pragma unroll
+      for (int k = 0; k < kSlots; ++k) z += s_gsum[k][row];
+      const bool live = r < n_valid;
+      const float inv_n = n_valid > 0 ? 1.f / (float)n_valid : 0.f;
+      const float scale = live ? inv_n / z : 0.f;
+      const int y = live ? labels[r] : 0;
+      float dot = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < DW; c += 16) {
+        uint32_t a16[16];
+        tmem_ld16(abase + c, a16);
+        tmem_ld_wait();
+        if (live) {
+          const uint4* ey = reinterpret_cast<const uint4*>(table + (size_t)y * D + slot * DW + c);
+          const uint4* hr = reinterpret_cast<const uint4*>(a_rows + (size_t)r * D + slot * DW + c);
+          uint4* dst = reinterpret_cast<uint4*>(direct.d_hc + (size_t)r * D + slot * DW + c);
+#pragma unroll
+          for (int q = 0; q < 16; q += 8) {
+            const uint4 e = __ldg(ey + (q >> 3)), hh = __ldg(hr + (q >> 3));
+            const __nv_bfloat162* e2 = reinterpret_cast<const __nv_bfloat162*>(&e);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hh);
+            uint4 w;
+            uint32_t* w32 = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+              const float2 ef = __bfloat1622float2(e2[pp]), hf = __bfloat1622float2(h2[pp]);
+              dot = fmaf(hf.x, ef.x, fmaf(hf.y, ef.y, dot));
+              w32[pp] = pack_bf16(__uint_as_float(a16[q + 2 * pp]) * scale - inv_n * ef.x,
+                                  __uint_as_float(a16[q + 2 * pp + 1]) * scale - inv_n * ef.y);
+            }
+            dst[q >> 3] = w;
+          }
+        }
+      }
+      s_dot[slot][row] = dot;
+      asm volatile("bar.sync 1, %0;" ::"r"(kEW * 32) : "memory");
+      if (slot == 0 && r < capacity) {
+        if (live) {
+          float zy = 0.f;
+#pragma unroll
+          for (int k = 0; k < kSlots; ++k) zy += s_dot[k][row];
+          if (HAS_BIAS) zy += bias[y];
+          const float lse2 = log2f(z);
+          direct.lse[r] = lse2 * kLn2;
+          direct.cvec[r] = -lse2 + (n_valid > 0 ? -log2f((float)n_valid) : 0.f);
+          direct.row_loss[r] = lse2 * kLn2 - zy;
+        } else {
+          direct.cvec[r] = -INFINITY;  // rows beyond T_v contribute nothing to the dE pass
         }
       }
     } else if (FUSED) {
@@ -935,7 +1022,7 @@ static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const v
                          const int32_t* labels,
                          const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, const float* bias,
                          float* d_bias, void* out, int grid, const int32_t* safe_flag, int run_if_safe, int n_splits,
-                         int capacity, float* zpart, cudaStream_t stream) {
+                         int capacity, float* zpart, cudaStream_t stream, const CeDirect& direct = CeDirect{nullptr, nullptr, nullptr, nullptr}) {
   // d <= 128: the row tile goes to TMEM (2 S buffers + accumulator + operand = 448 columns) and its 32 KB of smem become
   // an extra pipeline stage; d = 256: row tile in smem, 2 S buffers + accumulator = 512 columns
   // RP_CE_ORDER 1: both directions keep the row tile in TMEM (two S buffers suffice once the issue order no longer drains the
@@ -951,7 +1038,7 @@ static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const v
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, 64 + GROUPS * kBwdEpiWarps * 32, smem, stream>>>(tmA, tmB, reinterpret_cast<const __nv_bfloat16*>(a_rows), cvec, labels,
                                             reinterpret_cast<const __nv_bfloat16*>(table), loss_inv,
-                                         n_valid, n_items, bias, d_bias, out, safe_flag, run_if_safe, n_splits, capacity, zpart);
+                                         n_valid, n_items, bias, d_bias, out, safe_flag, run_if_safe, n_splits, capacity, zpart, direct);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }
@@ -961,17 +1048,17 @@ static int dispatch_ce_bwd(int d, const CUtensorMap& tmA, const CUtensorMap& tmB
                            const int32_t* labels,
                            const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, const float* bias,
                            float* d_bias, void* out, int grid, const int32_t* safe_flag, int run_if_safe, int n_splits,
-                           int capacity, float* zpart, cudaStream_t stream) {
+                           int capacity, float* zpart, cudaStream_t stream, const CeDirect& direct = CeDirect{nullptr, nullptr, nullptr, nullptr}) {
   switch (d) {
     case 64:
       return launch_ce_bwd<1, 6, MODE>(tmA, tmB, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
-                                       safe_flag, run_if_safe, n_splits, capacity, zpart, stream);
+                                       safe_flag, run_if_safe, n_splits, capacity, zpart, stream, direct);
     case 128:
       return launch_ce_bwd<2, RP_CE_NSTAGE_D128, MODE>(tmA, tmB, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
-                                       safe_flag, run_if_safe, n_splits, capacity, zpart, stream);
+                                       safe_flag, run_if_safe, n_splits, capacity, zpart, stream, direct);
     case 256:
       return launch_ce_bwd<4, 2, MODE>(tmA, tmB, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
-                                       safe_flag, run_if_safe, n_splits, capacity, zpart, stream);
+                                       safe_flag, run_if_safe, n_splits, capacity, zpart, stream, direct);
     default:
       return RP_ESHAPE;
   }
@@ -1013,9 +1100,20 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, 
     ce_flag_kernel<<<1, 1, 0, stream>>>(ws.bound, ws.flag);
     RP_LAUNCH_CHECK();
     const int P = pick_splits(hint_tiles, n_item_tiles);
+    CeDirect direct{nullptr, nullptr, nullptr, nullptr};
+    if (P == 1) {  // every CTA sees the whole catalog: lse / dH / loss terms come straight out of the fused kernel
+      direct.d_hc = reinterpret_cast<__nv_bfloat16*>(d_hc);
+      direct.lse = lse;
+      direct.cvec = cvec;
+      direct.row_loss = ws.zpart;  // the row-sum partials are not needed in this mode: reuse their buffer
+    }
     rc = dispatch_ce_bwd<2>(d, tmA, tmB, hc, cvec, labels, table, loss_out + 1, n_valid, n_items, bias, nullptr, ws.part_dh,
-                            n_tok_tiles * P, ws.flag, 1, P, capacity, ws.zpart, stream);
+                            n_tok_tiles * P, ws.flag, 1, P, capacity, ws.zpart, stream, direct);
     if (rc != RP_OK) return rc;
+    if (P == 1) {
+      ce_loss_reduce_kernel<<<1, 1024, 0, stream>>>(ws.zpart, n_valid, ws.flag, loss_out);
+      RP_LAUNCH_CHECK();
+    } else
     ce_fused_finalize_kernel<<<blocks, 256, 0, stream>>>(ws.part_dh, ws.zpart, reinterpret_cast<const __nv_bfloat16*>(hc),
                                                          reinterpret_cast<const __nv_bfloat16*>(table), labels, bias, n_valid,
                                                          ws.flag, P, ce_z_slots(d), capacity, d, lse, cvec,

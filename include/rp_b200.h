@@ -157,6 +157,8 @@ typedef struct rp_attn_desc {
   void* p_save; float* inv_sum;
   float drop_p; unsigned long long seed, drop_off; const unsigned long long* seed_ptr;
   float* m_save;  /* optional fp32 [B*H, Lp]: row max in exp2 units, input of rp_attn_bwd */
+  float scale;    /* softmax scale; 0 -> 1/sqrt(head_dim).  Padded head slots (true head_dim 32 / 48 / 50 inside a 64-wide
+                     slot) pass 1/sqrt(true head_dim) */
 } rp_attn_desc;
 int rp_attn_fwd(const rp_attn_desc* a, void* stream);
 
@@ -180,6 +182,7 @@ typedef struct rp_attn_bwd_desc {
   void* dk; int ld_dk, dk_c0;
   void* dv; int ld_dv, dv_c0;
   float drop_p; unsigned long long seed, drop_off; const unsigned long long* seed_ptr;
+  float scale;    /* as in rp_attn_desc */
 } rp_attn_bwd_desc;
 int rp_attn_bwd(const rp_attn_bwd_desc* a, void* stream);
 
@@ -193,7 +196,8 @@ int rp_attn_softmax_bwd(void* p_save, void* dpd, const float* inv_sum, int BH, i
  * (SasRec.forward_inference keeps only hidden[:, -1, :], nn/sequential/sasrec/model.py:301; legacy model.py:157).
  * q, out: compact bf16 [B, H*head_dim]; k, v: token-major 2-D arrays (rows b*L + j, head h at columns x_c0 + h*head_dim). */
 int rp_attn_last(const void* q, const void* k, const void* v, long long ldk, long long ldv, int k_c0, int v_c0,
-                 const uint8_t* pad_mask, int B, int H, int L, int head_dim, int mask_pad_keys, void* out, void* stream);
+                 const uint8_t* pad_mask, int B, int H, int L, int head_dim, int mask_pad_keys, void* out, float scale /* 0: 1/sqrt(head_dim) */,
+                 void* stream);
 
 /* int64 ids / bool masks of one [B, L] batch -> int32 ids (pads -> pad_id) and the compacted valid-target list
  * (replaces the masked_fill / boolean-index preparation in nn/loss/ce.py:70-80 and models/.../sasrec/model.py:236-239).
@@ -214,11 +218,19 @@ int rp_embed_bwd(const void* dx, const int32_t* ids, const uint8_t* pad_mask, in
 /* torch.nn.LayerNorm forward / backward (transformer.py:47-49,60-62 eps 1e-8; model.py:248 eps 1e-5).  With `gather`
  * output row r reads input row gather[r] and only *n_rows_dev rows exist (valid-target compaction); the backward then
  * scatters dx to those rows.  add_to (optional, bf16 [*, d]) is added to dx (residual-branch gradient). */
+/* PADDED FEATURE SLOTS (`hd_valid`, 0 = none): the reference's default shapes are not multiples of the 64-wide tensor-core
+ * feature tiles (SasRec.from_params: embedding_dim 192 / 4 heads = head_dim 48, nn/sequential/sasrec/model.py:199-253; legacy
+ * hidden_size 50, sasrec/lightning.py:30-47; examples: d = 64 / 2 heads = 32).  Such a model is stored with every head in its
+ * own slot of 64 columns (128 for head_dim in (64, 128]) whose first hd_valid columns are the real features and whose padded
+ * columns are ZERO in every activation, weight, bias and gradient (zero weights keep them zero through every GEMM, the
+ * optimizer never moves a parameter whose gradient is zero).  The only operator that is not blind to the padding is LayerNorm:
+ * its statistics run over the d_true = (d / slot) * hd_valid real features and its backward sends no gradient into padded
+ * inputs - every entry point that contains a LayerNorm takes `hd_valid`; the attention takes the true softmax scale. */
 int rp_layernorm_fwd(const void* x, const float* w, const float* b, float eps, int n_rows, int d, const int32_t* n_rows_dev,
-                     const int32_t* gather, void* y, float* mean, float* rstd, void* stream);
+                     const int32_t* gather, void* y, float* mean, float* rstd, int hd_valid, void* stream);
 int rp_layernorm_bwd(const void* dy, const void* x, const float* w, const float* mean, const float* rstd, int n_rows, int d,
                      const int32_t* n_rows_dev, const int32_t* gather, const void* add_to, void* dx, float* dw, float* db,
-                     void* stream);
+                     int hd_valid, void* stream);
 
 /* out = in * regenerated dropout mask / keep (and optional row mask); db[c] += column sums of a bf16 [rows, cols] array. */
 int rp_dropout_bwd(const void* in, void* out, long long rows, int cols, const uint8_t* rowmask, float drop_p,
@@ -252,7 +264,7 @@ int rp_ffn_fused(const void* y, const void* w1, const float* b1, const void* w2,
  *   replaces (eval)  replay/nn/sequential/sasrec/transformer.py:99-110 ; replay/models/nn/sequential/sasrec/model.py:435-441 */
 int rp_post_attn_fused(const void* o, const void* q_in, const void* wo, const float* bo, const float* ln_w, const float* ln_b,
                        float eps, const void* w1, const float* b1, const void* w2, const float* b2, const uint8_t* rowmask, int T,
-                       int d, void* out, void* stream);
+                       int d, void* out, int hd_valid, void* stream);
 
 /* Training forward of everything after the attention of one SASRec block in one pass over the tokens:
  *   h = o Wo^T + bo + q_in ; y = LN(h) ; u = dropout1(relu(y W1^T + b1)) ; out = (y + dropout2(u W2^T + b2)) [* rowmask]
@@ -266,7 +278,7 @@ int rp_post_attn_train(const void* o, const void* q_in, const void* wo, const fl
                        float eps, const void* w1, const float* b1, const void* w2, const float* b2, const uint8_t* rowmask, int T,
                        int d, float drop_p, unsigned long long seed, unsigned long long drop_off1, unsigned long long drop_off2,
                        const unsigned long long* seed_ptr, void* h_save, void* y_save, void* u_save, float* mean_out,
-                       float* rstd_out, void* out, void* stream);
+                       float* rstd_out, void* out, int hd_valid, void* stream);
 
 /* Backward of rp_post_attn_train in one pass over the tokens.  Given dz = d loss / d out:
  *   dzm = dz [* rowmask] ;  d_t = dropout2'(dzm) ;  du = (d_t W2) * [u != 0] / keep ;  dy = du W1 + dzm ;
@@ -278,7 +290,7 @@ int rp_post_attn_train(const void* o, const void* q_in, const void* wo, const fl
 int rp_post_attn_bwd(const void* dz, const void* u, const void* h, const float* mean, const float* rstd, const float* ln_w,
                      const void* w2, const void* w1, const void* wo, const uint8_t* rowmask, int T, int d, float drop_p,
                      unsigned long long seed, unsigned long long drop_off2, const unsigned long long* seed_ptr, void* d_t, void* du,
-                     void* dh, void* d_o, float* dln_w, float* dln_b, void* stream);
+                     void* dh, void* d_o, float* dln_w, float* dln_b, int hd_valid, void* stream);
 
 /* Everything BEFORE the attention of one SASRec block in one pass over the tokens (training and inference):
  *   q_in = LayerNorm(x) ;  Q = q_in Wq^T + bq ;  [K | V] = x [Wk | Wv]^T + [bk | bv]      (K, V from the un-normalised x)
@@ -286,11 +298,12 @@ int rp_post_attn_bwd(const void* dz, const void* u, const void* h, const float* 
  * launches read x / q_in three times).  w_in bf16 [3d, d] = packed in_proj_weight, b_in fp32 [3d]; d in {64,128}.
  *   replaces  replay/nn/sequential/sasrec/transformer.py:99-106 ; replay/models/nn/sequential/sasrec/model.py:434-435 */
 int rp_ln_qkv_fused(const void* x, const float* ln_w, const float* ln_b, float eps, const void* w_in, const float* b_in, int T,
-                    int d, void* q_in, void* Q, void* KV, float* mean_out, float* rstd_out, void* stream);
+                    int d, void* q_in, void* Q, void* KV, float* mean_out, float* rstd_out, int hd_valid, void* stream);
 /* Its backward in one pass:  dq_in = dQ Wq + dh ;  t = LayerNorm-backward(dq_in; x, mean, rstd, ln_w) ;  dx = [dK | dV] Wkv + t.
  * dln_w / dln_b fp32 [d] are ACCUMULATED (one fp32 atomic per column and CTA).  dx may not alias an input; d in {64,128}. */
 int rp_pre_attn_bwd(const void* dQ, const void* dKV, const void* dh, const void* x, const float* mean, const float* rstd,
-                    const float* ln_w, const void* w_in, int T, int d, void* dx, float* dln_w, float* dln_b, void* stream);
+                    const float* ln_w, const void* w_in, int T, int d, void* dx, float* dln_w, float* dln_b, int hd_valid,
+                    void* stream);
 
 /* ALL weight and bias gradients of one transformer block in one launch (+ one deterministic reduction launch):
  *   dW_i[n_out_i, n_in_i] (+)= dY_i[T, n_out_i]^T . X_i[T, n_in_i] ;  db_i[n_out_i] (+)= column sums of dY_i      i < n_pairs <= 8

@@ -393,7 +393,21 @@ def gen_sampled_losses():
     print("wrote sampled_losses")
 
 
+def gen_reference_default_shapes():
+    """The reference's OWN default / example shapes, which are not multiples of the kernels' 64-wide feature slots:
+    SasRec.from_params defaults embedding_dim=192, num_heads=4 (head_dim 48; nn/sequential/sasrec/model.py:199-253), the legacy
+    module's hidden_size=50, head_count=1 (sasrec/lightning.py:30-47) and SURVEY's config 1 (d=64, H=2: head_dim 32)."""
+    gen_new_sasrec("d192h4", B=4, L=12, d=192, H=4, n_items=200, n_blocks=2, seed=21, with_adam=False)
+    gen_new_sasrec("d64h2", B=4, L=12, d=64, H=2, n_items=200, n_blocks=2, seed=22, with_adam=False)
+    gen_legacy_sasrec("d50h1", B=4, L=12, d=50, H=1, n_items=200, n_blocks=2, seed=23)
+
+
 if __name__ == "__main__":
+    import sys as _sys
+
+    if len(_sys.argv) > 1 and _sys.argv[1] == "defaults":
+        gen_reference_default_shapes()
+        raise SystemExit(0)
     # shapes respect the CUDA path's tile constraints: hidden in {64,128,256,512}, head_dim in {64,128}
     gen_new_sasrec("tiny", B=6, L=16, d=64, H=1, n_items=300, n_blocks=2, seed=11)
     gen_new_sasrec("small", B=8, L=50, d=128, H=2, n_items=600, n_blocks=2, seed=12, with_adam=False)
@@ -403,3 +417,4 @@ if __name__ == "__main__":
     gen_seen_filter_known_answers()
     gen_dataset_layout()
     gen_sampled_losses()
+    gen_reference_default_shapes()

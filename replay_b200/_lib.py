@@ -64,8 +64,8 @@ def lib():
     _sig(L.rp_prepare_batch, c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P])
     _sig(L.rp_embed_fwd, c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_float, U64, U64, P, P, P])
     _sig(L.rp_embed_bwd, c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_float, U64, U64, P, P, P, P])
-    _sig(L.rp_layernorm_fwd, c_int, [P, P, P, c_float, c_int, c_int, P, P, P, P, P, P])
-    _sig(L.rp_layernorm_bwd, c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P])
+    _sig(L.rp_layernorm_fwd, c_int, [P, P, P, c_float, c_int, c_int, P, P, P, P, P, c_int, P])
+    _sig(L.rp_layernorm_bwd, c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, c_int, P])
     _sig(L.rp_dropout_bwd, c_int, [P, P, LL, c_int, P, c_float, U64, U64, P, P])
     _sig(L.rp_colsum, c_int, [P, c_int, c_int, LL, P, P])
     _sig(L.rp_adam_step, c_int, [P, P, P, P, P, LL, P, P, c_float, c_float, c_float, c_float, P, c_int, P])
@@ -73,7 +73,7 @@ def lib():
     _sig(L.rp_counter_add, c_int, [P, U64, P])
     _sig(L.rp_bert_embed_fwd, c_int, [P, P, P, P, P, c_int, c_int, c_int, c_float, U64, U64, P, P, P])
     _sig(L.rp_bert_embed_bwd, c_int, [P, P, P, P, c_int, c_int, c_int, c_float, U64, U64, P, P, P, P, P])
-    _sig(L.rp_attn_last, c_int, [P, P, P, LL, LL, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P])
+    _sig(L.rp_attn_last, c_int, [P, P, P, LL, LL, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, c_float, P])
     _sig(L.rp_gather_rows, c_int, [P, P, c_int, P, c_int, P, c_int, P])
     _sig(L.rp_sampled_head_workspace, c_size_t, [c_int, c_int, c_int, c_int])
     _sig(L.rp_sampled_head_fwd, c_int, [P, P])
@@ -81,14 +81,14 @@ def lib():
     _sig(L.rp_selftest_mma_probe, c_int, [c_int, c_int, c_int, P, P])
     _sig(L.rp_selftest_tma_probe, c_int, [P, LL, c_int, c_int, c_int, c_int, c_int, P])
     _sig(L.rp_colsum_multi, c_int, [c_int, P, P, P, P, c_int, P])
-    _sig(L.rp_post_attn_fused, c_int, [P, P, P, P, P, P, c_float, P, P, P, P, P, c_int, c_int, P, P])
+    _sig(L.rp_post_attn_fused, c_int, [P, P, P, P, P, P, c_float, P, P, P, P, P, c_int, c_int, P, c_int, P])
     _sig(L.rp_ffn_fused, c_int, [P, P, P, P, P, P, c_int, c_int, P, P])
     _sig(L.rp_build_batch, c_int, [P, P, LL, P, P, c_int, c_int, c_int, c_int, c_float, P, U64, U64, P, P, P, P, P, P, P])
     _sig(L.rp_post_attn_train, c_int, [P, P, P, P, P, P, c_float, P, P, P, P, P, c_int, c_int, c_float, U64, U64, U64, P,
-                                       P, P, P, P, P, P, P])
-    _sig(L.rp_post_attn_bwd, c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_float, U64, U64, P, P, P, P, P, P, P, P])
-    _sig(L.rp_ln_qkv_fused, c_int, [P, P, P, c_float, P, P, c_int, c_int, P, P, P, P, P, P])
-    _sig(L.rp_pre_attn_bwd, c_int, [P, P, P, P, P, P, P, P, c_int, c_int, P, P, P, P])
+                                       P, P, P, P, P, P, c_int, P])
+    _sig(L.rp_post_attn_bwd, c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_float, U64, U64, P, P, P, P, P, P, P, c_int, P])
+    _sig(L.rp_ln_qkv_fused, c_int, [P, P, P, c_float, P, P, c_int, c_int, P, P, P, P, P, c_int, P])
+    _sig(L.rp_pre_attn_bwd, c_int, [P, P, P, P, P, P, P, P, c_int, c_int, P, P, P, c_int, P])
     _sig(L.rp_wgrad_group_workspace, c_size_t, [ctypes.POINTER(WgradPair), c_int])
     _sig(L.rp_wgrad_group, c_int, [ctypes.POINTER(WgradPair), c_int, c_int, c_int, P, c_size_t, P])
     for name, restype, argtypes in _EXTRA_SIGS:
@@ -159,6 +159,7 @@ class AttnDesc(ctypes.Structure):
         ("p_save", c_void_p), ("inv_sum", c_void_p),
         ("drop_p", c_float), ("seed", ctypes.c_ulonglong), ("drop_off", ctypes.c_ulonglong), ("seed_ptr", c_void_p),
         ("m_save", c_void_p),
+        ("scale", c_float),
     ]
 
 
@@ -179,6 +180,7 @@ class AttnBwdDesc(ctypes.Structure):
         ("dk", c_void_p), ("ld_dk", c_int), ("dk_c0", c_int),
         ("dv", c_void_p), ("ld_dv", c_int), ("dv_c0", c_int),
         ("drop_p", c_float), ("seed", ctypes.c_ulonglong), ("drop_off", ctypes.c_ulonglong), ("seed_ptr", c_void_p),
+        ("scale", c_float),
     ]
 
 

@@ -147,7 +147,8 @@ class SasRecCore(torch.nn.Module):
         return tr
 
     def _export(self) -> dict:
-        return {self._keymap[k]: self._to_ref(k, v.detach().clone()) for k, v in self.engine.params.items()}
+        # true (reference) shapes: the engine stores every head in its own 64/128-wide feature slot (EncoderConfig.dp)
+        return {self._keymap[k]: self._to_ref(k, self.engine.export_named(k)) for k in self.engine.params}
 
     def _to_ref(self, k, v):
         return v.unsqueeze(-1) if k.endswith((".w1", ".w2")) else v  # Conv1d weight [d, d, 1]
@@ -162,7 +163,7 @@ class SasRecCore(torch.nn.Module):
                 val = val.to(self.engine.dev, torch.float32)
                 if k.endswith((".w1", ".w2")) and val.dim() == 3:
                     val = val[:, :, 0]
-                self.engine.params[k].copy_(val)
+                self.engine.import_named(k, val)
         self._shadow_dirty = True
 
     # ---- reference-compatible checkpoints
@@ -263,6 +264,9 @@ class SasRecCore(torch.nn.Module):
         """Last-position hidden state, bf16 [B, d] (get_query_embeddings / forward_inference's last_hidden_state)."""
         eng = self._eval_engine(ids)
         eng.set_batch(ids, pad_mask)
+        return eng.unpad_features(self._last_hidden_padded(eng, ids))
+
+    def _last_hidden_padded(self, eng, ids):
         return eng.forward_last_hidden()[: ids.shape[0]]
 
     @torch.no_grad()
@@ -270,7 +274,7 @@ class SasRecCore(torch.nn.Module):
         eng = self._eval_engine(ids)
         eng.set_batch(ids, pad_mask)
         B, L = ids.shape
-        return eng.forward_hidden_all().view(eng.B, L, -1)[:B]
+        return eng.unpad_features(eng.forward_hidden_all().view(eng.B, L, -1)[:B])
 
     @torch.no_grad()
     def item_table(self, candidates=None) -> torch.Tensor:
@@ -280,10 +284,12 @@ class SasRecCore(torch.nn.Module):
     @torch.no_grad()
     def logits(self, ids, pad_mask, candidates=None) -> torch.Tensor:
         """Materialised fp32 scores [B, |I|] or [B, |C|] (API compatibility; the fused top-K path never builds them)."""
-        hq = self.query_embeddings(ids, pad_mask)
+        eng = self._eval_engine(ids)
+        eng.set_batch(ids, pad_mask)
+        hq = self._last_hidden_padded(eng, ids)   # padded width: pairs with the padded table
         tab = self.item_table(candidates)
         out = torch.empty(hq.shape[0], tab.shape[0], device=hq.device, dtype=torch.float32)
-        self.engine._gemm(hq, tab, out, hq.shape[0], tab.shape[0], self.cfg.d, out_mode=2)
+        self.engine._gemm(hq, tab, out, hq.shape[0], tab.shape[0], self.cfg.dp, out_mode=2)
         return out
 
     @torch.no_grad()
@@ -291,7 +297,9 @@ class SasRecCore(torch.nn.Module):
         """Fused predict: body -> last hidden -> scores -> seen filter -> top-k.  Returns (item ids int64 [B,k], scores)."""
         from . import ops
 
-        hq = self.query_embeddings(ids, pad_mask).contiguous()
+        eng = self._eval_engine(ids)
+        eng.set_batch(ids, pad_mask)
+        hq = self._last_hidden_padded(eng, ids).contiguous()
         n_items = self.cfg.n_items
         inv = None
         if candidates is not None:

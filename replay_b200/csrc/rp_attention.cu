@@ -429,12 +429,12 @@ using namespace rp;
 
 RP_API int rp_attn_last(const void* q, const void* k, const void* v, long long ldk, long long ldv, int k_c0, int v_c0,
                         const uint8_t* pad_mask, int B, int H, int L, int head_dim, int mask_pad_keys, void* out,
-                        void* stream_) {
+                        float scale_in, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!q || !k || !v || !pad_mask || !out) return RP_EINVAL;
   if (B <= 0 || H <= 0 || L <= 0 || L > 512) return RP_ESHAPE;
   if ((ldk & 7) || (ldv & 7) || (k_c0 & 7) || (v_c0 & 7)) return RP_EALIGN;
-  const float scale = 1.f / sqrtf((float)head_dim);
+  const float scale = scale_in > 0.f ? scale_in : 1.f / sqrtf((float)head_dim);
   const int blocks = (B * H + 7) / 8;
   const __nv_bfloat16 *qq = reinterpret_cast<const __nv_bfloat16*>(q), *kk = reinterpret_cast<const __nv_bfloat16*>(k),
                       *vv = reinterpret_cast<const __nv_bfloat16*>(v);
@@ -461,6 +461,7 @@ struct rp_attn_desc {
   void* p_save; float* inv_sum;
   float drop_p; unsigned long long seed, drop_off; const unsigned long long* seed_ptr;
   float* m_save;
+  float scale;
 };
 
 RP_API int rp_attn_fwd(const rp_attn_desc* a, void* stream_) {
@@ -473,7 +474,7 @@ RP_API int rp_attn_fwd(const rp_attn_desc* a, void* stream_) {
   AttnParams p;
   p.B = a->B; p.H = a->H; p.L = a->L; p.Lp = (a->L + 63) & ~63;
   p.causal = a->causal; p.mask_pad_keys = a->mask_pad_keys;
-  p.scale = 1.f / sqrtf((float)a->head_dim);
+  p.scale = a->scale > 0.f ? a->scale : 1.f / sqrtf((float)a->head_dim);
   p.pad_mask = a->pad_mask;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
   p.p_save = reinterpret_cast<__nv_bfloat16*>(a->p_save); p.inv_sum = a->inv_sum; p.m_save = a->m_save;

@@ -310,6 +310,7 @@ struct rp_attn_bwd_desc {
   void* dk; int ld_dk, dk_c0;
   void* dv; int ld_dv, dv_c0;
   float drop_p; unsigned long long seed, drop_off; const unsigned long long* seed_ptr;
+  float scale;
 };
 
 RP_API int rp_attn_bwd(const rp_attn_bwd_desc* a, void* stream_) {
@@ -324,7 +325,7 @@ RP_API int rp_attn_bwd(const rp_attn_bwd_desc* a, void* stream_) {
   AttnBwdParams p;
   p.B = a->B; p.H = a->H; p.L = a->L; p.Lp = (a->L + 63) & ~63;
   p.causal = a->causal; p.mask_pad_keys = a->mask_pad_keys;
-  p.scale = 1.f / sqrtf((float)a->head_dim);
+  p.scale = a->scale > 0.f ? a->scale : 1.f / sqrtf((float)a->head_dim);
   p.pad_mask = a->pad_mask;
   p.O = reinterpret_cast<const __nv_bfloat16*>(a->out); p.ldo = a->ldo;
   p.dO = reinterpret_cast<const __nv_bfloat16*>(a->d_out); p.ld_do = (int)a->ld_do;

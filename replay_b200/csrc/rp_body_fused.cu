@@ -24,6 +24,7 @@ struct LnQkvParams {
   const float* b_in;          // [3d] packed in_proj_bias (q | k | v)
   float eps;
   int T;
+  int hd_valid;               // > 0: padded feature slots (rp_sm100.cuh feat_valid): statistics over the real features only
   __nv_bfloat16* q_in;        // [T, d]   LayerNorm output (residual of the block, saved for the backward)
   __nv_bfloat16* Q;           // [T, d]
   __nv_bfloat16* KV;          // [T, 2d]
@@ -173,8 +174,9 @@ ln_qkv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       s_stat[half][row] = make_float2(sum, sq);
       asm volatile("bar.sync 1, %0;" ::"r"(kBfEpiWarps * 32) : "memory");
       const float2 sa = s_stat[0][row], sb = (D > 64) ? s_stat[1][row] : make_float2(0.f, 0.f);
-      const float mean = (sa.x + sb.x) * (1.f / D);
-      const float var = fmaxf((sa.y + sb.y) * (1.f / D) - mean * mean, 0.f);
+      const float inv_d = 1.f / (float)feat_count(D, p.hd_valid);   // padded columns are zero: sums need no mask
+      const float mean = (sa.x + sb.x) * inv_d;
+      const float var = fmaxf((sa.y + sb.y) * inv_d - mean * mean, 0.f);
       const float rstd = rsqrtf(var + p.eps);
       asm volatile("bar.sync 1, %0;" ::"r"(kBfEpiWarps * 32) : "memory");   // s_stat is rewritten by the next tile
       if (has_half) {
@@ -292,11 +294,13 @@ using namespace rp;
 // Outputs: q_in bf16 [T, d] = LayerNorm(x), Q bf16 [T, d] = q_in Wq^T + bq, KV bf16 [T, 2d] = x [Wk | Wv]^T + [bk | bv],
 // mean / rstd fp32 [T] (optional, both or none).  No output may alias x.  d in {64, 128}.
 RP_API int rp_ln_qkv_fused(const void* x, const float* ln_w, const float* ln_b, float eps, const void* w_in, const float* b_in,
-                           int T, int d, void* q_in, void* Q, void* KV, float* mean_out, float* rstd_out, void* stream_) {
+                           int T, int d, void* q_in, void* Q, void* KV, float* mean_out, float* rstd_out, int hd_valid,
+                           void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!x || !ln_w || !ln_b || !w_in || !b_in || !q_in || !Q || !KV || T <= 0) return RP_EINVAL;
   if ((mean_out == nullptr) != (rstd_out == nullptr)) return RP_EINVAL;
   if (d != 64 && d != 128) return RP_ESHAPE;
+  if (hd_valid < 0 || hd_valid > 128 || (hd_valid > 0 && d % (hd_valid <= 64 ? 64 : 128))) return RP_ESHAPE;
   if (q_in == x || Q == x || KV == x) return RP_EINVAL;
   CUtensorMap tmX, tmWq, tmWkv;
   int rc;
@@ -305,7 +309,7 @@ RP_API int rp_ln_qkv_fused(const void* x, const float* ln_w, const float* ln_b, 
   if ((rc = make_tmap_bf16(&tmWkv, reinterpret_cast<const __nv_bfloat16*>(w_in) + (size_t)d * d, 2 * d, d, d, 2 * d)) != RP_OK)
     return rc;
   LnQkvParams p;
-  p.ln_w = ln_w; p.ln_b = ln_b; p.b_in = b_in; p.eps = eps; p.T = T;
+  p.ln_w = ln_w; p.ln_b = ln_b; p.b_in = b_in; p.eps = eps; p.T = T; p.hd_valid = hd_valid;
   p.q_in = reinterpret_cast<__nv_bfloat16*>(q_in); p.Q = reinterpret_cast<__nv_bfloat16*>(Q);
   p.KV = reinterpret_cast<__nv_bfloat16*>(KV); p.mean_out = mean_out; p.rstd_out = rstd_out;
   return d == 64 ? launch_ln_qkv<1>(tmX, tmWq, tmWkv, p, stream) : launch_ln_qkv<2>(tmX, tmWq, tmWkv, p, stream);
@@ -332,6 +336,7 @@ struct PreAttnBwdParams {
   float* dln_w;               // [d] +=
   float* dln_b;               // [d] +=
   int T;
+  int hd_valid;               // > 0: padded feature slots - statistics over the real features, no gradient into padded inputs
 };
 
 // column sums over the 32 rows of a warp: on return lane l holds the sums of columns 2l and 2l+1 in v[0], v[1]
@@ -525,7 +530,8 @@ pre_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_const
       s_stat[half][row] = make_float2(s1, s2);
       asm volatile("bar.sync 1, %0;" ::"r"(kBfEpiWarps * 32) : "memory");
       const float2 sa = s_stat[0][row], sb = (D > 64) ? s_stat[1][row] : make_float2(0.f, 0.f);
-      const float m1 = (sa.x + sb.x) * (1.f / D), m2 = (sa.y + sb.y) * (1.f / D);
+      const float inv_d = 1.f / (float)feat_count(D, p.hd_valid);
+      const float m1 = (sa.x + sb.x) * inv_d, m2 = (sa.y + sb.y) * inv_d;
       asm volatile("bar.sync 1, %0;" ::"r"(kBfEpiWarps * 32) : "memory");
       if (has_half) {
         // dx = dKV Wkv (second accumulator, read 32 columns at a time) + LayerNorm-backward(dq)
@@ -548,8 +554,12 @@ pre_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_const
               for (int e = 0; e < 4; ++e) {
                 const int q = hh * 32 + c8 * 8 + 2 * e;
                 const float2 xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xp[q >> 1]));
-                const float t0 = rstd * (dq[q] * s_lnw[c0 + q] - m1 - fmaf(xf.x, rs_ok, nmr) * m2);
-                const float t1 = rstd * (dq[q + 1] * s_lnw[c0 + q + 1] - m1 - fmaf(xf.y, rs_ok, nmr) * m2);
+                float t0 = rstd * (dq[q] * s_lnw[c0 + q] - m1 - fmaf(xf.x, rs_ok, nmr) * m2);
+                float t1 = rstd * (dq[q + 1] * s_lnw[c0 + q + 1] - m1 - fmaf(xf.y, rs_ok, nmr) * m2);
+                if (p.hd_valid > 0) {   // padded inputs of the LayerNorm do not exist: no gradient
+                  if (!feat_valid(c0 + q, p.hd_valid)) t0 = 0.f;
+                  if (!feat_valid(c0 + q + 1, p.hd_valid)) t1 = 0.f;
+                }
                 w32[e] = pack_bf16(t0 + __uint_as_float(r2[q - hh * 32]), t1 + __uint_as_float(r2[q + 1 - hh * 32]));
               }
               o[c8] = make_uint4(w32[0], w32[1], w32[2], w32[3]);
@@ -617,10 +627,11 @@ static int launch_pre_attn_bwd(const CUtensorMap& tmDQ, const CUtensorMap& tmDKV
 // ACCUMULATED (+=, fp32 atomics: one per column and CTA).  d in {64, 128}.
 RP_API int rp_pre_attn_bwd(const void* dQ, const void* dKV, const void* dh, const void* x, const float* mean, const float* rstd,
                            const float* ln_w, const void* w_in, int T, int d, void* dx, float* dln_w, float* dln_b,
-                           void* stream_) {
+                           int hd_valid, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!dQ || !dKV || !dh || !x || !mean || !rstd || !ln_w || !w_in || !dx || !dln_w || !dln_b || T <= 0) return RP_EINVAL;
   if (d != 64 && d != 128) return RP_ESHAPE;
+  if (hd_valid < 0 || hd_valid > 128 || (hd_valid > 0 && d % (hd_valid <= 64 ? 64 : 128))) return RP_ESHAPE;
   if (dx == dQ || dx == dKV || dx == dh || dx == x) return RP_EINVAL;
   CUtensorMap tmDQ, tmDKV, tmWq, tmWkv;
   int rc;
@@ -632,7 +643,7 @@ RP_API int rp_pre_attn_bwd(const void* dQ, const void* dKV, const void* dh, cons
   PreAttnBwdParams p;
   p.dh = reinterpret_cast<const __nv_bfloat16*>(dh); p.x = reinterpret_cast<const __nv_bfloat16*>(x);
   p.mean = mean; p.rstd = rstd; p.ln_w = ln_w; p.dx = reinterpret_cast<__nv_bfloat16*>(dx);
-  p.dln_w = dln_w; p.dln_b = dln_b; p.T = T;
+  p.dln_w = dln_w; p.dln_b = dln_b; p.T = T; p.hd_valid = hd_valid;
   return d == 64 ? launch_pre_attn_bwd<1>(tmDQ, tmDKV, tmWq, tmWkv, p, stream)
                  : launch_pre_attn_bwd<2>(tmDQ, tmDKV, tmWq, tmWkv, p, stream);
 }

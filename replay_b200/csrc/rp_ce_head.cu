@@ -48,7 +48,7 @@ static constexpr int kBwdThreads = 64 + kBwdEpiWarps * 32;
 // a tile need >= 1024 of the ~1170 tensor cycles of the tile) idles through every load / store / barrier phase; two sets on
 // different tiles fill each other's gaps (r2 ncu: MUFU 61-65 % and tensor 69-74 % busy with one set).
 #ifndef RP_CE_GROUPS
-#define RP_CE_GROUPS 2
+#define RP_CE_GROUPS 1   /* r2 A/B (profiles/r2_ce_variants.md): two sets measured 3-5 % SLOWER than one - kept as a knob */
 #endif
 static constexpr int kCeMaxGroups = 2;
 

@@ -218,8 +218,9 @@ __global__ void layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const 
                                      const float* __restrict__ b, float eps, int n_rows,
                                      const int32_t* __restrict__ n_rows_dev, const int32_t* __restrict__ gather,
                                      __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
-                                     float* __restrict__ rstd_out) {
+                                     float* __restrict__ rstd_out, int hd_valid) {
   constexpr int D = VEC * 32;
+  const float inv_d = 1.f / (float)feat_count(D, hd_valid);
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int rows = n_rows_dev ? min(n_rows, *n_rows_dev) : n_rows;
@@ -241,14 +242,14 @@ __global__ void layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const 
       v[i + 1] = f.y;
       s += f.x + f.y;
     }
-    const float mean = warp_sum(s) * (1.f / D);
+    const float mean = warp_sum(s) * inv_d;   // padded columns hold zeros: they add nothing to the sum
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const float dlt = v[i] - mean;
+      const float dlt = feat_valid(lane * VEC + i, hd_valid) ? v[i] - mean : 0.f;
       q += dlt * dlt;
     }
-    const float var = warp_sum(q) * (1.f / D);
+    const float var = warp_sum(q) * inv_d;
     const float rstd = rsqrtf(var + eps);
     __nv_bfloat16* yr = y + (size_t)r * D + lane * VEC;
 #pragma unroll
@@ -272,8 +273,9 @@ __global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const
                                      const float* __restrict__ rstd_in, int n_rows,
                                      const int32_t* __restrict__ n_rows_dev, const int32_t* __restrict__ gather,
                                      const __nv_bfloat16* __restrict__ add_to, __nv_bfloat16* __restrict__ dx,
-                                     float* __restrict__ dw, float* __restrict__ db) {
+                                     float* __restrict__ dw, float* __restrict__ db, int hd_valid) {
   constexpr int D = VEC * 32;
+  const float inv_d = 1.f / (float)feat_count(D, hd_valid);
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int rows = n_rows_dev ? min(n_rows, *n_rows_dev) : n_rows;
@@ -295,8 +297,8 @@ __global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const
     for (int i = 0; i < VEC; i += 2) {
       const float2 xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xr + i));
       const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gr + i));
-      xh[i] = (xf.x - mean) * rstd;
-      xh[i + 1] = (xf.y - mean) * rstd;
+      xh[i] = feat_valid(lane * VEC + i, hd_valid) ? (xf.x - mean) * rstd : 0.f;
+      xh[i + 1] = feat_valid(lane * VEC + i + 1, hd_valid) ? (xf.y - mean) * rstd : 0.f;
       dw_acc[i] += gf.x * xh[i];
       dw_acc[i + 1] += gf.y * xh[i + 1];
       db_acc[i] += gf.x;
@@ -306,13 +308,15 @@ __global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const
       s1 += g[i] + g[i + 1];
       s2 += g[i] * xh[i] + g[i + 1] * xh[i + 1];
     }
-    s1 = warp_sum(s1) * (1.f / D);
-    s2 = warp_sum(s2) * (1.f / D);
+    s1 = warp_sum(s1) * inv_d;
+    s2 = warp_sum(s2) * inv_d;
     __nv_bfloat16* o = dx + (size_t)row * D + lane * VEC;
     const __nv_bfloat16* a = add_to ? add_to + (size_t)row * D + lane * VEC : nullptr;
 #pragma unroll
     for (int i = 0; i < VEC; i += 2) {
       float o0 = rstd * (g[i] - s1 - xh[i] * s2), o1 = rstd * (g[i + 1] - s1 - xh[i + 1] * s2);
+      if (!feat_valid(lane * VEC + i, hd_valid)) o0 = 0.f;       // padded inputs do not exist: no gradient
+      if (!feat_valid(lane * VEC + i + 1, hd_valid)) o1 = 0.f;
       if (a) {
         const float2 af = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + i));
         o0 += af.x;
@@ -594,28 +598,30 @@ RP_API int rp_embed_bwd(const void* dx, const int32_t* ids, const uint8_t* pad_m
 
 RP_API int rp_layernorm_fwd(const void* x, const float* w, const float* b, float eps, int n_rows, int d,
                             const int32_t* n_rows_dev, const int32_t* gather, void* y, float* mean, float* rstd,
-                            void* stream_) {
+                            int hd_valid, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!x || !w || !b || !y || !mean || !rstd || n_rows <= 0) return RP_EINVAL;
+  if (hd_valid < 0 || hd_valid > 128 || (hd_valid > 0 && d % (hd_valid <= 64 ? 64 : 128))) return RP_ESHAPE;
   const int grid = grid_for(n_rows, 8);
   RP_DISPATCH_D(d, (layernorm_fwd_kernel<VEC><<<grid, 256, 0, stream>>>(
                        reinterpret_cast<const __nv_bfloat16*>(x), w, b, eps, n_rows, n_rows_dev, gather,
-                       reinterpret_cast<__nv_bfloat16*>(y), mean, rstd)));
+                       reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, hd_valid)));
   RP_LAUNCH_CHECK();
   return RP_OK;
 }
 
 RP_API int rp_layernorm_bwd(const void* dy, const void* x, const float* w, const float* mean, const float* rstd,
                             int n_rows, int d, const int32_t* n_rows_dev, const int32_t* gather, const void* add_to,
-                            void* dx, float* dw, float* db, void* stream_) {
+                            void* dx, float* dw, float* db, int hd_valid, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!dy || !x || !w || !mean || !rstd || !dx || !dw || !db || n_rows <= 0) return RP_EINVAL;
+  if (hd_valid < 0 || hd_valid > 128 || (hd_valid > 0 && d % (hd_valid <= 64 ? 64 : 128))) return RP_ESHAPE;
   int grid = grid_for(n_rows, 8 * 16);  // each warp walks ~16 rows so the dw/db atomics stay few
   const size_t smem = (size_t)2 * 8 * d * sizeof(float);
   RP_DISPATCH_D(d, (layernorm_bwd_kernel<VEC><<<grid, 256, smem, stream>>>(
                        reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), w, mean, rstd,
                        n_rows, n_rows_dev, gather, reinterpret_cast<const __nv_bfloat16*>(add_to),
-                       reinterpret_cast<__nv_bfloat16*>(dx), dw, db)));
+                       reinterpret_cast<__nv_bfloat16*>(dx), dw, db, hd_valid)));
   RP_LAUNCH_CHECK();
   return RP_OK;
 }

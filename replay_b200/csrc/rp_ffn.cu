@@ -238,6 +238,7 @@ struct PostAttnParams {
   float drop_p;
   unsigned long long seed, off1, off2;
   const unsigned long long* seed_ptr;
+  int hd_valid;                // > 0: padded feature slots (rp_sm100.cuh): LayerNorm statistics over the real features only
 };
 
 // keep/scale 4 consecutive elements starting at element index e (e % 4 == 0)
@@ -444,8 +445,9 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
             s_stat[half][row] = make_float2(sum, sq);
             asm volatile("bar.sync 1, %0;" ::"r"(kFfnEpiWarps * 32) : "memory");
             const float2 sa = s_stat[0][row], sb = (D > 64) ? s_stat[1][row] : make_float2(0.f, 0.f);
-            const float mean = (sa.x + sb.x) * (1.f / D);
-            const float var = fmaxf((sa.y + sb.y) * (1.f / D) - mean * mean, 0.f);
+            const float inv_d = 1.f / (float)feat_count(D, p.hd_valid);   // padded columns are zero: sums need no mask
+            const float mean = (sa.x + sb.x) * inv_d;
+            const float var = fmaxf((sa.y + sb.y) * inv_d - mean * mean, 0.f);
             const float rstd = rsqrtf(var + p.eps);
             asm volatile("bar.sync 1, %0;" ::"r"(kFfnEpiWarps * 32) : "memory");  // s_stat is rewritten by the next tile
             if (has_half) {
@@ -631,10 +633,11 @@ RP_API int rp_ffn_fused(const void* y, const void* w1, const float* b1, const vo
 //                                                              replay/models/nn/sequential/sasrec/model.py:435-441
 RP_API int rp_post_attn_fused(const void* o, const void* q_in, const void* wo, const float* bo, const float* ln_w,
                               const float* ln_b, float eps, const void* w1, const float* b1, const void* w2, const float* b2,
-                              const uint8_t* rowmask, int T, int d, void* out, void* stream_) {
+                              const uint8_t* rowmask, int T, int d, void* out, int hd_valid, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!o || !q_in || !wo || !bo || !ln_w || !ln_b || !w1 || !b1 || !w2 || !b2 || !out || T <= 0) return RP_EINVAL;
   if (d != 64 && d != 128) return RP_ESHAPE;
+  if (hd_valid < 0 || hd_valid > 128 || (hd_valid > 0 && d % (hd_valid <= 64 ? 64 : 128))) return RP_ESHAPE;
   if (out == o || out == q_in) return RP_EINVAL;
   CUtensorMap tmO, tmWo, tmW1, tmW2;
   int rc;
@@ -647,7 +650,7 @@ RP_API int rp_post_attn_fused(const void* o, const void* q_in, const void* wo, c
   p.q_in = reinterpret_cast<const __nv_bfloat16*>(q_in); p.rowmask = rowmask;
   p.out = reinterpret_cast<__nv_bfloat16*>(out); p.eps = eps; p.T = T;
   p.h_save = p.y_save = p.u_save = nullptr; p.mean_out = p.rstd_out = nullptr;
-  p.drop_p = 0.f; p.seed = p.off1 = p.off2 = 0ull; p.seed_ptr = nullptr;
+  p.drop_p = 0.f; p.seed = p.off1 = p.off2 = 0ull; p.seed_ptr = nullptr; p.hd_valid = hd_valid;
   return d == 64 ? launch_post_attn<1, false>(tmO, tmWo, tmW1, tmW2, p, stream)
                  : launch_post_attn<2, false>(tmO, tmWo, tmW1, tmW2, p, stream);
 }
@@ -665,12 +668,13 @@ RP_API int rp_post_attn_train(const void* o, const void* q_in, const void* wo, c
                               const uint8_t* rowmask, int T, int d, float drop_p, unsigned long long seed,
                               unsigned long long drop_off1, unsigned long long drop_off2, const unsigned long long* seed_ptr,
                               void* h_save, void* y_save, void* u_save, float* mean_out, float* rstd_out, void* out,
-                              void* stream_) {
+                              int hd_valid, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!o || !q_in || !wo || !bo || !ln_w || !ln_b || !w1 || !b1 || !w2 || !b2 || !out || T <= 0) return RP_EINVAL;
   if (!h_save || !y_save || !u_save || !mean_out || !rstd_out) return RP_EINVAL;
   if (d != 64 && d != 128) return RP_ESHAPE;
   if (drop_p < 0.f || drop_p >= 1.f || (drop_off1 & 3) || (drop_off2 & 3)) return RP_EINVAL;
+  if (hd_valid < 0 || hd_valid > 128 || (hd_valid > 0 && d % (hd_valid <= 64 ? 64 : 128))) return RP_ESHAPE;
   if (out == o || out == q_in) return RP_EINVAL;
   CUtensorMap tmO, tmWo, tmW1, tmW2;
   int rc;
@@ -684,7 +688,7 @@ RP_API int rp_post_attn_train(const void* o, const void* q_in, const void* wo, c
   p.out = reinterpret_cast<__nv_bfloat16*>(out); p.eps = eps; p.T = T;
   p.h_save = reinterpret_cast<__nv_bfloat16*>(h_save); p.y_save = reinterpret_cast<__nv_bfloat16*>(y_save);
   p.u_save = reinterpret_cast<__nv_bfloat16*>(u_save); p.mean_out = mean_out; p.rstd_out = rstd_out;
-  p.drop_p = drop_p; p.seed = seed; p.off1 = drop_off1; p.off2 = drop_off2; p.seed_ptr = seed_ptr;
+  p.drop_p = drop_p; p.seed = seed; p.off1 = drop_off1; p.off2 = drop_off2; p.seed_ptr = seed_ptr; p.hd_valid = hd_valid;
   return d == 64 ? launch_post_attn<1, true>(tmO, tmWo, tmW1, tmW2, p, stream)
                  : launch_post_attn<2, true>(tmO, tmWo, tmW1, tmW2, p, stream);
 }

@@ -38,6 +38,7 @@ struct PostAttnBwdParams {
   unsigned long long seed, off2;
   const unsigned long long* seed_ptr;
   int T;
+  int hd_valid;                // > 0: padded feature slots - LN statistics over the real features, no gradient into padded inputs
 };
 
 // column sums over the 32 rows of a warp: on return lane l holds the sums of columns 2l and 2l+1 in v[0], v[1]
@@ -309,15 +310,20 @@ post_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
             s_stat[half][row] = make_float2(s1, s2);
             asm volatile("bar.sync 1, %0;" ::"r"(kPbEpiWarps * 32) : "memory");
             const float2 sa = s_stat[0][row], sb = (D > 64) ? s_stat[1][row] : make_float2(0.f, 0.f);
-            const float m1 = (sa.x + sb.x) * (1.f / D), m2 = (sa.y + sb.y) * (1.f / D);
+            const float inv_d = 1.f / (float)feat_count(D, p.hd_valid);
+            const float m1 = (sa.x + sb.x) * inv_d, m2 = (sa.y + sb.y) * inv_d;
             asm volatile("bar.sync 1, %0;" ::"r"(kPbEpiWarps * 32) : "memory");
             if (has_half) {
               uint32_t pk[32];
 #pragma unroll
               for (int q = 0; q < 64; q += 2) {
                 const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hp[q >> 1]));
-                const float t0 = rstd * (dy[q] * s_lnw[c0 + q] - m1 - fmaf(hf.x, rs_ok, nmr) * m2);
-                const float t1 = rstd * (dy[q + 1] * s_lnw[c0 + q + 1] - m1 - fmaf(hf.y, rs_ok, nmr) * m2);
+                float t0 = rstd * (dy[q] * s_lnw[c0 + q] - m1 - fmaf(hf.x, rs_ok, nmr) * m2);
+                float t1 = rstd * (dy[q + 1] * s_lnw[c0 + q + 1] - m1 - fmaf(hf.y, rs_ok, nmr) * m2);
+                if (p.hd_valid > 0) {   // padded inputs of the LayerNorm do not exist: no gradient
+                  if (!feat_valid(c0 + q, p.hd_valid)) t0 = 0.f;
+                  if (!feat_valid(c0 + q + 1, p.hd_valid)) t1 = 0.f;
+                }
                 pk[q >> 1] = pack_bf16(t0, t1);
               }
               tmem_st16(R0 + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
@@ -421,12 +427,13 @@ using namespace rp;
 RP_API int rp_post_attn_bwd(const void* dz, const void* u, const void* h, const float* mean, const float* rstd, const float* ln_w,
                             const void* w2, const void* w1, const void* wo, const uint8_t* rowmask, int T, int d, float drop_p,
                             unsigned long long seed, unsigned long long drop_off2, const unsigned long long* seed_ptr, void* d_t,
-                            void* du, void* dh, void* d_o, float* dln_w, float* dln_b, void* stream_) {
+                            void* du, void* dh, void* d_o, float* dln_w, float* dln_b, int hd_valid, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!dz || !u || !h || !mean || !rstd || !ln_w || !w2 || !w1 || !wo || !du || !dh || !d_o || !dln_w || !dln_b || T <= 0)
     return RP_EINVAL;
   if (d != 64 && d != 128) return RP_ESHAPE;
   if (drop_p < 0.f || drop_p >= 1.f || (drop_off2 & 3)) return RP_EINVAL;
+  if (hd_valid < 0 || hd_valid > 128 || (hd_valid > 0 && d % (hd_valid <= 64 ? 64 : 128))) return RP_ESHAPE;
   if (!d_t && (drop_p > 0.f || rowmask)) return RP_EINVAL;
   if (d_t == dz || du == dz || dh == dz || d_o == dz) return RP_EINVAL;
   CUtensorMap tmDZ, tmW2, tmW1, tmWo;
@@ -441,6 +448,7 @@ RP_API int rp_post_attn_bwd(const void* dz, const void* u, const void* h, const 
   p.d_t = reinterpret_cast<__nv_bfloat16*>(d_t); p.du = reinterpret_cast<__nv_bfloat16*>(du);
   p.dh = reinterpret_cast<__nv_bfloat16*>(dh); p.d_o = reinterpret_cast<__nv_bfloat16*>(d_o);
   p.dln_w = dln_w; p.dln_b = dln_b; p.drop_p = drop_p; p.seed = seed; p.off2 = drop_off2; p.seed_ptr = seed_ptr; p.T = T;
+  p.hd_valid = hd_valid;
   return d == 64 ? launch_post_attn_bwd<1>(tmDZ, tmW2, tmW1, tmWo, p, stream)
                  : launch_post_attn_bwd<2>(tmDZ, tmW2, tmW1, tmWo, p, stream);
 }

@@ -224,4 +224,18 @@ __device__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t chunk16) {
   return row * 128u + ((chunk16 ^ (row & 7u)) << 4);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// padded feature layout ("feature slots")
+// ------------------------------------------------------------------------------------------------------------------
+// hd_valid > 0: PADDED feature layout (include/rp_b200.h "feature slots"): the row holds D/slot slots of `slot` = 64 (hd_valid
+// <= 64) or 128 columns of which only the first hd_valid are real features; the padded columns are zero in every activation,
+// weight and bias, the statistics run over the real features only and padded outputs / gradients stay zero.
+__device__ __forceinline__ bool feat_valid(int col, int hd_valid) {
+  return hd_valid <= 0 || (col & (hd_valid <= 64 ? 63 : 127)) < hd_valid;
+}
+__host__ __device__ __forceinline__ int feat_count(int D, int hd_valid) {
+  return hd_valid <= 0 ? D : (D / (hd_valid <= 64 ? 64 : 128)) * hd_valid;
+}
+
+
 }  // namespace rp

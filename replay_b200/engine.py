@@ -37,10 +37,11 @@ class EncoderConfig:
             raise ValueError(f"unknown variant {self.variant}")
         if self.d % self.n_heads:
             raise ValueError("d must be divisible by n_heads")
-        if self.d not in (64, 128, 256, 512):
-            raise ValueError("hidden size must be one of 64/128/256/512 (kernel tile constraint)")
-        if self.d // self.n_heads not in (64, 128):
-            raise ValueError("head_dim must be 64 or 128 (tcgen05 128B-swizzle tile constraint)")
+        if self.d // self.n_heads > 128:
+            raise ValueError("head_dim must not exceed 128 (one 128-wide tensor-core feature slot per head)")
+        if self.dp not in (64, 128, 256, 512):
+            raise ValueError(f"hidden size {self.d} with {self.n_heads} heads needs {self.dp} padded columns; the kernels "
+                             "support 64/128/256/512 (= n_heads x 64-wide slots, or 128-wide for head_dim > 64)")
         if self.lnf_eps is None:
             # new: torch.nn.LayerNorm default (nn/sequential/sasrec/model.py:248); legacy: 1e-8 (sasrec/model.py:463)
             self.lnf_eps = 1e-5 if self.variant == "new" else 1e-8
@@ -48,6 +49,33 @@ class EncoderConfig:
     @property
     def pad_id(self) -> int:
         return self.n_items
+
+    # ---- feature slots: every head occupies one 64-wide (head_dim <= 64) or 128-wide tensor-core slot.  The reference's own
+    # defaults (embedding_dim 192 / 4 heads -> head_dim 48; legacy hidden_size 50; examples d 64 / 2 heads -> 32) leave padded
+    # columns, which are zero in every activation / weight / gradient (include/rp_b200.h "PADDED FEATURE SLOTS")
+    @property
+    def head_dim(self) -> int:
+        return self.d // self.n_heads
+
+    @property
+    def head_slot(self) -> int:
+        return 64 if self.head_dim <= 64 else 128
+
+    @property
+    def dp(self) -> int:
+        """columns of the token-major activations / weights as the kernels see them"""
+        return self.n_heads * self.head_slot
+
+    @property
+    def hd_valid(self) -> int:
+        """the kernels' `hd_valid` argument: real features per slot, 0 when nothing is padded"""
+        return 0 if self.head_dim == self.head_slot else self.head_dim
+
+    def feat_index(self, device=None) -> torch.Tensor:
+        """padded column of every true feature: (head h, j) -> h * slot + j"""
+        h = torch.arange(self.n_heads, device=device).repeat_interleave(self.head_dim)
+        j = torch.arange(self.head_dim, device=device).repeat(self.n_heads)
+        return h * self.head_slot + j
 
 
 _BLOCK_PARAMS = ("ln1_w", "ln1_b", "in_w", "in_b", "out_w", "out_b", "ln2_w", "ln2_b", "w1", "b1", "w2", "b2")
@@ -96,7 +124,8 @@ class SasRecEngine:
         self.Lp = _ru(seq_len, 64)
         self.with_grad = with_grad
         self.lib = _CountingLib(lib())
-        d, I = cfg.d, cfg.n_items
+        d, I = cfg.dp, cfg.n_items   # padded width: what buffers and kernels use; cfg.d is the model's true hidden size
+        self._feat = cfg.feat_index(self.dev)
         # ---------------------------------------------------------------- flat parameter layout
         shapes = [("item_emb", (I + 1, d)), ("pos_emb", (cfg.max_len, d))]
         for i in range(cfg.n_blocks):
@@ -122,7 +151,7 @@ class SasRecEngine:
         self.seed = seed & 0xFFFFFFFFFFFF
         self.training = with_grad
         # fused tcgen05 attention backward: head_dim 64, L <= 256; otherwise saved probabilities + batched GEMMs
-        self.fused_attn_bwd = (cfg.d // cfg.n_heads) == 64 and seq_len <= 256
+        self.fused_attn_bwd = cfg.head_slot == 64 and seq_len <= 256
         self.sampled = None       # full-catalog CE unless set_loss() selects a sampled head
         self._loss_args = None
         self.fused_ffn_eval = True  # eval / predict: one-pass FFN kernel for d <= 128
@@ -157,7 +186,7 @@ class SasRecEngine:
             raise ValueError(f"sequence length {seq_len} exceeds max_len {cfg.max_len}")
         if cfg.variant == "legacy" and seq_len != cfg.max_len:
             raise ValueError("legacy SASRec needs seq_len == max_len (sasrec/model.py:528-529)")
-        if seq_len > 512 or (seq_len > 256 and cfg.d // cfg.n_heads != 64):
+        if seq_len > 512 or (seq_len > 256 and cfg.head_slot != 64):
             raise ValueError("attention kernels support seq_len <= 256 (head_dim 128) / <= 512 (head_dim 64)")
 
     def resize(self, max_batch: int, seq_len: int, with_grad: bool | None = None):
@@ -172,7 +201,7 @@ class SasRecEngine:
         self.B, self.L = max_batch, seq_len
         self.T = max_batch * seq_len
         self.Lp = _ru(seq_len, 64)
-        self.fused_attn_bwd = (self.cfg.d // self.cfg.n_heads) == 64 and seq_len <= 256
+        self.fused_attn_bwd = self.cfg.head_slot == 64 and seq_len <= 256
         self._realloc_workspace()
         if self._loss_args is not None and self._loss_args[0] != "ce":  # sampled-head buffers are sized by (B, T)
             self.sampled = None
@@ -184,27 +213,79 @@ class SasRecEngine:
         self._alloc_workspace()
 
     # ------------------------------------------------------------------------------------------------ parameters
+    def _pad_kind(self, name: str):
+        """(row kind, column kind) of a parameter in the padded layout: 'f' = feature axis (scattered into the head slots),
+        'f3' = three stacked feature axes (packed in-projection), None = not a feature axis."""
+        leaf = name.split(".")[-1]
+        if leaf in ("item_emb", "pos_emb"):
+            return (None, "f")
+        if leaf == "in_w":
+            return ("f3", "f")
+        if leaf == "in_b":
+            return ("f3", None)
+        if leaf in ("out_w", "w1", "w2"):
+            return ("f", "f")
+        return ("f", None)  # LayerNorm weights / biases, linear biases
+
+    def _axis_index(self, kind):
+        if kind == "f":
+            return self._feat
+        dp = self.cfg.dp
+        return torch.cat([self._feat + k * dp for k in range(3)])
+
+    def import_named(self, name: str, value: torch.Tensor, dst=None):
+        """Write a TRUE-shape tensor (reference layout) into the padded parameter ``name`` (padded entries become zero)."""
+        tgt = (self.params if dst is None else dst)[name]
+        v = value.to(self.dev, torch.float32)
+        if self._hdv() == 0:
+            tgt.copy_(v.reshape(tgt.shape))
+            return
+        rk, ck = self._pad_kind(name)
+        tgt.zero_()
+        if tgt.dim() == 1:
+            tgt[self._axis_index(rk)] = v
+        else:
+            rows = self._axis_index(rk) if rk else torch.arange(tgt.shape[0], device=self.dev)
+            cols = self._axis_index(ck) if ck else torch.arange(tgt.shape[1], device=self.dev)
+            tgt[rows[:, None], cols[None, :]] = v
+
+    def export_named(self, name: str, source=None) -> torch.Tensor:
+        """The TRUE-shape view (a copy) of the padded parameter / gradient ``name``."""
+        t = (self.params if source is None else source)[name].detach()
+        if self._hdv() == 0:
+            return t.clone()
+        rk, ck = self._pad_kind(name)
+        if t.dim() == 1:
+            return t[self._axis_index(rk)].clone()
+        rows = self._axis_index(rk) if rk else torch.arange(t.shape[0], device=t.device)
+        cols = self._axis_index(ck) if ck else torch.arange(t.shape[1], device=t.device)
+        return t[rows[:, None], cols[None, :]].clone()
+
+    def true_shape(self, name: str):
+        d, dp = self.cfg.d, self.cfg.dp
+        return tuple({dp: d, 3 * dp: 3 * d, 2 * dp: 2 * d}.get(x, x) for x in self.layout[name][1]) if self._hdv() else self.layout[name][1]
+
     def init_parameters(self, seed: int = 0):
         """Reference-style init: xavier_normal_ on >=2-D tensors, LN (1, 0), biases zero / U(+-1/sqrt(fan_in)) for the
-        conv layers, pad row zero (new path, nn/embedding.py:198-200).  Weights are normally loaded from a reference
-        state_dict instead (``load_canonical``)."""
+        conv layers, pad row zero (new path, nn/embedding.py:198-200) - drawn in the model's TRUE shapes, then laid out in the
+        head slots.  Weights are normally loaded from a reference state_dict instead (``load_canonical``)."""
         g = torch.Generator(device="cpu").manual_seed(seed)
         d = self.cfg.d
         with torch.no_grad():
-            for name, (o, shp) in self.layout.items():
-                p = self.params[name]
+            for name in self.layout:
+                shp = self.true_shape(name)
                 if len(shp) == 2:
                     std = math.sqrt(2.0 / (shp[0] + shp[1]))
-                    p.copy_((torch.randn(shp, generator=g) * std).to(self.dev))
+                    v = torch.randn(shp, generator=g) * std
+                    if name == "item_emb" and self.cfg.variant == "new":
+                        v[self.cfg.pad_id].zero_()
                 elif name.endswith(("ln1_w", "ln2_w", "lnf_w")):
-                    p.fill_(1.0)
+                    v = torch.ones(shp)
                 elif name.endswith((".b1", ".b2")):
-                    bound = 1.0 / math.sqrt(d)
-                    p.copy_(((torch.rand(shp, generator=g) * 2 - 1) * bound).to(self.dev))
+                    v = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(d)
                 else:
-                    p.zero_()
-            if self.cfg.variant == "new":
-                self.params["item_emb"][self.cfg.pad_id].zero_()
+                    v = torch.zeros(shp)
+                self.import_named(name, v)
         self.refresh_shadow()
 
     def refresh_shadow(self):
@@ -213,26 +294,36 @@ class SasRecEngine:
     def load_canonical(self, P: dict):
         """Copy weights from the canonical dict used by oracle/ (keys item_emb, pos_emb, blocks[i][...], lnf_w, lnf_b)."""
         with torch.no_grad():
-            self.params["item_emb"].copy_(P["item_emb"].to(self.dev, torch.float32))
-            self.params["pos_emb"].copy_(P["pos_emb"].to(self.dev, torch.float32))
+            self.import_named("item_emb", P["item_emb"])
+            self.import_named("pos_emb", P["pos_emb"])
             for i, blk in enumerate(P["blocks"]):
                 for k in _BLOCK_PARAMS:
-                    self.params[f"b{i}.{k}"].copy_(blk[k].to(self.dev, torch.float32))
-            self.params["lnf_w"].copy_(P["lnf_w"].to(self.dev, torch.float32))
-            self.params["lnf_b"].copy_(P["lnf_b"].to(self.dev, torch.float32))
+                    self.import_named(f"b{i}.{k}", blk[k])
+            self.import_named("lnf_w", P["lnf_w"])
+            self.import_named("lnf_b", P["lnf_b"])
         self.refresh_shadow()
 
     def export_canonical(self, source=None) -> dict:
-        src = self.params if source is None else source
-        P = {"item_emb": src["item_emb"].detach().cpu().clone(), "pos_emb": src["pos_emb"].detach().cpu().clone(),
-             "blocks": [], "lnf_w": src["lnf_w"].detach().cpu().clone(), "lnf_b": src["lnf_b"].detach().cpu().clone()}
+        ex = lambda k: self.export_named(k, source).cpu()  # noqa: E731
+        P = {"item_emb": ex("item_emb"), "pos_emb": ex("pos_emb"), "blocks": [], "lnf_w": ex("lnf_w"), "lnf_b": ex("lnf_b")}
         for i in range(self.cfg.n_blocks):
-            P["blocks"].append({k: src[f"b{i}.{k}"].detach().cpu().clone() for k in _BLOCK_PARAMS})
+            P["blocks"].append({k: ex(f"b{i}.{k}") for k in _BLOCK_PARAMS})
         return P
+
+    def unpad_features(self, t: torch.Tensor) -> torch.Tensor:
+        """[..., dp] activations -> [..., d] (the reference's hidden size)"""
+        return t if self._hdv() == 0 else t[..., self._feat].contiguous()
+
+    def pad_features(self, t: torch.Tensor) -> torch.Tensor:
+        if self._hdv() == 0:
+            return t
+        out = torch.zeros(*t.shape[:-1], self.cfg.dp, device=t.device, dtype=t.dtype)
+        out[..., self._feat] = t
+        return out
 
     # ------------------------------------------------------------------------------------------------ workspace
     def _alloc_workspace(self):
-        cfg, T, d, dev = self.cfg, self.T, self.cfg.d, self.dev
+        cfg, T, d, dev = self.cfg, self.T, self.cfg.dp, self.dev
         bf = dict(device=dev, dtype=torch.bfloat16)
         f32 = dict(device=dev, dtype=torch.float32)
         i32 = dict(device=dev, dtype=torch.int32)
@@ -366,17 +457,23 @@ class SasRecEngine:
         check(self.lib.rp_colsum_multi(n, dy, cols, ld, db, pairs[0][0].shape[0], self._stream()), "rp_colsum_multi")
 
     def _ln_fwd(self, x, w, b, eps, y, mean, rstd, n_rows, gather=None, n_rows_dev=None):
-        check(self.lib.rp_layernorm_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), eps, n_rows, self.cfg.d,
+        check(self.lib.rp_layernorm_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), eps, n_rows, self._dp(),
                                         None if n_rows_dev is None else n_rows_dev.data_ptr(),
                                         None if gather is None else gather.data_ptr(), y.data_ptr(), mean.data_ptr(),
-                                        rstd.data_ptr(), self._stream()), "rp_layernorm_fwd")
+                                        rstd.data_ptr(), self._hdv(), self._stream()), "rp_layernorm_fwd")
 
     def _ln_bwd(self, dy, x, w, mean, rstd, dx, dw, db, n_rows, gather=None, n_rows_dev=None, add_to=None):
         check(self.lib.rp_layernorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                        n_rows, self.cfg.d, None if n_rows_dev is None else n_rows_dev.data_ptr(),
+                                        n_rows, self._dp(), None if n_rows_dev is None else n_rows_dev.data_ptr(),
                                         None if gather is None else gather.data_ptr(),
                                         None if add_to is None else add_to.data_ptr(), dx.data_ptr(), dw.data_ptr(),
-                                        db.data_ptr(), self._stream()), "rp_layernorm_bwd")
+                                        db.data_ptr(), self._hdv(), self._stream()), "rp_layernorm_bwd")
+
+    def _dp(self) -> int:
+        return getattr(self.cfg, "dp", self.cfg.d)   # BertConfig has no padded layout
+
+    def _hdv(self) -> int:
+        return getattr(self.cfg, "hd_valid", 0)
 
     def _site(self, blk, k):
         return 1 + blk * 8 + k
@@ -414,7 +511,7 @@ class SasRecEngine:
             raise NotImplementedError(f"Not supported loss_type {kind!r}")
         mode = {"shared": 0, "perpos": 1, "perseq": 2}[neg_shape]
         rows = {0: 1, 1: self.T, 2: self.B}[mode]
-        ws_bytes = self.lib.rp_sampled_head_workspace(self.T, self.cfg.d, n_neg, mode)
+        ws_bytes = self.lib.rp_sampled_head_workspace(self.T, self._dp(), n_neg, mode)
         self.sampled = dict(kind=self.SAMPLED_KINDS[kind], n_neg=n_neg, mode=mode, ignore_index=ignore_index, log_eps=log_eps,
                             clamp=clamp, neg=torch.zeros(rows, n_neg, device=self.dev, dtype=torch.int64),
                             ws=torch.zeros(ws_bytes, device=self.dev, dtype=torch.uint8), ws_bytes=ws_bytes)
@@ -435,7 +532,7 @@ class SasRecEngine:
         sd.hc, sd.table = self.hc.data_ptr(), self.params16["item_emb"].data_ptr()
         sd.labels, sd.valid_idx, sd.negatives = self.labels_c.data_ptr(), self.valid_idx.data_ptr(), sp["neg"].data_ptr()
         sd.n_valid = self.n_valid.data_ptr()
-        sd.capacity, sd.n_items, sd.d, sd.n_neg, sd.neg_mode, sd.seq_len = self.T, cfg.n_items, cfg.d, sp["n_neg"], sp["mode"], self.L
+        sd.capacity, sd.n_items, sd.d, sd.n_neg, sd.neg_mode, sd.seq_len = self.T, cfg.n_items, self._dp(), sp["n_neg"], sp["mode"], self.L
         sd.kind, sd.ignore_index, sd.vocab_size = sp["kind"], sp["ignore_index"], cfg.n_items
         sd.log_eps, sd.clamp = sp["log_eps"], sp["clamp"]
         sd.loss_out = self.ce.loss.data_ptr()
@@ -454,14 +551,15 @@ class SasRecEngine:
         """``last_only`` (predict): the final block is evaluated for the LAST position of every sequence only - LN1, the Q
         projection, one-query attention, out-projection, LN2 and the FFN run on [B, d] rows; only the K/V projection of
         that block still covers all tokens.  Result rows land in ``self.last_rows`` (bf16 [B, d])."""
-        cfg, T, d, L = self.cfg, self.T, self.cfg.d, self.L
+        cfg, T, d, L = self.cfg, self.T, self.cfg.dp, self.L
+        hdv, att_scale = cfg.hd_valid, 1.0 / math.sqrt(cfg.head_dim)
         p16, prm = self.params16, self.params
         legacy = cfg.variant == "legacy"
         drop = cfg.dropout if training else 0.0
         pad = self.in_pad
         pos0 = 0 if legacy else cfg.max_len - L
         check(self.lib.rp_embed_fwd(p16["item_emb"].data_ptr(), prm["pos_emb"].data_ptr(), self.ids32.data_ptr(),
-                                    pad.data_ptr(), T, L, d, pos0, math.sqrt(d), int(legacy), drop, self.seed, 0,
+                                    pad.data_ptr(), T, L, d, pos0, math.sqrt(cfg.d), int(legacy), drop, self.seed, 0,
                                     self.rng_counter.data_ptr(), self.x[0].data_ptr(), self._stream()), "rp_embed_fwd")
         H, hd = cfg.n_heads, d // cfg.n_heads
         for i in range(cfg.n_blocks):
@@ -475,8 +573,8 @@ class SasRecEngine:
                 self._gemm(lb["q_in"], in_w[:d], lb["Q"], Bq, d, d, bias=in_b[:d])
                 self._gemm(x, in_w[d:], a["KV"], T, 2 * d, d, bias=in_b[d:])
                 check(self.lib.rp_attn_last(lb["Q"].data_ptr(), a["KV"].data_ptr(), a["KV"].data_ptr(), 2 * d, 2 * d, 0, d,
-                                            pad.data_ptr(), Bq, H, L, hd, int(not legacy), lb["O"].data_ptr(), self._stream()),
-                      "rp_attn_last")
+                                            pad.data_ptr(), Bq, H, L, hd, int(not legacy), lb["O"].data_ptr(), att_scale,
+                                            self._stream()), "rp_attn_last")
                 self._gemm(lb["O"], w("out_w"), lb["h"], Bq, d, d, bias=f("out_b"), residual=lb["q_in"])
                 self._ln_fwd(lb["h"], f("ln2_w"), f("ln2_b"), 1e-8, lb["y"], self.meanf, self.rstdf, Bq)
                 self._gemm(lb["y"], w("w1"), lb["u"], Bq, d, d, bias=f("b1"), act=1)
@@ -487,8 +585,8 @@ class SasRecEngine:
             if self.fused_pre_attn:
                 check(self.lib.rp_ln_qkv_fused(x.data_ptr(), f("ln1_w").data_ptr(), f("ln1_b").data_ptr(), 1e-8,
                                                in_w.data_ptr(), in_b.data_ptr(), T, d, a["q_in"].data_ptr(), a["Q"].data_ptr(),
-                                               a["KV"].data_ptr(), a["mean1"].data_ptr(), a["rstd1"].data_ptr(), self._stream()),
-                      "rp_ln_qkv_fused")
+                                               a["KV"].data_ptr(), a["mean1"].data_ptr(), a["rstd1"].data_ptr(), hdv,
+                                               self._stream()), "rp_ln_qkv_fused")
             else:
                 self._ln_fwd(x, f("ln1_w"), f("ln1_b"), 1e-8, a["q_in"], a["mean1"], a["rstd1"], T)
                 self._gemm(a["q_in"], in_w[:d], a["Q"], T, d, d, bias=in_b[:d])
@@ -499,6 +597,7 @@ class SasRecEngine:
             ad.v, ad.v_rows, ad.v_cols, ad.ldv, ad.v_c0 = a["KV"].data_ptr(), T, 2 * d, 2 * d, d
             ad.B, ad.H, ad.L, ad.head_dim = self.B, H, L, hd
             ad.causal, ad.mask_pad_keys = 1, int(not legacy)
+            ad.scale = att_scale
             ad.pad_mask = pad.data_ptr()
             ad.out, ad.ldo = a["O"].data_ptr(), d
             if training and self.with_grad:
@@ -513,7 +612,7 @@ class SasRecEngine:
                 check(self.lib.rp_post_attn_fused(a["O"].data_ptr(), a["q_in"].data_ptr(), w("out_w").data_ptr(),
                                                   f("out_b").data_ptr(), f("ln2_w").data_ptr(), f("ln2_b").data_ptr(), 1e-8,
                                                   w("w1").data_ptr(), f("b1").data_ptr(), w("w2").data_ptr(), f("b2").data_ptr(),
-                                                  pad.data_ptr() if legacy else None, T, d, self.x[i + 1].data_ptr(),
+                                                  pad.data_ptr() if legacy else None, T, d, self.x[i + 1].data_ptr(), hdv,
                                                   self._stream()), "rp_post_attn_fused")
                 continue
             if training and d <= 128 and self.fused_post_attn_train:
@@ -524,7 +623,7 @@ class SasRecEngine:
                                                   pad.data_ptr() if legacy else None, T, d, drop, self.seed,
                                                   self._site(i, 1) << 40, self._site(i, 2) << 40, self.rng_counter.data_ptr(),
                                                   a["h"].data_ptr(), a["y"].data_ptr(), a["u"].data_ptr(),
-                                                  a["mean2"].data_ptr(), a["rstd2"].data_ptr(), self.x[i + 1].data_ptr(),
+                                                  a["mean2"].data_ptr(), a["rstd2"].data_ptr(), self.x[i + 1].data_ptr(), hdv,
                                                   self._stream()), "rp_post_attn_train")
                 continue
             self._gemm(a["O"], w("out_w"), a["h"], T, d, d, bias=f("out_b"), residual=a["q_in"])
@@ -557,7 +656,8 @@ class SasRecEngine:
 
     # ------------------------------------------------------------------------------------------------ backward
     def backward(self):
-        cfg, T, d, L = self.cfg, self.T, self.cfg.d, self.L
+        cfg, T, d, L = self.cfg, self.T, self.cfg.dp, self.L
+        hdv, att_scale = cfg.hd_valid, 1.0 / math.sqrt(cfg.head_dim)
         p16, prm, G, s = self.params16, self.params, self.grads, self.s
         legacy = cfg.variant == "legacy"
         drop = cfg.dropout
@@ -595,7 +695,7 @@ class SasRecEngine:
                                                 self.in_pad.data_ptr() if legacy else None, T, d, drop, self.seed,
                                                 self._site(i, 2) << 40, self.rng_counter.data_ptr(),
                                                 s["d_t"].data_ptr() if masked else None, s["du"].data_ptr(), s["dh"].data_ptr(),
-                                                s["d_o"].data_ptr(), g("ln2_w").data_ptr(), g("ln2_b").data_ptr(), st()),
+                                                s["d_o"].data_ptr(), g("ln2_w").data_ptr(), g("ln2_b").data_ptr(), hdv, st()),
                       "rp_post_attn_bwd")
                 d_t = s["d_t"] if masked else dz
                 fw = self.fused_wgrad
@@ -645,6 +745,7 @@ class SasRecEngine:
                 bd.out, bd.ldo = a["O"].data_ptr(), d
                 bd.B, bd.H, bd.L, bd.head_dim = self.B, H, L, hd
                 bd.causal, bd.mask_pad_keys = 1, int(not legacy)
+                bd.scale = att_scale
                 bd.pad_mask = self.in_pad.data_ptr()
                 bd.m_save, bd.inv_sum = a["m2"].data_ptr(), a["inv_sum"].data_ptr()
                 bd.dq, bd.ld_dq, bd.dq_c0 = s["dQ"].data_ptr(), d, 0
@@ -658,7 +759,7 @@ class SasRecEngine:
                 self._gemm(s["d_o"], KV, dpd, L, L, hd, batch=BH, inner=H, a_off=(0, L, 0, 0, 0, hd), b_off=(0, L, 0, d, 0, hd),
                            c_geom=(Lp, 0, H * Lp * Lp, Lp * Lp))
                 check(self.lib.rp_attn_softmax_bwd(P.data_ptr(), dpd.data_ptr(), a["inv_sum"].data_ptr(), BH, L,
-                                                   1.0 / math.sqrt(hd), drop, self.seed, self._site(i, 0) << 40,
+                                                   att_scale, drop, self.seed, self._site(i, 0) << 40,
                                                    self.rng_counter.data_ptr(), st()), "rp_attn_softmax_bwd")
                 # dQ = dS . K      (A = dS [BH*Lp, Lp] K-major, B = K MN-major)
                 self._gemm(dpd, KV, s["dQ"], L, hd, L, b_mn=True, batch=BH, inner=H, a_off=(0, H * Lp, Lp, 0, 0, 0),
@@ -675,7 +776,7 @@ class SasRecEngine:
                 check(self.lib.rp_pre_attn_bwd(s["dQ"].data_ptr(), s["dKV"].data_ptr(), s["dh"].data_ptr(), x.data_ptr(),
                                                a["mean1"].data_ptr(), a["rstd1"].data_ptr(), f("ln1_w").data_ptr(),
                                                in_w.data_ptr(), T, d, other.data_ptr(), g("ln1_w").data_ptr(),
-                                               g("ln1_b").data_ptr(), st()), "rp_pre_attn_bwd")
+                                               g("ln1_b").data_ptr(), hdv, st()), "rp_pre_attn_bwd")
             else:
                 self._gemm(s["dQ"], in_w[:d], s["dq_in"], T, d, d, b_mn=True, residual=s["dh"])
                 self._ln_bwd(s["dq_in"], x, f("ln1_w"), a["mean1"], a["rstd1"], s["tmp"], g("ln1_w"), g("ln1_b"), T)
@@ -694,7 +795,7 @@ class SasRecEngine:
             dx, other = other, dx
         pos0 = 0 if legacy else cfg.max_len - L
         check(self.lib.rp_embed_bwd(dx.data_ptr(), self.ids32.data_ptr(), self.in_pad.data_ptr(), self.B, L, d, cfg.pad_id,
-                                    pos0, math.sqrt(d), int(legacy), drop, self.seed, 0, self.rng_counter.data_ptr(),
+                                    pos0, math.sqrt(cfg.d), int(legacy), drop, self.seed, 0, self.rng_counter.data_ptr(),
                                     G["item_emb"].data_ptr(), G["pos_emb"].data_ptr(), st()), "rp_embed_bwd")
 
     def optimizer_step(self, grad_scale: float = 1.0, beta1=0.9, beta2=0.98, eps=1e-8):
@@ -735,6 +836,6 @@ class SasRecEngine:
         """Eval-mode hidden states of every position, bf16 [T, d] (for parity tests / HiddenStatesCallback)."""
         self._prepare(False)
         self._body_forward(False)
-        out = torch.empty(self.T, self.cfg.d, device=self.dev, dtype=torch.bfloat16)
+        out = torch.empty(self.T, self.cfg.dp, device=self.dev, dtype=torch.bfloat16)
         self._ln_fwd(self.x[-1], self.params["lnf_w"], self.params["lnf_b"], self.cfg.lnf_eps, out, self.meanf, self.rstdf, self.T)
         return out

@@ -79,10 +79,11 @@ class SasRecModel(torch.nn.Module):
         return self.core.query_embeddings(feature_tensor[self.item_feature_name], padding_mask).float()
 
     def get_logits(self, out_embeddings, item_ids=None):
-        h = out_embeddings.reshape(-1, out_embeddings.shape[-1]).to(torch.bfloat16).contiguous()
+        h = out_embeddings.reshape(-1, out_embeddings.shape[-1]).to(torch.bfloat16)
+        h = self.core.engine.pad_features(h).contiguous()  # true hidden size -> the engine's feature slots
         tab = self.core.item_table(item_ids)
         out = torch.empty(h.shape[0], tab.shape[0], device=h.device, dtype=torch.float32)
-        self.core.engine._gemm(h, tab, out, h.shape[0], tab.shape[0], self.hidden_size, out_mode=2)
+        self.core.engine._gemm(h, tab, out, h.shape[0], tab.shape[0], self.core.cfg.dp, out_mode=2)
         return out.view(*out_embeddings.shape[:-1], tab.shape[0])
 
     def forward(self, feature_tensor, padding_mask):

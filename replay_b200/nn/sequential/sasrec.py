@@ -84,10 +84,11 @@ class SasRec(torch.nn.Module):
 
     def get_logits(self, model_embeddings, candidates_to_score=None):
         """model.py:258-265: scores of given hidden states [*, d] against the item table (materialised, fp32)."""
-        h = model_embeddings.reshape(-1, model_embeddings.shape[-1]).to(torch.bfloat16).contiguous()
+        h = model_embeddings.reshape(-1, model_embeddings.shape[-1]).to(torch.bfloat16)
+        h = self.core.engine.pad_features(h).contiguous()  # true hidden size -> the engine's feature slots
         tab = self.core.item_table(candidates_to_score)
         out = torch.empty(h.shape[0], tab.shape[0], device=h.device, dtype=torch.float32)
-        self.core.engine._gemm(h, tab, out, h.shape[0], tab.shape[0], self.core.cfg.d, out_mode=2)
+        self.core.engine._gemm(h, tab, out, h.shape[0], tab.shape[0], self.core.cfg.dp, out_mode=2)
         return out.view(*model_embeddings.shape[:-1], tab.shape[0])
 
     def forward_train(self, feature_tensors, padding_mask, positive_labels, negative_labels=None, target_padding_mask=None):

@@ -49,8 +49,16 @@ def test_left_pad_truncates_to_last_items_and_handles_empty():
 def test_new_path_from_params_validation():
     from replay_b200.nn.sequential import SasRec
 
-    with pytest.raises(ValueError):  # head_dim 48 is not a tcgen05 tile size
-        SasRec.from_params(_schema(), embedding_dim=192, num_heads=4)
+    # the reference's own defaults (embedding_dim 192, 4 heads -> head_dim 48) are laid out in padded 64-wide head slots
+    m = SasRec.from_params(_schema())
+    assert (m.core.cfg.d, m.core.cfg.n_heads, m.core.cfg.head_dim, m.core.cfg.dp, m.core.cfg.hd_valid) == (192, 4, 48, 256, 48)
+    m = SasRec.from_params(_schema(), embedding_dim=64, num_heads=2)  # SURVEY config 1 / examples/09: head_dim 32
+    assert (m.core.cfg.dp, m.core.cfg.hd_valid) == (128, 32)
+    assert m.core.cfg.feat_index().tolist() == list(range(32)) + list(range(64, 96))
+    with pytest.raises(ValueError):  # head_dim 150 does not fit one 128-wide slot
+        SasRec.from_params(_schema(), embedding_dim=300, num_heads=2)
+    with pytest.raises(ValueError):  # 8 heads x 128-wide slots = 1024 padded columns: beyond the kernels
+        SasRec.from_params(_schema(), embedding_dim=640, num_heads=8)
     with pytest.raises(ValueError):
         SasRec.from_params(TensorSchema(TensorFeatureInfo("item_id", 300, 0, 64)), embedding_dim=64, num_heads=1)
     m = SasRec.from_params(_schema(), embedding_dim=128, num_heads=2, max_sequence_length=50, dropout=0.1)
@@ -263,7 +271,14 @@ def test_c_abi_argument_errors_without_a_gpu():
     assert L.rp_ce_head_fwd(None, None, None, None, None, 1, 1, 128, None, None, None, None, 0, None, 0, None) == EINVAL
     assert L.rp_ce_head_bwd(None, None, None, None, None, 1, 1, 128, None, None, None, None, None, 0, 0, None, 0, None) == EINVAL
     assert L.rp_ffn_fused(None, None, None, None, None, None, 1, 128, None, None) == EINVAL
-    assert L.rp_post_attn_fused(None, None, None, None, None, None, 1e-8, None, None, None, None, None, 1, 128, None, None) == EINVAL
+    assert L.rp_post_attn_fused(None, None, None, None, None, None, 1e-8, None, None, None, None, None, 1, 128, None, 0, None) == EINVAL
+    assert L.rp_post_attn_train(None, None, None, None, None, None, 1e-8, None, None, None, None, None, 1, 128, 0.0, 0, 0, 0, None,
+                                None, None, None, None, None, None, 0, None) == EINVAL
+    assert L.rp_post_attn_bwd(None, None, None, None, None, None, None, None, None, None, 1, 128, 0.0, 0, 0, None, None, None, None,
+                              None, None, None, 0, None) == EINVAL
+    assert L.rp_ln_qkv_fused(None, None, None, 1e-8, None, None, 1, 128, None, None, None, None, None, 0, None) == EINVAL
+    assert L.rp_pre_attn_bwd(None, None, None, None, None, None, None, None, 1, 128, None, None, None, 0, None) == EINVAL
+    assert L.rp_wgrad_group(None, 0, 1, 1, None, 0, None) == EINVAL and L.rp_wgrad_group_workspace(None, 0) == 0
     assert L.rp_build_batch(None, None, 1, None, None, 1, 1, 0, 0, 0.0, None, 0, 0, None, None, None, None, None, None, None) == EINVAL
     assert L.rp_reduce_splits(None, 1, 4, 4, None, 0, None) == EINVAL
     assert L.rp_colsum(None, 1, 4, 4, None, None) == EINVAL

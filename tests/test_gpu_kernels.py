@@ -387,7 +387,7 @@ def test_fused_post_attention_block_matches_reference_formula(ops, T, d, mask):
     rmc = rm.to(torch.uint8).cuda() if mask else None
     check(lib().rp_post_attn_fused(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), t[5].data_ptr(),
                                    1e-8, t[6].data_ptr(), t[7].data_ptr(), t[8].data_ptr(), t[9].data_ptr(),
-                                   None if rmc is None else rmc.data_ptr(), T, d, out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                                   None if rmc is None else rmc.data_ptr(), T, d, out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream),
           "rp_post_attn_fused")
     torch.cuda.synchronize()
     err = (out[:T].cpu().double() - ref).abs().max().item()
@@ -465,7 +465,7 @@ def test_ln_qkv_fused_matches_formula(ops, T, d):
     mo, ro = torch.zeros(T, **dev), torch.zeros(T, **dev)
     xc, wc, bc, lw, lb = x.cuda(), w_in.cuda(), b_in.cuda(), ln_w.cuda(), ln_b.cuda()
     check(lib().rp_ln_qkv_fused(xc.data_ptr(), lw.data_ptr(), lb.data_ptr(), 1e-8, wc.data_ptr(), bc.data_ptr(), T, d,
-                                q_in.data_ptr(), Q.data_ptr(), KV.data_ptr(), mo.data_ptr(), ro.data_ptr(),
+                                q_in.data_ptr(), Q.data_ptr(), KV.data_ptr(), mo.data_ptr(), ro.data_ptr(), 0,
                                 torch.cuda.current_stream().cuda_stream), "rp_ln_qkv_fused")
     torch.cuda.synchronize()
     assert (q_in.cpu().double() - q_ref).abs().max() < 3e-2
@@ -501,7 +501,7 @@ def test_pre_attn_bwd_matches_formula(ops, T, d):
     dx = torch.zeros(T, d, dtype=torch.bfloat16, device="cuda")
     dw, db = torch.full((d,), 2.0, device="cuda"), torch.full((d,), -3.0, device="cuda")
     args = [t_.cuda() for t_ in (dQ, dKV, dh, x, mean.float(), rstd.float(), ln_w, w_in)]
-    check(lib().rp_pre_attn_bwd(*[a.data_ptr() for a in args], T, d, dx.data_ptr(), dw.data_ptr(), db.data_ptr(),
+    check(lib().rp_pre_attn_bwd(*[a.data_ptr() for a in args], T, d, dx.data_ptr(), dw.data_ptr(), db.data_ptr(), 0,
                                 torch.cuda.current_stream().cuda_stream), "rp_pre_attn_bwd")
     torch.cuda.synchronize()
     assert (dx.cpu().double() - dx_ref).norm() / dx_ref.norm() < 6e-3
@@ -556,7 +556,7 @@ def test_post_attn_bwd_matches_formula(ops, T, d, drop, masked):
     rmc = rowmask.cuda() if masked else None
     check(L.rp_post_attn_bwd(*[a.data_ptr() for a in args], None if rmc is None else rmc.data_ptr(), T, d, drop, seed, off2,
                              ctr.data_ptr(), o["d_t"].data_ptr() if need_dt else None, o["du"].data_ptr(), o["dh"].data_ptr(),
-                             o["d_o"].data_ptr(), dw.data_ptr(), db.data_ptr(), st), "rp_post_attn_bwd")
+                             o["d_o"].data_ptr(), dw.data_ptr(), db.data_ptr(), 0, st), "rp_post_attn_bwd")
     torch.cuda.synchronize()
     rel = lambda a, b: float((a.cpu().double() - b).norm() / b.norm())  # noqa: E731
     if need_dt:

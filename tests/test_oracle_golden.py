@@ -18,7 +18,7 @@ def load(golden_dir, name):
     return z, sd
 
 
-@pytest.mark.parametrize("name", ["sasrec_new_tiny.npz", "sasrec_new_small.npz"])
+@pytest.mark.parametrize("name", ["sasrec_new_tiny.npz", "sasrec_new_small.npz", "sasrec_new_d192h4.npz", "sasrec_new_d64h2.npz"])
 def test_new_sasrec_matches_reference(golden_dir, name):
     z, sd = load(golden_dir, name)
     P = osr.params_from_new_state_dict(sd)
@@ -57,8 +57,9 @@ def test_new_sasrec_matches_reference(golden_dir, name):
             torch.testing.assert_close(p1, ref, rtol=1e-5, atol=1e-6)
 
 
-def test_legacy_sasrec_matches_reference(golden_dir):
-    z, sd = load(golden_dir, "sasrec_legacy_tiny.npz")
+@pytest.mark.parametrize("name", ["sasrec_legacy_tiny.npz", "sasrec_legacy_d50h1.npz"])
+def test_legacy_sasrec_matches_reference(golden_dir, name):
+    z, sd = load(golden_dir, name)
     P = osr.params_from_legacy_state_dict(sd)
     ids, pm = torch.from_numpy(z["ids"]), torch.from_numpy(z["pad_mask"])
     labels, tm = torch.from_numpy(z["labels"]), torch.from_numpy(z["target_mask"])

@@ -36,6 +36,24 @@ class BertConfig:
             raise ValueError("head_dim must be 64 or 128 (tcgen05 128B-swizzle tile constraint)")
 
 
+    # the shared engine code asks every config for its feature-slot geometry; BERT4Rec has no padded layout (head_dim 64 / 128)
+    @property
+    def head_dim(self) -> int:
+        return self.d // self.n_heads
+
+    @property
+    def head_slot(self) -> int:
+        return self.head_dim
+
+    @property
+    def dp(self) -> int:
+        return self.d
+
+    @property
+    def hd_valid(self) -> int:
+        return 0
+
+
 _BERT_BLOCK = ("ln1_w", "ln1_b", "in_w", "in_b", "out_w", "out_b", "ln2_w", "ln2_b", "w1", "b1", "w2", "b2")
 
 

@@ -32,19 +32,34 @@ struct LnQkvParams {
   float* rstd_out;
 };
 
+// pack 8 fp32 accumulator words (+ bias) into 4 bf16 pairs
+__device__ __forceinline__ uint4 pack8_bias(const uint32_t* r, const float* bb) {
+  return make_uint4(pack_bf16(__uint_as_float(r[0]) + bb[0], __uint_as_float(r[1]) + bb[1]),
+                    pack_bf16(__uint_as_float(r[2]) + bb[2], __uint_as_float(r[3]) + bb[3]),
+                    pack_bf16(__uint_as_float(r[4]) + bb[4], __uint_as_float(r[5]) + bb[5]),
+                    pack_bf16(__uint_as_float(r[6]) + bb[6], __uint_as_float(r[7]) + bb[7]));
+}
+
+// Output tiles leave through shared memory and TMA stores: a thread owns one ROW of the tile, so direct global stores are 32
+// different 128-byte lines per warp instruction (ncu r2c: l1tex LSU wavefronts 60 % busy = the limiter of round 2's first
+// version, 31 sectors per store request); staged in a swizzled [128 x 64] tile the four warps of a column half write
+// conflict-free 16-byte pieces and ONE thread hands the tile to the TMA unit.
 template <int KCH, int NA>
 __global__ void __launch_bounds__(kBfThreads, 1)
 ln_qkv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWq,
-                    const __grid_constant__ CUtensorMap tmWkv, const LnQkvParams p) {
+                    const __grid_constant__ CUtensorMap tmWkv, const __grid_constant__ CUtensorMap tmOq,
+                    const __grid_constant__ CUtensorMap tmOQ, const __grid_constant__ CUtensorMap tmOKV, const LnQkvParams p) {
   constexpr int D = KCH * 64;
   constexpr int WQ_BYTES = KCH * D * 128;        // [D x D] as KCH chunks of [D rows x 64]
   constexpr int WKV_BYTES = KCH * 2 * D * 128;   // [2D x D]
   constexpr int X_STAGE = KCH * 128 * 128;       // [128 x D]
+  constexpr int STG = 128 * 128;                 // one [128 rows x 64 columns] bf16 staging tile per column half
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sWq = smem;
   uint8_t* sWkv = smem + WQ_BYTES;
   uint8_t* sX = smem + WQ_BYTES + WKV_BYTES;
+  uint8_t* sOut = sX + NA * X_STAGE;
   __shared__ uint64_t bar_w, x_full[NA], x_empty[NA], kv_full, kv_free, q_ready, q_full, q_free;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_lnw[D], s_lnb[D], s_bias[3 * D];
@@ -68,6 +83,9 @@ ln_qkv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmWq);
     tma_prefetch_desc(&tmWkv);
+    tma_prefetch_desc(&tmOq);
+    tma_prefetch_desc(&tmOQ);
+    tma_prefetch_desc(&tmOKV);
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
   if (threadIdx.x >= 64)
@@ -144,6 +162,23 @@ ln_qkv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const bool has_half = half * 64 < D;
     const int c0 = half * 64;
+    uint8_t* stg = sOut + half * STG;                      // this column half's staging tile
+    const bool leader = (ew & 3) == 0 && lane == 0;        // issues / tracks this half's TMA stores
+    // the row fragment `pk` (64 bf16 of this thread's row) -> staging tile -> global [128 x 64] box at (x, tile * 128)
+    auto stage_store = [&](const uint32_t(&pk)[32], const CUtensorMap* tm, int x, int y) {
+      if (leader) tma_store_wait_read();                   // the previous store has finished reading the staging tile
+      named_bar_sync(2 + half, 128);
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8)
+        *reinterpret_cast<uint4*>(stg + sw128_off((uint32_t)row, (uint32_t)c8)) =
+            make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
+      fence_proxy_async();
+      named_bar_sync(2 + half, 128);
+      if (leader) {
+        tma_store_2d(tm, stg, x, y);
+        tma_store_commit();
+      }
+    };
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t s = it % NA, ph = (it / NA) & 1, tp = it & 1;
       const int t = (int)blockIdx.x + it * (int)gridDim.x;
@@ -188,27 +223,27 @@ ln_qkv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         // TA is free: its last reader (the previous tile's Q GEMM) completed before q_full, which this warp waited for below
         tmem_st16(TA + lane_base + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
         tmem_st16(TA + lane_base + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
-        if (row_ok) {
-          uint4* qs = reinterpret_cast<uint4*>(p.q_in + (size_t)m * D + c0);
-#pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) qs[c8] = make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
-          if (half == 0 && p.mean_out) {
-            p.mean_out[m] = mean;
-            p.rstd_out[m] = rstd;
-          }
+        if (row_ok && half == 0 && p.mean_out) {
+          p.mean_out[m] = mean;
+          p.rstd_out[m] = rstd;
         }
         tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&q_ready);
+        stage_store(pk, &tmOq, c0, t * 128);
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&q_ready);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&q_ready);
       // ---- [K | V] = acc + bias: this thread drains columns [half*D, half*D + D) of its row, 64 at a time
       mbar_wait(&kv_full, tp);
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < D; cc += 64) {
         const int col = half * D + cc;
-        uint32_t r0[32], r1[32];
+        uint32_t r0[32], r1[32], pk[32];
         tmem_ld32(TKV + lane_base + col, r0);
         tmem_ld32(TKV + lane_base + col + 32, r1);
         tmem_ld_wait();
@@ -217,54 +252,41 @@ ln_qkv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(&kv_free);
         }
-        if (row_ok) {
-          uint4* o = reinterpret_cast<uint4*>(p.KV + (size_t)m * (2 * D) + col);
-          const float* bb = &s_bias[D + col];
+        const float* bb = &s_bias[D + col];
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            o[c8] = make_uint4(pack_bf16(__uint_as_float(r0[c8 * 8]) + bb[c8 * 8], __uint_as_float(r0[c8 * 8 + 1]) + bb[c8 * 8 + 1]),
-                               pack_bf16(__uint_as_float(r0[c8 * 8 + 2]) + bb[c8 * 8 + 2], __uint_as_float(r0[c8 * 8 + 3]) + bb[c8 * 8 + 3]),
-                               pack_bf16(__uint_as_float(r0[c8 * 8 + 4]) + bb[c8 * 8 + 4], __uint_as_float(r0[c8 * 8 + 5]) + bb[c8 * 8 + 5]),
-                               pack_bf16(__uint_as_float(r0[c8 * 8 + 6]) + bb[c8 * 8 + 6], __uint_as_float(r0[c8 * 8 + 7]) + bb[c8 * 8 + 7]));
-            o[4 + c8] = make_uint4(pack_bf16(__uint_as_float(r1[c8 * 8]) + bb[32 + c8 * 8], __uint_as_float(r1[c8 * 8 + 1]) + bb[32 + c8 * 8 + 1]),
-                                   pack_bf16(__uint_as_float(r1[c8 * 8 + 2]) + bb[32 + c8 * 8 + 2], __uint_as_float(r1[c8 * 8 + 3]) + bb[32 + c8 * 8 + 3]),
-                                   pack_bf16(__uint_as_float(r1[c8 * 8 + 4]) + bb[32 + c8 * 8 + 4], __uint_as_float(r1[c8 * 8 + 5]) + bb[32 + c8 * 8 + 5]),
-                                   pack_bf16(__uint_as_float(r1[c8 * 8 + 6]) + bb[32 + c8 * 8 + 6], __uint_as_float(r1[c8 * 8 + 7]) + bb[32 + c8 * 8 + 7]));
-          }
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const uint4 a = pack8_bias(&r0[c8 * 8], bb + c8 * 8), b = pack8_bias(&r1[c8 * 8], bb + 32 + c8 * 8);
+          pk[c8 * 4] = a.x; pk[c8 * 4 + 1] = a.y; pk[c8 * 4 + 2] = a.z; pk[c8 * 4 + 3] = a.w;
+          pk[16 + c8 * 4] = b.x; pk[16 + c8 * 4 + 1] = b.y; pk[16 + c8 * 4 + 2] = b.z; pk[16 + c8 * 4 + 3] = b.w;
         }
+        stage_store(pk, &tmOKV, col, t * 128);
       }
       // ---- Q = acc + bq
       mbar_wait(&q_full, tp);
       tc_fence_after();
       if (has_half) {
-        uint32_t r0[32], r1[32];
+        uint32_t r0[32], r1[32], pk[32];
         tmem_ld32(TQ + lane_base + c0, r0);
         tmem_ld32(TQ + lane_base + c0 + 32, r1);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&q_free);
-        if (row_ok) {
-          uint4* o = reinterpret_cast<uint4*>(p.Q + (size_t)m * D + c0);
-          const float* bb = &s_bias[c0];
+        const float* bb = &s_bias[c0];
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            o[c8] = make_uint4(pack_bf16(__uint_as_float(r0[c8 * 8]) + bb[c8 * 8], __uint_as_float(r0[c8 * 8 + 1]) + bb[c8 * 8 + 1]),
-                               pack_bf16(__uint_as_float(r0[c8 * 8 + 2]) + bb[c8 * 8 + 2], __uint_as_float(r0[c8 * 8 + 3]) + bb[c8 * 8 + 3]),
-                               pack_bf16(__uint_as_float(r0[c8 * 8 + 4]) + bb[c8 * 8 + 4], __uint_as_float(r0[c8 * 8 + 5]) + bb[c8 * 8 + 5]),
-                               pack_bf16(__uint_as_float(r0[c8 * 8 + 6]) + bb[c8 * 8 + 6], __uint_as_float(r0[c8 * 8 + 7]) + bb[c8 * 8 + 7]));
-            o[4 + c8] = make_uint4(pack_bf16(__uint_as_float(r1[c8 * 8]) + bb[32 + c8 * 8], __uint_as_float(r1[c8 * 8 + 1]) + bb[32 + c8 * 8 + 1]),
-                                   pack_bf16(__uint_as_float(r1[c8 * 8 + 2]) + bb[32 + c8 * 8 + 2], __uint_as_float(r1[c8 * 8 + 3]) + bb[32 + c8 * 8 + 3]),
-                                   pack_bf16(__uint_as_float(r1[c8 * 8 + 4]) + bb[32 + c8 * 8 + 4], __uint_as_float(r1[c8 * 8 + 5]) + bb[32 + c8 * 8 + 5]),
-                                   pack_bf16(__uint_as_float(r1[c8 * 8 + 6]) + bb[32 + c8 * 8 + 6], __uint_as_float(r1[c8 * 8 + 7]) + bb[32 + c8 * 8 + 7]));
-          }
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const uint4 a = pack8_bias(&r0[c8 * 8], bb + c8 * 8), b = pack8_bias(&r1[c8 * 8], bb + 32 + c8 * 8);
+          pk[c8 * 4] = a.x; pk[c8 * 4 + 1] = a.y; pk[c8 * 4 + 2] = a.z; pk[c8 * 4 + 3] = a.w;
+          pk[16 + c8 * 4] = b.x; pk[16 + c8 * 4 + 1] = b.y; pk[16 + c8 * 4 + 2] = b.z; pk[16 + c8 * 4 + 3] = b.w;
         }
+        stage_store(pk, &tmOQ, c0, t * 128);
       } else {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&q_free);
       }
     }
+    if (leader) tma_store_wait_all();   // the staging tile must outlive its last store
   }
   tc_fence_before();
   __syncthreads();
@@ -272,16 +294,16 @@ ln_qkv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 }
 
 template <int KCH>
-static int launch_ln_qkv(const CUtensorMap& tmX, const CUtensorMap& tmWq, const CUtensorMap& tmWkv, const LnQkvParams& p,
-                         cudaStream_t st) {
+static int launch_ln_qkv(const CUtensorMap& tmX, const CUtensorMap& tmWq, const CUtensorMap& tmWkv, const CUtensorMap& tmOq,
+                         const CUtensorMap& tmOQ, const CUtensorMap& tmOKV, const LnQkvParams& p, cudaStream_t st) {
   constexpr int D = KCH * 64;
-  constexpr int NA = 3;
-  const int smem = 3 * KCH * D * 128 + NA * KCH * 128 * 128 + 1024;
+  constexpr int NA = 2;
+  const int smem = 3 * KCH * D * 128 + NA * KCH * 128 * 128 + 2 * 128 * 128 + 1024;
   auto kern = ln_qkv_fused_kernel<KCH, NA>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int n_tiles = (p.T + 127) / 128;
   const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-  kern<<<grid, kBfThreads, smem, st>>>(tmX, tmWq, tmWkv, p);
+  kern<<<grid, kBfThreads, smem, st>>>(tmX, tmWq, tmWkv, tmOq, tmOQ, tmOKV, p);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }
@@ -302,17 +324,21 @@ RP_API int rp_ln_qkv_fused(const void* x, const float* ln_w, const float* ln_b, 
   if (d != 64 && d != 128) return RP_ESHAPE;
   if (hd_valid < 0 || hd_valid > 128 || (hd_valid > 0 && d % (hd_valid <= 64 ? 64 : 128))) return RP_ESHAPE;
   if (q_in == x || Q == x || KV == x) return RP_EINVAL;
-  CUtensorMap tmX, tmWq, tmWkv;
+  CUtensorMap tmX, tmWq, tmWkv, tmOq, tmOQ, tmOKV;
   int rc;
   if ((rc = make_tmap_bf16(&tmX, x, T, d, d, 128)) != RP_OK) return rc;
   if ((rc = make_tmap_bf16(&tmWq, w_in, d, d, d, d)) != RP_OK) return rc;
   if ((rc = make_tmap_bf16(&tmWkv, reinterpret_cast<const __nv_bfloat16*>(w_in) + (size_t)d * d, 2 * d, d, d, 2 * d)) != RP_OK)
     return rc;
+  if ((rc = make_tmap_bf16(&tmOq, q_in, T, d, d, 128)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmOQ, Q, T, d, d, 128)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&tmOKV, KV, T, 2 * d, 2 * d, 128)) != RP_OK) return rc;
   LnQkvParams p;
   p.ln_w = ln_w; p.ln_b = ln_b; p.b_in = b_in; p.eps = eps; p.T = T; p.hd_valid = hd_valid;
   p.q_in = reinterpret_cast<__nv_bfloat16*>(q_in); p.Q = reinterpret_cast<__nv_bfloat16*>(Q);
   p.KV = reinterpret_cast<__nv_bfloat16*>(KV); p.mean_out = mean_out; p.rstd_out = rstd_out;
-  return d == 64 ? launch_ln_qkv<1>(tmX, tmWq, tmWkv, p, stream) : launch_ln_qkv<2>(tmX, tmWq, tmWkv, p, stream);
+  return d == 64 ? launch_ln_qkv<1>(tmX, tmWq, tmWkv, tmOq, tmOQ, tmOKV, p, stream)
+                 : launch_ln_qkv<2>(tmX, tmWq, tmWkv, tmOq, tmOQ, tmOKV, p, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -377,7 +403,7 @@ template <int KCH, int NA>
 __global__ void __launch_bounds__(kBfThreads, 1)
 pre_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDKV,
                     const __grid_constant__ CUtensorMap tmWq, const __grid_constant__ CUtensorMap tmWkv,
-                    const PreAttnBwdParams p) {
+                    const __grid_constant__ CUtensorMap tmDX, const PreAttnBwdParams p) {
   constexpr int D = KCH * 64;
   constexpr int NCH = 3 * KCH;                  // A chunks ([128 x 64]) per tile: KCH of dQ, then 2 KCH of [dK | dV]
   constexpr int WQ_BYTES = KCH * KCH * 8192;    // MN-major B: K chunks (64 output features) x N chunks (64 input features)
@@ -388,6 +414,7 @@ pre_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_const
   uint8_t* sWq = smem;
   uint8_t* sWkv = smem + WQ_BYTES;
   uint8_t* sA = smem + WQ_BYTES + WKV_BYTES;
+  uint8_t* sOut = sA + NA * A_CHUNK;   // one [128 x 64] bf16 staging tile per column half: dx leaves through TMA stores
   __shared__ uint64_t bar_w, a_full[NA], a_empty[NA], acc_full[2], acc_free[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_lnw[D];
@@ -473,6 +500,8 @@ pre_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_const
     const bool has_half = half * 64 < D;
     const int c0 = half * 64;
     float acc_w0 = 0.f, acc_w1 = 0.f, acc_b0 = 0.f, acc_b1 = 0.f;   // columns c0 + 2*lane, +1 over this warp's rows, all tiles
+    uint8_t* stg = sOut + half * (128 * 128);
+    const bool leader = (ew & 3) == 0 && lane == 0;
     for (int n = 0; n < my_tiles; ++n) {
       const uint32_t pp = n & 1, pph = (n >> 1) & 1;
       const int t = (int)blockIdx.x + n * (int)gridDim.x;
@@ -534,7 +563,9 @@ pre_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_const
       const float m1 = (sa.x + sb.x) * inv_d, m2 = (sa.y + sb.y) * inv_d;
       asm volatile("bar.sync 1, %0;" ::"r"(kBfEpiWarps * 32) : "memory");
       if (has_half) {
-        // dx = dKV Wkv (second accumulator, read 32 columns at a time) + LayerNorm-backward(dq)
+        // dx = dKV Wkv (second accumulator, read 32 columns at a time) + LayerNorm-backward(dq), staged for one TMA store
+        if (leader) tma_store_wait_read();   // the previous tile's store has finished reading the staging tile
+        named_bar_sync(2 + half, 128);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t r2[32];
@@ -545,8 +576,7 @@ pre_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_free[pp]);
           }
-          if (row_ok) {
-            uint4* o = reinterpret_cast<uint4*>(p.dx + (size_t)m * D + c0 + hh * 32);
+          {
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
               uint32_t w32[4];
@@ -562,9 +592,15 @@ pre_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_const
                 }
                 w32[e] = pack_bf16(t0 + __uint_as_float(r2[q - hh * 32]), t1 + __uint_as_float(r2[q + 1 - hh * 32]));
               }
-              o[c8] = make_uint4(w32[0], w32[1], w32[2], w32[3]);
+              *reinterpret_cast<uint4*>(stg + sw128_off((uint32_t)row, (uint32_t)(hh * 4 + c8))) = make_uint4(w32[0], w32[1], w32[2], w32[3]);
             }
           }
+        }
+        fence_proxy_async();
+        named_bar_sync(2 + half, 128);
+        if (leader) {
+          tma_store_2d(&tmDX, stg, c0, t * 128);
+          tma_store_commit();
         }
         // LayerNorm parameter gradients: column sums over this warp's 32 rows (rows >= T hold zeros)
         {
@@ -588,6 +624,7 @@ pre_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_const
         if (lane == 0) mbar_arrive(&acc_free[pp]);
       }
     }
+    if (leader) tma_store_wait_all();   // the staging tile must outlive its last store
     // CTA-level reduction over the four lane quarters, then one atomic per column and CTA
     s_red[0][ew][2 * lane] = acc_w0;
     s_red[0][ew][2 * lane + 1] = acc_w1;
@@ -610,14 +647,14 @@ pre_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDQ, const __grid_const
 
 template <int KCH>
 static int launch_pre_attn_bwd(const CUtensorMap& tmDQ, const CUtensorMap& tmDKV, const CUtensorMap& tmWq,
-                               const CUtensorMap& tmWkv, const PreAttnBwdParams& p, cudaStream_t st) {
-  constexpr int NA = 6;
-  const int smem = 3 * KCH * KCH * 8192 + NA * 128 * 128 + 1024;
+                               const CUtensorMap& tmWkv, const CUtensorMap& tmDX, const PreAttnBwdParams& p, cudaStream_t st) {
+  constexpr int NA = 5;
+  const int smem = 3 * KCH * KCH * 8192 + NA * 128 * 128 + 2 * 128 * 128 + 1024;
   auto kern = pre_attn_bwd_kernel<KCH, NA>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int n_tiles = (p.T + 127) / 128;
   const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-  kern<<<grid, kBfThreads, smem, st>>>(tmDQ, tmDKV, tmWq, tmWkv, p);
+  kern<<<grid, kBfThreads, smem, st>>>(tmDQ, tmDKV, tmWq, tmWkv, tmDX, p);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }
@@ -633,8 +670,9 @@ RP_API int rp_pre_attn_bwd(const void* dQ, const void* dKV, const void* dh, cons
   if (d != 64 && d != 128) return RP_ESHAPE;
   if (hd_valid < 0 || hd_valid > 128 || (hd_valid > 0 && d % (hd_valid <= 64 ? 64 : 128))) return RP_ESHAPE;
   if (dx == dQ || dx == dKV || dx == dh || dx == x) return RP_EINVAL;
-  CUtensorMap tmDQ, tmDKV, tmWq, tmWkv;
+  CUtensorMap tmDQ, tmDKV, tmWq, tmWkv, tmDX;
   int rc;
+  if ((rc = make_tmap_bf16(&tmDX, dx, T, d, d, 128)) != RP_OK) return rc;
   if ((rc = make_tmap_bf16(&tmDQ, dQ, T, d, d, 128)) != RP_OK) return rc;
   if ((rc = make_tmap_bf16(&tmDKV, dKV, T, 2 * d, 2 * d, 128)) != RP_OK) return rc;
   if ((rc = make_tmap_bf16(&tmWq, w_in, d, d, d, 64)) != RP_OK) return rc;
@@ -644,6 +682,6 @@ RP_API int rp_pre_attn_bwd(const void* dQ, const void* dKV, const void* dh, cons
   p.dh = reinterpret_cast<const __nv_bfloat16*>(dh); p.x = reinterpret_cast<const __nv_bfloat16*>(x);
   p.mean = mean; p.rstd = rstd; p.ln_w = ln_w; p.dx = reinterpret_cast<__nv_bfloat16*>(dx);
   p.dln_w = dln_w; p.dln_b = dln_b; p.T = T; p.hd_valid = hd_valid;
-  return d == 64 ? launch_pre_attn_bwd<1>(tmDQ, tmDKV, tmWq, tmWkv, p, stream)
-                 : launch_pre_attn_bwd<2>(tmDQ, tmDKV, tmWq, tmWkv, p, stream);
+  return d == 64 ? launch_pre_attn_bwd<1>(tmDQ, tmDKV, tmWq, tmWkv, tmDX, p, stream)
+                 : launch_pre_attn_bwd<2>(tmDQ, tmDKV, tmWq, tmWkv, tmDX, p, stream);
 }

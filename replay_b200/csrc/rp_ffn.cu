@@ -251,11 +251,16 @@ __device__ __forceinline__ void drop4(float& a, float& b, float& c, float& d, un
   d = r.w >= thr ? d * ks : 0.f;
 }
 
+// the four output tensor maps (box [128 rows x 64 columns]): h, y, u (training only) and the block output
+struct PostAttnOutMaps {
+  CUtensorMap h, y, u, out;
+};
+
 template <int KCH, int NA, bool TRAIN>
 __global__ void __launch_bounds__(kFfnThreads, 1)
 post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWo,
                        const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                       const PostAttnParams p) {
+                       const __grid_constant__ PostAttnOutMaps om, const PostAttnParams p) {
   constexpr int D = KCH * 64;
   constexpr int W_BYTES = KCH * D * 128;
   constexpr int O_STAGE = KCH * 128 * 128;
@@ -265,6 +270,7 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
   uint8_t* sW1 = smem + W_BYTES;
   uint8_t* sW2 = smem + 2 * W_BYTES;
   uint8_t* sO = smem + 3 * W_BYTES;
+  uint8_t* sOut = sO + NA * O_STAGE;   // one [128 x 64] bf16 staging tile per column half: outputs leave through TMA stores
   // TWO tiles in flight per CTA (parity p = tile & 1): the three MMAs of one tile alternate with those of the other, so every
   // epilogue (LayerNorm, ReLU, output) overlaps an MMA of the other tile instead of sitting on a serial chain.
   __shared__ uint64_t bar_w, o_full[NA], o_empty[NA], g0_full[2], y_ready[2], g1_full[2], u_ready[2], g2_full[2], tile_done[2];
@@ -390,6 +396,25 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
     const float keep_scale = (TRAIN && p.drop_p > 0.f) ? 1.f / (1.f - p.drop_p) : 1.f;
     const uint32_t drop_thr = (TRAIN && p.drop_p > 0.f) ? (uint32_t)(p.drop_p * 4294967296.0) : 0u;
     const unsigned long long seed_eff = TRAIN ? p.seed + ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull) : 0ull;
+    // a thread owns one ROW: direct global stores would be 32 different 128-byte lines per warp instruction (the L1 LSU
+    // wavefront limit measured in profiles/r2c_body_ncu.md); the row pieces go to a swizzled staging tile instead and one
+    // thread per column half hands the [128 x 64] tile to the TMA unit (rows beyond T are clipped by the hardware)
+    uint8_t* stg = sOut + half * (128 * 128);
+    const bool leader = (ew & 3) == 0 && lane == 0;
+    auto stage_store = [&](const uint32_t(&pk)[32], const CUtensorMap* tm, int y) {
+      if (leader) tma_store_wait_read();
+      named_bar_sync(2 + half, 128);
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8)
+        *reinterpret_cast<uint4*>(stg + sw128_off((uint32_t)row, (uint32_t)c8)) =
+            make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
+      fence_proxy_async();
+      named_bar_sync(2 + half, 128);
+      if (leader) {
+        tma_store_2d(tm, stg, c0, y);
+        tma_store_commit();
+      }
+    };
     for (int pi = 0; pi < n_pairs; ++pi) {
       const uint32_t pph = pi & 1;
 #pragma unroll 1
@@ -434,12 +459,11 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
                   sq = fmaf(v0, v0, fmaf(v1, v1, sq));
                 }
               }
-              if (TRAIN && row_ok) {
-                uint4* hs = reinterpret_cast<uint4*>(p.h_save + (size_t)m * D + c0);
+              if (TRAIN) {
+                uint32_t ph[32];
 #pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8)
-                  hs[c8] = make_uint4(pack_bf16(hv[c8 * 8], hv[c8 * 8 + 1]), pack_bf16(hv[c8 * 8 + 2], hv[c8 * 8 + 3]),
-                                      pack_bf16(hv[c8 * 8 + 4], hv[c8 * 8 + 5]), pack_bf16(hv[c8 * 8 + 6], hv[c8 * 8 + 7]));
+                for (int q = 0; q < 64; q += 2) ph[q >> 1] = pack_bf16(hv[q], hv[q + 1]);
+                stage_store(ph, &om.h, t * 128);
               }
             }
             s_stat[half][row] = make_float2(sum, sq);
@@ -460,20 +484,20 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
               }
               tmem_st16(R0 + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
               tmem_st16(R0 + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
-              if (TRAIN && row_ok) {
-                uint4* ys = reinterpret_cast<uint4*>(p.y_save + (size_t)m * D + c0);
-#pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) ys[c8] = make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
-                if (half == 0) {
-                  p.mean_out[m] = mean;
-                  p.rstd_out[m] = rstd;
-                }
+              if (TRAIN && row_ok && half == 0) {
+                p.mean_out[m] = mean;
+                p.rstd_out[m] = rstd;
               }
               tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&y_ready[pp]);   // the next GEMM starts while y travels to HBM
+              if (TRAIN) stage_store(pk, &om.y, t * 128);
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&y_ready[pp]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&y_ready[pp]);
           } else if (stage == 1) {
             // ---- u = relu(y W1^T + b1) -> TMEM (R1, first 32 columns of the half); y copied next to it, R0 becomes free
             mbar_wait(&g1_full[pp], pph);
@@ -509,20 +533,20 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
                                                 fmaxf(__uint_as_float(r1[q + 1]) + s_vec[3][c0 + 32 + q + 1], 0.f));
                 }
               }
-              if (TRAIN && row_ok) {
-                uint4* us = reinterpret_cast<uint4*>(p.u_save + (size_t)m * D + c0);
-#pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) us[c8] = make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
-              }
               tmem_st16(R1 + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
               tmem_st16(R1 + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
               tmem_st16(R1 + c0 + 32, *reinterpret_cast<uint32_t(*)[16]>(&yk[0]));
               tmem_st16(R1 + c0 + 48, *reinterpret_cast<uint32_t(*)[16]>(&yk[16]));
               tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&u_ready[pp]);
+              if (TRAIN) stage_store(pk, &om.u, t * 128);
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&u_ready[pp]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&u_ready[pp]);
           } else {
             // ---- out = u W2^T + b2 + y   (acc2 in R0, y re-read from its copy in R1)
             mbar_wait(&g2_full[pp], pph);
@@ -537,29 +561,25 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
               __syncwarp();
               if (lane == 0) mbar_arrive(&tile_done[pp]);  // everything of this tile is in registers
               const float keep = (p.rowmask == nullptr || (row_ok && p.rowmask[m])) ? 1.f : 0.f;
-              if (row_ok) {
-                __nv_bfloat16* o = p.out + (size_t)m * D + c0;
+              uint32_t po[32];
 #pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {
-                  uint4 w;
-                  uint32_t* w32 = reinterpret_cast<uint32_t*>(&w);
+              for (int c8 = 0; c8 < 8; ++c8) {
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const int col = c8 * 8 + 2 * e;
-                    const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yk[col >> 1]));
-                    float f0 = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + s_vec[4][c0 + col];
-                    float f1 = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + s_vec[4][c0 + col + 1];
-                    if (TRAIN && p.drop_p > 0.f) {  // element pair (col, col+1) of the 4-group starting at col & ~3
-                      const uint4 rr = rng4x32(seed_eff, (p.off2 + (unsigned long long)m * D + c0 + col) >> 2);
-                      const uint32_t w0 = (col & 2) ? rr.z : rr.x, w1 = (col & 2) ? rr.w : rr.y;
-                      f0 = w0 >= drop_thr ? f0 * keep_scale : 0.f;
-                      f1 = w1 >= drop_thr ? f1 * keep_scale : 0.f;
-                    }
-                    w32[e] = pack_bf16((f0 + yf.x) * keep, (f1 + yf.y) * keep);
+                for (int e = 0; e < 4; ++e) {
+                  const int col = c8 * 8 + 2 * e;
+                  const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yk[col >> 1]));
+                  float f0 = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + s_vec[4][c0 + col];
+                  float f1 = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + s_vec[4][c0 + col + 1];
+                  if (TRAIN && p.drop_p > 0.f) {  // element pair (col, col+1) of the 4-group starting at col & ~3
+                    const uint4 rr = rng4x32(seed_eff, (p.off2 + (unsigned long long)m * D + c0 + col) >> 2);
+                    const uint32_t w0 = (col & 2) ? rr.z : rr.x, w1 = (col & 2) ? rr.w : rr.y;
+                    f0 = w0 >= drop_thr ? f0 * keep_scale : 0.f;
+                    f1 = w1 >= drop_thr ? f1 * keep_scale : 0.f;
                   }
-                  *reinterpret_cast<uint4*>(o + c8 * 8) = w;
+                  po[c8 * 4 + e] = pack_bf16((f0 + yf.x) * keep, (f1 + yf.y) * keep);
                 }
               }
+              stage_store(po, &om.out, t * 128);
             } else {
               tc_fence_before();
               __syncwarp();
@@ -569,6 +589,7 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
         }
       }
     }
+    if (leader) tma_store_wait_all();   // the staging tile must outlive its last store
   }
   tc_fence_before();
   __syncthreads();
@@ -580,12 +601,21 @@ static int launch_post_attn(const CUtensorMap& tmO, const CUtensorMap& tmWo, con
                             const PostAttnParams& p, cudaStream_t st) {
   constexpr int D = KCH * 64;
   constexpr int NA = KCH == 1 ? 4 : 2;
-  const int smem = 3 * KCH * D * 128 + NA * KCH * 128 * 128 + 1024;
+  const int smem = 3 * KCH * D * 128 + NA * KCH * 128 * 128 + 2 * 128 * 128 + 1024;
+  PostAttnOutMaps om;
+  int rc;
+  if ((rc = make_tmap_bf16(&om.out, p.out, p.T, D, D, 128)) != RP_OK) return rc;
+  om.h = om.y = om.u = om.out;
+  if (TRAIN) {
+    if ((rc = make_tmap_bf16(&om.h, p.h_save, p.T, D, D, 128)) != RP_OK) return rc;
+    if ((rc = make_tmap_bf16(&om.y, p.y_save, p.T, D, D, 128)) != RP_OK) return rc;
+    if ((rc = make_tmap_bf16(&om.u, p.u_save, p.T, D, D, 128)) != RP_OK) return rc;
+  }
   auto kern = post_attn_fused_kernel<KCH, NA, TRAIN>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int n_tiles = (p.T + 127) / 128;
   const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-  kern<<<grid, kFfnThreads, smem, st>>>(tmO, tmWo, tmW1, tmW2, p);
+  kern<<<grid, kFfnThreads, smem, st>>>(tmO, tmWo, tmW1, tmW2, om, p);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }

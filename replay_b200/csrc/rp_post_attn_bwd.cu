@@ -56,11 +56,16 @@ __device__ __forceinline__ void warp_colsum64_pb(float (&v)[64], int lane) {
   }
 }
 
+// output tensor maps (box [128 rows x 64 columns]): d_t (valid only when p.d_t != null), du, dh, d_o
+struct PostAttnBwdOutMaps {
+  CUtensorMap d_t, du, dh, d_o;
+};
+
 template <int KCH, int NA>
 __global__ void __launch_bounds__(kPbThreads, 1)
 post_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ CUtensorMap tmW2,
                      const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmWo,
-                     const PostAttnBwdParams p) {
+                     const __grid_constant__ PostAttnBwdOutMaps om, const PostAttnBwdParams p) {
   constexpr int D = KCH * 64;
   constexpr int W_BYTES = KCH * KCH * 8192;   // MN-major B: K chunks (64 output features) x N chunks (64 input features)
   constexpr int Z_STAGE = KCH * 128 * 128;
@@ -70,6 +75,7 @@ post_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
   uint8_t* sW1 = smem + W_BYTES;
   uint8_t* sWo = smem + 2 * W_BYTES;
   uint8_t* sZ = smem + 3 * W_BYTES;
+  uint8_t* sOut = sZ + NA * Z_STAGE;   // one [128 x 64] bf16 staging tile per column half: outputs leave through TMA stores
   __shared__ uint64_t bar_w, z_full[NA], z_empty[NA], a_ready[3][2], g_full[3][2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_lnw[D];
@@ -162,6 +168,24 @@ post_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
     const uint32_t thr = p.drop_p > 0.f ? (uint32_t)(p.drop_p * 4294967296.0) : 0u;
     const unsigned long long seed_eff = p.seed + ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
     float acc_w0 = 0.f, acc_w1 = 0.f, acc_b0 = 0.f, acc_b1 = 0.f;
+    // row pieces -> swizzled staging tile -> one TMA store per [128 x 64] tile (a thread owns a ROW: direct global stores are
+    // 32 different lines per warp instruction, the L1 LSU wavefront limit of profiles/r2c_body_ncu.md); rows >= T are clipped
+    uint8_t* stg = sOut + half * (128 * 128);
+    const bool leader = (ew & 3) == 0 && lane == 0;
+    auto stage_store = [&](const uint32_t(&pk)[32], const CUtensorMap* tm, int y) {
+      if (leader) tma_store_wait_read();
+      named_bar_sync(2 + half, 128);
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8)
+        *reinterpret_cast<uint4*>(stg + sw128_off((uint32_t)row, (uint32_t)c8)) =
+            make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
+      fence_proxy_async();
+      named_bar_sync(2 + half, 128);
+      if (leader) {
+        tma_store_2d(tm, stg, c0, y);
+        tma_store_commit();
+      }
+    };
     for (int pi = 0; pi < n_pairs; ++pi) {
       const uint32_t pph = pi & 1;
 #pragma unroll 1
@@ -206,16 +230,16 @@ post_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
               }
               tmem_st16(R0 + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
               tmem_st16(R0 + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
-              if (p.d_t != nullptr && row_ok) {
-                uint4* o = reinterpret_cast<uint4*>(p.d_t + (size_t)m * D + c0);
-#pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) o[c8] = make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
-              }
               tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&a_ready[0][pp]);
+              if (p.d_t != nullptr) stage_store(pk, &om.d_t, t * 128);
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&a_ready[0][pp]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_ready[0][pp]);
           } else if (stage == 1) {
             // ---- du = (d_t W2) * [u != 0] / keep  -> TMEM (in place over this warp's own accumulator columns) and HBM
             uint32_t uk[32];
@@ -243,16 +267,16 @@ post_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
               }
               tmem_st16(R1 + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
               tmem_st16(R1 + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
-              if (row_ok) {
-                uint4* o = reinterpret_cast<uint4*>(p.du + (size_t)m * D + c0);
-#pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) o[c8] = make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
-              }
               tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&a_ready[1][pp]);
+              stage_store(pk, &om.du, t * 128);
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&a_ready[1][pp]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_ready[1][pp]);
           } else if (stage == 2) {
             // ---- dy = du W1 + dz*pad ; dh = LayerNorm2-backward(dy) -> TMEM (in place) and HBM ; LN parameter gradients
             uint32_t hp[32];
@@ -328,16 +352,16 @@ post_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
               }
               tmem_st16(R0 + c0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
               tmem_st16(R0 + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
-              if (row_ok) {
-                uint4* o = reinterpret_cast<uint4*>(p.dh + (size_t)m * D + c0);
-#pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) o[c8] = make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
-              }
               tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&a_ready[2][pp]);   // GEMM 3 may start while dh travels and the column sums are formed
+              stage_store(pk, &om.dh, t * 128);
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&a_ready[2][pp]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_ready[2][pp]);   // GEMM 3 may start while the column sums below are formed
             if (has_half) {
               float pw[64];
 #pragma unroll
@@ -362,26 +386,20 @@ post_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
               tmem_ld32(R1 + c0, r0);
               tmem_ld32(R1 + c0 + 32, r1);
               tmem_ld_wait();
-              if (row_ok) {
-                uint4* o = reinterpret_cast<uint4*>(p.d_o + (size_t)m * D + c0);
+              tc_fence_before();   // the next pair's stage 0 overwrites R0 / GEMM 1 overwrites R1: ordered after these loads
+              uint32_t po[32];
 #pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
-                  o[c8] = make_uint4(pack_bf16(__uint_as_float(r0[c8 * 8]), __uint_as_float(r0[c8 * 8 + 1])),
-                                     pack_bf16(__uint_as_float(r0[c8 * 8 + 2]), __uint_as_float(r0[c8 * 8 + 3])),
-                                     pack_bf16(__uint_as_float(r0[c8 * 8 + 4]), __uint_as_float(r0[c8 * 8 + 5])),
-                                     pack_bf16(__uint_as_float(r0[c8 * 8 + 6]), __uint_as_float(r0[c8 * 8 + 7])));
-                  o[4 + c8] = make_uint4(pack_bf16(__uint_as_float(r1[c8 * 8]), __uint_as_float(r1[c8 * 8 + 1])),
-                                         pack_bf16(__uint_as_float(r1[c8 * 8 + 2]), __uint_as_float(r1[c8 * 8 + 3])),
-                                         pack_bf16(__uint_as_float(r1[c8 * 8 + 4]), __uint_as_float(r1[c8 * 8 + 5])),
-                                         pack_bf16(__uint_as_float(r1[c8 * 8 + 6]), __uint_as_float(r1[c8 * 8 + 7])));
-                }
+              for (int q = 0; q < 32; q += 2) {
+                po[q >> 1] = pack_bf16(__uint_as_float(r0[q]), __uint_as_float(r0[q + 1]));
+                po[16 + (q >> 1)] = pack_bf16(__uint_as_float(r1[q]), __uint_as_float(r1[q + 1]));
               }
+              stage_store(po, &om.d_o, t * 128);
             }
-            tc_fence_before();   // the next pair's stage 0 overwrites R0 / GEMM 1 overwrites R1: ordered after these loads
           }
         }
       }
     }
+    if (leader) tma_store_wait_all();   // the staging tile must outlive its last store
     s_red[0][ew][2 * lane] = acc_w0;
     s_red[0][ew][2 * lane + 1] = acc_w1;
     s_red[1][ew][2 * lane] = acc_b0;
@@ -404,13 +422,21 @@ post_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
 template <int KCH>
 static int launch_post_attn_bwd(const CUtensorMap& tmDZ, const CUtensorMap& tmW2, const CUtensorMap& tmW1,
                                 const CUtensorMap& tmWo, const PostAttnBwdParams& p, cudaStream_t st) {
-  constexpr int NA = 3;
-  const int smem = 3 * KCH * KCH * 8192 + NA * KCH * 128 * 128 + 1024;
+  constexpr int D = KCH * 64;
+  constexpr int NA = 2;   // two tiles in flight keep their dz tile until their LayerNorm stage
+  const int smem = 3 * KCH * KCH * 8192 + NA * KCH * 128 * 128 + 2 * 128 * 128 + 1024;
+  PostAttnBwdOutMaps om;
+  int rc;
+  if ((rc = make_tmap_bf16(&om.du, p.du, p.T, D, D, 128)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&om.dh, p.dh, p.T, D, D, 128)) != RP_OK) return rc;
+  if ((rc = make_tmap_bf16(&om.d_o, p.d_o, p.T, D, D, 128)) != RP_OK) return rc;
+  om.d_t = om.du;
+  if (p.d_t && (rc = make_tmap_bf16(&om.d_t, p.d_t, p.T, D, D, 128)) != RP_OK) return rc;
   auto kern = post_attn_bwd_kernel<KCH, NA>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int n_tiles = (p.T + 127) / 128;
   const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-  kern<<<grid, kPbThreads, smem, st>>>(tmDZ, tmW2, tmW1, tmWo, p);
+  kern<<<grid, kPbThreads, smem, st>>>(tmDZ, tmW2, tmW1, tmWo, om, p);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }

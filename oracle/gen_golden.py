@@ -393,6 +393,32 @@ def gen_sampled_losses():
     print("wrote sampled_losses")
 
 
+def gen_metrics_known():
+    """TorchMetricsBuilder (replay/metrics/torch_metrics_builder.py) on a seeded case incl. novelty and coverage: pins the
+    on-device mirror ``replay_b200.nn.lightning.RankingMetrics``."""
+    from replay.metrics.torch_metrics_builder import TorchMetricsBuilder
+
+    g = torch.Generator().manual_seed(77)
+    n_items, B, K = 60, 40, 20
+    names = ["recall", "precision", "ndcg", "map", "mrr", "novelty", "coverage"]
+    b = TorchMetricsBuilder(names, top_k=[1, 5, 10, 20], item_count=n_items)
+    out = {}
+    for i in range(3):
+        pred = torch.stack([torch.randperm(n_items, generator=g)[:K] for _ in range(B)])
+        gt = torch.randint(0, n_items, (B, 6), generator=g)
+        gt[torch.rand(B, 6, generator=g) < 0.4] = -1
+        train = torch.randint(0, n_items, (B, 12), generator=g)
+        train[torch.rand(B, 12, generator=g) < 0.3] = -2
+        b.add_prediction(pred, gt, train)
+        out[f"pred{i}"], out[f"gt{i}"], out[f"train{i}"] = pred.numpy(), gt.numpy(), train.numpy()
+    res = b.get_metrics()
+    out["names"] = np.array(sorted(res))
+    out["values"] = np.array([res[k] for k in sorted(res)], dtype=np.float64)
+    out["n_items"] = n_items
+    np.savez_compressed(os.path.join(OUT, "metrics_known.npz"), **out)
+    print("wrote metrics_known", {k: round(v, 4) for k, v in list(res.items())[:4]})
+
+
 def gen_reference_default_shapes():
     """The reference's OWN default / example shapes, which are not multiples of the kernels' 64-wide feature slots:
     SasRec.from_params defaults embedding_dim=192, num_heads=4 (head_dim 48; nn/sequential/sasrec/model.py:199-253), the legacy
@@ -408,6 +434,9 @@ if __name__ == "__main__":
     if len(_sys.argv) > 1 and _sys.argv[1] == "defaults":
         gen_reference_default_shapes()
         raise SystemExit(0)
+    if len(_sys.argv) > 1 and _sys.argv[1] == "metrics":
+        gen_metrics_known()
+        raise SystemExit(0)
     # shapes respect the CUDA path's tile constraints: hidden in {64,128,256,512}, head_dim in {64,128}
     gen_new_sasrec("tiny", B=6, L=16, d=64, H=1, n_items=300, n_blocks=2, seed=11)
     gen_new_sasrec("small", B=8, L=50, d=128, H=2, n_items=600, n_blocks=2, seed=12, with_adam=False)
@@ -418,3 +447,4 @@ if __name__ == "__main__":
     gen_dataset_layout()
     gen_sampled_losses()
     gen_reference_default_shapes()
+    gen_metrics_known()

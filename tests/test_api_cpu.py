@@ -311,3 +311,47 @@ def test_device_loader_sharding_covers_every_window_once():
         assert not torch.equal(loaders[0].epoch_indices(), shards[0])
     fixed = DeviceBatchLoader(st, 8, 16, 50, shuffle=False)
     assert torch.equal(fixed.epoch_indices(), torch.arange(fixed.n))
+
+
+def test_ranking_metrics_match_reference_builder_incl_novelty_and_coverage(golden_dir):
+    """tests/golden/metrics_known.npz holds the output of the REAL TorchMetricsBuilder (oracle/gen_golden.py metrics) over three
+    batches: recall / precision / ndcg / map / mrr / novelty @ {1,5,10,20} and coverage."""
+    import numpy as np
+
+    from replay_b200.nn.lightning import RankingMetrics
+
+    z = np.load(os.path.join(golden_dir, "metrics_known.npz"))
+    m = RankingMetrics(("recall", "precision", "ndcg", "map", "mrr", "novelty", "coverage"), (1, 5, 10, 20), item_count=int(z["n_items"]))
+    for i in range(3):
+        m.add_prediction(torch.from_numpy(z[f"pred{i}"]), torch.from_numpy(z[f"gt{i}"]), torch.from_numpy(z[f"train{i}"]))
+    r = m.get_metrics()
+    ref = dict(zip([str(n) for n in z["names"]], z["values"]))
+    assert set(r) == set(ref)
+    for k, v in ref.items():
+        assert abs(r[k] - v) < 1e-6, (k, r[k], v)
+
+
+def test_compute_metrics_callback_history_and_state_dict():
+    """metrics_callback.py:72-100,147-163: per-epoch history for validation and test stages, state_dict round trip."""
+    from replay_b200.nn.lightning import ComputeMetricsCallback
+
+    class _PL:  # a module without an engine: the callback takes the logits path
+        candidates_to_score = None
+        logged = {}
+
+        def log_dict(self, d, **k):
+            self.logged.update(d)
+
+    cb = ComputeMetricsCallback(metrics=("recall", "ndcg"), ks=(1, 2))
+    logits = torch.tensor([[0.1, 0.9, 0.3], [0.8, 0.2, 0.5]])
+    batch = {"ground_truth": torch.tensor([[1, -1], [2, -1]])}
+    for stage in ("validation", "test"):
+        getattr(cb, f"on_{stage}_epoch_start")(None, _PL())
+        getattr(cb, f"on_{stage}_batch_end")(None, _PL(), {"logits": logits}, batch, 0)
+        res = getattr(cb, f"on_{stage}_epoch_end")(None, _PL())
+        assert abs(res["recall@1"] - 0.5) < 1e-6 and abs(res["recall@2"] - 1.0) < 1e-6
+    assert cb.get_metrics("validate")[0]["recall@2"] == 1.0 and cb.get_metrics("test")[0]["recall@1"] == 0.5
+    sd = cb.state_dict()
+    cb2 = ComputeMetricsCallback(metrics=("recall", "ndcg"), ks=(1, 2))
+    cb2.load_state_dict({k: {str(e): m for e, m in v.items()} for k, v in sd.items()})  # keys come back as strings from json
+    assert cb2.get_metrics("validate") == cb.get_metrics("validate") and cb2.get_metrics("test") == cb.get_metrics("test")

@@ -269,9 +269,9 @@ int rp_post_attn_fused(const void* o, const void* q_in, const void* wo, const fl
 /* Training forward of everything after the attention of one SASRec block in one pass over the tokens:
  *   h = o Wo^T + bo + q_in ; y = LN(h) ; u = dropout1(relu(y W1^T + b1)) ; out = (y + dropout2(u W2^T + b2)) [* rowmask]
  * writing the activations the backward needs on the way (h, y, u bf16 [T, d]; LayerNorm mean / rstd fp32 [T]): 2 tensors read
- * and 4 written instead of the 14 [T, d] passes of out-projection GEMM + LayerNorm + two FFN GEMMs.  Dropout element e of a site
- * uses word (e & 3) of rng4x32(seed + *seed_ptr, (drop_off + e) >> 2), e = row * d + column - the stream of rp_gemm's epilogue
- * and rp_dropout_bwd, so the un-fused backward applies unchanged.  d in {64,128}; out may not alias o / q_in.
+ * and 4 written instead of the 14 [T, d] passes of out-projection GEMM + LayerNorm + two FFN GEMMs.  Element (row, column) of a
+ * dropout site is kept iff drop_mix(drop_row_key(seed + *seed_ptr, drop_off, row), drop_col_key(column)) >= p * 2^32
+ * (csrc/rp_philox.cuh) - the stream of rp_gemm's epilogue and rp_dropout_bwd, so the un-fused backward applies unchanged.  d in {64,128}; out may not alias o / q_in.
  *   replaces (train)  replay/nn/sequential/sasrec/transformer.py:99-110 ; replay/nn/ffn.py:43-57 ;
  *                     replay/models/nn/sequential/sasrec/model.py:435-441,496-506 */
 int rp_post_attn_train(const void* o, const void* q_in, const void* wo, const float* bo, const float* ln_w, const float* ln_b,

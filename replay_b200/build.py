@@ -21,7 +21,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", os.path.join(os.path.dirname(HERE), "include"),
-]
+] + os.environ.get("RP_NVCC_EXTRA", "").split()   # diagnostic builds only (e.g. -DRP_ATTN_TRACE), never the shipped library
 
 
 def _sources():

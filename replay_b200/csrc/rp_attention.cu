@@ -31,10 +31,16 @@ struct AttnParams {
 
 static constexpr float kLog2eA = 1.4426950408889634f;
 
+static constexpr int kAfThreads = 32 + 8 * 32;  // issuer warp + 8 softmax warps (lane quarter x even / odd 32-key chunks)
+
 // KB = number of 256-key blocks the CTA keeps resident (1: L <= 256, 2: L <= 512).  S [128 x 256*KB] fp32 fills 256*KB
 // TMEM columns; P (bf16) is written back over its first half and O accumulates behind it.
+// A query row is shared by TWO threads (even / odd 32-key chunks; row max and row sum meet in shared memory): 8 softmax
+// warps per CTA, 16 per SM - the kernel is bound by the integer / exp work of the element-wise passes, not by the MMAs, and
+// 4 warps per CTA left the ALU pipe half idle (ncu r2c).  Warps whose 32 rows lie beyond L do nothing; 32 x 32 chunks above
+// the causal diagonal are zero-filled without loads, exponentials or dropout draws.
 template <int HD, int KB>
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(kAfThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   constexpr int HC = HD / 64;                 // 64-wide head-dim chunks
@@ -46,7 +52,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Q_BYTES;
   uint8_t* sV = sK + KV_BYTES;
-  __shared__ uint64_t bar_load, bar_s, bar_p, bar_o;
+  __shared__ __align__(16) uint32_t s_colkey[256 * KB];   // dropout key of every key position
+  __shared__ float s_red[2][2][128];                        // [max | sum][chunk parity][row]
+  __shared__ uint64_t bar_load, bar_v, bar_s, bar_p, bar_o;
+  __shared__ uint64_t bar_pair[4][2][2];                    // [lane quarter][chunk parity of the loader][iteration parity]
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -59,15 +68,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (threadIdx.x == 0) {
     mbar_init(&bar_load, 1);
+    mbar_init(&bar_v, 1);
     mbar_init(&bar_s, 1);
-    mbar_init(&bar_p, 4);
+    mbar_init(&bar_p, 8);
     mbar_init(&bar_o, 1);
+    for (int t = 0; t < 16; ++t) mbar_init(&bar_pair[0][0][0] + t, 1);
     fence_barrier_init();
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
+    const int row0 = b * L;
+    mbar_arrive_expect_tx(&bar_load, HC * 128 * 128 + HC * n_boxes * 128 * 128);
+    mbar_arrive_expect_tx(&bar_v, HC * n_boxes * 128 * 128);
+    for (int c = 0; c < HC; ++c) {
+      tma_load_2d(sQ + c * 16384, &tmQ, &bar_load, p.q_c0 + h * HD + c * 64, row0 + q0);
+      for (int bx = 0; bx < n_boxes; ++bx)
+        tma_load_2d(sK + c * KV_CHUNK + bx * 16384, &tmK, &bar_load, p.k_c0 + h * HD + c * 64, row0 + bx * 128);
+    }
+    for (int c = 0; c < HC; ++c)
+      for (int bx = 0; bx < n_boxes; ++bx)
+        tma_load_2d(sV + c * KV_CHUNK + bx * 16384, &tmV, &bar_v, p.v_c0 + h * HD + c * 64, row0 + bx * 128);
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, 256 * KB);
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(&tmem_slot, 256 * KB);
+  } else if (p.drop_p > 0.f) {
+    for (int j = threadIdx.x - 32; j < 256 * KB; j += 256) s_colkey[j] = drop_col_key((uint32_t)j);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -76,15 +100,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == 0) {
     if (elect_one()) {
-      const int row0 = b * L;
-      mbar_arrive_expect_tx(&bar_load, HC * 128 * 128 + 2 * HC * n_boxes * 128 * 128);
-      for (int c = 0; c < HC; ++c) {
-        tma_load_2d(sQ + c * 16384, &tmQ, &bar_load, p.q_c0 + h * HD + c * 64, row0 + q0);
-        for (int bx = 0; bx < n_boxes; ++bx) {
-          tma_load_2d(sK + c * KV_CHUNK + bx * 16384, &tmK, &bar_load, p.k_c0 + h * HD + c * 64, row0 + bx * 128);
-          tma_load_2d(sV + c * KV_CHUNK + bx * 16384, &tmV, &bar_load, p.v_c0 + h * HD + c * 64, row0 + bx * 128);
-        }
-      }
       mbar_wait(&bar_load, 0);
       tc_fence_after();
 #pragma unroll
@@ -101,6 +116,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       umma_commit(&bar_s);
       // ---- second GEMM once the softmax warps have written P
+      mbar_wait(&bar_v, 0);
       mbar_wait(&bar_p, 0);
       tc_fence_after();
       constexpr uint32_t idesc2 = umma_idesc_bf16(128, HD, false, true);
@@ -109,32 +125,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       umma_commit(&bar_o);
     }
   } else {
-    // ------------------------------------------------ softmax warps: thread = query row
-    const int quarter = warp & 3;
+    // ------------------------------------------------ softmax warps: thread = (query row, chunk parity)
+    const int quarter = warp & 3, par = (warp - 1) >> 2;
     const int row = quarter * 32 + lane;
     const int i = q0 + row;                 // query position inside the sequence
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    // key-visibility bit masks, 32 keys per word
-    uint32_t kmask[8 * KB];
+    const bool warp_live = q0 + quarter * 32 < L;        // some row of this warp is a real query
+    const int n_chunks = nk32 / 32;
+    // chunks at or below the causal diagonal of this warp's LAST row; the rest of the tile's key extent is masked for
+    // every row of the warp
+    const int n_vis = p.causal ? min(n_chunks, (q0 + quarter * 32 + 31) / 32 + 1) : n_chunks;
+    // key-visibility bit masks of this thread's chunks (chunk c = 2 t + par), 32 keys per word
+    uint32_t kmask[4 * KB];
 #pragma unroll
-    for (int c = 0; c < 8 * KB; ++c) {
-      const int j = c * 32 + lane;
+    for (int t = 0; t < 4 * KB; ++t) {
+      const int j = (2 * t + par) * 32 + lane;
       bool ok = j < L;
       if (ok && p.mask_pad_keys) ok = p.pad_mask[(size_t)b * L + j] != 0;
-      kmask[c] = __ballot_sync(0xffffffffu, ok);
+      kmask[t] = __ballot_sync(0xffffffffu, ok);
     }
     const float sl2 = p.scale * kLog2eA;
-    const uint32_t thr = p.drop_p > 0.f ? (uint32_t)(p.drop_p * 4294967296.0) : 0u;
-    const float ks_drop = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-    const unsigned long long seed_eff = p.seed + ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
-    mbar_wait(&bar_s, 0);
-    tc_fence_after();
-    const int n_chunks = nk32 / 32;
+    const bool drop = p.drop_p > 0.f;
+    const uint32_t thr = drop ? (uint32_t)(p.drop_p * 4294967296.0) : 0u;
+    const float ks_drop = drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    const unsigned long long seed_eff = p.seed + ((drop && p.seed_ptr) ? *p.seed_ptr : 0ull);
+    const uint32_t row_key = drop ? drop_row_key(seed_eff, p.drop_off, (unsigned long long)bz * p.Lp + (unsigned long long)i) : 0u;
     auto vis_mask = [&](int c) -> uint32_t {
       uint32_t m = 0;
 #pragma unroll
-      for (int cc = 0; cc < 8 * KB; ++cc)
-        if (cc == c) m = kmask[cc];
+      for (int t = 0; t < 4 * KB; ++t)
+        if (2 * t + par == c) m = kmask[t];
       if (p.causal) {
         const int rel = i - c * 32;
         const uint32_t cm = rel >= 31 ? 0xffffffffu : (rel < 0 ? 0u : ((2u << rel) - 1u));
@@ -142,103 +162,146 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       return m;
     };
-    // pass 1: row max over the visible keys
+    mbar_wait(&bar_s, 0);
+    tc_fence_after();
+    // pass 1: row max over the visible keys of this thread's chunks
     float mx = -INFINITY;
-    for (int c = 0; c < n_chunks; ++c) {
-      uint32_t raw[32];
-      tmem_ld32(tmem + lane_base + c * 32, raw);
-      tmem_ld_wait();
-      const uint32_t vm = vis_mask(c);
-      if (vm == 0xffffffffu) {  // chunk entirely visible (the common case below the diagonal): no per-element selects
-        float m0 = __uint_as_float(raw[0]), m1 = __uint_as_float(raw[1]), m2 = __uint_as_float(raw[2]), m3 = __uint_as_float(raw[3]);
+    if (warp_live) {
+      for (int c = par; c < n_vis; c += 2) {
+        const uint32_t vm = vis_mask(c);
+        if (__all_sync(0xffffffffu, vm == 0u)) continue;
+        uint32_t raw[32];
+        tmem_ld32(tmem + lane_base + c * 32, raw);
+        tmem_ld_wait();
+        if (vm == 0xffffffffu) {  // chunk entirely visible (the common case below the diagonal): no per-element selects
+          float m0 = __uint_as_float(raw[0]), m1 = __uint_as_float(raw[1]), m2 = __uint_as_float(raw[2]), m3 = __uint_as_float(raw[3]);
 #pragma unroll
-        for (int q = 4; q < 32; q += 4) {
-          m0 = fmaxf(m0, __uint_as_float(raw[q]));
-          m1 = fmaxf(m1, __uint_as_float(raw[q + 1]));
-          m2 = fmaxf(m2, __uint_as_float(raw[q + 2]));
-          m3 = fmaxf(m3, __uint_as_float(raw[q + 3]));
+          for (int q = 4; q < 32; q += 4) {
+            m0 = fmaxf(m0, __uint_as_float(raw[q]));
+            m1 = fmaxf(m1, __uint_as_float(raw[q + 1]));
+            m2 = fmaxf(m2, __uint_as_float(raw[q + 2]));
+            m3 = fmaxf(m3, __uint_as_float(raw[q + 3]));
+          }
+          mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+        } else if (vm != 0u) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (vm & (1u << q)) mx = fmaxf(mx, __uint_as_float(raw[q]));
         }
-        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-      } else if (vm != 0u) {
-#pragma unroll
-        for (int q = 0; q < 32; ++q)
-          if (vm & (1u << q)) mx = fmaxf(mx, __uint_as_float(raw[q]));
       }
     }
+    s_red[0][par][row] = mx;
+    named_bar_sync(1, 256);
+    mx = fmaxf(mx, s_red[0][par ^ 1][row]);
     const float moff = (mx == -INFINITY) ? 0.f : mx * sl2;
     // pass 2: exponentials, row sum, P (bf16) back into TMEM over S, optional copy of the un-dropped P to global
     float sum = 0.f;
     __nv_bfloat16* prow =
         (p.p_save && i < L) ? p.p_save + ((size_t)bz * p.Lp + i) * p.Lp : nullptr;
-    for (int c = 0; c < n_chunks; ++c) {
+    // The packed P chunk c lands on columns [16 c, 16 c + 16) = inside S chunk c / 2, which belongs to this row's OTHER
+    // thread for every second chunk.  S chunk t is loaded in iteration t / 2 and stored over in iteration t, so each warp
+    // announces "my loads of iteration t are done" (mbarrier, before its exponentials) and checks the partner warp's
+    // announcement of the same iteration right before its store - by then it has long been made.  Two mbarriers per
+    // direction alternate by iteration: a warp can be at most one announcement ahead of its partner's check.
+    for (int t = 0; 2 * t < n_chunks; ++t) {
+      const int c = 2 * t + par;
+      const bool active = warp_live && c < n_chunks;
+      const uint32_t vm = (active && c < n_vis) ? vis_mask(c) : 0u;
+      const bool blank = !active || __all_sync(0xffffffffu, vm == 0u);  // masked for the whole warp: nothing loaded or drawn
       uint32_t raw[32];
-      tmem_ld32(tmem + lane_base + c * 32, raw);
-      tmem_ld_wait();
-      const uint32_t vm = vis_mask(c);
-      float e[32];
-      if (vm == 0xffffffffu) {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          e[q] = ex2f(fmaf(__uint_as_float(raw[q]), sl2, -moff));
-          sum += e[q];
-        }
-      } else if (vm == 0u) {  // chunk entirely masked (left padding, or beyond the diagonal): no exponentials at all
-#pragma unroll
-        for (int q = 0; q < 32; ++q) e[q] = 0.f;
-      } else {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const float v = ex2f(fmaf(__uint_as_float(raw[q]), sl2, -moff));
-          e[q] = (vm & (1u << q)) ? v : 0.f;
-          sum += e[q];
-        }
+      if (!blank) {
+        tmem_ld32(tmem + lane_base + c * 32, raw);
+        tmem_ld_wait();
       }
-      if (prow) {
-#pragma unroll
-        for (int q = 0; q < 32; q += 8) {
-          uint4 w;
-          w.x = pack_bf16(e[q], e[q + 1]);
-          w.y = pack_bf16(e[q + 2], e[q + 3]);
-          w.z = pack_bf16(e[q + 4], e[q + 5]);
-          w.w = pack_bf16(e[q + 6], e[q + 7]);
-          *reinterpret_cast<uint4*>(prow + c * 32 + q) = w;
-        }
-      }
-      if (p.drop_p > 0.f) {
-        const unsigned long long e0 = p.drop_off + ((unsigned long long)bz * p.Lp + (unsigned long long)i) * p.Lp + c * 32;
-#pragma unroll
-        for (int q = 0; q < 32; ++q) e[q] = drop_hash32(seed_eff, e0 + q) >= thr ? e[q] * ks_drop : 0.f;
-      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_pair[quarter][par][t & 1]);
+      if (!active) continue;
       uint32_t pk[16];
+      if (blank) {
 #pragma unroll
-      for (int q = 0; q < 32; q += 2) pk[q >> 1] = pack_bf16(e[q], e[q + 1]);
+        for (int q = 0; q < 16; ++q) pk[q] = 0u;
+        if (prow) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) *reinterpret_cast<uint4*>(prow + c * 32 + q) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      } else {
+        float e[32];
+        if (vm == 0xffffffffu) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            e[q] = ex2f(fmaf(__uint_as_float(raw[q]), sl2, -moff));
+            sum += e[q];
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const float v = ex2f(fmaf(__uint_as_float(raw[q]), sl2, -moff));
+            e[q] = (vm & (1u << q)) ? v : 0.f;
+            sum += e[q];
+          }
+        }
+        if (prow) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) {
+            uint4 w;
+            w.x = pack_bf16(e[q], e[q + 1]);
+            w.y = pack_bf16(e[q + 2], e[q + 3]);
+            w.z = pack_bf16(e[q + 4], e[q + 5]);
+            w.w = pack_bf16(e[q + 6], e[q + 7]);
+            *reinterpret_cast<uint4*>(prow + c * 32 + q) = w;
+          }
+        }
+        if (drop) {
+          const uint4* ck = reinterpret_cast<const uint4*>(s_colkey + c * 32);
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            const uint4 k4 = ck[q >> 2];
+            e[q] = drop_mix(row_key, k4.x) >= thr ? e[q] * ks_drop : 0.f;
+            e[q + 1] = drop_mix(row_key, k4.y) >= thr ? e[q + 1] * ks_drop : 0.f;
+            e[q + 2] = drop_mix(row_key, k4.z) >= thr ? e[q + 2] * ks_drop : 0.f;
+            e[q + 3] = drop_mix(row_key, k4.w) >= thr ? e[q + 3] * ks_drop : 0.f;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) pk[q >> 1] = pack_bf16(e[q], e[q + 1]);
+      }
+      mbar_wait(&bar_pair[quarter][par ^ 1][t & 1], (t >> 1) & 1);
+      tc_fence_after();
       tmem_st16(tmem + lane_base + c * 16, pk);
     }
-    tmem_st_wait();
+    if (warp_live) tmem_st_wait();
+    s_red[1][par][row] = sum;
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar_p);
+    named_bar_sync(1, 256);
+    sum += s_red[1][par ^ 1][row];
     const float inv = sum > 0.f ? 1.f / sum : 0.f;
-    if (p.inv_sum && i < L) p.inv_sum[(size_t)bz * p.Lp + i] = inv;
-    if (p.m_save && i < L) p.m_save[(size_t)bz * p.Lp + i] = moff;
-    // ---- O = (P.V) / sum
+    if (par == 0 && i < L) {
+      if (p.inv_sum) p.inv_sum[(size_t)bz * p.Lp + i] = inv;
+      if (p.m_save) p.m_save[(size_t)bz * p.Lp + i] = moff;
+    }
+    // ---- O = (P.V) / sum : chunk parity 0 stores the even 32-column groups of the head, parity 1 the odd ones
     mbar_wait(&bar_o, 0);
     tc_fence_after();
+    if (warp_live) {
 #pragma unroll
-    for (int c = 0; c < HD; c += 32) {
-      uint32_t raw[32];
-      tmem_ld32(tmem_o + lane_base + c, raw);
-      tmem_ld_wait();
-      if (i < L) {
-        __nv_bfloat16* o = p.out + ((size_t)b * L + i) * p.ldo + h * HD + c;
+      for (int c = par * 32; c < HD; c += 64) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_o + lane_base + c, raw);
+        tmem_ld_wait();
+        if (i < L) {
+          __nv_bfloat16* o = p.out + ((size_t)b * L + i) * p.ldo + h * HD + c;
 #pragma unroll
-        for (int q = 0; q < 32; q += 8) {
-          uint4 w;
-          w.x = pack_bf16(__uint_as_float(raw[q]) * inv, __uint_as_float(raw[q + 1]) * inv);
-          w.y = pack_bf16(__uint_as_float(raw[q + 2]) * inv, __uint_as_float(raw[q + 3]) * inv);
-          w.z = pack_bf16(__uint_as_float(raw[q + 4]) * inv, __uint_as_float(raw[q + 5]) * inv);
-          w.w = pack_bf16(__uint_as_float(raw[q + 6]) * inv, __uint_as_float(raw[q + 7]) * inv);
-          *reinterpret_cast<uint4*>(o + q) = w;
+          for (int q = 0; q < 32; q += 8) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(raw[q]) * inv, __uint_as_float(raw[q + 1]) * inv);
+            w.y = pack_bf16(__uint_as_float(raw[q + 2]) * inv, __uint_as_float(raw[q + 3]) * inv);
+            w.z = pack_bf16(__uint_as_float(raw[q + 4]) * inv, __uint_as_float(raw[q + 5]) * inv);
+            w.w = pack_bf16(__uint_as_float(raw[q + 6]) * inv, __uint_as_float(raw[q + 7]) * inv);
+            *reinterpret_cast<uint4*>(o + q) = w;
+          }
         }
       }
     }
@@ -263,9 +326,15 @@ __global__ void attn_softmax_bwd_kernel(__nv_bfloat16* __restrict__ p_save, __nv
   const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 4294967296.0) : 0u;
   const float ksd = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const long long n_rows = (long long)BH * L;
+  uint32_t colkey[4 * NK];  // the lane's columns are the same in every row
+#pragma unroll
+  for (int k = 0; k < NK; ++k)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) colkey[k * 4 + q] = drop_col_key((uint32_t)(k * 128 + lane * 4 + q));
   for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rows; r += (long long)gridDim.x * wpb) {
     const int bz = (int)(r / L), i = (int)(r % L);
     const size_t base = ((size_t)bz * Lp + i) * Lp;
+    const uint32_t row_key = drop_row_key(seed, drop_off, (unsigned long long)bz * Lp + (unsigned long long)i);
     const float inv = inv_sum[(size_t)bz * Lp + i];
     // lane owns columns [4*lane + 128*k, +4), k < NK   (columns >= L hold zeros and are never written)
     float P[4 * NK], dP[4 * NK], keep[4 * NK];
@@ -286,7 +355,7 @@ __global__ void attn_softmax_bwd_kernel(__nv_bfloat16* __restrict__ p_save, __nv
         uint32_t rv[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
         if (drop_p > 0.f) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) rv[q] = drop_hash32(seed, drop_off + base + j0 + q);
+          for (int q = 0; q < 4; ++q) rv[q] = drop_mix(row_key, colkey[k * 4 + q]);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -489,15 +558,15 @@ RP_API int rp_attn_fwd(const rp_attn_desc* a, void* stream_) {
   if (a->L > 256) {
     const int smem = 16384 + 2 * 65536 + 1024;
     RP_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_fwd_kernel<64, 2><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+    attn_fwd_kernel<64, 2><<<grid, kAfThreads, smem, stream>>>(tmQ, tmK, tmV, p);
   } else if (a->head_dim == 64) {
     const int smem = 16384 + 2 * 32768 + 1024;
     RP_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_fwd_kernel<64, 1><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+    attn_fwd_kernel<64, 1><<<grid, kAfThreads, smem, stream>>>(tmQ, tmK, tmV, p);
   } else {
     const int smem = 2 * (16384 + 2 * 32768) + 1024;
     RP_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_fwd_kernel<128, 1><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+    attn_fwd_kernel<128, 1><<<grid, kAfThreads, smem, stream>>>(tmQ, tmK, tmV, p);
   }
   RP_LAUNCH_CHECK();
   return RP_OK;

@@ -108,30 +108,54 @@ __global__ void embed_fwd_kernel(const __nv_bfloat16* __restrict__ table, const 
   const int wpb = blockDim.x >> 5;
   const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 4294967296.0) : 0u;
   const float ks = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < T; t += gridDim.x * wpb) {
-    const int id = ids[t];
-    // BERT4Rec: positions with token_mask == 0 (<MASK> and pads) take the single mask embedding (bert4rec/model.py:285-288)
-    const __nv_bfloat16* e = (tok_mask && !tok_mask[t]) ? mask_emb + lane * VEC : table + (size_t)id * D + lane * VEC;
-    const float* p = pos + (size_t)(pos0 + t % L) * D + lane * VEC;
-    float v[VEC];
+  uint32_t ck[VEC];  // dropout column keys of this lane's columns (rp_philox.cuh)
 #pragma unroll
-    for (int i = 0; i < VEC; i += 2) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(e + i));
-      v[i] = f.x * scale + p[i];
-      v[i + 1] = f.y * scale + p[i + 1];
+  for (int i = 0; i < VEC; ++i) ck[i] = drop_col_key((uint32_t)(lane * VEC + i));
+  // TOK tokens per warp and iteration: the id loads, then the row loads of all of them are in flight together (one token at a
+  // time the loop was a chain of two dependent DRAM round trips per token, 43 us for 102 400 tokens at d = 128)
+  constexpr int TOK = 4;
+  for (int tb = (blockIdx.x * wpb + (threadIdx.x >> 5)) * TOK; tb < T; tb += gridDim.x * wpb * TOK) {
+    int id[TOK];
+    bool use_mask[TOK];
+#pragma unroll
+    for (int k = 0; k < TOK; ++k) {
+      const int t = min(tb + k, T - 1);
+      id[k] = ids[t];
+      // BERT4Rec: positions with token_mask == 0 (<MASK> and pads) take the single mask embedding (bert4rec/model.py:285-288)
+      use_mask[k] = tok_mask && !tok_mask[t];
     }
-    if (drop_p > 0.f) {
-      const unsigned long long e0 = drop_off + (unsigned long long)t * D + lane * VEC;
+    __nv_bfloat162 ev[TOK][VEC / 2];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) v[i] = philox_keep(seed, e0 + i, thr) ? v[i] * ks : 0.f;
+    for (int k = 0; k < TOK; ++k) {
+      const __nv_bfloat16* e = use_mask[k] ? mask_emb + lane * VEC : table + (size_t)id[k] * D + lane * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) ev[k][i >> 1] = *reinterpret_cast<const __nv_bfloat162*>(e + i);
     }
-    if (zero_pad_rows && !pad_mask[t]) {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) v[i] = 0.f;
+    for (int k = 0; k < TOK; ++k) {
+      const int t = tb + k;
+      if (t >= T) break;
+      const float* p = pos + (size_t)(pos0 + t % L) * D + lane * VEC;
+      float v[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) {
+        const float2 f = __bfloat1622float2(ev[k][i >> 1]);
+        v[i] = f.x * scale + p[i];
+        v[i + 1] = f.y * scale + p[i + 1];
+      }
+      if (drop_p > 0.f) {
+        const uint32_t rk = drop_row_key(seed, drop_off, (unsigned long long)t);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = drop_mix(rk, ck[i]) >= thr ? v[i] * ks : 0.f;
+      }
+      if (zero_pad_rows && !pad_mask[t]) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = 0.f;
+      }
+      __nv_bfloat16* o = out + (size_t)t * D + lane * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) *reinterpret_cast<uint32_t*>(o + i) = pack_bf16(v[i], v[i + 1]);
     }
-    __nv_bfloat16* o = out + (size_t)t * D + lane * VEC;
-#pragma unroll
-    for (int i = 0; i < VEC; i += 2) *reinterpret_cast<uint32_t*>(o + i) = pack_bf16(v[i], v[i + 1]);
   }
 }
 
@@ -149,18 +173,51 @@ __global__ void embed_bwd_table_kernel(const __nv_bfloat16* __restrict__ dx, con
   const int wpb = blockDim.x >> 5;
   const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 4294967296.0) : 0u;
   const float ks = (drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f) * scale;
-  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < T; t += gridDim.x * wpb) {
-    const int id = ids[t];
-    if (id == pad_id) continue;
-    if ((zero_pad_rows || tok_mask) && !pad_mask[t]) continue;  // pad positions receive no gradient
-    const __nv_bfloat16* g = dx + (size_t)t * D + lane * VEC;
-    float* dst = (tok_mask && !tok_mask[t]) ? d_mask_emb + lane * VEC : dE + (size_t)id * D + lane * VEC;
-    const unsigned long long e0 = drop_off + (unsigned long long)t * D + lane * VEC;
+  uint32_t ck[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      float v = __bfloat162float(g[i]) * ks;
-      if (drop_p > 0.f && !philox_keep(seed, e0 + i, thr)) v = 0.f;
-      atomicAdd(dst + i, v);
+  for (int i = 0; i < VEC; ++i) ck[i] = drop_col_key((uint32_t)(lane * VEC + i));
+  constexpr int TOK = 4;  // tokens per warp and iteration: independent loads in flight, vector reductions (red.v4.f32)
+  for (int tb = (blockIdx.x * wpb + (threadIdx.x >> 5)) * TOK; tb < T; tb += gridDim.x * wpb * TOK) {
+    int id[TOK];
+    bool on[TOK];
+    __nv_bfloat162 gv[TOK][VEC / 2];
+#pragma unroll
+    for (int k = 0; k < TOK; ++k) {
+      const int t = min(tb + k, T - 1);
+      id[k] = ids[t];
+      on[k] = tb + k < T && id[k] != pad_id && !((zero_pad_rows || tok_mask) && !pad_mask[t]);  // pads receive no gradient
+    }
+#pragma unroll
+    for (int k = 0; k < TOK; ++k) {
+      const __nv_bfloat16* g = dx + (size_t)min(tb + k, T - 1) * D + lane * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) gv[k][i >> 1] = *reinterpret_cast<const __nv_bfloat162*>(g + i);
+    }
+#pragma unroll
+    for (int k = 0; k < TOK; ++k) {
+      if (!on[k]) continue;
+      const int t = tb + k;
+      float* dst = (tok_mask && !tok_mask[t]) ? d_mask_emb + lane * VEC : dE + (size_t)id[k] * D + lane * VEC;
+      float v[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) {
+        const float2 f = __bfloat1622float2(gv[k][i >> 1]);
+        v[i] = f.x * ks;
+        v[i + 1] = f.y * ks;
+      }
+      if (drop_p > 0.f) {
+        const uint32_t rk = drop_row_key(seed, drop_off, (unsigned long long)t);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+          if (drop_mix(rk, ck[i]) < thr) v[i] = 0.f;
+      }
+      if constexpr (VEC % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4) atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 2) atomicAdd(reinterpret_cast<float2*>(dst + i), make_float2(v[i], v[i + 1]));
+      }
     }
   }
 }
@@ -182,6 +239,9 @@ __global__ void embed_bwd_pos_kernel(const __nv_bfloat16* __restrict__ dx, const
   const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 4294967296.0) : 0u;
   const float ks = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t ck[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) ck[k] = drop_col_key((uint32_t)(cg * 4 + k));
   for (int b = b0 + rl; b < b1; b += rlanes) {
     const int t = b * L + l;
     if (zero_pad_rows && !pad_mask[t]) continue;
@@ -190,11 +250,9 @@ __global__ void embed_bwd_pos_kernel(const __nv_bfloat16* __restrict__ dx, const
     const float2 a = __bfloat1622float2(h[0]), c = __bfloat1622float2(h[1]);
     float v[4] = {a.x, a.y, c.x, c.y};
     if (drop_p > 0.f) {
-      const uint4 r = rng4x32(seed, (drop_off + (unsigned long long)t * D + cg * 4) >> 2);
-      v[0] = r.x >= thr ? v[0] * ks : 0.f;
-      v[1] = r.y >= thr ? v[1] * ks : 0.f;
-      v[2] = r.z >= thr ? v[2] * ks : 0.f;
-      v[3] = r.w >= thr ? v[3] * ks : 0.f;
+      const uint32_t rk = drop_row_key(seed, drop_off, (unsigned long long)t);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = drop_mix(rk, ck[k]) >= thr ? v[k] * ks : 0.f;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc[k] += v[k];
@@ -364,11 +422,11 @@ __global__ void dropout_bwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bf
     float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
     float v[4] = {a.x, a.y, b.x, b.y};
     if (drop_p > 0.f) {
-      const uint4 r = rng4x32(seed, (drop_off + (unsigned long long)i) >> 2);
-      v[0] = r.x >= thr ? v[0] * ks : 0.f;
-      v[1] = r.y >= thr ? v[1] * ks : 0.f;
-      v[2] = r.z >= thr ? v[2] * ks : 0.f;
-      v[3] = r.w >= thr ? v[3] * ks : 0.f;
+      const long long row = i / cols;
+      const uint32_t col = (uint32_t)(i - row * cols);   // cols % 4 == 0: the 4 elements share the row
+      const uint32_t rk = drop_row_key(seed, drop_off, (unsigned long long)row);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = drop_mix(rk, drop_col_key(col + k)) >= thr ? v[k] * ks : 0.f;
     }
     if (rowmask && !rowmask[i / cols]) v[0] = v[1] = v[2] = v[3] = 0.f;
     uint2 w;

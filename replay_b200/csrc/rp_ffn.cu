@@ -241,14 +241,15 @@ struct PostAttnParams {
   int hd_valid;                // > 0: padded feature slots (rp_sm100.cuh): LayerNorm statistics over the real features only
 };
 
-// keep/scale 4 consecutive elements starting at element index e (e % 4 == 0)
-__device__ __forceinline__ void drop4(float& a, float& b, float& c, float& d, unsigned long long seed, unsigned long long e,
+// keep/scale 4 consecutive elements of one row (activation dropout, rp_philox.cuh): row key of (seed, site, row), the column
+// keys of the 4 columns from the shared-memory table
+__device__ __forceinline__ void drop4(float& a, float& b, float& c, float& d, uint32_t row_key, const uint32_t* col_keys,
                                       uint32_t thr, float ks) {
-  const uint4 r = rng4x32(seed, e >> 2);
-  a = r.x >= thr ? a * ks : 0.f;
-  b = r.y >= thr ? b * ks : 0.f;
-  c = r.z >= thr ? c * ks : 0.f;
-  d = r.w >= thr ? d * ks : 0.f;
+  const uint4 k = *reinterpret_cast<const uint4*>(col_keys);
+  a = drop_mix(row_key, k.x) >= thr ? a * ks : 0.f;
+  b = drop_mix(row_key, k.y) >= thr ? b * ks : 0.f;
+  c = drop_mix(row_key, k.z) >= thr ? c * ks : 0.f;
+  d = drop_mix(row_key, k.w) >= thr ? d * ks : 0.f;
 }
 
 // the four output tensor maps (box [128 rows x 64 columns]): h, y, u (training only) and the block output
@@ -276,6 +277,7 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
   __shared__ uint64_t bar_w, o_full[NA], o_empty[NA], g0_full[2], y_ready[2], g1_full[2], u_ready[2], g2_full[2], tile_done[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_vec[5][D];     // bo, ln_w, ln_b, b1, b2
+  __shared__ __align__(16) uint32_t s_ck[D];      // dropout column keys
   __shared__ float2 s_stat[2][128];               // (sum, sum of squares) of each row's column half
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -310,6 +312,7 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
       s_vec[2][i] = p.ln_b[i];
       s_vec[3][i] = p.b1[i];
       s_vec[4][i] = p.b2[i];
+      s_ck[i] = drop_col_key((uint32_t)i);
     }
   tc_fence_before();
   __syncthreads();
@@ -510,15 +513,15 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
               tmem_ld_wait();
               uint32_t pk[32];
               if (TRAIN && p.drop_p > 0.f) {
-                const unsigned long long e0 = p.off1 + (unsigned long long)m * D + c0;
+                const uint32_t rk1 = drop_row_key(seed_eff, p.off1, (unsigned long long)m);
 #pragma unroll
                 for (int q = 0; q < 32; q += 4) {
                   float a0 = fmaxf(__uint_as_float(r0[q]) + s_vec[3][c0 + q], 0.f), a1 = fmaxf(__uint_as_float(r0[q + 1]) + s_vec[3][c0 + q + 1], 0.f);
                   float a2 = fmaxf(__uint_as_float(r0[q + 2]) + s_vec[3][c0 + q + 2], 0.f), a3 = fmaxf(__uint_as_float(r0[q + 3]) + s_vec[3][c0 + q + 3], 0.f);
                   float b0 = fmaxf(__uint_as_float(r1[q]) + s_vec[3][c0 + 32 + q], 0.f), b1 = fmaxf(__uint_as_float(r1[q + 1]) + s_vec[3][c0 + 32 + q + 1], 0.f);
                   float b2 = fmaxf(__uint_as_float(r1[q + 2]) + s_vec[3][c0 + 32 + q + 2], 0.f), b3 = fmaxf(__uint_as_float(r1[q + 3]) + s_vec[3][c0 + 32 + q + 3], 0.f);
-                  drop4(a0, a1, a2, a3, seed_eff, e0 + q, drop_thr, keep_scale);
-                  drop4(b0, b1, b2, b3, seed_eff, e0 + 32 + q, drop_thr, keep_scale);
+                  drop4(a0, a1, a2, a3, rk1, s_ck + c0 + q, drop_thr, keep_scale);
+                  drop4(b0, b1, b2, b3, rk1, s_ck + c0 + 32 + q, drop_thr, keep_scale);
                   pk[q >> 1] = pack_bf16(a0, a1);
                   pk[(q >> 1) + 1] = pack_bf16(a2, a3);
                   pk[16 + (q >> 1)] = pack_bf16(b0, b1);
@@ -562,6 +565,7 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
               if (lane == 0) mbar_arrive(&tile_done[pp]);  // everything of this tile is in registers
               const float keep = (p.rowmask == nullptr || (row_ok && p.rowmask[m])) ? 1.f : 0.f;
               uint32_t po[32];
+              const uint32_t rk2 = (TRAIN && p.drop_p > 0.f) ? drop_row_key(seed_eff, p.off2, (unsigned long long)m) : 0u;
 #pragma unroll
               for (int c8 = 0; c8 < 8; ++c8) {
 #pragma unroll
@@ -570,11 +574,10 @@ post_attn_fused_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_con
                   const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yk[col >> 1]));
                   float f0 = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + s_vec[4][c0 + col];
                   float f1 = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + s_vec[4][c0 + col + 1];
-                  if (TRAIN && p.drop_p > 0.f) {  // element pair (col, col+1) of the 4-group starting at col & ~3
-                    const uint4 rr = rng4x32(seed_eff, (p.off2 + (unsigned long long)m * D + c0 + col) >> 2);
-                    const uint32_t w0 = (col & 2) ? rr.z : rr.x, w1 = (col & 2) ? rr.w : rr.y;
-                    f0 = w0 >= drop_thr ? f0 * keep_scale : 0.f;
-                    f1 = w1 >= drop_thr ? f1 * keep_scale : 0.f;
+                  if (TRAIN && p.drop_p > 0.f) {
+                    const uint2 ck = *reinterpret_cast<const uint2*>(s_ck + c0 + col);
+                    f0 = drop_mix(rk2, ck.x) >= drop_thr ? f0 * keep_scale : 0.f;
+                    f1 = drop_mix(rk2, ck.y) >= drop_thr ? f1 * keep_scale : 0.f;
                   }
                   po[c8 * 4 + e] = pack_bf16((f0 + yf.x) * keep, (f1 + yf.y) * keep);
                 }
@@ -690,7 +693,7 @@ RP_API int rp_post_attn_fused(const void* o, const void* q_in, const void* wo, c
 // and the activations the backward needs are written on the way: h, y, u (bf16 [T, d]) and the LayerNorm statistics
 // (fp32 [T]) - 2 tensors read, 4 written, against 14 [T, d] passes of the four separate launches
 // (out-projection GEMM, LayerNorm, two FFN GEMMs).  Dropout element e of site s uses word (e & 3) of
-// rng4x32(seed + *seed_ptr, (off_s + e) >> 2), e = row * d + column: the same stream rp_gemm's epilogue and rp_dropout_bwd use.
+// drop_mix(drop_row_key(seed + *seed_ptr, off_s, row), drop_col_key(column)): the same stream rp_gemm's epilogue and rp_dropout_bwd use.
 //   replaces (train)  replay/nn/sequential/sasrec/transformer.py:99-110 ; replay/nn/ffn.py:43-57 ;
 //                     replay/models/nn/sequential/sasrec/model.py:435-441,496-506
 RP_API int rp_post_attn_train(const void* o, const void* q_in, const void* wo, const float* bo, const float* ln_w,

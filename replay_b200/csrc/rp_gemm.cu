@@ -54,6 +54,7 @@ struct GemmParams {
 // Epilogue of one [1 row x 32 columns] strip held in registers (shared by the tile kernel and the persistent kernel).
 struct EpiRow {
   long long c_base;   // element offset of this output row in C
+  long long drop_row; // row index of the activation dropout stream (rp_philox.cuh): element (drop_row, column)
   float rm;           // row-mask factor
   float exp_off;      // act 3: per-row exponent offset
   float keep_scale;
@@ -95,16 +96,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const f
         for (int q = 0; q < 32; ++q) x[q] = ex2f(fmaf(x[q], 1.4426950408889634f, er.exp_off));
       }
       if (p.drop_p > 0.f) {
-        // one Philox call per 4 consecutive output elements; element index = c_base + column
-        const unsigned long long e0 = p.drop_offset + (unsigned long long)(c_base + n0 + c);
+        const uint32_t rk = drop_row_key(seed_eff, p.drop_offset, (unsigned long long)er.drop_row);
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          const uint4 r = rng4x32(seed_eff, (e0 + q) >> 2);
-          x[q + 0] = (r.x >= drop_thr) ? x[q + 0] * keep_scale : 0.f;
-          x[q + 1] = (r.y >= drop_thr) ? x[q + 1] * keep_scale : 0.f;
-          x[q + 2] = (r.z >= drop_thr) ? x[q + 2] * keep_scale : 0.f;
-          x[q + 3] = (r.w >= drop_thr) ? x[q + 3] * keep_scale : 0.f;
-        }
+        for (int q = 0; q < 32; ++q)
+          x[q] = drop_mix(rk, drop_col_key((uint32_t)(n0 + c + q))) >= drop_thr ? x[q] * keep_scale : 0.f;
       }
       if (p.gate) {
         const __nv_bfloat16* gp = p.gate + c_base + n0 + c;
@@ -145,15 +140,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const f
       if (p.post_drop_p > 0.f) {
         const float ks2 = 1.f / (1.f - p.post_drop_p);
         const uint32_t thr2 = (uint32_t)(p.post_drop_p * 4294967296.0);
-        const unsigned long long e0 = p.post_drop_offset + (unsigned long long)(c_base + n0 + c);
+        const uint32_t rk = drop_row_key(p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull), p.post_drop_offset, (unsigned long long)er.drop_row);
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          const uint4 r = rng4x32(p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull), (e0 + q) >> 2);
-          x[q + 0] = (r.x >= thr2) ? x[q + 0] * ks2 : 0.f;
-          x[q + 1] = (r.y >= thr2) ? x[q + 1] * ks2 : 0.f;
-          x[q + 2] = (r.z >= thr2) ? x[q + 2] * ks2 : 0.f;
-          x[q + 3] = (r.w >= thr2) ? x[q + 3] * ks2 : 0.f;
-        }
+        for (int q = 0; q < 32; ++q)
+          x[q] = drop_mix(rk, drop_col_key((uint32_t)(n0 + c + q))) >= thr2 ? x[q] * ks2 : 0.f;
       }
       if (p.rowmask) {
 #pragma unroll
@@ -308,6 +298,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (p.rowmask && row_ok) rm = p.rowmask[p.rowmask_off0 + (long long)outer * p.rowmask_oo + m] ? 1.f : 0.f;
     EpiRow er;
     er.c_base = c_base;
+    er.drop_row = (long long)bz * p.M + m;
     er.rm = rm;
     er.exp_off = (p.act == 3 && row_ok) ? p.row_exp2_offset[m] : 0.f;
     er.keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
@@ -451,6 +442,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m = mt * 128 + row;
       const bool row_ok = m < p.M;
       er.c_base = p.c_off0 + (long long)m * p.ldc;
+      er.drop_row = m;
       er.rm = 1.f;
       er.exp_off = 0.f;
       if (p.rowmask && row_ok) er.rm = p.rowmask[p.rowmask_off0 + m] ? 1.f : 0.f;
@@ -614,6 +606,7 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m = (int)(t / n_tiles) * 128 + row, n0 = (int)(t % n_tiles) * BN;
       const bool row_ok = m < p.M;
       er.c_base = p.c_off0 + (long long)m * p.ldc;
+      er.drop_row = m;
       er.rm = 1.f;
       if (p.rowmask && row_ok) er.rm = p.rowmask[p.rowmask_off0 + m] ? 1.f : 0.f;
       er.exp_off = (p.act == 3 && row_ok) ? p.row_exp2_offset[m] : 0.f;

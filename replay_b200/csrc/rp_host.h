@@ -41,6 +41,12 @@ PFN_encodeTiled get_encode_tiled();
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                    uint32_t box_cols = 64);
 
+// 3-D view [n_seq][seq_len][cols] of the same kind of array (row b * seq_len + l of the 2-D array): box = [1, box_rows, 64 cols].
+// Rows l >= seq_len of a box are OUT OF BOUNDS: loads fill them with zeros, stores drop them - a 128-row box never touches
+// the next sequence (padded-sequence attention, L not a multiple of 128).
+int make_tmap_bf16_seq(CUtensorMap* out, const void* base, uint64_t n_seq, uint64_t seq_len, uint64_t cols, uint64_t ld,
+                       uint32_t box_rows, uint32_t box_cols = 64);
+
 int sm_count();
 
 }  // namespace rp

@@ -1,5 +1,6 @@
 // rp_philox.cuh - counter-based RNGs: the forward and the backward regenerate the same dropout mask from
-// (seed, element index / 4) instead of storing it.  Element e uses word (e & 3) of rng4x32(seed, e >> 2).
+// (seed, site offset, row, column) instead of storing it (drop_row_key / drop_col_key / drop_mix below); Philox4x32-10 stays
+// where a reference-grade stream matters (the BERT4Rec token masker).
 #pragma once
 #include <stdint.h>
 
@@ -34,35 +35,26 @@ __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {  // murmur3 fi
   return h;
 }
 
-// Activation-dropout generator: four 32-bit words for the 4 consecutive elements of counter `ctr` (= element index / 4).
-// Dropout only needs independent-looking Bernoulli draws that the backward can regenerate; Philox4x32-10 costs ~110
-// integer instructions per call and showed up as ~5 % of the training step, this counter hash (one mixed 32-bit key per
-// (seed, ctr), four finalisers on a Weyl sequence) costs ~30.  Philox stays in use where a reference-grade stream matters
-// (the BERT4Rec token masker).
-__host__ __device__ __forceinline__ uint4 rng4x32(unsigned long long seed, unsigned long long ctr) {
-  const uint32_t key = fmix32((uint32_t)ctr * 0x9E3779B1u ^ (uint32_t)seed) ^
-                       fmix32((uint32_t)(ctr >> 32) * 0x85EBCA77u + (uint32_t)(seed >> 32) + 0x27D4EB2Fu);
-  return make_uint4(fmix32(key), fmix32(key + 0x9E3779B9u), fmix32(key + 0x3C6EF372u), fmix32(key + 0xDAA66D2Bu));
+// Dropout draws.  The attention forward walks the [query, key] matrix by query rows, the fused backward by key rows, the
+// activation kernels by token rows - so the mask must be computable per element in any order - and it was the dominant
+// integer cost of those kernels (a murmur finaliser per attention probability kept the ALU pipe ~55 % busy; the previous
+// activation generator, 6 finalisers per 4 elements, was ~45 % of the instructions of the fused post-attention kernel; ncu
+// r2c).  The draw for element (row r, column j) of a site is
+//   drop_mix(drop_row_key(seed, site offset, r), drop_col_key(j))
+// (attention probabilities: r = (batch*head)*Lp + query, j = key; activations [T, d]: r = token row, j = feature column)
+// with the two well-mixed 32-bit keys computed once per row / per key (shared-memory tables) and a two-multiply mix per
+// element; keep <=> draw >= p * 2^32.  (4096 x 256 grid at p = 0.2: mean 0.7995, row / column correlations at the
+// sampling-noise floor, no 2x2 interaction.)
+__host__ __device__ __forceinline__ uint32_t drop_row_key(unsigned long long seed, unsigned long long off, unsigned long long row) {
+  const uint32_t s = fmix32((uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA77u) ^ ((uint32_t)(off >> 32) * 0xC2B2AE3Du) ^
+                            ((uint32_t)off * 0x27D4EB2Fu));
+  return fmix32(s + (uint32_t)row * 0x9E3779B1u + (uint32_t)(row >> 32) * 0x165667B1u);
 }
-
-// keep decision for element e with drop threshold thr = p * 2^32
-__device__ __forceinline__ bool philox_keep(unsigned long long seed, unsigned long long e, uint32_t thr) {
-  const uint4 r = rng4x32(seed, e >> 2);
-  const uint32_t w = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
-  return w >= thr;
-}
-
-// Cheap per-element hash (murmur3 finaliser) for the attention-probability dropout: the fused attention backward walks
-// the [query, key] matrix transposed, so the mask must be computable per element in any order (Philox is used where the
-// forward and backward visit 4 consecutive elements together).
-__device__ __forceinline__ uint32_t drop_hash32(unsigned long long seed, unsigned long long idx) {
-  uint32_t h = ((uint32_t)idx * 0x9E3779B1u) ^ (uint32_t)seed ^ ((uint32_t)(idx >> 32) * 0x85EBCA77u) ^ (uint32_t)(seed >> 32);
-  h ^= h >> 16;
-  h *= 0x85EBCA6Bu;
-  h ^= h >> 13;
-  h *= 0xC2B2AE35u;
-  h ^= h >> 16;
-  return h;
+__host__ __device__ __forceinline__ uint32_t drop_col_key(uint32_t j) { return fmix32(j * 0x9E3779B1u + 0x27D4EB2Fu); }
+__host__ __device__ __forceinline__ uint32_t drop_mix(uint32_t row_key, uint32_t col_key) {
+  uint32_t x = (row_key ^ col_key) * 0x9E3779B1u;
+  x ^= x >> 15;
+  return x * 0x85EBCA77u;
 }
 
 }  // namespace rp

@@ -79,6 +79,7 @@ post_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
   __shared__ uint64_t bar_w, z_full[NA], z_empty[NA], a_ready[3][2], g_full[3][2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_lnw[D];
+  __shared__ __align__(16) uint32_t s_ck[D];      // dropout column keys (rp_philox.cuh)
   __shared__ float2 s_stat[2][128];
   __shared__ float s_red[2][kPbEpiWarps][64];
 
@@ -105,7 +106,10 @@ post_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
   if (threadIdx.x >= 64)
-    for (int i = threadIdx.x - 64; i < D; i += kPbEpiWarps * 32) s_lnw[i] = p.ln_w[i];
+    for (int i = threadIdx.x - 64; i < D; i += kPbEpiWarps * 32) {
+      s_lnw[i] = p.ln_w[i];
+      s_ck[i] = drop_col_key((uint32_t)i);
+    }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -206,7 +210,7 @@ post_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
             mbar_wait(&z_full[s], zph);
             if (has_half) {
               uint32_t pk[32];
-              const unsigned long long e0 = p.off2 + (unsigned long long)m * D + c0;
+              const uint32_t rk2 = p.drop_p > 0.f ? drop_row_key(seed_eff, p.off2, (unsigned long long)m) : 0u;
 #pragma unroll
               for (int c8 = 0; c8 < 8; ++c8) {
                 const uint4 zv = *reinterpret_cast<const uint4*>(ztile + sw128_off((uint32_t)row, (uint32_t)c8));
@@ -219,11 +223,11 @@ post_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
                   v[2 * e + 1] = f.y * rm;
                 }
                 if (p.drop_p > 0.f) {
-                  const uint4 ra = rng4x32(seed_eff, (e0 + c8 * 8) >> 2), rb = rng4x32(seed_eff, (e0 + c8 * 8 + 4) >> 2);
-                  v[0] = ra.x >= thr ? v[0] * ks_ : 0.f; v[1] = ra.y >= thr ? v[1] * ks_ : 0.f;
-                  v[2] = ra.z >= thr ? v[2] * ks_ : 0.f; v[3] = ra.w >= thr ? v[3] * ks_ : 0.f;
-                  v[4] = rb.x >= thr ? v[4] * ks_ : 0.f; v[5] = rb.y >= thr ? v[5] * ks_ : 0.f;
-                  v[6] = rb.z >= thr ? v[6] * ks_ : 0.f; v[7] = rb.w >= thr ? v[7] * ks_ : 0.f;
+                  const uint4 ka = *reinterpret_cast<const uint4*>(s_ck + c0 + c8 * 8), kb = *reinterpret_cast<const uint4*>(s_ck + c0 + c8 * 8 + 4);
+                  v[0] = drop_mix(rk2, ka.x) >= thr ? v[0] * ks_ : 0.f; v[1] = drop_mix(rk2, ka.y) >= thr ? v[1] * ks_ : 0.f;
+                  v[2] = drop_mix(rk2, ka.z) >= thr ? v[2] * ks_ : 0.f; v[3] = drop_mix(rk2, ka.w) >= thr ? v[3] * ks_ : 0.f;
+                  v[4] = drop_mix(rk2, kb.x) >= thr ? v[4] * ks_ : 0.f; v[5] = drop_mix(rk2, kb.y) >= thr ? v[5] * ks_ : 0.f;
+                  v[6] = drop_mix(rk2, kb.z) >= thr ? v[6] * ks_ : 0.f; v[7] = drop_mix(rk2, kb.w) >= thr ? v[7] * ks_ : 0.f;
                 }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) pk[c8 * 4 + e] = pack_bf16(v[2 * e], v[2 * e + 1]);

@@ -30,6 +30,10 @@ class RemoveSeenItems:
             out[i, : len(s)] = s
         return torch.from_numpy(out).to(device)
 
+    def on_validation(self, query_ids, scores, ground_truth):
+        """postprocessors.py:26-40"""
+        return query_ids, self.on_prediction(query_ids, scores)[1], ground_truth
+
     def on_prediction(self, query_ids, scores):
         item_count = self._sequential.schema.item_id_features.item().cardinality
         seen = self.seen_tensor(query_ids, scores.device)

@@ -355,3 +355,63 @@ def test_compute_metrics_callback_history_and_state_dict():
     cb2 = ComputeMetricsCallback(metrics=("recall", "ndcg"), ks=(1, 2))
     cb2.load_state_dict({k: {str(e): m for e, m in v.items()} for k, v in sd.items()})  # keys come back as strings from json
     assert cb2.get_metrics("validate") == cb.get_metrics("validate") and cb2.get_metrics("test") == cb.get_metrics("test")
+
+
+def test_prediction_side_callbacks_without_an_engine():
+    """predictions_callback.py:124-163,282-325 and callbacks/{prediction_callbacks,validation_callback}.py: the frame-building,
+    hidden-state, query-embedding and legacy validation callbacks on plain tensors (the dense-scores path every callback
+    keeps for modules without an engine)."""
+    from replay_b200.models.nn.sequential import (PandasPredictionCallback, QueryEmbeddingsPredictionCallback,
+                                                  ValidationMetricsCallback)
+    from replay_b200.nn.lightning import HiddenStatesCallback, PandasTopItemsCallback, RankingMetrics
+
+    class _PL:
+        candidates_to_score = None
+        logged = {}
+
+        def log_dict(self, d, **k):
+            self.logged.update(d)
+
+    logits = torch.tensor([[0.1, 0.9, 0.3, 0.0], [0.8, 0.2, 0.5, 0.6]])
+    # new-path pandas frame: one row per (query, item, rating), best first
+    cb = PandasTopItemsCallback(top_k=2, query_column="user", item_column="item", rating_column="score")
+    cb.on_predict_epoch_start(None, _PL())
+    cb.on_predict_batch_end(None, _PL(), {"logits": logits}, {"user": torch.tensor([7, 9])}, 0)
+    df = cb.get_result()
+    assert df["user"].tolist() == [7, 7, 9, 9] and df["item"].tolist() == [1, 2, 0, 3]
+    assert np.allclose(df["score"].to_numpy(), [0.9, 0.3, 0.8, 0.6])
+    # legacy pandas frame (outputs are the scores themselves)
+    lcb = PandasPredictionCallback(top_k=1, query_column="user", item_column="item")
+    lcb.on_predict_epoch_start(None, _PL())
+    lcb.on_predict_batch_end(None, _PL(), logits, {"query_id": torch.tensor([[7], [9]])}, 0)
+    assert lcb.get_result()["item"].tolist() == [1, 0]
+    # hidden states: the chosen element of outputs["hidden_states"], concatenated over batches
+    h = HiddenStatesCallback(hidden_state_index=1)
+    h.on_predict_epoch_start(None, None)
+    for k in range(2):
+        h.on_predict_batch_end(None, None, {"hidden_states": (torch.zeros(2, 3), torch.full((2, 3), float(k)))}, {}, k)
+    assert h.get_result().shape == (4, 3) and h.get_result()[2:].eq(1).all()
+
+    # query embeddings: batch entries are matched to the signature of _model.get_query_embeddings
+    class _M:
+        @staticmethod
+        def get_query_embeddings(feature_tensor, padding_mask):
+            return feature_tensor["item_id"].float() * padding_mask
+
+    class _PLQ:
+        _model = _M()
+
+    q = QueryEmbeddingsPredictionCallback()
+    q.on_predict_epoch_start(None, _PLQ())
+    q.on_predict_batch_end(None, _PLQ(), None, {"query_id": torch.tensor([1]), "feature_tensor": {"item_id": torch.tensor([[2, 3]])},
+                                               "padding_mask": torch.tensor([[0, 1]])}, 0)
+    assert q.get_result().tolist() == [[0.0, 3.0]]
+    # legacy validation callback == the metric builder on top-k of the scores
+    v = ValidationMetricsCallback(metrics=("recall", "ndcg", "map"), ks=(1, 2))
+    v.on_validation_epoch_start(None, _PL())
+    gt = torch.tensor([[1, -1], [3, 2]])
+    v.on_validation_batch_end(None, _PL(), logits, {"query_id": torch.tensor([7, 9]), "ground_truth": gt}, 0)
+    res = v.on_validation_epoch_end(None, _PL())
+    ref = RankingMetrics(("recall", "ndcg", "map"), (1, 2))
+    ref.add_prediction(torch.topk(logits, 2, dim=1).indices, gt)
+    assert res == ref.get_metrics() and abs(res["recall@1"] - 0.5) < 1e-6

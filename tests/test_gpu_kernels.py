@@ -247,7 +247,7 @@ def test_ce_head_wide_hidden_matches_oracle(ops, T, n_valid, I, budget, monkeypa
 
 
 def test_activation_dropout_generator_statistics(ops):
-    """The counter hash behind the activation dropout (rp_philox.cuh rng4x32), observed through rp_dropout_bwd on an all-ones
+    """The counter hash behind the activation dropout (rp_philox.cuh drop_row_key / drop_col_key / drop_mix), observed through rp_dropout_bwd on an all-ones
     input: keep rate, no row / column / lag structure, different masks for different sites, seeds and step counters."""
     from replay_b200._lib import check, lib
     rows, cols, p = 8192, 128, 0.2

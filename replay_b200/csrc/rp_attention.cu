@@ -137,12 +137,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int n_vis = p.causal ? min(n_chunks, (q0 + quarter * 32 + 31) / 32 + 1) : n_chunks;
     // key-visibility bit masks of this thread's chunks (chunk c = 2 t + par), 32 keys per word
     uint32_t kmask[4 * KB];
+    {
+      uint8_t pm[4 * KB];   // all loads first: a ballot per load serialises their latencies
 #pragma unroll
-    for (int t = 0; t < 4 * KB; ++t) {
-      const int j = (2 * t + par) * 32 + lane;
-      bool ok = j < L;
-      if (ok && p.mask_pad_keys) ok = p.pad_mask[(size_t)b * L + j] != 0;
-      kmask[t] = __ballot_sync(0xffffffffu, ok);
+      for (int t = 0; t < 4 * KB; ++t) {
+        const int j = (2 * t + par) * 32 + lane;
+        pm[t] = (j < L && p.mask_pad_keys) ? p.pad_mask[(size_t)b * L + j] : (uint8_t)(j < L);
+      }
+#pragma unroll
+      for (int t = 0; t < 4 * KB; ++t) kmask[t] = __ballot_sync(0xffffffffu, pm[t] != 0);
     }
     const float sl2 = p.scale * kLog2eA;
     const bool drop = p.drop_p > 0.f;
@@ -162,7 +165,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       return m;
     };
-    mbar_wait(&bar_s, 0);
+    mbar_wait_relaxed(&bar_s, 0);
     tc_fence_after();
     // pass 1: row max over the visible keys of this thread's chunks
     float mx = -INFINITY;
@@ -191,7 +194,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
     s_red[0][par][row] = mx;
-    named_bar_sync(1, 256);
+    named_bar_sync(1 + quarter, 64);   // the two warps of this lane quarter
     mx = fmaxf(mx, s_red[0][par ^ 1][row]);
     const float moff = (mx == -INFINITY) ? 0.f : mx * sl2;
     // pass 2: exponentials, row sum, P (bf16) back into TMEM over S, optional copy of the un-dropped P to global
@@ -275,7 +278,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar_p);
-    named_bar_sync(1, 256);
+    named_bar_sync(1 + quarter, 64);   // the two warps of this lane quarter
     sum += s_red[1][par ^ 1][row];
     const float inv = sum > 0.f ? 1.f / sum : 0.f;
     if (par == 0 && i < L) {
@@ -283,7 +286,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (p.m_save) p.m_save[(size_t)bz * p.Lp + i] = moff;
     }
     // ---- O = (P.V) / sum : chunk parity 0 stores the even 32-column groups of the head, parity 1 the odd ones
-    mbar_wait(&bar_o, 0);
+    mbar_wait_relaxed(&bar_o, 0);
     tc_fence_after();
     if (warp_live) {
 #pragma unroll

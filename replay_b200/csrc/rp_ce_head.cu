@@ -738,14 +738,15 @@ __global__ void ce_label_scatter_kernel(const __nv_bfloat16* __restrict__ hc, co
   if (d_bias)
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_valid; t += gridDim.x * blockDim.x)
       atomicAdd(d_bias + labels[t], -inv_n);
-  const int per_row = d / 2;
+  const int per_row = d / 4;   // one 16-byte vector reduction (red.global.add.v4.f32) per 4 columns
   const long long total = (long long)n_valid * per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(i / per_row), c = (int)(i % per_row) * 2;
-    const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hc + (size_t)t * d + c));
-    float* dst = dE + (size_t)labels[t] * d + c;
-    atomicAdd(dst, -inv_n * h.x);
-    atomicAdd(dst + 1, -inv_n * h.y);
+    const int t = (int)(i / per_row), c = (int)(i % per_row) * 4;
+    const uint2 raw = *reinterpret_cast<const uint2*>(hc + (size_t)t * d + c);
+    const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+    const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    atomicAdd(reinterpret_cast<float4*>(dE + (size_t)labels[t] * d + c),
+              make_float4(-inv_n * h0.x, -inv_n * h0.y, -inv_n * h1.x, -inv_n * h1.y));
   }
 }
 
@@ -1093,7 +1094,7 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, 
   int blocks = (capacity + 7) / 8;
   if (blocks > 1024) blocks = 1024;
   if (fused) {
-    ce_bound_kernel<<<sm_count() * 2, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hc),
+    ce_bound_kernel<<<sm_count() * 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hc),
                                                         reinterpret_cast<const __nv_bfloat16*>(table), bias, n_valid, n_items, d,
                                                         ws.bound);
     RP_LAUNCH_CHECK();

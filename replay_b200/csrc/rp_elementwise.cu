@@ -288,35 +288,52 @@ __global__ void layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const 
     wv[i] = w[lane * VEC + i];
     bv[i] = b[lane * VEC + i];
   }
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
-    const int src = gather ? gather[r] : r;
-    const __nv_bfloat16* xr = x + (size_t)src * D + lane * VEC;
-    float v[VEC];
-    float s = 0.f;
+  constexpr int RB = VEC <= 8 ? 4 : 2;   // rows per warp and iteration: their index and row loads are in flight together
+  for (int rb = (blockIdx.x * wpb + (threadIdx.x >> 5)) * RB; rb < rows; rb += gridDim.x * wpb * RB) {
+    int src[RB];
 #pragma unroll
-    for (int i = 0; i < VEC; i += 2) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xr + i));
-      v[i] = f.x;
-      v[i + 1] = f.y;
-      s += f.x + f.y;
+    for (int k = 0; k < RB; ++k) {
+      const int rr = min(rb + k, rows - 1);
+      src[k] = gather ? gather[rr] : rr;
     }
-    const float mean = warp_sum(s) * inv_d;   // padded columns hold zeros: they add nothing to the sum
-    float q = 0.f;
+    __nv_bfloat162 xv[RB][VEC / 2];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const float dlt = feat_valid(lane * VEC + i, hd_valid) ? v[i] - mean : 0.f;
-      q += dlt * dlt;
+    for (int k = 0; k < RB; ++k) {
+      const __nv_bfloat16* xr = x + (size_t)src[k] * D + lane * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) xv[k][i >> 1] = *reinterpret_cast<const __nv_bfloat162*>(xr + i);
     }
-    const float var = warp_sum(q) * inv_d;
-    const float rstd = rsqrtf(var + eps);
-    __nv_bfloat16* yr = y + (size_t)r * D + lane * VEC;
 #pragma unroll
-    for (int i = 0; i < VEC; i += 2)
-      *reinterpret_cast<uint32_t*>(yr + i) =
-          pack_bf16((v[i] - mean) * rstd * wv[i] + bv[i], (v[i + 1] - mean) * rstd * wv[i + 1] + bv[i + 1]);
-    if (lane == 0) {
-      mean_out[r] = mean;
-      rstd_out[r] = rstd;
+    for (int k = 0; k < RB; ++k) {
+      const int r = rb + k;
+      if (r >= rows) break;
+      float v[VEC];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) {
+        const float2 f = __bfloat1622float2(xv[k][i >> 1]);
+        v[i] = f.x;
+        v[i + 1] = f.y;
+        s += f.x + f.y;
+      }
+      const float mean = warp_sum(s) * inv_d;   // padded columns hold zeros: they add nothing to the sum
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float dlt = feat_valid(lane * VEC + i, hd_valid) ? v[i] - mean : 0.f;
+        q += dlt * dlt;
+      }
+      const float var = warp_sum(q) * inv_d;
+      const float rstd = rsqrtf(var + eps);
+      __nv_bfloat16* yr = y + (size_t)r * D + lane * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2)
+        *reinterpret_cast<uint32_t*>(yr + i) =
+            pack_bf16((v[i] - mean) * rstd * wv[i] + bv[i], (v[i + 1] - mean) * rstd * wv[i + 1] + bv[i + 1]);
+      if (lane == 0) {
+        mean_out[r] = mean;
+        rstd_out[r] = rstd;
+      }
     }
   }
 }
@@ -344,43 +361,66 @@ __global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const
     dw_acc[i] = 0.f;
     db_acc[i] = 0.f;
   }
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
-    const int row = gather ? gather[r] : r;
-    const __nv_bfloat16* xr = x + (size_t)row * D + lane * VEC;
-    const __nv_bfloat16* gr = dy + (size_t)r * D + lane * VEC;
-    const float mean = mean_in[r], rstd = rstd_in[r];
-    float xh[VEC], g[VEC];
-    float s1 = 0.f, s2 = 0.f;
+  constexpr int RB = VEC <= 8 ? 2 : 1;   // rows per warp and iteration (loads of both rows in flight together)
+  for (int rb = (blockIdx.x * wpb + (threadIdx.x >> 5)) * RB; rb < rows; rb += gridDim.x * wpb * RB) {
+    int rowi[RB];
+    float mean_[RB], rstd_[RB];
 #pragma unroll
-    for (int i = 0; i < VEC; i += 2) {
-      const float2 xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xr + i));
-      const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gr + i));
-      xh[i] = feat_valid(lane * VEC + i, hd_valid) ? (xf.x - mean) * rstd : 0.f;
-      xh[i + 1] = feat_valid(lane * VEC + i + 1, hd_valid) ? (xf.y - mean) * rstd : 0.f;
-      dw_acc[i] += gf.x * xh[i];
-      dw_acc[i + 1] += gf.y * xh[i + 1];
-      db_acc[i] += gf.x;
-      db_acc[i + 1] += gf.y;
-      g[i] = gf.x * wv[i];
-      g[i + 1] = gf.y * wv[i + 1];
-      s1 += g[i] + g[i + 1];
-      s2 += g[i] * xh[i] + g[i + 1] * xh[i + 1];
+    for (int k = 0; k < RB; ++k) {
+      const int rr = min(rb + k, rows - 1);
+      rowi[k] = gather ? gather[rr] : rr;
+      mean_[k] = mean_in[rr];
+      rstd_[k] = rstd_in[rr];
     }
-    s1 = warp_sum(s1) * inv_d;
-    s2 = warp_sum(s2) * inv_d;
-    __nv_bfloat16* o = dx + (size_t)row * D + lane * VEC;
-    const __nv_bfloat16* a = add_to ? add_to + (size_t)row * D + lane * VEC : nullptr;
+    __nv_bfloat162 xv[RB][VEC / 2], gv[RB][VEC / 2], av[RB][VEC / 2];
 #pragma unroll
-    for (int i = 0; i < VEC; i += 2) {
-      float o0 = rstd * (g[i] - s1 - xh[i] * s2), o1 = rstd * (g[i + 1] - s1 - xh[i + 1] * s2);
-      if (!feat_valid(lane * VEC + i, hd_valid)) o0 = 0.f;       // padded inputs do not exist: no gradient
-      if (!feat_valid(lane * VEC + i + 1, hd_valid)) o1 = 0.f;
-      if (a) {
-        const float2 af = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + i));
-        o0 += af.x;
-        o1 += af.y;
+    for (int k = 0; k < RB; ++k) {
+      const __nv_bfloat16* xr = x + (size_t)rowi[k] * D + lane * VEC;
+      const __nv_bfloat16* gr = dy + (size_t)min(rb + k, rows - 1) * D + lane * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) {
+        xv[k][i >> 1] = *reinterpret_cast<const __nv_bfloat162*>(xr + i);
+        gv[k][i >> 1] = *reinterpret_cast<const __nv_bfloat162*>(gr + i);
+        if (add_to) av[k][i >> 1] = *reinterpret_cast<const __nv_bfloat162*>(add_to + (size_t)rowi[k] * D + lane * VEC + i);
       }
-      *reinterpret_cast<uint32_t*>(o + i) = pack_bf16(o0, o1);
+    }
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {
+      if (rb + k >= rows) break;
+      const int row = rowi[k];
+      const float mean = mean_[k], rstd = rstd_[k];
+      float xh[VEC], g[VEC];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) {
+        const float2 xf = __bfloat1622float2(xv[k][i >> 1]);
+        const float2 gf = __bfloat1622float2(gv[k][i >> 1]);
+        xh[i] = feat_valid(lane * VEC + i, hd_valid) ? (xf.x - mean) * rstd : 0.f;
+        xh[i + 1] = feat_valid(lane * VEC + i + 1, hd_valid) ? (xf.y - mean) * rstd : 0.f;
+        dw_acc[i] += gf.x * xh[i];
+        dw_acc[i + 1] += gf.y * xh[i + 1];
+        db_acc[i] += gf.x;
+        db_acc[i + 1] += gf.y;
+        g[i] = gf.x * wv[i];
+        g[i + 1] = gf.y * wv[i + 1];
+        s1 += g[i] + g[i + 1];
+        s2 += g[i] * xh[i] + g[i + 1] * xh[i + 1];
+      }
+      s1 = warp_sum(s1) * inv_d;
+      s2 = warp_sum(s2) * inv_d;
+      __nv_bfloat16* o = dx + (size_t)row * D + lane * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) {
+        float o0 = rstd * (g[i] - s1 - xh[i] * s2), o1 = rstd * (g[i + 1] - s1 - xh[i + 1] * s2);
+        if (!feat_valid(lane * VEC + i, hd_valid)) o0 = 0.f;       // padded inputs do not exist: no gradient
+        if (!feat_valid(lane * VEC + i + 1, hd_valid)) o1 = 0.f;
+        if (add_to) {
+          const float2 af = __bfloat1622float2(av[k][i >> 1]);
+          o0 += af.x;
+          o1 += af.y;
+        }
+        *reinterpret_cast<uint32_t*>(o + i) = pack_bf16(o0, o1);
+      }
     }
   }
   // block reduction of dw/db through shared memory, then one atomic per column per block

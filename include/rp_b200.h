@@ -324,6 +324,16 @@ int rp_wgrad_group(const rp_wgrad_pair* pairs, int n_pairs, int T, int accumulat
 int rp_adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, long long n, const float* lr_dev,
                  int32_t* step_dev, float beta1, float beta2, float eps, float grad_scale, const uint8_t* frozen,
                  int zero_grad, void* stream);
+/* Gradient exchange of data-parallel training over NVLink peer memory - ONE kernel inside the captured step graph.
+ *   replaces  the bucketed all-reduce of Lightning DDP under loss.backward()  replay/nn/lightning/module.py:62-75 with
+ *             Trainer(strategy="ddp"); replay/models/nn/sequential/sasrec/lightning.py:196-209
+ * bufs[w] / states[w] (host arrays of `world` device pointers): rank w's fp32 gradient buffer (n elements, 16-byte aligned)
+ * and its state block (rp_peer_allreduce_state_bytes() bytes, zeroed once) as mapped into THIS process - every rank passes
+ * pointers into the same symmetric allocation (replay_b200/peer.py).  world in 2..8, one node.  Result: every buffer holds
+ * the element-wise sum, bit-identical on all ranks (each element is summed by one rank in rank order and broadcast).
+ * Every rank must enqueue it exactly once per step; CUDA-graph capturable; the grid never exceeds the SM count. */
+size_t rp_peer_allreduce_state_bytes(void);
+int rp_peer_allreduce(void* const* bufs, void* const* states, int rank, int world, long long n, void* stream);
 int rp_cast_bf16(const float* src, void* dst, long long n, void* stream);
 int rp_counter_add(unsigned long long* counter, unsigned long long inc, void* stream);
 

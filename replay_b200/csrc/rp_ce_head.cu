@@ -76,6 +76,30 @@ static constexpr int kCeMaxGroups = 2;
 #ifndef RP_CE_ORDER
 #define RP_CE_ORDER 1
 #endif
+#ifndef RP_CE_TN64
+#define RP_CE_TN64 0      /* d <= 128: 64-wide column tiles in four S buffers (0 = 128-wide in two) */
+#endif
+#ifndef RP_CE_TN64_GROUPS
+#define RP_CE_TN64_GROUPS 2   /* TN = 64: two epilogue warp sets on alternating tiles (1 = all 8 warps on every tile) */
+#endif
+#ifndef RP_CE_RELAXED_WAITS
+#define RP_CE_RELAXED_WAITS 0   /* the MMA / TMA threads sleep between polls of their (long) waits: they share a sub-partition with two epilogue warps */
+#endif
+#ifndef RP_CE_PACE_DEPTH
+#define RP_CE_PACE_DEPTH 0   /* pairs of tcgen05.mma in flight before the issuing thread waits for a completion (0 = issue at will) */
+#endif
+#ifndef RP_CE_ISSUERS
+#define RP_CE_ISSUERS 1   /* MMA-issuing threads of the backward / fused kernels (1 = warp 1 alone) */
+#endif
+#ifndef RP_CE_PERSIST
+#define RP_CE_PERSIST 1   /* dE pass: one CTA per SM over balanced slices of the (item tile, token tile) pairs; 0 = one CTA per item tile */
+#endif
+#ifdef RP_CE_TRACE  // diagnostic build (-DRP_CE_TRACE): timeline of CTA 0 - 8 event kinds x the first 256 column tiles
+__device__ unsigned long long g_ce_trace[2][16 * 256];   // [0]: fused forward / dH pass, [1]: dE pass; kinds 8..15: hand-over time of epilogue warp 0..7
+#define RP_CTR(k, j) do { if (blockIdx.x == 0 && (j) < 256) g_ce_trace[MODE == 1][(k) * 256 + (j)] = clock64(); } while (0)
+#else
+#define RP_CTR(k, j) do { } while (0)
+#endif
 template <int DEG, int EVERY>
 __device__ __forceinline__ float ce_ex2(float x, int q) {
   if (EVERY > 0 && (q % (EVERY > 0 ? EVERY : 1)) == 1) return ex2_poly<DEG>(x);
@@ -340,8 +364,50 @@ __global__ void __launch_bounds__(1024) ce_loss_reduce_kernel(const float* __res
 // MODE 2: rows = tokens, FUSED forward+backward: G~ = exp(s + b) with reference max 0 (valid while |s| is bounded, see
 //         ce_bound_kernel), per-row sum of G~ and un-normalised dH~ = sum_i G~ E_i over this CTA's column split
 //                                                                                      -> out = partial dH~ fp32, zpart
-template <int KCH, int NSTAGE, int MODE, int NBUF, bool A_TMEM, bool INORDER, bool HAS_BIAS, int GROUPS>
-__global__ void __launch_bounds__(64 + GROUPS * kBwdEpiWarps * 32, 1)
+// One SEGMENT of a CTA's work = one row tile against a contiguous run of column tiles.  The per-row-tile launches (fused
+// forward / two-pass dH: grid = row tiles x column splits) have exactly one segment per CTA.  The dE pass is PERSISTENT: the
+// grid is one CTA per SM and CTA c owns the slice [W c / G, W (c+1) / G) of the W = row tiles x column tiles linearised
+// (row tile, column tile) pairs - up to a few segments, every SM busy to the last tile (391 item tiles as one CTA each were
+// 2.64 waves on 148 SMs: 12 % of the pass was an idle tail).  A segment that does not cover its row tile's whole column
+// range adds its partial accumulator to the (zeroed) output with vector reductions.
+struct CeSeg {
+  long long w, w_end;
+  int n_ct_all, row_tile, j0, n;
+  bool valid;
+  __device__ void set() {
+    valid = w < w_end;
+    row_tile = (int)(w / n_ct_all);
+    j0 = (int)(w - (long long)row_tile * n_ct_all);
+    const long long left = w_end - w;
+    n = (n_ct_all - j0 < left) ? n_ct_all - j0 : (int)left;
+  }
+  __device__ void advance() {
+    w += n;
+    set();
+  }
+};
+
+// TN = width of a column tile (= of one S buffer in TMEM).  TN = 64 with FOUR S buffers (d <= 128): the chain
+//   first GEMM (S) -> epilogue (G over S) -> second GEMM (reads G) -> first GEMM of the tile that reuses the buffer
+// is serial per buffer, so with two 128-wide buffers a tile took (tensor time + epilogue time + hand-off latencies) / 2 =
+// ~1535 cycles although the tensor pipe and the MUFU pipe were each busy for only 1024 of them (ncu r2i: both 67 %).  Four
+// 64-wide buffers use the same 256 TMEM columns, keep four such chains in flight, and leave S of the next tile complete long
+// before the epilogue gets to it (so its first TMEM load can be issued ahead of time).
+// CG / GROUPS = how the 8 epilogue warps divide the work.  TN = 128: CG = 2 column groups per TMEM lane quarter, all 8 warps
+// on every tile.  TN = 64: TWO warp SETS (GROUPS = 2) of one warp per lane quarter (CG = 1), set g owns the tiles j = g mod 2.
+// The timeline of a CTA (tools/trace_ce.py, profiles/r2_ce_timeline.md) shows ~450 cycles per tile in the epilogue that are
+// not exponentials - waking up on the S barrier, the first TMEM load, the drain of the last exponentials into the TMEM store,
+// the hand-over - next to 16 cycles per column of MUFU time (two warps share a sub-partition's MUFU).  With one set these
+// phases are serial (1500 cycles per 128 columns, MUFU 67 % busy); with two sets on different tiles the sub-partition's two
+// warps are out of phase and the other warp's exponentials fill them.
+// NI = number of MMA-issuing threads (warp 1 and the warps behind the epilogue warps, one per SM sub-partition).  Issuing a
+// tile's 16 tcgen05.mma keeps the issuing thread's sub-partition from issuing anything else for ~700 cycles (timeline: the
+// two epilogue warps that share warp 1's sub-partition handed their G over 700-900 cycles after the other six, and the tile
+// pace followed them).  NI = 3 issuers take the tiles round-robin, so sub-partitions 1-3 lose a third of that each (sub-
+// partition 0 hosts the TMA thread); an mbarrier token passes the right to issue from tile to tile, which keeps the
+// instructions in tile order in the (in-order) tensor pipe.
+template <int KCH, int NSTAGE, int MODE, int NBUF, bool A_TMEM, bool INORDER, bool HAS_BIAS, int GROUPS, bool PERSIST, int TN, int CG, int NI>
+__global__ void __launch_bounds__(64 + GROUPS * 4 * CG * 32 + (NI - 1) * 32, 1)
 ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __nv_bfloat16* __restrict__ a_rows /* the row-side matrix (tmA) as a plain pointer, for A_TMEM */,
               const float* __restrict__ cvec /* [T] exponent offsets per token */, const int32_t* __restrict__ labels,
@@ -351,35 +417,53 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               int n_splits, int capacity, float* __restrict__ zpart, const CeDirect direct) {
   constexpr bool COLCONST = (MODE == 1);
   constexpr bool FUSED = (MODE == 2);
-  constexpr int kW = kT / kBwdCG;  // S columns owned by one epilogue warp (its bf16 G lands in the first kW/2 of them)
-  constexpr int kEW = kBwdEpiWarps * GROUPS;   // epilogue warps in total
-  constexpr int kSlots = kBwdCG * GROUPS;      // column slots of the accumulator read-out / of the row-sum partials
-  static_assert(GROUPS == 1 || (GROUPS == 2 && NBUF == 2), "one epilogue warp set per S buffer");
+  constexpr int kW = TN / CG;  // S columns owned by one epilogue warp (its bf16 G lands in the first kW/2 of them)
+  constexpr int kChunkB = TN * 128;   // bytes of one [TN rows x 64 bf16] swizzled chunk of a column tile
+  constexpr int kEW = 4 * CG * GROUPS;   // epilogue warps in total
+  constexpr int kSlots = CG * GROUPS;      // column slots of the accumulator read-out / of the row-sum partials
+  static_assert(GROUPS == 1 || (GROUPS == 2 && NBUF % 2 == 0), "two epilogue warp sets: even / odd S buffers");
+  static_assert(NBUF * TN + KCH * 64 + (A_TMEM ? KCH * 32 : 0) <= 512, "TMEM: S buffers + accumulator + row tile");
   constexpr int D = KCH * 64;
   if (safe_flag && (*safe_flag != 0) != (run_if_safe != 0)) return;  // fused path vs two-pass fallback (uniform)
-  constexpr int kStage = KCH * kChunk;
+  constexpr int kStage = KCH * kChunkB;   // one column tile in shared memory
+  constexpr int kATile = KCH * kChunk;    // the row tile (when it is not in TMEM)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // A_TMEM: the resident row tile lives in TMEM (K-major, two bf16 per 32-bit column) and the first GEMM reads it from
   // there, which halves that GEMM's shared-memory traffic - M=128 x N=128 SS MMAs need the full 128 B/clk of smem.
   uint8_t* sA = smem;
-  uint8_t* sB = smem + (A_TMEM ? 0 : kStage);
-  __shared__ __align__(16) float s_cc[NSTAGE][kT];
+  uint8_t* sB = smem + (A_TMEM ? 0 : kATile);
+  __shared__ __align__(16) float s_cc[NSTAGE][TN];
   __shared__ float s_gsum[kSlots][kT];
   __shared__ float s_dot[FUSED ? kSlots : 1][kT];
-  __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_sfull[NBUF], bar_sfree[NBUF], bar_pfull[NBUF], bar_acc;
+  __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_sfull[NBUF], bar_sfree[NBUF], bar_pfull[NBUF], bar_acc, bar_tok[NI], bar_pace[8];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_valid = *n_valid_ptr;
-  const int row_tile = FUSED ? blockIdx.x / n_splits : blockIdx.x, split = FUSED ? blockIdx.x % n_splits : 0;
-  const int r0 = row_tile * kT;                             // first row (token or item) of this CTA
+  static_assert(!PERSIST || (COLCONST && A_TMEM), "persistent work slices: dE pass with the row tile in TMEM");
+  const int split = FUSED ? blockIdx.x % n_splits : 0;
   const int n_rows = COLCONST ? n_items : n_valid;
-  if (r0 >= n_rows) return;
   const int n_cols = COLCONST ? n_valid : n_items;
-  const int n_ct_all = (n_cols + kT - 1) / kT;              // column tiles of the whole problem
+  const int n_ct_all = (n_cols + TN - 1) / TN;              // column tiles of the whole problem
   const int jg0 = FUSED ? (int)(((long long)n_ct_all * split) / n_splits) : 0;        // first column tile of this CTA
-  const int n_ct = FUSED ? (int)(((long long)n_ct_all * (split + 1)) / n_splits) - jg0 : n_ct_all;
+  CeSeg seg0;
+  seg0.n_ct_all = n_ct_all > 0 ? n_ct_all : 1;
+  if (PERSIST) {
+    const long long W = (long long)((n_rows + kT - 1) / kT) * n_ct_all;
+    seg0.w = W * blockIdx.x / gridDim.x;
+    seg0.w_end = W * (blockIdx.x + 1) / gridDim.x;
+    seg0.set();
+    if (!seg0.valid) return;   // (uniform) nothing to do: the output was zeroed by the host side
+  } else {
+    seg0.row_tile = FUSED ? blockIdx.x / n_splits : blockIdx.x;
+    seg0.j0 = jg0;
+    seg0.n = FUSED ? (int)(((long long)n_ct_all * (split + 1)) / n_splits) - jg0 : n_ct_all;
+    seg0.w = 0;
+    seg0.w_end = seg0.n;       // advance() ends the iteration after this one segment (n = 0 included)
+    seg0.valid = true;
+    if (seg0.row_tile * kT >= n_rows) return;
+  }
 
   if (threadIdx.x == 0) {
     mbar_init(&bar_a, A_TMEM ? kEW : 1);
@@ -390,9 +474,11 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     for (int i = 0; i < NBUF; ++i) {
       mbar_init(&bar_sfull[i], 1);
       mbar_init(&bar_sfree[i], 1);
-      mbar_init(&bar_pfull[i], kBwdEpiWarps);
+      mbar_init(&bar_pfull[i], 4 * CG);
     }
     mbar_init(&bar_acc, 1);
+    for (int i = 0; i < NI; ++i) mbar_init(&bar_tok[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&bar_pace[i], 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -402,86 +488,161 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t tmem_acc = tmem + NBUF * kT;   // S buffers first, then the [128 x D] accumulator
+  const uint32_t tmem_acc = tmem + NBUF * TN;   // S buffers first, then the [128 x D] accumulator
   const uint32_t tmem_a = tmem_acc + D;         // A_TMEM: [128 x D] bf16 operand, D/2 columns
 
   if (warp == 0) {
     if (elect_one()) {
       if (!A_TMEM) {
-        mbar_arrive_expect_tx(&bar_a, kStage);
-        for (int kc = 0; kc < KCH; ++kc) tma_load_2d(sA + kc * kChunk, &tmA, &bar_a, kc * 64, r0);
+        mbar_arrive_expect_tx(&bar_a, kATile);
+        for (int kc = 0; kc < KCH; ++kc) tma_load_2d(sA + kc * kChunk, &tmA, &bar_a, kc * 64, seg0.row_tile * kT);
       }
-      for (int j = 0; j < n_ct; ++j) {
-        const uint32_t s = j % NSTAGE, ph = (j / NSTAGE) & 1;
-        mbar_wait(&bar_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&bar_full[s], kStage + (COLCONST ? kT * 4 : 0));
-        for (int kc = 0; kc < KCH; ++kc)
-          tma_load_2d(sB + s * kStage + kc * kChunk, &tmB, &bar_full[s], kc * 64, (jg0 + j) * kT);
-        if (COLCONST) {
-          asm volatile(
-              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                  smem_u32(&s_cc[s][0])),
-              "l"(cvec + (size_t)(jg0 + j) * kT), "r"(kT * 4), "r"(smem_u32(&bar_full[s]))
-              : "memory");
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t idesc1 = umma_idesc_bf16(kT, kT);
-      constexpr uint32_t idesc2 = umma_idesc_bf16(kT, D, false, true);
-      mbar_wait(&bar_a, 0);
-      tc_fence_after();
-      auto issue_mma1 = [&](int j) {
-        const uint32_t s = j % NSTAGE, ph = (j / NSTAGE) & 1;
-        mbar_wait(&bar_full[s], ph);
-        if (!INORDER && j >= NBUF) mbar_wait(&bar_sfree[j % NBUF], ((j / NBUF) - 1) & 1);
-        tc_fence_after();
-        const uint32_t dcol = tmem + (j % NBUF) * kT;
-#pragma unroll
-        for (int kc = 0; kc < KCH; ++kc) {
-          const uint32_t a0 = smem_u32(sA + kc * kChunk), b0 = smem_u32(sB + s * kStage + kc * kChunk);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            if (A_TMEM)
-              umma_ts(dcol, tmem_a + kc * 32 + ks * 8, umma_desc_sw128(b0 + ks * 32, 16, 1024), idesc1, (kc | ks) != 0);
-            else
-              umma_ss(dcol, umma_desc_sw128(a0 + ks * 32, 16, 1024), umma_desc_sw128(b0 + ks * 32, 16, 1024), idesc1,
-                      (kc | ks) != 0);
+      // the column-tile ring runs on a tile counter that continues across segments: the loads of the next segment's first
+      // tiles are already in flight while the current segment drains
+      uint32_t g = 0;
+      for (CeSeg sg = seg0; sg.valid; sg.advance())
+        for (int jl = 0; jl < sg.n; ++jl, ++g) {
+          const uint32_t s = g % NSTAGE, ph = (g / NSTAGE) & 1;
+          const int jc = sg.j0 + jl;   // column tile
+#if RP_CE_RELAXED_WAITS
+          mbar_wait_relaxed(&bar_empty[s], ph ^ 1);
+#else
+          mbar_wait(&bar_empty[s], ph ^ 1);
+#endif
+          mbar_arrive_expect_tx(&bar_full[s], kStage + (COLCONST ? TN * 4 : 0));
+          for (int kc = 0; kc < KCH; ++kc)
+            tma_load_2d(sB + s * kStage + kc * kChunkB, &tmB, &bar_full[s], kc * 64, jc * TN);
+          if (COLCONST) {
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    smem_u32(&s_cc[s][0])),
+                "l"(cvec + (size_t)jc * TN), "r"(TN * 4), "r"(smem_u32(&bar_full[s]))
+                : "memory");
           }
         }
-        umma_commit(&bar_sfull[j % NBUF]);
-      };
+    }
+  } else if (warp == 1 || warp >= 2 + kEW) {
+    const int ii = warp == 1 ? 0 : warp - (2 + kEW) + 1;   // issuer index: tiles with (ring position) % NI == ii are mine
+    if (elect_one()) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(kT, TN);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(kT, D, false, true);
       // PRE S tiles are in flight ahead of the second GEMM.  INORDER: tile j+NBUF follows the second GEMM of tile j through
       // the in-order tensor pipe (no barrier); otherwise tile j+PRE is issued before it and waits for the second GEMM of
       // tile j+PRE-NBUF (RP_CE_ORDER 0: the one issued last -> pipe drain; 2: two groups back)
       constexpr int PRE = INORDER ? NBUF : ((RP_CE_ORDER == 2 && NBUF >= 3) ? NBUF - 2 : NBUF - 1);
-      for (int j = 0; j < PRE && j < n_ct; ++j) issue_mma1(j);
-      for (int j = 0; j < n_ct; ++j) {
-        if (!INORDER && j + PRE < n_ct) issue_mma1(j + PRE);
-        const uint32_t s = j % NSTAGE;
-        mbar_wait(&bar_pfull[j % NBUF], (j / NBUF) & 1);
-        tc_fence_after();
-        const uint32_t pcol = tmem + (j % NBUF) * kT;  // G (bf16 pairs) lives over S: k-steps 0-3 at +0, 4-7 at +64
-        const uint32_t b0 = smem_u32(sB + s * kStage);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_ts(tmem_acc, pcol + ((ks * 16) / kW) * kW + ((ks * 16) % kW) / 2, umma_desc_sw128(b0 + ks * 2048, kChunk, 1024),
-                  idesc2, (j | ks) != 0);
-        umma_commit(&bar_empty[s]);
-        if (INORDER) {
-          if (j + PRE < n_ct) issue_mma1(j + PRE);
-        } else {
-          umma_commit(&bar_sfree[j % NBUF]);
+      uint32_t g0 = 0, nseg = 0;   // ring position of the segment's first tile (S buffers, smem stages); segment count
+      uint32_t n_tok = 0;          // tokens this issuer has consumed (parity of its token barrier)
+      // Issue pacing.  The tensor pipe's instruction queue holds ~6 tcgen05.mma; a further one does not just make this thread
+      // wait - it stalls the DISPATCH of this thread's SM sub-partition, and the two epilogue warps that live there with it
+      // (timeline, tools/trace_ce.py: their hand-over came 700-900 cycles after the other six warps', whichever sub-partition
+      // the issuer was moved to).  So instructions go out in pairs, each pair committed to a ring of eight mbarriers, and pair
+      // m is only issued once pair m - DEPTH has completed: the waiting happens on an mbarrier (harmless) instead of in the
+      // dispatch stage, and the pipe still has 2 (DEPTH - 1) .. 2 DEPTH instructions queued.
+      constexpr uint32_t DEPTH = RP_CE_PACE_DEPTH;
+      uint32_t n_pair = 0, n_half = 0;
+      auto pace = [&]() {          // call right before every tcgen05.mma
+        if (DEPTH == 0 || NI > 1) return;
+        if ((n_half & 1) == 0 && n_pair >= DEPTH) {
+          const uint32_t m = n_pair - DEPTH;
+          mbar_wait(&bar_pace[m & 7], (m >> 3) & 1);
         }
+      };
+      auto paced = [&]() {         // call right after every tcgen05.mma
+        if (DEPTH == 0 || NI > 1) return;
+        if (n_half & 1) {
+          umma_commit(&bar_pace[n_pair & 7]);
+          ++n_pair;
+        }
+        ++n_half;
+      };
+      for (CeSeg sg = seg0; sg.valid; sg.advance(), ++nseg) {
+        const int n_ct = sg.n;
+        auto issue_mma1 = [&](int jl) {
+          const uint32_t g = g0 + jl, s = g % NSTAGE, ph = (g / NSTAGE) & 1;
+          mbar_wait(&bar_full[s], ph);
+          if (!INORDER && g >= NBUF) mbar_wait(&bar_sfree[g % NBUF], ((g / NBUF) - 1) & 1);
+          tc_fence_after();
+          const uint32_t dcol = tmem + (g % NBUF) * TN;
+#pragma unroll
+          for (int kc = 0; kc < KCH; ++kc) {
+            const uint32_t a0 = smem_u32(sA + kc * kChunk), b0 = smem_u32(sB + s * kStage + kc * kChunkB);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              pace();
+              if (A_TMEM)
+                umma_ts(dcol, tmem_a + kc * 32 + ks * 8, umma_desc_sw128(b0 + ks * 32, 16, 1024), idesc1, (kc | ks) != 0);
+              else
+                umma_ss(dcol, umma_desc_sw128(a0 + ks * 32, 16, 1024), umma_desc_sw128(b0 + ks * 32, 16, 1024), idesc1,
+                        (kc | ks) != 0);
+              paced();
+            }
+          }
+          umma_commit(&bar_sfull[g % NBUF]);
+        };
+        for (int jl = 0; jl < n_ct; ++jl) {
+          const uint32_t g = g0 + jl, s = g % NSTAGE;
+          if (NI > 1) {
+            if ((int)(g % NI) != ii) continue;
+            if (g > 0) {   // the right to issue: the issuer of tile g-1 has queued all of its instructions
+              mbar_wait(&bar_tok[ii], n_tok & 1);
+              ++n_tok;
+              tc_fence_after();
+            }
+          }
+          if (jl == 0) {
+            // the row tile of this segment is in place (TMEM: written by the epilogue warps after they drained the previous
+            // segment's accumulator, so the accumulator may be overwritten as well); the segment's first S tiles go first
+            mbar_wait(&bar_a, nseg & 1);
+            tc_fence_after();
+            for (int q = 0; q < PRE && q < n_ct; ++q) issue_mma1(q);
+          }
+          if (!INORDER && jl + PRE < n_ct) issue_mma1(jl + PRE);
+          RP_CTR(4, g);   // MMA thread starts waiting for G of tile g
+#if RP_CE_RELAXED_WAITS
+          mbar_wait_relaxed(&bar_pfull[g % NBUF], (g / NBUF) & 1);
+#else
+          mbar_wait(&bar_pfull[g % NBUF], (g / NBUF) & 1);
+#endif
+          RP_CTR(5, g);   // ... G of tile g is there
+          tc_fence_after();
+          const uint32_t pcol = tmem + (g % NBUF) * TN;  // G (bf16 pairs) lives over S, kW/2 packed columns per column group
+          const uint32_t b0 = smem_u32(sB + s * kStage);
+#pragma unroll
+          for (int ks = 0; ks < TN / 16; ++ks) {
+            pace();
+            umma_ts(tmem_acc, pcol + ((ks * 16) / kW) * kW + ((ks * 16) % kW) / 2, umma_desc_sw128(b0 + ks * 2048, kChunkB, 1024),
+                    idesc2, (jl | ks) != 0);
+            paced();
+          }
+          umma_commit(&bar_empty[s]);
+          if (INORDER) {
+            if (jl + PRE < n_ct) issue_mma1(jl + PRE);
+          } else {
+            umma_commit(&bar_sfree[g % NBUF]);
+          }
+          if (jl == n_ct - 1) umma_commit(&bar_acc);   // (in-order pipe: everything issued before it has completed as well)
+          RP_CTR(6, g);   // second GEMM of tile g and first GEMM of tile g + PRE are queued
+          if (NI > 1) {
+            tc_fence_before();
+            mbar_arrive(&bar_tok[(g + 1) % NI]);
+          }
+        }
+        if (n_ct == 0 && ii == 0) {   // (single-segment launches only) nothing to multiply: release the epilogue's final wait
+          mbar_wait(&bar_a, nseg & 1);
+          umma_commit(&bar_acc);
+        }
+        g0 += n_ct;
       }
-      umma_commit(&bar_acc);
     }
   } else {
     const int ew = warp - 2, quarter = warp & 3;                 // lane quarter
-    const int grp = ew / kBwdEpiWarps, cg = (ew % kBwdEpiWarps) >> 2, slot = grp * kBwdCG + cg;   // warp set, column group
+    const int grp = ew / (4 * CG), cg = (ew % (4 * CG)) >> 2, slot = grp * CG + cg;   // warp set, column group
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    uint32_t g0 = 0, nseg = 0;   // ring position of the segment's first tile; segment count (parity of bar_a / bar_acc)
+    for (CeSeg sg = seg0; sg.valid; g0 += sg.n, ++nseg, sg.advance()) {
+    const int r0 = sg.row_tile * kT, n_ct = sg.n, jg0 = sg.j0;   // first row (token or item), column tiles [jg0, jg0 + n_ct)
+    const bool partial = PERSIST && n_ct != n_ct_all;            // other CTAs hold the rest of this row tile's columns
     float crow = 0.f;
     if (MODE == 0) crow = (r0 + row < n_valid) ? cvec[r0 + row] : -INFINITY;
     if (FUSED) crow = (r0 + row < n_valid) ? 0.f : -INFINITY;
@@ -509,88 +670,141 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_a);
     }
-    for (int j = grp; j < n_ct; j += GROUPS) {   // two warp sets: this one owns every GROUPS-th column tile (= one S buffer)
-      const uint32_t b = j % NBUF, s = j % NSTAGE;
-      if (COLCONST) mbar_wait(&bar_full[s], (j / NSTAGE) & 1);  // s_cc[s] was written by the async proxy
-      mbar_wait(&bar_sfull[b], (j / NBUF) & 1);
+    // Software pipeline over CW-column chunks of this warp's kW = 64 columns: while the exponentials of one chunk run, the
+    // tcgen05.ld of the next chunk of the SAME tile is in flight.  A warp-wide load occupies the quarter's TMEM read port for
+    // ~2 cycles per column (256 cycles per tile and SM sub-partition); with load-everything -> wait -> compute that time was
+    // MUFU idle time (ncu r2b: MUFU 61-65 % busy, ~1400 cycles per tile against 1024 of MUFU work and 1168 of tensor work).
+    // The pipeline does NOT reach into the next tile: S of tile j+1 only completes one tile of tensor work after the G of tile
+    // j-1 was handed over (two S buffers, in-order issue), i.e. about when this tile's epilogue ends - a prefetch placed
+    // before this tile's last chunk waited ~500 cycles for it (measured r2i: 1.02 -> 1.44 ms).
+    constexpr int CW = 16, NCH = kW / CW;
+    static_assert(NCH >= 2 && NCH % 2 == 0, "chunk pipeline: pairs of 16-column chunks");
+    // the first chunk of the NEXT tile is fetched before this tile's last chunk is exponentiated - only with >= 3 S buffers:
+    // with two, S of tile j+1 completes about when the epilogue of tile j ends (measured r2i: such a prefetch costs 40 %)
+    // (a set's next tile is j + GROUPS; its S is issued behind the second GEMM of tile j + GROUPS - NBUF, which must not
+    //  depend on THIS tile's G: NBUF > GROUPS)
+    constexpr bool PREFETCH = (NBUF >= 3) && (NBUF > GROUPS);
+    auto s_wait = [&](int j) {   // j: tile of this segment; g0 + j: its position in the S-buffer / smem rings
+      mbar_wait(&bar_sfull[(g0 + j) % NBUF], ((g0 + j) / NBUF) & 1);
       tc_fence_after();
-      const uint32_t sbase = tmem + lane_base + b * kT + cg * kW;
+    };
+    auto s_addr = [&](int j) -> uint32_t { return tmem + lane_base + (uint32_t)((g0 + j) % NBUF) * TN + cg * kW; };
+    uint32_t rawA[CW], rawB[CW];
+#if RP_CE_ABLATE == 4
+#pragma unroll
+    for (int q = 0; q < CW; ++q) rawA[q] = rawB[q] = __float_as_uint(-1.f - 0.01f * (lane + q));
+#endif
+    for (int j = grp; j < n_ct; j += GROUPS) {   // two warp sets: this one owns every GROUPS-th column tile (= one S buffer)
+      const uint32_t b = (g0 + j) % NBUF, s = (g0 + j) % NSTAGE;
+      if (COLCONST) mbar_wait(&bar_full[s], ((g0 + j) / NSTAGE) & 1);  // s_cc[s] was written by the async proxy
+      if (threadIdx.x == 64) RP_CTR(0, g0 + j);   // epilogue arrives at tile
+      if (!PREFETCH || j == grp || RP_CE_ABLATE == 2) s_wait(j);
+      if (threadIdx.x == 64) RP_CTR(1, g0 + j);   // S observed complete
 #if RP_CE_ABLATE == 2  // diagnostic build (tools/ce_variants.sh): no epilogue work at all -> MMA + TMA pipeline alone
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_pfull[b]);
       continue;
 #endif
-      uint32_t raw[kW];
+      const uint32_t sbase = s_addr(j);
+      // G = exp2(S*log2e + offset) of one CW-column chunk -> CW/2 packed bf16 pairs, written in place over the warp's own
+      // (already consumed) S columns: chunk k lands in packed columns [k CW/2, (k+1) CW/2)
+      auto chunk = [&](const uint32_t (&raw)[CW], int k) {
+        uint32_t pk[CW / 2];
+        const int col0 = (jg0 + j) * TN + cg * kW + k * CW;
+        if (COLCONST) {
+          const float4* cc = reinterpret_cast<const float4*>(&s_cc[s][cg * kW + k * CW]);
 #pragma unroll
-      for (int c = 0; c < kW; c += 32) tmem_ld32(sbase + c, *reinterpret_cast<uint32_t(*)[32]>(&raw[c]));
-      tmem_ld_wait();
-      uint32_t pk[kW / 2];
-      const int col0 = (jg0 + j) * kT + cg * kW;
-      // G = exp2(S*log2e + offset): mostly MUFU.EX2, a share on the FMA-pipe polynomial (RP_CE_POLY_EVERY_BWD)
-      if (COLCONST) {
-        const float4* cc = reinterpret_cast<const float4*>(&s_cc[s][cg * kW]);
-#pragma unroll
-        for (int q = 0; q < kW; q += 4) {
-          const float4 o = cc[q >> 2];
-          const float g0 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 0]), kLog2e, o.x), q + 0);
-          const float g1 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 1]), kLog2e, o.y), q + 1);
-          const float g2 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 2]), kLog2e, o.z), q + 2);
-          const float g3 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 3]), kLog2e, o.w), q + 3);
-          if (HAS_BIAS) gsum += (g0 + g1) + (g2 + g3);
-          pk[(q >> 1) + 0] = pack_bf16(g0, g1);
-          pk[(q >> 1) + 1] = pack_bf16(g2, g3);
-        }
-      } else {
-        if (HAS_BIAS) {  // per-column bias: s + b before the exponential (warp-uniform 16-byte loads)
-#pragma unroll
-          for (int q = 0; q < kW; q += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
-            raw[q + 0] = __float_as_uint(__uint_as_float(raw[q + 0]) + b4.x);
-            raw[q + 1] = __float_as_uint(__uint_as_float(raw[q + 1]) + b4.y);
-            raw[q + 2] = __float_as_uint(__uint_as_float(raw[q + 2]) + b4.z);
-            raw[q + 3] = __float_as_uint(__uint_as_float(raw[q + 3]) + b4.w);
+          for (int q = 0; q < CW; q += 4) {
+            const float4 o = cc[q >> 2];
+            const float g0_ = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 0]), kLog2e, o.x), q + 0);
+            const float g1_ = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 1]), kLog2e, o.y), q + 1);
+            const float g2_ = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 2]), kLog2e, o.z), q + 2);
+            const float g3_ = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 3]), kLog2e, o.w), q + 3);
+            if (HAS_BIAS) gsum += (g0_ + g1_) + (g2_ + g3_);
+            pk[(q >> 1) + 0] = pack_bf16(g0_, g1_);
+            pk[(q >> 1) + 1] = pack_bf16(g2_, g3_);
           }
-        }
-        if (col0 + kW <= n_items) {  // (warp-uniform) every column of this part exists: no per-element masking in the hot loop
-          float z0 = 0.f, z1 = 0.f;
+        } else {
+          float sv[CW];
 #pragma unroll
-          for (int q = 0; q < kW; q += 2) {
-            const float g0 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 0]), kLog2e, crow), q + 0);
-            const float g1 = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 1]), kLog2e, crow), q + 1);
-            if (FUSED) {
-              z0 += g0;
-              z1 += g1;
+          for (int q = 0; q < CW; ++q) sv[q] = __uint_as_float(raw[q]);
+          if (HAS_BIAS) {  // per-column bias: s + b before the exponential (warp-uniform 16-byte loads)
+#pragma unroll
+            for (int q = 0; q < CW; q += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
+              sv[q + 0] += b4.x;
+              sv[q + 1] += b4.y;
+              sv[q + 2] += b4.z;
+              sv[q + 3] += b4.w;
             }
-            pk[q >> 1] = pack_bf16(g0, g1);
           }
-          if (FUSED) zacc += z0 + z1;
-        } else {  // ragged last tile of the catalog: columns beyond it do not exist
+          if (col0 + CW <= n_items) {  // (warp-uniform) every column of this chunk exists: no per-element masking in the hot loop
+            float z0 = 0.f, z1 = 0.f;
 #pragma unroll
-          for (int q = 0; q < kW; q += 2) {
-            float g0 = ex2f(fmaf(__uint_as_float(raw[q + 0]), kLog2e, crow));
-            float g1 = ex2f(fmaf(__uint_as_float(raw[q + 1]), kLog2e, crow));
-            if (col0 + q >= n_items) g0 = 0.f;
-            if (col0 + q + 1 >= n_items) g1 = 0.f;
-            if (FUSED) zacc += g0 + g1;
-            pk[q >> 1] = pack_bf16(g0, g1);
+            for (int q = 0; q < CW; q += 2) {
+              const float g0_ = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(sv[q + 0], kLog2e, crow), q + 0);
+              const float g1_ = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(sv[q + 1], kLog2e, crow), q + 1);
+              if (FUSED) {
+                z0 += g0_;
+                z1 += g1_;
+              }
+              pk[q >> 1] = pack_bf16(g0_, g1_);
+            }
+            if (FUSED) zacc += z0 + z1;
+          } else {  // ragged last tile of the catalog: columns beyond it do not exist
+#pragma unroll
+            for (int q = 0; q < CW; q += 2) {
+              float g0_ = ex2f(fmaf(sv[q + 0], kLog2e, crow));
+              float g1_ = ex2f(fmaf(sv[q + 1], kLog2e, crow));
+              if (col0 + q >= n_items) g0_ = 0.f;
+              if (col0 + q + 1 >= n_items) g1_ = 0.f;
+              if (FUSED) zacc += g0_ + g1_;
+              pk[q >> 1] = pack_bf16(g0_, g1_);
+            }
           }
         }
-      }
 #if RP_CE_ABLATE == 1  // diagnostic build: keep the TMEM traffic, drop the exponentials (G = bf16(S))
 #pragma unroll
-      for (int q = 0; q < kW; q += 2) pk[q >> 1] = pack_bf16(__uint_as_float(raw[q]), __uint_as_float(raw[q + 1]));
+        for (int q = 0; q < CW; q += 2) pk[q >> 1] = pack_bf16(__uint_as_float(raw[q]), __uint_as_float(raw[q + 1]));
 #endif
-      // in place over this warp's own (already consumed) S columns: kW fp32 columns -> kW/2 packed columns
+#if RP_CE_ABLATE == 3   // diagnostic: exponentials without the TMEM store of G
+        if (pk[0] == 0x12345678u && pk[CW / 2 - 1] == 0x9abcdef0u) tmem_st8(sbase + k * (CW / 2), pk);
+#else
+        tmem_st8(sbase + k * (CW / 2), pk);
+#endif
+      };
+#if RP_CE_ABLATE == 4   // diagnostic: no TMEM loads (the exponentials run on whatever the registers hold)
+#define tmem_ld16(a, r) asm volatile("" : "+r"(r[0]), "+r"(r[5]), "+r"(r[10]), "+r"(r[15]))
+#endif
+      if (!PREFETCH || j == grp) tmem_ld16(sbase, rawA);
 #pragma unroll
-      for (int c = 0; c < kW / 2; c += 16) tmem_st16(sbase + c, *reinterpret_cast<uint32_t(*)[16]>(&pk[c]));
+      for (int k = 0; k < NCH; k += 2) {
+        tmem_ld_wait();                                   // chunk k has landed in rawA
+        tmem_ld16(sbase + (k + 1) * CW, rawB);            // chunk k+1 is on its way while chunk k is exponentiated
+        chunk(rawA, k);
+        tmem_ld_wait();                                   // chunk k+1 has landed in rawB
+        if (k + 2 < NCH) {
+          tmem_ld16(sbase + (k + 2) * CW, rawA);
+        } else if (PREFETCH && j + GROUPS < n_ct) {       // S of the set's next tile was issued long ago: normally complete
+          s_wait(j + GROUPS);
+          tmem_ld16(s_addr(j + GROUPS), rawA);
+        }
+        chunk(rawB, k + 1);
+      }
+#if RP_CE_ABLATE == 4
+#undef tmem_ld16
+#endif
+      if (threadIdx.x == 64) RP_CTR(2, g0 + j);   // exponentials done, stores issued
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_pfull[b]);
+      if (threadIdx.x == 64) RP_CTR(3, g0 + j);   // G handed to the MMA thread
+      if (lane == 0) RP_CTR(8 + (ew & 7), g0 + j);
     }
     // ---- final: accumulator -> global; this warp owns accumulator columns [cg*D/CG, (cg+1)*D/CG), 16 at a time
-    mbar_wait(&bar_acc, 0);
+    mbar_wait(&bar_acc, nseg & 1);
     tc_fence_after();
     const int r = r0 + row;
     constexpr int DW = D / kSlots;
@@ -606,8 +820,9 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           float tot = 0.f;
 #pragma unroll
           for (int k = 0; k < kSlots; ++k) tot += s_gsum[k][row];
-          d_bias[r] = tot * rs;
+          if (partial) atomicAdd(d_bias + r, tot * rs); else d_bias[r] = tot * rs;
         }
+        if (PERSIST) asm volatile("bar.sync 1, %0;" ::"r"(kEW * 32) : "memory");  // s_gsum is rewritten by the next segment
       }
 #pragma unroll 1
       for (int c = 0; c < DW; c += 16) {
@@ -617,11 +832,17 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (r < n_items) {
           float4* dst = reinterpret_cast<float4*>(o + (size_t)r * D + slot * DW + c);
 #pragma unroll
-          for (int q = 0; q < 16; q += 4)
-            dst[q >> 2] = make_float4(__uint_as_float(a16[q]) * rs, __uint_as_float(a16[q + 1]) * rs,
-                                      __uint_as_float(a16[q + 2]) * rs, __uint_as_float(a16[q + 3]) * rs);
+          for (int q = 0; q < 16; q += 4) {
+            const float4 v = make_float4(__uint_as_float(a16[q]) * rs, __uint_as_float(a16[q + 1]) * rs,
+                                         __uint_as_float(a16[q + 2]) * rs, __uint_as_float(a16[q + 3]) * rs);
+            // a slice of the row tile's columns: 16-byte vector reduction into the zeroed output (at most two CTAs share a
+            // row tile while a CTA's slice is longer than one row tile's column range, so the sum does not depend on order)
+            if (partial) atomicAdd(dst + (q >> 2), v); else dst[q >> 2] = v;
+          }
         }
       }
+      // the accumulator / row-tile columns are handed back to the MMA thread by the next segment's bar_a arrivals
+      tc_fence_before();
     } else if (FUSED && direct.d_hc != nullptr) {
       // ---- no column splits: finish here.  z_t = sum of the four slots' row sums; dH = acc / (z T_v) - E[y] / T_v
       s_gsum[slot][row] = zacc;
@@ -723,6 +944,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
       }
     }
+    }  // segments
   }
   tc_fence_before();
   __syncthreads();
@@ -993,6 +1215,14 @@ static CeWs ce_ws(void* workspace, int cap, int d) {
   return r;
 }
 
+#ifdef RP_CE_TRACE
+RP_API int rp_debug_ce_trace(unsigned long long* host_out, int n_words) {
+  RP_CUDA_CHECK(cudaDeviceSynchronize());
+  RP_CUDA_CHECK(cudaMemcpyFromSymbol(host_out, rp::g_ce_trace, sizeof(unsigned long long) * (size_t)n_words));
+  return RP_OK;
+}
+#endif
+
 RP_API size_t rp_ce_head_workspace(int capacity_tokens, int n_items, int d) {
   if (capacity_tokens <= 0 || n_items <= 0 || d <= 0) return 0;
   return ce_ws_bytes(capacity_tokens, n_items, d);
@@ -1015,11 +1245,12 @@ constexpr int ce_groups_of(int kch, int nbuf) { return (RP_CE_GROUPS == 2 && kch
 static int ce_z_slots(int d) {
   constexpr bool a_tmem = (RP_CE_A_TMEM != 0) && (RP_CE_ORDER == 1);
   const int nbuf = (d <= 128 && a_tmem) ? 2 : ((RP_CE_NBUF3 && d <= 128) ? 3 : 2);
+  if (d <= 128 && a_tmem && RP_CE_TN64 != 0) return RP_CE_TN64_GROUPS == 2 ? 2 : kBwdCG;
   return kBwdCG * ce_groups_of(d / 64, nbuf);
 }
 
 template <int KCH, int NSTAGE, int MODE>
-static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const void* a_rows, const float* cvec,
+static int launch_ce_bwd(const CUtensorMap& tmA, const void* b_mat, int b_rows, const void* a_rows, const float* cvec,
                          const int32_t* labels,
                          const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, const float* bias,
                          float* d_bias, void* out, int grid, const int32_t* safe_flag, int run_if_safe, int n_splits,
@@ -1029,15 +1260,34 @@ static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const v
   // RP_CE_ORDER 1: both directions keep the row tile in TMEM (two S buffers suffice once the issue order no longer drains the
   // pipe); otherwise round 1's choice (measured then: the TMEM row tile paid for the dE pass only, because it forces 2 buffers)
   constexpr bool A_TMEM = (RP_CE_A_TMEM != 0) && KCH <= 2 && (MODE == 1 || RP_CE_ORDER == 1);
-  constexpr int NBUF = A_TMEM ? 2 : ((RP_CE_NBUF3 && KCH <= 2) ? 3 : 2);
-  constexpr bool INORDER = (RP_CE_ORDER == 1) && NBUF == 2;
-  const int smem = ((A_TMEM ? 0 : 1) + NSTAGE + (A_TMEM ? 1 : 0)) * KCH * kChunk + 1024;
+  // column tiles: 64 wide in four S buffers when the row tile is in TMEM and the issue order is the in-order one (see the
+  // kernel's header comment), else 128 wide in two (three without the TMEM row tile)
+  constexpr int TN = (A_TMEM && RP_CE_ORDER == 1 && RP_CE_TN64 != 0) ? 64 : 128;
+  constexpr int NBUF = TN == 64 ? 4 : (A_TMEM ? 2 : ((RP_CE_NBUF3 && KCH <= 2) ? 3 : 2));
+  constexpr bool INORDER = (RP_CE_ORDER == 1) && (NBUF == 2 || TN == 64);
+  constexpr int NST = (NSTAGE + (A_TMEM ? 1 : 0)) * (128 / TN);   // the same bytes of column tiles in flight
+  const int smem = (A_TMEM ? 0 : 1) * KCH * kChunk + NST * KCH * TN * 128 + 1024;
+  CUtensorMap tmB;   // column-side matrix, one [TN rows x 64 columns] box per chunk
+  {
+    const int rc = make_tmap_bf16(&tmB, b_mat, b_rows, KCH * 64, KCH * 64, TN);
+    if (rc != RP_OK) return rc;
+  }
   // the biased head (BERT4Rec) is a separate instantiation: its per-column adds / row sums cost an instruction per logit
-  constexpr int GROUPS = ce_groups_of(KCH, NBUF);
-  auto kern = bias ? ce_bwd_kernel<KCH, NSTAGE + (A_TMEM ? 1 : 0), MODE, NBUF, A_TMEM, INORDER, true, GROUPS>
-                   : ce_bwd_kernel<KCH, NSTAGE + (A_TMEM ? 1 : 0), MODE, NBUF, A_TMEM, INORDER, false, GROUPS>;
+  constexpr int GROUPS = TN == 64 ? RP_CE_TN64_GROUPS : ce_groups_of(KCH, NBUF);
+  constexpr int CG = (TN == 64 && GROUPS == 2) ? 1 : kBwdCG;
+  // dE pass with the row tile in TMEM: persistent work slices (see CeSeg) - `grid` row tiles become one CTA per SM, the
+  // output is zeroed first because slices that end inside a row tile add their part with reductions
+  constexpr bool PERSIST = (MODE == 1) && A_TMEM && (RP_CE_PERSIST != 0);
+  constexpr int NI = (INORDER && RP_CE_ISSUERS > 1) ? RP_CE_ISSUERS : 1;
+  auto kern = bias ? ce_bwd_kernel<KCH, NST, MODE, NBUF, A_TMEM, INORDER, true, GROUPS, PERSIST, TN, CG, NI>
+                   : ce_bwd_kernel<KCH, NST, MODE, NBUF, A_TMEM, INORDER, false, GROUPS, PERSIST, TN, CG, NI>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, 64 + GROUPS * kBwdEpiWarps * 32, smem, stream>>>(tmA, tmB, reinterpret_cast<const __nv_bfloat16*>(a_rows), cvec, labels,
+  if (PERSIST) {
+    RP_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)n_items * KCH * 64 * sizeof(float), stream));
+    if (d_bias) RP_CUDA_CHECK(cudaMemsetAsync(d_bias, 0, (size_t)n_items * sizeof(float), stream));
+    if (grid > sm_count()) grid = sm_count();
+  }
+  kern<<<grid, 64 + GROUPS * 4 * CG * 32 + (NI - 1) * 32, smem, stream>>>(tmA, tmB, reinterpret_cast<const __nv_bfloat16*>(a_rows), cvec, labels,
                                             reinterpret_cast<const __nv_bfloat16*>(table), loss_inv,
                                          n_valid, n_items, bias, d_bias, out, safe_flag, run_if_safe, n_splits, capacity, zpart, direct);
   RP_LAUNCH_CHECK();
@@ -1045,20 +1295,20 @@ static int launch_ce_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const v
 }
 
 template <int MODE>
-static int dispatch_ce_bwd(int d, const CUtensorMap& tmA, const CUtensorMap& tmB, const void* a_rows, const float* cvec,
+static int dispatch_ce_bwd(int d, const CUtensorMap& tmA, const void* b_mat, int b_rows, const void* a_rows, const float* cvec,
                            const int32_t* labels,
                            const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, const float* bias,
                            float* d_bias, void* out, int grid, const int32_t* safe_flag, int run_if_safe, int n_splits,
                            int capacity, float* zpart, cudaStream_t stream, const CeDirect& direct = CeDirect{nullptr, nullptr, nullptr, nullptr}) {
   switch (d) {
     case 64:
-      return launch_ce_bwd<1, 6, MODE>(tmA, tmB, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
+      return launch_ce_bwd<1, 6, MODE>(tmA, b_mat, b_rows, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
                                        safe_flag, run_if_safe, n_splits, capacity, zpart, stream, direct);
     case 128:
-      return launch_ce_bwd<2, RP_CE_NSTAGE_D128, MODE>(tmA, tmB, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
+      return launch_ce_bwd<2, RP_CE_NSTAGE_D128, MODE>(tmA, b_mat, b_rows, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
                                        safe_flag, run_if_safe, n_splits, capacity, zpart, stream, direct);
     case 256:
-      return launch_ce_bwd<4, 2, MODE>(tmA, tmB, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
+      return launch_ce_bwd<4, 2, MODE>(tmA, b_mat, b_rows, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
                                        safe_flag, run_if_safe, n_splits, capacity, zpart, stream, direct);
     default:
       return RP_ESHAPE;
@@ -1108,7 +1358,7 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, 
       direct.cvec = cvec;
       direct.row_loss = ws.zpart;  // the row-sum partials are not needed in this mode: reuse their buffer
     }
-    rc = dispatch_ce_bwd<2>(d, tmA, tmB, hc, cvec, labels, table, loss_out + 1, n_valid, n_items, bias, nullptr, ws.part_dh,
+    rc = dispatch_ce_bwd<2>(d, tmA, table, n_items, hc, cvec, labels, table, loss_out + 1, n_valid, n_items, bias, nullptr, ws.part_dh,
                             n_tok_tiles * P, ws.flag, 1, P, capacity, ws.zpart, stream, direct);
     if (rc != RP_OK) return rc;
     if (P == 1) {
@@ -1222,10 +1472,10 @@ RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, 
   const float* loss_inv = loss_out + 1;
   const int32_t* flag = fused ? ce_ws(workspace, capacity, d).flag : nullptr;
   // token-major pass: only when the forward did not already produce d_hc
-  rc = dispatch_ce_bwd<0>(d, tmH, tmE, hc, cvec, labels, table, loss_inv, n_valid, n_items, bias, nullptr, d_hc, n_tok_tiles, flag, 0,
+  rc = dispatch_ce_bwd<0>(d, tmH, table, n_items, hc, cvec, labels, table, loss_inv, n_valid, n_items, bias, nullptr, d_hc, n_tok_tiles, flag, 0,
                           1, capacity, nullptr, stream);
   if (rc != RP_OK) return rc;
-  rc = dispatch_ce_bwd<1>(d, tmE, tmH, table, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, d_table, n_item_tiles,
+  rc = dispatch_ce_bwd<1>(d, tmE, hc, capacity, table, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, d_table, n_item_tiles,
                           nullptr, 0, 1, capacity, nullptr, stream);
   if (rc != RP_OK) return rc;
   ce_label_scatter_kernel<<<sm_count() * 4, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hc), labels, loss_inv,

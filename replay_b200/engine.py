@@ -173,7 +173,12 @@ class SasRecEngine:
         """Flat gradient, Adam moments, learning rate and step counter: sized by the configuration only, allocated once."""
         f32 = dict(device=self.dev, dtype=torch.float32)
         n = self.n_flat
-        self.g32 = torch.zeros(n, **f32)
+        # data-parallel runs on one NVLink node: the gradient lives in a symmetric (peer-mapped) allocation so that the
+        # all-reduce is this repo's own in-graph kernel (replay_b200/peer.py); otherwise a plain buffer (ncclAllReduce)
+        from .peer import alloc_peer_grad
+
+        self.peer = alloc_peer_grad(n, self.dev)
+        self.g32 = self.peer.g32 if self.peer is not None else torch.zeros(n, **f32)
         self.adam_m = torch.zeros(n, **f32)
         self.adam_v = torch.zeros(n, **f32)
         self.grads = {k: self.g32[o:o + math.prod(s)].view(s) for k, (o, s) in self.layout.items()}

@@ -5,6 +5,8 @@ every rank runs forward/backward on its own shard of the batch, the flat fp32 gr
 one ``ncclAllReduce`` and Adam applies it scaled by 1/world_size on every rank."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -12,10 +14,18 @@ from .engine import SasRecEngine
 
 
 class Trainer:
-    def __init__(self, engine: SasRecEngine, use_graph: bool = True, betas=(0.9, 0.98)):
+    def __init__(self, engine: SasRecEngine, use_graph: bool = True, betas=(0.9, 0.98), one_graph: bool | None = None):
         self.engine = engine
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.use_graph = use_graph
+        # RP_DDP_ONE_GRAPH=1 (experimental, off): capture ncclAllReduce inside the step graph.  With torch 2.11 / NCCL 2.28 on
+        # the B200 boxes the capture hangs (also in "thread_local" capture-error mode, measured r2 on 2 GPUs), so the NCCL
+        # fallback keeps round 1's scheme: graph (forward + backward), eager all-reduce, graph (Adam).
+        self.one_graph = (os.environ.get("RP_DDP_ONE_GRAPH", "0") != "0") if one_graph is None else one_graph
+        if self.world > 1 and dist.get_backend() != "nccl":
+            self.one_graph = False   # gloo stages CUDA tensors through the host: not capturable
+        # the engine's gradient sits in a symmetric allocation: the exchange is rp_peer_allreduce, a kernel of the step graph
+        self.peer = getattr(engine, "peer", None) if self.world > 1 else None
         self.betas = tuple(betas)
         self.launches_per_step = None
         self.invalidate()
@@ -28,7 +38,10 @@ class Trainer:
 
     # gradient exchange: one flat fp32 bucket (the CE backward finishes the big item-table gradient first)
     def _all_reduce(self):
-        if self.world > 1:
+        if self.peer is not None:
+            self.peer.all_reduce(self.engine._stream())
+            self.engine.lib.count += 1
+        elif self.world > 1:
             dist.all_reduce(self.engine.g32, op=dist.ReduceOp.SUM)
         return 1.0 / self.world
 
@@ -67,15 +80,28 @@ class Trainer:
                 return e.ce.loss
             torch.cuda.synchronize()
             self._g_fb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._g_fb):
-                self._fwd_bwd()
-            self._g_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._g_opt):
-                self._opt(1.0 / self.world)
+            if self.peer is not None:   # forward / backward, the peer all-reduce kernel and Adam: one graph, one launch
+                with torch.cuda.graph(self._g_fb):
+                    self._fwd_bwd()
+                    self._opt(self._all_reduce())
+                self._g_opt = None
+            elif self.world > 1 and self.one_graph:
+                with torch.cuda.graph(self._g_fb, capture_error_mode="thread_local"):
+                    self._fwd_bwd()
+                    dist.all_reduce(e.g32, op=dist.ReduceOp.SUM)
+                    self._opt(1.0 / self.world)
+                self._g_opt = None
+            else:
+                with torch.cuda.graph(self._g_fb):
+                    self._fwd_bwd()
+                self._g_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._g_opt):
+                    self._opt(1.0 / self.world)
             # capture does not execute: run the captured work once so this call is a real step
         self._g_fb.replay()
-        self._all_reduce()
-        self._g_opt.replay()
+        if self._g_opt is not None:
+            self._all_reduce()
+            self._g_opt.replay()
         return e.ce.loss
 
 

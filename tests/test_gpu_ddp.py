@@ -77,7 +77,7 @@ def test_lightning_training_step_two_ranks_keeps_replicas_identical():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, backend, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=600) for _ in range(2))
+    res = dict(q.get(timeout=180) for _ in range(2))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -89,3 +89,67 @@ def test_lightning_training_step_two_ranks_keeps_replicas_identical():
     assert np.array_equal(a["legacy"], b["legacy"]), "legacy SasRec module: replicas diverged"
     assert not np.array_equal(a["local_only"], b["local_only"])  # different data per rank really gives different local updates
     assert not np.array_equal(a["new"], a["local_only"])
+
+
+def _peer_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        from replay_b200.peer import alloc_peer_grad
+
+        out = {"available": False}
+        for n in (1 << 20, 6_502_147, 1000):   # a round size, the config-2 flat gradient's order of magnitude (odd), a tiny one
+            peer = alloc_peer_grad(n, dev)
+            if peer is None:
+                break
+            out["available"] = True
+            st = torch.cuda.current_stream(dev).cuda_stream
+            worst = 0.0
+            for it in range(4):   # repeated launches: the flags carry a launch counter, nothing is reset in between
+                g = torch.Generator(device=dev).manual_seed(100 * rank + it)
+                x = torch.randn(n, device=dev, generator=g)
+                ref = x.clone()
+                dist.all_reduce(ref)
+                peer.g32.copy_(x)
+                peer.all_reduce(st)
+                torch.cuda.synchronize()
+                worst = max(worst, float((peer.g32 - ref).abs().max()))
+                gathered = [torch.empty_like(peer.g32) for _ in range(world)]
+                dist.all_gather(gathered, peer.g32.contiguous())
+                assert all(torch.equal(gathered[0], t) for t in gathered), "replicas differ bitwise"
+            out[f"err_{n}"] = worst
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_allreduce_matches_nccl_and_is_bit_identical_across_ranks():
+    """rp_peer_allreduce (the in-graph NVLink exchange of the training step) against ncclAllReduce on random data, several
+    launches in a row; every rank must end up with bit-identical buffers.  Needs two GPUs with peer access."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    if not res[0]["available"]:
+        pytest.skip("symmetric memory refused on this box: the trainer uses ncclAllReduce")
+    for r in res.values():
+        for k, v in r.items():
+            if k.startswith("err_"):
+                assert v < 1e-5, (k, v)   # two-rank sums: the same two addends, at most an ordering difference

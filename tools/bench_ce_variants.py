@@ -34,4 +34,5 @@ for path in sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file
     r["dh_abs_sum"] = float(d_hc[:nv_].float().abs().sum()); r["de_abs_sum"] = float(d_tab[:I].abs().sum())
     r["dh_probe"] = float(d_hc[nv_ // 2].float().sum()); r["de_probe"] = float(d_tab[I // 3].sum())
     res[os.path.basename(path)] = r
+    print(os.path.basename(path), json.dumps(r), file=sys.stderr, flush=True)   # progress: a variant that hangs is the next one
 print(json.dumps(res, indent=1))

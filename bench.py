@@ -292,8 +292,18 @@ def run_ours(args):
     tr = Trainer(eng, use_graph=not args.no_graph)
     n_batches = 6
     data = make_batches(c, B * n_batches * world, seed=1234)
-    sh = slice(rank * B * n_batches, (rank + 1) * B * n_batches)
-    host = [t[sh].reshape(n_batches, B, L).pin_memory() for t in data]
+    if world > 1 and not args.no_balance:
+        # global batch j = windows [j * world * B, (j + 1) * world * B) of the pool, dealt to the ranks by their number of valid
+        # targets (replay_b200.data.balanced_rank_shards): the gradient exchange is a barrier, so every step runs at the pace
+        # of the rank with the most targets - 3.7 % above the mean with index sharding at 8 ranks
+        from replay_b200.data import balanced_rank_shards
+
+        work = (data[3] if c["kind"] == "sasrec" else (data[1] & ~data[2])).reshape(n_batches, world * B, L).sum(-1)
+        pick = torch.stack([balanced_rank_shards(work[j], world)[rank] + j * world * B for j in range(n_batches)])  # [n_batches, B]
+        host = [t[pick.reshape(-1)].reshape(n_batches, B, L).pin_memory() for t in data]
+    else:
+        sh = slice(rank * B * n_batches, (rank + 1) * B * n_batches)
+        host = [t[sh].reshape(n_batches, B, L).pin_memory() for t in data]
     devb = [t.to(dev) for t in host]
     valid_per_seq = valid_targets(c, data)
     eng.n_valid_hint = int(valid_per_seq * B)  # the data loader knows how many targets a batch holds (load balance only)
@@ -336,6 +346,16 @@ def run_ours(args):
     ms, loss = timed(step_dev, K)
     clocks = sampler.stop() if rank == 0 else None
     final_loss = float(loss[0].item())
+    # ---- (N > 1) the gradient exchange alone: 20 back-to-back calls on the staged gradient, ranks in lock step
+    exchange = None
+    if world > 1:
+        def xchg(_i):
+            tr._all_reduce()
+        xchg(0)
+        ms_x, _ = timed(xchg, 20)
+        exchange = {"kind": "rp_peer_allreduce (in-graph NVLink kernel)" if tr.peer is not None else "ncclAllReduce (eager, between two graphs)",
+                    "ms": ms_x / 20, "bytes": int(eng.g32.numel() * 4), "balanced_batches": not args.no_balance}
+        eng.g32.zero_()
     # ---- sustained: the same step for >= 2 s (power / thermal steady state), clocks sampled over the whole window
     sustained = None
     if not args.no_sustained:
@@ -457,7 +477,7 @@ def run_ours(args):
                 "path": ("LightningModule(SasRec).training_step" if c["kind"] == "sasrec" else "Bert4Rec.training_step")
                         + " on pinned host batches (fused step: CUDA-graph replays + NCCL all-reduce inside the module)"},
         "e2e_device_batches": dev_batches,
-        "sustained": sustained,
+        "sustained": sustained, "gradient_exchange": exchange,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roof,
@@ -620,6 +640,7 @@ def main():
     ap.add_argument("--no-scoring", action="store_true")
     ap.add_argument("--quick-scoring", action="store_true", help="scoring leg on 65 536 users at 4096 users per call only")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained window")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: shard the global batch by index instead of dealing it by valid-target count")
     ap.add_argument("--no-device-batches", action="store_true", help="skip the device-side batch construction leg")
     ap.add_argument("--batch", type=int, default=None, help="sequences per GPU and step (SURVEY 8d sweeps {128, 256, 512} at config 2)")
     ap.add_argument("--dropout", type=float, default=None, help="diagnostic override of the workload's dropout; "

@@ -45,6 +45,24 @@ __device__ __forceinline__ float ld_sys_f1(const float* p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *f has reached `epoch`; gives up after ~20 s (a peer process died: better a wrong gradient and a clean exit of
+// this kernel than a GPU that spins until the box is reclaimed) and reports it through the state block
+__device__ __forceinline__ void wait_flag(const uint32_t* f, uint32_t epoch, uint32_t* timed_out) {
+  const unsigned long long t0 = global_ns();
+  uint32_t polls = 0;
+  while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+    if ((++polls & 0xfffu) == 0 && global_ns() - t0 > 20000000000ull) {
+      *timed_out = 1u;
+      return;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(512, 1)
 peer_allreduce_kernel(const PeerArgs a, int rank, int world, long long n, uint32_t* __restrict__ epoch_dev,
                       uint32_t* __restrict__ done_ctas) {
@@ -55,9 +73,7 @@ peer_allreduce_kernel(const PeerArgs a, int rank, int world, long long n, uint32
     st_release_sys(a.flags[threadIdx.x] + 0 * kMaxPeers + rank, epoch);
   }
   if ((int)threadIdx.x < world) {
-    const uint32_t* f = a.flags[rank] + 0 * kMaxPeers + threadIdx.x;
-    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-    }
+    wait_flag(a.flags[rank] + 0 * kMaxPeers + threadIdx.x, epoch, done_ctas + 1);
   }
   __syncthreads();
   // ---- this rank's slice [lo, hi), multiples of 4 floats (the last slice takes the tail)
@@ -109,9 +125,7 @@ peer_allreduce_kernel(const PeerArgs a, int rank, int world, long long n, uint32
   if ((int)threadIdx.x < world) {
     __threadfence_system();
     st_release_sys(a.flags[threadIdx.x] + 1 * kMaxPeers + rank, epoch);
-    const uint32_t* f = a.flags[rank] + 1 * kMaxPeers + threadIdx.x;
-    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-    }
+    wait_flag(a.flags[rank] + 1 * kMaxPeers + threadIdx.x, epoch, done_ctas + 1);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -125,8 +139,8 @@ peer_allreduce_kernel(const PeerArgs a, int rank, int world, long long n, uint32
 
 using namespace rp;
 
-// flags / counters of one rank: uint32 [2 * 8] flags + epoch + done counter, zeroed once by the caller (rp_peer_allreduce_state_bytes)
-RP_API size_t rp_peer_allreduce_state_bytes(void) { return (2 * kMaxPeers + 2) * sizeof(uint32_t); }
+// flags / counters of one rank: uint32 [2 * 8] flags + epoch + done counter + timed-out marker (non-zero: a peer never answered), zeroed once by the caller (rp_peer_allreduce_state_bytes)
+RP_API size_t rp_peer_allreduce_state_bytes(void) { return (2 * kMaxPeers + 3) * sizeof(uint32_t); }
 
 // bufs[w] / states[w]: device pointers of rank w's gradient buffer / state block as mapped into THIS process (symmetric
 // memory), w = 0..world-1; n fp32 elements, 16-byte aligned buffers.  Every rank must launch it once per step.

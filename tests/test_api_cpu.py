@@ -415,3 +415,22 @@ def test_prediction_side_callbacks_without_an_engine():
     ref = RankingMetrics(("recall", "ndcg", "map"), (1, 2))
     ref.add_prediction(torch.topk(logits, 2, dim=1).indices, gt)
     assert res == ref.get_metrics() and abs(res["recall@1"] - 0.5) < 1e-6
+
+
+def test_balanced_rank_shards_deals_equal_counts_and_near_equal_work():
+    """replay_b200.data.balanced_rank_shards: a partition, equal sample counts, per-rank work within one sample of the mean."""
+    import torch
+
+    from replay_b200.data import balanced_rank_shards
+
+    g = torch.Generator().manual_seed(0)
+    work = torch.randint(1, 200, (4096,), generator=g)
+    sh = balanced_rank_shards(work, 8)
+    assert sh.shape == (8, 512)
+    assert torch.equal(torch.sort(sh.reshape(-1)).values, torch.arange(4096))
+    tot = work[sh].sum(1).float()
+    assert float(tot.max() - tot.min()) <= 200
+    import pytest
+
+    with pytest.raises(ValueError):
+        balanced_rank_shards(work[:4095], 8)

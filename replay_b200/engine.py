@@ -11,6 +11,7 @@ the reference API delegate to it.  torch supplies device memory, streams, CUDA g
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import math
 import os
@@ -329,6 +330,7 @@ class SasRecEngine:
     # ------------------------------------------------------------------------------------------------ workspace
     def _alloc_workspace(self):
         cfg, T, d, dev = self.cfg, self.T, self.cfg.dp, self.dev
+        self._alloc_B, self._alloc_T, self._sub_last_idx = self.B, self.T, {}
         bf = dict(device=dev, dtype=torch.bfloat16)
         f32 = dict(device=dev, dtype=torch.float32)
         i32 = dict(device=dev, dtype=torch.int32)
@@ -378,6 +380,25 @@ class SasRecEngine:
 
     def _stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
+
+    @contextlib.contextmanager
+    def sub_geometry(self, batch: int, seq_len: int):
+        """Inference only: run a SMALLER [batch, seq_len] problem inside the allocated workspace (every activation buffer is a
+        flat [T, ...] array, so a problem with batch * seq_len <= T rows uses a prefix of each).  Used by the length-bucketed
+        predict (core.py): users whose whole history fits the last ``seq_len`` positions are evaluated on that window only -
+        positions are right-aligned (``pos0 = max_len - L``), so the trimmed window sees the same position embeddings."""
+        self._check_geometry(seq_len)
+        if batch > self._alloc_B or batch * seq_len > self._alloc_T:
+            raise ValueError(f"sub-geometry ({batch}, {seq_len}) exceeds the workspace ({self._alloc_B} x {self._alloc_T // self._alloc_B})")
+        saved = (self.B, self.L, self.T, self.Lp, self.last_idx)
+        key = (batch, seq_len)
+        if key not in self._sub_last_idx:
+            self._sub_last_idx[key] = (torch.arange(batch, device=self.dev, dtype=torch.int32) * seq_len + (seq_len - 1)).contiguous()
+        self.B, self.L, self.T, self.Lp, self.last_idx = batch, seq_len, batch * seq_len, _ru(seq_len, 64), self._sub_last_idx[key]
+        try:
+            yield self
+        finally:
+            self.B, self.L, self.T, self.Lp, self.last_idx = saved
 
     # ------------------------------------------------------------------------------------------------ kernel helpers
     def _gemm(self, A, B, C, M, N, K, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, rowmask=None,

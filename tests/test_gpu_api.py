@@ -326,3 +326,47 @@ def test_lightning_module_checkpoint_optimizer_and_lazy_predict(golden_dir, cuda
     assert items50.shape == (ids.shape[0], 50)
     torch.testing.assert_close(scores50[:, :10], scores10, rtol=1e-3, atol=1e-3)
     assert (items50[:, :10] == items10).float().mean() > 0.98
+
+
+def test_length_bucketed_predict_matches_full_window_predict(cuda):
+    """core._last_hidden evaluates users whose history fits the last 64 / 128 positions on that window only (left-padded
+    windows, right-aligned positions, pad keys masked): query embeddings and top-K must agree with the full-window pass and
+    with the fp32 oracle; a batch that is NOT left-padded must take the full-window path."""
+    from oracle import sasrec as osr
+    from replay_b200.nn.sequential import SasRec
+    from replay_b200.schema import TensorFeatureInfo, TensorSchema
+    from replay_b200.synthetic import make_sequences
+
+    n_items, L, B = 3000, 200, 768
+    schema = TensorSchema(TensorFeatureInfo("item_id", n_items, n_items, 64))
+    model = SasRec.from_params(schema, embedding_dim=64, num_heads=1, num_blocks=2, max_sequence_length=L, dropout=0.0,
+                               device=cuda, seed=3)
+    core = model.core
+    ids, pm, _, _ = make_sequences(B, n_items, L, seed=11)
+    ids, pm = ids.to(cuda), pm.to(cuda)
+    n_real = pm.sum(1)
+    assert int((n_real <= 64).sum()) > 50 and int((n_real > 128).sum()) > 50   # all three buckets are populated
+    core.predict_bucket_min_users, core.predict_bucket_min_batch = 8, 16
+    core.predict_buckets = (64, 128)
+    hq_b = core.query_embeddings(ids, pm).float()
+    top_b, sc_b = core.predict_topk(ids, pm, 10, seen_ids=ids)
+    core.predict_buckets = ()
+    hq_f = core.query_embeddings(ids, pm).float()
+    top_f, sc_f = core.predict_topk(ids, pm, 10, seen_ids=ids)
+    assert torch.allclose(hq_b, hq_f, atol=6e-2, rtol=0)
+    assert float((hq_b - hq_f).abs().mean()) < 4e-3
+    same = (top_b == top_f).float().mean().item()
+    assert same > 0.97, same                                   # bf16 round-off may swap near-ties, nothing else
+    assert torch.allclose(sc_b, sc_f, atol=0.15, rtol=0)
+    # fp32 oracle on the shortest users, evaluated on their full windows
+    Pc = core.engine.export_canonical()
+    P = {k: ([{kk: vv.float().cpu() for kk, vv in b.items()} for b in v] if k == "blocks" else v.float().cpu()) for k, v in Pc.items()}
+    short = torch.nonzero(n_real <= 64).flatten()[:32].cpu()
+    h = osr.sasrec_body(P, ids.cpu()[short], pm.cpu()[short], 1, variant="new")[:, -1]
+    assert torch.allclose(hq_b.cpu()[short], h, atol=6e-2, rtol=0)
+    # right-padded batch: the bucketed path must refuse (falls back to the full window, i.e. the same numbers as before)
+    core.predict_buckets = (64, 128)
+    ids_r, pm_r = torch.flip(ids, dims=[1]), torch.flip(pm, dims=[1])
+    hq_r = core.query_embeddings(ids_r, pm_r).float()
+    core.predict_buckets = ()
+    assert torch.equal(hq_r, core.query_embeddings(ids_r, pm_r).float())

@@ -92,6 +92,17 @@ int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, const i
  * the softmax numerators of a token chunk are materialised in bf16 inside the workspace (chunk sized by RP_CE_WIDE_G_BYTES,
  * default 8 GiB) and three GEMMs per chunk produce dH and dE; the workspace is then always required.
  * n_valid_hint: host estimate of *n_valid (0 = unknown), load-balance only. */
+/* Per-row variants of the full-catalog head, single positive label per position:
+ *   row_weight  fp32 [capacity], >= 0, in the compacted order of the valid targets (NULL = 1): loss = mean_t w_t ce_t
+ *               replaces  replay/nn/loss/logout_ce.py:148-228 LogOutCEWeighted (and :10-145 LogOutCE = the plain head) ;
+ *                         replay/nn/loss/ce.py:84-143 CEWeighted
+ *   loss_kind 1 LogInCE   replay/nn/loss/login_ce.py:102-239: loss_t = -clamp(log(p_t + log_eps), -clamp, clamp) with p_t the
+ *               softmax probability of the positive over the catalog; gradient = CE gradient of the row x p / (p + eps)
+ * Same buffers and fused behaviour as rp_ce_head_fwd; rp_ce_head_bwd with the same workspace completes it. */
+int rp_ce_head_fwd_w(const void* hc, const void* table, const float* bias, const int32_t* labels, const int32_t* n_valid,
+                     int capacity, int n_items, int d, float* loss_out, float* lse, float* cvec, void* d_hc, int n_valid_hint,
+                     const float* row_weight, int loss_kind, float log_eps, float clamp, void* workspace,
+                     size_t workspace_bytes, void* stream);
 int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, const int32_t* labels, const int32_t* n_valid,
                    int capacity, int n_items, int d, const float* loss_out, const float* cvec, void* d_hc, float* d_table,
                    float* d_bias, int fused, int n_valid_hint, void* workspace, size_t workspace_bytes, void* stream);

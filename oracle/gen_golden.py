@@ -393,6 +393,49 @@ def gen_sampled_losses():
     print("wrote sampled_losses")
 
 
+def gen_row_losses():
+    """Real reference full-catalog per-row losses on the weights / batch of sasrec_new_tiny: LogOutCE, LogOutCEWeighted,
+    CEWeighted (incl. its broadcast quirk), LogInCE (default eps / clamp and a tight clamp that is active on some rows)
+    -> tests/golden/row_losses.npz (losses + gradient of the item table and of one block weight + the sample weights)."""
+    from replay.nn.loss import CEWeighted, LogInCE, LogOutCE, LogOutCEWeighted
+
+    out = {}
+    z = np.load(os.path.join(OUT, "sasrec_new_tiny.npz"))
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}
+    n_items, d, H, L, nb = int(z["n_items"]), int(z["d"]), int(z["H"]), int(z["L"]), int(z["n_blocks"])
+    ids, pm = torch.from_numpy(z["ids"]), torch.from_numpy(z["pad_mask"])
+    labels, tm = torch.from_numpy(z["labels"]), torch.from_numpy(z["target_mask"])
+    B = ids.shape[0]
+    g = torch.Generator().manual_seed(91)
+    w = torch.rand(B, L, 1, generator=g) * 1.5 + 0.25
+    out["weights"] = w.numpy()
+    cases = {"logout": lambda: LogOutCE(cardinality=n_items),
+             "logout_weighted": lambda: LogOutCEWeighted(cardinality=n_items, feature_name="w"),
+             "ce_weighted": lambda: CEWeighted(feature_name="w"),
+             "login": lambda: LogInCE(cardinality=n_items),
+             "login_clamped": lambda: LogInCE(cardinality=n_items, log_epsilon=1e-3, clamp_border=5.5)}
+    for name, mk in cases.items():
+        model = SasRec.from_params(schema(n_items, d, n_items), embedding_dim=d, num_heads=H, num_blocks=nb,
+                                   max_sequence_length=L, dropout=0.0)
+        model.load_state_dict(sd)
+        model.loss = mk()
+        model.loss.logits_callback = model.get_logits
+        model.train()
+        res = model(feature_tensors={"item_id": ids, "w": w}, padding_mask=pm, positive_labels=labels.unsqueeze(-1),
+                    negative_labels=None, target_padding_mask=tm.unsqueeze(-1).clone())
+        res["loss"].backward()
+        gr = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+        ek = [k for k in gr if "item_id" in k or "item_emb" in k]
+        wk = [k for k in gr if k.endswith("in_proj_weight")]
+        out[f"{name}_loss"] = res["loss"].detach().numpy()
+        out[f"{name}_gE"] = gr[ek[0]].numpy().copy()
+        out[f"{name}_gW"] = gr[wk[0]].numpy().copy()
+        print("row loss", name, float(res["loss"]))
+    np.savez_compressed(os.path.join(OUT, "row_losses.npz"), **out)
+    print("wrote row_losses")
+
+
+
 def gen_metrics_known():
     """TorchMetricsBuilder (replay/metrics/torch_metrics_builder.py) on a seeded case incl. novelty and coverage: pins the
     on-device mirror ``replay_b200.nn.lightning.RankingMetrics``."""
@@ -434,6 +477,9 @@ if __name__ == "__main__":
     if len(_sys.argv) > 1 and _sys.argv[1] == "defaults":
         gen_reference_default_shapes()
         raise SystemExit(0)
+    if len(_sys.argv) > 1 and _sys.argv[1] == "row_losses":
+        gen_row_losses()
+        raise SystemExit(0)
     if len(_sys.argv) > 1 and _sys.argv[1] == "metrics":
         gen_metrics_known()
         raise SystemExit(0)
@@ -446,5 +492,6 @@ if __name__ == "__main__":
     gen_seen_filter_known_answers()
     gen_dataset_layout()
     gen_sampled_losses()
+    gen_row_losses()
     gen_reference_default_shapes()
     gen_metrics_known()

@@ -102,3 +102,57 @@ def loss_and_grads(P, ids, pad_mask, labels, target_mask, negatives, n_heads, ki
             G[k] = v.grad if v.grad is not None else torch.zeros_like(v)
     G["item_emb"][-1].zero_()
     return loss.detach(), G
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# full-catalog per-row losses, one positive label per position
+#   LogOutCE          replay/nn/loss/logout_ce.py:74-145   CrossEntropyLoss over [positive | catalog with the positive masked]
+#   LogOutCEWeighted  replay/nn/loss/logout_ce.py:198-228  mean(loss_t * w_t), w masked by the target padding mask
+#   CEWeighted        replay/nn/loss/ce.py:111-143         (loss [B * L] * w [B, L, 1]).mean() - the broadcast product, i.e.
+#                                                          sum of the valid rows' CE / (B * L) * mean(w over ALL positions);
+#                                                          restated as the reference computes it
+#   LogInCE           replay/nn/loss/login_ce.py:170-239   -clamp(log(p + eps), -c, c), p = softmax prob of the positive
+# Pinned against the real classes by oracle/gen_golden.py::gen_row_losses -> tests/golden/row_losses.npz.
+# ----------------------------------------------------------------------------------------------------------------------
+def row_loss(hidden, table, labels, target_mask, kind, weights=None, log_eps=1e-6, clamp=100.0):
+    """hidden [B, L, d], table [|I|(+1), d] (rows >= |I| ignored via n_items = labels' range), labels [B, L], target_mask
+    [B, L] bool, weights [B, L, 1] or None."""
+    h = hidden[target_mask]
+    y = labels[target_mask]
+    logits = h @ table.T
+    ce = torch.nn.functional.cross_entropy(logits, y, reduction="none")
+    if kind == "logout":
+        return ce.mean()
+    if kind == "logout_weighted":
+        return (ce * weights[..., 0][target_mask]).mean()
+    if kind == "ce_weighted":
+        # CE.forward keeps all B * L positions (ignore_index, reduction="none": zeros at the ignored ones); the product with
+        # the [B, L, 1] weights broadcasts to [B, L, B * L] and its mean is mean(loss over B * L) * mean(w) - as the reference
+        full = torch.zeros(target_mask.numel(), dtype=ce.dtype)
+        full = full.masked_scatter(target_mask.reshape(-1), ce)
+        return (full * weights).mean()
+    if kind == "login":
+        p = torch.exp(-ce)
+        return (-torch.clamp(torch.log(p + log_eps), -clamp, clamp)).mean()
+    raise ValueError(kind)
+
+
+def row_loss_and_grads(P, ids, pad_mask, labels, target_mask, n_heads, kind, weights=None, **kw):
+    from .sasrec import sasrec_body
+
+    Pg = {}
+    for k, v in P.items():
+        Pg[k] = [{kk: vv.detach().clone().requires_grad_(True) for kk, vv in b.items()} for b in v] if k == "blocks" \
+            else v.detach().clone().requires_grad_(True)
+    hidden = sasrec_body(Pg, ids, pad_mask, n_heads, variant="new")
+    n_items = Pg["item_emb"].shape[0] - 1
+    loss = row_loss(hidden, Pg["item_emb"][:n_items], labels, target_mask, kind, weights, **kw)
+    loss.backward()
+    G = {}
+    for k, v in Pg.items():
+        if k == "blocks":
+            G[k] = [{kk: (vv.grad if vv.grad is not None else torch.zeros_like(vv)) for kk, vv in b.items()} for b in v]
+        else:
+            G[k] = v.grad if v.grad is not None else torch.zeros_like(v)
+    G["item_emb"][-1].zero_()
+    return loss.detach(), G

@@ -197,11 +197,23 @@ class SasRecCore(torch.nn.Module):
         self._loss_spec = (kind, kw)
         if self.engine is not None:
             self.engine._loss_applied = None  # re-applied with the negatives' shape when the next batch is staged
-            if kind == "ce":
-                self.engine.set_loss("ce")
+            if kind in self._FULL_CATALOG:
+                self.engine.set_loss(kind, **kw)
 
-    def _stage(self, eng, ids, pad_mask, labels, target_mask, negatives):
+    _FULL_CATALOG = ("ce", "ce_weighted", "login_ce")   # heads over the whole catalog (no negatives)
+
+    def _stage(self, eng, ids, pad_mask, labels, target_mask, negatives, row_weights=None):
         spec = getattr(self, "_loss_spec", ("ce", {}))
+        if spec[0] in self._FULL_CATALOG:
+            if eng.sampled is not None or getattr(eng, "_loss_applied", None) != (spec[0], tuple(sorted(spec[1].items()))):
+                eng.set_loss(spec[0], **spec[1])
+                eng._loss_applied = (spec[0], tuple(sorted(spec[1].items())))
+            eng.set_batch(ids, pad_mask, labels, target_mask)
+            if spec[0] == "ce_weighted":
+                if row_weights is None:
+                    raise ValueError("this loss needs the sample weights of the batch")
+                eng.set_row_weights(row_weights)
+            return
         if spec[0] != "ce":
             shape = {1: "shared", 2: "perseq", 3: "perpos"}[negatives.dim()]
             want = dict(spec[1], n_neg=negatives.shape[-1], neg_shape=shape)
@@ -217,14 +229,14 @@ class SasRecCore(torch.nn.Module):
             eng.set_negatives(negatives)
 
     # ---- training / inference on [B, L] batches
-    def loss(self, ids, pad_mask, labels, target_mask, negatives=None) -> torch.Tensor:
+    def loss(self, ids, pad_mask, labels, target_mask, negatives=None, row_weights=None) -> torch.Tensor:
         B, L = ids.shape
         eng = self.ensure_engine(B, L, with_grad=True)
-        self._stage(eng, ids, pad_mask, labels, target_mask, negatives)
+        self._stage(eng, ids, pad_mask, labels, target_mask, negatives, row_weights)
         return _EngineLoss.apply(self.flat, self)
 
     def fused_step(self, ids, pad_mask, labels, target_mask, all_reduce="auto", lr: float | None = None,
-                   negatives=None) -> torch.Tensor:
+                   negatives=None, row_weights=None) -> torch.Tensor:
         """forward + backward + Adam entirely inside the engine (no autograd, no torch optimizer).  ``all_reduce="auto"``
         exchanges the gradient over ``torch.distributed`` whenever a process group with more than one rank is initialised
         (Lightning ``strategy="ddp"``): this path has no autograd backward for DDP's hooks to fire on."""
@@ -235,7 +247,7 @@ class SasRecCore(torch.nn.Module):
             self._shadow_dirty = False
         self._set_lr(eng, lr)
         loss_before = getattr(eng, "_loss_applied", None), eng.sampled is None
-        self._stage(eng, ids, pad_mask, labels, target_mask, negatives)
+        self._stage(eng, ids, pad_mask, labels, target_mask, negatives, row_weights)
         if (getattr(eng, "_loss_applied", None), eng.sampled is None) != loss_before:
             self._drop_graphs()  # another loss head: different kernels / buffers
         if isinstance(all_reduce, str):  # "auto": torch.distributed when initialised (inside Trainer.run)

@@ -251,6 +251,33 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
+// Per-row variants of the full-catalog head (all single positive label per position):
+//   w_ext   sample weights of the valid targets (compacted order): loss = mean_t w_t ce_t
+//           replay/nn/loss/logout_ce.py:148-228 LogOutCEWeighted ; replay/nn/loss/ce.py:84-143 CEWeighted
+//   kind 1  LogInCE (replay/nn/loss/login_ce.py:170-239): loss_t = -clamp(log(p_t + eps), -c, c), p_t = softmax prob of
+//           the positive; its gradient is the CE gradient of the row times p / (p + eps) (0 where the clamp is active)
+// Both act as a per-row factor w_t on (softmax - onehot) / T_v: the forward's finalisation writes it to roww[t], folds it into
+// the exponent offset cvec[t] = -lse2 + log2(w_t / T_v) the gradient passes exponentiate with, and the one-hot terms read it.
+struct CeRowOpts {
+  const float* w_ext;    // [capacity] or null
+  float* roww;           // [capacity] gradient weight per row (workspace); null only for the plain head without workspace
+  int kind;              // 0 CE, 1 LogInCE
+  float log_eps, clamp;
+};
+// row loss and gradient weight from the log-sum-exp (natural log) and the target logit
+__device__ __forceinline__ void ce_row_terms(const CeRowOpts& o, int t, float lse, float zy, float& row_loss, float& wg) {
+  const float wx = o.w_ext ? o.w_ext[t] : 1.f;
+  float lt = lse - zy;
+  wg = wx;
+  if (o.kind == 1) {
+    const float pr = __expf(zy - lse);
+    const float lg = __logf(pr + o.log_eps);
+    lt = -fminf(fmaxf(lg, -o.clamp), o.clamp);
+    wg *= (lg > -o.clamp && lg < o.clamp) ? pr / (pr + o.log_eps) : 0.f;
+  }
+  row_loss = wx * lt;
+}
+
 // lse / loss / per-token exponent offsets.  One warp per token: merges the (max, sum) partials, computes the target logit
 // z_y = hc[t] . E[y_t] as a gather-dot (keeps the per-element target pick out of the MMA epilogue), accumulates the loss.
 // Deterministic: per-block partial sums, the last block adds them in index order.
@@ -260,11 +287,10 @@ __global__ void ce_finalize_kernel(const float2* __restrict__ part, const __nv_b
                                    int capacity, int d,
                                    float* __restrict__ lse_out, float* __restrict__ cvec, float* __restrict__ block_sums,
                                    unsigned int* __restrict__ ticket, float* __restrict__ loss_out,
-                                   const int32_t* __restrict__ skip_if_safe) {
+                                   const int32_t* __restrict__ skip_if_safe, const CeRowOpts row) {
   if (skip_if_safe && *skip_if_safe != 0) return;
   const int n_valid = *n_valid_ptr;
   const float inv_n = n_valid > 0 ? 1.f / (float)n_valid : 0.f;
-  const float log2_inv_n = n_valid > 0 ? -log2f((float)n_valid) : 0.f;
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   float local = 0.f;
   for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < capacity; t += gridDim.x * wpb) {
@@ -294,9 +320,12 @@ __global__ void ce_finalize_kernel(const float2* __restrict__ part, const __nv_b
       const float lse2 = M + log2f(S);  // log2 units
       const float lse = lse2 * kLn2;
       if (lane == 0) {
+        float rl, wg;
+        ce_row_terms(row, t, lse, z, rl, wg);
         lse_out[t] = lse;
-        cvec[t] = -lse2 + log2_inv_n;
-        local += lse - z;
+        cvec[t] = -lse2 + log2f(wg * inv_n);
+        if (row.roww) row.roww[t] = wg;
+        local += rl;
       }
     } else if (lane == 0) {
       cvec[t] = -INFINITY;  // rows beyond T_v contribute nothing to the backward
@@ -330,7 +359,8 @@ struct CeDirect {
   __nv_bfloat16* d_hc;   // null: column-split mode (partials + ce_fused_finalize_kernel)
   float* lse;
   float* cvec;
-  float* row_loss;       // [capacity] lse_t - z_{t, y_t}; summed in a fixed order by ce_loss_reduce_kernel
+  float* row_loss;       // [capacity] weighted row losses; summed in a fixed order by ce_loss_reduce_kernel
+  CeRowOpts row;         // (row.roww is also what MODE 0 scales its one-hot term with)
 };
 
 // loss = mean over the valid targets of row_loss, deterministic (fixed partition + tree); also publishes 1 / T_v
@@ -852,8 +882,38 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       for (int k = 0; k < kSlots; ++k) z += s_gsum[k][row];
       const bool live = r < n_valid;
       const float inv_n = n_valid > 0 ? 1.f / (float)n_valid : 0.f;
-      const float scale = live ? inv_n / z : 0.f;
       const int y = live ? labels[r] : 0;
+      float wg = (live && direct.row.w_ext) ? direct.row.w_ext[r] : 1.f;   // gradient weight of the row
+      if (direct.row.kind == 1) {
+        // LogInCE: the weight needs the target logit before the gradient can be scaled - one extra pass over h . E[y]
+        float dp = 0.f;
+        if (live) {
+          const uint4* ey = reinterpret_cast<const uint4*>(table + (size_t)y * D + slot * DW);
+          const uint4* hr = reinterpret_cast<const uint4*>(a_rows + (size_t)r * D + slot * DW);
+#pragma unroll
+          for (int q = 0; q < DW / 8; ++q) {
+            const uint4 e = __ldg(ey + q), hh = __ldg(hr + q);
+            const __nv_bfloat162* e2 = reinterpret_cast<const __nv_bfloat162*>(&e);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hh);
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+              const float2 ef = __bfloat1622float2(e2[pp]), hf = __bfloat1622float2(h2[pp]);
+              dp = fmaf(hf.x, ef.x, fmaf(hf.y, ef.y, dp));
+            }
+          }
+        }
+        s_dot[slot][row] = dp;
+        asm volatile("bar.sync 1, %0;" ::"r"(kEW * 32) : "memory");
+        float zy0 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kSlots; ++k) zy0 += s_dot[k][row];
+        if (HAS_BIAS) zy0 += bias[y];
+        asm volatile("bar.sync 1, %0;" ::"r"(kEW * 32) : "memory");   // s_dot is written again below
+        float rl_unused;
+        if (live) ce_row_terms(direct.row, r, __logf(z), zy0, rl_unused, wg);
+      }
+      const float scale = live ? wg * inv_n / z : 0.f;
+      const float lab = wg * inv_n;
       float dot = 0.f;
 #pragma unroll 1
       for (int c = 0; c < DW; c += 16) {
@@ -875,8 +935,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             for (int pp = 0; pp < 4; ++pp) {
               const float2 ef = __bfloat1622float2(e2[pp]), hf = __bfloat1622float2(h2[pp]);
               dot = fmaf(hf.x, ef.x, fmaf(hf.y, ef.y, dot));
-              w32[pp] = pack_bf16(__uint_as_float(a16[q + 2 * pp]) * scale - inv_n * ef.x,
-                                  __uint_as_float(a16[q + 2 * pp + 1]) * scale - inv_n * ef.y);
+              w32[pp] = pack_bf16(__uint_as_float(a16[q + 2 * pp]) * scale - lab * ef.x,
+                                  __uint_as_float(a16[q + 2 * pp + 1]) * scale - lab * ef.y);
             }
             dst[q >> 3] = w;
           }
@@ -891,9 +951,12 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           for (int k = 0; k < kSlots; ++k) zy += s_dot[k][row];
           if (HAS_BIAS) zy += bias[y];
           const float lse2 = log2f(z);
+          float rl, wg2;
+          ce_row_terms(direct.row, r, lse2 * kLn2, zy, rl, wg2);
           direct.lse[r] = lse2 * kLn2;
-          direct.cvec[r] = -lse2 + (n_valid > 0 ? -log2f((float)n_valid) : 0.f);
-          direct.row_loss[r] = lse2 * kLn2 - zy;
+          direct.cvec[r] = -lse2 + log2f(wg2 * inv_n);
+          direct.row_loss[r] = rl;
+          if (direct.row.roww) direct.row.roww[r] = wg2;
         } else {
           direct.cvec[r] = -INFINITY;  // rows beyond T_v contribute nothing to the dE pass
         }
@@ -917,7 +980,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     } else {
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-      const float inv_n = loss_inv[0];
+      const float inv_n = loss_inv[0] * ((direct.row.roww && r < n_valid) ? direct.row.roww[r] : 1.f);
       const int y = (r < n_valid) ? labels[r] : 0;
 #pragma unroll 1
       for (int c = 0; c < DW; c += 16) {
@@ -954,16 +1017,18 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 // dE[y_t, :] -= Hc[t, :] / T_v   (fp32 atomics; several tokens may share a label)
 __global__ void ce_label_scatter_kernel(const __nv_bfloat16* __restrict__ hc, const int32_t* __restrict__ labels,
                                         const float* __restrict__ loss_inv, const int32_t* __restrict__ n_valid_ptr,
-                                        int d, float* __restrict__ dE, float* __restrict__ d_bias) {
+                                        int d, float* __restrict__ dE, float* __restrict__ d_bias,
+                                        const float* __restrict__ roww) {
   const int n_valid = *n_valid_ptr;
-  const float inv_n = loss_inv[0];
+  const float inv_n0 = loss_inv[0];
   if (d_bias)
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_valid; t += gridDim.x * blockDim.x)
-      atomicAdd(d_bias + labels[t], -inv_n);
+      atomicAdd(d_bias + labels[t], -inv_n0 * (roww ? roww[t] : 1.f));
   const int per_row = d / 4;   // one 16-byte vector reduction (red.global.add.v4.f32) per 4 columns
   const long long total = (long long)n_valid * per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i / per_row), c = (int)(i % per_row) * 4;
+    const float inv_n = inv_n0 * (roww ? roww[t] : 1.f);
     const uint2 raw = *reinterpret_cast<const uint2*>(hc + (size_t)t * d + c);
     const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
     const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
@@ -1043,11 +1108,10 @@ __global__ void ce_fused_finalize_kernel(const float* __restrict__ part_dh, cons
                                          int n_splits, int z_slots, int capacity, int d, float* __restrict__ lse_out,
                                          float* __restrict__ cvec, __nv_bfloat16* __restrict__ d_hc,
                                          float* __restrict__ block_sums, unsigned int* __restrict__ ticket,
-                                         float* __restrict__ loss_out) {
+                                         float* __restrict__ loss_out, const CeRowOpts row) {
   if (*safe_flag == 0) return;
   const int n_valid = *n_valid_ptr;
   const float inv_n = n_valid > 0 ? 1.f / (float)n_valid : 0.f;
-  const float log2_inv_n = n_valid > 0 ? -log2f((float)n_valid) : 0.f;
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   float local = 0.f;
   for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < capacity; t += gridDim.x * wpb) {
@@ -1062,15 +1126,27 @@ __global__ void ce_fused_finalize_kernel(const float* __restrict__ part_dh, cons
     const int y = labels[t];
     const __nv_bfloat16* hr = hc + (size_t)t * d;
     const __nv_bfloat16* er = table + (size_t)y * d;
-    const float scale = inv_n / z;
+    // target logit first: the per-row variants (CeRowOpts) scale the gradient with a weight that may depend on it
     float dot = 0.f;
-    for (int c = lane * 4; c < d; c += 128) {  // 16-byte loads of the partials, all splits in flight
+    for (int c = lane * 4; c < d; c += 128) {
       const uint2 hraw = *reinterpret_cast<const uint2*>(hr + c), eraw = *reinterpret_cast<const uint2*>(er + c);
       const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hraw.x));
       const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hraw.y));
       const float2 e0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&eraw.x));
       const float2 e1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&eraw.y));
       dot = fmaf(h0.x, e0.x, fmaf(h0.y, e0.y, fmaf(h1.x, e1.x, fmaf(h1.y, e1.y, dot))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (bias) dot += bias[y];
+    const float lse2 = log2f(z);
+    float rl, wg;
+    ce_row_terms(row, t, lse2 * kLn2, dot, rl, wg);
+    const float scale = wg * inv_n / z, lab = wg * inv_n;
+    for (int c = lane * 4; c < d; c += 128) {  // 16-byte loads of the partials, all splits in flight
+      const uint2 eraw = *reinterpret_cast<const uint2*>(er + c);
+      const float2 e0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&eraw.x));
+      const float2 e1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&eraw.y));
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
       for (int p = 0; p < n_splits; ++p) {
@@ -1078,18 +1154,15 @@ __global__ void ce_fused_finalize_kernel(const float* __restrict__ part_dh, cons
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
       }
       uint2 o;
-      o.x = pack_bf16(a.x * scale - inv_n * e0.x, a.y * scale - inv_n * e0.y);
-      o.y = pack_bf16(a.z * scale - inv_n * e1.x, a.w * scale - inv_n * e1.y);
+      o.x = pack_bf16(a.x * scale - lab * e0.x, a.y * scale - lab * e0.y);
+      o.y = pack_bf16(a.z * scale - lab * e1.x, a.w * scale - lab * e1.y);
       *reinterpret_cast<uint2*>(d_hc + (size_t)t * d + c) = o;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    if (bias) dot += bias[y];
-    const float lse2 = log2f(z);
     if (lane == 0) {
       lse_out[t] = lse2 * kLn2;
-      cvec[t] = -lse2 + log2_inv_n;
-      local += lse2 * kLn2 - dot;
+      cvec[t] = -lse2 + log2f(wg * inv_n);
+      if (row.roww) row.roww[t] = wg;
+      local += rl;
     }
   }
   __shared__ float red[32];
@@ -1118,12 +1191,12 @@ __global__ void ce_fused_finalize_kernel(const float* __restrict__ part_dh, cons
 __global__ void ce_dh_reduce_kernel(const float* __restrict__ part, int n_splits, long long split_stride, int rows, int c0,
                                     __nv_bfloat16* __restrict__ d_hc, const __nv_bfloat16* __restrict__ table,
                                     const int32_t* __restrict__ labels, const float* __restrict__ loss_inv,
-                                    const int32_t* __restrict__ n_valid_ptr, int d) {
+                                    const int32_t* __restrict__ n_valid_ptr, int d, const float* __restrict__ roww) {
   const int n_valid = *n_valid_ptr;
-  const float inv_n = loss_inv[0];
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows && c0 + r < n_valid; r += gridDim.x * wpb) {
     const int t = c0 + r;
+    const float inv_n = loss_inv[0] * (roww ? roww[t] : 1.f);
     const __nv_bfloat16* e = table + (size_t)labels[t] * d;
     for (int c = lane * 4; c < d; c += 128) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1178,7 +1251,7 @@ using namespace rp;
 // workspace layout: [part float2 cap*8*2][block_sums 1024 f][ticket, bound[3], flag, pad -> 64 B][zpart 16*cap f]
 //                   [part_dh 8*cap*d f]
 struct CeWs {
-  float2* part; float* block_sums; unsigned int* ticket; unsigned int* bound; int32_t* flag; float* zpart; float* part_dh;
+  float2* part; float* block_sums; unsigned int* ticket; unsigned int* bound; int32_t* flag; float* zpart; float* roww; float* part_dh;
 };
 static const int kMaxSplits = 8;       // fused forward + dH: partial gradients per split
 static const int kMaxSplitsFwd = 32;   // two-pass forward: only (max, sum) pairs per split
@@ -1186,7 +1259,7 @@ static const int kWideSplitK = 16;     // d = 512 backward: split-K partials of 
 
 static size_t ce_ws_base_bytes(int cap, int d) {
   return (size_t)cap * kMaxSplitsFwd * 2 * sizeof(float2) + 4096 + 64 + (size_t)kMaxSplits * kBwdCG * kCeMaxGroups * cap * 4 +
-         (d <= 256 ? (size_t)kMaxSplits * cap * d * 4 : 0) + 256;
+         (size_t)(cap + 3) / 4 * 16 + (d <= 256 ? (size_t)kMaxSplits * cap * d * 4 : 0) + 256;
 }
 static size_t ce_ws_bytes(int cap, int n_items, int d) {
   size_t b = (ce_ws_base_bytes(cap, d) + 1023) / 1024 * 1024;
@@ -1210,6 +1283,8 @@ static CeWs ce_ws(void* workspace, int cap, int d) {
   w += 64;
   r.zpart = reinterpret_cast<float*>(w);
   w += (size_t)kMaxSplits * kBwdCG * kCeMaxGroups * cap * 4;
+  r.roww = reinterpret_cast<float*>(w);   // gradient weight per row (CeRowOpts), written by every forward finalisation
+  w += (size_t)(cap + 3) / 4 * 16;
   r.part_dh = reinterpret_cast<float*>(w);
   (void)d;
   return r;
@@ -1254,7 +1329,7 @@ static int launch_ce_bwd(const CUtensorMap& tmA, const void* b_mat, int b_rows, 
                          const int32_t* labels,
                          const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, const float* bias,
                          float* d_bias, void* out, int grid, const int32_t* safe_flag, int run_if_safe, int n_splits,
-                         int capacity, float* zpart, cudaStream_t stream, const CeDirect& direct = CeDirect{nullptr, nullptr, nullptr, nullptr}) {
+                         int capacity, float* zpart, cudaStream_t stream, const CeDirect& direct = CeDirect{nullptr, nullptr, nullptr, nullptr, CeRowOpts{nullptr, nullptr, 0, 0.f, 0.f}}) {
   // d <= 128: the row tile goes to TMEM (2 S buffers + accumulator + operand = 448 columns) and its 32 KB of smem become
   // an extra pipeline stage; d = 256: row tile in smem, 2 S buffers + accumulator = 512 columns
   // RP_CE_ORDER 1: both directions keep the row tile in TMEM (two S buffers suffice once the issue order no longer drains the
@@ -1299,7 +1374,7 @@ static int dispatch_ce_bwd(int d, const CUtensorMap& tmA, const void* b_mat, int
                            const int32_t* labels,
                            const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, const float* bias,
                            float* d_bias, void* out, int grid, const int32_t* safe_flag, int run_if_safe, int n_splits,
-                           int capacity, float* zpart, cudaStream_t stream, const CeDirect& direct = CeDirect{nullptr, nullptr, nullptr, nullptr}) {
+                           int capacity, float* zpart, cudaStream_t stream, const CeDirect& direct = CeDirect{nullptr, nullptr, nullptr, nullptr, CeRowOpts{nullptr, nullptr, 0, 0.f, 0.f}}) {
   switch (d) {
     case 64:
       return launch_ce_bwd<1, 6, MODE>(tmA, b_mat, b_rows, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
@@ -1323,10 +1398,26 @@ static int dispatch_ce_bwd(int d, const CUtensorMap& tmA, const void* b_mat, int
 // disappears and d_hc is already final after this call.  A device-side Cauchy-Schwarz bound on |s| guards the trick; if
 // it fails the two-pass kernels run instead (both variants are launched, the losing one exits at once), so the call
 // stays CUDA-graph capturable.  n_valid_hint (host estimate of *n_valid, 0 = unknown) only tunes the load balance.
+RP_API int rp_ce_head_fwd_w(const void* hc, const void* table, const float* bias, const int32_t* labels,
+                            const int32_t* n_valid, int capacity, int n_items, int d, float* loss_out, float* lse, float* cvec,
+                            void* d_hc, int n_valid_hint, const float* row_weight, int loss_kind, float log_eps, float clamp,
+                            void* workspace, size_t workspace_bytes, void* stream_);
 RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, const int32_t* labels,
                           const int32_t* n_valid, int capacity, int n_items, int d, float* loss_out, float* lse, float* cvec,
                           void* d_hc, int n_valid_hint, void* workspace, size_t workspace_bytes, void* stream_) {
+  return rp_ce_head_fwd_w(hc, table, bias, labels, n_valid, capacity, n_items, d, loss_out, lse, cvec, d_hc, n_valid_hint, nullptr,
+                          0, 0.f, 0.f, workspace, workspace_bytes, stream_);
+}
+
+// Per-row variants of the head (CeRowOpts): row_weight fp32 [capacity] (>= 0, compacted order of the valid targets, NULL = 1),
+// loss_kind 0 = CE, 1 = LogInCE with (log_eps, clamp).  The backward must be rp_ce_head_bwd with the SAME workspace (the
+// per-row gradient weights live there); everything else as rp_ce_head_fwd.
+RP_API int rp_ce_head_fwd_w(const void* hc, const void* table, const float* bias, const int32_t* labels,
+                            const int32_t* n_valid, int capacity, int n_items, int d, float* loss_out, float* lse, float* cvec,
+                            void* d_hc, int n_valid_hint, const float* row_weight, int loss_kind, float log_eps, float clamp,
+                            void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (loss_kind != 0 && loss_kind != 1) return RP_EINVAL;
   if (!hc || !table || !labels || !n_valid || !loss_out || !lse || !cvec || !workspace) return RP_EINVAL;
   if (capacity <= 0 || n_items <= 0) return RP_ESHAPE;
   if (d != 64 && d != 128 && d != 256 && d != 512) return RP_ESHAPE;
@@ -1351,7 +1442,7 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, 
     ce_flag_kernel<<<1, 1, 0, stream>>>(ws.bound, ws.flag);
     RP_LAUNCH_CHECK();
     const int P = pick_splits(hint_tiles, n_item_tiles);
-    CeDirect direct{nullptr, nullptr, nullptr, nullptr};
+    CeDirect direct{nullptr, nullptr, nullptr, nullptr, CeRowOpts{row_weight, ws.roww, loss_kind, log_eps, clamp}};
     if (P == 1) {  // every CTA sees the whole catalog: lse / dH / loss terms come straight out of the fused kernel
       direct.d_hc = reinterpret_cast<__nv_bfloat16*>(d_hc);
       direct.lse = lse;
@@ -1368,7 +1459,8 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, 
     ce_fused_finalize_kernel<<<blocks, 256, 0, stream>>>(ws.part_dh, ws.zpart, reinterpret_cast<const __nv_bfloat16*>(hc),
                                                          reinterpret_cast<const __nv_bfloat16*>(table), labels, bias, n_valid,
                                                          ws.flag, P, ce_z_slots(d), capacity, d, lse, cvec,
-                                                         reinterpret_cast<__nv_bfloat16*>(d_hc), ws.block_sums, ws.ticket, loss_out);
+                                                         reinterpret_cast<__nv_bfloat16*>(d_hc), ws.block_sums, ws.ticket, loss_out,
+                                                         CeRowOpts{row_weight, ws.roww, loss_kind, log_eps, clamp});
     RP_LAUNCH_CHECK();
     skip = ws.flag;
   }
@@ -1387,7 +1479,8 @@ RP_API int rp_ce_head_fwd(const void* hc, const void* table, const float* bias, 
   if (rc != RP_OK) return rc;
   ce_finalize_kernel<<<blocks, 256, 0, stream>>>(ws.part, reinterpret_cast<const __nv_bfloat16*>(hc),
                                                  reinterpret_cast<const __nv_bfloat16*>(table), labels, bias, n_valid, P2 * 2,
-                                                 capacity, d, lse, cvec, ws.block_sums, ws.ticket, loss_out, skip);
+                                                 capacity, d, lse, cvec, ws.block_sums, ws.ticket, loss_out, skip,
+                                                 CeRowOpts{row_weight, ws.roww, loss_kind, log_eps, clamp});
   RP_LAUNCH_CHECK();
   return RP_OK;
 }
@@ -1408,6 +1501,8 @@ RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, 
   if (capacity <= 0 || n_items <= 0) return RP_ESHAPE;
   if (d != 64 && d != 128 && d != 256 && d != 512) return RP_ESHAPE;
   if ((fused || d == 512) && (!workspace || workspace_bytes < ce_ws_bytes(capacity, n_items, d))) return RP_EWORKSPACE;
+  // gradient weight per row, written by the forward (all ones for the plain CE head); without a workspace: plain head
+  const float* roww = (workspace && workspace_bytes >= ce_ws_bytes(capacity, n_items, d)) ? ce_ws(workspace, capacity, d).roww : nullptr;
   if (d == 512) {
     // ---- wide-hidden path: per token chunk  G = exp2((hc.E^T + b) log2e + c_t)  ->  dH = G.E,  dE += G^T.hc
     if (bias) return RP_ESHAPE;  // biased (BERT4Rec) head at d = 512 is not built
@@ -1447,7 +1542,7 @@ RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, 
       ce_dh_reduce_kernel<<<sm_count() * 4, 256, 0, stream>>>(part, split, part_stride, rows, c0,
                                                                reinterpret_cast<__nv_bfloat16*>(d_hc),
                                                                reinterpret_cast<const __nv_bfloat16*>(table), labels,
-                                                               loss_out + 1, n_valid, d);
+                                                               loss_out + 1, n_valid, d, roww);
       RP_LAUNCH_CHECK();
       // dE (+)= G^T . hc[c0:c0+rows]      (A = G read MN-major, contraction over the chunk's valid tokens)
       memset(&g, 0, sizeof(g));
@@ -1460,7 +1555,7 @@ RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, 
       if ((rc = rp_gemm(&g, stream_)) != RP_OK) return rc;
     }
     ce_label_scatter_kernel<<<sm_count() * 4, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hc), labels, loss_out + 1,
-                                                                 n_valid, d, d_table, d_bias);
+                                                                 n_valid, d, d_table, d_bias, roww);
     RP_LAUNCH_CHECK();
     return RP_OK;
   }
@@ -1473,13 +1568,14 @@ RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, 
   const int32_t* flag = fused ? ce_ws(workspace, capacity, d).flag : nullptr;
   // token-major pass: only when the forward did not already produce d_hc
   rc = dispatch_ce_bwd<0>(d, tmH, table, n_items, hc, cvec, labels, table, loss_inv, n_valid, n_items, bias, nullptr, d_hc, n_tok_tiles, flag, 0,
-                          1, capacity, nullptr, stream);
+                          1, capacity, nullptr, stream,
+                          CeDirect{nullptr, nullptr, nullptr, nullptr, CeRowOpts{nullptr, const_cast<float*>(roww), 0, 0.f, 0.f}});
   if (rc != RP_OK) return rc;
   rc = dispatch_ce_bwd<1>(d, tmE, hc, capacity, table, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, d_table, n_item_tiles,
                           nullptr, 0, 1, capacity, nullptr, stream);
   if (rc != RP_OK) return rc;
   ce_label_scatter_kernel<<<sm_count() * 4, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hc), labels, loss_inv,
-                                                               n_valid, d, d_table, d_bias);
+                                                               n_valid, d, d_table, d_bias, roww);
   RP_LAUNCH_CHECK();
   return RP_OK;
 }

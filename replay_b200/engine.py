@@ -530,8 +530,16 @@ class SasRecEngine:
         replay/nn/loss/ce.py:146, bce.py:98) and ``legacy_ce_sampled`` / ``legacy_bce_sampled`` (sasrec/lightning.py:310-376)
         with ``n_neg`` negatives per target, ``neg_shape`` in shared [N] / perseq [B, N] / perpos [B, L, N]."""
         self._loss_args = (kind, dict(n_neg=n_neg, neg_shape=neg_shape, ignore_index=ignore_index, log_eps=log_eps, clamp=clamp))
-        if kind == "ce":
+        # per-row variants of the full-catalog head (rp_ce_head_fwd_w): "ce_weighted" (LogOutCEWeighted / CEWeighted: sample
+        # weights staged with set_row_weights) and "login_ce" (LogInCE); "ce" is the plain head
+        self.ce_row = None
+        if kind in ("ce", "ce_weighted", "login_ce"):
             self.sampled = None
+            if kind != "ce":
+                self.ce_row = dict(kind=1 if kind == "login_ce" else 0, log_eps=log_eps, clamp=clamp, weighted=(kind == "ce_weighted"))
+                if not hasattr(self, "in_roww") or self.in_roww.numel() < self.T:
+                    self.in_roww = torch.ones(self.T, device=self.dev, dtype=torch.float32)
+                    self.roww_c = torch.ones(self.T, device=self.dev, dtype=torch.float32)
             return
         if kind not in self.SAMPLED_KINDS:
             raise NotImplementedError(f"Not supported loss_type {kind!r}")
@@ -541,6 +549,11 @@ class SasRecEngine:
         self.sampled = dict(kind=self.SAMPLED_KINDS[kind], n_neg=n_neg, mode=mode, ignore_index=ignore_index, log_eps=log_eps,
                             clamp=clamp, neg=torch.zeros(rows, n_neg, device=self.dev, dtype=torch.int64),
                             ws=torch.zeros(ws_bytes, device=self.dev, dtype=torch.uint8), ws_bytes=ws_bytes)
+
+    def set_row_weights(self, weights):
+        """Stage the sample weights of the current batch ([B, L] float, one per position; only valid targets are read)."""
+        n = weights.numel()
+        self.in_roww[:n].copy_(weights.reshape(-1).to(torch.float32), non_blocking=True)
 
     def set_negatives(self, negative_labels):
         """Stage the negatives of the current batch ([N] | [B, N] | [B, L, N] int64, device copy)."""
@@ -677,8 +690,15 @@ class SasRecEngine:
         from .ops import ce_head_fwd
 
         self.lib.count += 2
+        row = getattr(self, "ce_row", None)
+        roww = None
+        if row is not None and row["weighted"]:   # weights of the valid targets in the head's compacted order
+            torch.index_select(self.in_roww, 0, self.valid_idx, out=self.roww_c)
+            roww = self.roww_c
         return ce_head_fwd(self.ce, self.hc, self.params16["item_emb"][: cfg.n_items], self.labels_c, self.n_valid,
-                           d_hc=self.s["dhc"] if self.fused_ce else None, n_valid_hint=self.n_valid_hint)
+                           d_hc=self.s["dhc"] if self.fused_ce else None, n_valid_hint=self.n_valid_hint, row_weight=roww,
+                           loss_kind=row["kind"] if row else 0, log_eps=row["log_eps"] if row else 1e-6,
+                           clamp=row["clamp"] if row else 100.0)
 
     # ------------------------------------------------------------------------------------------------ backward
     def backward(self):

@@ -45,7 +45,8 @@ class SasRec(torch.nn.Module):
     @loss.setter
     def loss(self, spec):
         if not hasattr(spec, "kind"):
-            raise NotImplementedError(f"loss {type(spec).__name__} has no fused CUDA head (supported: CE, CESampled, BCESampled)")
+            raise NotImplementedError(f"loss {type(spec).__name__} has no fused CUDA head (supported: CE, CEWeighted, LogOutCE, "
+                                      "LogOutCEWeighted, LogInCE, CESampled, BCESampled)")
         self._loss = spec
         self.core.set_loss(spec.kind, **spec.engine_kwargs())
 
@@ -101,8 +102,9 @@ class SasRec(torch.nn.Module):
         ids = feature_tensors[self.core.item_feature]
         if self._loss.needs_negatives and negative_labels is None:
             raise ValueError(f"{type(self._loss).__name__} needs negative_labels")
+        rw = self._loss.row_weights(feature_tensors, target_padding_mask) if hasattr(self._loss, "row_weights") else None
         loss = self.core.loss(ids, padding_mask, positive_labels, target_padding_mask,
-                              negatives=negative_labels if self._loss.needs_negatives else None)
+                              negatives=negative_labels if self._loss.needs_negatives else None, row_weights=rw)
         return {"loss": loss, "hidden_states": ()}
 
     def forward_inference(self, feature_tensors, padding_mask, candidates_to_score=None):

@@ -81,10 +81,12 @@ class CEHeadState:
         self.cvec = torch.full((cap128,), float("-inf"), device=device, dtype=torch.float32)
 
 
-def ce_head_fwd(st: CEHeadState, hc, table, labels, n_valid, bias=None, d_hc=None, n_valid_hint: int = 0):
+def ce_head_fwd(st: CEHeadState, hc, table, labels, n_valid, bias=None, d_hc=None, n_valid_hint: int = 0, row_weight=None,
+                loss_kind: int = 0, log_eps: float = 1e-6, clamp: float = 100.0):
     """hc bf16 [capacity,d] (zero/finite beyond n_valid), table bf16 [I,d], labels int32 [capacity], n_valid int32 [1].
     With ``d_hc`` (bf16 [capacity,d]) the fused forward+dH pass runs and d_hc is final after this call.
-    Returns st.loss (fp32 [2]: mean CE, 1/n_valid) - a view that the next call overwrites."""
+    ``row_weight`` fp32 [capacity] (compacted order) / ``loss_kind`` 1 = LogInCE: the per-row variants (rp_ce_head_fwd_w).
+    Returns st.loss (fp32 [2]: mean loss, 1/n_valid) - a view that the next call overwrites."""
     _need(hc, torch.bfloat16, "hc")
     _need(table, torch.bfloat16, "table")
     _need(labels, torch.int32, "labels")
@@ -92,9 +94,12 @@ def ce_head_fwd(st: CEHeadState, hc, table, labels, n_valid, bias=None, d_hc=Non
     if d_hc is not None:
         _need(d_hc, torch.bfloat16, "d_hc")
     st.fused = d_hc is not None and st.d <= 256
-    check(lib().rp_ce_head_fwd(_ptr(hc), _ptr(table), _ptr(bias), _ptr(labels), _ptr(n_valid), st.capacity, st.n_items, st.d,
-                               _ptr(st.loss), _ptr(st.lse), _ptr(st.cvec), _ptr(d_hc), int(n_valid_hint), _ptr(st.ws),
-                               st.ws_bytes, _stream()), "rp_ce_head_fwd")
+    if row_weight is not None:
+        _need(row_weight, torch.float32, "row_weight")
+    check(lib().rp_ce_head_fwd_w(_ptr(hc), _ptr(table), _ptr(bias), _ptr(labels), _ptr(n_valid), st.capacity, st.n_items, st.d,
+                                 _ptr(st.loss), _ptr(st.lse), _ptr(st.cvec), _ptr(d_hc), int(n_valid_hint), _ptr(row_weight),
+                                 int(loss_kind), float(log_eps), float(clamp), _ptr(st.ws), st.ws_bytes, _stream()),
+          "rp_ce_head_fwd_w")
     return st.loss
 
 

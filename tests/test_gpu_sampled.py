@@ -181,3 +181,51 @@ def test_api_mirrors_select_the_sampled_heads(golden_dir, cuda):
     with pytest.raises(NotImplementedError):
         LegacySasRec(TensorSchema(TensorFeatureInfo("item_id", n_items, 0, d)), loss_type="CE", loss_sample_count=8,
                      negative_sampling_strategy="inbatch")
+
+
+# ------------------------------------------------------------------------------------------------ full-catalog per-row losses (§8 f.2)
+ROW_CASES = {"logout": ("LogOutCE", {}), "logout_weighted": ("LogOutCEWeighted", dict(feature_name="w")),
+             "ce_weighted": ("CEWeighted", dict(feature_name="w")), "login": ("LogInCE", {}),
+             "login_clamped": ("LogInCE", dict(log_epsilon=1e-3, clamp_border=5.5))}
+
+
+@pytest.mark.parametrize("case", sorted(ROW_CASES))
+@pytest.mark.parametrize("fused", [True, False])
+def test_row_losses_match_reference(golden_dir, cuda, case, fused):
+    """LogOutCE / LogOutCEWeighted / CEWeighted / LogInCE through the new-path mirror (SasRec.loss = selector) against loss and
+    gradients of the REAL reference classes; ``fused=False`` forces the two-pass head (separate code path for the weights)."""
+    from oracle import sasrec as osr
+    from replay_b200 import nn as _nn  # noqa: F401
+    from replay_b200.nn import loss as L
+    from replay_b200.nn.sequential import SasRec
+    from replay_b200.schema import TensorFeatureInfo, TensorSchema
+
+    z, sd = _load(golden_dir, "sasrec_new_tiny.npz")
+    zr = np.load(os.path.join(golden_dir, "row_losses.npz"))
+    n_items, d = int(z["n_items"]), int(z["d"])
+    Lmax = z["ids"].shape[1]
+    model = SasRec.from_params(TensorSchema(TensorFeatureInfo("item_id", n_items, n_items, d)), embedding_dim=d,
+                               num_heads=int(z["H"]), num_blocks=int(z["n_blocks"]), max_sequence_length=Lmax, dropout=0.0,
+                               device=cuda)
+    model.load_state_dict(sd)
+    cls, kw = ROW_CASES[case]
+    if cls != "CEWeighted":
+        kw = dict(kw, cardinality=n_items)
+    model.loss = getattr(L, cls)(**kw)
+    model.train()
+    ids, pm = torch.from_numpy(z["ids"]).cuda(), torch.from_numpy(z["pad_mask"]).cuda()
+    lab, tm = torch.from_numpy(z["labels"]).cuda(), torch.from_numpy(z["target_mask"]).cuda()
+    w = torch.from_numpy(zr["weights"]).cuda()
+    eng = model.core.ensure_engine(ids.shape[0], Lmax, with_grad=True)
+    eng.fused_ce = fused
+    out = model(feature_tensors={"item_id": ids, "w": w}, padding_mask=pm, positive_labels=lab.unsqueeze(-1),
+                target_padding_mask=tm.unsqueeze(-1))
+    out["loss"].backward()
+    torch.cuda.synchronize()
+    ref = float(zr[f"{case}_loss"])
+    assert abs(float(out["loss"]) - ref) < 5e-3 * abs(ref), (float(out["loss"]), ref)
+    G = eng.export_canonical(eng.grads)
+    gE, gW = torch.from_numpy(zr[f"{case}_gE"]), torch.from_numpy(zr[f"{case}_gW"])
+    for nm, a, b in (("item_emb", G["item_emb"].cpu(), gE), ("in_w", G["blocks"][0]["in_w"].cpu(), gW)):
+        c, r = _cos(a, b), float(a.double().norm() / b.double().norm())
+        assert c > 0.995 and abs(r - 1) < 0.03, (nm, c, r)

@@ -189,3 +189,23 @@ def test_sampled_losses_legacy_match_reference(golden_dir, loss):
     torch.testing.assert_close(l, torch.from_numpy(zs[f"legacy_{loss}_loss"]), rtol=2e-5, atol=2e-6)
     torch.testing.assert_close(G["item_emb"], torch.from_numpy(zs[f"legacy_{loss}_gE"]), rtol=1e-4, atol=2e-6)
     torch.testing.assert_close(G["blocks"][0]["in_w"], torch.from_numpy(zs[f"legacy_{loss}_gW"]), rtol=1e-4, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------ full-catalog per-row losses (§8 f.2)
+ROW_CASES = {"logout": ("logout", {}), "logout_weighted": ("logout_weighted", {}), "ce_weighted": ("ce_weighted", {}),
+             "login": ("login", {}), "login_clamped": ("login", dict(log_eps=1e-3, clamp=5.5))}
+
+
+@pytest.mark.parametrize("case", sorted(ROW_CASES))
+def test_row_losses_match_reference(golden_dir, case):
+    from oracle import sampled as osm
+    z, sd = load(golden_dir, "sasrec_new_tiny.npz")
+    zr = np.load(os.path.join(golden_dir, "row_losses.npz"))
+    P = osr.params_from_new_state_dict(sd)
+    ids, pm = torch.from_numpy(z["ids"]), torch.from_numpy(z["pad_mask"])
+    labels, tm = torch.from_numpy(z["labels"]), torch.from_numpy(z["target_mask"])
+    kind, kw = ROW_CASES[case]
+    l, G = osm.row_loss_and_grads(P, ids, pm, labels, tm, int(z["H"]), kind, weights=torch.from_numpy(zr["weights"]), **kw)
+    torch.testing.assert_close(l, torch.from_numpy(zr[f"{case}_loss"]), rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(G["item_emb"], torch.from_numpy(zr[f"{case}_gE"]), rtol=2e-4, atol=2e-6)
+    torch.testing.assert_close(G["blocks"][0]["in_w"], torch.from_numpy(zr[f"{case}_gW"]), rtol=2e-4, atol=2e-6)

@@ -88,6 +88,12 @@ static constexpr int kCeMaxGroups = 2;
 #ifndef RP_CE_PACE_DEPTH
 #define RP_CE_PACE_DEPTH 0   /* pairs of tcgen05.mma in flight before the issuing thread waits for a completion (0 = issue at will) */
 #endif
+#ifndef RP_CE_ISSUE_GROUP
+#define RP_CE_ISSUE_GROUP 0      /* > 0: the issuing thread sleeps RP_CE_ISSUE_SLEEP_NS after every so many tcgen05.mma */
+#endif
+#ifndef RP_CE_ISSUE_SLEEP_NS
+#define RP_CE_ISSUE_SLEEP_NS 150
+#endif
 #ifndef RP_CE_ISSUERS
 #define RP_CE_ISSUERS 1   /* MMA-issuing threads of the backward / fused kernels (1 = warp 1 alone) */
 #endif
@@ -570,7 +576,15 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       // dispatch stage, and the pipe still has 2 (DEPTH - 1) .. 2 DEPTH instructions queued.
       constexpr uint32_t DEPTH = RP_CE_PACE_DEPTH;
       uint32_t n_pair = 0, n_half = 0;
+      // Open-loop variant (RP_CE_ISSUE_GROUP / RP_CE_ISSUE_SLEEP_NS): after every GROUP instructions the issuing thread
+      // sleeps (nanosleep deschedules the warp: the sub-partition's dispatch is free) for about the time the pipe needs to
+      // drain them, instead of sitting in the dispatch stage until the queue has room.
+      uint32_t n_issued = 0;
       auto pace = [&]() {          // call right before every tcgen05.mma
+        if (RP_CE_ISSUE_GROUP > 0 && NI == 1) {
+          if (n_issued != 0 && n_issued % RP_CE_ISSUE_GROUP == 0) __nanosleep(RP_CE_ISSUE_SLEEP_NS);
+          ++n_issued;
+        }
         if (DEPTH == 0 || NI > 1) return;
         if ((n_half & 1) == 0 && n_pair >= DEPTH) {
           const uint32_t m = n_pair - DEPTH;

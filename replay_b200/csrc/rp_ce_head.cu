@@ -17,6 +17,8 @@
 //   ce_bwd_kernel<COL> CTA = 128 items, loops over token tiles:   S^T = E_tile . Hc^T, G = exp2(S^T*log2e + c_col),
 //                      dE += G . Hc_tile                                                          -> dE fp32 [I, d] (=)
 //   ce_label_scatter   dE[y_t] -= Hc[t] / T_v   (the one-hot part of softmax - onehot, sparse)
+#include <type_traits>
+
 #include "rp_host.h"
 #include "rp_gemm_desc.h"
 #include "rp_sm100.cuh"
@@ -87,6 +89,9 @@ static constexpr int kCeMaxGroups = 2;
 #endif
 #ifndef RP_CE_PACE_DEPTH
 #define RP_CE_PACE_DEPTH 0   /* pairs of tcgen05.mma in flight before the issuing thread waits for a completion (0 = issue at will) */
+#endif
+#ifndef RP_CE_POLY_EVERY_Q1
+#define RP_CE_POLY_EVERY_Q1 RP_CE_POLY_EVERY_BWD   /* polynomial share of lane quarter 1's epilogue warps (see the chunk lambda) */
 #endif
 #ifndef RP_CE_ISSUE_GROUP
 #define RP_CE_ISSUE_GROUP 0      /* > 0: the issuing thread sleeps RP_CE_ISSUE_SLEEP_NS after every so many tcgen05.mma */
@@ -753,7 +758,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const uint32_t sbase = s_addr(j);
       // G = exp2(S*log2e + offset) of one CW-column chunk -> CW/2 packed bf16 pairs, written in place over the warp's own
       // (already consumed) S columns: chunk k lands in packed columns [k CW/2, (k+1) CW/2)
-      auto chunk = [&](const uint32_t (&raw)[CW], int k) {
+      auto chunk_e = [&](const uint32_t (&raw)[CW], int k, auto every_c) {
+        constexpr int EVERY = decltype(every_c)::value;
         uint32_t pk[CW / 2];
         const int col0 = (jg0 + j) * TN + cg * kW + k * CW;
         if (COLCONST) {
@@ -761,10 +767,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
           for (int q = 0; q < CW; q += 4) {
             const float4 o = cc[q >> 2];
-            const float g0_ = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 0]), kLog2e, o.x), q + 0);
-            const float g1_ = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 1]), kLog2e, o.y), q + 1);
-            const float g2_ = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 2]), kLog2e, o.z), q + 2);
-            const float g3_ = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(__uint_as_float(raw[q + 3]), kLog2e, o.w), q + 3);
+            const float g0_ = ce_ex2<3, EVERY>(fmaf(__uint_as_float(raw[q + 0]), kLog2e, o.x), q + 0);
+            const float g1_ = ce_ex2<3, EVERY>(fmaf(__uint_as_float(raw[q + 1]), kLog2e, o.y), q + 1);
+            const float g2_ = ce_ex2<3, EVERY>(fmaf(__uint_as_float(raw[q + 2]), kLog2e, o.z), q + 2);
+            const float g3_ = ce_ex2<3, EVERY>(fmaf(__uint_as_float(raw[q + 3]), kLog2e, o.w), q + 3);
             if (HAS_BIAS) gsum += (g0_ + g1_) + (g2_ + g3_);
             pk[(q >> 1) + 0] = pack_bf16(g0_, g1_);
             pk[(q >> 1) + 1] = pack_bf16(g2_, g3_);
@@ -787,8 +793,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             float z0 = 0.f, z1 = 0.f;
 #pragma unroll
             for (int q = 0; q < CW; q += 2) {
-              const float g0_ = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(sv[q + 0], kLog2e, crow), q + 0);
-              const float g1_ = ce_ex2<3, RP_CE_POLY_EVERY_BWD>(fmaf(sv[q + 1], kLog2e, crow), q + 1);
+              const float g0_ = ce_ex2<3, EVERY>(fmaf(sv[q + 0], kLog2e, crow), q + 0);
+              const float g1_ = ce_ex2<3, EVERY>(fmaf(sv[q + 1], kLog2e, crow), q + 1);
               if (FUSED) {
                 z0 += g0_;
                 z1 += g1_;
@@ -817,6 +823,14 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #else
         tmem_st8(sbase + k * (CW / 2), pk);
 #endif
+      };
+      // the two epilogue warps that share the MMA-issuing thread's sub-partition (lane quarter 1) lose ~700 cycles per tile to
+      // its blocked dispatch: RP_CE_POLY_EVERY_Q1 moves a share of THEIR exponentials to the FMA pipe
+      auto chunk = [&](const uint32_t (&raw)[CW], int k) {
+        if (RP_CE_POLY_EVERY_Q1 != RP_CE_POLY_EVERY_BWD && quarter == 1)
+          chunk_e(raw, k, std::integral_constant<int, RP_CE_POLY_EVERY_Q1>{});
+        else
+          chunk_e(raw, k, std::integral_constant<int, RP_CE_POLY_EVERY_BWD>{});
       };
 #if RP_CE_ABLATE == 4   // diagnostic: no TMEM loads (the exponentials run on whatever the registers hold)
 #define tmem_ld16(a, r) asm volatile("" : "+r"(r[0]), "+r"(r[5]), "+r"(r[10]), "+r"(r[15]))

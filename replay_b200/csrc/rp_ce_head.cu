@@ -90,6 +90,9 @@ static constexpr int kCeMaxGroups = 2;
 #ifndef RP_CE_PACE_DEPTH
 #define RP_CE_PACE_DEPTH 0   /* pairs of tcgen05.mma in flight before the issuing thread waits for a completion (0 = issue at will) */
 #endif
+#ifndef RP_CE_PRESCALE
+#define RP_CE_PRESCALE 0   /* fused pass: log2(e) folded into the TMEM row tile (one instruction less per logit; measured: no gain, 1.061 vs 1.050 ms, and the extra bf16 rounding breaks the 1e-2 gradient tolerance of test_ce_head at d = 64) */
+#endif
 #ifndef RP_CE_POLY_EVERY_Q1
 #define RP_CE_POLY_EVERY_Q1 RP_CE_POLY_EVERY_BWD   /* polynomial share of lane quarter 1's epilogue warps (see the chunk lambda) */
 #endif
@@ -460,6 +463,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   constexpr bool FUSED = (MODE == 2);
   constexpr int kW = TN / CG;  // S columns owned by one epilogue warp (its bf16 G lands in the first kW/2 of them)
   constexpr int kChunkB = TN * 128;   // bytes of one [TN rows x 64 bf16] swizzled chunk of a column tile
+  // fused pass with the row tile in TMEM and no bias: the tile is multiplied by log2(e) on its way into TMEM, so a logit's
+  // exponential is ONE instruction (ex2 of the accumulator word: live rows have offset 0) instead of FFMA + ex2 - the
+  // epilogue warps next to the MMA-issuing thread are short of issue slots (profiles/r2_ce_timeline.md)
+  constexpr bool PRESCALE = FUSED && A_TMEM && !HAS_BIAS && (RP_CE_PRESCALE != 0);
   constexpr int kEW = 4 * CG * GROUPS;   // epilogue warps in total
   constexpr int kSlots = CG * GROUPS;      // column slots of the accumulator read-out / of the row-sum partials
   static_assert(GROUPS == 1 || (GROUPS == 2 && NBUF % 2 == 0), "two epilogue warp sets: even / odd S buffers");
@@ -712,6 +719,13 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const uint4 t4 = in ? __ldg(src + ((c + q) >> 2)) : make_uint4(0u, 0u, 0u, 0u);
           v[q] = t4.x; v[q + 1] = t4.y; v[q + 2] = t4.z; v[q + 3] = t4.w;
         }
+        if (PRESCALE) {   // fused pass: the row tile carries log2(e), so S comes out of the tensor core in log2 units
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[q]));
+            v[q] = pack_bf16(f.x * kLog2e, f.y * kLog2e);
+          }
+        }
         tmem_st16(tmem_a + lane_base + slot * WORDS + c, v);
       }
       tmem_st_wait();
@@ -793,8 +807,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             float z0 = 0.f, z1 = 0.f;
 #pragma unroll
             for (int q = 0; q < CW; q += 2) {
-              const float g0_ = ce_ex2<3, EVERY>(fmaf(sv[q + 0], kLog2e, crow), q + 0);
-              const float g1_ = ce_ex2<3, EVERY>(fmaf(sv[q + 1], kLog2e, crow), q + 1);
+              const float g0_ = PRESCALE ? ce_ex2<3, EVERY>(sv[q + 0], q + 0) : ce_ex2<3, EVERY>(fmaf(sv[q + 0], kLog2e, crow), q + 0);
+              const float g1_ = PRESCALE ? ce_ex2<3, EVERY>(sv[q + 1], q + 1) : ce_ex2<3, EVERY>(fmaf(sv[q + 1], kLog2e, crow), q + 1);
               if (FUSED) {
                 z0 += g0_;
                 z1 += g1_;
@@ -805,8 +819,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           } else {  // ragged last tile of the catalog: columns beyond it do not exist
 #pragma unroll
             for (int q = 0; q < CW; q += 2) {
-              float g0_ = ex2f(fmaf(sv[q + 0], kLog2e, crow));
-              float g1_ = ex2f(fmaf(sv[q + 1], kLog2e, crow));
+              float g0_ = PRESCALE ? ex2f(sv[q + 0]) : ex2f(fmaf(sv[q + 0], kLog2e, crow));
+              float g1_ = PRESCALE ? ex2f(sv[q + 1]) : ex2f(fmaf(sv[q + 1], kLog2e, crow));
               if (col0 + q >= n_items) g0_ = 0.f;
               if (col0 + q + 1 >= n_items) g1_ = 0.f;
               if (FUSED) zacc += g0_ + g1_;

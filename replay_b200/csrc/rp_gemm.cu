@@ -449,7 +449,22 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&bar_tfull[as], aph);
       tc_fence_after();
       const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + as * BN + half * HALF;
-      if (HALF == 64) {
+      if (HALF == 128) {   // BN = 256 (both halves of a fused K | V projection in one pass over the activations)
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tbase, r0);
+        tmem_ld32(tbase + 32, r1);
+        tmem_ld_wait();
+        if (row_ok && n0 + half * HALF < p.N) gemm_epilogue_chunk(p, s_bias, er, r0, n0, half * HALF);
+        if (row_ok && n0 + half * HALF + 32 < p.N) gemm_epilogue_chunk(p, s_bias, er, r1, n0, half * HALF + 32);
+        tmem_ld32(tbase + 64, r0);
+        tmem_ld32(tbase + 96, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[as]);
+        if (row_ok && n0 + half * HALF + 64 < p.N) gemm_epilogue_chunk(p, s_bias, er, r0, n0, half * HALF + 64);
+        if (row_ok && n0 + half * HALF + 96 < p.N) gemm_epilogue_chunk(p, s_bias, er, r1, n0, half * HALF + 96);
+      } else if (HALF == 64) {
         uint32_t r0[32], r1[32];
         tmem_ld32(tbase, r0);
         tmem_ld32(tbase + 32, r1);
@@ -482,7 +497,7 @@ static int launch_gemm_ws(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   auto kern = gemm_ws_kernel<BN, KCH, B_MN, NA>;
   RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + 127) / 128;
-  int per_n = (KCH <= 2 ? 2 : 1) * sm_count() / n_tiles;
+  int per_n = ((KCH <= 2 && BN <= 128) ? 2 : 1) * sm_count() / n_tiles;
   if (per_n < 1) per_n = 1;
   if (per_n > m_tiles) per_n = m_tiles;
   dim3 grid(per_n, n_tiles);
@@ -703,6 +718,12 @@ RP_API int rp_gemm(const rp_gemm_desc* g, void* stream_) {
   const bool ws_ok = g->act != 3 && g->out_mode != 4 && !g->m_limit_dev && !g->k_limit_dev && g->M >= ws_min_m && !g->a_mn && g->batch == 1 && g->split_k == 1 && g->M >= 1024 && g->N >= 64 &&
                      (g->K == 64 || g->K == 128 || g->K == 256) && g->a_ro == 0 && g->a_ri == 0 && g->b_ro == 0 && g->b_ri == 0 &&
                      g->a_co == 0 && g->a_ci == 0 && g->b_co == 0 && g->b_ci == 0 && g->c_oo == 0 && g->c_oi == 0;
+  if (ws_ok && bn == 128 && g->N == 256 && !g->b_mn && g->K <= 128 && !getenv("RP_GEMM_WS_NO_WIDE")) {
+    // both 128-column halves in one CTA: the activations are read once (two n-tiles each streamed the whole [M, K] matrix:
+    // 421 MB of DRAM reads for a 210 MB input in the predict body's K | V projection, ncu r2j)
+    if ((rc = make_tmap_bf16(&tmB, g->B, g->b_rows, g->b_cols, g->ldb, 256)) != RP_OK) return rc;
+    return g->K == 64 ? launch_gemm_ws<256, 1, false>(tmA, tmB, p, stream) : launch_gemm_ws<256, 2, false>(tmA, tmB, p, stream);
+  }
   if (ws_ok && bn == 128) {
 #define RP_WS_CASE(KCH_)                                                             \
   return g->b_mn ? launch_gemm_ws<128, KCH_, true>(tmA, tmB, p, stream) : launch_gemm_ws<128, KCH_, false>(tmA, tmB, p, stream)

@@ -566,3 +566,21 @@ def test_post_attn_bwd_matches_formula(ops, T, d, drop, masked):
     assert rel(o["d_o"], d_o) < 1.2e-2, rel(o["d_o"], d_o)
     assert float(((dw.cpu().double() - 1.0) - (dy * xhat).sum(0)).norm() / (dy * xhat).sum(0).norm()) < 1e-2
     assert float(((db.cpu().double() + 1.0) - dy.sum(0)).norm() / dy.sum(0).norm()) < 1e-2
+
+
+def test_gemm_weight_stationary_wide_tile_matches_matmul(ops):
+    """The predict body's K | V projection shape (M >= 131072 rows, N = 256, K = 128, bias): gemm_ws_kernel<256> keeps both
+    128-column halves of the weight in one CTA so the activations are read once; against a fp32 matmul of the same bf16 data."""
+    cuda = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 131072 + 300, 256, 128
+    A = (torch.randn(M, K, device=cuda, generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device=cuda, generator=g) * 0.2).bfloat16()
+    b = torch.randn(N, device=cuda, generator=g)
+    C = torch.zeros(M, N, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(A, W, C, M, N, K, bias=b)
+    torch.cuda.synchronize()
+    rows = torch.cat([torch.arange(0, 4096, device=cuda), torch.arange(M - 4096, M, device=cuda)])
+    ref = A[rows].float() @ W.float().T + b
+    assert torch.allclose(C[rows].float(), ref, atol=3e-2, rtol=2e-2)
+    assert float((C[rows].float() - ref).abs().mean()) < 4e-3

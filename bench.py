@@ -422,6 +422,7 @@ def run_ours(args):
                                                 d_hc=eng.s["dhc"] if eng.fused_ce else None, n_valid_hint=eng.n_valid_hint))
     t_bwd = time_kernel(lambda: ops.ce_head_bwd(eng.ce, eng.hc, W16, eng.labels_c, eng.n_valid, eng.s["dhc"], dW, bias=bias,
                                                 d_bias=dbias, n_valid_hint=eng.n_valid_hint))
+    fused_taken = bool(ops.ce_head_fused_taken(eng.ce)) if (eng.fused_ce and d <= 256) else False
     eng.g32.zero_()
     gemm_flops = 2.0 * n_valid * I * d
     ce_ms = t_fwd + t_bwd
@@ -441,6 +442,7 @@ def run_ours(args):
         "detail": {"ce_fwd_ms": t_fwd, "ce_bwd_ms": t_bwd, "n_valid_targets": n_valid,
                    "algorithmic_flops_per_launch_pair": 3 * gemm_flops,
                    "executed_tflops": n_exec * gemm_flops / (ce_ms * 1e-3) / 1e12, "fused_fwd_dh": fused,
+                   "fused_path_taken": fused_taken,  # False: the device-side bound on |logit| failed, the two-pass kernels ran
                    "share_of_step": ce_ms / (ms / K)},
     }
     launches = (tr.launches_per_step or 0) * K

@@ -375,12 +375,15 @@ struct CeDirect {
   float* cvec;
   float* row_loss;       // [capacity] weighted row losses; summed in a fixed order by ce_loss_reduce_kernel
   CeRowOpts row;         // (row.roww is also what MODE 0 scales its one-hot term with)
+  int use_lse_off;       // fused pass as the FALLBACK's gradient pass: exponent offset of row t = -lse[t] (from the two-pass
+                         // forward) instead of the fixed reference 0, so G is the softmax itself (z ~ 1) whatever |logit| is
 };
 
 // loss = mean over the valid targets of row_loss, deterministic (fixed partition + tree); also publishes 1 / T_v
 __global__ void __launch_bounds__(1024) ce_loss_reduce_kernel(const float* __restrict__ row_loss, const int32_t* __restrict__ n_valid_ptr,
-                                                              const int32_t* __restrict__ safe_flag, float* __restrict__ loss_out) {
-  if (safe_flag && *safe_flag == 0) return;  // the two-pass fallback computes the loss itself
+                                                              const int32_t* __restrict__ safe_flag, float* __restrict__ loss_out,
+                                                              int run_if_safe) {
+  if (safe_flag && (*safe_flag != 0) != (run_if_safe != 0)) return;
   __shared__ float red[1024];
   const int n_valid = *n_valid_ptr;
   float a = 0.f;
@@ -701,7 +704,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const bool partial = PERSIST && n_ct != n_ct_all;            // other CTAs hold the rest of this row tile's columns
     float crow = 0.f;
     if (MODE == 0) crow = (r0 + row < n_valid) ? cvec[r0 + row] : -INFINITY;
-    if (FUSED) crow = (r0 + row < n_valid) ? 0.f : -INFINITY;
+    if (FUSED) crow = (r0 + row < n_valid) ? (direct.use_lse_off ? -direct.lse[r0 + row] * kLog2e : 0.f) : -INFINITY;
     float zacc = 0.f;  // FUSED: sum of G~ over this thread's columns
     float gsum = 0.f;  // COL mode with bias: sum over tokens of G (before the e^{b_i} row factor) -> bias gradient
     if (A_TMEM) {
@@ -952,7 +955,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (HAS_BIAS) zy0 += bias[y];
         asm volatile("bar.sync 1, %0;" ::"r"(kEW * 32) : "memory");   // s_dot is written again below
         float rl_unused;
-        if (live) ce_row_terms(direct.row, r, __logf(z), zy0, rl_unused, wg);
+        if (live) ce_row_terms(direct.row, r, __logf(z) - crow * kLn2, zy0, rl_unused, wg);
       }
       const float scale = live ? wg * inv_n / z : 0.f;
       const float lab = wg * inv_n;
@@ -992,7 +995,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
           for (int k = 0; k < kSlots; ++k) zy += s_dot[k][row];
           if (HAS_BIAS) zy += bias[y];
-          const float lse2 = log2f(z);
+          const float lse2 = log2f(z) - crow;   // (crow = 0 unless the pass runs behind the two-pass forward)
           float rl, wg2;
           ce_row_terms(direct.row, r, lse2 * kLn2, zy, rl, wg2);
           direct.lse[r] = lse2 * kLn2;
@@ -1150,8 +1153,8 @@ __global__ void ce_fused_finalize_kernel(const float* __restrict__ part_dh, cons
                                          int n_splits, int z_slots, int capacity, int d, float* __restrict__ lse_out,
                                          float* __restrict__ cvec, __nv_bfloat16* __restrict__ d_hc,
                                          float* __restrict__ block_sums, unsigned int* __restrict__ ticket,
-                                         float* __restrict__ loss_out, const CeRowOpts row) {
-  if (*safe_flag == 0) return;
+                                         float* __restrict__ loss_out, const CeRowOpts row, int use_lse_off, int run_if_safe) {
+  if ((*safe_flag != 0) != (run_if_safe != 0)) return;
   const int n_valid = *n_valid_ptr;
   const float inv_n = n_valid > 0 ? 1.f / (float)n_valid : 0.f;
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -1181,7 +1184,7 @@ __global__ void ce_fused_finalize_kernel(const float* __restrict__ part_dh, cons
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
     if (bias) dot += bias[y];
-    const float lse2 = log2f(z);
+    const float lse2 = log2f(z) + (use_lse_off ? lse_out[t] * kLog2e : 0.f);   // behind the two-pass forward: offsets -lse
     float rl, wg;
     ce_row_terms(row, t, lse2 * kLn2, dot, rl, wg);
     const float scale = wg * inv_n / z, lab = wg * inv_n;
@@ -1371,7 +1374,7 @@ static int launch_ce_bwd(const CUtensorMap& tmA, const void* b_mat, int b_rows, 
                          const int32_t* labels,
                          const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, const float* bias,
                          float* d_bias, void* out, int grid, const int32_t* safe_flag, int run_if_safe, int n_splits,
-                         int capacity, float* zpart, cudaStream_t stream, const CeDirect& direct = CeDirect{nullptr, nullptr, nullptr, nullptr, CeRowOpts{nullptr, nullptr, 0, 0.f, 0.f}}) {
+                         int capacity, float* zpart, cudaStream_t stream, const CeDirect& direct = CeDirect{nullptr, nullptr, nullptr, nullptr, CeRowOpts{nullptr, nullptr, 0, 0.f, 0.f}, 0}) {
   // d <= 128: the row tile goes to TMEM (2 S buffers + accumulator + operand = 448 columns) and its 32 KB of smem become
   // an extra pipeline stage; d = 256: row tile in smem, 2 S buffers + accumulator = 512 columns
   // RP_CE_ORDER 1: both directions keep the row tile in TMEM (two S buffers suffice once the issue order no longer drains the
@@ -1416,7 +1419,7 @@ static int dispatch_ce_bwd(int d, const CUtensorMap& tmA, const void* b_mat, int
                            const int32_t* labels,
                            const void* table, const float* loss_inv, const int32_t* n_valid, int n_items, const float* bias,
                            float* d_bias, void* out, int grid, const int32_t* safe_flag, int run_if_safe, int n_splits,
-                           int capacity, float* zpart, cudaStream_t stream, const CeDirect& direct = CeDirect{nullptr, nullptr, nullptr, nullptr, CeRowOpts{nullptr, nullptr, 0, 0.f, 0.f}}) {
+                           int capacity, float* zpart, cudaStream_t stream, const CeDirect& direct = CeDirect{nullptr, nullptr, nullptr, nullptr, CeRowOpts{nullptr, nullptr, 0, 0.f, 0.f}, 0}) {
   switch (d) {
     case 64:
       return launch_ce_bwd<1, 6, MODE>(tmA, b_mat, b_rows, a_rows, cvec, labels, table, loss_inv, n_valid, n_items, bias, d_bias, out, grid,
@@ -1484,10 +1487,9 @@ RP_API int rp_ce_head_fwd_w(const void* hc, const void* table, const float* bias
     ce_flag_kernel<<<1, 1, 0, stream>>>(ws.bound, ws.flag);
     RP_LAUNCH_CHECK();
     const int P = pick_splits(hint_tiles, n_item_tiles);
-    CeDirect direct{nullptr, nullptr, nullptr, nullptr, CeRowOpts{row_weight, ws.roww, loss_kind, log_eps, clamp}};
+    CeDirect direct{nullptr, lse, nullptr, nullptr, CeRowOpts{row_weight, ws.roww, loss_kind, log_eps, clamp}, 0};
     if (P == 1) {  // every CTA sees the whole catalog: lse / dH / loss terms come straight out of the fused kernel
       direct.d_hc = reinterpret_cast<__nv_bfloat16*>(d_hc);
-      direct.lse = lse;
       direct.cvec = cvec;
       direct.row_loss = ws.zpart;  // the row-sum partials are not needed in this mode: reuse their buffer
     }
@@ -1495,14 +1497,14 @@ RP_API int rp_ce_head_fwd_w(const void* hc, const void* table, const float* bias
                             n_tok_tiles * P, ws.flag, 1, P, capacity, ws.zpart, stream, direct);
     if (rc != RP_OK) return rc;
     if (P == 1) {
-      ce_loss_reduce_kernel<<<1, 1024, 0, stream>>>(ws.zpart, n_valid, ws.flag, loss_out);
+      ce_loss_reduce_kernel<<<1, 1024, 0, stream>>>(ws.zpart, n_valid, ws.flag, loss_out, 1);
       RP_LAUNCH_CHECK();
     } else
     ce_fused_finalize_kernel<<<blocks, 256, 0, stream>>>(ws.part_dh, ws.zpart, reinterpret_cast<const __nv_bfloat16*>(hc),
                                                          reinterpret_cast<const __nv_bfloat16*>(table), labels, bias, n_valid,
                                                          ws.flag, P, ce_z_slots(d), capacity, d, lse, cvec,
                                                          reinterpret_cast<__nv_bfloat16*>(d_hc), ws.block_sums, ws.ticket, loss_out,
-                                                         CeRowOpts{row_weight, ws.roww, loss_kind, log_eps, clamp});
+                                                         CeRowOpts{row_weight, ws.roww, loss_kind, log_eps, clamp}, 0, 1);
     RP_LAUNCH_CHECK();
     skip = ws.flag;
   }
@@ -1524,6 +1526,33 @@ RP_API int rp_ce_head_fwd_w(const void* hc, const void* table, const float* bias
                                                  capacity, d, lse, cvec, ws.block_sums, ws.ticket, loss_out, skip,
                                                  CeRowOpts{row_weight, ws.roww, loss_kind, log_eps, clamp});
   RP_LAUNCH_CHECK();
+  if (fused) {
+    // The bound failed (these launches exit at once otherwise): the two-pass forward above has produced lse; the gradient
+    // dH comes from the SAME fused kernel, now with the exponent offset -lse[t] per row (G = softmax, z ~ 1) - with its column
+    // splits and all SMs busy, where the row-tile-per-CTA MODE 0 pass ran 32 CTAs at BERT4Rec's ~4000 masked positions
+    // (2.2 ms of a 4.3 ms step at config 3, whose un-normalised outputs outgrow the bound within a few hundred steps).
+    const int P = pick_splits(hint_tiles, n_item_tiles);
+    CeDirect direct{nullptr, lse, nullptr, nullptr, CeRowOpts{row_weight, ws.roww, loss_kind, log_eps, clamp}, 1};
+    if (P == 1) {
+      direct.d_hc = reinterpret_cast<__nv_bfloat16*>(d_hc);
+      direct.cvec = cvec;
+      direct.row_loss = ws.zpart;
+    }
+    RP_CUDA_CHECK(cudaMemsetAsync(ws.ticket, 0, 4, stream));   // the deterministic loss reduction's ticket was used above
+    rc = dispatch_ce_bwd<2>(d, tmA, table, n_items, hc, cvec, labels, table, loss_out + 1, n_valid, n_items, bias, nullptr, ws.part_dh,
+                            n_tok_tiles * P, ws.flag, 0, P, capacity, ws.zpart, stream, direct);
+    if (rc != RP_OK) return rc;
+    if (P == 1) {
+      ce_loss_reduce_kernel<<<1, 1024, 0, stream>>>(ws.zpart, n_valid, ws.flag, loss_out, 0);
+    } else {
+      ce_fused_finalize_kernel<<<blocks, 256, 0, stream>>>(ws.part_dh, ws.zpart, reinterpret_cast<const __nv_bfloat16*>(hc),
+                                                           reinterpret_cast<const __nv_bfloat16*>(table), labels, bias, n_valid,
+                                                           ws.flag, P, ce_z_slots(d), capacity, d, lse, cvec,
+                                                           reinterpret_cast<__nv_bfloat16*>(d_hc), ws.block_sums, ws.ticket, loss_out,
+                                                           CeRowOpts{row_weight, ws.roww, loss_kind, log_eps, clamp}, 1, 0);
+    }
+    RP_LAUNCH_CHECK();
+  }
   return RP_OK;
 }
 
@@ -1608,7 +1637,9 @@ RP_API int rp_ce_head_bwd(const void* hc, const void* table, const float* bias, 
   const int n_tok_tiles = (capacity + kT - 1) / kT, n_item_tiles = (n_items + kT - 1) / kT;
   const float* loss_inv = loss_out + 1;
   const int32_t* flag = fused ? ce_ws(workspace, capacity, d).flag : nullptr;
-  // token-major pass: only when the forward did not already produce d_hc
+  // token-major pass: only when the forward did not already produce d_hc (a fused forward always does: from the fused pass
+  // itself, or - bound failed - from its second launch behind the two-pass forward)
+  if (!fused)
   rc = dispatch_ce_bwd<0>(d, tmH, table, n_items, hc, cvec, labels, table, loss_inv, n_valid, n_items, bias, nullptr, d_hc, n_tok_tiles, flag, 0,
                           1, capacity, nullptr, stream,
                           CeDirect{nullptr, nullptr, nullptr, nullptr, CeRowOpts{nullptr, const_cast<float*>(roww), 0, 0.f, 0.f}});

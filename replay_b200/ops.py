@@ -103,6 +103,13 @@ def ce_head_fwd(st: CEHeadState, hc, table, labels, n_valid, bias=None, d_hc=Non
     return st.loss
 
 
+def ce_head_fused_taken(st: CEHeadState) -> bool:
+    """Diagnostic (one device read): did the last fused forward pass run, i.e. did the device-side bound on |logit| hold?
+    (workspace layout of csrc/rp_ce_head.cu: the flag follows the partials, the block sums, the ticket and bound[3])"""
+    off = st.capacity * 32 * 2 * 8 + 4096 + 16
+    return bool(st.ws[off:off + 4].view(torch.int32).item() != 0)
+
+
 def ce_head_bwd(st: CEHeadState, hc, table, labels, n_valid, d_hc, d_table, bias=None, d_bias=None, n_valid_hint: int = 0):
     """d_hc bf16 [capacity,d] (computed here unless the forward ran fused), d_table fp32 [>=I, d] (rows < I overwritten)."""
     _need(d_hc, torch.bfloat16, "d_hc")

@@ -64,3 +64,26 @@ def balanced_rank_shards(work: torch.Tensor, world: int) -> torch.Tensor:
     r = pos % (2 * world)
     rank_of = torch.where(r < world, r, 2 * world - 1 - r)
     return torch.stack([order[rank_of == k] for k in range(world)])
+
+
+def replica_partition(length: int, curr_replica: int, num_replicas: int, generator: torch.Generator | None = None,
+                      device="cpu") -> torch.Tensor:
+    """Row indices of one data-parallel replica, exactly as the reference's parquet reader assigns them
+    (``Partitioning.generate``, replay/data/nn/parquet/info/partitioning.py:64-122): the index range is padded to a multiple
+    of the replica count, optionally permuted with ``generator`` (a permutation of the PADDED range), replica r takes every
+    ``num_replicas``-th entry starting at r, and padded indices wrap around modulo ``length`` - so the last replicas may see
+    a few rows twice (``trainer.user_shard`` is the exact, duplicate-free partition used for predict()).
+    Returns int64 [ceil(length / num_replicas)]."""
+    if length < 1:
+        raise ValueError(f"Length is invalid. Got {length}.")
+    if num_replicas < 1:
+        raise ValueError(f"Num Replicas is invalid. Got {num_replicas}.")
+    if curr_replica < 0 or num_replicas <= curr_replica:
+        raise ValueError(f"Curr Replicas is invalid. Got {curr_replica}.")
+    per_replica = -(-length // num_replicas)
+    full = per_replica * num_replicas
+    if generator is None:
+        raw = torch.arange(full, dtype=torch.int64, device=device)
+    else:
+        raw = torch.randperm(full, dtype=torch.int64, generator=generator).to(device)
+    return torch.remainder(raw[curr_replica:full:num_replicas], length)

@@ -177,9 +177,12 @@ class DeviceBatchLoader:
 
     def __init__(self, store: DeviceSequenceStore, max_len: int, batch_size: int, pad_value: int, kind: str = "sasrec",
                  sliding_window_step: int | None = None, shuffle: bool = True, drop_last: bool = False, seed: int = 0,
-                 rank: int = 0, world_size: int = 1, mask_prob: float = 0.15):
+                 rank: int = 0, world_size: int = 1, mask_prob: float = 0.15, partitioning: str = "sampler"):
         if kind not in ("sasrec", "bert4rec"):
             raise ValueError(f"unknown kind {kind!r}")
+        if partitioning not in ("sampler", "replay"):
+            raise ValueError(f"unknown partitioning {partitioning!r}")
+        self.partitioning = partitioning
         self.store, self.L, self.bs, self.pad, self.kind = store, int(max_len), int(batch_size), int(pad_value), kind
         window = self.L + (1 if kind == "sasrec" else 0)
         seq, off = window_index(store.lengths, window, sliding_window_step)
@@ -199,8 +202,15 @@ class DeviceBatchLoader:
 
     def epoch_indices(self) -> torch.Tensor:
         """This rank's window indices for the current epoch (on the store's device): seeded permutation shared by all ranks,
-        wrap-around padding to a multiple of the world size, strided over the ranks (DistributedSampler semantics)."""
+        wrap-around padding to a multiple of the world size, strided over the ranks (DistributedSampler semantics).
+        ``partitioning="replay"``: the reference parquet reader's assignment instead (``replay_b200.data.replica_partition`` =
+        ``Partitioning.generate``, replay/data/nn/parquet/info/partitioning.py:64-122: permutation of the PADDED range, modulo)."""
         dev = self.store.device
+        if getattr(self, "partitioning", "sampler") == "replay":
+            from .data import replica_partition
+
+            g = torch.Generator(device="cpu").manual_seed(self.seed + self.epoch) if self.shuffle else None
+            return replica_partition(self.n, self.rank, self.world, generator=g, device=dev)
         if self.shuffle:
             g = torch.Generator(device="cpu").manual_seed(self.seed + self.epoch)
             order = torch.randperm(self.n, generator=g).to(dev)

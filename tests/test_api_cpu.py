@@ -434,3 +434,26 @@ def test_balanced_rank_shards_deals_equal_counts_and_near_equal_work():
 
     with pytest.raises(ValueError):
         balanced_rank_shards(work[:4095], 8)
+
+
+def test_replica_partition_reproduces_reference_known_answers(golden_dir):
+    """replay_b200.data.replica_partition against outputs of the real ``Partitioning.generate`` (tests/golden/partitioning_known.npz,
+    produced in the build container; the generator variant was checked there element by element against the reference)."""
+    import numpy as np
+    import pytest
+    import torch
+
+    from replay_b200.data import replica_partition
+
+    z = np.load(os.path.join(golden_dir, "partitioning_known.npz"))
+    assert len(z.files) == 14
+    for key in z.files:
+        _, n, w, r = key.split("_")
+        got = replica_partition(int(n), int(r), int(w))
+        assert torch.equal(got, torch.from_numpy(z[key])), key
+    # every row is covered, padding wraps around (5 rows over 7 replicas: every replica one row, two of them repeats)
+    allrows = torch.cat([replica_partition(5, r, 7) for r in range(7)])
+    assert set(allrows.tolist()) == set(range(5)) and allrows.numel() == 7
+    for bad in ((0, 0, 1), (4, 2, 2), (4, 0, 0)):
+        with pytest.raises(ValueError):
+            replica_partition(*bad)

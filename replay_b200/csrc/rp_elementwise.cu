@@ -112,14 +112,21 @@ __global__ void embed_fwd_kernel(const __nv_bfloat16* __restrict__ table, const 
 #pragma unroll
   for (int i = 0; i < VEC; ++i) ck[i] = drop_col_key((uint32_t)(lane * VEC + i));
   // TOK tokens per warp and iteration: the id loads, then the row loads of all of them are in flight together (one token at a
-  // time the loop was a chain of two dependent DRAM round trips per token, 43 us for 102 400 tokens at d = 128)
-  constexpr int TOK = 4;
-  for (int tb = (blockIdx.x * wpb + (threadIdx.x >> 5)) * TOK; tb < T; tb += gridDim.x * wpb * TOK) {
+  // time the loop was a chain of two dependent DRAM round trips per token, 43 us for 102 400 tokens at d = 128).  The TOK
+  // tokens sit at the SAME position of TOK consecutive sequences, so the fp32 position row (2 x the bytes of the bf16 item
+  // row) is fetched once per iteration instead of once per token: the predict body's 819 200 tokens moved 420 MB of position
+  // rows through L2 next to 210 MB of item rows and 210 MB of output (102 us, L2-bound).
+  constexpr int TOK = VEC <= 4 ? 8 : 4;
+  const int n_seq = T / L;                      // T is a multiple of L (whole sequences)
+  const int n_grp = (n_seq + TOK - 1) / TOK;
+  const long long n_work = (long long)n_grp * L;
+  for (long long u = blockIdx.x * wpb + (threadIdx.x >> 5); u < n_work; u += (long long)gridDim.x * wpb) {
+    const int pidx = (int)(u % L), s0 = (int)(u / L) * TOK;
     int id[TOK];
     bool use_mask[TOK];
 #pragma unroll
     for (int k = 0; k < TOK; ++k) {
-      const int t = min(tb + k, T - 1);
+      const int t = min(s0 + k, n_seq - 1) * L + pidx;
       id[k] = ids[t];
       // BERT4Rec: positions with token_mask == 0 (<MASK> and pads) take the single mask embedding (bert4rec/model.py:285-288)
       use_mask[k] = tok_mask && !tok_mask[t];
@@ -131,17 +138,22 @@ __global__ void embed_fwd_kernel(const __nv_bfloat16* __restrict__ table, const 
 #pragma unroll
       for (int i = 0; i < VEC; i += 2) ev[k][i >> 1] = *reinterpret_cast<const __nv_bfloat162*>(e + i);
     }
+    float pv[VEC];
+    {
+      const float* p = pos + (size_t)(pos0 + pidx) * D + lane * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) pv[i] = p[i];
+    }
 #pragma unroll
     for (int k = 0; k < TOK; ++k) {
-      const int t = tb + k;
-      if (t >= T) break;
-      const float* p = pos + (size_t)(pos0 + t % L) * D + lane * VEC;
+      if (s0 + k >= n_seq) break;
+      const int t = (s0 + k) * L + pidx;
       float v[VEC];
 #pragma unroll
       for (int i = 0; i < VEC; i += 2) {
         const float2 f = __bfloat1622float2(ev[k][i >> 1]);
-        v[i] = f.x * scale + p[i];
-        v[i + 1] = f.y * scale + p[i + 1];
+        v[i] = f.x * scale + pv[i];
+        v[i + 1] = f.y * scale + pv[i + 1];
       }
       if (drop_p > 0.f) {
         const uint32_t rk = drop_row_key(seed, drop_off, (unsigned long long)t);
@@ -661,6 +673,7 @@ RP_API int rp_embed_fwd(const void* table, const float* pos, const int32_t* ids,
                         unsigned long long drop_off, const unsigned long long* seed_ptr, void* out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!table || !pos || !ids || !out || T <= 0 || L <= 0) return RP_EINVAL;
+  if (T % L != 0) return RP_ESHAPE;   // whole sequences (the kernel walks position by position)
   const int grid = grid_for(T, 8);
   RP_DISPATCH_D(d, (embed_fwd_kernel<VEC><<<grid, 256, 0, stream>>>(
                        reinterpret_cast<const __nv_bfloat16*>(table), pos, ids, pad_mask, T, L, pos0, scale, zero_pad_rows,
@@ -813,6 +826,7 @@ RP_API int rp_bert_embed_fwd(const void* table, const void* mask_emb, const floa
                              unsigned long long drop_off, const unsigned long long* seed_ptr, void* out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!table || !mask_emb || !pos || !ids || !tok_mask || !out || T <= 0 || L <= 0) return RP_EINVAL;
+  if (T % L != 0) return RP_ESHAPE;
   const int grid = grid_for(T, 8);
   RP_DISPATCH_D(d, (embed_fwd_kernel<VEC><<<grid, 256, 0, stream>>>(
                        reinterpret_cast<const __nv_bfloat16*>(table), pos, ids, tok_mask, T, L, 0, 1.f, 0, drop_p, seed, drop_off,

@@ -614,6 +614,15 @@ class SasRecEngine:
                 check(self.lib.rp_attn_last(lb["Q"].data_ptr(), a["KV"].data_ptr(), a["KV"].data_ptr(), 2 * d, 2 * d, 0, d,
                                             pad.data_ptr(), Bq, H, L, hd, int(not legacy), lb["O"].data_ptr(), att_scale,
                                             self._stream()), "rp_attn_last")
+                if d <= 128 and self.fused_post_attn_eval:
+                    # out-projection + residual + LayerNorm + FFN of the B last rows in the same fused pass the full blocks
+                    # use (one launch instead of GEMM, LayerNorm, GEMM, GEMM: ~10 us each on [4096, d] rows)
+                    check(self.lib.rp_post_attn_fused(lb["O"].data_ptr(), lb["q_in"].data_ptr(), w("out_w").data_ptr(),
+                                                      f("out_b").data_ptr(), f("ln2_w").data_ptr(), f("ln2_b").data_ptr(), 1e-8,
+                                                      w("w1").data_ptr(), f("b1").data_ptr(), w("w2").data_ptr(), f("b2").data_ptr(),
+                                                      self.last_pad.data_ptr() if legacy else None, Bq, d,
+                                                      self.last_rows.data_ptr(), hdv, self._stream()), "rp_post_attn_fused")
+                    return
                 self._gemm(lb["O"], w("out_w"), lb["h"], Bq, d, d, bias=f("out_b"), residual=lb["q_in"])
                 self._ln_fwd(lb["h"], f("ln2_w"), f("ln2_b"), 1e-8, lb["y"], self.meanf, self.rstdf, Bq)
                 self._gemm(lb["y"], w("w1"), lb["u"], Bq, d, d, bias=f("b1"), act=1)

@@ -62,6 +62,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int bz = b * p.H + h;
   const int L = p.L;
+  // Inference: a query tile whose rows are ALL padding (left-padded windows: the first tile of every user with at most L - 128
+  // items, ~40 % of the MovieLens-shaped users at L = 200) produces nothing anybody reads - the new path masks pad positions as
+  // keys and never queries them, the legacy path zeroes pad rows after the block.  Such a CTA writes zeros and leaves before
+  // any load or MMA.  (Training keeps the rows: the backward reads their saved statistics.)
+  if (p.pad_mask && p.inv_sum == nullptr && p.p_save == nullptr && p.m_save == nullptr) {
+    const int r = q0 + (int)threadIdx.x;
+    const int live = (threadIdx.x < 128 && r < L) ? (p.pad_mask[(size_t)b * L + r] != 0) : 0;
+    if (!__syncthreads_or(live)) {
+      // 128 rows x HD bf16 of this head: 16-byte stores, HD / 8 per row
+      constexpr int PER_ROW = HD / 8;
+      for (int i = threadIdx.x; i < 128 * PER_ROW; i += blockDim.x) {
+        const int rr = q0 + i / PER_ROW;
+        if (rr < L)
+          *reinterpret_cast<uint4*>(p.out + ((size_t)b * L + rr) * p.ldo + h * HD + (i % PER_ROW) * 8) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      return;
+    }
+  }
   int nk = p.causal ? min(L, q0 + 128) : L;        // keys that can be visible to this query tile
   const int nk32 = (nk + 31) & ~31;                // MMA N / K extent (<= 256 per block, KB blocks)
   const int n_boxes = (nk32 + 127) / 128;

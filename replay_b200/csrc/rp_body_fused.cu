@@ -30,6 +30,7 @@ struct LnQkvParams {
   __nv_bfloat16* KV;          // [T, 2d]
   float* mean_out;            // [T] or null
   float* rstd_out;
+  int kv_only;                // predict, final block: only [K | V] = x Wkv^T + bkv (no LayerNorm, no Q: those run on the B last rows)
 };
 
 // pack 8 fp32 accumulator words (+ bias) into 4 bf16 pairs
@@ -90,7 +91,7 @@ ln_qkv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
   if (threadIdx.x >= 64)
     for (int i = threadIdx.x - 64; i < 3 * D; i += kBfEpiWarps * 32) {
-      if (i < D) {
+      if (i < D && !p.kv_only) {
         s_lnw[i] = p.ln_w[i];
         s_lnb[i] = p.ln_b[i];
       }
@@ -140,6 +141,7 @@ ln_qkv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         umma_commit(&x_empty[s]);
         umma_commit(&kv_full);
+        if (p.kv_only) continue;
         // Q = LN(x) . Wq^T : A operand = packed bf16 q_in written to TMEM by the epilogue warps
         mbar_wait(&q_ready, tp);
         if (it > 0) mbar_wait(&q_free, tp ^ 1);
@@ -184,6 +186,36 @@ ln_qkv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int t = (int)blockIdx.x + it * (int)gridDim.x;
       const int m = t * 128 + row;
       const bool row_ok = m < p.T;
+      if (p.kv_only) {
+        // ---- [K | V] only: wait for the accumulator (its GEMM has also released the staged tile on x_empty: arriving after
+        // this wait keeps every warp inside the current phase of that barrier), drain, store
+        mbar_wait(&kv_full, tp);
+        tc_fence_after();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&x_empty[s]);
+#pragma unroll 1
+        for (int cc = 0; cc < D; cc += 64) {
+          const int col = half * D + cc;
+          uint32_t r0[32], r1[32], pk[32];
+          tmem_ld32(TKV + lane_base + col, r0);
+          tmem_ld32(TKV + lane_base + col + 32, r1);
+          tmem_ld_wait();
+          if (cc + 64 >= D) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&kv_free);
+          }
+          const float* bb = &s_bias[D + col];
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            const uint4 a = pack8_bias(&r0[c8 * 8], bb + c8 * 8), b = pack8_bias(&r1[c8 * 8], bb + 32 + c8 * 8);
+            pk[c8 * 4] = a.x; pk[c8 * 4 + 1] = a.y; pk[c8 * 4 + 2] = a.z; pk[c8 * 4 + 3] = a.w;
+            pk[16 + c8 * 4] = b.x; pk[16 + c8 * 4 + 1] = b.y; pk[16 + c8 * 4 + 2] = b.z; pk[16 + c8 * 4 + 3] = b.w;
+          }
+          stage_store(pk, &tmOKV, col, t * 128);
+        }
+        continue;
+      }
       // ---- LayerNorm of this thread's 64 columns of the staged x tile
       mbar_wait(&x_full[s], ph);
       float xv[64];
@@ -319,11 +351,18 @@ RP_API int rp_ln_qkv_fused(const void* x, const float* ln_w, const float* ln_b, 
                            int T, int d, void* q_in, void* Q, void* KV, float* mean_out, float* rstd_out, int hd_valid,
                            void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (!x || !ln_w || !ln_b || !w_in || !b_in || !q_in || !Q || !KV || T <= 0) return RP_EINVAL;
+  const bool kv_only = q_in == nullptr && Q == nullptr;   // [K | V] projection alone (LayerNorm parameters not read)
+  if (!x || !w_in || !b_in || !KV || T <= 0) return RP_EINVAL;
+  if (!kv_only && (!ln_w || !ln_b || !q_in || !Q)) return RP_EINVAL;
   if ((mean_out == nullptr) != (rstd_out == nullptr)) return RP_EINVAL;
+  if (kv_only) {
+    q_in = KV;   // tensor maps need a valid address; nothing is stored through them in this mode
+    Q = KV;
+    mean_out = rstd_out = nullptr;
+  }
   if (d != 64 && d != 128) return RP_ESHAPE;
   if (hd_valid < 0 || hd_valid > 128 || (hd_valid > 0 && d % (hd_valid <= 64 ? 64 : 128))) return RP_ESHAPE;
-  if (q_in == x || Q == x || KV == x) return RP_EINVAL;
+  if ((!kv_only && (q_in == x || Q == x)) || KV == x) return RP_EINVAL;
   CUtensorMap tmX, tmWq, tmWkv, tmOq, tmOQ, tmOKV;
   int rc;
   if ((rc = make_tmap_bf16(&tmX, x, T, d, d, 128)) != RP_OK) return rc;
@@ -337,6 +376,7 @@ RP_API int rp_ln_qkv_fused(const void* x, const float* ln_w, const float* ln_b, 
   p.ln_w = ln_w; p.ln_b = ln_b; p.b_in = b_in; p.eps = eps; p.T = T; p.hd_valid = hd_valid;
   p.q_in = reinterpret_cast<__nv_bfloat16*>(q_in); p.Q = reinterpret_cast<__nv_bfloat16*>(Q);
   p.KV = reinterpret_cast<__nv_bfloat16*>(KV); p.mean_out = mean_out; p.rstd_out = rstd_out;
+  p.kv_only = kv_only ? 1 : 0;
   return d == 64 ? launch_ln_qkv<1>(tmX, tmWq, tmWkv, tmOq, tmOQ, tmOKV, p, stream)
                  : launch_ln_qkv<2>(tmX, tmWq, tmWkv, tmOq, tmOQ, tmOKV, p, stream);
 }

@@ -366,6 +366,8 @@ class SasRecCore(torch.nn.Module):
             graphs = self.__dict__.setdefault("_predict_graphs", {})
             st = graphs.get(key)
             if st is None:
+                while len(graphs) >= 8:   # a handful of call shapes per deployment; the oldest capture goes first
+                    graphs.pop(next(iter(graphs)))
                 st = graphs[key] = {"seen": torch.empty_like(seen_ids, memory_format=torch.contiguous_format), "calls": 0}
             st["seen"].copy_(seen_ids, non_blocking=True)
             eng.set_batch(ids, pad_mask)

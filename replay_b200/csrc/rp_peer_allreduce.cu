@@ -19,6 +19,9 @@
 
 namespace rp {
 
+#ifndef RP_PEER_LD_VOLATILE
+#define RP_PEER_LD_VOLATILE 0
+#endif
 static constexpr int kMaxPeers = 8;
 struct PeerArgs {
   float* buf[kMaxPeers];        // the gradient buffer of every rank (this rank's own included), peer-mapped
@@ -36,7 +39,11 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 // peer data must not come out of this SM's L1 (it may hold last step's lines): relaxed system-scope loads go to the owner
 __device__ __forceinline__ float4 ld_sys_f4(const float* p) {
   float4 v;
+#if RP_PEER_LD_VOLATILE
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+#else
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+#endif
   return v;
 }
 __device__ __forceinline__ float ld_sys_f1(const float* p) {

@@ -457,3 +457,32 @@ def test_replica_partition_reproduces_reference_known_answers(golden_dir):
     for bad in ((0, 0, 1), (4, 2, 2), (4, 0, 0)):
         with pytest.raises(ValueError):
             replica_partition(*bad)
+
+
+def test_row_loss_selectors_weights_and_kinds():
+    """replay_b200.nn.loss selectors of the per-row heads: which fused head they select and the per-position weights they hand
+    to it (CEWeighted reproduces the reference's broadcast: every valid row gets mean(w) * T_v / (B * L))."""
+    import torch
+
+    from replay_b200.nn import loss as L
+
+    tm = torch.tensor([[False, True, True], [True, True, True]])
+    w = torch.tensor([[[2.0], [1.0], [0.5]], [[1.5], [1.0], [3.0]]])
+    lo = L.LogOutCE(cardinality=10)
+    assert lo.kind == "ce" and not lo.needs_negatives and not hasattr(lo, "row_weights")
+    low = L.LogOutCEWeighted(cardinality=10, feature_name="w")
+    assert low.kind == "ce_weighted"
+    assert torch.equal(low.row_weights({"w": w}, tm), w[..., 0])
+    cw = L.CEWeighted(feature_name="w")
+    got = cw.row_weights({"w": w}, tm)
+    assert got.shape == (2, 3) and torch.allclose(got, torch.full((2, 3), float(w.mean()) * 5 / 6))
+    li = L.LogInCE(cardinality=10, log_epsilon=1e-3, clamp_border=5.0)
+    assert li.kind == "login_ce" and li.engine_kwargs() == {"log_eps": 1e-3, "clamp": 5.0}
+    assert L.LogOutCESampled is L.CE
+
+
+def test_peer_gradient_buffer_needs_an_nccl_group():
+    """replay_b200.peer.alloc_peer_grad: no process group (or a non-NCCL one) -> None, the trainer keeps ncclAllReduce / gloo."""
+    from replay_b200.peer import alloc_peer_grad
+
+    assert alloc_peer_grad(1024, "cpu") is None

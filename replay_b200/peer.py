@@ -41,6 +41,7 @@ def alloc_peer_grad(n: int, device) -> PeerGrad | None:
     world = dist.get_world_size()
     if world < 2 or world > 8:
         return None
+    peer, err = None, None
     try:
         import torch.distributed._symmetric_memory as symm_mem
 
@@ -50,9 +51,16 @@ def alloc_peer_grad(n: int, device) -> PeerGrad | None:
         hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
         buf.zero_()
         torch.cuda.synchronize(device)
-        dist.barrier()   # nobody raises a flag in a peer's state block before that peer has zeroed it
-        return PeerGrad(buf, hdl, n, n_pad)
+        peer = PeerGrad(buf, hdl, n, n_pad)
     except Exception as e:  # noqa: BLE001 - any refusal (driver, container, torch build) means "use NCCL"
+        err = e
+    # every rank must take the same path: agree on the outcome (this collective also is the barrier after which nobody's
+    # state block is zeroed any more - flags are only raised by the kernel, i.e. later)
+    ok = torch.tensor([1 if peer is not None else 0], device=device, dtype=torch.int32)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0:
         if dist.get_rank() == 0:
-            print(f"[replay_b200] symmetric gradient buffer unavailable ({type(e).__name__}: {e}); using ncclAllReduce", flush=True)
+            why = f"{type(err).__name__}: {err}" if err is not None else "refused on another rank"
+            print(f"[replay_b200] symmetric gradient buffer unavailable ({why}); using ncclAllReduce", flush=True)
         return None
+    return peer

@@ -90,6 +90,9 @@ static constexpr int kCeMaxGroups = 2;
 #ifndef RP_CE_PACE_DEPTH
 #define RP_CE_PACE_DEPTH 0   /* pairs of tcgen05.mma in flight before the issuing thread waits for a completion (0 = issue at will) */
 #endif
+#ifndef RP_CE_NO_EMPTY
+#define RP_CE_NO_EMPTY 1   /* in-order issue: stages are released by the S-complete barrier of tile j + NBUF (one commit per tile less) */
+#endif
 #ifndef RP_CE_PRESCALE
 #define RP_CE_PRESCALE 0   /* fused pass: log2(e) folded into the TMEM row tile (one instruction less per logit; measured: no gain, 1.061 vs 1.050 ms, and the extra bf16 rounding breaks the 1e-2 gradient tolerance of test_ce_head at d = 64) */
 #endif
@@ -487,7 +490,13 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   __shared__ __align__(16) float s_cc[NSTAGE][TN];
   __shared__ float s_gsum[kSlots][kT];
   __shared__ float s_dot[FUSED ? kSlots : 1][kT];
-  __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_sfull[NBUF], bar_sfree[NBUF], bar_pfull[NBUF], bar_acc, bar_tok[NI], bar_pace[8];
+  // S-complete barriers form a ring over the smem STAGES (not the NBUF TMEM buffers): the TMA thread, which runs up to
+  // NSTAGE tiles ahead, can then wait for one particular tile's first GEMM without its phase being lapped (see NO_EMPTY)
+  __shared__ uint64_t bar_a, bar_full[NSTAGE], bar_empty[NSTAGE], bar_sfull[NSTAGE], bar_sfree[NBUF], bar_pfull[NBUF], bar_acc, bar_tok[NI], bar_pace[8];
+  // NO_EMPTY: with the in-order issue a tile's smem stage is free once the first GEMM of tile j + NBUF has completed (it is
+  // queued right behind the second GEMM of tile j, the stage's last reader) - the S-complete barrier of that tile doubles as
+  // the stage-free signal and the tcgen05.commit on bar_empty (~50 cycles per tile, profiles/r2_ce_timeline.md) goes away
+  constexpr bool NO_EMPTY = INORDER && NI == 1 && (NSTAGE > NBUF + 1) && (RP_CE_NO_EMPTY != 0);
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -522,8 +531,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
     }
+    for (int i = 0; i < NSTAGE; ++i) mbar_init(&bar_sfull[i], 1);
     for (int i = 0; i < NBUF; ++i) {
-      mbar_init(&bar_sfull[i], 1);
       mbar_init(&bar_sfree[i], 1);
       mbar_init(&bar_pfull[i], 4 * CG);
     }
@@ -555,11 +564,19 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int jl = 0; jl < sg.n; ++jl, ++g) {
           const uint32_t s = g % NSTAGE, ph = (g / NSTAGE) & 1;
           const int jc = sg.j0 + jl;   // column tile
+          if (NO_EMPTY) {
+            // stage s was last used by tile g - NSTAGE; it is free when S of tile g - NSTAGE + NBUF is complete
+            if (g >= (uint32_t)NSTAGE) {
+              const uint32_t w = g - NSTAGE + NBUF;
+              mbar_wait(&bar_sfull[w % NSTAGE], (w / NSTAGE) & 1);
+            }
+          } else {
 #if RP_CE_RELAXED_WAITS
-          mbar_wait_relaxed(&bar_empty[s], ph ^ 1);
+            mbar_wait_relaxed(&bar_empty[s], ph ^ 1);
 #else
-          mbar_wait(&bar_empty[s], ph ^ 1);
+            mbar_wait(&bar_empty[s], ph ^ 1);
 #endif
+          }
           mbar_arrive_expect_tx(&bar_full[s], kStage + (COLCONST ? TN * 4 : 0));
           for (int kc = 0; kc < KCH; ++kc)
             tma_load_2d(sB + s * kStage + kc * kChunkB, &tmB, &bar_full[s], kc * 64, jc * TN);
@@ -636,7 +653,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               paced();
             }
           }
-          umma_commit(&bar_sfull[g % NBUF]);
+          umma_commit(&bar_sfull[g % NSTAGE]);
         };
         for (int jl = 0; jl < n_ct; ++jl) {
           const uint32_t g = g0 + jl, s = g % NSTAGE;
@@ -673,7 +690,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     idesc2, (jl | ks) != 0);
             paced();
           }
-          umma_commit(&bar_empty[s]);
+          if (!NO_EMPTY) umma_commit(&bar_empty[s]);
           if (INORDER) {
             if (jl + PRE < n_ct) issue_mma1(jl + PRE);
           } else {
@@ -751,7 +768,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     //  depend on THIS tile's G: NBUF > GROUPS)
     constexpr bool PREFETCH = (NBUF >= 3) && (NBUF > GROUPS);
     auto s_wait = [&](int j) {   // j: tile of this segment; g0 + j: its position in the S-buffer / smem rings
-      mbar_wait(&bar_sfull[(g0 + j) % NBUF], ((g0 + j) / NBUF) & 1);
+      mbar_wait(&bar_sfull[(g0 + j) % NSTAGE], ((g0 + j) / NSTAGE) & 1);
       tc_fence_after();
     };
     auto s_addr = [&](int j) -> uint32_t { return tmem + lane_base + (uint32_t)((g0 + j) % NBUF) * TN + cg * kW; };

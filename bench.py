@@ -541,12 +541,11 @@ def run_scoring(args, dev, rank, world, PK, barrier, time_kernel):
             j = i % per
             return slice(j * Bu, (j + 1) * Bu)
 
-        # device-resident
+        # device-resident inputs, through the model's fused predict (what the callbacks call): one graph replay per call
+        # below 8192 users, the length-bucketed body above
         def call_dev(i):
             s = sl(i)
-            eng.set_batch(uid_d[s], upm_d[s])
-            hq = eng.forward_last_hidden()
-            return ops.score_topk(hq[: s.stop - s.start], tab, K, ops.seen_prepare(uid_d[s], I))
+            return core.predict_topk(uid_d[s], upm_d[s], K, seen_ids=uid_d[s])
 
         for i in range(3):
             call_dev(i)

@@ -57,13 +57,13 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// spin until *f has reached `epoch`; gives up after ~20 s (a peer process died: better a wrong gradient and a clean exit of
+// spin until *f has reached `epoch`; gives up after ~60 s (a peer process died: better a wrong gradient and a clean exit of
 // this kernel than a GPU that spins until the box is reclaimed) and reports it through the state block
 __device__ __forceinline__ void wait_flag(const uint32_t* f, uint32_t epoch, uint32_t* timed_out) {
   const unsigned long long t0 = global_ns();
   uint32_t polls = 0;
   while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-    if ((++polls & 0xfffu) == 0 && global_ns() - t0 > 20000000000ull) {
+    if ((++polls & 0xfffu) == 0 && global_ns() - t0 > 60000000000ull) {
       *timed_out = 1u;
       return;
     }

@@ -473,11 +473,13 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": workload_string(c), "global_batch": world * B, "per_gpu_batch": B, "seq_len": L, "d": d, "n_items": I,
                    "parallelism": f"dp{world}", "valid_targets_per_seq": valid_per_seq, "cuda_graph": not args.no_graph,
+                   "batch_sharding": ("one rank" if world == 1 else
+                                      ("index" if args.no_balance else "global batch dealt to the ranks by valid-target count")),
                    "l2": "no flush: every step streams > 126 MB of activations / table"},
         "e2e": {"value": world * B * K / ms_e2e * 1e3, "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / K,
                 "path": ("LightningModule(SasRec).training_step" if c["kind"] == "sasrec" else "Bert4Rec.training_step")
-                        + " on pinned host batches (fused step: CUDA-graph replays + NCCL all-reduce inside the module)"},
+                        + " on pinned host batches (fused step: CUDA-graph replay, gradient exchange inside the module)"},
         "e2e_device_batches": dev_batches,
         "sustained": sustained, "gradient_exchange": exchange,
         "gpu_launches": launches,

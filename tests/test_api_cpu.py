@@ -486,3 +486,26 @@ def test_peer_gradient_buffer_needs_an_nccl_group():
     from replay_b200.peer import alloc_peer_grad
 
     assert alloc_peer_grad(1024, "cpu") is None
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference algorithm - oracle port - on the host cores; what the driver runs next to
+    the GPU arm): ONE JSON line with the contract's keys, same metric / unit as the GPU arm, e2e == value, no GPU needed."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+              "data", "config", "cpu_baseline", "e2e"):
+        assert k in j, k
+    assert j["impl"] == "reference" and j["metric"] == "sasrec_train_seq_per_s" and j["unit"] == "seq/s"
+    assert j["value"] > 0 and j["higher_is_better"] is True
+    assert j["e2e"]["value"] == j["value"] and j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
